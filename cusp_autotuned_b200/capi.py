@@ -1,0 +1,402 @@
+"""ctypes binding of libb200sp.so (the C ABI declared in include/b200sp.h).
+
+This is the only way Python reaches the engine: every call below goes through
+the C-ABI entry point of the same name.  PyTorch is used for device memory and
+streams only.  There is no CPU fallback: if the shared library is missing, or no
+B200 is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200sp.so")
+
+
+class B200spError(RuntimeError):
+    """cusp::runtime_exception analogue (cusp/exception.h:74-84)."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(f"[b200sp status {status}] {message}")
+        self.status = status
+
+
+class InvalidInput(B200spError, ValueError):
+    """cusp::invalid_input_exception analogue (cusp/exception.h:53-58)."""
+
+
+class Cfg(C.Structure):
+    """b200sp_cfg — one point of the tuning space."""
+
+    _fields_ = [
+        ("kernel", C.c_int),
+        ("block_size", C.c_int),
+        ("threads_per_row", C.c_int),
+        ("unroll", C.c_int),
+        ("vector_width", C.c_int),
+        ("tile_rows", C.c_int),
+        ("stages", C.c_int),
+        ("ctas_per_sm", C.c_int),
+    ]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+    def __repr__(self):
+        return "Cfg(" + ", ".join(f"{k}={v}" for k, v in self.as_dict().items() if v) + ")"
+
+
+class Matrix(C.Structure):
+    """b200sp_matrix — non-owning device matrix descriptor."""
+
+    _fields_ = [
+        ("format", C.c_int),
+        ("dtype", C.c_int),
+        ("num_rows", C.c_int64),
+        ("num_cols", C.c_int64),
+        ("num_entries", C.c_int64),
+        ("num_cols_per_row", C.c_int64),
+        ("pitch", C.c_int64),
+        ("row_offsets", C.c_void_p),
+        ("row_indices", C.c_void_p),
+        ("column_indices", C.c_void_p),
+        ("diagonal_offsets", C.c_void_p),
+        ("values", C.c_void_p),
+        ("coo_num_entries", C.c_int64),
+        ("coo_row_indices", C.c_void_p),
+        ("coo_column_indices", C.c_void_p),
+        ("coo_values", C.c_void_p),
+    ]
+
+
+class CgParams(C.Structure):
+    _fields_ = [
+        ("iteration_limit", C.c_int64),
+        ("relative_tolerance", C.c_double),
+        ("absolute_tolerance", C.c_double),
+        ("check_interval", C.c_int),
+    ]
+
+
+class CgResult(C.Structure):
+    _fields_ = [
+        ("iteration_count", C.c_int64),
+        ("converged", C.c_int),
+        ("residual_norm", C.c_double),
+        ("b_norm", C.c_double),
+        ("num_residuals", C.c_int64),
+    ]
+
+
+class Halo(C.Structure):
+    _fields_ = [("halo_lo", C.c_int64), ("halo_hi", C.c_int64)]
+
+
+class TuneResult(C.Structure):
+    _fields_ = [
+        ("cfg", Cfg),
+        ("status", C.c_int),
+        ("milliseconds", C.c_float),
+        ("max_rel_error", C.c_double),
+    ]
+
+
+FMT_CSR, FMT_ELL, FMT_DIA, FMT_COO, FMT_HYB, FMT_ELLR = range(6)
+F32, F64 = 0, 1
+K_CSR_VECTOR, K_CSR_STREAM = 1, 2
+K_ELL_LDG, K_ELL_BULK = 1, 2
+K_DIA_LDG, K_DIA_BULK = 1, 2
+K_COO_SEGSCAN = 1
+ST_OK, ST_INVALID_INPUT, ST_CUDA_ERROR, ST_NOT_IMPLEMENTED, ST_ALLOC_FAILED, ST_COMM_ERROR = range(6)
+
+# every symbol include/b200sp.h declares (checked by tests/test_abi.py)
+_SFX = ("f32", "f64")
+EXPORTED_SYMBOLS = (
+    ["b200sp_version", "b200sp_create", "b200sp_destroy", "b200sp_last_error_string",
+     "b200sp_status_string", "b200sp_launch_count", "b200sp_set_l2_persist",
+     "b200sp_ell_row_lengths", "b200sp_spmv", "b200sp_spmv_host", "b200sp_cg",
+     "b200sp_comm_unique_id", "b200sp_comm_init", "b200sp_comm_destroy", "b200sp_cg_dist",
+     "b200sp_spmv_dist", "b200sp_cfg_space", "b200sp_tune", "b200sp_tune_step",
+     "b200sp_tune_reset", "b200sp_tune_lookup", "b200sp_tune_save", "b200sp_tune_load",
+     "b200sp_poisson_num_entries", "b200sp_poisson_csr_offsets"]
+    + [f"b200sp_spmv_{f}_{s}" for f in ("csr", "ell", "dia", "coo", "hyb", "ellr") for s in _SFX]
+    + [f"b200sp_{op}_{s}" for op in ("axpy", "axpby", "copy", "fill", "scal", "dot", "nrm2") for s in _SFX]
+    + [f"b200sp_poisson_{f}_{s}" for f in ("dia", "ell", "csr") for s in _SFX]
+)
+
+_lib: Optional[C.CDLL] = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen libb200sp.so (built in-tree by __graft_entry__.build() / csrc/Makefile)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200spError(-1, f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    lib.b200sp_version.restype = C.c_int
+    lib.b200sp_last_error_string.restype = C.c_char_p
+    lib.b200sp_last_error_string.argtypes = [C.c_void_p]
+    lib.b200sp_status_string.restype = C.c_char_p
+    lib.b200sp_launch_count.restype = C.c_uint64
+    lib.b200sp_launch_count.argtypes = [C.c_void_p]
+    lib.b200sp_cfg_space.restype = C.c_int64
+    lib.b200sp_cfg_space.argtypes = [C.c_int, C.c_int, C.POINTER(Cfg), C.c_int64]
+    lib.b200sp_poisson_num_entries.restype = C.c_int64
+    lib.b200sp_poisson_num_entries.argtypes = [C.c_int] + [C.c_int64] * 5
+    lib.b200sp_tune_lookup.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def _ptr(t):
+    """device (or host) address of a torch tensor / numpy array / None."""
+    if t is None:
+        return C.c_void_p(0)
+    if hasattr(t, "data_ptr"):
+        return C.c_void_p(t.data_ptr())
+    return C.c_void_p(t.ctypes.data)
+
+
+def _sfx(dtype) -> str:
+    import torch
+    if dtype == torch.float32:
+        return "f32"
+    if dtype == torch.float64:
+        return "f64"
+    raise InvalidInput(ST_INVALID_INPUT, f"unsupported value type {dtype}: the engine computes in f32 or f64")
+
+
+def _ctype(dtype):
+    import torch
+    return C.c_float if dtype == torch.float32 else C.c_double
+
+
+def _stream() -> C.c_void_p:
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Handle:
+    """b200sp_handle bound to the current CUDA device."""
+
+    def __init__(self):
+        self.lib = load_library()
+        h = C.c_void_p()
+        st = self.lib.b200sp_create(C.byref(h))
+        if st != ST_OK:
+            raise B200spError(st, self.lib.b200sp_last_error_string(None).decode())
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.b200sp_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, st: int):
+        if st == ST_OK:
+            return
+        msg = self.lib.b200sp_last_error_string(self._h).decode()
+        raise (InvalidInput if st == ST_INVALID_INPUT else B200spError)(st, msg)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.b200sp_launch_count(self._h))
+
+    # -- typed SpMV entry points ------------------------------------------------
+    def spmv_csr(self, rows, cols, nnz, Ap, Aj, Ax, x, y, accumulate=False, cfg: Optional[Cfg] = None):
+        f = getattr(self.lib, "b200sp_spmv_csr_" + _sfx(y.dtype))
+        self.check(f(self._h, _stream(), C.c_int64(rows), C.c_int64(cols), C.c_int64(nnz), _ptr(Ap), _ptr(Aj),
+                     _ptr(Ax), _ptr(x), _ptr(y), C.c_int(int(accumulate)), C.byref(cfg) if cfg else None))
+
+    def spmv_ell(self, rows, cols, K, pitch, cidx, vals, x, y, accumulate=False, cfg: Optional[Cfg] = None):
+        f = getattr(self.lib, "b200sp_spmv_ell_" + _sfx(y.dtype))
+        self.check(f(self._h, _stream(), C.c_int64(rows), C.c_int64(cols), C.c_int64(K), C.c_int64(pitch),
+                     _ptr(cidx), _ptr(vals), _ptr(x), _ptr(y), C.c_int(int(accumulate)),
+                     C.byref(cfg) if cfg else None))
+
+    def spmv_ellr(self, rows, cols, K, pitch, cidx, vals, row_lengths, x, y, accumulate=False,
+                  cfg: Optional[Cfg] = None):
+        f = getattr(self.lib, "b200sp_spmv_ellr_" + _sfx(y.dtype))
+        self.check(f(self._h, _stream(), C.c_int64(rows), C.c_int64(cols), C.c_int64(K), C.c_int64(pitch),
+                     _ptr(cidx), _ptr(vals), _ptr(row_lengths), _ptr(x), _ptr(y), C.c_int(int(accumulate)),
+                     C.byref(cfg) if cfg else None))
+
+    def ell_row_lengths(self, rows, K, pitch, cidx, out):
+        self.check(self.lib.b200sp_ell_row_lengths(self._h, _stream(), C.c_int64(rows), C.c_int64(K),
+                                                   C.c_int64(pitch), _ptr(cidx), _ptr(out)))
+
+    def spmv_dia(self, rows, cols, ndiag, pitch, offs, vals, x, y, accumulate=False, cfg: Optional[Cfg] = None):
+        f = getattr(self.lib, "b200sp_spmv_dia_" + _sfx(y.dtype))
+        self.check(f(self._h, _stream(), C.c_int64(rows), C.c_int64(cols), C.c_int64(ndiag), C.c_int64(pitch),
+                     _ptr(offs), _ptr(vals), _ptr(x), _ptr(y), C.c_int(int(accumulate)),
+                     C.byref(cfg) if cfg else None))
+
+    def spmv_coo(self, rows, cols, nnz, Ai, Aj, Ax, x, y, accumulate=False, cfg: Optional[Cfg] = None):
+        f = getattr(self.lib, "b200sp_spmv_coo_" + _sfx(y.dtype))
+        self.check(f(self._h, _stream(), C.c_int64(rows), C.c_int64(cols), C.c_int64(nnz), _ptr(Ai), _ptr(Aj),
+                     _ptr(Ax), _ptr(x), _ptr(y), C.c_int(int(accumulate)), C.byref(cfg) if cfg else None))
+
+    def spmv_hyb(self, rows, cols, K, pitch, ecidx, evals, cnnz, ci, cj, cv, x, y, accumulate=False,
+                 ell_cfg: Optional[Cfg] = None, coo_cfg: Optional[Cfg] = None):
+        f = getattr(self.lib, "b200sp_spmv_hyb_" + _sfx(y.dtype))
+        self.check(f(self._h, _stream(), C.c_int64(rows), C.c_int64(cols), C.c_int64(K), C.c_int64(pitch),
+                     _ptr(ecidx), _ptr(evals), C.c_int64(cnnz), _ptr(ci), _ptr(cj), _ptr(cv), _ptr(x), _ptr(y),
+                     C.c_int(int(accumulate)), C.byref(ell_cfg) if ell_cfg else None,
+                     C.byref(coo_cfg) if coo_cfg else None))
+
+    # -- descriptor based ---------------------------------------------------------
+    def spmv(self, A: Matrix, x, y, accumulate=False, cfg: Optional[Cfg] = None):
+        self.check(self.lib.b200sp_spmv(self._h, _stream(), C.byref(A), _ptr(x), _ptr(y),
+                                        C.c_int(int(accumulate)), C.byref(cfg) if cfg else None))
+
+    def spmv_host(self, A: Matrix, x_host, y_host, accumulate=False, cfg: Optional[Cfg] = None):
+        self.check(self.lib.b200sp_spmv_host(self._h, _stream(), C.byref(A), _ptr(x_host), _ptr(y_host),
+                                             C.c_int(int(accumulate)), C.byref(cfg) if cfg else None))
+
+    def set_l2_persist(self, tensor=None):
+        nbytes = 0 if tensor is None else tensor.numel() * tensor.element_size()
+        self.check(self.lib.b200sp_set_l2_persist(self._h, _stream(), _ptr(tensor), C.c_size_t(nbytes)))
+
+    # -- BLAS-1 -----------------------------------------------------------------------
+    def axpy(self, alpha, x, y):
+        f = getattr(self.lib, "b200sp_axpy_" + _sfx(y.dtype))
+        self.check(f(self._h, _stream(), C.c_int64(y.numel()), _ctype(y.dtype)(alpha), _ptr(x), _ptr(y)))
+
+    def axpby(self, alpha, x, beta, y, z):
+        f = getattr(self.lib, "b200sp_axpby_" + _sfx(z.dtype))
+        ct = _ctype(z.dtype)
+        self.check(f(self._h, _stream(), C.c_int64(z.numel()), ct(alpha), _ptr(x), ct(beta), _ptr(y), _ptr(z)))
+
+    def copy(self, x, y):
+        f = getattr(self.lib, "b200sp_copy_" + _sfx(y.dtype))
+        self.check(f(self._h, _stream(), C.c_int64(y.numel()), _ptr(x), _ptr(y)))
+
+    def fill(self, alpha, x):
+        f = getattr(self.lib, "b200sp_fill_" + _sfx(x.dtype))
+        self.check(f(self._h, _stream(), C.c_int64(x.numel()), _ctype(x.dtype)(alpha), _ptr(x)))
+
+    def scal(self, alpha, x):
+        f = getattr(self.lib, "b200sp_scal_" + _sfx(x.dtype))
+        self.check(f(self._h, _stream(), C.c_int64(x.numel()), _ctype(x.dtype)(alpha), _ptr(x)))
+
+    def dot(self, x, y) -> float:
+        f = getattr(self.lib, "b200sp_dot_" + _sfx(x.dtype))
+        out = _ctype(x.dtype)()
+        self.check(f(self._h, _stream(), C.c_int64(x.numel()), _ptr(x), _ptr(y), None, C.byref(out)))
+        return out.value
+
+    def nrm2(self, x) -> float:
+        f = getattr(self.lib, "b200sp_nrm2_" + _sfx(x.dtype))
+        out = _ctype(x.dtype)()
+        self.check(f(self._h, _stream(), C.c_int64(x.numel()), _ptr(x), None, C.byref(out)))
+        return out.value
+
+    # -- CG ------------------------------------------------------------------------------
+    def cg(self, A: Matrix, x, b, iteration_limit=500, relative_tolerance=1e-5, absolute_tolerance=0.0,
+           check_interval=0, cfg: Optional[Cfg] = None, want_residuals=True, halo: Optional[Halo] = None):
+        import numpy as np
+        prm = CgParams(iteration_limit, relative_tolerance, absolute_tolerance, check_interval)
+        res = CgResult()
+        hist = np.zeros(iteration_limit + 2, dtype=np.float64) if want_residuals else None
+        hp = hist.ctypes.data_as(C.c_void_p) if hist is not None else None
+        if halo is None:
+            st = self.lib.b200sp_cg(self._h, _stream(), C.byref(A), _ptr(x), _ptr(b), C.byref(prm),
+                                    C.byref(cfg) if cfg else None, C.byref(res), hp)
+        else:
+            st = self.lib.b200sp_cg_dist(self._h, _stream(), C.byref(A), C.byref(halo), _ptr(x), _ptr(b),
+                                         C.byref(prm), C.byref(cfg) if cfg else None, C.byref(res), hp)
+        self.check(st)
+        return res, (hist[: res.num_residuals] if hist is not None else None)
+
+    # -- multi-GPU ---------------------------------------------------------------------------
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self.check(self.lib.b200sp_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, world_size: int, rank: int):
+        buf = C.create_string_buffer(unique_id, 128)
+        self.check(self.lib.b200sp_comm_init(self._h, buf, C.c_int(world_size), C.c_int(rank)))
+
+    def comm_destroy(self):
+        self.check(self.lib.b200sp_comm_destroy(self._h))
+
+    def spmv_dist(self, A: Matrix, halo: Halo, x_window, y, cfg: Optional[Cfg] = None):
+        self.check(self.lib.b200sp_spmv_dist(self._h, _stream(), C.byref(A), C.byref(halo), _ptr(x_window),
+                                             _ptr(y), C.byref(cfg) if cfg else None))
+
+    # -- tuning ----------------------------------------------------------------------------------
+    @staticmethod
+    def cfg_space(fmt: int, dtype: int):
+        lib = load_library()
+        n = lib.b200sp_cfg_space(fmt, dtype, None, 0)
+        arr = (Cfg * n)()
+        lib.b200sp_cfg_space(fmt, dtype, arr, n)
+        return list(arr)
+
+    def tune(self, A: Matrix, x, y, y_reference=None, tol=0.0, repeats=5):
+        n = self.lib.b200sp_cfg_space(A.format, A.dtype, None, 0)
+        results = (TuneResult * n)()
+        count = C.c_int64(0)
+        best = Cfg()
+        self.check(self.lib.b200sp_tune(self._h, _stream(), C.byref(A), _ptr(x), _ptr(y), _ptr(y_reference),
+                                        C.c_double(tol), C.c_int(repeats), results, C.c_int64(n),
+                                        C.byref(count), C.byref(best)))
+        return best, list(results)[: count.value]
+
+    def tune_step(self, A: Matrix, x, y) -> TuneResult:
+        r = TuneResult()
+        self.check(self.lib.b200sp_tune_step(self._h, _stream(), C.byref(A), _ptr(x), _ptr(y), C.byref(r)))
+        return r
+
+    def tune_reset(self, A: Optional[Matrix] = None):
+        self.check(self.lib.b200sp_tune_reset(self._h, C.byref(A) if A is not None else None))
+
+    def tune_lookup(self, A: Matrix) -> Optional[Cfg]:
+        c = Cfg()
+        return c if self.lib.b200sp_tune_lookup(self._h, C.byref(A), C.byref(c)) else None
+
+    def tune_save(self, path: str):
+        self.check(self.lib.b200sp_tune_save(self._h, path.encode()))
+
+    def tune_load(self, path: str):
+        self.check(self.lib.b200sp_tune_load(self._h, path.encode()))
+
+    # -- gallery ------------------------------------------------------------------------------------
+    def poisson_dia(self, stencil, nx, ny, nz, row_begin, num_rows, col_shift, pitch, offsets, values):
+        f = getattr(self.lib, "b200sp_poisson_dia_" + _sfx(values.dtype))
+        self.check(f(self._h, _stream(), C.c_int(stencil), C.c_int64(nx), C.c_int64(ny), C.c_int64(nz),
+                     C.c_int64(row_begin), C.c_int64(num_rows), C.c_int64(col_shift), C.c_int64(pitch),
+                     _ptr(offsets), _ptr(values)))
+
+    def poisson_ell(self, stencil, nx, ny, nz, row_begin, num_rows, col_shift, pitch, cidx, values):
+        f = getattr(self.lib, "b200sp_poisson_ell_" + _sfx(values.dtype))
+        self.check(f(self._h, _stream(), C.c_int(stencil), C.c_int64(nx), C.c_int64(ny), C.c_int64(nz),
+                     C.c_int64(row_begin), C.c_int64(num_rows), C.c_int64(col_shift), C.c_int64(pitch),
+                     _ptr(cidx), _ptr(values)))
+
+    def poisson_csr_offsets(self, stencil, nx, ny, nz, row_begin, num_rows, row_offsets):
+        self.check(self.lib.b200sp_poisson_csr_offsets(self._h, _stream(), C.c_int(stencil), C.c_int64(nx),
+                                                       C.c_int64(ny), C.c_int64(nz), C.c_int64(row_begin),
+                                                       C.c_int64(num_rows), _ptr(row_offsets)))
+
+    def poisson_csr(self, stencil, nx, ny, nz, row_begin, num_rows, col_shift, row_offsets, cidx, values):
+        f = getattr(self.lib, "b200sp_poisson_csr_" + _sfx(values.dtype))
+        self.check(f(self._h, _stream(), C.c_int(stencil), C.c_int64(nx), C.c_int64(ny), C.c_int64(nz),
+                     C.c_int64(row_begin), C.c_int64(num_rows), C.c_int64(col_shift), _ptr(row_offsets),
+                     _ptr(cidx), _ptr(values)))
+
+
+def poisson_num_entries(stencil, nx, ny, nz, row_begin, num_rows) -> int:
+    return int(load_library().b200sp_poisson_num_entries(stencil, nx, ny, nz, row_begin, num_rows))

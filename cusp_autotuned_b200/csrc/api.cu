@@ -1,0 +1,553 @@
+// api.cu — handle lifecycle, error reporting, host-buffer SpMV and the tuner.
+//
+// The tuner replaces the KTT glue of the reference: cusp::ktt::{multiply,tune,
+// reset_tuning} (cusp/ktt/detail/ktt.inl:83-142), cusp::system::cuda::ktt::
+// {multiply,tune} (cusp/system/cuda/ktt/multiply.h:56-153) and the per-format
+// parameter spaces (cusp/system/cuda/ktt/{csr,ell,dia,coo}_multiply.h).  KTT
+// JIT-compiles every configuration with NVRTC; here every point of the space is
+// a precompiled template instantiation, so a tuning step costs one launch.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static char g_global_err[1024] = "no error";
+
+namespace b200sp {
+
+b200sp_status set_error(b200sp_handle h, b200sp_status s, const char *fmt, ...) {
+  char *dst = h ? h->err : g_global_err;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 1024, fmt, ap);
+  va_end(ap);
+  return s;
+}
+
+b200sp_status ensure_scratch(b200sp_handle h, size_t bytes) {
+  if (h->scratch_bytes >= bytes) return B200SP_OK;
+  if (h->scratch) cudaFree(h->scratch);  // implicit device sync: in-flight users are done
+  h->scratch = nullptr;
+  h->scratch_bytes = 0;
+  size_t want = bytes + bytes / 4 + 4096;
+  if (cudaMalloc(&h->scratch, want) != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(h, B200SP_ALLOC_FAILED, "cannot allocate %zu B of scratch", want);
+  }
+  h->scratch_bytes = want;
+  return B200SP_OK;
+}
+
+template <typename T>
+b200sp_status spmv_any(b200sp_handle h, cudaStream_t st, const b200sp_matrix *A, const T *x, T *y,
+                       int accumulate, const b200sp_cfg *cfg, const T *dotv, T *dot_result);
+
+static i64 stored_entries(const b200sp_matrix *A) {
+  switch (A->format) {
+    case B200SP_FMT_ELL:
+    case B200SP_FMT_ELLR:
+    case B200SP_FMT_DIA:
+      return A->num_entries > 0 ? A->num_entries : A->num_cols_per_row * A->num_rows;
+    case B200SP_FMT_HYB:
+      return A->num_cols_per_row * A->num_rows + A->coo_num_entries;
+    default:
+      return A->num_entries;
+  }
+}
+
+static int ilog2(i64 v) {
+  int l = 0;
+  while (v > 1) {
+    v >>= 1;
+    ++l;
+  }
+  return l;
+}
+
+static b200sp_tune_key make_key(const b200sp_matrix *A) {
+  b200sp_tune_key k;
+  k.format = (int)A->format;
+  k.dtype = (int)A->dtype;
+  k.rows_log2 = ilog2(A->num_rows > 0 ? A->num_rows : 1);
+  const i64 rows = A->num_rows > 0 ? A->num_rows : 1;
+  k.nnz_per_row_log2 = ilog2((stored_entries(A) + rows - 1) / rows);
+  return k;
+}
+
+// ---- configuration spaces -----------------------------------------------------
+static void push(std::vector<b200sp_cfg> &v, int kernel, int block, int tpr, int unroll, int stages, int cps) {
+  b200sp_cfg c{};
+  c.kernel = kernel;
+  c.block_size = block;
+  c.threads_per_row = tpr;
+  c.unroll = unroll;
+  c.vector_width = 1;
+  c.tile_rows = (kernel == B200SP_K_ELL_BULK) ? block * unroll : 0;
+  c.stages = stages;
+  c.ctas_per_sm = cps;
+  v.push_back(c);
+}
+
+static std::vector<b200sp_cfg> cfg_space_vec(b200sp_format f, b200sp_dtype) {
+  std::vector<b200sp_cfg> v;
+  const int blocks[3] = {128, 256, 512};
+  switch (f) {
+    case B200SP_FMT_CSR:
+      for (int b : blocks)
+        for (int tpr : {1, 2, 4, 8, 16, 32})
+          for (int u : {1, 2, 4}) push(v, B200SP_K_CSR_VECTOR, b, tpr, u, 0, 0);
+      break;
+    case B200SP_FMT_ELL:
+    case B200SP_FMT_ELLR:
+    case B200SP_FMT_HYB:
+    case B200SP_FMT_DIA: {
+      const int k_ldg = (f == B200SP_FMT_DIA) ? B200SP_K_DIA_LDG : B200SP_K_ELL_LDG;
+      const int k_bulk = (f == B200SP_FMT_DIA) ? B200SP_K_DIA_BULK : B200SP_K_ELL_BULK;
+      for (int b : blocks)
+        for (int u : {1, 2, 4}) push(v, k_ldg, b, 0, u, 0, 0);
+      const int bu[6][2] = {{128, 2}, {128, 4}, {128, 8}, {256, 1}, {256, 2}, {256, 4}};
+      for (auto &p : bu)
+        for (int st : {2, 3, 4})
+          for (int cps : {1, 2, 4}) push(v, k_bulk, p[0], 0, p[1], st, cps);
+      break;
+    }
+    case B200SP_FMT_COO:
+      for (int b : blocks)
+        for (int u : {5, 7, 9, 11}) {
+          if (b == 512 && u > 7) continue;
+          push(v, B200SP_K_COO_SEGSCAN, b, 0, u, 0, 0);
+        }
+      break;
+  }
+  return v;
+}
+
+// ---- validation ---------------------------------------------------------------
+template <typename T>
+__global__ void absmax_kernel(i64 n, const T *a, unsigned int *out) {
+  float m = 0.f;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf((float)a[i]));
+  atomicMax(out, __float_as_uint(m));
+}
+
+template <typename T>
+__global__ void relerr_kernel(i64 n, const T *y, const T *ref, const unsigned int *scale_bits,
+                              unsigned int *out) {
+  const double floor_ = 1e-6 * (double)__uint_as_float(*scale_bits) + 1e-300;
+  float m = 0.f;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+    const double d = fabs((double)y[i] - (double)ref[i]);
+    const double den = fmax(fabs((double)ref[i]), floor_);
+    float e = (float)(d / den);
+    if (!(d == d)) e = 3.0e38f;  // NaN
+    m = fmaxf(m, e);
+  }
+  atomicMax(out, __float_as_uint(m));
+}
+
+template <typename T>
+static b200sp_status max_rel_error(b200sp_handle h, cudaStream_t st, i64 n, const T *y, const T *ref,
+                                   double *out) {
+  unsigned int *bits = h->red_counters + 8;  // [8]=scale, [9]=err
+  B200SP_CUDA(h, cudaMemsetAsync(bits, 0, 2 * sizeof(unsigned int), st));
+  if (n > 0) {
+    const unsigned g = (unsigned)(ceil_div(n, 256) < 1184 ? ceil_div(n, 256) : 1184);
+    absmax_kernel<T><<<g, 256, 0, st>>>(n, ref, bits);
+    relerr_kernel<T><<<g, 256, 0, st>>>(n, y, ref, bits, bits + 1);
+    h->launches += 2;
+  }
+  unsigned int hb[2];
+  B200SP_CUDA(h, cudaMemcpyAsync(hb, bits, sizeof(hb), cudaMemcpyDeviceToHost, st));
+  B200SP_CUDA(h, cudaStreamSynchronize(st));
+  float e;
+  memcpy(&e, &hb[1], 4);
+  *out = (double)e;
+  return B200SP_OK;
+}
+
+static b200sp_status tune_events(b200sp_handle h) {
+  if (h->tune_events.size() == 2) return B200SP_OK;
+  cudaEvent_t a, b;
+  B200SP_CUDA(h, cudaEventCreate(&a));
+  B200SP_CUDA(h, cudaEventCreate(&b));
+  h->tune_events.push_back(a);
+  h->tune_events.push_back(b);
+  return B200SP_OK;
+}
+
+template <typename T>
+static b200sp_status tune_impl(b200sp_handle h, cudaStream_t st, const b200sp_matrix *A, const T *x, T *y,
+                               const T *yref_in, double tol, int repeats, b200sp_tune_result *results,
+                               int64_t capacity, int64_t *num_results, b200sp_cfg *best) {
+  if (repeats <= 0) repeats = 5;
+  if (tol <= 0) tol = sizeof(T) == 4 ? 1e-5 : 1e-12;
+  b200sp_status s = tune_events(h);
+  if (s != B200SP_OK) return s;
+  cudaEvent_t e0 = (cudaEvent_t)h->tune_events[0], e1 = (cudaEvent_t)h->tune_events[1];
+  const i64 n = A->num_rows;
+  std::vector<b200sp_cfg> space = cfg_space_vec(A->format, A->dtype);
+
+  // reference output: caller's, or the engine-default configuration's
+  T *yref = nullptr;
+  const T *ref = yref_in;
+  if (!ref) {
+    B200SP_CUDA(h, cudaMalloc(&yref, (size_t)(n > 0 ? n : 1) * sizeof(T)));
+    b200sp_cfg dflt{};
+    s = spmv_any<T>(h, st, A, x, yref, 0, &dflt, nullptr, nullptr);
+    if (s != B200SP_OK) {
+      cudaFree(yref);
+      return s;
+    }
+    ref = yref;
+  }
+
+  float best_ms = 1e30f;
+  b200sp_cfg best_cfg{};
+  bool have = false;
+  i64 count = 0;
+  for (const b200sp_cfg &c : space) {
+    b200sp_tune_result r{};
+    r.cfg = c;
+    char saved[1024];
+    memcpy(saved, h->err, sizeof(saved));
+    s = spmv_any<T>(h, st, A, x, y, 0, &c, nullptr, nullptr);
+    cudaError_t ce = (s == B200SP_OK) ? cudaStreamSynchronize(st) : cudaSuccess;
+    if (s == B200SP_INVALID_INPUT || s == B200SP_NOT_IMPLEMENTED) {
+      r.status = B200SP_TUNE_UNSUPPORTED;
+      memcpy(h->err, saved, sizeof(saved));
+    } else if (s != B200SP_OK || ce != cudaSuccess) {
+      r.status = B200SP_TUNE_LAUNCH_FAILED;
+      cudaGetLastError();
+    } else {
+      s = max_rel_error<T>(h, st, n, y, ref, &r.max_rel_error);
+      if (s != B200SP_OK) {
+        if (yref) cudaFree(yref);
+        return s;
+      }
+      if (r.max_rel_error > tol) {
+        r.status = B200SP_TUNE_VALIDATION_FAILED;
+      } else {
+        cudaEventRecord(e0, st);
+        for (int k = 0; k < repeats; ++k) spmv_any<T>(h, st, A, x, y, 0, &c, nullptr, nullptr);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        r.milliseconds = ms / repeats;
+        r.status = B200SP_TUNE_OK;
+        if (r.milliseconds < best_ms) {
+          best_ms = r.milliseconds;
+          best_cfg = c;
+          have = true;
+        }
+      }
+    }
+    if (results && count < capacity) results[count] = r;
+    ++count;
+  }
+  if (num_results) *num_results = count;
+  if (yref) cudaFree(yref);
+  if (!have) return set_error(h, B200SP_CUDA_ERROR, "tune: no configuration produced a valid result");
+  b200sp_tune_entry &e = h->tune_cache[make_key(A)];
+  e.best = best_cfg;
+  e.has_best = true;
+  e.best_ms = best_ms;
+  e.next_index = (i64)space.size();
+  if (best) *best = best_cfg;
+  // leave y = A x computed by the winner
+  return spmv_any<T>(h, st, A, x, y, 0, &best_cfg, nullptr, nullptr);
+}
+
+template <typename T>
+static b200sp_status tune_step_impl(b200sp_handle h, cudaStream_t st, const b200sp_matrix *A, const T *x,
+                                    T *y, b200sp_tune_result *result) {
+  std::vector<b200sp_cfg> space = cfg_space_vec(A->format, A->dtype);
+  b200sp_tune_entry &e = h->tune_cache[make_key(A)];
+  b200sp_status s;
+  while (e.next_index < (i64)space.size()) {
+    const b200sp_cfg c = space[(size_t)e.next_index++];
+    s = tune_events(h);
+    if (s != B200SP_OK) return s;
+    cudaEvent_t e0 = (cudaEvent_t)h->tune_events[0], e1 = (cudaEvent_t)h->tune_events[1];
+    char saved[1024];
+    memcpy(saved, h->err, sizeof(saved));
+    cudaEventRecord(e0, st);
+    s = spmv_any<T>(h, st, A, x, y, 0, &c, nullptr, nullptr);
+    if (s == B200SP_INVALID_INPUT || s == B200SP_NOT_IMPLEMENTED) {  // not runnable here: next point
+      memcpy(h->err, saved, sizeof(saved));
+      continue;
+    }
+    if (s != B200SP_OK) return s;
+    cudaEventRecord(e1, st);
+    B200SP_CUDA(h, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (!e.has_best || ms < e.best_ms) {
+      e.best = c;
+      e.best_ms = ms;
+      e.has_best = true;
+    }
+    if (result) {
+      result->cfg = c;
+      result->status = B200SP_TUNE_OK;
+      result->milliseconds = ms;
+      result->max_rel_error = 0.0;
+    }
+    return B200SP_OK;
+  }
+  // space exhausted: steady state, no synchronisation
+  b200sp_cfg c = e.has_best ? e.best : b200sp_cfg{};
+  s = spmv_any<T>(h, st, A, x, y, 0, &c, nullptr, nullptr);
+  if (result) {
+    result->cfg = c;
+    result->status = s == B200SP_OK ? B200SP_TUNE_OK : B200SP_TUNE_LAUNCH_FAILED;
+    result->milliseconds = e.best_ms;
+    result->max_rel_error = 0.0;
+  }
+  return s;
+}
+
+}  // namespace b200sp
+
+extern "C" {
+
+int b200sp_version(void) { return B200SP_VERSION; }
+
+const char *b200sp_status_string(b200sp_status s) {
+  switch (s) {
+    case B200SP_OK: return "ok";
+    case B200SP_INVALID_INPUT: return "invalid input";
+    case B200SP_CUDA_ERROR: return "CUDA error";
+    case B200SP_NOT_IMPLEMENTED: return "not implemented";
+    case B200SP_ALLOC_FAILED: return "allocation failed";
+    case B200SP_COMM_ERROR: return "communication error";
+  }
+  return "unknown status";
+}
+
+const char *b200sp_last_error_string(b200sp_handle h) { return h ? h->err : g_global_err; }
+
+uint64_t b200sp_launch_count(b200sp_handle h) { return h ? h->launches : 0; }
+
+b200sp_status b200sp_create(b200sp_handle *out) {
+  if (!out) return b200sp::set_error(nullptr, B200SP_INVALID_INPUT, "create: null output pointer");
+  *out = nullptr;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return b200sp::set_error(nullptr, B200SP_CUDA_ERROR,
+                             "no usable CUDA device (%s): libb200sp has no CPU fallback",
+                             cudaGetErrorString(e));
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return b200sp::set_error(nullptr, B200SP_CUDA_ERROR, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  }
+  if (prop.major != 10)
+    return b200sp::set_error(nullptr, B200SP_CUDA_ERROR,
+                             "device %d is sm_%d%d; libb200sp contains sm_100a code only", dev, prop.major,
+                             prop.minor);
+  b200sp_context *h = new b200sp_context();
+  strcpy(h->err, "no error");
+  h->device = dev;
+  h->num_sms = prop.multiProcessorCount;
+  h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  h->l2_bytes = (size_t)prop.l2CacheSize;
+  h->max_persist_l2 = prop.persistingL2CacheMaxSize;
+  bool ok = cudaMalloc(&h->red_partials, (size_t)RED_MAX_PARTIALS * sizeof(double)) == cudaSuccess &&
+            cudaMalloc(&h->red_counters, 16 * sizeof(unsigned int)) == cudaSuccess &&
+            cudaMalloc(&h->dev_scalars, 64 * sizeof(double)) == cudaSuccess &&
+            cudaMallocHost(&h->pinned_scalars, 64 * sizeof(double)) == cudaSuccess &&
+            cudaMemset(h->red_counters, 0, 16 * sizeof(unsigned int)) == cudaSuccess &&
+            cudaMemset(h->dev_scalars, 0, 64 * sizeof(double)) == cudaSuccess;
+  if (!ok) {
+    cudaGetLastError();
+    b200sp_destroy(h);
+    return b200sp::set_error(nullptr, B200SP_ALLOC_FAILED, "create: cannot allocate handle workspace");
+  }
+  *out = h;
+  return B200SP_OK;
+}
+
+b200sp_status b200sp_destroy(b200sp_handle h) {
+  if (!h) return B200SP_OK;
+  if (h->nccl_comm) b200sp_comm_destroy(h);
+  if (h->scratch) cudaFree(h->scratch);
+  if (h->red_partials) cudaFree(h->red_partials);
+  if (h->red_counters) cudaFree(h->red_counters);
+  if (h->dev_scalars) cudaFree(h->dev_scalars);
+  if (h->pinned_scalars) cudaFreeHost(h->pinned_scalars);
+  if (h->stage_x) cudaFree(h->stage_x);
+  if (h->stage_y) cudaFree(h->stage_y);
+  if (h->cg_ws) cudaFree(h->cg_ws);
+  if (h->cg_residuals) cudaFree(h->cg_residuals);
+  for (void *ev : h->tune_events) cudaEventDestroy((cudaEvent_t)ev);
+  delete h;
+  return B200SP_OK;
+}
+
+b200sp_status b200sp_set_l2_persist(b200sp_handle h, b200sp_stream stream, const void *ptr, size_t bytes) {
+  B200SP_CHECK_HANDLE(h);
+  cudaStreamAttrValue attr;
+  memset(&attr, 0, sizeof(attr));
+  if (bytes == 0 || ptr == nullptr) {
+    attr.accessPolicyWindow.base_ptr = nullptr;
+    attr.accessPolicyWindow.num_bytes = 0;
+    attr.accessPolicyWindow.hitRatio = 0.f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    B200SP_CUDA(h, cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    B200SP_CUDA(h, cudaCtxResetPersistingL2Cache());
+    return B200SP_OK;
+  }
+  int max_window = 0;
+  B200SP_CUDA(h, cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, h->device));
+  size_t carve = bytes < (size_t)h->max_persist_l2 ? bytes : (size_t)h->max_persist_l2;
+  if (carve == 0) return b200sp::set_error(h, B200SP_NOT_IMPLEMENTED, "device has no persisting L2");
+  B200SP_CUDA(h, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+  const size_t win = bytes < (size_t)max_window ? bytes : (size_t)max_window;
+  attr.accessPolicyWindow.base_ptr = const_cast<void *>(ptr);
+  attr.accessPolicyWindow.num_bytes = win;
+  attr.accessPolicyWindow.hitRatio = (float)((double)carve / (double)win > 1.0 ? 1.0 : (double)carve / (double)win);
+  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  B200SP_CUDA(h, cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+  return B200SP_OK;
+}
+
+b200sp_status b200sp_spmv_host(b200sp_handle h, b200sp_stream stream, const b200sp_matrix *A,
+                               const void *x_host, void *y_host, int accumulate, const b200sp_cfg *cfg) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, A && x_host && y_host, "spmv_host: null argument");
+  const size_t elem = A->dtype == B200SP_F64 ? 8 : 4;
+  const size_t xb = (size_t)A->num_cols * elem, yb = (size_t)A->num_rows * elem;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->stage_x_bytes < xb) {
+    if (h->stage_x) cudaFree(h->stage_x);
+    h->stage_x = nullptr;
+    h->stage_x_bytes = 0;
+    if (cudaMalloc(&h->stage_x, xb ? xb : 1) != cudaSuccess) {
+      cudaGetLastError();
+      return b200sp::set_error(h, B200SP_ALLOC_FAILED, "spmv_host: cannot stage x (%zu B)", xb);
+    }
+    h->stage_x_bytes = xb;
+  }
+  if (h->stage_y_bytes < yb) {
+    if (h->stage_y) cudaFree(h->stage_y);
+    h->stage_y = nullptr;
+    h->stage_y_bytes = 0;
+    if (cudaMalloc(&h->stage_y, yb ? yb : 1) != cudaSuccess) {
+      cudaGetLastError();
+      return b200sp::set_error(h, B200SP_ALLOC_FAILED, "spmv_host: cannot stage y (%zu B)", yb);
+    }
+    h->stage_y_bytes = yb;
+  }
+  B200SP_CUDA(h, cudaMemcpyAsync(h->stage_x, x_host, xb, cudaMemcpyHostToDevice, st));
+  if (accumulate) B200SP_CUDA(h, cudaMemcpyAsync(h->stage_y, y_host, yb, cudaMemcpyHostToDevice, st));
+  b200sp_status s = b200sp_spmv(h, stream, A, h->stage_x, h->stage_y, accumulate, cfg);
+  if (s != B200SP_OK) return s;
+  B200SP_CUDA(h, cudaMemcpyAsync(y_host, h->stage_y, yb, cudaMemcpyDeviceToHost, st));
+  B200SP_CUDA(h, cudaStreamSynchronize(st));
+  return B200SP_OK;
+}
+
+int64_t b200sp_cfg_space(b200sp_format format, b200sp_dtype dtype, b200sp_cfg *out, int64_t capacity) {
+  std::vector<b200sp_cfg> v = b200sp::cfg_space_vec(format, dtype);
+  if (out)
+    for (int64_t i = 0; i < (int64_t)v.size() && i < capacity; ++i) out[i] = v[(size_t)i];
+  return (int64_t)v.size();
+}
+
+b200sp_status b200sp_tune(b200sp_handle h, b200sp_stream stream, const b200sp_matrix *A, const void *x,
+                          void *y, const void *y_reference, double tol, int repeats,
+                          b200sp_tune_result *results, int64_t capacity, int64_t *num_results,
+                          b200sp_cfg *best) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, A && x && y, "tune: null argument");
+  if (A->dtype == B200SP_F32)
+    return b200sp::tune_impl<float>(h, (cudaStream_t)stream, A, (const float *)x, (float *)y,
+                                    (const float *)y_reference, tol, repeats, results, capacity,
+                                    num_results, best);
+  if (A->dtype == B200SP_F64)
+    return b200sp::tune_impl<double>(h, (cudaStream_t)stream, A, (const double *)x, (double *)y,
+                                     (const double *)y_reference, tol, repeats, results, capacity,
+                                     num_results, best);
+  return b200sp::set_error(h, B200SP_INVALID_INPUT, "tune: unknown dtype");
+}
+
+b200sp_status b200sp_tune_step(b200sp_handle h, b200sp_stream stream, const b200sp_matrix *A, const void *x,
+                               void *y, b200sp_tune_result *result) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, A && x && y, "tune_step: null argument");
+  if (A->dtype == B200SP_F32)
+    return b200sp::tune_step_impl<float>(h, (cudaStream_t)stream, A, (const float *)x, (float *)y, result);
+  if (A->dtype == B200SP_F64)
+    return b200sp::tune_step_impl<double>(h, (cudaStream_t)stream, A, (const double *)x, (double *)y, result);
+  return b200sp::set_error(h, B200SP_INVALID_INPUT, "tune_step: unknown dtype");
+}
+
+b200sp_status b200sp_tune_reset(b200sp_handle h, const b200sp_matrix *A) {
+  B200SP_CHECK_HANDLE(h);
+  if (!A)
+    h->tune_cache.clear();
+  else
+    h->tune_cache.erase(b200sp::make_key(A));
+  return B200SP_OK;
+}
+
+int b200sp_tune_lookup(b200sp_handle h, const b200sp_matrix *A, b200sp_cfg *cfg) {
+  if (!h || !A || h->tune_cache.empty()) return 0;
+  auto it = h->tune_cache.find(b200sp::make_key(A));
+  if (it == h->tune_cache.end() || !it->second.has_best) return 0;
+  // during dynamic tuning the cached "best so far" is only used once the space is exhausted
+  if (it->second.next_index < b200sp_cfg_space(A->format, A->dtype, nullptr, 0)) return 0;
+  if (cfg) *cfg = it->second.best;
+  return 1;
+}
+
+b200sp_status b200sp_tune_save(b200sp_handle h, const char *path) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, path, "tune_save: null path");
+  FILE *f = fopen(path, "w");
+  if (!f) return b200sp::set_error(h, B200SP_INVALID_INPUT, "tune_save: cannot open %s", path);
+  fprintf(f, "# b200sp tuning cache v1: format dtype rows_log2 nnz_per_row_log2 kernel block tpr unroll vec "
+             "tile stages ctas_per_sm ms\n");
+  for (auto &kv : h->tune_cache) {
+    if (!kv.second.has_best) continue;
+    const b200sp_cfg &c = kv.second.best;
+    fprintf(f, "%d %d %d %d %d %d %d %d %d %d %d %d %.6f\n", kv.first.format, kv.first.dtype,
+            kv.first.rows_log2, kv.first.nnz_per_row_log2, c.kernel, c.block_size, c.threads_per_row,
+            c.unroll, c.vector_width, c.tile_rows, c.stages, c.ctas_per_sm, kv.second.best_ms);
+  }
+  fclose(f);
+  return B200SP_OK;
+}
+
+b200sp_status b200sp_tune_load(b200sp_handle h, const char *path) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, path, "tune_load: null path");
+  FILE *f = fopen(path, "r");
+  if (!f) return b200sp::set_error(h, B200SP_INVALID_INPUT, "tune_load: cannot open %s", path);
+  char line[512];
+  while (fgets(line, sizeof(line), f)) {
+    if (line[0] == '#') continue;
+    b200sp_tune_key k;
+    b200sp_cfg c{};
+    float ms = 0.f;
+    if (sscanf(line, "%d %d %d %d %d %d %d %d %d %d %d %d %f", &k.format, &k.dtype, &k.rows_log2,
+               &k.nnz_per_row_log2, &c.kernel, &c.block_size, &c.threads_per_row, &c.unroll,
+               &c.vector_width, &c.tile_rows, &c.stages, &c.ctas_per_sm, &ms) != 13)
+      continue;
+    b200sp_tune_entry &e = h->tune_cache[k];
+    e.best = c;
+    e.has_best = true;
+    e.best_ms = ms;
+    e.next_index = 1 << 30;
+  }
+  fclose(f);
+  return B200SP_OK;
+}
+}

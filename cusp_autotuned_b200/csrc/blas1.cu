@@ -1,0 +1,181 @@
+// blas1.cu — BLAS-1 kernels for sm_100a.
+//
+// Replaces the thrust implementations behind cusp::blas::{axpy,axpby,copy,fill,
+// scal,dot,dotc,nrm2} (cusp/system/detail/generic/blas.h:64-96,180-340;
+// front end cusp/detail/blas.inl:84-461).  Element-wise expressions are written
+// exactly as the reference functors write them (AXPY: alpha*x + y, AXPBY:
+// alpha*x + beta*y), so with -fmad=false every output element is bit-identical
+// to the reference's host result.  Reductions are two-level and deterministic
+// (per-CTA partial in thread order, last CTA adds partials in index order);
+// thrust::inner_product / transform_reduce leave the order unspecified.
+//
+// All kernels are HBM streams: 4 independent coalesced accesses per thread,
+// grid sized as a multiple of the SM count for the reductions.
+#include "common.cuh"
+
+namespace b200sp {
+
+constexpr int EW_BLOCK = 256;
+constexpr int EW_UNROLL = 4;
+
+template <typename T, typename F>
+__global__ void __launch_bounds__(EW_BLOCK) elementwise_kernel(i64 n, F f) {
+  const i64 base = (i64)blockIdx.x * (EW_BLOCK * EW_UNROLL) + threadIdx.x;
+#pragma unroll
+  for (int u = 0; u < EW_UNROLL; ++u) {
+    const i64 i = base + (i64)u * EW_BLOCK;
+    if (i < n) f(i);
+  }
+}
+
+template <typename T>
+struct AxpyF {
+  T alpha; const T *x; T *y;
+  __device__ void operator()(i64 i) const { y[i] = alpha * x[i] + y[i]; }
+};
+template <typename T>
+struct AxpbyF {
+  T alpha, beta; const T *x; const T *y; T *z;
+  __device__ void operator()(i64 i) const { z[i] = alpha * x[i] + beta * y[i]; }
+};
+template <typename T>
+struct FillF {
+  T alpha; T *x;
+  __device__ void operator()(i64 i) const { x[i] = alpha; }
+};
+template <typename T>
+struct ScalF {
+  T alpha; T *x;
+  __device__ void operator()(i64 i) const { x[i] = alpha * x[i]; }
+};
+template <typename T>
+struct CopyF {
+  const T *x; T *y;
+  __device__ void operator()(i64 i) const { y[i] = x[i]; }
+};
+
+template <typename T, typename F>
+static b200sp_status launch_ew(b200sp_handle h, cudaStream_t st, i64 n, F f, const char *name) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, n >= 0, "blas: negative length");
+  if (n == 0) return B200SP_OK;
+  const i64 grid = ceil_div(n, (i64)EW_BLOCK * EW_UNROLL);
+  elementwise_kernel<T, F><<<(unsigned)grid, EW_BLOCK, 0, st>>>(n, f);
+  B200SP_LAUNCH_CHECK(h, name);
+  return B200SP_OK;
+}
+
+// ---- reductions -------------------------------------------------------------
+constexpr int RED_BLOCK = 256;
+constexpr int RED_UNROLL = 4;
+
+// mode 0: sum x*y ; mode 1: sqrt(sum x*x)
+template <typename T, int MODE>
+__global__ void __launch_bounds__(RED_BLOCK) reduce_kernel(i64 n, const T *x, const T *y, T *partials,
+                                                           unsigned int *ticket, T *result) {
+  __shared__ T s_red[32];
+  T acc = T(0);
+  const i64 stride = (i64)gridDim.x * RED_BLOCK;
+  i64 i = (i64)blockIdx.x * RED_BLOCK + threadIdx.x;
+  for (; i + (RED_UNROLL - 1) * stride < n; i += RED_UNROLL * stride) {
+    T a[RED_UNROLL], b[RED_UNROLL];
+#pragma unroll
+    for (int u = 0; u < RED_UNROLL; ++u) {
+      a[u] = x[i + u * stride];
+      b[u] = (MODE == 0) ? y[i + u * stride] : a[u];
+    }
+#pragma unroll
+    for (int u = 0; u < RED_UNROLL; ++u) acc = acc + a[u] * b[u];
+  }
+  for (; i < n; i += stride) {
+    const T a = x[i];
+    const T b = (MODE == 0) ? y[i] : a;
+    acc = acc + a * b;
+  }
+  T bs = block_sum<RED_BLOCK>(acc, s_red);
+  grid_reduce_finish<RED_BLOCK>(bs, partials, ticket, s_red, [&](T total) {
+    *result = (MODE == 1) ? (T)sqrt((double)total) : total;
+  });
+}
+
+static inline i64 reduce_grid(b200sp_handle h, i64 n) {
+  i64 g = ceil_div(n, (i64)RED_BLOCK * RED_UNROLL);
+  const i64 cap = (i64)h->num_sms * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return g;
+}
+
+template <typename T, int MODE>
+b200sp_status reduce(b200sp_handle h, cudaStream_t st, i64 n, const T *x, const T *y, T *result_dev,
+                     T *result_host) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, n >= 0, "blas: negative length");
+  T *res = result_dev ? result_dev : reinterpret_cast<T *>(h->dev_scalars + 63);
+  if (n == 0) {
+    B200SP_CUDA(h, cudaMemsetAsync(res, 0, sizeof(T), st));
+  } else {
+    B200SP_REQUIRE(h, x && (MODE == 1 || y), "blas: null pointer");
+    reduce_kernel<T, MODE><<<(unsigned)reduce_grid(h, n), RED_BLOCK, 0, st>>>(
+        n, x, y, reinterpret_cast<T *>(h->red_partials), h->red_counters, res);
+    B200SP_LAUNCH_CHECK(h, "reduce_kernel");
+  }
+  if (result_host) {
+    T *pin = reinterpret_cast<T *>(h->pinned_scalars);
+    B200SP_CUDA(h, cudaMemcpyAsync(pin, res, sizeof(T), cudaMemcpyDeviceToHost, st));
+    B200SP_CUDA(h, cudaStreamSynchronize(st));
+    *result_host = *pin;
+  }
+  return B200SP_OK;
+}
+
+template b200sp_status reduce<float, 0>(b200sp_handle, cudaStream_t, i64, const float *, const float *,
+                                        float *, float *);
+template b200sp_status reduce<double, 0>(b200sp_handle, cudaStream_t, i64, const double *, const double *,
+                                         double *, double *);
+template b200sp_status reduce<float, 1>(b200sp_handle, cudaStream_t, i64, const float *, const float *,
+                                        float *, float *);
+template b200sp_status reduce<double, 1>(b200sp_handle, cudaStream_t, i64, const double *, const double *,
+                                         double *, double *);
+
+}  // namespace b200sp
+
+extern "C" {
+#define DEF(T, sfx)                                                                               \
+  b200sp_status b200sp_axpy_##sfx(b200sp_handle h, b200sp_stream s, int64_t n, T alpha,           \
+                                  const T *x, T *y) {                                             \
+    if (h && n > 0 && !(x && y)) return b200sp::set_error(h, B200SP_INVALID_INPUT, "axpy: null"); \
+    return b200sp::launch_ew<T>(h, (cudaStream_t)s, n, b200sp::AxpyF<T>{alpha, x, y}, "axpy");    \
+  }                                                                                               \
+  b200sp_status b200sp_axpby_##sfx(b200sp_handle h, b200sp_stream s, int64_t n, T alpha,          \
+                                   const T *x, T beta, const T *y, T *z) {                        \
+    if (h && n > 0 && !(x && y && z))                                                             \
+      return b200sp::set_error(h, B200SP_INVALID_INPUT, "axpby: null");                           \
+    return b200sp::launch_ew<T>(h, (cudaStream_t)s, n, b200sp::AxpbyF<T>{alpha, beta, x, y, z},   \
+                                "axpby");                                                         \
+  }                                                                                               \
+  b200sp_status b200sp_copy_##sfx(b200sp_handle h, b200sp_stream s, int64_t n, const T *x,        \
+                                  T *y) {                                                         \
+    if (h && n > 0 && !(x && y)) return b200sp::set_error(h, B200SP_INVALID_INPUT, "copy: null"); \
+    return b200sp::launch_ew<T>(h, (cudaStream_t)s, n, b200sp::CopyF<T>{x, y}, "copy");           \
+  }                                                                                               \
+  b200sp_status b200sp_fill_##sfx(b200sp_handle h, b200sp_stream s, int64_t n, T alpha, T *x) {   \
+    if (h && n > 0 && !x) return b200sp::set_error(h, B200SP_INVALID_INPUT, "fill: null");        \
+    return b200sp::launch_ew<T>(h, (cudaStream_t)s, n, b200sp::FillF<T>{alpha, x}, "fill");       \
+  }                                                                                               \
+  b200sp_status b200sp_scal_##sfx(b200sp_handle h, b200sp_stream s, int64_t n, T alpha, T *x) {   \
+    if (h && n > 0 && !x) return b200sp::set_error(h, B200SP_INVALID_INPUT, "scal: null");        \
+    return b200sp::launch_ew<T>(h, (cudaStream_t)s, n, b200sp::ScalF<T>{alpha, x}, "scal");       \
+  }                                                                                               \
+  b200sp_status b200sp_dot_##sfx(b200sp_handle h, b200sp_stream s, int64_t n, const T *x,         \
+                                 const T *y, T *result_dev, T *result_host) {                     \
+    return b200sp::reduce<T, 0>(h, (cudaStream_t)s, n, x, y, result_dev, result_host);            \
+  }                                                                                               \
+  b200sp_status b200sp_nrm2_##sfx(b200sp_handle h, b200sp_stream s, int64_t n, const T *x,        \
+                                  T *result_dev, T *result_host) {                                \
+    return b200sp::reduce<T, 1>(h, (cudaStream_t)s, n, x, nullptr, result_dev, result_host);      \
+  }
+DEF(float, f32)
+DEF(double, f64)
+#undef DEF
+}

@@ -1,0 +1,456 @@
+// cg.cu — conjugate gradients with device-resident scalars, and the generic
+// SpMV dispatch on a b200sp_matrix descriptor.
+//
+// Replaces cusp::krylov::cg with the identity preconditioner
+// (cusp/krylov/detail/cg.inl:35-107) + cusp::monitor (cusp/detail/monitor.inl:
+// 107-111,178-208).  The reference runs, per iteration, 1 SpMV + dotc + axpy +
+// axpy + copy + dotc + axpby + nrm2 = 8 passes, 18*N*sizeof(V) bytes of vector
+// traffic and 3 host round trips.  Here one iteration is
+//   K1  y = A p  with  <y,p>  fused into the SpMV epilogue           (matrix + 2N)
+//   K2  alpha = rz/<y,p>; x += alpha p; r -= alpha y; rz' = <r,r>    (6N)
+//       last CTA: beta = rz'/rz, ||r|| = sqrt(rz'), residual log, stop flag
+//   K3  p = r + beta p                                               (3N)
+// i.e. matrix + 11N, no host round trip: the host only polls a flag every
+// `check_interval` iterations; kernels launched after convergence see the flag
+// and return immediately, so x holds exactly the iterate at which the
+// reference's monitor would have stopped.  Every element update uses the
+// reference's expression (alpha*p + x, (-alpha)*y + r, z + beta*p with z == r).
+//
+// Multi-GPU (row-block partition): halo planes of p are exchanged
+// with ncclSend/ncclRecv before K1 and the two scalars are all-reduced with
+// NCCL between the kernels; the scalar step then runs as its own 1-thread kernel.
+#include "common.cuh"
+#include "comm.h"
+
+namespace b200sp {
+
+template <typename T>
+b200sp_status spmv_csr(b200sp_handle, cudaStream_t, i64, i64, i64, const int *, const int *, const T *,
+                       const T *, T *, int, const b200sp_cfg *, const T *, T *);
+template <typename T>
+b200sp_status spmv_ell(b200sp_handle, cudaStream_t, i64, i64, i64, i64, const int *, const T *, const int *,
+                       const T *, T *, int, const b200sp_cfg *, const T *, T *);
+template <typename T>
+b200sp_status spmv_dia(b200sp_handle, cudaStream_t, i64, i64, i64, i64, const int *, const T *, const T *,
+                       T *, int, const b200sp_cfg *, const T *, T *);
+template <typename T>
+b200sp_status spmv_coo(b200sp_handle, cudaStream_t, i64, i64, i64, const int *, const int *, const T *,
+                       const T *, T *, int, const b200sp_cfg *);
+template <typename T>
+b200sp_status spmv_hyb(b200sp_handle, cudaStream_t, i64, i64, i64, i64, const int *, const T *, i64,
+                       const int *, const int *, const T *, const T *, T *, int, const b200sp_cfg *,
+                       const b200sp_cfg *);
+template <typename T, int MODE>
+b200sp_status reduce(b200sp_handle, cudaStream_t, i64, const T *, const T *, T *, T *);
+
+// y = A x (+ optional fused <y, dotv>).  Formats whose kernel has no fused
+// epilogue (COO / HYB) get a separate deterministic dot kernel.
+template <typename T>
+b200sp_status spmv_any(b200sp_handle h, cudaStream_t st, const b200sp_matrix *A, const T *x, T *y,
+                       int accumulate, const b200sp_cfg *cfg, const T *dotv, T *dot_result) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, A != nullptr, "spmv: null matrix descriptor");
+  const T *vals = reinterpret_cast<const T *>(A->values);
+  b200sp_cfg cached;
+  if (!cfg && b200sp_tune_lookup(h, A, &cached)) cfg = &cached;
+  b200sp_status s;
+  switch (A->format) {
+    case B200SP_FMT_CSR:
+      return spmv_csr<T>(h, st, A->num_rows, A->num_cols, A->num_entries, A->row_offsets,
+                         A->column_indices, vals, x, y, accumulate, cfg, dotv, dot_result);
+    case B200SP_FMT_ELL:
+      return spmv_ell<T>(h, st, A->num_rows, A->num_cols, A->num_cols_per_row, A->pitch,
+                         A->column_indices, vals, nullptr, x, y, accumulate, cfg, dotv, dot_result);
+    case B200SP_FMT_ELLR:
+      B200SP_REQUIRE(h, A->row_offsets != nullptr, "ellr: row_lengths (row_offsets field) is null");
+      return spmv_ell<T>(h, st, A->num_rows, A->num_cols, A->num_cols_per_row, A->pitch,
+                         A->column_indices, vals, A->row_offsets, x, y, accumulate, cfg, dotv, dot_result);
+    case B200SP_FMT_DIA:
+      return spmv_dia<T>(h, st, A->num_rows, A->num_cols, A->num_cols_per_row, A->pitch,
+                         A->diagonal_offsets, vals, x, y, accumulate, cfg, dotv, dot_result);
+    case B200SP_FMT_COO:
+      s = spmv_coo<T>(h, st, A->num_rows, A->num_cols, A->num_entries, A->row_indices, A->column_indices,
+                      vals, x, y, accumulate, cfg);
+      break;
+    case B200SP_FMT_HYB:
+      s = spmv_hyb<T>(h, st, A->num_rows, A->num_cols, A->num_cols_per_row, A->pitch, A->column_indices,
+                      vals, A->coo_num_entries, A->coo_row_indices, A->coo_column_indices,
+                      reinterpret_cast<const T *>(A->coo_values), x, y, accumulate, cfg, nullptr);
+      break;
+    default:
+      return set_error(h, B200SP_INVALID_INPUT, "spmv: unknown format %d", (int)A->format);
+  }
+  if (s != B200SP_OK) return s;
+  if (dotv) return reduce<T, 0>(h, st, A->num_rows, y, dotv, dot_result, nullptr);
+  return B200SP_OK;
+}
+
+template b200sp_status spmv_any<float>(b200sp_handle, cudaStream_t, const b200sp_matrix *, const float *,
+                                       float *, int, const b200sp_cfg *, const float *, float *);
+template b200sp_status spmv_any<double>(b200sp_handle, cudaStream_t, const b200sp_matrix *, const double *,
+                                        double *, int, const b200sp_cfg *, const double *, double *);
+
+// ---------------------------------------------------------------------------
+// CG state in device memory
+// ---------------------------------------------------------------------------
+template <typename T>
+struct CgState {
+  T rz;      // <r,z> of the current iterate (z == r)
+  T yp;      // <A p, p>
+  T rz_new;  // scratch for the reduction
+  T beta;
+  T tol;     // absolute + relative*||b||
+  T bnorm;
+  T rnorm;
+  int iter;
+  int limit;
+  int done;       // 1 once the monitor says finished
+  int converged;  // rnorm <= tol
+  int nres;       // residuals recorded
+};
+
+// the monitor step (cusp/detail/monitor.inl:178-208): record ||r||, decide
+template <typename T>
+__device__ __forceinline__ void monitor_step(CgState<T> *S, double *residuals) {
+  const T rn = (T)sqrt((double)S->rz);
+  S->rnorm = rn;
+  residuals[S->nres++] = (double)rn;
+  if (rn <= S->tol) {
+    S->converged = 1;
+    S->done = 1;
+  } else if (S->iter >= S->limit) {
+    S->done = 1;
+  }
+}
+
+constexpr int CG_BLOCK = 256;
+constexpr int CG_UNROLL = 4;
+
+static inline i64 cg_grid(b200sp_handle h, i64 n) {
+  i64 g = ceil_div(n, (i64)CG_BLOCK * CG_UNROLL);
+  const i64 cap = (i64)h->num_sms * 8;
+  if (g > cap) g = cap;
+  return g < 1 ? 1 : g;
+}
+
+// r = b - y (axpby(b,y,r,1,-1)); p = r (z = M r = r; p = z); rz = <r,r>
+template <typename T, bool DIST>
+__global__ void __launch_bounds__(CG_BLOCK) cg_init_kernel(i64 n, const T *b, const T *y, T *r, T *p,
+                                                           CgState<T> *S, T *partials, unsigned int *ticket,
+                                                           double *residuals) {
+  __shared__ T s_red[32];
+  T acc = T(0);
+  const i64 stride = (i64)gridDim.x * CG_BLOCK;
+  for (i64 i = (i64)blockIdx.x * CG_BLOCK + threadIdx.x; i < n; i += stride) {
+    const T ri = T(1) * b[i] + T(-1) * y[i];
+    r[i] = ri;
+    p[i] = ri;
+    acc = acc + ri * ri;
+  }
+  T bs = block_sum<CG_BLOCK>(acc, s_red);
+  grid_reduce_finish<CG_BLOCK>(bs, partials, ticket, s_red, [&](T total) {
+    S->rz = total;
+    if (!DIST) monitor_step(S, residuals);
+  });
+}
+
+// x += alpha p ; r -= alpha y ; rz_new = <r,r> ; then the scalar step
+template <typename T, bool DIST>
+__global__ void __launch_bounds__(CG_BLOCK) cg_update_kernel(i64 n, const T *p, const T *y, T *x, T *r,
+                                                             CgState<T> *S, T *partials,
+                                                             unsigned int *ticket, double *residuals) {
+  __shared__ T s_red[32];
+  if (S->done) return;
+  const T alpha = S->rz / S->yp;
+  const T nalpha = -alpha;
+  T acc = T(0);
+  const i64 stride = (i64)gridDim.x * CG_BLOCK;
+  i64 i = (i64)blockIdx.x * CG_BLOCK + threadIdx.x;
+  for (; i + (CG_UNROLL - 1) * stride < n; i += CG_UNROLL * stride) {
+    T pv[CG_UNROLL], yv[CG_UNROLL], xv[CG_UNROLL], rv[CG_UNROLL];
+#pragma unroll
+    for (int u = 0; u < CG_UNROLL; ++u) {
+      pv[u] = p[i + u * stride];
+      yv[u] = y[i + u * stride];
+      xv[u] = x[i + u * stride];
+      rv[u] = r[i + u * stride];
+    }
+#pragma unroll
+    for (int u = 0; u < CG_UNROLL; ++u) {
+      x[i + u * stride] = alpha * pv[u] + xv[u];
+      const T rn = nalpha * yv[u] + rv[u];
+      r[i + u * stride] = rn;
+      acc = acc + rn * rn;
+    }
+  }
+  for (; i < n; i += stride) {
+    x[i] = alpha * p[i] + x[i];
+    const T rn = nalpha * y[i] + r[i];
+    r[i] = rn;
+    acc = acc + rn * rn;
+  }
+  T bs = block_sum<CG_BLOCK>(acc, s_red);
+  grid_reduce_finish<CG_BLOCK>(bs, partials, ticket, s_red, [&](T total) {
+    S->rz_new = total;
+    if (!DIST) {
+      S->beta = total / S->rz;
+      S->rz = total;
+      S->iter += 1;
+      monitor_step(S, residuals);
+    }
+  });
+}
+
+// distributed: after the all-reduce of rz_new
+template <typename T>
+__global__ void cg_scalar_step_kernel(CgState<T> *S, double *residuals, int first) {
+  if (first) {
+    monitor_step(S, residuals);
+    return;
+  }
+  if (S->done) return;
+  S->beta = S->rz_new / S->rz;
+  S->rz = S->rz_new;
+  S->iter += 1;
+  monitor_step(S, residuals);
+}
+
+// p = z + beta p  (axpby(z,p,p,1,beta), z == r)
+template <typename T>
+__global__ void __launch_bounds__(CG_BLOCK) cg_direction_kernel(i64 n, const T *r, T *p, const CgState<T> *S) {
+  if (S->done) return;
+  const T beta = S->beta;
+  const i64 base = (i64)blockIdx.x * (CG_BLOCK * CG_UNROLL) + threadIdx.x;
+  T rv[CG_UNROLL], pv[CG_UNROLL];
+#pragma unroll
+  for (int u = 0; u < CG_UNROLL; ++u) {
+    const i64 i = base + (i64)u * CG_BLOCK;
+    rv[u] = i < n ? r[i] : T(0);
+    pv[u] = i < n ? p[i] : T(0);
+  }
+#pragma unroll
+  for (int u = 0; u < CG_UNROLL; ++u) {
+    const i64 i = base + (i64)u * CG_BLOCK;
+    if (i < n) p[i] = T(1) * rv[u] + beta * pv[u];
+  }
+}
+
+template <typename T>
+__global__ void cg_setup_state_kernel(CgState<T> *S, const T *bnorm, double rel, double abs_tol, int limit) {
+  S->bnorm = *bnorm;
+  // monitor::tolerance(): absolute + relative*b_norm evaluated in Real
+  S->tol = (T)abs_tol + (T)rel * (*bnorm);
+  S->iter = 0;
+  S->limit = limit;
+  S->done = 0;
+  S->converged = 0;
+  S->nres = 0;
+  S->beta = T(0);
+  S->yp = T(1);
+  S->rz = T(0);
+  S->rz_new = T(0);
+  S->rnorm = T(0);
+}
+
+// kernels that must not run once `done` is set are gated inside; the SpMV is
+// not gated (its output y is scratch) — it is simply not launched after the
+// host has seen the flag.
+template <typename T>
+static b200sp_status cg_impl(b200sp_handle h, cudaStream_t st, const b200sp_matrix *A, const b200sp_halo *halo,
+                             T *x, const T *b, const b200sp_cg_params *params, const b200sp_cfg *cfg,
+                             b200sp_cg_result *result, double *residuals_host) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, A && x && b && result, "cg: null argument");
+  const bool dist = halo != nullptr;
+  const i64 n = A->num_rows;
+  const i64 halo_lo = dist ? halo->halo_lo : 0, halo_hi = dist ? halo->halo_hi : 0;
+  B200SP_REQUIRE(h, dist || A->num_rows == A->num_cols, "cg: matrix must be square");
+  B200SP_REQUIRE(h, !dist || A->num_cols == n + halo_lo + halo_hi, "cg: num_cols != halo_lo+local+halo_hi");
+  B200SP_REQUIRE(h, !dist || h->nccl_comm, "cg: distributed call without b200sp_comm_init");
+  b200sp_cg_params prm = params ? *params : b200sp_cg_params{500, 1e-5, 0.0, 0};
+  if (prm.check_interval <= 0) prm.check_interval = 16;
+  B200SP_REQUIRE(h, prm.iteration_limit >= 0 && prm.iteration_limit < (1ll << 30), "cg: bad iteration limit");
+
+  // workspace: y, r (n each) and the p window (halo_lo + n + halo_hi)
+  const size_t need = ((size_t)3 * n + halo_lo + halo_hi) * sizeof(T) + 256;
+  if (h->cg_ws_bytes < need) {
+    if (h->cg_ws) cudaFree(h->cg_ws);
+    h->cg_ws = nullptr;
+    h->cg_ws_bytes = 0;
+    if (cudaMalloc(&h->cg_ws, need) != cudaSuccess) {
+      cudaGetLastError();
+      return set_error(h, B200SP_ALLOC_FAILED, "cg: cannot allocate %zu B workspace", need);
+    }
+    h->cg_ws_bytes = need;
+  }
+  const size_t nres_cap = (size_t)prm.iteration_limit + 2;
+  if (h->cg_residuals_cap < nres_cap) {
+    if (h->cg_residuals) cudaFree(h->cg_residuals);
+    h->cg_residuals = nullptr;
+    h->cg_residuals_cap = 0;
+    if (cudaMalloc(&h->cg_residuals, nres_cap * sizeof(double)) != cudaSuccess) {
+      cudaGetLastError();
+      return set_error(h, B200SP_ALLOC_FAILED, "cg: cannot allocate residual log");
+    }
+    h->cg_residuals_cap = nres_cap;
+  }
+  T *y = reinterpret_cast<T *>(h->cg_ws);
+  T *r = y + n;
+  T *pwin = r + n;       // [halo_lo | n | halo_hi]
+  T *p = pwin + halo_lo;
+  CgState<T> *S = reinterpret_cast<CgState<T> *>(h->dev_scalars);
+  T *bn = reinterpret_cast<T *>(h->dev_scalars + 32);
+  T *partials = reinterpret_cast<T *>(h->red_partials);
+  unsigned int *ticket = h->red_counters;
+  double *res = h->cg_residuals;
+  const i64 g = cg_grid(h, n);
+  b200sp_status s;
+
+  // ||b||  (monitor constructor, monitor.inl:26-45)
+  if (dist) {
+    s = reduce<T, 0>(h, st, n, b, b, bn, nullptr);
+    if (s != B200SP_OK) return s;
+    s = comm_allreduce_sum(h, st, bn, 1, sizeof(T) == 8);
+    if (s != B200SP_OK) return s;
+    comm_sqrt_inplace(h, st, bn, sizeof(T) == 8);
+  } else {
+    s = reduce<T, 1>(h, st, n, b, nullptr, bn, nullptr);
+    if (s != B200SP_OK) return s;
+  }
+  cg_setup_state_kernel<T><<<1, 1, 0, st>>>(S, bn, prm.relative_tolerance, prm.absolute_tolerance,
+                                            (int)prm.iteration_limit);
+  B200SP_LAUNCH_CHECK(h, "cg_setup_state_kernel");
+
+  // y = A x0 ; r = b - y ; p = r ; rz = <r,r>
+  if (dist) {
+    // x0 needs its own halo: reuse the p window as staging
+    B200SP_CUDA(h, cudaMemcpyAsync(p, x, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    s = comm_halo_exchange(h, st, pwin, n, halo_lo, halo_hi, sizeof(T));
+    if (s != B200SP_OK) return s;
+    s = spmv_any<T>(h, st, A, pwin, y, 0, cfg, nullptr, nullptr);
+  } else {
+    s = spmv_any<T>(h, st, A, x, y, 0, cfg, nullptr, nullptr);
+  }
+  if (s != B200SP_OK) return s;
+  if (dist) {
+    cg_init_kernel<T, true><<<(unsigned)g, CG_BLOCK, 0, st>>>(n, b, y, r, p, S, partials, ticket, res);
+    B200SP_LAUNCH_CHECK(h, "cg_init_kernel");
+    s = comm_allreduce_sum(h, st, &S->rz, 1, sizeof(T) == 8);
+    if (s != B200SP_OK) return s;
+    cg_scalar_step_kernel<T><<<1, 1, 0, st>>>(S, res, 1);
+    B200SP_LAUNCH_CHECK(h, "cg_scalar_step_kernel");
+  } else {
+    cg_init_kernel<T, false><<<(unsigned)g, CG_BLOCK, 0, st>>>(n, b, y, r, p, S, partials, ticket, res);
+    B200SP_LAUNCH_CHECK(h, "cg_init_kernel");
+  }
+
+  CgState<T> *hs = reinterpret_cast<CgState<T> *>(h->pinned_scalars);
+  auto poll = [&]() -> b200sp_status {
+    B200SP_CUDA(h, cudaMemcpyAsync(hs, S, sizeof(CgState<T>), cudaMemcpyDeviceToHost, st));
+    B200SP_CUDA(h, cudaStreamSynchronize(st));
+    return B200SP_OK;
+  };
+  s = poll();
+  if (s != B200SP_OK) return s;
+
+  const i64 gdir = ceil_div(n, (i64)CG_BLOCK * CG_UNROLL);
+  while (!hs->done) {
+    for (int k = 0; k < prm.check_interval; ++k) {
+      if (dist) {
+        s = comm_halo_exchange(h, st, pwin, n, halo_lo, halo_hi, sizeof(T));
+        if (s != B200SP_OK) return s;
+        s = spmv_any<T>(h, st, A, pwin, y, 0, cfg, p, &S->yp);
+        if (s != B200SP_OK) return s;
+        s = comm_allreduce_sum(h, st, &S->yp, 1, sizeof(T) == 8);
+        if (s != B200SP_OK) return s;
+        cg_update_kernel<T, true><<<(unsigned)g, CG_BLOCK, 0, st>>>(n, p, y, x, r, S, partials, ticket, res);
+        B200SP_LAUNCH_CHECK(h, "cg_update_kernel");
+        s = comm_allreduce_sum(h, st, &S->rz_new, 1, sizeof(T) == 8);
+        if (s != B200SP_OK) return s;
+        cg_scalar_step_kernel<T><<<1, 1, 0, st>>>(S, res, 0);
+        B200SP_LAUNCH_CHECK(h, "cg_scalar_step_kernel");
+      } else {
+        s = spmv_any<T>(h, st, A, p, y, 0, cfg, p, &S->yp);
+        if (s != B200SP_OK) return s;
+        cg_update_kernel<T, false><<<(unsigned)g, CG_BLOCK, 0, st>>>(n, p, y, x, r, S, partials, ticket, res);
+        B200SP_LAUNCH_CHECK(h, "cg_update_kernel");
+      }
+      cg_direction_kernel<T><<<(unsigned)gdir, CG_BLOCK, 0, st>>>(n, r, p, S);
+      B200SP_LAUNCH_CHECK(h, "cg_direction_kernel");
+    }
+    s = poll();
+    if (s != B200SP_OK) return s;
+  }
+
+  result->iteration_count = hs->iter;
+  result->converged = hs->converged;
+  result->residual_norm = (double)hs->rnorm;
+  result->b_norm = (double)hs->bnorm;
+  result->num_residuals = hs->nres;
+  if (residuals_host && hs->nres > 0) {
+    B200SP_CUDA(h, cudaMemcpyAsync(residuals_host, res, (size_t)hs->nres * sizeof(double),
+                                   cudaMemcpyDeviceToHost, st));
+    B200SP_CUDA(h, cudaStreamSynchronize(st));
+  }
+  return B200SP_OK;
+}
+
+}  // namespace b200sp
+
+extern "C" {
+
+b200sp_status b200sp_spmv(b200sp_handle h, b200sp_stream stream, const b200sp_matrix *A, const void *x,
+                          void *y, int accumulate, const b200sp_cfg *cfg) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, A != nullptr, "spmv: null matrix descriptor");
+  if (A->dtype == B200SP_F32)
+    return b200sp::spmv_any<float>(h, (cudaStream_t)stream, A, (const float *)x, (float *)y, accumulate,
+                                   cfg, nullptr, nullptr);
+  if (A->dtype == B200SP_F64)
+    return b200sp::spmv_any<double>(h, (cudaStream_t)stream, A, (const double *)x, (double *)y, accumulate,
+                                    cfg, nullptr, nullptr);
+  return b200sp::set_error(h, B200SP_INVALID_INPUT, "spmv: unknown dtype %d", (int)A->dtype);
+}
+
+b200sp_status b200sp_cg(b200sp_handle h, b200sp_stream stream, const b200sp_matrix *A, void *x,
+                        const void *b, const b200sp_cg_params *params, const b200sp_cfg *spmv_cfg,
+                        b200sp_cg_result *result, double *residuals_host) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, A != nullptr, "cg: null matrix descriptor");
+  if (A->dtype == B200SP_F32)
+    return b200sp::cg_impl<float>(h, (cudaStream_t)stream, A, nullptr, (float *)x, (const float *)b, params,
+                                  spmv_cfg, result, residuals_host);
+  if (A->dtype == B200SP_F64)
+    return b200sp::cg_impl<double>(h, (cudaStream_t)stream, A, nullptr, (double *)x, (const double *)b,
+                                   params, spmv_cfg, result, residuals_host);
+  return b200sp::set_error(h, B200SP_INVALID_INPUT, "cg: unknown dtype %d", (int)A->dtype);
+}
+
+b200sp_status b200sp_cg_dist(b200sp_handle h, b200sp_stream stream, const b200sp_matrix *A_local,
+                             const b200sp_halo *halo, void *x_local, const void *b_local,
+                             const b200sp_cg_params *params, const b200sp_cfg *spmv_cfg,
+                             b200sp_cg_result *result, double *residuals_host) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, A_local != nullptr && halo != nullptr, "cg_dist: null argument");
+  if (A_local->dtype == B200SP_F32)
+    return b200sp::cg_impl<float>(h, (cudaStream_t)stream, A_local, halo, (float *)x_local,
+                                  (const float *)b_local, params, spmv_cfg, result, residuals_host);
+  if (A_local->dtype == B200SP_F64)
+    return b200sp::cg_impl<double>(h, (cudaStream_t)stream, A_local, halo, (double *)x_local,
+                                   (const double *)b_local, params, spmv_cfg, result, residuals_host);
+  return b200sp::set_error(h, B200SP_INVALID_INPUT, "cg_dist: unknown dtype %d", (int)A_local->dtype);
+}
+
+b200sp_status b200sp_spmv_dist(b200sp_handle h, b200sp_stream stream, const b200sp_matrix *A_local,
+                               const b200sp_halo *halo, void *x_window, void *y_local,
+                               const b200sp_cfg *cfg) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, A_local && halo && x_window && y_local, "spmv_dist: null argument");
+  B200SP_REQUIRE(h, h->nccl_comm, "spmv_dist: b200sp_comm_init has not been called");
+  const size_t elem = A_local->dtype == B200SP_F64 ? 8 : 4;
+  b200sp_status s = b200sp::comm_halo_exchange(h, (cudaStream_t)stream, x_window, A_local->num_rows,
+                                               halo->halo_lo, halo->halo_hi, elem);
+  if (s != B200SP_OK) return s;
+  return b200sp_spmv(h, stream, A_local, x_window, y_local, 0, cfg);
+}
+}

@@ -1,0 +1,321 @@
+// spmv_coo.cu — COO and HYB SpMV for sm_100a.
+//
+// Replaces, for coo_matrix on device_memory:
+//   - the thrust::reduce_by_key path that actually runs today
+//     (cusp/system/detail/generic/multiply/spmv.h:182-238: 3 kernels, 2 temporaries
+//     of num_rows, allocations per call),
+//   - the dormant spmv_coo_flat_kernel + reduce_update + serial trio
+//     (cusp/system/cuda/detail/multiply/coo_flat_spmv.h:225-463, coo_serial.h:35-54),
+//   - the KTT coo_spmv variants that all finish with global atomicAdd
+//     (cusp/system/cuda/ktt/kernels/coo_kernel.h:25-392).
+// and for hyb_matrix the two-pass generic/multiply/spmv.h:272-290.
+// Semantics: host loop cusp/system/detail/sequential/multiply/coo_spmv.h:35-68
+//     y[i] = init(y[i]);  for n ascending: y[Ai[n]] += Ax[n]*x[Aj[n]]
+// with row indices sorted ascending (duplicates allowed), as cusp requires.
+//
+// K_COO_SEGSCAN — nnz-balanced, deterministic, no atomics:
+//   * a CTA owns a tile of BLOCK*VPT consecutive entries (hub rows of any length
+//     are split evenly: "merge-path" balance degenerates to an even nnz split
+//     because COO stores the row of every entry);
+//   * entries are loaded coalesced (ld.global.cs), x gathered (ld.global.nc),
+//     products + rows parked in shared memory, then each thread reduces VPT
+//     consecutive entries serially (VPT odd -> conflict-free) and a block-wide
+//     segmented scan in shared memory/shuffles stitches rows across threads;
+//   * rows that lie entirely inside a tile are written straight to y; the (at
+//     most two) rows a tile shares with its neighbours go to a per-tile carry
+//     record; a second tiny kernel walks each carry chain in tile order.
+//   Summation order is fixed by (nnz, BLOCK, VPT) -> bit-reproducible.
+//
+// Algorithmic bytes: nnz*(8+sizeof(T)) + cols*sizeof(T) + rows*sizeof(T).
+#include "common.cuh"
+
+namespace b200sp {
+
+template <typename T>
+struct CooCarry {
+  int head_row;  // row continued from the previous tile that ends here, or -1
+  int tail_row;  // row left open at the end of this tile, or -1
+  int leader;    // tail_row began inside this tile
+  int pad;
+  T head_val;
+  T tail_val;
+};
+
+template <typename T>
+struct CooArgs {
+  i64 rows, cols, nnz;
+  const int *Ai;
+  const int *Aj;
+  const T *Ax;
+  const T *x;
+  T *y;
+  int accumulate;
+  CooCarry<T> *carry;
+};
+
+template <typename T, int BLOCK, int VPT>
+__global__ void __launch_bounds__(BLOCK) coo_segscan_kernel(CooArgs<T> a) {
+  constexpr int TILE = BLOCK * VPT;
+  constexpr int NW = BLOCK / 32;
+  __shared__ int s_row[TILE + 1];
+  __shared__ T s_val[TILE];
+  __shared__ T s_wv[NW];
+  __shared__ int s_wf[NW];
+  __shared__ int s_head_row;
+  __shared__ T s_head_val;
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const i64 start = (i64)blockIdx.x * TILE;
+  const int n = (int)min((i64)TILE, a.nnz - start);
+  const unsigned cols = (unsigned)a.cols;
+
+  // ---- coalesced load + gather + multiply -------------------------------
+  {
+    int r[VPT], c[VPT];
+    T v[VPT], xv[VPT];
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const i64 g = min(start + i * BLOCK + tid, a.nnz - 1);
+      r[i] = ld_stream(a.Ai + g);
+      c[i] = ld_stream(a.Aj + g);
+      v[i] = ld_stream(a.Ax + g);
+    }
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      pin(c[i]);
+      xv[i] = ld_ro(a.x + min((unsigned)c[i], cols - 1));
+    }
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      pin(xv[i]);
+      const int idx = i * BLOCK + tid;
+      const bool ok = idx < n;
+      s_row[idx] = ok ? r[i] : -1;
+      s_val[idx] = ok ? v[i] * xv[i] : T(0);
+    }
+  }
+  int prev_row = -1;
+  if (tid == 0) {
+    s_row[TILE] = (start + TILE < a.nnz) ? a.Ai[start + TILE] : -1;
+    s_head_row = -1;
+    s_head_val = T(0);
+  }
+  if (start > 0) prev_row = ld_ro(a.Ai + start - 1);
+  __syncthreads();
+
+  // ---- per-thread serial segmented reduction over VPT consecutive entries ----
+  int rr[VPT + 1];
+  T pv[VPT];
+#pragma unroll
+  for (int q = 0; q < VPT; ++q) {
+    rr[q] = s_row[tid * VPT + q];
+    pv[q] = s_val[tid * VPT + q];
+  }
+  rr[VPT] = s_row[tid * VPT + VPT];
+
+  T run = T(0), head = T(0);
+  int head_row = -1;
+  bool has_b = false;
+#pragma unroll
+  for (int q = 0; q < VPT; ++q) {
+    run = run + pv[q];
+    if (rr[q] != rr[q + 1]) {  // row rr[q] ends at this entry
+      if (!has_b) {
+        head = run;
+        head_row = rr[q];
+        has_b = true;
+      } else if (rr[q] >= 0) {
+        // began and ended inside this thread: sole owner of y[row]
+        a.y[rr[q]] = a.accumulate ? a.y[rr[q]] + run : run;
+      }
+      run = T(0);
+    }
+  }
+
+  // ---- block-wide segmented scan of (has_b, tail) ---------------------------
+  T vi = run;
+  int fi = has_b ? 1 : 0;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const T vu = __shfl_up_sync(0xffffffffu, vi, d);
+    const int fu = __shfl_up_sync(0xffffffffu, fi, d);
+    if (lane >= d) {
+      if (!fi) vi = vu + vi;
+      fi |= fu;
+    }
+  }
+  if (lane == 31) {
+    s_wv[w] = vi;
+    s_wf[w] = fi;
+  }
+  __syncthreads();
+  // exclusive prefix over warps (serial over <= 16 warps: fixed order)
+  T VW = T(0);
+  for (int k = 0; k < w; ++k) VW = s_wf[k] ? s_wv[k] : VW + s_wv[k];
+  const T Vi = fi ? vi : VW + vi;  // block-inclusive tail sum
+  T carry_in = __shfl_up_sync(0xffffffffu, Vi, 1);
+  if (lane == 0) carry_in = VW;
+
+  if (has_b && head_row >= 0) {
+    const T total = carry_in + head;
+    if (head_row == prev_row) {  // row continued from the previous tile
+      s_head_row = head_row;
+      s_head_val = total;
+    } else {
+      a.y[head_row] = a.accumulate ? a.y[head_row] + total : total;
+    }
+  }
+  __syncthreads();
+  if (tid == BLOCK - 1) {
+    CooCarry<T> cr;
+    cr.head_row = s_head_row;
+    cr.head_val = s_head_val;
+    cr.pad = 0;
+    const int last_row = rr[VPT - 1];
+    if (last_row >= 0 && last_row == rr[VPT]) {
+      cr.tail_row = last_row;
+      cr.tail_val = Vi;
+      cr.leader = (last_row != prev_row) ? 1 : 0;
+    } else {
+      cr.tail_row = -1;
+      cr.tail_val = T(0);
+      cr.leader = 0;
+    }
+    a.carry[blockIdx.x] = cr;
+  }
+}
+
+// one thread per tile: leaders walk their carry chain in tile order
+template <typename T>
+__global__ void coo_fixup_kernel(i64 num_tiles, const CooCarry<T> *carry, T *y) {
+  const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= num_tiles) return;
+  const CooCarry<T> me = carry[t];
+  if (me.tail_row < 0 || !me.leader) return;
+  const int row = me.tail_row;
+  T total = me.tail_val;
+  for (i64 u = t + 1; u < num_tiles; ++u) {
+    const CooCarry<T> nx = carry[u];
+    if (nx.head_row == row) {
+      total = total + nx.head_val;
+      break;
+    } else if (nx.tail_row == row && !nx.leader) {
+      total = total + nx.tail_val;
+    } else {
+      break;
+    }
+  }
+  y[row] = y[row] + total;
+}
+
+template <typename T, int BLOCK, int VPT>
+static b200sp_status launch_coo(b200sp_handle h, cudaStream_t st, CooArgs<T> a) {
+  constexpr int TILE = BLOCK * VPT;
+  const i64 tiles = ceil_div(a.nnz, (i64)TILE);
+  b200sp_status s = ensure_scratch(h, (size_t)tiles * sizeof(CooCarry<T>));
+  if (s != B200SP_OK) return s;
+  a.carry = reinterpret_cast<CooCarry<T> *>(h->scratch);
+  coo_segscan_kernel<T, BLOCK, VPT><<<(unsigned)tiles, BLOCK, 0, st>>>(a);
+  B200SP_LAUNCH_CHECK(h, "coo_segscan_kernel");
+  coo_fixup_kernel<T><<<(unsigned)ceil_div(tiles, 256), 256, 0, st>>>(tiles, a.carry, a.y);
+  B200SP_LAUNCH_CHECK(h, "coo_fixup_kernel");
+  return B200SP_OK;
+}
+
+static void coo_defaults(b200sp_cfg &c) {
+  if (c.kernel == 0) c.kernel = B200SP_K_COO_SEGSCAN;
+  if (c.block_size == 0) c.block_size = 256;
+  if (c.unroll == 0) c.unroll = 7;
+}
+
+template <typename T>
+b200sp_status spmv_coo(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64 nnz, const int *Ai,
+                       const int *Aj, const T *Ax, const T *x, T *y, int accumulate,
+                       const b200sp_cfg *cfg) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, rows >= 0 && cols >= 0 && nnz >= 0, "coo: negative dimension");
+  B200SP_REQUIRE(h, rows < (1ll << 31) && cols < (1ll << 31), "coo: int32 index range");
+  if (rows == 0) return B200SP_OK;
+  B200SP_REQUIRE(h, y != nullptr, "coo: null pointer");
+  if (!accumulate) B200SP_CUDA(h, cudaMemsetAsync(y, 0, (size_t)rows * sizeof(T), st));
+  if (nnz == 0) return B200SP_OK;
+  B200SP_REQUIRE(h, Ai && Aj && Ax && x, "coo: null pointer");
+  B200SP_REQUIRE(h, cols > 0, "coo: num_cols == 0 with stored entries");
+
+  b200sp_cfg c = cfg ? *cfg : b200sp_cfg{};
+  coo_defaults(c);
+  if (c.kernel != B200SP_K_COO_SEGSCAN) return set_error(h, B200SP_INVALID_INPUT, "coo: unknown kernel id %d", c.kernel);
+
+  CooArgs<T> a;
+  a.rows = rows; a.cols = cols; a.nnz = nnz; a.Ai = Ai; a.Aj = Aj; a.Ax = Ax; a.x = x; a.y = y;
+  // y was zeroed above for y = A x, so both modes accumulate into y from here
+  a.accumulate = 1;
+  a.carry = nullptr;
+#define CASE(B, V) \
+  if (c.block_size == B && c.unroll == V) return launch_coo<T, B, V>(h, st, a);
+  CASE(128, 5) CASE(128, 7) CASE(128, 9) CASE(128, 11)
+  CASE(256, 5) CASE(256, 7) CASE(256, 9) CASE(256, 11)
+  CASE(512, 5) CASE(512, 7)
+#undef CASE
+  return set_error(h, B200SP_INVALID_INPUT, "coo: unsupported block_size=%d unroll=%d", c.block_size, c.unroll);
+}
+
+template b200sp_status spmv_coo<float>(b200sp_handle, cudaStream_t, i64, i64, i64, const int *, const int *,
+                                       const float *, const float *, float *, int, const b200sp_cfg *);
+template b200sp_status spmv_coo<double>(b200sp_handle, cudaStream_t, i64, i64, i64, const int *, const int *,
+                                        const double *, const double *, double *, int, const b200sp_cfg *);
+
+// declared in spmv_ell.cu
+template <typename T>
+b200sp_status spmv_ell(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64 K, i64 pitch,
+                       const int *cidx, const T *vals, const int *row_lengths, const T *x, T *y,
+                       int accumulate, const b200sp_cfg *cfg, const T *dotv, T *dot_result);
+
+// HYB = ELL pass (init = caller's) then COO pass with identity
+// (cusp/system/detail/sequential/multiply/hyb_spmv.h:35-57)
+template <typename T>
+b200sp_status spmv_hyb(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64 K, i64 pitch,
+                       const int *ecidx, const T *evals, i64 cnnz, const int *ci, const int *cj,
+                       const T *cv, const T *x, T *y, int accumulate, const b200sp_cfg *ecfg,
+                       const b200sp_cfg *ccfg) {
+  B200SP_CHECK_HANDLE(h);
+  b200sp_status s = spmv_ell<T>(h, st, rows, cols, K, pitch, ecidx, evals, nullptr, x, y, accumulate, ecfg,
+                                nullptr, nullptr);
+  if (s != B200SP_OK) return s;
+  return spmv_coo<T>(h, st, rows, cols, cnnz, ci, cj, cv, x, y, 1, ccfg);
+}
+
+template b200sp_status spmv_hyb<float>(b200sp_handle, cudaStream_t, i64, i64, i64, i64, const int *,
+                                       const float *, i64, const int *, const int *, const float *,
+                                       const float *, float *, int, const b200sp_cfg *, const b200sp_cfg *);
+template b200sp_status spmv_hyb<double>(b200sp_handle, cudaStream_t, i64, i64, i64, i64, const int *,
+                                        const double *, i64, const int *, const int *, const double *,
+                                        const double *, double *, int, const b200sp_cfg *, const b200sp_cfg *);
+
+}  // namespace b200sp
+
+extern "C" {
+#define DEF(T, sfx)                                                                              \
+  b200sp_status b200sp_spmv_coo_##sfx(b200sp_handle h, b200sp_stream stream, int64_t num_rows,   \
+                                      int64_t num_cols, int64_t num_entries,                     \
+                                      const int32_t *row_indices, const int32_t *column_indices, \
+                                      const T *values, const T *x, T *y, int accumulate,         \
+                                      const b200sp_cfg *cfg) {                                   \
+    return b200sp::spmv_coo<T>(h, (cudaStream_t)stream, num_rows, num_cols, num_entries,         \
+                               row_indices, column_indices, values, x, y, accumulate, cfg);      \
+  }                                                                                              \
+  b200sp_status b200sp_spmv_hyb_##sfx(                                                           \
+      b200sp_handle h, b200sp_stream stream, int64_t num_rows, int64_t num_cols,                 \
+      int64_t ell_cols_per_row, int64_t ell_pitch, const int32_t *ell_column_indices,            \
+      const T *ell_values, int64_t coo_num_entries, const int32_t *coo_row_indices,              \
+      const int32_t *coo_column_indices, const T *coo_values, const T *x, T *y, int accumulate,  \
+      const b200sp_cfg *ell_cfg, const b200sp_cfg *coo_cfg) {                                    \
+    return b200sp::spmv_hyb<T>(h, (cudaStream_t)stream, num_rows, num_cols, ell_cols_per_row,    \
+                               ell_pitch, ell_column_indices, ell_values, coo_num_entries,       \
+                               coo_row_indices, coo_column_indices, coo_values, x, y,            \
+                               accumulate, ell_cfg, coo_cfg);                                    \
+  }
+DEF(float, f32)
+DEF(double, f64)
+#undef DEF
+}

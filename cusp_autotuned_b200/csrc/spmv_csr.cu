@@ -1,0 +1,232 @@
+// spmv_csr.cu — CSR SpMV for sm_100a.
+//
+// Replaces spmv_csr_vector_kernel (cusp/system/cuda/detail/multiply/
+// csr_vector_spmv.h:66-161; volatile-smem warp-synchronous reduction, undefined
+// on Volta+), spmv_csr_scalar_kernel (csr_scalar.h:48-73) and the KTT kernels
+// csr_kernel_{naive,warp} (cusp/system/cuda/ktt/kernels/csr_kernel.h:160-235).
+// Semantics: host loop cusp/system/detail/sequential/multiply/csr_spmv.h:35-74
+//     acc = init(y[i]); for jj in row i: acc += Ax[jj]*x[Aj[jj]]; y[i] = acc
+//
+//  K_CSR_VECTOR : a sub-warp of TPR in {1,2,4,8,16,32} lanes owns a row; lanes
+//     stride the row, partial sums are combined with __shfl_down_sync (width TPR);
+//     each sub-warp keeps RPT independent rows in flight (adjacent sub-warps take
+//     adjacent rows, so a warp's loads of Aj/Ax cover one contiguous nnz range).
+//     TPR == 1 is the scalar kernel and keeps the reference's summation order
+//     (bit-identical with -fmad=false); TPR > 1 changes only the grouping.
+//     Long rows continue in a 4x-unrolled strided loop.
+//
+// Algorithmic bytes: (rows+1)*4 + nnz*(4+sizeof(T)) + cols*sizeof(T) + rows*sizeof(T).
+#include "common.cuh"
+
+namespace b200sp {
+
+template <typename T>
+struct CsrArgs {
+  i64 rows, cols, nnz;
+  const int *Ap;
+  const int *Aj;
+  const T *Ax;
+  const T *x;
+  T *y;
+  int accumulate;
+  const T *dotv;
+  T *dot_partials;
+  unsigned int *dot_ticket;
+  T *dot_result;
+};
+
+template <typename T, int BLOCK, int TPR, int RPT>
+__global__ void __launch_bounds__(BLOCK) csr_vector_kernel(CsrArgs<T> a) {
+  constexpr int VPB = BLOCK / TPR;  // rows in flight per CTA per step
+  __shared__ T s_red[32];
+  const int lane = threadIdx.x & (TPR - 1);
+  const unsigned vec = threadIdx.x / TPR;
+  const unsigned rows = (unsigned)a.rows, cols = (unsigned)a.cols;
+  const int last = (int)(a.nnz - 1);
+  const unsigned base = blockIdx.x * (unsigned)(VPB * RPT) + vec;
+
+  int s[RPT], e[RPT];
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    const unsigned r = base + i * VPB;
+    const unsigned rc = min(r, rows - 1);
+    s[i] = ld_ro(a.Ap + rc);
+    e[i] = ld_ro(a.Ap + rc + 1);
+  }
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    pin(s[i]);
+    pin(e[i]);
+    if (base + i * VPB >= rows) e[i] = s[i];
+  }
+
+  T sum[RPT];
+  {
+    int c[RPT];
+    T v[RPT], xv[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const int jc = min(s[i] + lane, last);
+      c[i] = ld_stream(a.Aj + jc);
+      v[i] = ld_stream(a.Ax + jc);
+    }
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      pin(c[i]);
+      xv[i] = ld_ro(a.x + min((unsigned)c[i], cols - 1));
+    }
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      pin(xv[i]);
+      T init = T(0);
+      if (TPR == 1 && a.accumulate && base + i * VPB < rows) init = a.y[base + i * VPB];
+      const T t = init + v[i] * xv[i];
+      sum[i] = (s[i] + lane < e[i]) ? t : init;
+    }
+  }
+  // rows longer than TPR
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    for (int jj = s[i] + lane + TPR; jj < e[i]; jj += 4 * TPR) {
+      int c[4];
+      T v[4], xv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int jc = min(jj + q * TPR, last);
+        c[q] = ld_stream(a.Aj + jc);
+        v[q] = ld_stream(a.Ax + jc);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        pin(c[q]);
+        xv[q] = ld_ro(a.x + min((unsigned)c[q], cols - 1));
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const T t = sum[i] + v[q] * xv[q];
+        sum[i] = (jj + q * TPR < e[i]) ? t : sum[i];
+      }
+    }
+  }
+
+  T dsum = 0;
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    const unsigned r = base + i * VPB;
+    T tot = subwarp_sum<TPR>(sum[i]);
+    if (lane == 0 && r < rows) {
+      if (TPR > 1 && a.accumulate) tot = a.y[r] + tot;
+      a.y[r] = tot;
+      if (a.dotv) dsum = dsum + tot * ld_ro(a.dotv + r);
+    }
+  }
+  if (a.dotv) {
+    T bs = block_sum<BLOCK>(dsum, s_red);
+    grid_reduce_finish<BLOCK>(bs, a.dot_partials, a.dot_ticket, s_red,
+                              [&](T total) { *a.dot_result = total; });
+  }
+}
+
+template <typename T, int BLOCK, int TPR, int RPT>
+static b200sp_status launch_vec(b200sp_handle h, cudaStream_t st, CsrArgs<T> a) {
+  const i64 grid = ceil_div(a.rows, (i64)(BLOCK / TPR) * RPT);
+  if (a.dotv && grid > RED_MAX_PARTIALS)
+    return set_error(h, B200SP_INVALID_INPUT, "csr: too many CTAs for fused dot");
+  csr_vector_kernel<T, BLOCK, TPR, RPT><<<(unsigned)grid, BLOCK, 0, st>>>(a);
+  B200SP_LAUNCH_CHECK(h, "csr_vector_kernel");
+  return B200SP_OK;
+}
+
+template <typename T, int BLOCK>
+static b200sp_status dispatch_tpr(b200sp_handle h, cudaStream_t st, const CsrArgs<T> &a, int tpr, int rpt) {
+#define CASE(P, R) \
+  if (tpr == P && rpt == R) return launch_vec<T, BLOCK, P, R>(h, st, a);
+  CASE(1, 1) CASE(1, 2) CASE(1, 4)
+  CASE(2, 1) CASE(2, 2) CASE(2, 4)
+  CASE(4, 1) CASE(4, 2) CASE(4, 4)
+  CASE(8, 1) CASE(8, 2) CASE(8, 4)
+  CASE(16, 1) CASE(16, 2) CASE(16, 4)
+  CASE(32, 1) CASE(32, 2) CASE(32, 4)
+#undef CASE
+  return set_error(h, B200SP_INVALID_INPUT, "csr: unsupported threads_per_row=%d unroll=%d", tpr, rpt);
+}
+
+static void csr_defaults(b200sp_cfg &c, i64 rows, i64 nnz) {
+  if (c.kernel == 0) c.kernel = B200SP_K_CSR_VECTOR;
+  if (c.block_size == 0) c.block_size = 256;
+  if (c.threads_per_row == 0) {
+    // smallest power of two >= mean row length (the reference uses the integer
+    // mean nnz/rows, csr_vector_spmv.h:236-257, which under-sizes e.g. 7 -> 4)
+    const double mean = rows > 0 ? (double)nnz / (double)rows : 0.0;
+    int t = 2;
+    while (t < 32 && (double)t < mean) t *= 2;
+    c.threads_per_row = t;
+  }
+  if (c.unroll == 0) c.unroll = (c.threads_per_row >= 32) ? 2 : 4;
+}
+
+template <typename T>
+b200sp_status spmv_csr(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64 nnz, const int *Ap,
+                       const int *Aj, const T *Ax, const T *x, T *y, int accumulate,
+                       const b200sp_cfg *cfg, const T *dotv, T *dot_result) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, rows >= 0 && cols >= 0 && nnz >= 0, "csr: negative dimension");
+  B200SP_REQUIRE(h, rows < (1ll << 31) && cols < (1ll << 31) && nnz < (1ll << 31), "csr: int32 index range");
+  if (rows == 0) {
+    if (dot_result) B200SP_CUDA(h, cudaMemsetAsync(dot_result, 0, sizeof(T), st));
+    return B200SP_OK;
+  }
+  B200SP_REQUIRE(h, y != nullptr && Ap != nullptr, "csr: null pointer");
+  if (nnz == 0) {  // every row is empty: y = init(y)
+    if (!accumulate) B200SP_CUDA(h, cudaMemsetAsync(y, 0, (size_t)rows * sizeof(T), st));
+    if (dot_result) B200SP_CUDA(h, cudaMemsetAsync(dot_result, 0, sizeof(T), st));
+    return B200SP_OK;
+  }
+  B200SP_REQUIRE(h, Aj && Ax && x, "csr: null pointer");
+  B200SP_REQUIRE(h, cols > 0, "csr: num_cols == 0 with stored entries");
+
+  b200sp_cfg c = cfg ? *cfg : b200sp_cfg{};
+  csr_defaults(c, rows, nnz);
+  if (c.kernel != B200SP_K_CSR_VECTOR && c.kernel != B200SP_K_CSR_STREAM)
+    return set_error(h, B200SP_INVALID_INPUT, "csr: unknown kernel id %d", c.kernel);
+  if (c.kernel == B200SP_K_CSR_STREAM)
+    return set_error(h, B200SP_NOT_IMPLEMENTED, "csr: K_CSR_STREAM is not built in this release");
+
+  CsrArgs<T> a;
+  a.rows = rows; a.cols = cols; a.nnz = nnz; a.Ap = Ap; a.Aj = Aj; a.Ax = Ax; a.x = x; a.y = y;
+  a.accumulate = accumulate; a.dotv = dotv; a.dot_result = dot_result;
+  a.dot_partials = reinterpret_cast<T *>(h->red_partials);
+  a.dot_ticket = h->red_counters;
+
+  switch (c.block_size) {
+    case 128: return dispatch_tpr<T, 128>(h, st, a, c.threads_per_row, c.unroll);
+    case 256: return dispatch_tpr<T, 256>(h, st, a, c.threads_per_row, c.unroll);
+    case 512: return dispatch_tpr<T, 512>(h, st, a, c.threads_per_row, c.unroll);
+  }
+  return set_error(h, B200SP_INVALID_INPUT, "csr: unsupported block_size=%d", c.block_size);
+}
+
+template b200sp_status spmv_csr<float>(b200sp_handle, cudaStream_t, i64, i64, i64, const int *, const int *,
+                                       const float *, const float *, float *, int, const b200sp_cfg *,
+                                       const float *, float *);
+template b200sp_status spmv_csr<double>(b200sp_handle, cudaStream_t, i64, i64, i64, const int *, const int *,
+                                        const double *, const double *, double *, int, const b200sp_cfg *,
+                                        const double *, double *);
+
+}  // namespace b200sp
+
+extern "C" {
+#define DEF(T, sfx)                                                                             \
+  b200sp_status b200sp_spmv_csr_##sfx(b200sp_handle h, b200sp_stream stream, int64_t num_rows,  \
+                                      int64_t num_cols, int64_t num_entries,                    \
+                                      const int32_t *row_offsets, const int32_t *column_indices, \
+                                      const T *values, const T *x, T *y, int accumulate,        \
+                                      const b200sp_cfg *cfg) {                                  \
+    return b200sp::spmv_csr<T>(h, (cudaStream_t)stream, num_rows, num_cols, num_entries,        \
+                               row_offsets, column_indices, values, x, y, accumulate, cfg,      \
+                               nullptr, nullptr);                                               \
+  }
+DEF(float, f32)
+DEF(double, f64)
+#undef DEF
+}

@@ -1,0 +1,402 @@
+// spmv_dia.cu — DIA SpMV for sm_100a.
+//
+// Replaces spmv_dia_kernel (cusp/system/cuda/detail/multiply/dia_spmv.h:66-126)
+// and the KTT kernel ktt_dia_vector_kernel (cusp/system/cuda/ktt/kernels/
+// dia_kernel.h:129-252).  Semantics follow the host loop
+// cusp/system/detail/sequential/multiply/dia_spmv.h:36-82:
+//     y[i] = init(y[i]);  for d ascending:  y[i] += values(i,d) * x[i+off[d]]
+// for every (i,d) with 0 <= i+off[d] < num_cols.  One thread owns a row and adds
+// the diagonals in ascending d, so with -fmad=false the result is bit-identical
+// to that loop.
+//
+// Data layout (HBM): values is column-major, entry (row,d) at values[d*pitch+row]
+// -> for a fixed d a tile of rows is one contiguous slab.
+//
+//  K_DIA_LDG : thread handles RPT rows strided by BLOCK (perfectly coalesced
+//              32-lane loads), diagonals unrolled 8-deep so RPT*8 slab loads and
+//              RPT*8 x loads are in flight per thread; slabs via ld.global.cs,
+//              x via ld.global.nc.
+//  K_DIA_BULK: persistent CTAs; a producer thread stages [KC diagonals x R rows]
+//              slabs into a ring of shared-memory stages with cp.async.bulk
+//              (TMA engine, SASS UBLKCP) completing on mbarriers with an L2
+//              evict-first policy; consumer warps read the slabs from smem and x
+//              through ld.global.nc.  Needs pitch*sizeof(T) % 16 == 0.
+//
+// Algorithmic bytes / row: K*sizeof(T) slab + sizeof(T) x + sizeof(T) y.
+#include "common.cuh"
+
+namespace b200sp {
+
+template <typename T>
+struct DiaArgs {
+  i64 rows, cols, pitch;
+  int ndiag;
+  const int *offs;
+  const T *vals;
+  const T *x;
+  T *y;
+  int accumulate;
+  // optional fused dot product  sum_r y[r]*dotv[r]  (CG: <Ap,p>)
+  const T *dotv;
+  T *dot_partials;
+  unsigned int *dot_ticket;
+  T *dot_result;
+  i64 row_begin;  // first row handled by this launch (remainder launches)
+};
+
+constexpr int DIA_DU = 8;            // diagonals in flight per thread
+constexpr int DIA_SMEM_OFFS = 2048;  // offsets cached in smem per chunk
+
+// Row / column arithmetic is done in 32-bit unsigned: rows, cols < 2^31, so
+// c = row + offset (mod 2^32) is a valid column  <=>  c < cols  (a true sum
+// outside [0, 2^31) wraps to >= 2^31).  Loads are issued unconditionally on
+// clamped addresses (predicated loads would need more predicate registers than
+// exist and serialise the batch); the bounds decision is re-derived at the add.
+template <typename T, int RPT>
+__device__ __forceinline__ void dia_accumulate_group(const T *__restrict__ vals, i64 pitch,
+                                                     const T *__restrict__ x, const int *s_off,
+                                                     int d0, const unsigned (&rc)[RPT],
+                                                     unsigned cols, T (&acc)[RPT]) {
+  T v[DIA_DU][RPT], xv[DIA_DU][RPT];
+  unsigned off[DIA_DU];
+#pragma unroll
+  for (int u = 0; u < DIA_DU; ++u) {
+    off[u] = (unsigned)s_off[d0 + u];
+    const T *slab = vals + (i64)(d0 + u) * pitch;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      v[u][i] = ld_stream(slab + rc[i]);
+      xv[u][i] = ld_ro(x + min(rc[i] + off[u], cols - 1));
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < DIA_DU; ++u)
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      pin(v[u][i]);
+      pin(xv[u][i]);
+    }
+#pragma unroll
+  for (int u = 0; u < DIA_DU; ++u)
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const T t = acc[i] + v[u][i] * xv[u][i];
+      acc[i] = (rc[i] + off[u] < cols) ? t : acc[i];
+    }
+}
+
+template <typename T, int BLOCK, int RPT>
+__global__ void __launch_bounds__(BLOCK) dia_ldg_kernel(DiaArgs<T> a) {
+  __shared__ int s_off[DIA_SMEM_OFFS];
+  __shared__ T s_red[32];
+
+  const unsigned rows = (unsigned)a.rows, cols = (unsigned)a.cols;
+  const unsigned base = (unsigned)a.row_begin + blockIdx.x * (unsigned)(BLOCK * RPT) + threadIdx.x;
+  T acc[RPT];
+  unsigned rc[RPT];
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    const unsigned r = base + i * BLOCK;
+    rc[i] = min(r, rows - 1);
+    acc[i] = (a.accumulate && r < rows) ? a.y[r] : T(0);
+  }
+
+  for (int dc = 0; dc < a.ndiag; dc += DIA_SMEM_OFFS) {
+    const int nd = min(DIA_SMEM_OFFS, a.ndiag - dc);
+    if (dc > 0) __syncthreads();
+    for (int d = threadIdx.x; d < nd; d += BLOCK) s_off[d] = a.offs[dc + d];
+    __syncthreads();
+    const T *vals = a.vals + (i64)dc * a.pitch;
+    int d0 = 0;
+    for (; d0 + DIA_DU <= nd; d0 += DIA_DU)
+      dia_accumulate_group<T, RPT>(vals, a.pitch, a.x, s_off, d0, rc, cols, acc);
+    for (; d0 < nd; ++d0) {  // ragged tail of the diagonal list
+      const unsigned off = (unsigned)s_off[d0];
+      const T *slab = vals + (i64)d0 * a.pitch;
+      T v[RPT], xv[RPT];
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        v[i] = ld_stream(slab + rc[i]);
+        xv[i] = ld_ro(a.x + min(rc[i] + off, cols - 1));
+      }
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const T t = acc[i] + v[i] * xv[i];
+        acc[i] = (rc[i] + off < cols) ? t : acc[i];
+      }
+    }
+  }
+
+  T dsum = 0;
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    const unsigned r = base + i * BLOCK;
+    if (r < rows) {
+      a.y[r] = acc[i];
+      if (a.dotv) dsum = dsum + acc[i] * ld_ro(a.dotv + r);
+    }
+  }
+  if (a.dotv) {  // uniform branch
+    T bs = block_sum<BLOCK>(dsum, s_red);
+    grid_reduce_finish<BLOCK>(bs, a.dot_partials, a.dot_ticket, s_red,
+                              [&](T total) { *a.dot_result = total; });
+  }
+}
+
+// ---------------------------------------------------------------------------
+// bulk-async (TMA) staged variant
+// ---------------------------------------------------------------------------
+constexpr int DIA_KC = 8;  // diagonals per stage
+
+template <typename T, int BLOCK, int RPT>
+__global__ void __launch_bounds__(BLOCK + 32) dia_bulk_kernel(DiaArgs<T> a, int stages,
+                                                              i64 num_tiles) {
+  constexpr int R = BLOCK * RPT;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // layout: [stages][KC][R] T | full[stages] | empty[stages] | offs[ndiag]
+  T *s_vals = reinterpret_cast<T *>(smem_raw);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)stages * DIA_KC * R * sizeof(T));
+  uint64_t *empty = full + stages;
+  int *s_off = reinterpret_cast<int *>(empty + stages);
+  __shared__ T s_red[32];
+
+  const int tid = threadIdx.x;
+  for (int d = tid; d < a.ndiag; d += BLOCK + 32) s_off[d] = a.offs[d];
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], BLOCK / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const int nchunks = (a.ndiag + DIA_KC - 1) / DIA_KC;
+  const unsigned rows = (unsigned)a.rows, cols = (unsigned)a.cols;
+  T dsum = 0;
+
+  if (tid >= BLOCK) {
+    // ===== producer warp: one elected lane drives the TMA engine =====
+    if (tid == BLOCK) {
+      const uint64_t pol = l2_policy_evict_first();
+      int s = 0;
+      uint32_t ph = 0;
+      for (i64 tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const i64 r0 = a.row_begin + tile * R;
+        if (r0 + R > a.rows) continue;  // ragged last tile: consumers load it directly
+        for (int c = 0; c < nchunks; ++c) {
+          const int d0 = c * DIA_KC;
+          const int kc = min(DIA_KC, a.ndiag - d0);
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], (uint32_t)(kc * R * sizeof(T)));
+          for (int u = 0; u < kc; ++u)
+            bulk_g2s(s_vals + ((size_t)s * DIA_KC + u) * R, a.vals + (i64)(d0 + u) * a.pitch + r0,
+                     (uint32_t)(R * sizeof(T)), &full[s], pol);
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ===== consumer warps =====
+    int s = 0;
+    uint32_t ph = 0;
+    const int lane = tid & 31;
+    for (i64 tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const unsigned r0 = (unsigned)(a.row_begin + tile * R);
+      T acc[RPT];
+      if ((i64)r0 + R > a.rows) {
+        // ragged last tile (< R rows): same arithmetic, slabs straight from global
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const unsigned r = r0 + tid + i * BLOCK;
+          if (r >= rows) continue;
+          T s_acc = a.accumulate ? a.y[r] : T(0);
+          for (int d = 0; d < a.ndiag; ++d) {
+            const unsigned cidx = r + (unsigned)s_off[d];
+            if (cidx < cols)
+              s_acc = s_acc + ld_stream(a.vals + (i64)d * a.pitch + r) * ld_ro(a.x + cidx);
+          }
+          a.y[r] = s_acc;
+          if (a.dotv) dsum = dsum + s_acc * ld_ro(a.dotv + r);
+        }
+        continue;
+      }
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) acc[i] = a.accumulate ? a.y[r0 + tid + i * BLOCK] : T(0);
+      for (int c = 0; c < nchunks; ++c) {
+        const int d0 = c * DIA_KC;
+        const int kc = min(DIA_KC, a.ndiag - d0);
+        // x for this chunk is requested before waiting on the slab stage
+        T xv[DIA_KC][RPT];
+        unsigned off[DIA_KC];
+#pragma unroll
+        for (int u = 0; u < DIA_KC; ++u) {
+          off[u] = (unsigned)s_off[min(d0 + u, a.ndiag - 1)];
+#pragma unroll
+          for (int i = 0; i < RPT; ++i)
+            xv[u][i] = ld_ro(a.x + min(r0 + tid + i * BLOCK + off[u], cols - 1));
+        }
+        mbar_wait(&full[s], ph);
+        const T *sv = s_vals + (size_t)s * DIA_KC * R;
+#pragma unroll
+        for (int u = 0; u < DIA_KC; ++u)
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            pin(xv[u][i]);
+            const T t = acc[i] + sv[u * R + tid + i * BLOCK] * xv[u][i];
+            acc[i] = (u < kc && r0 + tid + i * BLOCK + off[u] < cols) ? t : acc[i];
+          }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const unsigned r = r0 + tid + i * BLOCK;
+        a.y[r] = acc[i];
+        if (a.dotv) dsum = dsum + acc[i] * ld_ro(a.dotv + r);
+      }
+    }
+  }
+  if (a.dotv) {
+    if (tid >= BLOCK) dsum = 0;
+    T bs = block_sum<BLOCK + 32>(dsum, s_red);
+    grid_reduce_finish<BLOCK + 32>(bs, a.dot_partials, a.dot_ticket, s_red,
+                                   [&](T total) { *a.dot_result = total; });
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host dispatch
+// ---------------------------------------------------------------------------
+template <typename T, int BLOCK, int RPT>
+static b200sp_status launch_ldg(b200sp_handle h, cudaStream_t st, DiaArgs<T> a, i64 nrows) {
+  const i64 grid = ceil_div(nrows, (i64)BLOCK * RPT);
+  if (grid == 0) return B200SP_OK;
+  if (a.dotv && grid > RED_MAX_PARTIALS)
+    return set_error(h, B200SP_INVALID_INPUT, "dia: too many CTAs for fused dot");
+  dia_ldg_kernel<T, BLOCK, RPT><<<(unsigned)grid, BLOCK, 0, st>>>(a);
+  B200SP_LAUNCH_CHECK(h, "dia_ldg_kernel");
+  return B200SP_OK;
+}
+
+template <typename T>
+static b200sp_status dispatch_ldg(b200sp_handle h, cudaStream_t st, const DiaArgs<T> &a, i64 nrows,
+                                  int block, int rpt) {
+#define CASE(B, R) \
+  if (block == B && rpt == R) return launch_ldg<T, B, R>(h, st, a, nrows);
+  CASE(128, 1) CASE(128, 2) CASE(128, 4) CASE(256, 1) CASE(256, 2) CASE(256, 4) CASE(512, 1)
+  CASE(512, 2) CASE(512, 4)
+#undef CASE
+  return set_error(h, B200SP_INVALID_INPUT, "dia ldg: unsupported block_size=%d unroll=%d", block, rpt);
+}
+
+template <typename T, int BLOCK, int RPT>
+static b200sp_status launch_bulk(b200sp_handle h, cudaStream_t st, DiaArgs<T> a, i64 num_tiles,
+                                 int stages, int ctas_per_sm) {
+  constexpr int R = BLOCK * RPT;
+  auto kern = dia_bulk_kernel<T, BLOCK, RPT>;
+  size_t smem = (size_t)stages * DIA_KC * R * sizeof(T) + 2 * stages * sizeof(uint64_t) +
+                (size_t)a.ndiag * sizeof(int) + 16;
+  if (smem > (size_t)h->max_smem_optin)
+    return set_error(h, B200SP_INVALID_INPUT, "dia bulk: %zu B smem exceeds %d", smem, h->max_smem_optin);
+  B200SP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  i64 grid = (i64)h->num_sms * ctas_per_sm;
+  if (grid > num_tiles) grid = num_tiles;
+  if (a.dotv && grid > RED_MAX_PARTIALS) return set_error(h, B200SP_INVALID_INPUT, "dia: grid too large");
+  kern<<<(unsigned)grid, BLOCK + 32, smem, st>>>(a, stages, num_tiles);
+  B200SP_LAUNCH_CHECK(h, "dia_bulk_kernel");
+  return B200SP_OK;
+}
+
+template <typename T>
+static b200sp_status dispatch_bulk(b200sp_handle h, cudaStream_t st, const DiaArgs<T> &a, i64 num_tiles,
+                                   int block, int rpt, int stages, int cps) {
+#define CASE(B, R) \
+  if (block == B && rpt == R) return launch_bulk<T, B, R>(h, st, a, num_tiles, stages, cps);
+  CASE(128, 2) CASE(128, 4) CASE(128, 8) CASE(256, 1) CASE(256, 2) CASE(256, 4)
+#undef CASE
+  return set_error(h, B200SP_INVALID_INPUT, "dia bulk: unsupported block_size=%d unroll=%d", block, rpt);
+}
+
+// Engine defaults (overridden by cfg / tuning cache).  Chosen on B200 from the
+// round-1 sweep in profiles/.
+static void dia_defaults(b200sp_cfg &c, size_t elem) {
+  if (c.kernel == 0) c.kernel = B200SP_K_DIA_LDG;
+  if (c.block_size == 0) c.block_size = 256;
+  if (c.unroll == 0) c.unroll = (elem == 4) ? 4 : 2;
+  if (c.stages == 0) c.stages = 3;
+  if (c.ctas_per_sm == 0) c.ctas_per_sm = 2;
+}
+
+template <typename T>
+b200sp_status spmv_dia(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64 ndiag, i64 pitch,
+                       const int *offs, const T *vals, const T *x, T *y, int accumulate,
+                       const b200sp_cfg *cfg, const T *dotv, T *dot_result) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, rows >= 0 && cols >= 0 && ndiag >= 0, "dia: negative dimension");
+  B200SP_REQUIRE(h, rows < (1ll << 31) && cols < (1ll << 31), "dia: int32 index range");
+  B200SP_REQUIRE(h, pitch >= rows, "dia: pitch < num_rows");
+  if (rows == 0) {
+    if (dot_result) B200SP_CUDA(h, cudaMemsetAsync(dot_result, 0, sizeof(T), st));
+    return B200SP_OK;
+  }
+  B200SP_REQUIRE(h, y != nullptr && (ndiag == 0 || (offs && vals && x)), "dia: null pointer");
+
+  b200sp_cfg c = cfg ? *cfg : b200sp_cfg{};
+  dia_defaults(c, sizeof(T));
+
+  DiaArgs<T> a;
+  a.rows = rows; a.cols = cols; a.pitch = pitch; a.ndiag = (int)ndiag;
+  a.offs = offs; a.vals = vals; a.x = x; a.y = y; a.accumulate = accumulate;
+  a.dotv = dotv; a.dot_result = dot_result;
+  a.dot_partials = reinterpret_cast<T *>(h->red_partials);
+  a.dot_ticket = h->red_counters;
+  a.row_begin = 0;
+
+  if (c.kernel == B200SP_K_DIA_BULK) {
+    const int R = c.block_size * c.unroll;
+    const bool ok = (pitch * sizeof(T)) % 16 == 0 && aligned16(vals) && ((size_t)R * sizeof(T)) % 16 == 0 &&
+                    ndiag > 0;
+    const i64 tiles = ceil_div(rows, (i64)R);
+    if (ok) return dispatch_bulk<T>(h, st, a, tiles, c.block_size, c.unroll, c.stages, c.ctas_per_sm);
+    // layout not bulk-copyable -> LDG kernel (same results)
+    c.kernel = B200SP_K_DIA_LDG;
+    if (c.unroll > 4) c.unroll = 4;
+  }
+  if (c.kernel != B200SP_K_DIA_LDG)
+    return set_error(h, B200SP_INVALID_INPUT, "dia: unknown kernel id %d", c.kernel);
+  return dispatch_ldg<T>(h, st, a, rows, c.block_size, c.unroll);
+}
+
+template b200sp_status spmv_dia<float>(b200sp_handle, cudaStream_t, i64, i64, i64, i64, const int *,
+                                       const float *, const float *, float *, int, const b200sp_cfg *,
+                                       const float *, float *);
+template b200sp_status spmv_dia<double>(b200sp_handle, cudaStream_t, i64, i64, i64, i64, const int *,
+                                        const double *, const double *, double *, int,
+                                        const b200sp_cfg *, const double *, double *);
+
+}  // namespace b200sp
+
+extern "C" {
+b200sp_status b200sp_spmv_dia_f32(b200sp_handle h, b200sp_stream stream, int64_t num_rows,
+                                  int64_t num_cols, int64_t num_diagonals, int64_t pitch,
+                                  const int32_t *diagonal_offsets, const float *values, const float *x,
+                                  float *y, int accumulate, const b200sp_cfg *cfg) {
+  return b200sp::spmv_dia<float>(h, (cudaStream_t)stream, num_rows, num_cols, num_diagonals, pitch,
+                                 diagonal_offsets, values, x, y, accumulate, cfg, nullptr, nullptr);
+}
+b200sp_status b200sp_spmv_dia_f64(b200sp_handle h, b200sp_stream stream, int64_t num_rows,
+                                  int64_t num_cols, int64_t num_diagonals, int64_t pitch,
+                                  const int32_t *diagonal_offsets, const double *values, const double *x,
+                                  double *y, int accumulate, const b200sp_cfg *cfg) {
+  return b200sp::spmv_dia<double>(h, (cudaStream_t)stream, num_rows, num_cols, num_diagonals, pitch,
+                                  diagonal_offsets, values, x, y, accumulate, cfg, nullptr, nullptr);
+}
+}

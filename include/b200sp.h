@@ -1,0 +1,407 @@
+/*
+ * b200sp.h — C ABI of the B200-native sparse matrix-vector engine (libb200sp.so).
+ *
+ * This is the drop-in boundary for the SpMV / BLAS-1 / CG hot path of
+ * bigno78/cusp-autotuned.  The reference has no C ABI: its boundary is a C++
+ * overload set found by ADL on the execution policy.  Every entry point below
+ * names the reference overload / function it replaces (paths relative to the
+ * reference root).  The templated `cusp::` compatibility headers under
+ * include/cusp/ unpack containers into the raw pointers + sizes taken here.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name says `_host`;
+ *   - indices are int32 (the reference's tests and benchmarks only use
+ *     IndexType=int); slab arithmetic (pitch*K) is done in 64 bit inside;
+ *   - ELL / DIA slabs are column-major with an explicit pitch, exactly the
+ *     cusp::array2d<column_major> layout (cusp/detail/ell_matrix.inl:35-36,
+ *     cusp/detail/dia_matrix.inl:34): entry (row, k) at values[k*pitch + row];
+ *   - `accumulate` selects the `initialize` functor of the reference's 7-arg
+ *     multiply: 0 -> constant_functor(0)  (y  = A x,  generic/multiply.inl:158-162)
+ *               1 -> identity             (y += A x,  testing/multiply.cu:514-645);
+ *     `combine` is always multiplies, `reduce` always plus;
+ *   - every call is asynchronous on `stream` unless it returns a scalar to the
+ *     host, in which case it synchronises that stream only;
+ *   - scratch memory is owned by the handle (the reference allocates per call,
+ *     cuda/detail/multiply/coo_flat_spmv.h:445-446);
+ *   - a handle is bound to the device current at creation and is not
+ *     thread-safe: use one handle per host thread.
+ *   - status != B200SP_OK  <=>  nothing usable was written; the message is
+ *     available from b200sp_last_error_string().  The C++ shim maps
+ *     B200SP_INVALID_INPUT -> cusp::invalid_input_exception and everything else
+ *     -> cusp::runtime_exception (cusp/exception.h:31-84).
+ *   - There is NO CPU fallback anywhere behind this ABI.
+ */
+#ifndef B200SP_H
+#define B200SP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SP_VERSION 100 /* 0.1.0 */
+
+typedef struct b200sp_context *b200sp_handle;
+typedef void *b200sp_stream; /* cudaStream_t */
+
+typedef enum {
+  B200SP_OK = 0,
+  B200SP_INVALID_INPUT = 1, /* bad sizes / null pointers / unsupported cfg */
+  B200SP_CUDA_ERROR = 2,    /* a CUDA runtime call or launch failed */
+  B200SP_NOT_IMPLEMENTED = 3,
+  B200SP_ALLOC_FAILED = 4,
+  B200SP_COMM_ERROR = 5 /* NCCL / peer-access failure */
+} b200sp_status;
+
+/* ---------------------------------------------------------------------------
+ * Tuning configuration — replaces the KTT parameter spaces of
+ * cusp/system/cuda/ktt/{csr,ell,dia,coo}_multiply.h.
+ * A zero field means "engine default".  b200sp_cfg_space_* enumerates the
+ * valid points per format.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  int kernel;          /* variant id, see B200SP_K_*                           */
+  int block_size;      /* threads per CTA: 128, 256, 512                        */
+  int threads_per_row; /* CSR row-split width 1,2,4,8,16,32 (1 = scalar)        */
+  int unroll;          /* independent rows (CSR/ELL/DIA) or nnz (COO) per thread */
+  int vector_width;    /* elements per global load (1,2,4); slab kernels: unused */
+  int tile_rows;       /* rows per staged slab tile (bulk-async kernels)         */
+  int stages;          /* smem pipeline depth (bulk-async kernels)               */
+  int ctas_per_sm;     /* persistent-grid multiplier (bulk-async kernels)        */
+} b200sp_cfg;
+
+enum {
+  B200SP_K_AUTO = 0,
+  /* CSR  (replaces spmv_csr_vector_kernel / spmv_csr_scalar_kernel,
+   *       cuda/detail/multiply/csr_vector_spmv.h:66-161, csr_scalar.h:48-73,
+   *       and KTT csr_kernel_{naive,warp,block,balanced}, ktt/kernels/csr_kernel.h) */
+  B200SP_K_CSR_VECTOR = 1, /* sub-warp per row, shuffle reduction              */
+  B200SP_K_CSR_STREAM = 2, /* CTA streams a row block's nnz through smem        */
+  /* ELL  (replaces spmv_ell_kernel ell_spmv.h:47-93, ktt_ell_kernel)          */
+  B200SP_K_ELL_LDG = 1,  /* thread per row, coalesced loads, deep unroll      */
+  B200SP_K_ELL_BULK = 2, /* slabs staged by cp.async.bulk + mbarrier pipeline  */
+  /* DIA  (replaces spmv_dia_kernel dia_spmv.h:66-126, ktt_dia_vector_kernel)  */
+  B200SP_K_DIA_LDG = 1,
+  B200SP_K_DIA_BULK = 2,
+  /* COO  (replaces thrust reduce_by_key generic/multiply/spmv.h:182-238,
+   *       spmv_coo_flat_kernel coo_flat_spmv.h:225-463, KTT coo_spmv)         */
+  B200SP_K_COO_SEGSCAN = 1 /* nnz-balanced tiles, smem segmented scan, no atomics */
+};
+
+/* ---- lifecycle ---------------------------------------------------------- */
+int b200sp_version(void);
+b200sp_status b200sp_create(b200sp_handle *out);
+b200sp_status b200sp_destroy(b200sp_handle h);
+/* last error text of this handle (never NULL). h may be NULL -> global text. */
+const char *b200sp_last_error_string(b200sp_handle h);
+const char *b200sp_status_string(b200sp_status s);
+/* number of kernels this handle has launched since creation (bench bookkeeping) */
+uint64_t b200sp_launch_count(b200sp_handle h);
+/* pin `bytes` at `ptr` (typically x) in L2 with an access-policy window on
+ * `stream` ("x through the read-only / L2-persisting path"); bytes==0 clears. */
+b200sp_status b200sp_set_l2_persist(b200sp_handle h, b200sp_stream stream,
+                                    const void *ptr, size_t bytes);
+
+/* ---- SpMV ---------------------------------------------------------------
+ * y = A x  (accumulate==0)   or   y += A x  (accumulate==1)
+ * cfg may be NULL (engine default / cached tuned configuration).
+ *
+ * csr: cusp::system::cuda::detail::multiply(exec, A, x, y, init, combine, reduce,
+ *      csr_format, array1d_format, array1d_format)   csr_vector_spmv.h:218-258
+ * ell: ... ell_format ...                             ell_spmv.h:96-155
+ * dia: ... dia_format ...                             dia_spmv.h:129-188
+ * coo: ... coo_format ...                             coo_flat_spmv.h:486-502 /
+ *                                                     generic/multiply/spmv.h:182-238
+ * hyb: generic/multiply/spmv.h:272-290 (ELL pass, then COO pass with identity)
+ */
+#define B200SP_DECL_SPMV(T, sfx)                                                   \
+  b200sp_status b200sp_spmv_csr_##sfx(                                             \
+      b200sp_handle h, b200sp_stream stream, int64_t num_rows, int64_t num_cols,   \
+      int64_t num_entries, const int32_t *row_offsets,                             \
+      const int32_t *column_indices, const T *values, const T *x, T *y,            \
+      int accumulate, const b200sp_cfg *cfg);                                      \
+  b200sp_status b200sp_spmv_ell_##sfx(                                             \
+      b200sp_handle h, b200sp_stream stream, int64_t num_rows, int64_t num_cols,   \
+      int64_t num_cols_per_row, int64_t pitch, const int32_t *column_indices,      \
+      const T *values, const T *x, T *y, int accumulate, const b200sp_cfg *cfg);   \
+  b200sp_status b200sp_spmv_dia_##sfx(                                             \
+      b200sp_handle h, b200sp_stream stream, int64_t num_rows, int64_t num_cols,   \
+      int64_t num_diagonals, int64_t pitch, const int32_t *diagonal_offsets,       \
+      const T *values, const T *x, T *y, int accumulate, const b200sp_cfg *cfg);   \
+  b200sp_status b200sp_spmv_coo_##sfx(                                             \
+      b200sp_handle h, b200sp_stream stream, int64_t num_rows, int64_t num_cols,   \
+      int64_t num_entries, const int32_t *row_indices,                             \
+      const int32_t *column_indices, const T *values, const T *x, T *y,            \
+      int accumulate, const b200sp_cfg *cfg);                                      \
+  b200sp_status b200sp_spmv_hyb_##sfx(                                             \
+      b200sp_handle h, b200sp_stream stream, int64_t num_rows, int64_t num_cols,   \
+      int64_t ell_cols_per_row, int64_t ell_pitch,                                 \
+      const int32_t *ell_column_indices, const T *ell_values,                      \
+      int64_t coo_num_entries, const int32_t *coo_row_indices,                     \
+      const int32_t *coo_column_indices, const T *coo_values, const T *x, T *y,    \
+      int accumulate, const b200sp_cfg *ell_cfg, const b200sp_cfg *coo_cfg);       \
+  /* ELL-R (cusp::ktt::ellr_matrix, cusp/ktt/ellr_matrix.h:18): ELL plus         \
+   * row_lengths[num_rows]; the kernel stops at row_lengths[row]. */              \
+  b200sp_status b200sp_spmv_ellr_##sfx(                                            \
+      b200sp_handle h, b200sp_stream stream, int64_t num_rows, int64_t num_cols,   \
+      int64_t num_cols_per_row, int64_t pitch, const int32_t *column_indices,      \
+      const T *values, const int32_t *row_lengths, const T *x, T *y,               \
+      int accumulate, const b200sp_cfg *cfg);
+
+B200SP_DECL_SPMV(float, f32)
+B200SP_DECL_SPMV(double, f64)
+#undef B200SP_DECL_SPMV
+
+/* row_lengths for ELL-R: count of leading non-negative column slots per row
+ * (cusp/ktt/detail/ellr_matrix.inl:16-52). */
+b200sp_status b200sp_ell_row_lengths(b200sp_handle h, b200sp_stream stream,
+                                     int64_t num_rows, int64_t num_cols_per_row,
+                                     int64_t pitch, const int32_t *column_indices,
+                                     int32_t *row_lengths);
+
+/* ---- BLAS-1 (cusp::blas::*, cusp/detail/blas.inl:84-461,
+ *      cusp/system/detail/generic/blas.h:180-340) ---------------------------
+ * Reductions are deterministic (fixed two-level order).  `result_dev` may be
+ * NULL; `result_host` may be NULL.  If result_host != NULL the call
+ * synchronises `stream` (the reference's reductions always block).
+ */
+#define B200SP_DECL_BLAS(T, sfx)                                                   \
+  /* y <- alpha*x + y            generic/blas.h:180-198 */                         \
+  b200sp_status b200sp_axpy_##sfx(b200sp_handle h, b200sp_stream s, int64_t n,     \
+                                  T alpha, const T *x, T *y);                      \
+  /* z <- alpha*x + beta*y       generic/blas.h:200-220 */                         \
+  b200sp_status b200sp_axpby_##sfx(b200sp_handle h, b200sp_stream s, int64_t n,    \
+                                   T alpha, const T *x, T beta, const T *y, T *z); \
+  /* y <- x                      generic/blas.h copy */                            \
+  b200sp_status b200sp_copy_##sfx(b200sp_handle h, b200sp_stream s, int64_t n,     \
+                                  const T *x, T *y);                               \
+  b200sp_status b200sp_fill_##sfx(b200sp_handle h, b200sp_stream s, int64_t n,     \
+                                  T alpha, T *x);                                  \
+  b200sp_status b200sp_scal_##sfx(b200sp_handle h, b200sp_stream s, int64_t n,     \
+                                  T alpha, T *x);                                  \
+  /* sum x_i*y_i                 generic/blas.h:284-313 (dot == dotc for reals) */ \
+  b200sp_status b200sp_dot_##sfx(b200sp_handle h, b200sp_stream s, int64_t n,      \
+                                 const T *x, const T *y, T *result_dev,            \
+                                 T *result_host);                                  \
+  /* sqrt(sum |x_i|^2), unscaled generic/blas.h:328-340 */                         \
+  b200sp_status b200sp_nrm2_##sfx(b200sp_handle h, b200sp_stream s, int64_t n,     \
+                                  const T *x, T *result_dev, T *result_host);
+
+B200SP_DECL_BLAS(float, f32)
+B200SP_DECL_BLAS(double, f64)
+#undef B200SP_DECL_BLAS
+
+/* ---- sparse matrix descriptor (for CG / tuning / host-buffer calls) ------ */
+typedef enum {
+  B200SP_FMT_CSR = 0,
+  B200SP_FMT_ELL = 1,
+  B200SP_FMT_DIA = 2,
+  B200SP_FMT_COO = 3,
+  B200SP_FMT_HYB = 4,
+  B200SP_FMT_ELLR = 5
+} b200sp_format;
+
+typedef enum { B200SP_F32 = 0, B200SP_F64 = 1 } b200sp_dtype;
+
+/* Non-owning view of a device-resident matrix.  Unused fields are 0/NULL.
+ *   CSR : row_offsets[num_rows+1], column_indices[nnz], values[nnz]
+ *   ELL : column_indices[pitch*K], values[pitch*K], K = num_cols_per_row
+ *   ELLR: ELL + row_offsets := row_lengths[num_rows]
+ *   DIA : diagonal_offsets[K], values[pitch*K],     K = num_cols_per_row (#diagonals)
+ *   COO : row_indices[nnz], column_indices[nnz], values[nnz] (sorted by row)
+ *   HYB : ELL fields + coo_* fields                                          */
+typedef struct {
+  b200sp_format format;
+  b200sp_dtype dtype;
+  int64_t num_rows, num_cols, num_entries;
+  int64_t num_cols_per_row, pitch;
+  const int32_t *row_offsets;
+  const int32_t *row_indices;
+  const int32_t *column_indices;
+  const int32_t *diagonal_offsets;
+  const void *values;
+  int64_t coo_num_entries;
+  const int32_t *coo_row_indices;
+  const int32_t *coo_column_indices;
+  const void *coo_values;
+} b200sp_matrix;
+
+/* generic dispatch on the descriptor (same kernels as the typed calls) */
+b200sp_status b200sp_spmv(b200sp_handle h, b200sp_stream stream,
+                          const b200sp_matrix *A, const void *x, void *y,
+                          int accumulate, const b200sp_cfg *cfg);
+
+/* Same product through HOST buffers: x_host -> device, SpMV, y -> y_host.
+ * The matrix stays device-resident like a cusp::*_matrix<.., device_memory>;
+ * this is what `cusp::array1d<T,host_memory> y_h = y_d` after cusp::multiply
+ * costs end to end.  Synchronises `stream`. */
+b200sp_status b200sp_spmv_host(b200sp_handle h, b200sp_stream stream,
+                               const b200sp_matrix *A, const void *x_host,
+                               void *y_host, int accumulate, const b200sp_cfg *cfg);
+
+/* ---- conjugate gradients -------------------------------------------------
+ * cusp::krylov::cg(A, x, b, monitor) with the identity preconditioner
+ * (cusp/krylov/detail/cg.inl:35-107) and cusp::monitor semantics
+ * (cusp/detail/monitor.inl:107-111,178-208): stop when
+ *   ||r||_2 <= absolute_tolerance + relative_tolerance*||b||_2
+ * or iteration_count >= iteration_limit; the residual norm is recorded before
+ * every iteration and once more at exit, exactly like monitor.residuals.
+ * Same iterate sequence as the reference (same operation order per entry);
+ * fused into 3 kernels / iteration with device-resident scalars.
+ */
+typedef struct {
+  int64_t iteration_limit;   /* monitor default 500  */
+  double relative_tolerance; /* monitor default 1e-5 */
+  double absolute_tolerance; /* monitor default 0    */
+  int check_interval;        /* iterations between host convergence polls; 0 -> 16 */
+} b200sp_cg_params;
+
+typedef struct {
+  int64_t iteration_count;
+  int converged; /* residual_norm <= tolerance */
+  double residual_norm;
+  double b_norm;
+  int64_t num_residuals; /* entries written to residuals_host */
+} b200sp_cg_result;
+
+/* x (in: initial guess, out: solution) and b are device vectors of A.dtype.
+ * residuals_host: optional host array with room for iteration_limit+1 doubles. */
+b200sp_status b200sp_cg(b200sp_handle h, b200sp_stream stream,
+                        const b200sp_matrix *A, void *x, const void *b,
+                        const b200sp_cg_params *params, const b200sp_cfg *spmv_cfg,
+                        b200sp_cg_result *result, double *residuals_host);
+
+/* ---- multi-GPU: row-block partitioned operator ---------------------------
+ * One process per GPU.  Each rank owns a contiguous block of rows of A and the
+ * matching slices of x, b.  Column j of the global matrix is owned by the rank
+ * whose row block contains j (square operator).  A rank's local matrix has
+ * num_rows = local rows and addresses x through a window
+ *        [halo_lo | local | halo_hi]
+ * i.e. local column index c (0-based in the window) = global j - (row_begin - halo_lo).
+ * For DIA the diagonal offsets are unchanged and the kernel is simply given
+ * x_window + halo_lo.  Halo planes are exchanged with the two neighbouring
+ * ranks before every SpMV (NCCL send/recv on `stream`), dot products are
+ * all-reduced with NCCL.  The communicator is created from a 128-byte NCCL
+ * unique id that the host distributes (torch.distributed / MPI / files).
+ */
+#define B200SP_NCCL_UNIQUE_ID_BYTES 128
+b200sp_status b200sp_comm_unique_id(void *id128);
+b200sp_status b200sp_comm_init(b200sp_handle h, const void *id128, int world_size,
+                               int rank);
+b200sp_status b200sp_comm_destroy(b200sp_handle h);
+
+typedef struct {
+  int64_t halo_lo; /* elements received from rank-1 (0 on rank 0)            */
+  int64_t halo_hi; /* elements received from rank+1 (0 on the last rank)     */
+} b200sp_halo;
+
+/* Partitioned CG: A is the LOCAL block (num_rows = local rows, num_cols =
+ * halo_lo + local + halo_hi window width), x/b are local slices. */
+b200sp_status b200sp_cg_dist(b200sp_handle h, b200sp_stream stream,
+                             const b200sp_matrix *A_local, const b200sp_halo *halo,
+                             void *x_local, const void *b_local,
+                             const b200sp_cg_params *params,
+                             const b200sp_cfg *spmv_cfg, b200sp_cg_result *result,
+                             double *residuals_host);
+/* Partitioned SpMV (halo exchange + local product); x_window has room for
+ * halo_lo + local + halo_hi elements with the local slice already in place. */
+b200sp_status b200sp_spmv_dist(b200sp_handle h, b200sp_stream stream,
+                               const b200sp_matrix *A_local, const b200sp_halo *halo,
+                               void *x_window, void *y_local,
+                               const b200sp_cfg *cfg);
+
+/* ---- autotuning (cusp::ktt::{multiply,tune,reset_tuning},
+ *      cusp/ktt/detail/ktt.inl:83-142, cuda/ktt/multiply.h:56-153) ----------- */
+typedef enum {
+  B200SP_TUNE_OK = 0,
+  B200SP_TUNE_LAUNCH_FAILED = 1,     /* ~ ktt::ResultStatus::ComputationFailed   */
+  B200SP_TUNE_VALIDATION_FAILED = 2, /* ~ ktt::ResultStatus::ValidationFailed    */
+  B200SP_TUNE_UNSUPPORTED = 3        /* ~ ktt::ResultStatus::DeviceLimitsExceeded */
+} b200sp_tune_status;
+
+typedef struct {
+  b200sp_cfg cfg;
+  b200sp_tune_status status;
+  float milliseconds; /* mean over `repeats` launches */
+  double max_rel_error; /* vs the reference output */
+} b200sp_tune_result;
+
+/* enumerate the valid configurations for (format,dtype); returns the count and
+ * fills up to `capacity` entries of `out` (out may be NULL to query). */
+int64_t b200sp_cfg_space(b200sp_format format, b200sp_dtype dtype, b200sp_cfg *out,
+                         int64_t capacity);
+
+/* Exhaustive offline tuning (cusp::ktt::tune): runs every configuration
+ * `repeats` times, validates y against `y_reference` (device, may be NULL ->
+ * the engine-default configuration's output is the reference) with
+ * |y - y_ref| <= tol*|y_ref| + tol, records results, stores the winner in the
+ * handle's tuning cache (key: format, dtype, log2 rows bucket, nnz/row bucket)
+ * and returns it in *best.  y is restored semantics-wise: on return it holds
+ * A x computed by the best configuration. */
+b200sp_status b200sp_tune(b200sp_handle h, b200sp_stream stream,
+                          const b200sp_matrix *A, const void *x, void *y,
+                          const void *y_reference, double tol, int repeats,
+                          b200sp_tune_result *results, int64_t capacity,
+                          int64_t *num_results, b200sp_cfg *best);
+/* One step of dynamic tuning (cusp::ktt::multiply(A,x,y) / what plain
+ * cusp::multiply does for ELL & DIA when ktt is enabled, cuda/ktt/multiply.h:56-77):
+ * runs the next untried configuration (timed), or the best one when the space
+ * is exhausted.  result may be NULL. */
+b200sp_status b200sp_tune_step(b200sp_handle h, b200sp_stream stream,
+                               const b200sp_matrix *A, const void *x, void *y,
+                               b200sp_tune_result *result);
+/* cusp::ktt::reset_tuning: forget cached winners / dynamic-tuning progress for
+ * the class of A (A == NULL: everything). */
+b200sp_status b200sp_tune_reset(b200sp_handle h, const b200sp_matrix *A);
+/* look up the cached winner for A's class; returns 1 and fills *cfg if present */
+int b200sp_tune_lookup(b200sp_handle h, const b200sp_matrix *A, b200sp_cfg *cfg);
+/* persist / restore the tuning cache (SURVEY §5 "checkpoint": the fork never
+ * saves KTT results) as a small text file */
+b200sp_status b200sp_tune_save(b200sp_handle h, const char *path);
+b200sp_status b200sp_tune_load(b200sp_handle h, const char *path);
+
+/* ---- device-side input builders (cusp::gallery::poisson5pt/7pt via
+ *      generate_matrix_from_stencil, gallery/detail/stencil.inl:143-206, then
+ *      cusp::convert; produce bit-identical arrays to that pipeline without
+ *      the O(rows) launches of conversions/dia_to_other.h:227-251) -----------
+ * grid = (nx, ny, nz) with nz == 1 for the 2-D 5-point stencil; row index
+ * = ix + nx*(iy + ny*iz).  Rows [row_begin, row_begin+num_rows) of the global
+ * operator are produced (row-block partition); column indices are global minus
+ * `col_shift`.  `stencil` = 5 or 7.
+ */
+#define B200SP_DECL_GALLERY(T, sfx)                                                \
+  /* DIA: values[K*pitch] (K = stencil), offsets[K] ascending; the stored        \
+   * offset is global_offset + row_begin - col_shift (window coordinates) */       \
+  b200sp_status b200sp_poisson_dia_##sfx(                                          \
+      b200sp_handle h, b200sp_stream s, int stencil, int64_t nx, int64_t ny,       \
+      int64_t nz, int64_t row_begin, int64_t num_rows, int64_t col_shift,          \
+      int64_t pitch, int32_t *diagonal_offsets, T *values);                                       \
+  /* ELL: left-packed, K = stencil columns, pad col=-1 val=0 */                    \
+  b200sp_status b200sp_poisson_ell_##sfx(                                          \
+      b200sp_handle h, b200sp_stream s, int stencil, int64_t nx, int64_t ny,       \
+      int64_t nz, int64_t row_begin, int64_t num_rows, int64_t col_shift,          \
+      int64_t pitch, int32_t *column_indices, T *values);                          \
+  /* CSR: row_offsets must be computed first with b200sp_poisson_csr_offsets */    \
+  b200sp_status b200sp_poisson_csr_##sfx(                                          \
+      b200sp_handle h, b200sp_stream s, int stencil, int64_t nx, int64_t ny,       \
+      int64_t nz, int64_t row_begin, int64_t num_rows, int64_t col_shift,          \
+      const int32_t *row_offsets, int32_t *column_indices, T *values);
+
+B200SP_DECL_GALLERY(float, f32)
+B200SP_DECL_GALLERY(double, f64)
+#undef B200SP_DECL_GALLERY
+
+/* number of stored entries of the rows [row_begin,row_begin+num_rows) */
+int64_t b200sp_poisson_num_entries(int stencil, int64_t nx, int64_t ny, int64_t nz,
+                                   int64_t row_begin, int64_t num_rows);
+b200sp_status b200sp_poisson_csr_offsets(b200sp_handle h, b200sp_stream s, int stencil,
+                                         int64_t nx, int64_t ny, int64_t nz,
+                                         int64_t row_begin, int64_t num_rows,
+                                         int32_t *row_offsets);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SP_H */
