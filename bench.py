@@ -1,0 +1,452 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the SpMV / CG hot path (BASELINE.json).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--quick]
+
+Metric (BASELINE.json): SpMV GFLOP/s (2*nnz/time, performance/spmv/benchmark.h:171)
+and fraction of the HBM roofline per format; CG iterations/s.
+
+Headline workload (config.workload): BASELINE configs[1], cusp::gallery::poisson7pt
+256^3 (16 777 216 rows, 117 047 296 nnz), DIA fp64, y = A x through
+b200sp_spmv (the call cusp::multiply makes).  One step = one SpMV over the whole
+operator.  N > 1: the operator is row-block partitioned, one 256^3 block per GPU
+stacked along z (weak scaling); a step = halo exchange of x (NCCL send/recv issued
+by libb200sp) + the local product.
+
+Extra objects on the same JSON line: `formats` (ELL/DIA fp32+fp64, CSR, COO/HYB
+R-MAT: GFLOP/s, GB/s, roofline fraction each), `cg` (cusp::krylov::cg on
+poisson7pt 512^3 fp64, iterations/s, row-partitioned at N > 1), `roofline`,
+`cpu_baseline`, `e2e`, `clocks`.
+
+--impl reference: the reference's own host loop (oracle/_ref, built from
+/root/reference's cusp/system/detail/sequential/multiply/dia_spmv.h) on the host
+cores of this box, same workload / metric / unit.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GRID = (256, 256, 256)        # BASELINE configs[1]
+CG_GRID = (512, 512, 512)     # BASELINE configs[4]
+HEAD_FMT, HEAD_DT = "dia", "f64"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 0) or 0)
+    return 6650.0, "fallback (B200_PROFILING.md)", 0.0
+
+
+# ---------------------------------------------------------------------------
+# compulsory (algorithmic) bytes per SpMV: matrix arrays once + x once + y once
+# 
+# ---------------------------------------------------------------------------
+def compulsory_bytes(A, es):
+    from cusp_autotuned_b200 import capi
+    r, c = A.num_rows, A.num_cols
+    f = A.format
+    if f == capi.FMT_DIA:
+        return A.num_diagonals * A.pitch * es + A.num_diagonals * 4 + c * es + r * es
+    if f in (capi.FMT_ELL, capi.FMT_ELLR):
+        return A.num_cols_per_row * A.pitch * (4 + es) + c * es + r * es
+    if f == capi.FMT_CSR:
+        return (r + 1) * 4 + A.num_entries * (4 + es) + c * es + r * es
+    if f == capi.FMT_COO:
+        return A.num_entries * (8 + es) + c * es + r * es
+    if f == capi.FMT_HYB:
+        e, co = A.ell, A.coo
+        return e.num_cols_per_row * e.pitch * (4 + es) + co.num_entries * (8 + es) + c * es + r * es
+    raise ValueError(f)
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock and throttle reasons through NVML while the benchmark runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = 0
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                if util > 20:
+                    self.samples.append(mhz)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz or None,
+                "reasons": sorted(self.reasons), "samples_under_load": len(s)}
+
+
+# ---------------------------------------------------------------------------
+# reference arm: the reference's host loop on this box's cores
+# ---------------------------------------------------------------------------
+def run_reference(args):
+    import numpy as np
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle as O
+    kind = "reference" if O.ref_available() else "port"
+    threads = O.num_threads()
+    A = O.poisson(7, GRID, np.float64, "dia")
+    rows, nnz = A["num_rows"], A["num_entries"]
+    x = ((np.arange(A["num_cols"]) % 21) - 10).astype(np.float64)
+    impl = "ref" if kind == "reference" else "oracle_mt"
+
+    def one(Av):
+        t0 = time.perf_counter()
+        O.spmv(Av, x, impl=impl, nthreads=threads)
+        return time.perf_counter() - t0
+
+    t_full = min(one(A), one(A))
+    # bounded sample: a leading block of rows sized so that the whole run stays ~<= 90 s
+    budget = 90.0
+    frac = min(1.0, budget / max(1e-9, t_full * (args.steps + args.warmup)))
+    srows = rows if frac >= 1.0 else max(1 << 16, int(rows * frac) // 65536 * 65536)
+    S = A if srows == rows else dict(A, num_rows=srows)
+    snnz = nnz if srows == rows else int(np.count_nonzero(A["values"].reshape(7, A["pitch"])[:, :srows]))
+    for _ in range(args.warmup):
+        one(S)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.spmv(S, x, impl=impl, nthreads=threads)
+    dt = time.perf_counter() - t0
+    ms = dt / args.steps * 1e3
+    val = 2.0 * snnz / (ms * 1e-3) / 1e9
+    sample = f"rows [0,{srows}) of poisson7pt 256^3 DIA fp64 ({snnz} nnz), {args.steps} steps"
+    line = {
+        "impl": "reference", "metric": "spmv_gflops", "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cusp::gallery::poisson7pt 256^3 DIA fp64 SpMV (BASELINE configs[1])",
+                   "format": "dia", "rows": rows, "nnz": nnz, "sample_rows": srows,
+                   "path": "cusp/system/detail/sequential/multiply/dia_spmv.h over row blocks, std::thread"},
+        "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------
+def time_launches(fn, steps, warmup, sync):
+    import torch
+    for _ in range(warmup):
+        fn()
+    sync()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1) / steps  # ms per step
+
+
+def bench_format(h, A, tdt, steps, warmup, peak, cfg=None, label=None):
+    import torch
+    es = 4 if tdt == torch.float32 else 8
+    dev = torch.device("cuda", torch.cuda.current_device())
+    x = ((torch.arange(A.num_cols, device=dev) % 21) - 10).to(tdt)
+    y = torch.empty(A.num_rows, dtype=tdt, device=dev)
+    d = A.descriptor()
+    ms = time_launches(lambda: h.spmv(d, x, y, cfg=cfg), steps, warmup, torch.cuda.synchronize)
+    B = compulsory_bytes(A, es)
+    nnz = A.num_entries
+    return {"label": label, "rows": A.num_rows, "nnz": nnz, "ms": ms, "gflops": 2.0 * nnz / ms / 1e6,
+            "bytes": B, "gbs": B / ms / 1e6, "frac": B / ms / 1e6 / peak, "frac_of_8TBs": B / ms / 1e6 / 8000.0}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--quick", action="store_true", help="headline metric only (no per-format / CG / CPU legs)")
+    ap.add_argument("--cg-iters", type=int, default=50)
+    ap.add_argument("--rmat-scale", type=int, default=24)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as td
+
+    import cusp_autotuned_b200 as cusp
+    from cusp_autotuned_b200 import capi, convert, dist, gallery
+    from cusp_autotuned_b200.partition import plane_partition
+
+    rank, world, local = dist.init_process_group_from_env()
+    assert torch.cuda.is_available(), "bench.py needs a GPU: the engine has no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    h = cusp.default_handle()
+    dist.init_engine_comm(h, rank, world)
+    peak, peak_src, _ = peaks()
+    tdt, es = torch.float64, 8
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    # ---- headline: DIA fp64, poisson7pt 256^3 per GPU -------------------------------------
+    nx, ny, nz = GRID
+    gdims = (nx, ny, nz * world)
+    blk = plane_partition(gdims, world, rank)
+    A = gallery.poisson("dia", 7, gdims, dtype=tdt, row_begin=blk.row_begin, num_rows=blk.num_rows,
+                        halo_lo=blk.halo_lo, halo_hi=blk.halo_hi)
+    halo = capi.Halo(blk.halo_lo, blk.halo_hi)
+    xw = ((torch.arange(blk.window, device=dev) + blk.col_shift) % 21 - 10).to(tdt)
+    y = torch.empty(blk.num_rows, dtype=tdt, device=dev)
+    d = A.descriptor()
+    nnz_local = A.num_entries
+    if world > 1:
+        step = lambda: h.spmv_dist(d, halo, xw, y)
+    else:
+        step = lambda: h.spmv(d, xw, y)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    l0 = h.launch_count
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = h.launch_count - l0
+    ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    nnz_total = nnz_local
+    if world > 1:
+        t = torch.tensor([nnz_local], dtype=torch.int64, device=dev)
+        td.all_reduce(t)
+        nnz_total = int(t.item())
+    value = 2.0 * nnz_total / ms / 1e6  # GFLOP/s, whole job
+    B = compulsory_bytes(A, es)
+    roof = {"bound": "hbm", "achieved": B / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": B / ms / 1e6 / peak,
+            "traffic": None, "peak_source": peak_src, "kernel": "dia_bulk_kernel<double,128,2>",
+            "algorithmic_bytes_per_launch": B, "frac_of_nominal_8TBs": B / ms / 1e6 / 8000.0,
+            "note": "per-GPU kernel; achieved = compulsory bytes / mean launch time over the timed region"}
+    tr = os.path.join(ROOT, "profiles", "r01_dia_f64_traffic.json")
+    if os.path.exists(tr):
+        try:
+            roof["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- e2e: host buffers through b200sp_spmv_host (x up, y down every step) ------------------
+    xh = torch.empty(blk.window, dtype=tdt).pin_memory()
+    xh.copy_(xw.cpu())
+    yh = torch.empty(blk.num_rows, dtype=tdt).pin_memory()
+    e2e_steps = max(3, min(args.steps, 20))
+    if world == 1:
+        estep = lambda: h.spmv_host(d, xh, yh)
+    else:
+        def estep():
+            xw.copy_(xh, non_blocking=True)
+            h.spmv_dist(d, halo, xw, y)
+            yh.copy_(y, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+    for _ in range(3):
+        estep()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        estep()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) / e2e_steps * 1e3)
+    e2e = {"value": 2.0 * nnz_total / e2e_ms / 1e6, "unit": "GFLOP/s", "h2d_bytes_per_step": blk.window * es,
+           "d2h_bytes_per_step": blk.num_rows * es, "ms_per_step": e2e_ms, "steps": e2e_steps,
+           "note": "matrix device-resident (cusp::dia_matrix<..,device_memory>), x from / y to pinned host memory"}
+    y_check = float(y.double().abs().sum().item())
+
+    formats, cg, cpu = {}, None, None
+    if not args.quick:
+        del xh, yh
+        # ---- per-format SpMV at the BASELINE configs (rank 0 of a single-GPU run) -----------------
+        if world == 1:
+            fs, fw = max(20, min(args.steps, 100)), 5
+            formats["dia_f64_poisson7pt_256"] = {"label": "DIA fp64 poisson7pt 256^3 (headline)", "rows": A.num_rows,
+                                                 "nnz": nnz_local, "ms": ms, "gflops": value, "bytes": B,
+                                                 "gbs": roof["achieved"], "frac": roof["frac"],
+                                                 "frac_of_8TBs": roof["frac_of_nominal_8TBs"]}
+            del A, xw, y
+            torch.cuda.empty_cache()
+            for fmt in ("dia", "ell", "csr"):
+                for tt, nm in ((torch.float32, "f32"), (torch.float64, "f64")):
+                    if fmt == "dia" and nm == "f64":
+                        continue
+                    M = gallery.poisson(fmt, 7, GRID, dtype=tt)
+                    formats[f"{fmt}_{nm}_poisson7pt_256"] = bench_format(
+                        h, M, tt, fs, fw, peak, label=f"{fmt.upper()} {nm} poisson7pt 256^3")
+                    del M
+            M = gallery.poisson("csr", 5, (512, 512), dtype=torch.float64)
+            formats["csr_f64_poisson5pt_512"] = bench_format(h, M, torch.float64, 200, 20, peak,
+                                                             label="CSR fp64 poisson5pt 512^2 (L2-resident)")
+            del M
+            try:
+                coo = convert.rmat(args.rmat_scale, 16, seed=42, dtype=torch.float32)
+                formats[f"coo_f32_rmat_s{args.rmat_scale}"] = bench_format(
+                    h, coo, torch.float32, max(10, fs // 4), 3, peak, label=f"COO fp32 R-MAT scale {args.rmat_scale} ef 16")
+                hyb = convert.csr_to_hyb(convert.coo_to_csr(coo))
+                del coo
+                r = bench_format(h, hyb, torch.float32, max(10, fs // 4), 3, peak,
+                                 label=f"HYB fp32 R-MAT scale {args.rmat_scale} ef 16")
+                r["ell_cols_per_row"] = hyb.ell.num_cols_per_row
+                r["coo_tail_nnz"] = hyb.coo.num_entries
+                formats[f"hyb_f32_rmat_s{args.rmat_scale}"] = r
+                del hyb
+            except Exception as ex:  # keep the headline line even if the big graph does not fit
+                formats["rmat_error"] = repr(ex)
+            torch.cuda.empty_cache()
+        else:
+            del A, xw, y
+            torch.cuda.empty_cache()
+
+        # ---- CG: poisson7pt 512^3 fp64, b = 1, x0 = 0, fixed iteration count (strong scaling) -------
+        cblk = plane_partition(CG_GRID, world, rank)
+        Ac = gallery.poisson("dia", 7, CG_GRID, dtype=tdt, row_begin=cblk.row_begin, num_rows=cblk.num_rows,
+                             halo_lo=cblk.halo_lo, halo_hi=cblk.halo_hi)
+        b = torch.ones(cblk.num_rows, dtype=tdt, device=dev)
+        xs = torch.zeros(cblk.num_rows, dtype=tdt, device=dev)
+        chalo = capi.Halo(cblk.halo_lo, cblk.halo_hi) if world > 1 else None
+        iters = args.cg_iters
+        h.cg(Ac.descriptor(), xs, b, iteration_limit=3, relative_tolerance=0.0, check_interval=3, halo=chalo,
+             want_residuals=False)  # warm-up
+        xs.zero_()
+        barrier()
+        c0 = torch.cuda.Event(enable_timing=True)
+        c1 = torch.cuda.Event(enable_timing=True)
+        c0.record()
+        res, hist = h.cg(Ac.descriptor(), xs, b, iteration_limit=iters, relative_tolerance=0.0,
+                         check_interval=iters, halo=chalo)
+        c1.record()
+        barrier()
+        cg_ms = max_over_ranks(c0.elapsed_time(c1))
+        Bc = compulsory_bytes(Ac, es) + 9 * cblk.num_rows * es
+        cg = {"workload": "cusp::krylov::cg, poisson7pt 512^3 DIA fp64, b=1, x0=0, identity preconditioner",
+              "iterations": int(res.iteration_count), "ms_total": cg_ms, "iters_per_sec": iters / cg_ms * 1e3,
+              "ms_per_iter": cg_ms / iters, "scaling": "strong", "residual_first": float(hist[0]),
+              "residual_last": float(hist[-1]), "bytes_per_iter_per_gpu": Bc,
+              "gbs_per_gpu": Bc / (cg_ms / iters) / 1e6, "frac": Bc / (cg_ms / iters) / 1e6 / peak,
+              "includes": "setup SpMV + ||b|| + residual init (1 extra SpMV over %d iterations)" % iters}
+        del Ac, b, xs
+        torch.cuda.empty_cache()
+
+        # ---- CPU baseline: the reference's host loop on this box's cores (rank 0, N == 1) -----------
+        if world == 1 and rank == 0:
+            from oracle import oracle as O
+            kind = "reference" if O.ref_available() else "port"
+            threads = O.num_threads()
+            Ah = O.poisson(7, GRID, np.float64, "dia")
+            xv = ((np.arange(Ah["num_cols"]) % 21) - 10).astype(np.float64)
+            impl = "ref" if kind == "reference" else "oracle_mt"
+            best1 = best = 1e30
+            yc = None
+            t_start = time.perf_counter()
+            for rep in range(5):
+                t0 = time.perf_counter()
+                yc = O.spmv(Ah, xv, impl=impl, nthreads=threads)
+                best = min(best, time.perf_counter() - t0)
+                if time.perf_counter() - t_start > 25:
+                    break
+            t0 = time.perf_counter()
+            O.spmv(Ah, xv, impl=impl, nthreads=1)
+            best1 = time.perf_counter() - t0
+            cpu = {"value": 2.0 * Ah["num_entries"] / best / 1e9, "unit": "GFLOP/s", "cores": threads, "kind": kind,
+                   "sample": "full workload (poisson7pt 256^3 DIA fp64), best of <=5 SpMVs after 1 warm-up",
+                   "ms": best * 1e3, "one_core_gflops": 2.0 * Ah["num_entries"] / best1 / 1e9,
+                   "checksum_matches_gpu": bool(abs(float(np.abs(yc).sum()) - y_check) <= 1e-9 * max(1.0, y_check))}
+            del Ah, xv, yc
+
+    clocks = sampler.stop()
+    if rank == 0:
+        line = {
+            "metric": "spmv_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cusp::gallery::poisson7pt 256^3 per GPU, DIA fp64, y = A x "
+                                   "(BASELINE configs[1]); N>1: blocks stacked along z, halo exchange per step",
+                       "format": "dia", "rows_per_gpu": blk.num_rows, "nnz_total": nnz_total,
+                       "x": "x_i = (i mod 21) - 10 (performance/spmv/benchmark.h convention)",
+                       "l2": "per-step inputs (1.21 GB) exceed the 126 MB L2, no flush needed",
+                       "parallelism": f"rowblock{world}", "api": "b200sp_spmv / b200sp_spmv_dist (C ABI)"},
+            "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "cpu_baseline": cpu, "formats": formats, "cg": cg,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        h.comm_destroy()
+        td.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -328,11 +328,13 @@ static b200sp_status dispatch_bulk(b200sp_handle h, cudaStream_t st, const DiaAr
 // Engine defaults (overridden by cfg / tuning cache).  Chosen on B200 from the
 // round-1 sweep in profiles/.
 static void dia_defaults(b200sp_cfg &c, size_t elem) {
-  if (c.kernel == 0) c.kernel = B200SP_K_DIA_LDG;
-  if (c.block_size == 0) c.block_size = 256;
+  // round-1 sweep on B200, poisson7pt 256^3 (profiles/r01_probe_256.md): the
+  // bulk-async kernel wins for both value types (6.0 / 6.5 TB/s vs 4.8 / 6.3 LDG)
+  if (c.kernel == 0) c.kernel = B200SP_K_DIA_BULK;
+  if (c.block_size == 0) c.block_size = 128;
   if (c.unroll == 0) c.unroll = (elem == 4) ? 4 : 2;
-  if (c.stages == 0) c.stages = 3;
-  if (c.ctas_per_sm == 0) c.ctas_per_sm = 2;
+  if (c.stages == 0) c.stages = 2;
+  if (c.ctas_per_sm == 0) c.ctas_per_sm = 4;
 }
 
 template <typename T>

@@ -312,11 +312,12 @@ static b200sp_status dispatch_bulk(b200sp_handle h, cudaStream_t st, const EllAr
 }
 
 static void ell_defaults(b200sp_cfg &c, size_t elem) {
-  if (c.kernel == 0) c.kernel = B200SP_K_ELL_LDG;
+  // round-1 sweep on B200, poisson7pt 256^3 (profiles/r01_probe_256.md)
+  if (c.kernel == 0) c.kernel = B200SP_K_ELL_BULK;
   if (c.block_size == 0) c.block_size = 256;
-  if (c.unroll == 0) c.unroll = (elem == 4) ? 4 : 2;
-  if (c.stages == 0) c.stages = 4;
-  if (c.ctas_per_sm == 0) c.ctas_per_sm = 2;
+  if (c.unroll == 0) c.unroll = (c.kernel == B200SP_K_ELL_BULK) ? ((elem == 4) ? 2 : 1) : 4;
+  if (c.stages == 0) c.stages = 3;
+  if (c.ctas_per_sm == 0) c.ctas_per_sm = 4;
 }
 
 template <typename T>

@@ -284,7 +284,7 @@ b200sp_status b200sp_cg(b200sp_handle h, b200sp_stream stream,
  * x_window + halo_lo.  Halo planes are exchanged with the two neighbouring
  * ranks before every SpMV (NCCL send/recv on `stream`), dot products are
  * all-reduced with NCCL.  The communicator is created from a 128-byte NCCL
- * unique id that the host distributes (torch.distributed / MPI / files).
+ * unique id that the host distributes (any out-of-band channel: MPI, a file, a socket).
  */
 #define B200SP_NCCL_UNIQUE_ID_BYTES 128
 b200sp_status b200sp_comm_unique_id(void *id128);

