@@ -415,7 +415,9 @@ def convert(A: dict, fmt: str, alignment=32, num_entries_per_row=0) -> dict:
 def ell_row_lengths(A: dict):
     """cusp/ktt/detail/ellr_matrix.inl:16-52"""
     p, K, rows = A["pitch"], A["num_cols_per_row"], A["num_rows"]
-    c = A["column_indices"].reshape(K, p)[:, :rows] if K else np.zeros((0, rows), np.int32)
+    if K == 0:
+        return np.zeros(rows, np.int32)
+    c = A["column_indices"].reshape(K, p)[:, :rows]
     neg = c < 0
     first_neg = np.where(neg.any(axis=0), neg.argmax(axis=0), K)
     return first_neg.astype(np.int32)

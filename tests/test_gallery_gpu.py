@@ -53,7 +53,8 @@ def test_partitioned_builders_reassemble_the_global_operator(world, dev):
             assert A.num_rows == blk.num_rows and A.num_cols == blk.window
             xw = torch.from_numpy(x[blk.col_shift: blk.col_shift + blk.window].copy()).to(dev)
             y = torch.zeros(blk.num_rows, dtype=torch.float64, device=dev)
-            cusp.multiply(A, xw, y, cfg=capi.Cfg())
+            # threads_per_row=1: the CSR kernel that keeps the reference's summation order
+            cusp.multiply(A, xw, y, cfg=capi.Cfg(threads_per_row=1))
             got.append(y.cpu().numpy())
         assert np.array_equal(np.concatenate(got), want), fmt
 

@@ -1,0 +1,30 @@
+"""Launches each hot kernel a few times on the BASELINE workloads (for ncu)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import cusp_autotuned_b200 as cusp
+from cusp_autotuned_b200 import capi, gallery, convert
+
+which = sys.argv[1].split(",") if len(sys.argv) > 1 else ["dia", "ell", "csr", "coo"]
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+h = cusp.default_handle()
+dev = torch.device("cuda", 0)
+n = 256
+for fmt in which:
+    if fmt in ("dia", "ell", "csr"):
+        A = gallery.poisson(fmt, 7, (n, n, n), dtype=torch.float64)
+        x = ((torch.arange(A.num_cols, device=dev) % 21) - 10).double()
+    else:
+        A = convert.rmat(22, 16, seed=42, dtype=torch.float32)
+        x = torch.rand(A.num_cols, device=dev) + 0.5
+    y = torch.empty(A.num_rows, dtype=x.dtype, device=dev)
+    d = A.descriptor()
+    cfgs = [None]
+    if fmt == "csr":
+        cfgs = [None, capi.Cfg(threads_per_row=1, unroll=1, block_size=128)]
+    for cfg in cfgs:
+        for _ in range(reps):
+            h.spmv(d, x, y, cfg=cfg)
+    torch.cuda.synchronize()
+    del A, x, y
+print("done")
