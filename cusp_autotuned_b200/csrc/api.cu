@@ -95,6 +95,11 @@ static std::vector<b200sp_cfg> cfg_space_vec(b200sp_format f, b200sp_dtype) {
       for (int b : blocks)
         for (int tpr : {1, 2, 4, 8, 16, 32})
           for (int u : {1, 2, 4}) push(v, B200SP_K_CSR_VECTOR, b, tpr, u, 0, 0);
+      for (int b : blocks)
+        for (int u : {4, 8, 16}) {
+          if (b == 512 && u == 16) continue;
+          push(v, B200SP_K_CSR_STREAM, b, 0, u, 0, 0);
+        }
       break;
     case B200SP_FMT_ELL:
     case B200SP_FMT_ELLR:

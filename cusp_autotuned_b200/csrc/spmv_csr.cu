@@ -15,6 +15,20 @@
 //     (bit-identical with -fmad=false); TPR > 1 changes only the grouping.
 //     Long rows continue in a 4x-unrolled strided loop.
 //
+//  K_CSR_STREAM : a CTA owns R consecutive rows (R chosen on the host so that the
+//     block's nnz fill one shared-memory chunk).  The block's contiguous nnz range
+//     [Ap[r0], Ap[r0+R)) is streamed with perfectly coalesced ld.global.cs loads
+//     [Ap[r0], Ap[r0+R)) of Aj and Ax is staged into shared memory by two
+//     cp.async.bulk copies (TMA engine, UBLKCP, L2 evict-first) regardless of row
+//     boundaries; then one thread per row walks its entries in order, gathering x
+//     with 8 independent ld.global.nc in flight: acc = init(y); acc += a0*x0; ...
+//     — exactly the reference's order, so this kernel is bit-identical to the host
+//     loop on any data.  Because lanes map to ROWS in the gather phase, a warp's
+//     gather touches neighbouring x entries for banded matrices (ELL-like L1
+//     behaviour) instead of the 5-10 cache lines a lane-per-entry mapping touches.
+//     Row pieces longer than 128 entries inside a chunk are reduced by a whole warp
+//     instead (power-law hubs; only the grouping of that piece changes).
+//
 // Algorithmic bytes: (rows+1)*4 + nnz*(4+sizeof(T)) + cols*sizeof(T) + rows*sizeof(T).
 #include "common.cuh"
 
@@ -127,6 +141,165 @@ __global__ void __launch_bounds__(BLOCK) csr_vector_kernel(CsrArgs<T> a) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// K_CSR_STREAM
+// ---------------------------------------------------------------------------
+constexpr int CSR_LONG = 128;   // row pieces longer than this are reduced by a warp
+constexpr int CSR_MAXQ = 96;    // >= CAP/CSR_LONG + 2 for every instantiated CAP
+constexpr int CSR_GU = 8;       // x gathers in flight per thread in the row phase
+
+template <typename T, int BLOCK, int NPT>
+__global__ void __launch_bounds__(BLOCK) csr_stream_kernel(CsrArgs<T> a, int R, int tma_aligned) {
+  constexpr int CAP = BLOCK * NPT;
+  constexpr int EPV = 16 / (int)sizeof(T);  // values per 16 bytes
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T *s_val = reinterpret_cast<T *>(smem_raw);              // CAP + 16   values of the chunk (+ slack)
+  int *s_col = reinterpret_cast<int *>(s_val + CAP + 16);    // CAP + 16   column indices  (+ slack)
+  T *s_acc = reinterpret_cast<T *>(s_col + CAP + 16);        // R          row accumulators
+  int *s_off = reinterpret_cast<int *>(s_acc + R);           // R + 1      row offsets
+  __shared__ uint64_t s_bar;
+  __shared__ int s_long[CSR_MAXQ];
+  __shared__ int s_nlong;
+  __shared__ T s_red[32];
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const i64 r0 = (i64)blockIdx.x * R;
+  const int nr = (int)min((i64)R, a.rows - r0);
+  const unsigned cols = (unsigned)a.cols;
+  const int nnz = (int)a.nnz;
+
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+    s_nlong = 0;
+  }
+  for (int i = tid; i <= nr; i += BLOCK) s_off[i] = ld_ro(a.Ap + r0 + i);
+  for (int i = tid; i < nr; i += BLOCK) s_acc[i] = a.accumulate ? a.y[r0 + i] : T(0);
+  __syncthreads();
+  const int s0 = s_off[0], s1 = s_off[nr];
+  uint32_t parity = 0;
+
+  for (int lo = s0; lo < s1; lo += CAP) {
+    const int hi = min(lo + CAP, s1);
+    // ---- phase 1: the chunk's contiguous (Aj, Ax) range -> shared memory ---------------
+    // bulk-async copies start at the enclosing 16-byte boundary; `sc`/`sv` are the
+    // resulting shifts.  The last chunk of the matrix (rounded end past nnz) and
+    // unaligned base pointers use plain coalesced loads.
+    const int ga_c = lo & ~3, ga_v = lo & ~(EPV - 1);
+    const int n_c = ((hi - ga_c) + 3) & ~3, n_v = ((hi - ga_v) + EPV - 1) & ~(EPV - 1);
+    int sc = 0, sv = 0;
+    if (tma_aligned && ga_c + n_c <= nnz && ga_v + n_v <= nnz) {
+      if (tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const uint64_t pol = l2_policy_evict_first();
+        mbar_expect_tx(&s_bar, (uint32_t)(n_c * sizeof(int) + n_v * sizeof(T)));
+        bulk_g2s(s_col, a.Aj + ga_c, (uint32_t)(n_c * sizeof(int)), &s_bar, pol);
+        bulk_g2s(s_val, a.Ax + ga_v, (uint32_t)(n_v * sizeof(T)), &s_bar, pol);
+      }
+      sc = lo - ga_c;
+      sv = lo - ga_v;
+      if (w == 0) mbar_wait(&s_bar, parity);  // one warp polls, the rest sleep at the barrier
+      parity ^= 1;
+      __syncthreads();
+    } else {
+      for (int idx = tid; idx < hi - lo; idx += BLOCK) {
+        s_col[idx] = ld_stream(a.Aj + lo + idx);
+        s_val[idx] = ld_stream(a.Ax + lo + idx);
+      }
+      __syncthreads();
+    }
+    const int *pc = s_col + sc - lo;  // pc[j], pv[j] for absolute entry index j
+    const T *pv = s_val + sv - lo;
+
+    // ---- phase 2: one thread per row, entries in order (the reference's order) ---------
+    for (int i = tid; i < nr; i += BLOCK) {
+      const int b = max(s_off[i], lo), e = min(s_off[i + 1], hi);
+      if (b < e) {
+        if (e - b <= CSR_LONG) {
+          T t = s_acc[i];
+          // slots past `e` read stale shared memory inside the buffers' 16-entry slack:
+          // their column is clamped to a valid address and their product discarded
+          for (int j = b; j < e; j += CSR_GU) {
+            T xv[CSR_GU];
+#pragma unroll
+            for (int q = 0; q < CSR_GU; ++q) xv[q] = ld_ro(a.x + min((unsigned)pc[j + q], cols - 1));
+#pragma unroll
+            for (int q = 0; q < CSR_GU; ++q) {
+              pin(xv[q]);
+              const T u = t + pv[j + q] * xv[q];
+              t = (j + q < e) ? u : t;
+            }
+          }
+          s_acc[i] = t;
+        } else {
+          s_long[atomicAdd(&s_nlong, 1)] = i;
+        }
+      }
+    }
+    __syncthreads();
+    const int nlong = s_nlong;
+    if (nlong > 0) {  // uniform: power-law hub pieces, one warp each
+      for (int q = w; q < nlong; q += BLOCK / 32) {
+        const int i = s_long[q];
+        const int b = max(s_off[i], lo), e = min(s_off[i + 1], hi);
+        T part = T(0);
+        for (int j = b + lane; j < e; j += 32) part = part + pv[j] * ld_ro(a.x + min((unsigned)pc[j], cols - 1));
+        part = warp_sum(part);
+        if (lane == 0) s_acc[i] = s_acc[i] + part;
+      }
+      __syncthreads();
+      if (tid == 0) s_nlong = 0;
+      __syncthreads();
+    }
+  }
+
+  T dsum = 0;
+  for (int i = tid; i < nr; i += BLOCK) {
+    const T t = s_acc[i];
+    a.y[r0 + i] = t;
+    if (a.dotv) dsum = dsum + t * ld_ro(a.dotv + r0 + i);
+  }
+  if (a.dotv) {
+    T bs = block_sum<BLOCK>(dsum, s_red);
+    grid_reduce_finish<BLOCK>(bs, a.dot_partials, a.dot_ticket, s_red,
+                              [&](T total) { *a.dot_result = total; });
+  }
+}
+
+template <typename T, int BLOCK, int NPT>
+static b200sp_status launch_stream(b200sp_handle h, cudaStream_t st, CsrArgs<T> a) {
+  constexpr int CAP = BLOCK * NPT;
+  static_assert(CAP / CSR_LONG + 2 <= CSR_MAXQ, "long-row queue too small");
+  // rows per CTA: the block's nnz should fill about one chunk
+  const double mean = (double)a.nnz / (double)a.rows;
+  i64 R = (i64)((double)CAP / (mean > 1.0 ? mean : 1.0));
+  R = (R / 32) * 32;
+  if (R < 32) R = 32;
+  if (R > 2048) R = 2048;
+  const i64 grid = ceil_div(a.rows, R);
+  if (a.dotv && grid > RED_MAX_PARTIALS)
+    return set_error(h, B200SP_INVALID_INPUT, "csr: too many CTAs for fused dot");
+  const size_t smem = (size_t)(CAP + 16 + R) * sizeof(T) + (size_t)(CAP + 16 + R + 1) * sizeof(int);
+  auto kern = csr_stream_kernel<T, BLOCK, NPT>;
+  if (smem > 48 * 1024)
+    B200SP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tma_aligned = aligned16(a.Aj) && aligned16(a.Ax);
+  kern<<<(unsigned)grid, BLOCK, smem, st>>>(a, (int)R, tma_aligned);
+  B200SP_LAUNCH_CHECK(h, "csr_stream_kernel");
+  return B200SP_OK;
+}
+
+template <typename T>
+static b200sp_status dispatch_stream(b200sp_handle h, cudaStream_t st, const CsrArgs<T> &a, int block, int npt) {
+#define CASE(B, N) \
+  if (block == B && npt == N) return launch_stream<T, B, N>(h, st, a);
+  CASE(128, 4) CASE(128, 8) CASE(128, 16)
+  CASE(256, 4) CASE(256, 8) CASE(256, 16)
+  CASE(512, 4) CASE(512, 8)
+#undef CASE
+  return set_error(h, B200SP_INVALID_INPUT, "csr stream: unsupported block_size=%d unroll=%d", block, npt);
+}
+
 template <typename T, int BLOCK, int TPR, int RPT>
 static b200sp_status launch_vec(b200sp_handle h, cudaStream_t st, CsrArgs<T> a) {
   const i64 grid = ceil_div(a.rows, (i64)(BLOCK / TPR) * RPT);
@@ -151,8 +324,14 @@ static b200sp_status dispatch_tpr(b200sp_handle h, cudaStream_t st, const CsrArg
   return set_error(h, B200SP_INVALID_INPUT, "csr: unsupported threads_per_row=%d unroll=%d", tpr, rpt);
 }
 
-static void csr_defaults(b200sp_cfg &c, i64 rows, i64 nnz) {
-  if (c.kernel == 0) c.kernel = B200SP_K_CSR_VECTOR;
+static void csr_defaults(b200sp_cfg &c, i64 rows, i64 nnz, size_t elem) {
+  if (c.kernel == 0) c.kernel = B200SP_K_CSR_STREAM;
+  if (c.kernel == B200SP_K_CSR_STREAM) {
+    // round-1 sweep on B200 (profiles/r01_probe_256.md)
+    if (c.block_size == 0) c.block_size = 128;
+    if (c.unroll == 0) c.unroll = (elem == 4) ? 16 : 8;
+    return;
+  }
   if (c.block_size == 0) c.block_size = 256;
   if (c.threads_per_row == 0) {
     // smallest power of two >= mean row length (the reference uses the integer
@@ -186,11 +365,9 @@ b200sp_status spmv_csr(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64
   B200SP_REQUIRE(h, cols > 0, "csr: num_cols == 0 with stored entries");
 
   b200sp_cfg c = cfg ? *cfg : b200sp_cfg{};
-  csr_defaults(c, rows, nnz);
+  csr_defaults(c, rows, nnz, sizeof(T));
   if (c.kernel != B200SP_K_CSR_VECTOR && c.kernel != B200SP_K_CSR_STREAM)
     return set_error(h, B200SP_INVALID_INPUT, "csr: unknown kernel id %d", c.kernel);
-  if (c.kernel == B200SP_K_CSR_STREAM)
-    return set_error(h, B200SP_NOT_IMPLEMENTED, "csr: K_CSR_STREAM is not built in this release");
 
   CsrArgs<T> a;
   a.rows = rows; a.cols = cols; a.nnz = nnz; a.Ap = Ap; a.Aj = Aj; a.Ax = Ax; a.x = x; a.y = y;
@@ -198,6 +375,7 @@ b200sp_status spmv_csr(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64
   a.dot_partials = reinterpret_cast<T *>(h->red_partials);
   a.dot_ticket = h->red_counters;
 
+  if (c.kernel == B200SP_K_CSR_STREAM) return dispatch_stream<T>(h, st, a, c.block_size, c.unroll);
   switch (c.block_size) {
     case 128: return dispatch_tpr<T, 128>(h, st, a, c.threads_per_row, c.unroll);
     case 256: return dispatch_tpr<T, 256>(h, st, a, c.threads_per_row, c.unroll);

@@ -52,11 +52,14 @@ def test_version_and_strings():
 
 def test_cfg_spaces_enumerate():
     sizes = {f: len(capi.Handle.cfg_space(f, capi.F32)) for f in range(6)}
-    assert sizes[capi.FMT_CSR] == 54 and sizes[capi.FMT_COO] == 10
+    assert sizes[capi.FMT_CSR] == 62 and sizes[capi.FMT_COO] == 10
     assert sizes[capi.FMT_ELL] == sizes[capi.FMT_DIA] == sizes[capi.FMT_ELLR] == 63
     for c in capi.Handle.cfg_space(capi.FMT_CSR, capi.F64):
-        assert c.kernel == capi.K_CSR_VECTOR and c.block_size in (128, 256, 512)
-        assert c.threads_per_row in (1, 2, 4, 8, 16, 32) and c.unroll in (1, 2, 4)
+        assert c.kernel in (capi.K_CSR_VECTOR, capi.K_CSR_STREAM) and c.block_size in (128, 256, 512)
+        if c.kernel == capi.K_CSR_VECTOR:
+            assert c.threads_per_row in (1, 2, 4, 8, 16, 32) and c.unroll in (1, 2, 4)
+        else:
+            assert c.unroll in (4, 8, 16)
 
 
 def test_poisson_entry_count_closed_form():

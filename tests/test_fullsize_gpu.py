@@ -26,8 +26,8 @@ def _boundary_count_7pt(n, dev):
 
 @pytest.mark.parametrize("tdt", [torch.float32, torch.float64])
 def test_poisson7pt_256_all_formats_agree_bitwise(tdt, dev, handle):
-    """configs[1]: 16.7M rows.  DIA, ELL (both kernels) and scalar CSR keep the
-    reference's per-row order -> identical bits; A*1 has a closed form."""
+    """configs[1]: 16.7M rows.  DIA, ELL (both kernels), stream CSR and scalar CSR keep
+    the reference's per-row order -> identical bits; A*1 has a closed form."""
     n = 256
     N = n ** 3
     ones = torch.ones(N, dtype=tdt, device=dev)
@@ -37,7 +37,8 @@ def test_poisson7pt_256_all_formats_agree_bitwise(tdt, dev, handle):
     outs = {}
     for fmt, cfgs in (("dia", [capi.Cfg(kernel=1), capi.Cfg(kernel=2)]),
                       ("ell", [capi.Cfg(kernel=1), capi.Cfg(kernel=2)]),
-                      ("csr", [capi.Cfg(threads_per_row=1), capi.Cfg(threads_per_row=8)])):
+                      ("csr", [capi.Cfg(kernel=capi.K_CSR_STREAM), capi.Cfg(kernel=capi.K_CSR_VECTOR, threads_per_row=8),
+                               capi.Cfg(kernel=capi.K_CSR_VECTOR, threads_per_row=1)])):
         A = gallery.poisson(fmt, 7, (n, n, n), dtype=tdt)
         assert A.num_entries == 117047296
         for ci, cfg in enumerate(cfgs):
@@ -79,9 +80,11 @@ def test_poisson5pt_512_csr_fp64_vs_oracle(dev, handle):
     x = rng.uniform(0.5, 1.5, 262144)
     xd = torch.from_numpy(x).to(dev)
     y = torch.empty(262144, dtype=torch.float64, device=dev)
-    cusp.multiply(A, xd, y, cfg=capi.Cfg(threads_per_row=1))
+    cusp.multiply(A, xd, y, cfg=capi.Cfg(kernel=capi.K_CSR_VECTOR, threads_per_row=1))
     assert np.array_equal(y.cpu().numpy(), O.spmv(Ah, x))           # scalar kernel: bit-exact
-    cusp.multiply(A, xd, y)                                          # default (sub-warp) kernel
+    cusp.multiply(A, xd, y)                                          # default (stream) kernel
+    assert np.array_equal(y.cpu().numpy(), O.spmv(Ah, x))           # keeps the order too: bit-exact
+    cusp.multiply(A, xd, y, cfg=capi.Cfg(kernel=capi.K_CSR_VECTOR, threads_per_row=8))  # sub-warp kernel
     scale = O.spmv(dict(Ah, values=np.abs(Ah["values"])), x)
     assert np.max(np.abs(y.cpu().numpy() - O.spmv(Ah, x)) / scale) <= 1e-12
 

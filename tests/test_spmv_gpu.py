@@ -108,8 +108,8 @@ def test_committed_reference_outputs(fmt, ndt, tdt, dev, golden):
 
 
 @pytest.mark.parametrize("ndt,tdt", DTYPES)
-def test_csr_scalar_is_bit_exact_on_any_data(ndt, tdt, dev):
-    """threads_per_row == 1 keeps the reference's order (csr_spmv.h:35-74)"""
+def test_csr_order_preserving_kernels_bit_exact_on_any_data(ndt, tdt, dev):
+    """threads_per_row == 1 and the stream kernel keep the reference's order (csr_spmv.h:35-74)"""
     rng = np.random.default_rng(3)
     A = O.poisson(7, (11, 9, 8), ndt, "csr")
     A["values"] = (A["values"] * rng.uniform(0.5, 1.5, len(A["values"]))).astype(ndt)
@@ -121,6 +121,28 @@ def test_csr_scalar_is_bit_exact_on_any_data(ndt, tdt, dev):
             assert np.array_equal(gpu_multiply("csr", A, x, dev, cfg=cfg), O.spmv(A, x))
             assert np.array_equal(gpu_multiply("csr", A, x, dev, y0=y0, accumulate=True, cfg=cfg),
                                   O.spmv(A, x, y0, accumulate=True))
+    for cfg in [c for c in capi.Handle.cfg_space(capi.FMT_CSR, 0) if c.kernel == capi.K_CSR_STREAM]:
+        assert np.array_equal(gpu_multiply("csr", A, x, dev, cfg=cfg), O.spmv(A, x)), cfg
+        assert np.array_equal(gpu_multiply("csr", A, x, dev, y0=y0, accumulate=True, cfg=cfg),
+                              O.spmv(A, x, y0, accumulate=True)), cfg
+
+
+@pytest.mark.parametrize("ndt,tdt", DTYPES)
+def test_csr_long_rows_and_skewed_lengths(ndt, tdt, dev):
+    """rows far longer than a shared-memory chunk, next to empty and 1-entry rows"""
+    rng = np.random.default_rng(8)
+    n = 3000
+    lens = np.concatenate([rng.integers(0, 4, 500), [20000], rng.integers(0, 9, 700), [129, 128, 127, 4097, 0, 0],
+                           rng.integers(0, 300, 200)])
+    rows = len(lens)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    nnz = int(offs[-1])
+    A = dict(format="csr", num_rows=rows, num_cols=n, num_entries=nnz, row_offsets=offs,
+             column_indices=rng.integers(0, n, nnz).astype(np.int32), values=rng.integers(1, 4, nnz).astype(ndt))
+    x = rng.integers(-3, 4, n).astype(ndt)
+    want = O.spmv(A, x)
+    for cfg in capi.Handle.cfg_space(capi.FMT_CSR, 0):
+        assert np.array_equal(gpu_multiply("csr", A, x, dev, cfg=cfg), want), cfg
 
 
 # ---------------------------------------------------------------------------

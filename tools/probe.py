@@ -7,6 +7,7 @@ import cusp_autotuned_b200 as cusp
 from cusp_autotuned_b200 import capi, gallery
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+fmts = sys.argv[2].split(",") if len(sys.argv) > 2 else ["dia", "ell", "csr"]
 reps = 20
 dev = torch.device("cuda", 0)
 h = cusp.default_handle()
@@ -33,7 +34,7 @@ def comp_bytes(fmt, A, es):
 out = []
 for dtype in (torch.float32, torch.float64):
     es = 4 if dtype == torch.float32 else 8
-    for fmt in ("dia", "ell", "csr"):
+    for fmt in fmts:
         A = gallery.poisson7pt(n, n, n, fmt=fmt, dtype=dtype)
         x = torch.rand(A.num_cols, dtype=dtype, device=dev) + 0.5
         y = torch.empty(A.num_rows, dtype=dtype, device=dev)
@@ -53,7 +54,7 @@ for dtype in (torch.float32, torch.float64):
             print(f"{fmt} {es*8} k={cfg.kernel} b={cfg.block_size} tpr={cfg.threads_per_row} u={cfg.unroll} st={cfg.stages} cps={cfg.ctas_per_sm}: {med:.4f} ms  {B/med/1e6:8.1f} GB/s same={ok}", flush=True)
         del A, x, y
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open(f"gpurun_out/probe_{n}.json", "w"))
+json.dump(out, open(f"gpurun_out/probe_{n}_{'_'.join(fmts)}.json", "w"))
 best = {}
 for r in out:
     k = (r["fmt"], r["dtype"])

@@ -21,7 +21,7 @@ for fmt in which:
     d = A.descriptor()
     cfgs = [None]
     if fmt == "csr":
-        cfgs = [None, capi.Cfg(threads_per_row=1, unroll=1, block_size=128)]
+        cfgs = [None]
     for cfg in cfgs:
         for _ in range(reps):
             h.spmv(d, x, y, cfg=cfg)
