@@ -1,0 +1,74 @@
+// cusp/detail/engine.h — the one place where the compatibility headers meet the
+// C ABI (include/b200sp.h).  A thread-local engine handle is created on first
+// use; every status other than B200SP_OK becomes a cusp exception
+// (B200SP_INVALID_INPUT -> cusp::invalid_input_exception, else
+// cusp::runtime_exception), mirroring cusp/exception.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "../../b200sp.h"
+#include "../exception.h"
+
+namespace cusp {
+namespace detail {
+
+struct engine_holder {
+  b200sp_handle h = nullptr;
+  ~engine_holder() {
+    if (h) b200sp_destroy(h);
+  }
+};
+
+inline b200sp_handle engine() {
+  static thread_local engine_holder holder;
+  if (!holder.h) {
+    b200sp_status s = b200sp_create(&holder.h);
+    if (s != B200SP_OK) throw cusp::runtime_exception(std::string("b200sp_create: ") + b200sp_last_error_string(nullptr));
+  }
+  return holder.h;
+}
+
+inline void check(b200sp_status s) {
+  if (s == B200SP_OK) return;
+  std::string msg = b200sp_last_error_string(engine());
+  if (s == B200SP_INVALID_INPUT) throw cusp::invalid_input_exception(msg);
+  throw cusp::runtime_exception(msg);
+}
+
+inline void cuda_check(cudaError_t e, const char *what) {
+  if (e != cudaSuccess) throw cusp::runtime_exception(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+// stream used by the default device policy: the legacy default stream, like
+// cusp::device_memory == cusp::cuda::par (cusp/system/cuda/detail/par.h:36-54)
+inline b200sp_stream &current_stream() {
+  static thread_local b200sp_stream s = nullptr;
+  return s;
+}
+
+template <typename T>
+struct dtype_of;
+template <>
+struct dtype_of<float> {
+  static const b200sp_dtype value = B200SP_F32;
+};
+template <>
+struct dtype_of<double> {
+  static const b200sp_dtype value = B200SP_F64;
+};
+
+}  // namespace detail
+
+namespace cuda {
+// cusp::cuda::par.on(stream): run subsequent device calls of this thread on `stream`
+struct par_t {
+  const par_t &on(cudaStream_t s) const {
+    cusp::detail::current_stream() = (b200sp_stream)s;
+    return *this;
+  }
+};
+static const par_t par{};
+}  // namespace cuda
+}  // namespace cusp

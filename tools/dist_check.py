@@ -1,0 +1,104 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check of the row-partitioned operator, one process
+per GPU:
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+      --master-port 29511 tools/dist_check.py
+
+Every rank builds its row block of poisson7pt on the device, then
+  * b200sp_spmv_dist: the gathered y must be BIT-IDENTICAL to the oracle's
+    single-domain y (each y entry is computed by exactly one GPU, same order);
+  * b200sp_cg_dist: iteration count equal and residual history within 1e-10
+    relative of the oracle's sequential CG (only the dot-product grouping differs).
+Prints one JSON line on rank 0 and exits non-zero on a mismatch.  The oracle is
+the checker only.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as td
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import cusp_autotuned_b200 as cusp  # noqa: E402
+from cusp_autotuned_b200 import capi, dist, gallery  # noqa: E402
+from cusp_autotuned_b200.partition import plane_partition  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+
+def main():
+    rank, world, local = dist.init_process_group_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    h = cusp.default_handle()
+    dist.init_engine_comm(h, rank, world)
+    out = {"world": world, "cases": []}
+    ok = True
+    for grid in ((24, 20, 16), (32, 32, 8 * world), (17, 13, world)):
+        for tdt, ndt in ((torch.float64, np.float64), (torch.float32, np.float32)):
+            for fmt in ("dia", "ell", "csr"):
+                blk = plane_partition(grid, world, rank)
+                A = gallery.poisson(fmt, 7, grid, dtype=tdt, row_begin=blk.row_begin, num_rows=blk.num_rows,
+                                    halo_lo=blk.halo_lo, halo_hi=blk.halo_hi)
+                ref = O.poisson(7, grid, ndt, "dia")
+                n = ref["num_rows"]
+                rng = np.random.default_rng(11)
+                xg = rng.uniform(0.5, 1.5, n).astype(ndt)
+                xw = torch.zeros(blk.window, dtype=tdt, device=dev)
+                xw[blk.halo_lo: blk.halo_lo + blk.num_rows] = torch.from_numpy(
+                    xg[blk.row_begin: blk.row_begin + blk.num_rows]).to(dev)
+                y = torch.empty(blk.num_rows, dtype=tdt, device=dev)
+                halo = capi.Halo(blk.halo_lo, blk.halo_hi)
+                if world > 1:
+                    h.spmv_dist(A.descriptor(), halo, xw, y)
+                else:
+                    h.spmv(A.descriptor(), xw, y)
+                want = O.spmv(O.convert(ref, fmt), xg)[blk.row_begin: blk.row_begin + blk.num_rows]
+                got = y.cpu().numpy()
+                exact = bool(np.array_equal(got, want)) if fmt != "csr" else bool(
+                    np.allclose(got, want, rtol=1e-5 if ndt == np.float32 else 1e-12, atol=1e-5 if ndt == np.float32 else 1e-12))
+                # CG
+                b = np.ones(n, ndt)
+                xo, it_o, conv_o, hist_o = O.cg(O.convert(ref, "csr"), np.zeros_like(b), b, 40, 1e-6)
+                xl = torch.zeros(blk.num_rows, dtype=tdt, device=dev)
+                bl = torch.ones(blk.num_rows, dtype=tdt, device=dev)
+                res, hist = h.cg(A.descriptor(), xl, bl, iteration_limit=40, relative_tolerance=1e-6,
+                                 check_interval=4, halo=halo if world > 1 else None)
+                # fp64: 1e-10 relative over the whole history; fp32: the regrouped dot products
+                # perturb the iterates at 1e-7 and CG amplifies that, so the history is compared against the
+                # initial residual (absolute) instead
+                hist_o = np.asarray(hist_o, dtype=np.float64)
+                same_it = int(res.iteration_count) == int(it_o)
+                m = min(len(hist), len(hist_o))
+                if ndt == np.float64:
+                    hist_ok = bool(np.allclose(hist[:m], hist_o[:m], rtol=1e-10, atol=0))
+                else:
+                    hist_ok = bool(np.all(np.abs(hist[:m] - hist_o[:m]) <= 1e-4 * hist_o[0]))
+                hist_ok = hist_ok and len(hist) == len(hist_o)
+                x_ok = bool(np.allclose(xl.cpu().numpy(), xo[blk.row_begin: blk.row_begin + blk.num_rows],
+                                        rtol=1e-3 if ndt == np.float32 else 1e-9))
+                flags = torch.tensor([int(exact), int(same_it), int(hist_ok), int(x_ok)], device=dev)
+                if world > 1:
+                    td.all_reduce(flags, op=td.ReduceOp.MIN)
+                f = [int(v) for v in flags.cpu().tolist()]
+                out["cases"].append({"grid": list(grid), "dtype": ndt.__name__, "fmt": fmt, "spmv_exact": f[0],
+                                     "cg_same_iters": f[1], "cg_hist": f[2], "cg_x": f[3],
+                                     "iters": int(res.iteration_count)})
+                ok = ok and all(f)
+    out["ok"] = ok
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        h.comm_destroy()
+        td.destroy_process_group()
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
