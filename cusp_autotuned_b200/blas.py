@@ -51,3 +51,31 @@ dotc = dot  # real value types: conj is the identity
 
 def nrm2(x, handle=None) -> float:
     return (handle or default_handle()).nrm2(x)
+
+
+def axpbypcz(x, y, z, output, alpha, beta, gamma, handle=None):
+    """output <- alpha*x + beta*y + gamma*z"""
+    _same(x, y, z, output)
+    (handle or default_handle()).axpbypcz(alpha, x, beta, y, gamma, z, output)
+
+
+def xmy(x, y, z, handle=None):
+    """z <- x .* y"""
+    _same(x, y, z)
+    (handle or default_handle()).xmy(x, y, z)
+
+
+def asum(x, handle=None) -> float:
+    return (handle or default_handle()).asum(x)
+
+
+nrm1 = asum
+
+
+def nrmmax(x, handle=None) -> float:
+    return (handle or default_handle()).nrmmax(x)
+
+
+def amax(x, handle=None) -> int:
+    """index of the first element of maximal magnitude"""
+    return (handle or default_handle()).amax(x)

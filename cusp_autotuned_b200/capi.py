@@ -122,7 +122,8 @@ EXPORTED_SYMBOLS = (
      "b200sp_tune_reset", "b200sp_tune_lookup", "b200sp_tune_save", "b200sp_tune_load",
      "b200sp_poisson_num_entries", "b200sp_poisson_csr_offsets"]
     + [f"b200sp_spmv_{f}_{s}" for f in ("csr", "ell", "dia", "coo", "hyb", "ellr") for s in _SFX]
-    + [f"b200sp_{op}_{s}" for op in ("axpy", "axpby", "copy", "fill", "scal", "dot", "nrm2") for s in _SFX]
+    + [f"b200sp_{op}_{s}" for op in ("axpy", "axpby", "axpbypcz", "xmy", "copy", "fill", "scal", "dot", "nrm2", "asum", "nrmmax",
+                                       "amax") for s in _SFX]
     + [f"b200sp_poisson_{f}_{s}" for f in ("dia", "ell", "csr") for s in _SFX]
 )
 
@@ -289,6 +290,34 @@ class Handle:
     def scal(self, alpha, x):
         f = getattr(self.lib, "b200sp_scal_" + _sfx(x.dtype))
         self.check(f(self._h, _stream(), C.c_int64(x.numel()), _ctype(x.dtype)(alpha), _ptr(x)))
+
+    def axpbypcz(self, alpha, x, beta, y, gamma, z, out):
+        f = getattr(self.lib, "b200sp_axpbypcz_" + _sfx(out.dtype))
+        ct = _ctype(out.dtype)
+        self.check(f(self._h, _stream(), C.c_int64(out.numel()), ct(alpha), _ptr(x), ct(beta), _ptr(y), ct(gamma),
+                     _ptr(z), _ptr(out)))
+
+    def xmy(self, x, y, z):
+        f = getattr(self.lib, "b200sp_xmy_" + _sfx(z.dtype))
+        self.check(f(self._h, _stream(), C.c_int64(z.numel()), _ptr(x), _ptr(y), _ptr(z)))
+
+    def _reduce1(self, name, x) -> float:
+        f = getattr(self.lib, f"b200sp_{name}_" + _sfx(x.dtype))
+        out = _ctype(x.dtype)()
+        self.check(f(self._h, _stream(), C.c_int64(x.numel()), _ptr(x), None, C.byref(out)))
+        return out.value
+
+    def asum(self, x) -> float:
+        return self._reduce1("asum", x)
+
+    def nrmmax(self, x) -> float:
+        return self._reduce1("nrmmax", x)
+
+    def amax(self, x) -> int:
+        f = getattr(self.lib, "b200sp_amax_" + _sfx(x.dtype))
+        out = C.c_int()
+        self.check(f(self._h, _stream(), C.c_int64(x.numel()), _ptr(x), C.byref(out)))
+        return out.value
 
     def dot(self, x, y) -> float:
         f = getattr(self.lib, "b200sp_dot_" + _sfx(x.dtype))

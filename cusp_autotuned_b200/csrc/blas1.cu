@@ -39,6 +39,16 @@ struct AxpbyF {
   __device__ void operator()(i64 i) const { z[i] = alpha * x[i] + beta * y[i]; }
 };
 template <typename T>
+struct AxpbypczF {  // generic/blas.h AXPBYPCZ: alpha*x + beta*y + gamma*z, left to right
+  T alpha, beta, gamma; const T *x; const T *y; const T *z; T *out;
+  __device__ void operator()(i64 i) const { out[i] = alpha * x[i] + beta * y[i] + gamma * z[i]; }
+};
+template <typename T>
+struct XmyF {  // generic/blas.h XMY
+  const T *x; const T *y; T *z;
+  __device__ void operator()(i64 i) const { z[i] = x[i] * y[i]; }
+};
+template <typename T>
 struct FillF {
   T alpha; T *x;
   __device__ void operator()(i64 i) const { x[i] = alpha; }
@@ -69,7 +79,8 @@ static b200sp_status launch_ew(b200sp_handle h, cudaStream_t st, i64 n, F f, con
 constexpr int RED_BLOCK = 256;
 constexpr int RED_UNROLL = 4;
 
-// mode 0: sum x*y ; mode 1: sqrt(sum x*x)
+// mode 0: sum x*y ; mode 1: sqrt(sum x*x) ; mode 2: sum |x| (asum / nrm1) ;
+// mode 3: max |x| (nrmmax)
 template <typename T, int MODE>
 __global__ void __launch_bounds__(RED_BLOCK) reduce_kernel(i64 n, const T *x, const T *y, T *partials,
                                                            unsigned int *ticket, T *result) {
@@ -85,17 +96,65 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_kernel(i64 n, const T *x, co
       b[u] = (MODE == 0) ? y[i + u * stride] : a[u];
     }
 #pragma unroll
-    for (int u = 0; u < RED_UNROLL; ++u) acc = acc + a[u] * b[u];
+    for (int u = 0; u < RED_UNROLL; ++u) {
+      if (MODE <= 1) acc = acc + a[u] * b[u];
+      else if (MODE == 2) acc = acc + fabs(a[u]);
+      else acc = fmax(acc, fabs(a[u]));
+    }
   }
   for (; i < n; i += stride) {
     const T a = x[i];
     const T b = (MODE == 0) ? y[i] : a;
-    acc = acc + a * b;
+    if (MODE <= 1) acc = acc + a * b;
+    else if (MODE == 2) acc = acc + fabs(a);
+    else acc = fmax(acc, fabs(a));
+  }
+  if (MODE == 3) {
+    // max is order-independent: reuse the sum machinery on a max-combine
+    __shared__ T s_max[RED_BLOCK / 32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc = fmax(acc, __shfl_down_sync(0xffffffffu, acc, o));
+    if (lane == 0) s_max[w] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      T m = s_max[0];
+      for (int k = 1; k < RED_BLOCK / 32; ++k) m = fmax(m, s_max[k]);
+      partials[blockIdx.x] = m;
+      __threadfence();
+      is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+      __threadfence();
+      T m = T(0);
+      for (unsigned int k = 0; k < gridDim.x; ++k) m = fmax(m, *((volatile T *)(partials + k)));
+      *result = m;
+      *ticket = 0;
+      __threadfence();
+    }
+    return;
   }
   T bs = block_sum<RED_BLOCK>(acc, s_red);
   grid_reduce_finish<RED_BLOCK>(bs, partials, ticket, s_red, [&](T total) {
     *result = (MODE == 1) ? (T)sqrt((double)total) : total;
   });
+}
+
+// amax: index of the first element of maximal |x| (thrust::max_element semantics,
+// generic/blas.h:119-138).  Two tiny passes: nrmmax, then the smallest index whose
+// |x| equals it (atomicMin on an int).
+template <typename T>
+__global__ void __launch_bounds__(RED_BLOCK) amax_index_kernel(i64 n, const T *x, const T *maxval, int *index) {
+  const T m = *maxval;
+  const i64 stride = (i64)gridDim.x * RED_BLOCK;
+  int best = 0x7fffffff;
+  for (i64 i = (i64)blockIdx.x * RED_BLOCK + threadIdx.x; i < n; i += stride)
+    if (fabs(x[i]) == m && (int)i < best) best = (int)i;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_down_sync(0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0 && best != 0x7fffffff) atomicMin(index, best);
 }
 
 static inline i64 reduce_grid(b200sp_handle h, i64 n) {
@@ -115,7 +174,7 @@ b200sp_status reduce(b200sp_handle h, cudaStream_t st, i64 n, const T *x, const 
   if (n == 0) {
     B200SP_CUDA(h, cudaMemsetAsync(res, 0, sizeof(T), st));
   } else {
-    B200SP_REQUIRE(h, x && (MODE == 1 || y), "blas: null pointer");
+    B200SP_REQUIRE(h, x && (MODE != 0 || y), "blas: null pointer");
     reduce_kernel<T, MODE><<<(unsigned)reduce_grid(h, n), RED_BLOCK, 0, st>>>(
         n, x, y, reinterpret_cast<T *>(h->red_partials), h->red_counters, res);
     B200SP_LAUNCH_CHECK(h, "reduce_kernel");
@@ -137,6 +196,26 @@ template b200sp_status reduce<float, 1>(b200sp_handle, cudaStream_t, i64, const 
                                         float *, float *);
 template b200sp_status reduce<double, 1>(b200sp_handle, cudaStream_t, i64, const double *, const double *,
                                          double *, double *);
+
+template <typename T>
+static b200sp_status amax(b200sp_handle h, cudaStream_t st, i64 n, const T *x, int *index_host) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, n >= 0 && n < (1ll << 31) && index_host, "amax: bad arguments");
+  *index_host = 0;
+  if (n == 0) return B200SP_OK;
+  T *mx = reinterpret_cast<T *>(h->dev_scalars + 62);
+  int *idx = reinterpret_cast<int *>(h->dev_scalars + 61);
+  b200sp_status s = reduce<T, 3>(h, st, n, x, nullptr, mx, nullptr);
+  if (s != B200SP_OK) return s;
+  B200SP_CUDA(h, cudaMemsetAsync(idx, 0x7f, sizeof(int), st));
+  amax_index_kernel<T><<<(unsigned)reduce_grid(h, n), RED_BLOCK, 0, st>>>(n, x, mx, idx);
+  B200SP_LAUNCH_CHECK(h, "amax_index_kernel");
+  int *pin = reinterpret_cast<int *>(h->pinned_scalars);
+  B200SP_CUDA(h, cudaMemcpyAsync(pin, idx, sizeof(int), cudaMemcpyDeviceToHost, st));
+  B200SP_CUDA(h, cudaStreamSynchronize(st));
+  *index_host = *pin;
+  return B200SP_OK;
+}
 
 }  // namespace b200sp
 
@@ -166,6 +245,33 @@ extern "C" {
   b200sp_status b200sp_scal_##sfx(b200sp_handle h, b200sp_stream s, int64_t n, T alpha, T *x) {   \
     if (h && n > 0 && !x) return b200sp::set_error(h, B200SP_INVALID_INPUT, "scal: null");        \
     return b200sp::launch_ew<T>(h, (cudaStream_t)s, n, b200sp::ScalF<T>{alpha, x}, "scal");       \
+  }                                                                                               \
+  b200sp_status b200sp_axpbypcz_##sfx(b200sp_handle h, b200sp_stream s, int64_t n, T alpha,       \
+                                      const T *x, T beta, const T *y, T gamma, const T *z,        \
+                                      T *out) {                                                   \
+    if (h && n > 0 && !(x && y && z && out))                                                      \
+      return b200sp::set_error(h, B200SP_INVALID_INPUT, "axpbypcz: null");                        \
+    return b200sp::launch_ew<T>(h, (cudaStream_t)s, n,                                            \
+                                b200sp::AxpbypczF<T>{alpha, beta, gamma, x, y, z, out},           \
+                                "axpbypcz");                                                      \
+  }                                                                                               \
+  b200sp_status b200sp_xmy_##sfx(b200sp_handle h, b200sp_stream s, int64_t n, const T *x,         \
+                                 const T *y, T *z) {                                              \
+    if (h && n > 0 && !(x && y && z))                                                             \
+      return b200sp::set_error(h, B200SP_INVALID_INPUT, "xmy: null");                             \
+    return b200sp::launch_ew<T>(h, (cudaStream_t)s, n, b200sp::XmyF<T>{x, y, z}, "xmy");          \
+  }                                                                                               \
+  b200sp_status b200sp_asum_##sfx(b200sp_handle h, b200sp_stream s, int64_t n, const T *x,        \
+                                  T *result_dev, T *result_host) {                                \
+    return b200sp::reduce<T, 2>(h, (cudaStream_t)s, n, x, nullptr, result_dev, result_host);      \
+  }                                                                                               \
+  b200sp_status b200sp_nrmmax_##sfx(b200sp_handle h, b200sp_stream s, int64_t n, const T *x,      \
+                                    T *result_dev, T *result_host) {                              \
+    return b200sp::reduce<T, 3>(h, (cudaStream_t)s, n, x, nullptr, result_dev, result_host);      \
+  }                                                                                               \
+  b200sp_status b200sp_amax_##sfx(b200sp_handle h, b200sp_stream s, int64_t n, const T *x,        \
+                                  int *index_host) {                                              \
+    return b200sp::amax<T>(h, (cudaStream_t)s, n, x, index_host);                                 \
   }                                                                                               \
   b200sp_status b200sp_dot_##sfx(b200sp_handle h, b200sp_stream s, int64_t n, const T *x,         \
                                  const T *y, T *result_dev, T *result_host) {                     \

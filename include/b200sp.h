@@ -181,6 +181,22 @@ b200sp_status b200sp_ell_row_lengths(b200sp_handle h, b200sp_stream stream,
                                   T alpha, T *x);                                  \
   b200sp_status b200sp_scal_##sfx(b200sp_handle h, b200sp_stream s, int64_t n,     \
                                   T alpha, T *x);                                  \
+  /* out <- alpha*x + beta*y + gamma*z   generic/blas.h:99-117,222-246 */          \
+  b200sp_status b200sp_axpbypcz_##sfx(b200sp_handle h, b200sp_stream s, int64_t n, \
+                                      T alpha, const T *x, T beta, const T *y,     \
+                                      T gamma, const T *z, T *out);                \
+  /* z <- x .* y                 generic/blas.h:119-127,248-266 */                 \
+  b200sp_status b200sp_xmy_##sfx(b200sp_handle h, b200sp_stream s, int64_t n,      \
+                                 const T *x, const T *y, T *z);                    \
+  /* sum |x_i| (asum == nrm1)    generic/blas.h:160-176 */                         \
+  b200sp_status b200sp_asum_##sfx(b200sp_handle h, b200sp_stream s, int64_t n,     \
+                                  const T *x, T *result_dev, T *result_host);      \
+  /* max |x_i|                   generic/blas.h nrmmax */                          \
+  b200sp_status b200sp_nrmmax_##sfx(b200sp_handle h, b200sp_stream s, int64_t n,   \
+                                    const T *x, T *result_dev, T *result_host);    \
+  /* index of the first max |x_i| generic/blas.h:138-158; synchronises */          \
+  b200sp_status b200sp_amax_##sfx(b200sp_handle h, b200sp_stream s, int64_t n,     \
+                                  const T *x, int *index_host);                    \
   /* sum x_i*y_i                 generic/blas.h:284-313 (dot == dotc for reals) */ \
   b200sp_status b200sp_dot_##sfx(b200sp_handle h, b200sp_stream s, int64_t n,      \
                                  const T *x, const T *y, T *result_dev,            \

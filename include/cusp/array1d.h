@@ -1,44 +1,143 @@
-// cusp/array1d.h — cusp::array1d<T,MemorySpace> and array1d_view
-// (cusp/array1d.h:98-517), written without Thrust: host arrays sit on
-// std::vector, device arrays on cudaMalloc.  Element access on device arrays goes
-// through a proxy reference (one cudaMemcpy per access, as thrust::device_reference).
+// cusp/array1d.h — cusp::array1d<T,MemorySpace>, cusp::array1d_view<Iterator>
+// (reference: cusp/array1d.h:98-517), written without Thrust: host arrays sit on
+// std::vector, device arrays on cudaMalloc.  Device iterators are tagged
+// pointers (cusp::device_ptr<T>, the role thrust::device_ptr<T> plays in the
+// reference); element access on device arrays goes through a proxy reference
+// (one cudaMemcpy per access, as thrust::device_reference).  When Thrust headers
+// are on the include path, thrust::device_ptr<T> is accepted wherever a
+// cusp::device_ptr<T> is (examples/Views/cg_raw.cu wraps raw pointers that way).
 #pragma once
 #include <algorithm>
 #include <cstddef>
 #include <cstring>
+#include <iterator>
 #include <type_traits>
 #include <vector>
 
 #include "detail/engine.h"
 #include "memory.h"
 
+#if !defined(CUSP_B200_NO_THRUST) && defined(__has_include)
+#if __has_include(<thrust/device_ptr.h>) && defined(__CUDACC__)
+#include <thrust/device_ptr.h>
+#define CUSP_B200_HAVE_THRUST 1
+#endif
+#endif
+
 namespace cusp {
 
 template <typename T, typename MemorySpace>
 class array1d;
-template <typename T, typename MemorySpace>
+template <typename Iterator>
 class array1d_view;
+template <typename T>
+class device_ptr;
 
 namespace detail {
 
 template <typename T>
 class device_reference {
  public:
+  typedef typename std::remove_const<T>::type value_type;
   explicit device_reference(T *p) : p_(p) {}
-  operator T() const {
-    T v;
+  operator value_type() const {
+    value_type v;
     cuda_check(cudaMemcpy(&v, p_, sizeof(T), cudaMemcpyDeviceToHost), "device_reference read");
     return v;
   }
-  device_reference &operator=(const T &v) {
-    cuda_check(cudaMemcpy(p_, &v, sizeof(T), cudaMemcpyHostToDevice), "device_reference write");
+  device_reference &operator=(const value_type &v) {
+    cuda_check(cudaMemcpy(const_cast<value_type *>(p_), &v, sizeof(T), cudaMemcpyHostToDevice),
+               "device_reference write");
     return *this;
   }
-  device_reference &operator=(const device_reference &o) { return *this = (T)o; }
+  device_reference &operator=(const device_reference &o) { return *this = (value_type)o; }
+  device_ptr<T> operator&() const;
 
  private:
   T *p_;
 };
+
+}  // namespace detail
+
+// tagged device pointer: the iterator of device arrays and views
+template <typename T>
+class device_ptr {
+ public:
+  typedef typename std::remove_const<T>::type value_type;
+  typedef std::ptrdiff_t difference_type;
+  typedef T *pointer;
+  typedef detail::device_reference<T> reference;
+  typedef std::random_access_iterator_tag iterator_category;
+
+  device_ptr() : p_(nullptr) {}
+  explicit device_ptr(T *p) : p_(p) {}
+  template <typename U, typename = typename std::enable_if<std::is_convertible<U *, T *>::value>::type>
+  device_ptr(const device_ptr<U> &o) : p_(o.get()) {}
+  T *get() const { return p_; }
+  reference operator*() const { return reference(p_); }
+  reference operator[](std::ptrdiff_t i) const { return reference(p_ + i); }
+  device_ptr operator+(std::ptrdiff_t n) const { return device_ptr(p_ + n); }
+  device_ptr operator-(std::ptrdiff_t n) const { return device_ptr(p_ - n); }
+  std::ptrdiff_t operator-(const device_ptr &o) const { return p_ - o.p_; }
+  device_ptr &operator++() { ++p_; return *this; }
+  device_ptr operator++(int) { device_ptr t(*this); ++p_; return t; }
+  device_ptr &operator--() { --p_; return *this; }
+  device_ptr &operator+=(std::ptrdiff_t n) { p_ += n; return *this; }
+  bool operator==(const device_ptr &o) const { return p_ == o.p_; }
+  bool operator!=(const device_ptr &o) const { return p_ != o.p_; }
+  bool operator<(const device_ptr &o) const { return p_ < o.p_; }
+
+ private:
+  T *p_;
+};
+
+template <typename T>
+device_ptr<T> device_pointer_cast(T *p) {
+  return device_ptr<T>(p);
+}
+template <typename T>
+T *raw_pointer_cast(const device_ptr<T> &p) {
+  return p.get();
+}
+template <typename T>
+T *raw_pointer_cast(T *p) {
+  return p;
+}
+
+namespace detail {
+
+template <typename T>
+device_ptr<T> device_reference<T>::operator&() const {
+  return device_ptr<T>(p_);
+}
+
+// iterator -> (value type, memory space, raw pointer).  Raw pointers are host
+// iterators, exactly like in the reference (thrust's host system).
+template <typename Iterator>
+struct iter_traits;
+template <typename T>
+struct iter_traits<T *> {
+  typedef typename std::remove_const<T>::type value_type;
+  typedef T element_type;
+  typedef host_memory memory_space;
+  static T *raw(T *p) { return p; }
+};
+template <typename T>
+struct iter_traits<cusp::device_ptr<T>> {
+  typedef typename std::remove_const<T>::type value_type;
+  typedef T element_type;
+  typedef device_memory memory_space;
+  static T *raw(const cusp::device_ptr<T> &p) { return p.get(); }
+};
+#ifdef CUSP_B200_HAVE_THRUST
+template <typename T>
+struct iter_traits<thrust::device_ptr<T>> {
+  typedef typename std::remove_const<T>::type value_type;
+  typedef T element_type;
+  typedef device_memory memory_space;
+  static T *raw(const thrust::device_ptr<T> &p) { return thrust::raw_pointer_cast(p); }
+};
+#endif
 
 template <typename Space1, typename Space2>
 struct copy_kind;
@@ -79,6 +178,28 @@ inline void convert_copy(const U *src, T *dst, size_t n) {
   raw_copy<T, host_memory, DstSpace>(hd.data(), dst, n);
 }
 
+template <typename T, typename U, typename SrcSpace, typename DstSpace>
+inline void any_copy(const U *src, T *dst, size_t n) {
+  typedef typename std::remove_const<U>::type UU;
+  if (std::is_same<UU, T>::value)
+    raw_copy<T, SrcSpace, DstSpace>(reinterpret_cast<const T *>(src), dst, n);
+  else
+    convert_copy<T, UU, SrcSpace, DstSpace>(src, dst, n);
+}
+
+// raw pointer of any array1d / array1d_view (possibly const)
+template <typename Array>
+auto raw_ptr(Array &a) -> decltype(iter_traits<decltype(a.begin())>::raw(a.begin())) {
+  return iter_traits<decltype(a.begin())>::raw(a.begin());
+}
+
+template <typename Array>
+std::vector<typename Array::value_type> to_host_vector(const Array &a) {
+  std::vector<typename Array::value_type> h(a.size());
+  raw_copy<typename Array::value_type, typename Array::memory_space, host_memory>(raw_ptr(a), h.data(), a.size());
+  return h;
+}
+
 }  // namespace detail
 
 // ---------------------------------------------------------------------------
@@ -92,9 +213,12 @@ class array1d<T, host_memory> {
   typedef array1d_format format;
   typedef T *iterator;
   typedef const T *const_iterator;
+  typedef T *pointer;
   typedef T &reference;
-  typedef array1d_view<T, host_memory> view;
-  typedef array1d_view<const T, host_memory> const_view;
+  typedef size_t size_type;
+  typedef array1d container;
+  typedef array1d_view<iterator> view;
+  typedef array1d_view<const_iterator> const_view;
   template <typename Space>
   struct rebind {
     typedef array1d<T, Space> type;
@@ -106,11 +230,11 @@ class array1d<T, host_memory> {
   array1d(const array1d &o) : v_(o.v_) {}
   template <typename U, typename Space>
   array1d(const array1d<U, Space> &o) {
-    assign_from(o.data(), o.size(), Space());
+    assign_from(o);
   }
-  template <typename U, typename Space>
-  array1d(const array1d_view<U, Space> &o) {
-    assign_from(o.data(), o.size(), Space());
+  template <typename It>
+  array1d(const array1d_view<It> &o) {
+    assign_from(o);
   }
   template <typename It, typename = typename std::enable_if<!std::is_integral<It>::value>::type>
   array1d(It first, It last) : v_(first, last) {}
@@ -121,12 +245,12 @@ class array1d<T, host_memory> {
   }
   template <typename U, typename Space>
   array1d &operator=(const array1d<U, Space> &o) {
-    assign_from(o.data(), o.size(), Space());
+    assign_from(o);
     return *this;
   }
-  template <typename U, typename Space>
-  array1d &operator=(const array1d_view<U, Space> &o) {
-    assign_from(o.data(), o.size(), Space());
+  template <typename It>
+  array1d &operator=(const array1d_view<It> &o) {
+    assign_from(o);
     return *this;
   }
 
@@ -138,25 +262,29 @@ class array1d<T, host_memory> {
   void push_back(const T &x) { v_.push_back(x); }
   void clear() { v_.clear(); }
   void swap(array1d &o) { v_.swap(o.v_); }
+  void assign(size_t n, const T &value) { v_.assign(n, value); }
   T &operator[](size_t i) { return v_[i]; }
   const T &operator[](size_t i) const { return v_[i]; }
+  T &front() { return v_.front(); }
+  T &back() { return v_.back(); }
+  const T &back() const { return v_.back(); }
   T *data() { return v_.data(); }
   const T *data() const { return v_.data(); }
   iterator begin() { return v_.data(); }
   iterator end() { return v_.data() + v_.size(); }
   const_iterator begin() const { return v_.data(); }
   const_iterator end() const { return v_.data() + v_.size(); }
-  view subarray(size_t start, size_t num) { return view(data() + start, num); }
+  view subarray(size_t start, size_t num) { return view(begin() + start, begin() + start + num); }
+  const_view subarray(size_t start, size_t num) const {
+    return const_view(begin() + start, begin() + start + num);
+  }
 
  private:
-  template <typename U, typename Space>
-  void assign_from(const U *src, size_t n, Space) {
-    v_.resize(n);
-    typedef typename std::remove_const<U>::type UU;
-    if (std::is_same<UU, T>::value)
-      detail::raw_copy<T, Space, host_memory>(reinterpret_cast<const T *>(src), v_.data(), n);
-    else
-      detail::convert_copy<T, UU, Space, host_memory>(src, v_.data(), n);
+  template <typename A>
+  void assign_from(const A &o) {
+    v_.resize(o.size());
+    detail::any_copy<T, typename A::value_type, typename A::memory_space, host_memory>(detail::raw_ptr(o),
+                                                                                       v_.data(), o.size());
   }
   std::vector<T> v_;
 };
@@ -170,45 +298,62 @@ class array1d<T, device_memory> {
   typedef T value_type;
   typedef device_memory memory_space;
   typedef array1d_format format;
-  typedef T *iterator;  // raw device pointers (not dereferenceable on the host)
-  typedef const T *const_iterator;
+  typedef device_ptr<T> iterator;
+  typedef device_ptr<const T> const_iterator;
+  typedef device_ptr<T> pointer;
   typedef detail::device_reference<T> reference;
-  typedef array1d_view<T, device_memory> view;
-  typedef array1d_view<const T, device_memory> const_view;
+  typedef size_t size_type;
+  typedef array1d container;
+  typedef array1d_view<iterator> view;
+  typedef array1d_view<const_iterator> const_view;
   template <typename Space>
   struct rebind {
     typedef array1d<T, Space> type;
   };
 
   array1d() {}
-  explicit array1d(size_t n) { resize(n); fill_bytes_zero(); }
+  explicit array1d(size_t n) {
+    resize(n);
+    if (n_) detail::cuda_check(cudaMemset(p_, 0, n_ * sizeof(T)), "cusp::array1d<device> zero fill");
+  }
   array1d(size_t n, const T &value) {
     resize(n);
-    fill(value);
+    fill_range(0, n_, value);
   }
-  array1d(const array1d &o) { assign_from(o.data(), o.size(), device_memory()); }
+  array1d(const array1d &o) { assign_from(o); }
+  array1d(array1d &&o) noexcept : p_(o.p_), n_(o.n_), cap_(o.cap_) { o.p_ = nullptr; o.n_ = o.cap_ = 0; }
   template <typename U, typename Space>
   array1d(const array1d<U, Space> &o) {
-    assign_from(o.data(), o.size(), Space());
+    assign_from(o);
   }
-  template <typename U, typename Space>
-  array1d(const array1d_view<U, Space> &o) {
-    assign_from(o.data(), o.size(), Space());
+  template <typename It>
+  array1d(const array1d_view<It> &o) {
+    assign_from(o);
+  }
+  template <typename It, typename = typename std::enable_if<!std::is_integral<It>::value>::type>
+  array1d(It first, It last) {
+    std::vector<T> h(first, last);
+    resize(h.size());
+    detail::raw_copy<T, host_memory, device_memory>(h.data(), p_, n_);
   }
   ~array1d() { release(); }
 
   array1d &operator=(const array1d &o) {
-    if (this != &o) assign_from(o.data(), o.size(), device_memory());
+    if (this != &o) assign_from(o);
+    return *this;
+  }
+  array1d &operator=(array1d &&o) noexcept {
+    swap(o);
     return *this;
   }
   template <typename U, typename Space>
   array1d &operator=(const array1d<U, Space> &o) {
-    assign_from(o.data(), o.size(), Space());
+    assign_from(o);
     return *this;
   }
-  template <typename U, typename Space>
-  array1d &operator=(const array1d_view<U, Space> &o) {
-    assign_from(o.data(), o.size(), Space());
+  template <typename It>
+  array1d &operator=(const array1d_view<It> &o) {
+    assign_from(o);
     return *this;
   }
 
@@ -230,10 +375,11 @@ class array1d<T, device_memory> {
   void resize(size_t n, const T &value) {
     const size_t old = n_;
     resize(n);
-    if (n > old) {
-      std::vector<T> h(n - old, value);
-      detail::raw_copy<T, host_memory, device_memory>(h.data(), p_ + old, n - old);
-    }
+    if (n > old) fill_range(old, n, value);
+  }
+  void assign(size_t n, const T &value) {
+    resize(n);
+    fill_range(0, n, value);
   }
   void push_back(const T &x) {
     if (n_ == cap_) reserve(cap_ ? 2 * cap_ : 16);
@@ -247,32 +393,29 @@ class array1d<T, device_memory> {
     std::swap(cap_, o.cap_);
   }
   reference operator[](size_t i) { return reference(p_ + i); }
-  T operator[](size_t i) const { return (T)detail::device_reference<T>(p_ + i); }
-  T *data() { return p_; }
-  const T *data() const { return p_; }
-  iterator begin() { return p_; }
-  iterator end() { return p_ + n_; }
-  const_iterator begin() const { return p_; }
-  const_iterator end() const { return p_ + n_; }
-  view subarray(size_t start, size_t num) { return view(p_ + start, num); }
+  T operator[](size_t i) const { return (T)detail::device_reference<const T>(p_ + i); }
+  pointer data() { return pointer(p_); }
+  device_ptr<const T> data() const { return device_ptr<const T>(p_); }
+  iterator begin() { return iterator(p_); }
+  iterator end() { return iterator(p_ + n_); }
+  const_iterator begin() const { return const_iterator(p_); }
+  const_iterator end() const { return const_iterator(p_ + n_); }
+  view subarray(size_t start, size_t num) { return view(begin() + start, begin() + start + num); }
+  const_view subarray(size_t start, size_t num) const {
+    return const_view(begin() + start, begin() + start + num);
+  }
 
  private:
-  void fill(const T &value) {
-    if (!n_) return;
-    std::vector<T> h(n_, value);
-    detail::raw_copy<T, host_memory, device_memory>(h.data(), p_, n_);
+  void fill_range(size_t lo, size_t hi, const T &value) {
+    if (hi <= lo) return;
+    std::vector<T> h(hi - lo, value);
+    detail::raw_copy<T, host_memory, device_memory>(h.data(), p_ + lo, hi - lo);
   }
-  void fill_bytes_zero() {
-    if (n_) detail::cuda_check(cudaMemset(p_, 0, n_ * sizeof(T)), "cusp::array1d<device> zero fill");
-  }
-  template <typename U, typename Space>
-  void assign_from(const U *src, size_t n, Space) {
-    resize(n);
-    typedef typename std::remove_const<U>::type UU;
-    if (std::is_same<UU, T>::value)
-      detail::raw_copy<T, Space, device_memory>(reinterpret_cast<const T *>(src), p_, n);
-    else
-      detail::convert_copy<T, UU, Space, device_memory>(src, p_, n);
+  template <typename A>
+  void assign_from(const A &o) {
+    resize(o.size());
+    detail::any_copy<T, typename A::value_type, typename A::memory_space, device_memory>(detail::raw_ptr(o), p_,
+                                                                                         o.size());
   }
   void release() {
     if (p_) cudaFree(p_);
@@ -284,80 +427,110 @@ class array1d<T, device_memory> {
 };
 
 // ---------------------------------------------------------------------------
-// non-owning view over [first, first+n) in a memory space
-// (the reference's array1d_view<Iterator>; examples/Views/cg_raw.cu wraps raw
-// device pointers this way)
+// non-owning view over [first, last)   (cusp/array1d.h:361-517)
 // ---------------------------------------------------------------------------
-template <typename T, typename MemorySpace>
+template <typename Iterator>
 class array1d_view {
- public:
-  typedef typename std::remove_const<T>::type value_type;
-  typedef MemorySpace memory_space;
-  typedef array1d_format format;
-  typedef T *iterator;
-  typedef array1d_view view;
+  typedef detail::iter_traits<Iterator> traits;
 
-  array1d_view() : p_(nullptr), n_(0) {}
-  array1d_view(T *first, size_t n) : p_(first), n_(n) {}
-  array1d_view(T *first, T *last) : p_(first), n_((size_t)(last - first)) {}
-  array1d_view(array1d<value_type, MemorySpace> &a) : p_(a.data()), n_(a.size()) {}
-  array1d_view(const array1d<value_type, MemorySpace> &a) : p_(const_cast<T *>(a.data())), n_(a.size()) {}
+ public:
+  typedef Iterator iterator;
+  typedef Iterator const_iterator;
+  typedef typename traits::value_type value_type;
+  typedef typename traits::memory_space memory_space;
+  typedef array1d_format format;
+  typedef size_t size_type;
+  typedef array1d<value_type, memory_space> container;
+  typedef array1d_view view;
+  typedef array1d_view const_view;
+  typedef decltype(std::declval<Iterator>()[0]) reference;
+
+  array1d_view() : first_(), n_(0), cap_(0) {}
+  array1d_view(Iterator first, Iterator last) : first_(first), n_((size_t)(last - first)), cap_(n_) {}
+  array1d_view(const array1d_view &o) = default;
+  // from a container or another view whose iterator converts to ours
+  template <typename Array, typename = typename std::enable_if<
+                                std::is_convertible<decltype(std::declval<Array &>().begin()), Iterator>::value &&
+                                !std::is_same<typename std::decay<Array>::type, array1d_view>::value>::type>
+  array1d_view(Array &a) : first_(a.begin()), n_(a.size()), cap_(a.size()) {}
+
+  // views assign element-wise (like the reference: view = array copies data)
+  array1d_view &operator=(const array1d_view &o) = default;
 
   size_t size() const { return n_; }
-  T *data() const { return p_; }
-  T *begin() const { return p_; }
-  T *end() const { return p_ + n_; }
+  size_t capacity() const { return cap_; }
+  bool empty() const { return n_ == 0; }
+  Iterator begin() const { return first_; }
+  Iterator end() const { return first_ + (std::ptrdiff_t)n_; }
+  Iterator data() const { return first_; }
+  reference operator[](size_t i) const { return first_[(std::ptrdiff_t)i]; }
+  reference front() const { return first_[0]; }
+  reference back() const { return first_[(std::ptrdiff_t)n_ - 1]; }
+  // cusp/detail/array1d.inl: a view may shrink or grow back up to its capacity
   void resize(size_t n) {
-    if (n > n_) throw cusp::not_implemented_exception("array1d_view cannot resize() larger than the wrapped range");
+    if (n > cap_) throw cusp::not_implemented_exception("array1d_view cannot resize() larger than capacity()");
     n_ = n;
   }
-  // host views index directly; device views through a proxy
-  template <typename S = MemorySpace>
-  typename std::enable_if<std::is_same<S, host_memory>::value, T &>::type operator[](size_t i) const {
-    return p_[i];
-  }
-  template <typename S = MemorySpace>
-  typename std::enable_if<std::is_same<S, device_memory>::value, detail::device_reference<value_type>>::type
-  operator[](size_t i) const {
-    return detail::device_reference<value_type>(const_cast<value_type *>(p_) + i);
+  array1d_view subarray(size_t start, size_t num) const {
+    return array1d_view(first_ + (std::ptrdiff_t)start, first_ + (std::ptrdiff_t)(start + num));
   }
 
  private:
-  T *p_;
-  size_t n_;
+  Iterator first_;
+  size_t n_, cap_;
 };
 
-template <typename T, typename Space>
-array1d_view<T, Space> make_array1d_view(array1d<T, Space> &a) {
-  return array1d_view<T, Space>(a);
+template <typename Iterator>
+array1d_view<Iterator> make_array1d_view(Iterator first, Iterator last) {
+  return array1d_view<Iterator>(first, last);
 }
-template <typename Space, typename T>
-array1d_view<T, Space> make_array1d_view(T *first, T *last) {
-  return array1d_view<T, Space>(first, last);
+template <typename T, typename Space>
+typename array1d<T, Space>::view make_array1d_view(array1d<T, Space> &a) {
+  return typename array1d<T, Space>::view(a);
+}
+template <typename T, typename Space>
+typename array1d<T, Space>::const_view make_array1d_view(const array1d<T, Space> &a) {
+  return typename array1d<T, Space>::const_view(a);
+}
+template <typename Iterator>
+array1d_view<Iterator> make_array1d_view(const array1d_view<Iterator> &a) {
+  return a;
 }
 
-// equality across memory spaces (testing uses ASSERT_EQUAL(device_array, host_array))
+// ---------------------------------------------------------------------------
+// equality across memory spaces (the unit tests compare device and host arrays)
+// ---------------------------------------------------------------------------
 namespace detail {
-template <typename A>
-std::vector<typename A::value_type> to_host_vector(const A &a) {
-  std::vector<typename A::value_type> h(a.size());
-  raw_copy<typename A::value_type, typename A::memory_space, host_memory>(a.data(), h.data(), a.size());
-  return h;
+template <typename A, typename B>
+bool arrays_equal(const A &a, const B &b) {
+  if (a.size() != b.size()) return false;
+  auto ha = to_host_vector(a);
+  auto hb = to_host_vector(b);
+  for (size_t i = 0; i < ha.size(); ++i)
+    if (!(ha[i] == hb[i])) return false;
+  return true;
 }
 }  // namespace detail
 
 template <typename T1, typename S1, typename T2, typename S2>
 bool operator==(const array1d<T1, S1> &a, const array1d<T2, S2> &b) {
-  if (a.size() != b.size()) return false;
-  auto ha = detail::to_host_vector(a);
-  auto hb = detail::to_host_vector(b);
-  for (size_t i = 0; i < ha.size(); ++i)
-    if (!(ha[i] == hb[i])) return false;
-  return true;
+  return detail::arrays_equal(a, b);
 }
 template <typename T1, typename S1, typename T2, typename S2>
 bool operator!=(const array1d<T1, S1> &a, const array1d<T2, S2> &b) {
-  return !(a == b);
+  return !detail::arrays_equal(a, b);
+}
+template <typename T1, typename S1, typename It>
+bool operator==(const array1d<T1, S1> &a, const array1d_view<It> &b) {
+  return detail::arrays_equal(a, b);
+}
+template <typename T1, typename S1, typename It>
+bool operator==(const array1d_view<It> &a, const array1d<T1, S1> &b) {
+  return detail::arrays_equal(a, b);
+}
+template <typename It1, typename It2>
+bool operator==(const array1d_view<It1> &a, const array1d_view<It2> &b) {
+  return detail::arrays_equal(a, b);
 }
 
 }  // namespace cusp
