@@ -28,6 +28,10 @@ inline size_t round_up(size_t n, size_t k) { return k ? k * ((n + k - 1) / k) : 
 template <typename ArrayView, typename Orientation>
 class array2d_view;
 
+// defined in cusp/convert.h
+template <typename SourceType, typename DestinationType>
+void convert(const SourceType &src, DestinationType &dst);
+
 template <typename T, typename MemorySpace, typename Orientation = row_major>
 class array2d {
  public:
@@ -60,6 +64,18 @@ class array2d {
   template <typename U, typename Space>
   array2d(const array2d<U, Space, Orientation> &o)
       : num_rows(o.num_rows), num_cols(o.num_cols), num_entries(o.num_entries), pitch(o.pitch), values(o.values) {}
+  // dense image of any sparse matrix (cusp/detail/array2d.inl:100-126 -> cusp::convert)
+  template <typename MatrixType,
+            typename = typename std::enable_if<std::is_base_of<sparse_format, typename MatrixType::format>::value>::type>
+  array2d(const MatrixType &m) {
+    cusp::convert(m, *this);
+  }
+  template <typename MatrixType,
+            typename = typename std::enable_if<std::is_base_of<sparse_format, typename MatrixType::format>::value>::type>
+  array2d &operator=(const MatrixType &m) {
+    cusp::convert(m, *this);
+    return *this;
+  }
   template <typename U, typename Space>
   array2d &operator=(const array2d<U, Space, Orientation> &o) {
     num_rows = o.num_rows;

@@ -10,6 +10,7 @@
 
 #include "../../b200sp.h"
 #include "../exception.h"
+#include "../memory.h"
 
 namespace cusp {
 namespace detail {
@@ -63,7 +64,7 @@ struct dtype_of<double> {
 
 namespace cuda {
 // cusp::cuda::par.on(stream): run subsequent device calls of this thread on `stream`
-struct par_t {
+struct par_t : cusp::execution_policy<par_t> {
   const par_t &on(cudaStream_t s) const {
     cusp::detail::current_stream() = (b200sp_stream)s;
     return *this;

@@ -1,0 +1,171 @@
+// cusp/ktt/ktt.h — the fork's autotuning API
+// (reference: cusp/ktt/ktt.h:14-127, cusp/ktt/detail/ktt.inl:20-142,
+// cusp/system/cuda/ktt/multiply.h:27-153).
+//
+//   enable() / disable()          the switch read by plain cusp::multiply for ELL / DIA
+//   get_tuner()                   process-wide ::ktt::Tuner stand-in (logging, CreateConfiguration)
+//   multiply(A, x, y)             one step of dynamic tuning            -> b200sp_tune_step
+//   multiply(A, x, y, conf)       run exactly `conf`                    -> b200sp_spmv(cfg)
+//   tune(A, x, y[, ref, stop, searcher])  offline tuning with validation -> b200sp_tune
+//   reset_tuning(A, x, y)         forget results for A's kernel         -> b200sp_tune_reset
+//
+// Every configuration is a precompiled sm_100a instantiation: a tuning step costs
+// a launch, not an NVRTC compile.  Works for csr / coo / ell / dia / hyb / ellr
+// matrices in device_memory (the reference's KTT glue covers csr, coo, ell, dia, ellr).
+#pragma once
+#include <memory>
+#include <optional>
+#include <string>
+#include <vector>
+
+#include "../array1d.h"
+#include "../detail/descriptor.h"
+#include "ktt_types.h"
+#include "state.h"
+
+namespace cusp {
+
+namespace system {
+namespace cuda {
+namespace ktt {
+// cuda/ktt/kernel.h: what get_kernel() hands back (main.cu:448,510 read kernel_id)
+struct kernel_context {
+  ::ktt::KernelId kernel_id = 0;
+  std::string name;
+};
+inline const char *format_name(b200sp_format f) {
+  switch (f) {
+    case B200SP_FMT_CSR: return "csr_spmv";
+    case B200SP_FMT_ELL: return "ell_spmv";
+    case B200SP_FMT_DIA: return "dia_spmv";
+    case B200SP_FMT_COO: return "coo_spmv";
+    case B200SP_FMT_HYB: return "hyb_spmv";
+    default: return "ellr_spmv";
+  }
+}
+template <typename Matrix, typename V1, typename V2>
+kernel_context get_kernel(::ktt::Tuner &, const Matrix &A, const V1 &, const V2 &) {
+  b200sp_matrix d = cusp::detail::describe(A);
+  kernel_context k;
+  k.kernel_id = (::ktt::KernelId)d.format * 2 + (::ktt::KernelId)d.dtype;
+  k.name = format_name(d.format);
+  return k;
+}
+}  // namespace ktt
+}  // namespace cuda
+}  // namespace system
+
+namespace ktt {
+
+inline ::ktt::Tuner &get_tuner() {
+  static ::ktt::Tuner tuner;
+  return tuner;
+}
+
+namespace detail {
+using cusp::detail::check;
+using cusp::detail::current_stream;
+using cusp::detail::describe;
+using cusp::detail::engine;
+using cusp::detail::raw_ptr;
+
+template <typename Matrix, typename V1, typename V2>
+void require_device(const Matrix &A, const V1 &x, const V2 &y) {
+  static_assert(cusp::detail::abi_matrix<Matrix>::value,
+                "cusp::ktt: device_memory sparse matrix with 32-bit indices and float/double values required");
+  static_assert(std::is_same<typename V1::memory_space, cusp::device_memory>::value &&
+                    std::is_same<typename V2::memory_space, cusp::device_memory>::value,
+                "cusp::ktt: x and y must be device arrays");
+  if (A.num_cols != x.size() || A.num_rows != y.size())
+    throw cusp::invalid_input_exception("cusp::ktt: matrix and vector dimensions do not match");
+}
+}  // namespace detail
+
+// one step of dynamic autotuning (cuda/ktt/multiply.h:56-77)
+template <typename Matrix, typename V1, typename V2>
+::ktt::KernelResult multiply(const Matrix &A, const V1 &x, V2 &y) {
+  detail::require_device(A, x, y);
+  b200sp_matrix d = detail::describe(A);
+  b200sp_tune_result r;
+  detail::check(
+      b200sp_tune_step(detail::engine(), detail::current_stream(), &d, detail::raw_ptr(x), detail::raw_ptr(y), &r));
+  return ::ktt::KernelResult(cusp::system::cuda::ktt::format_name(d.format), r);
+}
+
+// run one given configuration (cuda/ktt/multiply.h:79-104); timed with CUDA events
+template <typename Matrix, typename V1, typename V2>
+::ktt::KernelResult multiply(const Matrix &A, const V1 &x, V2 &y, const ::ktt::KernelConfiguration &configuration,
+                             bool run_with_profiling = false) {
+  (void)run_with_profiling;  // CUPTI counters: use ncu on the precompiled kernels instead
+  detail::require_device(A, x, y);
+  b200sp_matrix d = detail::describe(A);
+  cudaStream_t s = (cudaStream_t)detail::current_stream();
+  cudaEvent_t e0, e1;
+  cusp::detail::cuda_check(cudaEventCreate(&e0), "cudaEventCreate");
+  cusp::detail::cuda_check(cudaEventCreate(&e1), "cudaEventCreate");
+  cudaEventRecord(e0, s);
+  b200sp_status st =
+      b200sp_spmv(detail::engine(), detail::current_stream(), &d, detail::raw_ptr(x), detail::raw_ptr(y), 0,
+                  &configuration.cfg());
+  cudaEventRecord(e1, s);
+  cudaEventSynchronize(e1);
+  b200sp_tune_result r;
+  r.cfg = configuration.cfg();
+  r.max_rel_error = 0;
+  r.milliseconds = 0;
+  cudaEventElapsedTime(&r.milliseconds, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  r.status = st == B200SP_OK ? B200SP_TUNE_OK : (st == B200SP_INVALID_INPUT ? B200SP_TUNE_UNSUPPORTED
+                                                                            : B200SP_TUNE_LAUNCH_FAILED);
+  return ::ktt::KernelResult(cusp::system::cuda::ktt::format_name(d.format), r);
+}
+
+// offline tuning over the whole space, each configuration validated
+// (cuda/ktt/multiply.h:106-153).  reference_computation fills a host buffer of
+// y.size() values with the expected result; without it the engine-default
+// configuration's output is the reference.
+template <typename Matrix, typename V1, typename V2>
+std::vector<::ktt::KernelResult> tune(const Matrix &A, const V1 &x, V2 &y,
+                                      std::optional<::ktt::ReferenceComputation> reference_computation = std::nullopt,
+                                      std::unique_ptr<::ktt::StopCondition> stop_condition = nullptr,
+                                      std::unique_ptr<::ktt::Searcher> searcher = nullptr) {
+  (void)searcher;
+  typedef typename V2::value_type T;
+  detail::require_device(A, x, y);
+  b200sp_matrix d = detail::describe(A);
+  const int64_t space = b200sp_cfg_space(d.format, d.dtype, nullptr, 0);
+  std::vector<b200sp_tune_result> raw((size_t)std::max<int64_t>(space, 1));
+  cusp::array1d<T, cusp::device_memory> y_ref;
+  const void *ref_ptr = nullptr;
+  if (reference_computation) {
+    std::vector<T> host_ref(y.size());
+    (*reference_computation)((void *)host_ref.data());
+    y_ref = cusp::array1d<T, cusp::device_memory>(host_ref.begin(), host_ref.end());
+    ref_ptr = detail::raw_ptr(y_ref);
+  }
+  int64_t n = 0;
+  b200sp_cfg best;
+  const double tol = std::is_same<T, float>::value ? 1e-5 : 1e-12;  // north-star parity bound
+  detail::check(b200sp_tune(detail::engine(), detail::current_stream(), &d, detail::raw_ptr(x), detail::raw_ptr(y),
+                            ref_ptr, tol, 3, raw.data(), (int64_t)raw.size(), &n, &best));
+  std::vector<::ktt::KernelResult> results;
+  if (stop_condition) stop_condition->Initialize((uint64_t)n);
+  const char *name = cusp::system::cuda::ktt::format_name(d.format);
+  for (int64_t i = 0; i < n; ++i) {
+    if (stop_condition && stop_condition->IsFulfilled()) break;
+    results.emplace_back(name, raw[(size_t)i]);
+    if (stop_condition) stop_condition->Update(results.back());
+  }
+  if (stop_condition) get_tuner().log() << stop_condition->GetStatusString() << std::endl;
+  return results;
+}
+
+template <typename MatrixType, typename V1, typename V2>
+void reset_tuning(const MatrixType &A, const V1 &, V2 &) {
+  b200sp_matrix d = detail::describe(A);
+  detail::check(b200sp_tune_reset(detail::engine(), &d));
+}
+
+}  // namespace ktt
+}  // namespace cusp
