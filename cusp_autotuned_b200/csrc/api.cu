@@ -100,6 +100,12 @@ static std::vector<b200sp_cfg> cfg_space_vec(b200sp_format f, b200sp_dtype) {
           if (b == 512 && u == 16) continue;
           push(v, B200SP_K_CSR_STREAM, b, 0, u, 0, 0);
         }
+      {
+        const int bu[5][2] = {{128, 4}, {128, 8}, {128, 16}, {256, 4}, {256, 8}};
+        for (auto &p : bu)
+          for (int st : {2, 3, 4})
+            for (int cps : {2, 4, 6}) push(v, B200SP_K_CSR_RING, p[0], 0, p[1], st, cps);
+      }
       break;
     case B200SP_FMT_ELL:
     case B200SP_FMT_ELLR:

@@ -266,6 +266,231 @@ __global__ void __launch_bounds__(BLOCK) csr_stream_kernel(CsrArgs<T> a, int R, 
   }
 }
 
+// ---------------------------------------------------------------------------
+// K_CSR_RING — persistent, pipelined version of the stream kernel.
+//
+// grid = ctas_per_sm x 148 persistent CTAs of BLOCK consumer threads + one
+// producer warp.  Tiles of R consecutive rows (R <= BLOCK, chosen on the host so
+// that a tile's nnz fill ~one ring stage) are dealt round-robin.  For each tile the
+// producer thread issues two cp.async.bulk copies (TMA engine, L2 evict-first) of
+// the tile's contiguous [Ap[r0], Ap[r0+R)) range of Aj and Ax into the next free
+// stage of an mbarrier ring, up to `stages` tiles ahead of the consumers; tiles
+// with more entries than a stage holds (power-law hubs) become several chunks.
+// Consumers: thread-per-row in the reference's entry order (bit-identical to
+// csr_spmv.h:35-74 with -fmad=false), x through ld.global.nc, 8 gathers in
+// flight; next tile's row offsets are prefetched while the current one is
+// processed.  A row piece longer than CSR_LONG inside a chunk is reduced by its
+// whole warp (only the grouping of that piece changes).  The column ring is
+// zero-filled once, so slots past a row's end always hold a valid column and the
+// gather needs no clamp; their products are discarded by a select.
+// ---------------------------------------------------------------------------
+template <typename T, int BLOCK, int NPT>
+__global__ void __launch_bounds__(BLOCK + 32) csr_ring_kernel(CsrArgs<T> a, int R, int stages, i64 num_tiles) {
+  constexpr int CAP = BLOCK * NPT;   // entries per stage
+  constexpr int STR = CAP + 16;      // stage stride (alignment shift + read-ahead slack)
+  constexpr int EPV = 16 / (int)sizeof(T);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T *s_val = reinterpret_cast<T *>(smem_raw);
+  int *s_col = reinterpret_cast<int *>(smem_raw + (size_t)stages * STR * sizeof(T));
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)stages * STR * (sizeof(T) + sizeof(int)));
+  uint64_t *empty = full + stages;
+  __shared__ T s_red[32];
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], BLOCK / 32);
+    }
+    mbar_fence_init();
+  }
+  for (int i = tid; i < stages * STR; i += BLOCK + 32) s_col[i] = 0;
+  __syncthreads();
+
+  const i64 rows = a.rows;
+  const int nnz = (int)a.nnz;
+  T dsum = 0;
+
+  if (tid >= BLOCK) {
+    // ------------------------------ producer --------------------------------
+    if (tid == BLOCK) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const uint64_t pol = l2_policy_evict_first();
+      const int nnz_c = nnz & ~3, nnz_v = nnz & ~(EPV - 1);  // last 16-byte-complete entry
+      int s = 0;
+      uint32_t ph = 0;
+      i64 tile = blockIdx.x;
+      int s0 = 0, s1 = 0;
+      if (tile < num_tiles) {
+        s0 = ld_ro(a.Ap + tile * R);
+        s1 = ld_ro(a.Ap + min(tile * R + R, rows));
+      }
+      while (tile < num_tiles) {
+        const i64 next = tile + gridDim.x;
+        int n0 = 0, n1 = 0;
+        if (next < num_tiles) {  // bounds of the next tile: in flight while this one is issued
+          n0 = ld_ro(a.Ap + next * R);
+          n1 = ld_ro(a.Ap + min(next * R + R, rows));
+        }
+        for (int lo = s0; lo < s1; lo += CAP) {
+          const int hi = min(lo + CAP, s1);
+          mbar_wait(&empty[s], ph ^ 1);
+          int *dc = s_col + (size_t)s * STR;
+          T *dv = s_val + (size_t)s * STR;
+          const int ga_c = lo & ~3, ga_v = lo & ~(EPV - 1);
+          const int end_c = min((hi + 3) & ~3, nnz_c), end_v = min((hi + EPV - 1) & ~(EPV - 1), nnz_v);
+          // the (at most 3) entries after the last complete 16 bytes of the arrays
+          for (int j = max(end_c, ga_c); j < hi; ++j) dc[j - ga_c] = a.Aj[j];
+          for (int j = max(end_v, ga_v); j < hi; ++j) dv[j - ga_v] = a.Ax[j];
+          const int bc = max(end_c - ga_c, 0), bv = max(end_v - ga_v, 0);
+          mbar_expect_tx(&full[s], (uint32_t)(bc * sizeof(int) + bv * sizeof(T)));
+          if (bc > 0) bulk_g2s(dc, a.Aj + ga_c, (uint32_t)(bc * sizeof(int)), &full[s], pol);
+          if (bv > 0) bulk_g2s(dv, a.Ax + ga_v, (uint32_t)(bv * sizeof(T)), &full[s], pol);
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+        tile = next;
+        s0 = n0;
+        s1 = n1;
+      }
+    }
+  } else {
+    // ------------------------------ consumers -------------------------------
+    const int lane = tid & 31;
+    int s = 0;
+    uint32_t ph = 0;
+    i64 tile = blockIdx.x;
+    int b_i = 0, e_i = 0, s0 = 0, s1 = 0;
+    if (tile < num_tiles) {
+      const i64 r = tile * R + tid;
+      if (tid < R && r < rows) {
+        b_i = ld_ro(a.Ap + r);
+        e_i = ld_ro(a.Ap + r + 1);
+      }
+      s0 = ld_ro(a.Ap + tile * R);
+      s1 = ld_ro(a.Ap + min(tile * R + R, rows));
+    }
+    while (tile < num_tiles) {
+      const i64 r = tile * R + tid;
+      const bool valid = tid < R && r < rows;
+      const i64 next = tile + gridDim.x;
+      int nb = 0, ne = 0, n0 = 0, n1 = 0;
+      if (next < num_tiles) {
+        const i64 rn = next * R + tid;
+        if (tid < R && rn < rows) {
+          nb = ld_ro(a.Ap + rn);
+          ne = ld_ro(a.Ap + rn + 1);
+        }
+        n0 = ld_ro(a.Ap + next * R);
+        n1 = ld_ro(a.Ap + min(next * R + R, rows));
+      }
+      T acc = (valid && a.accumulate) ? a.y[r] : T(0);
+      for (int lo = s0; lo < s1; lo += CAP) {
+        const int hi = min(lo + CAP, s1);
+        mbar_wait(&full[s], ph);
+        const int *pc = s_col + (size_t)s * STR + (lo & 3) - lo;           // pc[j], absolute entry index j
+        const T *pv = s_val + (size_t)s * STR + (lo & (EPV - 1)) - lo;
+        const int b = max(b_i, lo), e = min(e_i, hi);
+        const int len = e - b;
+        if (len > 0 && len <= CSR_LONG) {
+          T t = acc;
+          for (int j = b; j < e; j += CSR_GU) {
+            int c[CSR_GU];
+            T xv[CSR_GU];
+#pragma unroll
+            for (int q = 0; q < CSR_GU; ++q) c[q] = pc[j + q];
+#pragma unroll
+            for (int q = 0; q < CSR_GU; ++q) xv[q] = ld_ro(a.x + (unsigned)c[q]);
+#pragma unroll
+            for (int q = 0; q < CSR_GU; ++q) {
+              pin(xv[q]);
+              const T u = t + pv[j + q] * xv[q];
+              t = (j + q < e) ? u : t;
+            }
+          }
+          acc = t;
+        }
+        unsigned long_mask = __ballot_sync(0xffffffffu, len > CSR_LONG);
+        while (long_mask) {  // warp-uniform: hub pieces, the whole warp on one row piece
+          const int src = __ffs(long_mask) - 1;
+          long_mask &= long_mask - 1;
+          const int lb = __shfl_sync(0xffffffffu, b, src), le = __shfl_sync(0xffffffffu, e, src);
+          T part = T(0);
+          for (int j = lb + lane; j < le; j += 32) part = part + pv[j] * ld_ro(a.x + (unsigned)pc[j]);
+          part = warp_sum(part);
+          part = __shfl_sync(0xffffffffu, part, 0);
+          if (lane == src) acc = acc + part;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+      if (valid) {
+        a.y[r] = acc;
+        if (a.dotv) dsum = dsum + acc * ld_ro(a.dotv + r);
+      }
+      tile = next;
+      b_i = nb;
+      e_i = ne;
+      s0 = n0;
+      s1 = n1;
+    }
+  }
+  if (a.dotv) {
+    if (tid >= BLOCK) dsum = 0;
+    T bs = block_sum<BLOCK + 32>(dsum, s_red);
+    grid_reduce_finish<BLOCK + 32>(bs, a.dot_partials, a.dot_ticket, s_red,
+                                   [&](T total) { *a.dot_result = total; });
+  }
+}
+
+template <typename T, int BLOCK, int NPT>
+static b200sp_status launch_ring(b200sp_handle h, cudaStream_t st, CsrArgs<T> a, int stages, int ctas_per_sm) {
+  constexpr int CAP = BLOCK * NPT;
+  const double mean = (double)a.nnz / (double)a.rows;
+  // rows per tile: ~90 % of a stage at the mean row length, one row per consumer thread at most
+  i64 R = (i64)(0.9 * (double)CAP / (mean > 1.0 ? mean : 1.0));
+  R = (R / 32) * 32;
+  if (R < 32) R = 32;
+  if (R > BLOCK) R = BLOCK;
+  const i64 num_tiles = ceil_div(a.rows, R);
+  const size_t smem = (size_t)stages * (CAP + 16) * (sizeof(T) + sizeof(int)) + 2 * (size_t)stages * sizeof(uint64_t) + 16;
+  if (smem > (size_t)h->max_smem_optin)
+    return set_error(h, B200SP_INVALID_INPUT, "csr ring: %zu B smem exceeds %d", smem, h->max_smem_optin);
+  auto kern = csr_ring_kernel<T, BLOCK, NPT>;
+  B200SP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // persistent grid: never more CTAs than are resident at once (a second wave would
+  // start only when a first-wave CTA has finished ALL of its tiles)
+  int resident = 0;
+  B200SP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, BLOCK + 32, smem));
+  if (resident < 1) return set_error(h, B200SP_INVALID_INPUT, "csr ring: configuration does not fit on an SM");
+  i64 grid = (i64)h->num_sms * (ctas_per_sm < resident ? ctas_per_sm : resident);
+  if (grid > num_tiles) grid = num_tiles;
+  if (a.dotv && grid > RED_MAX_PARTIALS)
+    return set_error(h, B200SP_INVALID_INPUT, "csr: too many CTAs for fused dot");
+  kern<<<(unsigned)grid, BLOCK + 32, smem, st>>>(a, (int)R, stages, num_tiles);
+  B200SP_LAUNCH_CHECK(h, "csr_ring_kernel");
+  return B200SP_OK;
+}
+
+template <typename T>
+static b200sp_status dispatch_ring(b200sp_handle h, cudaStream_t st, const CsrArgs<T> &a, int block, int npt,
+                                   int stages, int cps) {
+  if (stages < 2 || stages > 8 || cps < 1 || cps > 16)
+    return set_error(h, B200SP_INVALID_INPUT, "csr ring: unsupported stages=%d ctas_per_sm=%d", stages, cps);
+#define CASE(B, N) \
+  if (block == B && npt == N) return launch_ring<T, B, N>(h, st, a, stages, cps);
+  CASE(128, 4) CASE(128, 8) CASE(128, 16)
+  CASE(256, 4) CASE(256, 8)
+#undef CASE
+  return set_error(h, B200SP_INVALID_INPUT, "csr ring: unsupported block_size=%d unroll=%d", block, npt);
+}
+
 template <typename T, int BLOCK, int NPT>
 static b200sp_status launch_stream(b200sp_handle h, cudaStream_t st, CsrArgs<T> a) {
   constexpr int CAP = BLOCK * NPT;
@@ -325,23 +550,39 @@ static b200sp_status dispatch_tpr(b200sp_handle h, cudaStream_t st, const CsrArg
 }
 
 static void csr_defaults(b200sp_cfg &c, i64 rows, i64 nnz, size_t elem) {
-  if (c.kernel == 0) c.kernel = B200SP_K_CSR_STREAM;
+  const double mean = rows > 0 ? (double)nnz / (double)rows : 0.0;
+  if (c.kernel == 0) {
+    // round-1 sweeps on B200 (profiles/r01_sweep_*.md): short rows -> thread-per-row from a
+    // TMA-staged ring (RING; STREAM when the matrix is too small to fill persistent CTAs);
+    // longer rows -> lane-per-entry sub-warps (VECTOR).  cusp::ktt::tune refines per matrix.
+    if (mean <= 12.0)
+      c.kernel = (rows >= (i64)B200SP_NUM_SMS_FALLBACK * 4 * 256 * 2) ? B200SP_K_CSR_RING : B200SP_K_CSR_STREAM;
+    else
+      c.kernel = B200SP_K_CSR_VECTOR;
+  }
+  if (c.kernel == B200SP_K_CSR_RING) {
+    if (c.block_size == 0) c.block_size = 256;
+    if (c.unroll == 0) c.unroll = 8;
+    if (c.stages == 0) c.stages = 2;
+    if (c.ctas_per_sm == 0) c.ctas_per_sm = 4;
+    return;
+  }
   if (c.kernel == B200SP_K_CSR_STREAM) {
-    // round-1 sweep on B200 (profiles/r01_probe_256.md)
     if (c.block_size == 0) c.block_size = 128;
     if (c.unroll == 0) c.unroll = (elem == 4) ? 16 : 8;
     return;
   }
-  if (c.block_size == 0) c.block_size = 256;
   if (c.threads_per_row == 0) {
-    // smallest power of two >= mean row length (the reference uses the integer
-    // mean nnz/rows, csr_vector_spmv.h:236-257, which under-sizes e.g. 7 -> 4)
-    const double mean = rows > 0 ? (double)nnz / (double)rows : 0.0;
+    // smallest power of two >= mean row length up to 32 nnz/row (the reference uses the
+    // integer mean nnz/rows, csr_vector_spmv.h:236-257, which under-sizes e.g. 7 -> 4);
+    // beyond that 16 lanes with deeper per-lane loops won the random-matrix sweep
     int t = 2;
     while (t < 32 && (double)t < mean) t *= 2;
+    if (mean > 32.0) t = 16;
     c.threads_per_row = t;
   }
-  if (c.unroll == 0) c.unroll = (c.threads_per_row >= 32) ? 2 : 4;
+  if (c.block_size == 0) c.block_size = (mean > 32.0) ? 512 : ((elem == 4) ? 512 : 128);
+  if (c.unroll == 0) c.unroll = (mean > 32.0) ? 1 : 4;
 }
 
 template <typename T>
@@ -366,8 +607,14 @@ b200sp_status spmv_csr(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64
 
   b200sp_cfg c = cfg ? *cfg : b200sp_cfg{};
   csr_defaults(c, rows, nnz, sizeof(T));
-  if (c.kernel != B200SP_K_CSR_VECTOR && c.kernel != B200SP_K_CSR_STREAM)
+  if (c.kernel != B200SP_K_CSR_VECTOR && c.kernel != B200SP_K_CSR_STREAM && c.kernel != B200SP_K_CSR_RING)
     return set_error(h, B200SP_INVALID_INPUT, "csr: unknown kernel id %d", c.kernel);
+  if (c.kernel == B200SP_K_CSR_RING && !(aligned16(Aj) && aligned16(Ax))) {
+    // bulk copies need 16-byte aligned array bases: same arithmetic through the stream kernel's LDG path
+    c.kernel = B200SP_K_CSR_STREAM;
+    c.stages = c.ctas_per_sm = 0;
+    if (c.block_size == 256 && c.unroll > 16) c.unroll = 16;
+  }
 
   CsrArgs<T> a;
   a.rows = rows; a.cols = cols; a.nnz = nnz; a.Ap = Ap; a.Aj = Aj; a.Ax = Ax; a.x = x; a.y = y;
@@ -375,6 +622,8 @@ b200sp_status spmv_csr(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64
   a.dot_partials = reinterpret_cast<T *>(h->red_partials);
   a.dot_ticket = h->red_counters;
 
+  if (c.kernel == B200SP_K_CSR_RING)
+    return dispatch_ring<T>(h, st, a, c.block_size, c.unroll, c.stages, c.ctas_per_sm);
   if (c.kernel == B200SP_K_CSR_STREAM) return dispatch_stream<T>(h, st, a, c.block_size, c.unroll);
   switch (c.block_size) {
     case 128: return dispatch_tpr<T, 128>(h, st, a, c.threads_per_row, c.unroll);

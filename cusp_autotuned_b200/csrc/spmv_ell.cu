@@ -294,7 +294,12 @@ static b200sp_status launch_bulk(b200sp_handle h, cudaStream_t st, EllArgs<T> a,
   if (smem > (size_t)h->max_smem_optin)
     return set_error(h, B200SP_INVALID_INPUT, "ell bulk: %zu B smem exceeds %d", smem, h->max_smem_optin);
   B200SP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  i64 grid = (i64)h->num_sms * ctas_per_sm;
+  // persistent grid: no more CTAs than are resident at once (a second wave would start
+  // only after a first-wave CTA has finished all of its tiles)
+  int resident = 0;
+  B200SP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, BLOCK + 32, smem));
+  if (resident < 1) return set_error(h, B200SP_INVALID_INPUT, "ell bulk: configuration does not fit on an SM");
+  i64 grid = (i64)h->num_sms * (ctas_per_sm < resident ? ctas_per_sm : resident);
   if (grid > num_tiles) grid = num_tiles;
   kern<<<(unsigned)grid, BLOCK + 32, smem, st>>>(a, stages, num_tiles);
   B200SP_LAUNCH_CHECK(h, "ell_bulk_kernel");

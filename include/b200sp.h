@@ -79,6 +79,8 @@ enum {
    *       and KTT csr_kernel_{naive,warp,block,balanced}, ktt/kernels/csr_kernel.h) */
   B200SP_K_CSR_VECTOR = 1, /* sub-warp per row, shuffle reduction              */
   B200SP_K_CSR_STREAM = 2, /* CTA streams a row block's nnz through smem        */
+  B200SP_K_CSR_RING = 3,   /* persistent CTAs, producer warp + mbarrier ring of
+                              bulk-async staged row blocks (default)            */
   /* ELL  (replaces spmv_ell_kernel ell_spmv.h:47-93, ktt_ell_kernel)          */
   B200SP_K_ELL_LDG = 1,  /* thread per row, coalesced loads, deep unroll      */
   B200SP_K_ELL_BULK = 2, /* slabs staged by cp.async.bulk + mbarrier pipeline  */

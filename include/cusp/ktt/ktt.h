@@ -154,6 +154,9 @@ std::vector<::ktt::KernelResult> tune(const Matrix &A, const V1 &x, V2 &y,
   const char *name = cusp::system::cuda::ktt::format_name(d.format);
   for (int64_t i = 0; i < n; ++i) {
     if (stop_condition && stop_condition->IsFulfilled()) break;
+    // points whose resources (smem ring = stages x K x tile) do not fit this matrix are
+    // outside its space, the way KTT constraints drop configurations before tuning
+    if (raw[(size_t)i].status == B200SP_TUNE_UNSUPPORTED) continue;
     results.emplace_back(name, raw[(size_t)i]);
     if (stop_condition) stop_condition->Update(results.back());
   }

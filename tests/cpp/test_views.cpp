@@ -49,8 +49,8 @@ void TestCgRawPointers() {
   cusp::krylov::cg(A, x, b, monitor);
   cudaMemcpy(host_x, device_x, 4 * sizeof(float), cudaMemcpyDeviceToHost);
   ASSERT_TRUE(monitor.converged());
-  // tridiag(-1,2,-1) x = (1,2,2,1)  ->  x = (2,3,3,2)
-  const float expect[4] = {2, 3, 3, 2};
+  // tridiag(-1,2,-1) x = (1,2,2,1)  ->  x = (3,5,5,3)
+  const float expect[4] = {3, 5, 5, 3};
   for (int i = 0; i < 4; ++i) ASSERT_NEAR(host_x[i], expect[i], 1e-4);
   cudaFree(device_I); cudaFree(device_J); cudaFree(device_V); cudaFree(device_x); cudaFree(device_b);
 }

@@ -121,7 +121,7 @@ def test_csr_order_preserving_kernels_bit_exact_on_any_data(ndt, tdt, dev):
             assert np.array_equal(gpu_multiply("csr", A, x, dev, cfg=cfg), O.spmv(A, x))
             assert np.array_equal(gpu_multiply("csr", A, x, dev, y0=y0, accumulate=True, cfg=cfg),
                                   O.spmv(A, x, y0, accumulate=True))
-    for cfg in [c for c in capi.Handle.cfg_space(capi.FMT_CSR, 0) if c.kernel == capi.K_CSR_STREAM]:
+    for cfg in [c for c in capi.Handle.cfg_space(capi.FMT_CSR, 0) if c.kernel in (capi.K_CSR_STREAM, capi.K_CSR_RING)]:
         assert np.array_equal(gpu_multiply("csr", A, x, dev, cfg=cfg), O.spmv(A, x)), cfg
         assert np.array_equal(gpu_multiply("csr", A, x, dev, y0=y0, accumulate=True, cfg=cfg),
                               O.spmv(A, x, y0, accumulate=True)), cfg
