@@ -396,6 +396,9 @@ def main():
               "ms_per_iter": cg_ms / iters, "scaling": "strong", "residual_first": float(hist[0]),
               "residual_last": float(hist[-1]), "bytes_per_iter_per_gpu": Bc,
               "gbs_per_gpu": Bc / (cg_ms / iters) / 1e6, "frac": Bc / (cg_ms / iters) / 1e6 / peak,
+              "comm": ("none" if world == 1 else ("nvlink-p2p: halo planes + both scalars stored into peer memory "
+                                                  "from inside the 3 CG kernels" if h.comm_p2p_enabled()
+                                                  else "nccl send/recv + all-reduce per iteration")),
               "includes": "setup SpMV + ||b|| + residual init (1 extra SpMV over %d iterations)" % iters}
         del Ac, b, xs
         torch.cuda.empty_cache()

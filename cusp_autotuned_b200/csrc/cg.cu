@@ -235,6 +235,203 @@ __global__ void __launch_bounds__(CG_BLOCK) cg_direction_kernel(i64 n, const T *
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// NVLink peer-memory variants (row-block partitioned CG, comm.h: Mailbox / P2PView)
+//
+// One CG iteration on N GPUs is the same three kernels as on one GPU, and the
+// exchange steps ride inside them as stores into peer memory:
+//   K1  y = A p, local <y,p>                                  (unchanged SpMV kernel)
+//   K2  CTA 0 stores the local <y,p> into slot[0][rank] of EVERY rank's mailbox; every
+//       CTA spins until all N slots carry this iteration's epoch and adds them in rank
+//       order (bit-identical alpha everywhere); x += alpha p; r -= alpha y; the last CTA
+//       stores the local <r,r> into slot[1][rank] of every mailbox
+//   K3  every CTA sums slot[1][*] -> beta; p = r + beta p, and the threads that own the
+//       first / last halo plane also store it straight into the neighbour's p window
+//       over NVLink; the last CTA publishes halo_flag = epoch to both neighbours,
+//       performs the monitor step, and leaves only when both neighbours' planes have
+//       landed here, so the next K1 may read its halos without any further sync.
+// No NCCL call, no extra launch, no host round trip per iteration.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// lane r < world: publish `v` tagged `tag` in rank r's mailbox (two atomic 8-byte words)
+__device__ __forceinline__ void p2p_publish(const P2PView &c, int ch, double v, unsigned tag, int r) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  MailSlot *s = &c.peer[r]->slot[ch][c.rank];
+  st_relaxed_sys(&s->w[0], ((unsigned long long)tag << 32) | (bits & 0xffffffffull));
+  st_relaxed_sys(&s->w[1], ((unsigned long long)tag << 32) | (bits >> 32));
+}
+// first warp of a CTA: lane r polls rank r's slot, then the values are added in rank
+// order (every rank forms the bit-identical sum).  Result valid in every lane.
+template <typename T>
+__device__ __forceinline__ T p2p_sum_warp(const P2PView &c, int ch, unsigned tag) {
+  const int lane = threadIdx.x & 31;
+  double mine = 0.0;
+  if (lane < c.world) {
+    const MailSlot *s = &c.mine->slot[ch][lane];
+    unsigned long long w0, w1;
+    do {
+      w0 = ld_relaxed_sys(&s->w[0]);
+      w1 = ld_relaxed_sys(&s->w[1]);
+    } while ((unsigned)(w0 >> 32) != tag || (unsigned)(w1 >> 32) != tag);
+    mine = __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
+  }
+  T sum = T(0);
+  for (int r = 0; r < c.world; ++r) sum = sum + (T)__shfl_sync(0xffffffffu, mine, r);
+  return sum;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CG_BLOCK) cg_update_p2p_kernel(i64 n, const T *p, const T *y, T *x, T *r,
+                                                                 CgState<T> *S, T *partials, unsigned int *ticket,
+                                                                 P2PView c, unsigned tag) {
+  __shared__ T s_red[32];
+  __shared__ T s_yp;
+  __shared__ double s_pub;
+  __shared__ int s_fin;
+  if (S->done) return;
+  if (threadIdx.x == 0) s_fin = 0;
+  if (blockIdx.x == 0 && threadIdx.x < c.world) p2p_publish(c, 0, (double)S->yp, tag, threadIdx.x);
+  if (threadIdx.x < 32) {
+    const T t = p2p_sum_warp<T>(c, 0, tag);
+    if (threadIdx.x == 0) s_yp = t;
+  }
+  __syncthreads();
+  const T alpha = S->rz / s_yp;
+  const T nalpha = -alpha;
+  T acc = T(0);
+  const i64 stride = (i64)gridDim.x * CG_BLOCK;
+  i64 i = (i64)blockIdx.x * CG_BLOCK + threadIdx.x;
+  for (; i + (CG_UNROLL - 1) * stride < n; i += CG_UNROLL * stride) {
+    T pv[CG_UNROLL], yv[CG_UNROLL], xv[CG_UNROLL], rv[CG_UNROLL];
+#pragma unroll
+    for (int u = 0; u < CG_UNROLL; ++u) {
+      pv[u] = p[i + u * stride];
+      yv[u] = y[i + u * stride];
+      xv[u] = x[i + u * stride];
+      rv[u] = r[i + u * stride];
+    }
+#pragma unroll
+    for (int u = 0; u < CG_UNROLL; ++u) {
+      x[i + u * stride] = alpha * pv[u] + xv[u];
+      const T rn = nalpha * yv[u] + rv[u];
+      r[i + u * stride] = rn;
+      acc = acc + rn * rn;
+    }
+  }
+  for (; i < n; i += stride) {
+    x[i] = alpha * p[i] + x[i];
+    const T rn = nalpha * y[i] + r[i];
+    r[i] = rn;
+    acc = acc + rn * rn;
+  }
+  T bs = block_sum<CG_BLOCK>(acc, s_red);
+  grid_reduce_finish<CG_BLOCK>(bs, partials, ticket, s_red, [&](T total) {
+    S->rz_new = total;  // local part; the global sum is formed by every CTA of K3
+    s_pub = (double)total;
+    s_fin = 1;
+  });
+  __syncthreads();
+  if (s_fin && threadIdx.x < c.world) p2p_publish(c, 1, s_pub, tag, threadIdx.x);  // one lane per peer
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CG_BLOCK) cg_direction_p2p_kernel(i64 n, const T *r, T *p, CgState<T> *S,
+                                                                    unsigned int *ticket, double *residuals,
+                                                                    P2PView c, unsigned tag,
+                                                                    unsigned long long epoch, i64 halo_lo,
+                                                                    i64 halo_hi, T *dst_lo, T *dst_hi) {
+  __shared__ T s_rz;
+  __shared__ bool is_last;
+  if (S->done) return;
+  if (threadIdx.x < 32) {
+    const T t = p2p_sum_warp<T>(c, 1, tag);
+    if (threadIdx.x == 0) s_rz = t;
+  }
+  __syncthreads();
+  const T rz_new = s_rz;
+  const T beta = rz_new / S->rz;
+  const i64 stride = (i64)gridDim.x * CG_BLOCK;
+  const i64 hi_begin = n - halo_hi;
+  bool remote = false;
+  i64 i = (i64)blockIdx.x * CG_BLOCK + threadIdx.x;
+  for (; i + (CG_UNROLL - 1) * stride < n; i += CG_UNROLL * stride) {
+    T rv[CG_UNROLL], pv[CG_UNROLL];
+#pragma unroll
+    for (int u = 0; u < CG_UNROLL; ++u) {
+      rv[u] = r[i + u * stride];
+      pv[u] = p[i + u * stride];
+    }
+#pragma unroll
+    for (int u = 0; u < CG_UNROLL; ++u) {
+      const i64 j = i + u * stride;
+      const T v = T(1) * rv[u] + beta * pv[u];
+      p[j] = v;
+      if (dst_lo && j < halo_lo) {  // rank-1's upper halo, straight over NVLink
+        dst_lo[j] = v;
+        remote = true;
+      }
+      if (dst_hi && j >= hi_begin) {  // rank+1's lower halo
+        dst_hi[j - hi_begin] = v;
+        remote = true;
+      }
+    }
+  }
+  for (; i < n; i += stride) {
+    const T v = T(1) * r[i] + beta * p[i];
+    p[i] = v;
+    if (dst_lo && i < halo_lo) {
+      dst_lo[i] = v;
+      remote = true;
+    }
+    if (dst_hi && i >= hi_begin) {
+      dst_hi[i - hi_begin] = v;
+      remote = true;
+    }
+  }
+  // last CTA: publish the halo epoch, do the monitor step, wait for the neighbours' planes.
+  // Only threads that stored into peer memory pay for a system-scope fence.
+  if (remote) __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence_system();
+    if (dst_lo) st_release_sys(&c.peer[c.rank - 1]->halo_flag[1], epoch);  // I am its rank+1
+    if (dst_hi) st_release_sys(&c.peer[c.rank + 1]->halo_flag[0], epoch);  // I am its rank-1
+    S->beta = beta;
+    S->rz = rz_new;
+    S->iter += 1;
+    monitor_step(S, residuals);
+    if (dst_lo)
+      while (ld_acquire_sys(&c.mine->halo_flag[0]) != epoch) {
+      }
+    if (dst_hi)
+      while (ld_acquire_sys(&c.mine->halo_flag[1]) != epoch) {
+      }
+    *ticket = 0;
+    __threadfence();
+  }
+}
+
 template <typename T>
 __global__ void cg_setup_state_kernel(CgState<T> *S, const T *bnorm, double rel, double abs_tol, int limit) {
   S->bnorm = *bnorm;
@@ -354,8 +551,40 @@ static b200sp_status cg_impl(b200sp_handle h, cudaStream_t st, const b200sp_matr
   if (s != B200SP_OK) return s;
 
   const i64 gdir = ceil_div(n, (i64)CG_BLOCK * CG_UNROLL);
+
+  // NVLink peer-memory path: map the neighbours' p windows, agree on a solve id, and
+  // exchange the halos of p_0 once with NCCL; from then on the iteration is NCCL-free.
+  const bool p2p = dist && h->p2p_ok && h->world > 1;
+  P2PView view;
+  T *dst_lo = nullptr, *dst_hi = nullptr;
+  unsigned long long solve = 0, kiter = 0;
+  if (p2p) {
+    void *dl = nullptr, *dh = nullptr;
+    s = comm_p2p_map_windows(h, st, h->cg_ws, (size_t)((char *)pwin - (char *)h->cg_ws), n, halo_lo, halo_hi,
+                             sizeof(T), &dl, &dh);
+    if (s != B200SP_OK) return s;
+    dst_lo = reinterpret_cast<T *>(dl);
+    dst_hi = reinterpret_cast<T *>(dh);
+    s = comm_next_solve_id(h, st, &solve);
+    if (s != B200SP_OK) return s;
+    view = comm_p2p_view(h);
+    s = comm_halo_exchange(h, st, pwin, n, halo_lo, halo_hi, sizeof(T));
+    if (s != B200SP_OK) return s;
+  }
   while (!hs->done) {
     for (int k = 0; k < prm.check_interval; ++k) {
+      if (p2p) {
+        const unsigned long long epoch = (solve << 32) | (++kiter);
+        const unsigned tag = (unsigned)((solve << 20) + kiter);  // differs from whatever the slot held before
+        s = spmv_any<T>(h, st, A, pwin, y, 0, cfg, p, &S->yp);
+        if (s != B200SP_OK) return s;
+        cg_update_p2p_kernel<T><<<(unsigned)g, CG_BLOCK, 0, st>>>(n, p, y, x, r, S, partials, ticket, view, tag);
+        B200SP_LAUNCH_CHECK(h, "cg_update_p2p_kernel");
+        cg_direction_p2p_kernel<T><<<(unsigned)g, CG_BLOCK, 0, st>>>(n, r, p, S, ticket + 1, res, view, tag, epoch,
+                                                                     halo_lo, halo_hi, dst_lo, dst_hi);
+        B200SP_LAUNCH_CHECK(h, "cg_direction_p2p_kernel");
+        continue;
+      }
       if (dist) {
         s = comm_halo_exchange(h, st, pwin, n, halo_lo, halo_hi, sizeof(T));
         if (s != B200SP_OK) return s;
@@ -448,8 +677,8 @@ b200sp_status b200sp_spmv_dist(b200sp_handle h, b200sp_stream stream, const b200
   B200SP_REQUIRE(h, A_local && halo && x_window && y_local, "spmv_dist: null argument");
   B200SP_REQUIRE(h, h->nccl_comm, "spmv_dist: b200sp_comm_init has not been called");
   const size_t elem = A_local->dtype == B200SP_F64 ? 8 : 4;
-  b200sp_status s = b200sp::comm_halo_exchange(h, (cudaStream_t)stream, x_window, A_local->num_rows,
-                                               halo->halo_lo, halo->halo_hi, elem);
+  b200sp_status s = b200sp::comm_halo_exchange_auto(h, (cudaStream_t)stream, x_window, A_local->num_rows,
+                                                    halo->halo_lo, halo->halo_hi, elem);
   if (s != B200SP_OK) return s;
   return b200sp_spmv(h, stream, A_local, x_window, y_local, 0, cfg);
 }

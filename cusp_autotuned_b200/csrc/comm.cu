@@ -5,6 +5,7 @@
 // process (e.g. torch.distributed) already loaded.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdlib.h>
 
 #include "comm.h"
 
@@ -17,6 +18,7 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                             cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
@@ -44,13 +46,14 @@ static NcclApi &nccl() {
   SYM(CommInitRank, "ncclCommInitRank");
   SYM(CommDestroy, "ncclCommDestroy");
   SYM(AllReduce, "ncclAllReduce");
+  SYM(AllGather, "ncclAllGather");
   SYM(Send, "ncclSend");
   SYM(Recv, "ncclRecv");
   SYM(GroupStart, "ncclGroupStart");
   SYM(GroupEnd, "ncclGroupEnd");
   SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
-  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.Send && api.Recv &&
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.Send && api.Recv &&
            api.GroupStart && api.GroupEnd && api.GetErrorString;
   return api;
 }
@@ -107,6 +110,293 @@ b200sp_status comm_halo_exchange(b200sp_handle h, cudaStream_t st, void *window,
   return B200SP_OK;
 }
 
+
+// ---------------------------------------------------------------------------
+// NVLink peer-memory path: CUDA-IPC mapped mailboxes + neighbour workspaces
+// ---------------------------------------------------------------------------
+b200sp_status comm_allgather_host(b200sp_handle h, cudaStream_t st, const void *host_in, size_t bytes,
+                                  void *host_out) {
+  B200SP_REQUIRE(h, h->nccl_comm && bytes > 0 && bytes <= 256, "allgather: bad arguments");
+  b200sp_status s = ensure_scratch(h, (size_t)(h->world + 1) * 256);
+  if (s != B200SP_OK) return s;
+  char *d = reinterpret_cast<char *>(h->scratch);
+  B200SP_CUDA(h, cudaMemcpyAsync(d, host_in, bytes, cudaMemcpyHostToDevice, st));
+  B200SP_NCCL(h, nccl().AllGather(d, d + 256, bytes, ncclChar, (ncclComm_t)h->nccl_comm, st));
+  B200SP_CUDA(h, cudaMemcpyAsync(host_out, d + 256, bytes * (size_t)h->world, cudaMemcpyDeviceToHost, st));
+  B200SP_CUDA(h, cudaStreamSynchronize(st));
+  return B200SP_OK;
+}
+
+static bool all_ranks_ok(b200sp_handle h, cudaStream_t st, int mine) {
+  int flags[P2P_MAX_WORLD];
+  if (comm_allgather_host(h, st, &mine, sizeof(int), flags) != B200SP_OK) return false;
+  for (int r = 0; r < h->world; ++r)
+    if (!flags[r]) return false;
+  return true;
+}
+
+static void p2p_teardown(b200sp_handle h) {
+  for (int r = 0; r < P2P_MAX_WORLD; ++r) {
+    if (h->peer_mail[r] && h->peer_mail[r] != h->mail) cudaIpcCloseMemHandle(h->peer_mail[r]);
+    h->peer_mail[r] = nullptr;
+  }
+  for (int k = 0; k < 2; ++k) {
+    if (h->nbr_ws[k]) cudaIpcCloseMemHandle(h->nbr_ws[k]);
+    h->nbr_ws[k] = nullptr;
+    memset(h->nbr_ws_handle[k], 0, 64);
+  }
+  for (int k = 0; k < 2; ++k) {
+    if (h->nbr_stage[k]) cudaIpcCloseMemHandle(h->nbr_stage[k]);
+    h->nbr_stage[k] = nullptr;
+  }
+  if (h->halo_stage) cudaFree(h->halo_stage);
+  h->halo_stage = nullptr;
+  if (h->mail) cudaFree(h->mail);
+  h->mail = nullptr;
+  h->p2p_ok = false;
+  h->xchg_epoch = 0;
+  cudaGetLastError();
+}
+
+// collective, called from b200sp_comm_init: every rank exports its mailbox and maps
+// everybody else's.  Any failure on any rank leaves the whole job on the NCCL path.
+static void p2p_setup(b200sp_handle h) {
+  h->p2p_ok = false;
+  const char *off = getenv("B200SP_DISABLE_P2P");
+  int want = !(off && off[0] && off[0] != '0') && h->world > 1 && h->world <= P2P_MAX_WORLD;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  struct Info {
+    unsigned char handle[64];
+    unsigned char stage_handle[64];
+    int ok;
+  } mine;
+  memset(&mine, 0, sizeof(mine));
+  if (want) {
+    if (cudaMalloc(&h->mail, 4096) == cudaSuccess && cudaMemset(h->mail, 0, 4096) == cudaSuccess &&
+        cudaMalloc(&h->halo_stage, 4 * P2P_STAGE_SIDE) == cudaSuccess) {
+      cudaIpcMemHandle_t hd, hs;
+      if (cudaIpcGetMemHandle(&hd, h->mail) == cudaSuccess && cudaIpcGetMemHandle(&hs, h->halo_stage) == cudaSuccess) {
+        memcpy(mine.handle, &hd, 64);
+        memcpy(mine.stage_handle, &hs, 64);
+        mine.ok = 1;
+      }
+    }
+    cudaGetLastError();
+  }
+  Info all[P2P_MAX_WORLD];
+  if (h->world > P2P_MAX_WORLD || comm_allgather_host(h, nullptr, &mine, sizeof(Info), all) != B200SP_OK) {
+    p2p_teardown(h);
+    return;
+  }
+  int ok = 1;
+  for (int r = 0; r < h->world; ++r) ok = ok && all[r].ok;
+  if (ok) {
+    for (int r = 0; r < h->world && ok; ++r) {
+      if (r == h->rank) {
+        h->peer_mail[r] = h->mail;
+        continue;
+      }
+      cudaIpcMemHandle_t hd;
+      memcpy(&hd, all[r].handle, 64);
+      if (cudaIpcOpenMemHandle(&h->peer_mail[r], hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        h->peer_mail[r] = nullptr;
+        ok = 0;
+        cudaGetLastError();
+      }
+      const int side = (r == h->rank - 1) ? 0 : ((r == h->rank + 1) ? 1 : -1);
+      if (ok && side >= 0) {
+        memcpy(&hd, all[r].stage_handle, 64);
+        if (cudaIpcOpenMemHandle(&h->nbr_stage[side], hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          h->nbr_stage[side] = nullptr;
+          ok = 0;
+          cudaGetLastError();
+        }
+      }
+    }
+  }
+  if (!all_ranks_ok(h, nullptr, ok)) {
+    p2p_teardown(h);
+    return;
+  }
+  h->p2p_ok = true;
+}
+
+
+// ---- one-kernel halo exchange through peer memory ---------------------------------
+// grid of XCHG_CTAS co-resident CTAs (the stream is otherwise idle when it runs):
+//   A  copy my first halo_lo / last halo_hi local elements into the staging buffers of
+//      rank-1 / rank+1 (16-byte stores over NVLink);
+//   B  last CTA to finish A publishes xchg_flag = epoch in both neighbours' mailboxes,
+//      waits until both neighbours have published theirs here, then raises xchg_go;
+//   C  every CTA waits for xchg_go and copies the staged planes into my window.
+// Staging is double-buffered by epoch parity: a neighbour can be at most one exchange
+// ahead (its next-but-one push needs my next push, which follows my copy-out in stream
+// order).
+constexpr int XCHG_CTAS = 64;
+constexpr int XCHG_BLOCK = 256;
+
+__device__ __forceinline__ void copy_bytes16(char *dst, const char *src, size_t bytes, size_t tid, size_t nthreads) {
+  // both pointers 16-byte aligned when bytes % 16 == 0 in our layouts; otherwise byte-wise tail
+  const size_t n16 = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) ? 0 : bytes / 16;
+  const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+  uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+  for (size_t i = tid; i < n16; i += nthreads) d4[i] = s4[i];
+  for (size_t i = n16 * 16 + tid; i < bytes; i += nthreads) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(XCHG_BLOCK) halo_xchg_kernel(char *window, size_t local_off, size_t n_bytes,
+                                                               size_t lo_bytes, size_t hi_bytes, char *stage_mine,
+                                                               char *stage_lo_nbr, char *stage_hi_nbr, Mailbox *mine,
+                                                               Mailbox *mail_lo_nbr, Mailbox *mail_hi_nbr,
+                                                               unsigned int *ticket, unsigned long long epoch) {
+  const size_t tid = (size_t)blockIdx.x * XCHG_BLOCK + threadIdx.x, nth = (size_t)gridDim.x * XCHG_BLOCK;
+  const size_t par = (size_t)(epoch & 1) * 2 * P2P_STAGE_SIDE;
+  char *local = window + local_off;
+  // A: my low edge is rank-1's upper halo (its slot "from rank+1"), my high edge rank+1's lower halo
+  if (stage_lo_nbr) copy_bytes16(stage_lo_nbr + par + P2P_STAGE_SIDE, local, lo_bytes, tid, nth);
+  if (stage_hi_nbr) copy_bytes16(stage_hi_nbr + par, local + n_bytes - hi_bytes, hi_bytes, tid, nth);
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence_system();
+    unsigned long long *f;
+    if (mail_lo_nbr) {
+      f = &mail_lo_nbr->xchg_flag[1];
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+    }
+    if (mail_hi_nbr) {
+      f = &mail_hi_nbr->xchg_flag[0];
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+    }
+    for (int side = 0; side < 2; ++side) {
+      if (!(side == 0 ? mail_lo_nbr : mail_hi_nbr)) continue;
+      unsigned long long v;
+      do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(&mine->xchg_flag[side]) : "memory");
+      } while (v != epoch);
+    }
+    *ticket = 0;
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&mine->xchg_go), "l"(epoch) : "memory");
+  }
+  // C
+  if (threadIdx.x == 0) {
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(&mine->xchg_go) : "memory");
+    } while (v != epoch);
+  }
+  __syncthreads();
+  if (mail_lo_nbr) copy_bytes16(window, stage_mine + par, lo_bytes, tid, nth);
+  if (mail_hi_nbr) copy_bytes16(local + n_bytes, stage_mine + par + P2P_STAGE_SIDE, hi_bytes, tid, nth);
+}
+
+b200sp_status comm_halo_exchange_auto(b200sp_handle h, cudaStream_t st, void *window, i64 n, i64 halo_lo,
+                                      i64 halo_hi, size_t elem) {
+  if (h->world <= 1) return B200SP_OK;
+  const bool has_lo = h->rank > 0 && halo_lo > 0, has_hi = h->rank < h->world - 1 && halo_hi > 0;
+  const size_t lo_bytes = (size_t)halo_lo * elem, hi_bytes = (size_t)halo_hi * elem;
+  // symmetric sizes make this decision identical on both ends of every link
+  if (!h->p2p_ok || lo_bytes > P2P_STAGE_SIDE || hi_bytes > P2P_STAGE_SIDE)
+    return comm_halo_exchange(h, st, window, n, halo_lo, halo_hi, elem);
+  B200SP_REQUIRE(h, halo_lo <= n && halo_hi <= n, "halo larger than the local block");
+  const unsigned long long epoch = ++h->xchg_epoch;
+  if (!has_lo && !has_hi) return B200SP_OK;
+  Mailbox *mine = reinterpret_cast<Mailbox *>(h->mail);
+  halo_xchg_kernel<<<XCHG_CTAS, XCHG_BLOCK, 0, st>>>(
+      reinterpret_cast<char *>(window), (size_t)halo_lo * elem, (size_t)n * elem, has_lo ? lo_bytes : 0,
+      has_hi ? hi_bytes : 0, reinterpret_cast<char *>(h->halo_stage),
+      has_lo ? reinterpret_cast<char *>(h->nbr_stage[0]) : nullptr,
+      has_hi ? reinterpret_cast<char *>(h->nbr_stage[1]) : nullptr, mine,
+      has_lo ? reinterpret_cast<Mailbox *>(h->peer_mail[h->rank - 1]) : nullptr,
+      has_hi ? reinterpret_cast<Mailbox *>(h->peer_mail[h->rank + 1]) : nullptr, h->red_counters + 2, epoch);
+  B200SP_LAUNCH_CHECK(h, "halo_xchg_kernel");
+  return B200SP_OK;
+}
+
+P2PView comm_p2p_view(b200sp_handle h) {
+  P2PView v;
+  memset(&v, 0, sizeof(v));
+  for (int r = 0; r < h->world && r < P2P_MAX_WORLD; ++r) v.peer[r] = reinterpret_cast<Mailbox *>(h->peer_mail[r]);
+  v.mine = reinterpret_cast<Mailbox *>(h->mail);
+  v.world = h->world;
+  v.rank = h->rank;
+  return v;
+}
+
+b200sp_status comm_next_solve_id(b200sp_handle h, cudaStream_t st, unsigned long long *id) {
+  unsigned long long mine = h->solve_id, all[P2P_MAX_WORLD];
+  b200sp_status s = comm_allgather_host(h, st, &mine, sizeof(mine), all);
+  if (s != B200SP_OK) return s;
+  unsigned long long m = 0;
+  for (int r = 0; r < h->world; ++r) m = all[r] > m ? all[r] : m;
+  h->solve_id = m + 1;
+  *id = h->solve_id;
+  return B200SP_OK;
+}
+
+b200sp_status comm_p2p_map_windows(b200sp_handle h, cudaStream_t st, void *ws_base, size_t pwin_offset, i64 n,
+                                   i64 halo_lo, i64 halo_hi, size_t elem, void **dst_lo, void **dst_hi) {
+  B200SP_REQUIRE(h, h->p2p_ok && ws_base && dst_lo && dst_hi, "p2p_map_windows: peer path not available");
+  struct WInfo {
+    unsigned char handle[64];
+    unsigned long long pwin_offset;
+    long long n, halo_lo, halo_hi;
+    int ok, pad;
+  } mine, all[P2P_MAX_WORLD];
+  memset(&mine, 0, sizeof(mine));
+  cudaIpcMemHandle_t hd;
+  if (cudaIpcGetMemHandle(&hd, ws_base) == cudaSuccess) {
+    memcpy(mine.handle, &hd, 64);
+    mine.ok = 1;
+  } else {
+    cudaGetLastError();
+  }
+  mine.pwin_offset = pwin_offset;
+  mine.n = n;
+  mine.halo_lo = halo_lo;
+  mine.halo_hi = halo_hi;
+  b200sp_status s = comm_allgather_host(h, st, &mine, sizeof(WInfo), all);
+  if (s != B200SP_OK) return s;
+  int ok = 1;
+  for (int r = 0; r < h->world; ++r) ok = ok && all[r].ok;
+  *dst_lo = *dst_hi = nullptr;
+  for (int side = 0; side < 2 && ok; ++side) {
+    const int nb = side == 0 ? h->rank - 1 : h->rank + 1;
+    const i64 my_halo = side == 0 ? halo_lo : halo_hi;
+    if (nb < 0 || nb >= h->world || my_halo == 0) continue;
+    // halos are symmetric: what I send to a neighbour has the size of what I receive from it
+    const long long nb_halo = side == 0 ? all[nb].halo_hi : all[nb].halo_lo;
+    if (nb_halo != my_halo) {
+      ok = 0;
+      break;
+    }
+    if (!h->nbr_ws[side] || memcmp(h->nbr_ws_handle[side], all[nb].handle, 64) != 0) {
+      if (h->nbr_ws[side]) cudaIpcCloseMemHandle(h->nbr_ws[side]);
+      h->nbr_ws[side] = nullptr;
+      cudaIpcMemHandle_t nh;
+      memcpy(&nh, all[nb].handle, 64);
+      if (cudaIpcOpenMemHandle(&h->nbr_ws[side], nh, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        h->nbr_ws[side] = nullptr;
+        cudaGetLastError();
+        ok = 0;
+        break;
+      }
+      memcpy(h->nbr_ws_handle[side], all[nb].handle, 64);
+    }
+    char *base = reinterpret_cast<char *>(h->nbr_ws[side]) + all[nb].pwin_offset;
+    if (side == 0)
+      *dst_lo = base + (size_t)(all[nb].halo_lo + all[nb].n) * elem;  // the neighbour's halo_hi region
+    else
+      *dst_hi = base;  // the neighbour's halo_lo region
+  }
+  if (!all_ranks_ok(h, st, ok))
+    return set_error(h, B200SP_COMM_ERROR, "p2p: mapping the neighbours' CG workspaces failed on some rank");
+  return B200SP_OK;
+}
+
 }  // namespace b200sp
 
 extern "C" {
@@ -130,6 +420,7 @@ b200sp_status b200sp_comm_init(b200sp_handle h, const void *id128, int world_siz
   auto &api = b200sp::nccl();
   if (!api.ok) return b200sp::set_error(h, B200SP_COMM_ERROR, "NCCL library not found (libnccl.so.2)");
   if (h->nccl_comm) {
+    b200sp::p2p_teardown(h);
     api.CommDestroy((ncclComm_t)h->nccl_comm);
     h->nccl_comm = nullptr;
   }
@@ -140,12 +431,16 @@ b200sp_status b200sp_comm_init(b200sp_handle h, const void *id128, int world_siz
   h->nccl_comm = comm;
   h->world = world_size;
   h->rank = rank;
+  b200sp::p2p_setup(h);  // NVLink peer-memory mailboxes; silently stays on NCCL if unavailable
   return B200SP_OK;
 }
+
+int b200sp_comm_p2p_enabled(b200sp_handle h) { return (h && h->p2p_ok) ? 1 : 0; }
 
 b200sp_status b200sp_comm_destroy(b200sp_handle h) {
   B200SP_CHECK_HANDLE(h);
   if (h->nccl_comm) {
+    b200sp::p2p_teardown(h);
     b200sp::nccl().CommDestroy((ncclComm_t)h->nccl_comm);
     h->nccl_comm = nullptr;
   }

@@ -14,4 +14,50 @@ void comm_sqrt_inplace(b200sp_handle h, cudaStream_t st, void *dev, bool is_doub
 // what it sends to it (true for the stencil operators partitioned by planes).
 b200sp_status comm_halo_exchange(b200sp_handle h, cudaStream_t st, void *window, i64 n, i64 halo_lo,
                                  i64 halo_hi, size_t elem);
+
+// ---- NVLink peer-memory path -------------------------------------------------
+// Mailbox layout (device memory, one per rank, mapped into every peer through CUDA IPC):
+//   slot[ch][r]  ch in {0,1}: value + epoch written by rank r (scalar all-reduce by
+//                "everyone writes to everyone, everyone sums in rank order")
+//   halo_flag[2] epoch of the last halo push from rank-1 / rank+1
+constexpr int P2P_MAX_WORLD = 16;
+// A scalar travels as two 8-byte words, each = (32 data bits | 32-bit epoch tag).  An
+// aligned 8-byte store is single-copy atomic, so data and tag arrive together and the
+// reader needs no fence: it spins until both tags carry the expected epoch (the
+// "LL" idea of NCCL's low-latency protocol).
+struct MailSlot {
+  unsigned long long w[2];
+};
+struct Mailbox {
+  MailSlot slot[2][P2P_MAX_WORLD];
+  unsigned long long halo_flag[2];  // CG: epoch of the last p-halo push from rank-1 / rank+1
+  unsigned long long xchg_flag[2];  // spmv_dist: epoch of the last staged plane from rank-1 / rank+1
+  unsigned long long xchg_go;       // spmv_dist: local "both planes have landed" signal
+};
+// staging buffer layout (bytes): [parity 0 | parity 1] x [from rank-1 | from rank+1] x P2P_STAGE_SIDE
+constexpr size_t P2P_STAGE_SIDE = (size_t)16 << 20;
+struct P2PView {  // passed by value to the CG kernels
+  Mailbox *peer[P2P_MAX_WORLD];
+  Mailbox *mine;
+  int world, rank;
+};
+// all-gather `bytes` (<= 256) of host data from every rank into host_out[world*bytes]
+b200sp_status comm_allgather_host(b200sp_handle h, cudaStream_t st, const void *host_in, size_t bytes,
+                                  void *host_out);
+// map the CG workspaces of rank-1 / rank+1 (collective; every rank passes its own cg_ws
+// base, the byte offset of its p window inside it and its local sizes).  On return
+// dst_lo / dst_hi are the addresses, in the neighbours' windows, where this rank's
+// first halo_lo / last halo_hi elements of p belong (nullptr at the ends of the chain).
+b200sp_status comm_p2p_map_windows(b200sp_handle h, cudaStream_t st, void *ws_base, size_t pwin_offset,
+                                   i64 n, i64 halo_lo, i64 halo_hi, size_t elem, void **dst_lo,
+                                   void **dst_hi);
+P2PView comm_p2p_view(b200sp_handle h);
+// halo exchange through NVLink peer memory (one kernel: store my edge planes into the
+// neighbours' staging buffers, publish, wait for theirs, copy them into my window);
+// falls back to NCCL send/recv when the peer path is not available or a plane exceeds
+// P2P_STAGE_SIDE.  Same contract as comm_halo_exchange.
+b200sp_status comm_halo_exchange_auto(b200sp_handle h, cudaStream_t st, void *window, i64 n, i64 halo_lo,
+                                      i64 halo_hi, size_t elem);
+// agree on a fresh solve id (max over ranks + 1): epochs never repeat across solves
+b200sp_status comm_next_solve_id(b200sp_handle h, cudaStream_t st, unsigned long long *id);
 }  // namespace b200sp

@@ -78,6 +78,20 @@ struct b200sp_context {
   // multi-GPU
   void *nccl_comm = nullptr;
   int world = 1, rank = 0;
+  // NVLink peer-memory path (comm.cu): a 4 KiB mailbox per rank, IPC-mapped into every
+  // peer, carries the CG scalars and the halo-arrival flags; the CG workspace of the two
+  // neighbouring ranks is mapped on demand so halo planes are stored straight into it.
+  bool p2p_ok = false;
+  void *mail = nullptr;             // this rank's mailbox (device)
+  void *peer_mail[16] = {nullptr};  // every rank's mailbox as seen from this device
+  void *nbr_ws[2] = {nullptr, nullptr};        // mapped cg_ws of rank-1 / rank+1
+  unsigned char nbr_ws_handle[2][64] = {{0}};  // IPC handles currently mapped in nbr_ws
+  unsigned long long solve_id = 0;
+  // staging for the peer-memory halo exchange of b200sp_spmv_dist: this rank's buffer
+  // (IPC-exported) and the two neighbours' buffers as mapped here
+  void *halo_stage = nullptr;
+  void *nbr_stage[2] = {nullptr, nullptr};
+  unsigned long long xchg_epoch = 0;
 };
 
 enum { RED_MAX_PARTIALS = 1 << 16 };

@@ -309,6 +309,12 @@ b200sp_status b200sp_comm_unique_id(void *id128);
 b200sp_status b200sp_comm_init(b200sp_handle h, const void *id128, int world_size,
                                int rank);
 b200sp_status b200sp_comm_destroy(b200sp_handle h);
+/* 1 when the NVLink peer-memory path is active for this communicator: every rank's
+ * mailbox is CUDA-IPC mapped into every peer, b200sp_cg_dist then stores halo planes and
+ * the two CG scalars straight into peer memory from inside its three kernels (no NCCL
+ * call per iteration).  0: NCCL send/recv + all-reduce per iteration (also forced by the
+ * environment variable B200SP_DISABLE_P2P=1). */
+int b200sp_comm_p2p_enabled(b200sp_handle h);
 
 typedef struct {
   int64_t halo_lo; /* elements received from rank-1 (0 on rank 0)            */
