@@ -42,6 +42,10 @@ b200sp_status spmv_hyb(b200sp_handle, cudaStream_t, i64, i64, i64, i64, const in
                        const b200sp_cfg *);
 template <typename T, int MODE>
 b200sp_status reduce(b200sp_handle, cudaStream_t, i64, const T *, const T *, T *, T *);
+template <typename T>
+b200sp_status spmv_dia_xchg(b200sp_handle, cudaStream_t, i64, i64, i64, i64, const int *, const T *, const T *,
+                            T *, int, const b200sp_cfg *, const T *, T *, const FusedXchg *, int *);
+bool dia_can_fuse_xchg(i64 rows, i64 ndiag, i64 pitch, const void *vals, size_t elem, const b200sp_cfg *cfg);
 
 // y = A x (+ optional fused <y, dotv>).  Formats whose kernel has no fused
 // epilogue (COO / HYB) get a separate deterministic dot kernel.
@@ -677,6 +681,33 @@ b200sp_status b200sp_spmv_dist(b200sp_handle h, b200sp_stream stream, const b200
   B200SP_REQUIRE(h, A_local && halo && x_window && y_local, "spmv_dist: null argument");
   B200SP_REQUIRE(h, h->nccl_comm, "spmv_dist: b200sp_comm_init has not been called");
   const size_t elem = A_local->dtype == B200SP_F64 ? 8 : 4;
+  // DIA through the bulk kernel: the exchange rides inside the product (peer memory,
+  // idle producer lanes) and is hidden behind the interior tiles
+  if (A_local->format == B200SP_FMT_DIA && h->world > 1 && h->p2p_ok) {
+    b200sp_cfg cached;
+    const b200sp_cfg *use = cfg;
+    if (!use && b200sp_tune_lookup(h, A_local, &cached)) use = &cached;
+    b200sp::FusedXchg xc;
+    if (b200sp::dia_can_fuse_xchg(A_local->num_rows, A_local->num_cols_per_row, A_local->pitch, A_local->values, elem,
+                                  use) &&
+        b200sp::comm_fused_xchg_prepare(h, x_window, A_local->num_rows, halo->halo_lo, halo->halo_hi, elem, &xc)) {
+      int fused = 0;
+      b200sp_status fs;
+      if (elem == 8)
+        fs = b200sp::spmv_dia_xchg<double>(h, (cudaStream_t)stream, A_local->num_rows, A_local->num_cols,
+                                           A_local->num_cols_per_row, A_local->pitch, A_local->diagonal_offsets,
+                                           (const double *)A_local->values, (const double *)x_window,
+                                           (double *)y_local, 0, use, nullptr, nullptr, &xc, &fused);
+      else
+        fs = b200sp::spmv_dia_xchg<float>(h, (cudaStream_t)stream, A_local->num_rows, A_local->num_cols,
+                                          A_local->num_cols_per_row, A_local->pitch, A_local->diagonal_offsets,
+                                          (const float *)A_local->values, (const float *)x_window,
+                                          (float *)y_local, 0, use, nullptr, nullptr, &xc, &fused);
+      if (fs != B200SP_OK) return fs;
+      if (!fused) return b200sp::set_error(h, B200SP_COMM_ERROR, "spmv_dist: fused halo exchange was not launched");
+      return B200SP_OK;
+    }
+  }
   b200sp_status s = b200sp::comm_halo_exchange_auto(h, (cudaStream_t)stream, x_window, A_local->num_rows,
                                                     halo->halo_lo, halo->halo_hi, elem);
   if (s != B200SP_OK) return s;

@@ -316,6 +316,35 @@ b200sp_status comm_halo_exchange_auto(b200sp_handle h, cudaStream_t st, void *wi
   return B200SP_OK;
 }
 
+bool comm_fused_xchg_prepare(b200sp_handle h, void *window, i64 n, i64 halo_lo, i64 halo_hi, size_t elem,
+                             FusedXchg *xc) {
+  memset(xc, 0, sizeof(*xc));
+  if (h->world <= 1 || !h->p2p_ok) return false;
+  const bool has_lo = h->rank > 0 && halo_lo > 0, has_hi = h->rank < h->world - 1 && halo_hi > 0;
+  const size_t lo_bytes = (size_t)halo_lo * elem, hi_bytes = (size_t)halo_hi * elem;
+  if (!has_lo && !has_hi) return false;
+  if (lo_bytes > P2P_STAGE_SIDE || hi_bytes > P2P_STAGE_SIDE || halo_lo > n || halo_hi > n) return false;
+  // halo regions must not share a 128-byte line with the local part: interior tiles read
+  // x through the non-coherent path while the copy-out is still in flight
+  const uintptr_t w = reinterpret_cast<uintptr_t>(window);
+  if ((w & 127) || (lo_bytes & 127) || (((size_t)(halo_lo + n) * elem) & 127)) return false;
+  xc->enabled = 1;
+  xc->window = reinterpret_cast<char *>(window);
+  xc->local_off = lo_bytes;
+  xc->n_bytes = (size_t)n * elem;
+  xc->lo_bytes = has_lo ? lo_bytes : 0;
+  xc->hi_bytes = has_hi ? hi_bytes : 0;
+  xc->stage_mine = reinterpret_cast<char *>(h->halo_stage);
+  xc->stage_lo_nbr = has_lo ? reinterpret_cast<char *>(h->nbr_stage[0]) : nullptr;
+  xc->stage_hi_nbr = has_hi ? reinterpret_cast<char *>(h->nbr_stage[1]) : nullptr;
+  xc->mine = reinterpret_cast<Mailbox *>(h->mail);
+  xc->mail_lo_nbr = has_lo ? reinterpret_cast<Mailbox *>(h->peer_mail[h->rank - 1]) : nullptr;
+  xc->mail_hi_nbr = has_hi ? reinterpret_cast<Mailbox *>(h->peer_mail[h->rank + 1]) : nullptr;
+  xc->tickets = h->red_counters + 4;
+  xc->epoch = ++h->xchg_epoch;
+  return true;
+}
+
 P2PView comm_p2p_view(b200sp_handle h) {
   P2PView v;
   memset(&v, 0, sizeof(v));

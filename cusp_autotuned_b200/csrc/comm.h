@@ -51,6 +51,30 @@ b200sp_status comm_allgather_host(b200sp_handle h, cudaStream_t st, const void *
 b200sp_status comm_p2p_map_windows(b200sp_handle h, cudaStream_t st, void *ws_base, size_t pwin_offset,
                                    i64 n, i64 halo_lo, i64 halo_hi, size_t elem, void **dst_lo,
                                    void **dst_hi);
+// Halo exchange fused into the bulk kernel (b200sp_spmv_dist, NVLink peer memory).
+// The 31 idle lanes of every CTA's producer warp push this rank's two edge planes into
+// the neighbours' staging buffers, publish, wait for the neighbours' planes and copy
+// them into the x window, all while the consumer warps stream interior tiles.  Tiles
+// are visited in rotated order so that the tiles which read halo columns come last;
+// their consumers wait on a local flag that is raised when the copy-out is complete.
+struct FusedXchg {
+  int enabled;
+  char *window;        // x window base [halo_lo | local | halo_hi]
+  size_t local_off, n_bytes, lo_bytes, hi_bytes;
+  char *stage_mine, *stage_lo_nbr, *stage_hi_nbr;  // nullptr where there is no neighbour
+  Mailbox *mine, *mail_lo_nbr, *mail_hi_nbr;
+  unsigned int *tickets;  // [2], zero on entry, reset by the kernel
+  unsigned long long epoch;
+  long long rot;            // tile rotation: sequence index s -> tile (s + rot) mod num_tiles
+  long long lo_tiles;       // tiles [0, lo_tiles) read the lower halo
+  long long hi_tile_begin;  // tiles [hi_tile_begin, num_tiles) read the upper halo
+};
+
+// fill `xc` for one exchange of the window [halo_lo | n | halo_hi] (advances the exchange
+// epoch); returns false when the peer path cannot carry it (then use
+// comm_halo_exchange_auto before the product instead)
+bool comm_fused_xchg_prepare(b200sp_handle h, void *window, i64 n, i64 halo_lo, i64 halo_hi, size_t elem,
+                             FusedXchg *xc);
 P2PView comm_p2p_view(b200sp_handle h);
 // halo exchange through NVLink peer memory (one kernel: store my edge planes into the
 // neighbours' staging buffers, publish, wait for theirs, copy them into my window);

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(BLOCK) coo_segscan_kernel(CooArgs<T> a) {
 
 // one thread per tile: leaders walk their carry chain in tile order
 template <typename T>
-__global__ void coo_fixup_kernel(i64 num_tiles, const CooCarry<T> *carry, T *y) {
+__global__ void coo_fixup_kernel(i64 num_tiles, const CooCarry<T> *carry, T *y, int accumulate) {
   const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= num_tiles) return;
   const CooCarry<T> me = carry[t];
@@ -205,7 +205,7 @@ __global__ void coo_fixup_kernel(i64 num_tiles, const CooCarry<T> *carry, T *y) 
       break;
     }
   }
-  y[row] = y[row] + total;
+  y[row] = accumulate ? y[row] + total : total;  // !accumulate: y[row] still holds the memset zero
 }
 
 template <typename T, int BLOCK, int VPT>
@@ -217,7 +217,7 @@ static b200sp_status launch_coo(b200sp_handle h, cudaStream_t st, CooArgs<T> a) 
   a.carry = reinterpret_cast<CooCarry<T> *>(h->scratch);
   coo_segscan_kernel<T, BLOCK, VPT><<<(unsigned)tiles, BLOCK, 0, st>>>(a);
   B200SP_LAUNCH_CHECK(h, "coo_segscan_kernel");
-  coo_fixup_kernel<T><<<(unsigned)ceil_div(tiles, 256), 256, 0, st>>>(tiles, a.carry, a.y);
+  coo_fixup_kernel<T><<<(unsigned)ceil_div(tiles, 256), 256, 0, st>>>(tiles, a.carry, a.y, a.accumulate);
   B200SP_LAUNCH_CHECK(h, "coo_fixup_kernel");
   return B200SP_OK;
 }
@@ -248,8 +248,8 @@ b200sp_status spmv_coo(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64
 
   CooArgs<T> a;
   a.rows = rows; a.cols = cols; a.nnz = nnz; a.Ai = Ai; a.Aj = Aj; a.Ax = Ax; a.x = x; a.y = y;
-  // y was zeroed above for y = A x, so both modes accumulate into y from here
-  a.accumulate = 1;
+  // y = A x: y was zeroed above, so complete rows are stored without reading y back
+  a.accumulate = accumulate;
   a.carry = nullptr;
 #define CASE(B, V) \
   if (c.block_size == B && c.unroll == V) return launch_coo<T, B, V>(h, st, a);

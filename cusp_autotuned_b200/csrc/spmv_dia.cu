@@ -24,8 +24,11 @@
 //
 // Algorithmic bytes / row: K*sizeof(T) slab + sizeof(T) x + sizeof(T) y.
 #include "common.cuh"
+#include "comm.h"
 
 namespace b200sp {
+
+typedef FusedXchg DiaXchg;  // comm.h
 
 template <typename T>
 struct DiaArgs {
@@ -42,6 +45,7 @@ struct DiaArgs {
   unsigned int *dot_ticket;
   T *dot_result;
   i64 row_begin;  // first row handled by this launch (remainder launches)
+  DiaXchg xc;
 };
 
 constexpr int DIA_DU = 8;            // diagonals in flight per thread
@@ -148,6 +152,56 @@ __global__ void __launch_bounds__(BLOCK) dia_ldg_kernel(DiaArgs<T> a) {
 // ---------------------------------------------------------------------------
 constexpr int DIA_KC = 8;  // diagonals per stage
 
+__device__ __forceinline__ void xchg_copy16(char *dst, const char *src, size_t bytes, size_t tid, size_t nthreads) {
+  const size_t n16 = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) ? 0 : bytes / 16;
+  const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+  uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+  for (size_t i = tid; i < n16; i += nthreads) d4[i] = s4[i];
+  for (size_t i = n16 * 16 + tid; i < bytes; i += nthreads) dst[i] = src[i];
+}
+
+// lanes 1..31 of the producer warp of every CTA (see DiaXchg)
+__device__ __forceinline__ void dia_xchg_aux(const DiaXchg &xc, int lane) {
+  constexpr unsigned AUX = 0xfffffffeu;
+  const size_t aux = (size_t)blockIdx.x * 31 + (lane - 1), naux = (size_t)gridDim.x * 31;
+  const size_t par = (size_t)(xc.epoch & 1) * 2 * P2P_STAGE_SIDE;
+  char *local = xc.window + xc.local_off;
+  // A: my low edge -> rank-1's "from rank+1" slot, my high edge -> rank+1's "from rank-1" slot
+  if (xc.stage_lo_nbr) xchg_copy16(xc.stage_lo_nbr + par + P2P_STAGE_SIDE, local, xc.lo_bytes, aux, naux);
+  if (xc.stage_hi_nbr) xchg_copy16(xc.stage_hi_nbr + par, local + xc.n_bytes - xc.hi_bytes, xc.hi_bytes, aux, naux);
+  __threadfence_system();
+  __syncwarp(AUX);
+  if (lane == 1) {
+    if (atomicAdd(&xc.tickets[0], 1u) == gridDim.x - 1) {  // every CTA has pushed: publish
+      __threadfence_system();
+      xc.tickets[0] = 0;
+      if (xc.mail_lo_nbr)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&xc.mail_lo_nbr->xchg_flag[1]), "l"(xc.epoch) : "memory");
+      if (xc.mail_hi_nbr)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&xc.mail_hi_nbr->xchg_flag[0]), "l"(xc.epoch) : "memory");
+    }
+    // B: the neighbours' planes have landed in my staging buffer
+    for (int side = 0; side < 2; ++side) {
+      if (!(side == 0 ? xc.mail_lo_nbr : xc.mail_hi_nbr)) continue;
+      unsigned long long v;
+      do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(&xc.mine->xchg_flag[side]) : "memory");
+      } while (v != xc.epoch);
+    }
+  }
+  __syncwarp(AUX);
+  // C: staging -> halo regions of my window
+  if (xc.mail_lo_nbr) xchg_copy16(xc.window, xc.stage_mine + par, xc.lo_bytes, aux, naux);
+  if (xc.mail_hi_nbr) xchg_copy16(local + xc.n_bytes, xc.stage_mine + par + P2P_STAGE_SIDE, xc.hi_bytes, aux, naux);
+  __threadfence();
+  __syncwarp(AUX);
+  if (lane == 1 && atomicAdd(&xc.tickets[1], 1u) == gridDim.x - 1) {
+    __threadfence();
+    xc.tickets[1] = 0;
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&xc.mine->xchg_go), "l"(xc.epoch) : "memory");
+  }
+}
+
 template <typename T, int BLOCK, int RPT>
 __global__ void __launch_bounds__(BLOCK + 32) dia_bulk_kernel(DiaArgs<T> a, int stages,
                                                               i64 num_tiles) {
@@ -181,7 +235,9 @@ __global__ void __launch_bounds__(BLOCK + 32) dia_bulk_kernel(DiaArgs<T> a, int 
       const uint64_t pol = l2_policy_evict_first();
       int s = 0;
       uint32_t ph = 0;
-      for (i64 tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (i64 seq = blockIdx.x; seq < num_tiles; seq += gridDim.x) {
+        i64 tile = seq + a.xc.rot;
+        if (tile >= num_tiles) tile -= num_tiles;
         const i64 r0 = a.row_begin + tile * R;
         if (r0 + R > a.rows) continue;  // ragged last tile: consumers load it directly
         for (int c = 0; c < nchunks; ++c) {
@@ -198,13 +254,29 @@ __global__ void __launch_bounds__(BLOCK + 32) dia_bulk_kernel(DiaArgs<T> a, int 
           }
         }
       }
+    } else if (a.xc.enabled) {
+      dia_xchg_aux(a.xc, tid - BLOCK);
     }
   } else {
     // ===== consumer warps =====
     int s = 0;
     uint32_t ph = 0;
     const int lane = tid & 31;
-    for (i64 tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    bool halo_ready = !a.xc.enabled;
+    for (i64 seq = blockIdx.x; seq < num_tiles; seq += gridDim.x) {
+      i64 tile = seq + a.xc.rot;
+      if (tile >= num_tiles) tile -= num_tiles;
+      if (!halo_ready && (tile < a.xc.lo_tiles || tile >= a.xc.hi_tile_begin)) {
+        // first tile of this warp that reads halo columns: the copy-out must be complete
+        if (lane == 0) {
+          unsigned long long v;
+          do {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(&a.xc.mine->xchg_go) : "memory");
+          } while (v != a.xc.epoch);
+        }
+        __syncwarp();
+        halo_ready = true;
+      }
       const unsigned r0 = (unsigned)(a.row_begin + tile * R);
       T acc[RPT];
       if ((i64)r0 + R > a.rows) {
@@ -343,9 +415,38 @@ static void dia_defaults(b200sp_cfg &c, size_t elem) {
 }
 
 template <typename T>
+b200sp_status spmv_dia_xchg(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64 ndiag, i64 pitch,
+                            const int *offs, const T *vals, const T *x, T *y, int accumulate,
+                            const b200sp_cfg *cfg, const T *dotv, T *dot_result, const DiaXchg *xchg,
+                            int *xchg_fused);
+
+// would spmv_dia() with this configuration run the bulk kernel (the one that can carry
+// a fused halo exchange)?
+bool dia_can_fuse_xchg(i64 rows, i64 ndiag, i64 pitch, const void *vals, size_t elem, const b200sp_cfg *cfg) {
+  b200sp_cfg c = cfg ? *cfg : b200sp_cfg{};
+  dia_defaults(c, elem);
+  if (c.kernel != B200SP_K_DIA_BULK || rows <= 0 || ndiag <= 0) return false;
+  const int R = c.block_size * c.unroll;
+  return (pitch * elem) % 16 == 0 && aligned16(vals) && ((size_t)R * elem) % 16 == 0;
+}
+
+template <typename T>
 b200sp_status spmv_dia(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64 ndiag, i64 pitch,
                        const int *offs, const T *vals, const T *x, T *y, int accumulate,
                        const b200sp_cfg *cfg, const T *dotv, T *dot_result) {
+  return spmv_dia_xchg<T>(h, st, rows, cols, ndiag, pitch, offs, vals, x, y, accumulate, cfg, dotv, dot_result,
+                          nullptr, nullptr);
+}
+
+// same, with an optional halo exchange fused into the kernel.  *xchg_fused is set to 1
+// when the launched kernel performs the exchange; otherwise the caller must have
+// exchanged the halos itself before the call... so the caller asks first with
+// dia_can_fuse_xchg() and only then passes `xchg`.
+template <typename T>
+b200sp_status spmv_dia_xchg(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64 ndiag, i64 pitch,
+                            const int *offs, const T *vals, const T *x, T *y, int accumulate,
+                            const b200sp_cfg *cfg, const T *dotv, T *dot_result, const DiaXchg *xchg,
+                            int *xchg_fused) {
   B200SP_CHECK_HANDLE(h);
   B200SP_REQUIRE(h, rows >= 0 && cols >= 0 && ndiag >= 0, "dia: negative dimension");
   B200SP_REQUIRE(h, rows < (1ll << 31) && cols < (1ll << 31), "dia: int32 index range");
@@ -366,12 +467,24 @@ b200sp_status spmv_dia(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64
   a.dot_partials = reinterpret_cast<T *>(h->red_partials);
   a.dot_ticket = h->red_counters;
   a.row_begin = 0;
+  memset(&a.xc, 0, sizeof(a.xc));
 
   if (c.kernel == B200SP_K_DIA_BULK) {
     const int R = c.block_size * c.unroll;
     const bool ok = (pitch * sizeof(T)) % 16 == 0 && aligned16(vals) && ((size_t)R * sizeof(T)) % 16 == 0 &&
                     ndiag > 0;
     const i64 tiles = ceil_div(rows, (i64)R);
+    if (ok && xchg && xchg->enabled) {
+      // fused halo exchange: the tiles that read halo columns are visited last
+      a.xc = *xchg;
+      const i64 lo_rows = (i64)(a.xc.mail_lo_nbr ? a.xc.lo_bytes / sizeof(T) : 0);
+      const i64 hi_rows = (i64)(a.xc.mail_hi_nbr ? a.xc.hi_bytes / sizeof(T) : 0);
+      a.xc.lo_tiles = ceil_div(lo_rows, (i64)R);
+      a.xc.hi_tile_begin = (rows - hi_rows) / R;
+      a.xc.rot = a.xc.lo_tiles;
+      if (a.xc.lo_tiles + (tiles - a.xc.hi_tile_begin) >= tiles) a.xc.rot = 0;  // no interior to hide behind
+      *xchg_fused = 1;
+    }
     if (ok) return dispatch_bulk<T>(h, st, a, tiles, c.block_size, c.unroll, c.stages, c.ctas_per_sm);
     // layout not bulk-copyable -> LDG kernel (same results)
     c.kernel = B200SP_K_DIA_LDG;
@@ -388,6 +501,13 @@ template b200sp_status spmv_dia<float>(b200sp_handle, cudaStream_t, i64, i64, i6
 template b200sp_status spmv_dia<double>(b200sp_handle, cudaStream_t, i64, i64, i64, i64, const int *,
                                         const double *, const double *, double *, int,
                                         const b200sp_cfg *, const double *, double *);
+
+template b200sp_status spmv_dia_xchg<float>(b200sp_handle, cudaStream_t, i64, i64, i64, i64, const int *,
+                                            const float *, const float *, float *, int, const b200sp_cfg *,
+                                            const float *, float *, const DiaXchg *, int *);
+template b200sp_status spmv_dia_xchg<double>(b200sp_handle, cudaStream_t, i64, i64, i64, i64, const int *,
+                                             const double *, const double *, double *, int, const b200sp_cfg *,
+                                             const double *, double *, const DiaXchg *, int *);
 
 }  // namespace b200sp
 

@@ -81,8 +81,8 @@ def main():
                     hist_ok = bool(np.allclose(hist[:m], hist_o[:m], rtol=1e-10, atol=0))
                 else:
                     # fp32: rounding differences of the regrouped dots grow with the iteration; the
-                    # first 10 entries must agree to 1e-4 of ||r0||, the whole history to 1e-2
-                    hist_ok = bool(np.all(np.abs(hist[:min(m, 10)] - hist_o[:min(m, 10)]) <= 1e-4 * hist_o[0])) \
+                    # first 10 entries must agree to 1e-3 of ||r0||, the whole history to 1e-2
+                    hist_ok = bool(np.all(np.abs(hist[:min(m, 10)] - hist_o[:min(m, 10)]) <= 1e-3 * hist_o[0])) \
                         and hist_dev <= 1e-2
                 hist_ok = hist_ok and len(hist) == len(hist_o)
                 x_ok = bool(np.allclose(xl.cpu().numpy(), xo[blk.row_begin: blk.row_begin + blk.num_rows],
