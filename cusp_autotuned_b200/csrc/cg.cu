@@ -289,10 +289,11 @@ __device__ __forceinline__ T p2p_sum_warp(const P2PView &c, int ch, unsigned tag
   if (lane < c.world) {
     const MailSlot *s = &c.mine->slot[ch][lane];
     unsigned long long w0, w1;
+    SpinGuard guard;
     do {
       w0 = ld_relaxed_sys(&s->w[0]);
       w1 = ld_relaxed_sys(&s->w[1]);
-    } while ((unsigned)(w0 >> 32) != tag || (unsigned)(w1 >> 32) != tag);
+    } while (((unsigned)(w0 >> 32) != tag || (unsigned)(w1 >> 32) != tag) && !guard.expired(c.mine));
     mine = __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
   }
   T sum = T(0);
@@ -425,11 +426,12 @@ __global__ void __launch_bounds__(CG_BLOCK) cg_direction_p2p_kernel(i64 n, const
     S->rz = rz_new;
     S->iter += 1;
     monitor_step(S, residuals);
+    SpinGuard guard;
     if (dst_lo)
-      while (ld_acquire_sys(&c.mine->halo_flag[0]) != epoch) {
+      while (ld_acquire_sys(&c.mine->halo_flag[0]) < epoch && !guard.expired(c.mine)) {
       }
     if (dst_hi)
-      while (ld_acquire_sys(&c.mine->halo_flag[1]) != epoch) {
+      while (ld_acquire_sys(&c.mine->halo_flag[1]) < epoch && !guard.expired(c.mine)) {
       }
     *ticket = 0;
     __threadfence();
@@ -615,6 +617,13 @@ static b200sp_status cg_impl(b200sp_handle h, cudaStream_t st, const b200sp_matr
     if (s != B200SP_OK) return s;
   }
 
+  if (p2p) {
+    unsigned long long timeouts = 0;
+    B200SP_CUDA(h, cudaMemcpyAsync(&timeouts, &view.mine->timeouts, sizeof(timeouts), cudaMemcpyDeviceToHost, st));
+    B200SP_CUDA(h, cudaStreamSynchronize(st));
+    if (timeouts)
+      return set_error(h, B200SP_COMM_ERROR, "cg_dist: a peer never published its data (%llu spin time-outs)", timeouts);
+  }
   result->iteration_count = hs->iter;
   result->converged = hs->converged;
   result->residual_norm = (double)hs->rnorm;

@@ -274,9 +274,10 @@ __global__ void __launch_bounds__(XCHG_BLOCK) halo_xchg_kernel(char *window, siz
     for (int side = 0; side < 2; ++side) {
       if (!(side == 0 ? mail_lo_nbr : mail_hi_nbr)) continue;
       unsigned long long v;
+      SpinGuard guard;
       do {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(&mine->xchg_flag[side]) : "memory");
-      } while (v != epoch);
+      } while (v < epoch && !guard.expired(mine));  // monotonic epochs: a neighbour may be one exchange ahead
     }
     *ticket = 0;
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&mine->xchg_go), "l"(epoch) : "memory");
@@ -284,9 +285,10 @@ __global__ void __launch_bounds__(XCHG_BLOCK) halo_xchg_kernel(char *window, siz
   // C
   if (threadIdx.x == 0) {
     unsigned long long v;
+    SpinGuard guard;
     do {
       asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(&mine->xchg_go) : "memory");
-    } while (v != epoch);
+    } while (v < epoch && !guard.expired(mine));
   }
   __syncthreads();
   if (mail_lo_nbr) copy_bytes16(window, stage_mine + par, lo_bytes, tid, nth);

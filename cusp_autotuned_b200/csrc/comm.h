@@ -33,7 +33,28 @@ struct Mailbox {
   unsigned long long halo_flag[2];  // CG: epoch of the last p-halo push from rank-1 / rank+1
   unsigned long long xchg_flag[2];  // spmv_dist: epoch of the last staged plane from rank-1 / rank+1
   unsigned long long xchg_go;       // spmv_dist: local "both planes have landed" signal
+  unsigned long long timeouts;      // spin loops that gave up (a peer never arrived): results are invalid
 };
+#ifdef __CUDACC__
+// every cross-GPU spin is bounded (~4 s of SM clocks): a peer that died must not hang this GPU
+struct SpinGuard {
+  long long t0;
+  __device__ SpinGuard() {
+#ifdef __CUDA_ARCH__
+    t0 = clock64();
+#else
+    t0 = 0;
+#endif
+  }
+  __device__ bool expired(Mailbox *mine) {
+#ifdef __CUDA_ARCH__
+    if (clock64() - t0 < (1ll << 33)) return false;
+    atomicAdd(&mine->timeouts, 1ull);
+#endif
+    return true;
+  }
+};
+#endif
 // staging buffer layout (bytes): [parity 0 | parity 1] x [from rank-1 | from rank+1] x P2P_STAGE_SIDE
 constexpr size_t P2P_STAGE_SIDE = (size_t)16 << 20;
 struct P2PView {  // passed by value to the CG kernels

@@ -184,9 +184,10 @@ __device__ __forceinline__ void dia_xchg_aux(const DiaXchg &xc, int lane) {
     for (int side = 0; side < 2; ++side) {
       if (!(side == 0 ? xc.mail_lo_nbr : xc.mail_hi_nbr)) continue;
       unsigned long long v;
+      SpinGuard guard;
       do {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(&xc.mine->xchg_flag[side]) : "memory");
-      } while (v != xc.epoch);
+      } while (v < xc.epoch && !guard.expired(xc.mine));  // monotonic epochs: a neighbour may be one exchange ahead
     }
   }
   __syncwarp(AUX);
@@ -270,9 +271,10 @@ __global__ void __launch_bounds__(BLOCK + 32) dia_bulk_kernel(DiaArgs<T> a, int 
         // first tile of this warp that reads halo columns: the copy-out must be complete
         if (lane == 0) {
           unsigned long long v;
+          SpinGuard guard;
           do {
             asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(&a.xc.mine->xchg_go) : "memory");
-          } while (v != a.xc.epoch);
+          } while (v < a.xc.epoch && !guard.expired(a.xc.mine));
         }
         __syncwarp();
         halo_ready = true;

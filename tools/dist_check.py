@@ -95,6 +95,32 @@ def main():
                                      "cg_same_iters": f[1], "cg_hist": f[2], "cg_x": f[3], "hist_dev": hist_dev,
                                      "iters": int(res.iteration_count)})
                 ok = ok and all(f)
+    # skew stress: ranks take turns being late by ~1 ms before an exchange, so neighbours run one
+    # exchange ahead of each other (epoch waits must be monotonic, staging double-buffered)
+    if world > 1:
+        grid = (64, 32, 4 * world)
+        blk = plane_partition(grid, world, rank)
+        A = gallery.poisson("dia", 7, grid, dtype=torch.float64, row_begin=blk.row_begin, num_rows=blk.num_rows,
+                            halo_lo=blk.halo_lo, halo_hi=blk.halo_hi)
+        halo = capi.Halo(blk.halo_lo, blk.halo_hi)
+        ref = O.poisson(7, grid, np.float64, "dia")
+        stress_ok = 1
+        for it in range(48):
+            xg = ((np.arange(ref["num_cols"]) * (it + 1)) % 23 - 11).astype(np.float64)
+            xw = torch.full((blk.window,), float("nan"), dtype=torch.float64, device=dev)
+            xw[blk.halo_lo: blk.halo_lo + blk.num_rows] = torch.from_numpy(
+                xg[blk.row_begin: blk.row_begin + blk.num_rows]).to(dev)
+            y = torch.empty(blk.num_rows, dtype=torch.float64, device=dev)
+            if it % world == rank:
+                torch.cuda._sleep(2_000_000)
+            h.spmv_dist(A.descriptor(), halo, xw, y)
+            want = O.spmv(ref, xg)[blk.row_begin: blk.row_begin + blk.num_rows]
+            if not np.array_equal(y.cpu().numpy(), want):
+                stress_ok = 0
+        flags = torch.tensor([stress_ok], device=dev)
+        td.all_reduce(flags, op=td.ReduceOp.MIN)
+        out["skew_stress_ok"] = int(flags.item())
+        ok = ok and bool(out["skew_stress_ok"])
     out["ok"] = ok
     if rank == 0:
         print(json.dumps(out), flush=True)
