@@ -105,7 +105,7 @@ class TuneResult(C.Structure):
 
 FMT_CSR, FMT_ELL, FMT_DIA, FMT_COO, FMT_HYB, FMT_ELLR = range(6)
 F32, F64 = 0, 1
-K_CSR_VECTOR, K_CSR_STREAM, K_CSR_RING = 1, 2, 3
+K_CSR_VECTOR, K_CSR_STREAM, K_CSR_RING, K_CSR_BALANCED = 1, 2, 3, 4
 K_ELL_LDG, K_ELL_BULK = 1, 2
 K_DIA_LDG, K_DIA_BULK = 1, 2
 K_COO_SEGSCAN = 1

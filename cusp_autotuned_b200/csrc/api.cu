@@ -105,6 +105,8 @@ static std::vector<b200sp_cfg> cfg_space_vec(b200sp_format f, b200sp_dtype) {
         for (auto &p : bu)
           for (int st : {2, 3, 4})
             for (int cps : {2, 4, 6}) push(v, B200SP_K_CSR_RING, p[0], 0, p[1], st, cps);
+        push(v, B200SP_K_CSR_BALANCED, 128, 0, 7, 0, 0);
+        for (int u : {5, 7, 9}) push(v, B200SP_K_CSR_BALANCED, 256, 0, u, 0, 0);
       }
       break;
     case B200SP_FMT_ELL:

@@ -51,9 +51,23 @@ struct CooArgs {
   T *y;
   int accumulate;
   CooCarry<T> *carry;
+  // CSR source (K_CSR_BALANCED): row indices are rebuilt per tile from row_offsets
+  const int *Ap;
+  const int *tile_first_row;  // row that contains entry t*TILE, for every tile t
 };
 
-template <typename T, int BLOCK, int VPT>
+// first row of every nnz tile of a CSR matrix: tile t starts at entry t*TILE, which lies in
+// the row r with Ap[r] <= t*TILE < Ap[r+1].  Replaces gpu_compute_row_starts
+// (cusp/system/cuda/ktt/csr_multiply.h:64-105, the preprocessing of the KTT kernel's
+// DYNAMIC=2 "balanced" mode); like there it runs before every product (Ap may change).
+__global__ void csr_tile_rows_kernel(i64 rows, const int *Ap, int tile, int *tile_first_row) {
+  const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int lo = Ap[r], hi = Ap[r + 1];
+  for (int t = (lo + tile - 1) / tile; (i64)t * tile < hi; ++t) tile_first_row[t] = (int)r;
+}
+
+template <typename T, int BLOCK, int VPT, bool CSR>
 __global__ void __launch_bounds__(BLOCK) coo_segscan_kernel(CooArgs<T> a) {
   constexpr int TILE = BLOCK * VPT;
   constexpr int NW = BLOCK / 32;
@@ -76,7 +90,7 @@ __global__ void __launch_bounds__(BLOCK) coo_segscan_kernel(CooArgs<T> a) {
 #pragma unroll
     for (int i = 0; i < VPT; ++i) {
       const i64 g = min(start + i * BLOCK + tid, a.nnz - 1);
-      r[i] = ld_stream(a.Ai + g);
+      r[i] = CSR ? -1 : ld_stream(a.Ai + g);
       c[i] = ld_stream(a.Aj + g);
       v[i] = ld_stream(a.Ax + g);
     }
@@ -95,13 +109,56 @@ __global__ void __launch_bounds__(BLOCK) coo_segscan_kernel(CooArgs<T> a) {
     }
   }
   int prev_row = -1;
-  if (tid == 0) {
-    s_row[TILE] = (start + TILE < a.nnz) ? a.Ai[start + TILE] : -1;
-    s_head_row = -1;
-    s_head_val = T(0);
+  if (CSR) {
+    // rebuild the row of every entry: each row that owns entries of this tile marks its
+    // first slot, an inclusive max-scan spreads the marks (rows ascend)
+    __shared__ int s_wmax[NW];
+    const int r_first = a.tile_first_row[blockIdx.x];
+    const int r_last = (start + TILE < a.nnz) ? a.tile_first_row[blockIdx.x + 1] : (int)a.rows - 1;
+    if (tid == 0) {
+      s_row[TILE] = (start + TILE < a.nnz) ? r_last : -1;
+      s_head_row = -1;
+      s_head_val = T(0);
+    }
+    prev_row = (ld_ro(a.Ap + r_first) < start) ? r_first : -2;  // does the first row continue from the previous tile?
+    __syncthreads();  // slots hold -1 (or stale -1 beyond n) from the load phase
+    for (int rr_ = r_first + tid; rr_ <= r_last; rr_ += BLOCK) {
+      const i64 lo = ld_ro(a.Ap + rr_), hi = ld_ro(a.Ap + rr_ + 1);
+      if (hi > lo && lo < start + n && hi > start) s_row[(int)(max(lo, start) - start)] = rr_;
+    }
+    __syncthreads();
+    int loc[VPT], m = -1;
+#pragma unroll
+    for (int q = 0; q < VPT; ++q) {
+      m = max(m, s_row[tid * VPT + q]);
+      loc[q] = m;
+    }
+    int incl = m;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl = max(incl, u);
+    }
+    if (lane == 31) s_wmax[w] = incl;
+    __syncthreads();
+    int excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = -1;
+    for (int k = 0; k < w; ++k) excl = max(excl, s_wmax[k]);
+#pragma unroll
+    for (int q = 0; q < VPT; ++q) {
+      const int idx = tid * VPT + q;
+      s_row[idx] = (idx < n) ? max(loc[q], excl) : -1;
+    }
+    __syncthreads();
+  } else {
+    if (tid == 0) {
+      s_row[TILE] = (start + TILE < a.nnz) ? a.Ai[start + TILE] : -1;
+      s_head_row = -1;
+      s_head_val = T(0);
+    }
+    if (start > 0) prev_row = ld_ro(a.Ai + start - 1);
+    __syncthreads();
   }
-  if (start > 0) prev_row = ld_ro(a.Ai + start - 1);
-  __syncthreads();
 
   // ---- per-thread serial segmented reduction over VPT consecutive entries ----
   int rr[VPT + 1];
@@ -215,12 +272,54 @@ static b200sp_status launch_coo(b200sp_handle h, cudaStream_t st, CooArgs<T> a) 
   b200sp_status s = ensure_scratch(h, (size_t)tiles * sizeof(CooCarry<T>));
   if (s != B200SP_OK) return s;
   a.carry = reinterpret_cast<CooCarry<T> *>(h->scratch);
-  coo_segscan_kernel<T, BLOCK, VPT><<<(unsigned)tiles, BLOCK, 0, st>>>(a);
+  coo_segscan_kernel<T, BLOCK, VPT, false><<<(unsigned)tiles, BLOCK, 0, st>>>(a);
   B200SP_LAUNCH_CHECK(h, "coo_segscan_kernel");
   coo_fixup_kernel<T><<<(unsigned)ceil_div(tiles, 256), 256, 0, st>>>(tiles, a.carry, a.y, a.accumulate);
   B200SP_LAUNCH_CHECK(h, "coo_fixup_kernel");
   return B200SP_OK;
 }
+
+// CSR through the nnz-balanced segmented scan (K_CSR_BALANCED)
+template <typename T, int BLOCK, int VPT>
+static b200sp_status launch_csr_balanced(b200sp_handle h, cudaStream_t st, CooArgs<T> a) {
+  constexpr int TILE = BLOCK * VPT;
+  const i64 tiles = ceil_div(a.nnz, (i64)TILE);
+  const size_t carry_bytes = ((size_t)tiles * sizeof(CooCarry<T>) + 255) & ~(size_t)255;
+  b200sp_status s = ensure_scratch(h, carry_bytes + (size_t)(tiles + 1) * sizeof(int));
+  if (s != B200SP_OK) return s;
+  a.carry = reinterpret_cast<CooCarry<T> *>(h->scratch);
+  int *tfr = reinterpret_cast<int *>(reinterpret_cast<char *>(h->scratch) + carry_bytes);
+  a.tile_first_row = tfr;
+  csr_tile_rows_kernel<<<(unsigned)ceil_div(a.rows, 256), 256, 0, st>>>(a.rows, a.Ap, TILE, tfr);
+  B200SP_LAUNCH_CHECK(h, "csr_tile_rows_kernel");
+  coo_segscan_kernel<T, BLOCK, VPT, true><<<(unsigned)tiles, BLOCK, 0, st>>>(a);
+  B200SP_LAUNCH_CHECK(h, "coo_segscan_kernel<csr>");
+  coo_fixup_kernel<T><<<(unsigned)ceil_div(tiles, 256), 256, 0, st>>>(tiles, a.carry, a.y, a.accumulate);
+  B200SP_LAUNCH_CHECK(h, "coo_fixup_kernel");
+  return B200SP_OK;
+}
+
+// entry used by spmv_csr (spmv_csr.cu) for cfg.kernel == B200SP_K_CSR_BALANCED
+template <typename T>
+b200sp_status spmv_csr_balanced(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64 nnz, const int *Ap,
+                                const int *Aj, const T *Ax, const T *x, T *y, int accumulate, int block, int vpt) {
+  if (!accumulate) B200SP_CUDA(h, cudaMemsetAsync(y, 0, (size_t)rows * sizeof(T), st));
+  CooArgs<T> a;
+  a.rows = rows; a.cols = cols; a.nnz = nnz; a.Ai = nullptr; a.Aj = Aj; a.Ax = Ax; a.x = x; a.y = y;
+  a.accumulate = accumulate;
+  a.carry = nullptr;
+  a.Ap = Ap;
+  a.tile_first_row = nullptr;
+#define CASE(B, V) \
+  if (block == B && vpt == V) return launch_csr_balanced<T, B, V>(h, st, a);
+  CASE(128, 7) CASE(256, 5) CASE(256, 7) CASE(256, 9)
+#undef CASE
+  return set_error(h, B200SP_INVALID_INPUT, "csr balanced: unsupported block_size=%d unroll=%d", block, vpt);
+}
+template b200sp_status spmv_csr_balanced<float>(b200sp_handle, cudaStream_t, i64, i64, i64, const int *, const int *,
+                                                const float *, const float *, float *, int, int, int);
+template b200sp_status spmv_csr_balanced<double>(b200sp_handle, cudaStream_t, i64, i64, i64, const int *, const int *,
+                                                 const double *, const double *, double *, int, int, int);
 
 static void coo_defaults(b200sp_cfg &c) {
   if (c.kernel == 0) c.kernel = B200SP_K_COO_SEGSCAN;
@@ -251,6 +350,8 @@ b200sp_status spmv_coo(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64
   // y = A x: y was zeroed above, so complete rows are stored without reading y back
   a.accumulate = accumulate;
   a.carry = nullptr;
+  a.Ap = nullptr;
+  a.tile_first_row = nullptr;
 #define CASE(B, V) \
   if (c.block_size == B && c.unroll == V) return launch_coo<T, B, V>(h, st, a);
   CASE(128, 5) CASE(128, 7) CASE(128, 9) CASE(128, 11)

@@ -34,6 +34,11 @@
 
 namespace b200sp {
 
+// spmv_coo.cu: nnz-balanced segmented scan over a CSR matrix (K_CSR_BALANCED)
+template <typename T>
+b200sp_status spmv_csr_balanced(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64 nnz, const int *Ap,
+                                const int *Aj, const T *Ax, const T *x, T *y, int accumulate, int block, int vpt);
+
 template <typename T>
 struct CsrArgs {
   i64 rows, cols, nnz;
@@ -567,6 +572,11 @@ static void csr_defaults(b200sp_cfg &c, i64 rows, i64 nnz, size_t elem) {
     if (c.ctas_per_sm == 0) c.ctas_per_sm = 4;
     return;
   }
+  if (c.kernel == B200SP_K_CSR_BALANCED) {
+    if (c.block_size == 0) c.block_size = 256;
+    if (c.unroll == 0) c.unroll = 7;
+    return;
+  }
   if (c.kernel == B200SP_K_CSR_STREAM) {
     if (c.block_size == 0) c.block_size = 128;
     if (c.unroll == 0) c.unroll = (elem == 4) ? 16 : 8;
@@ -607,6 +617,10 @@ b200sp_status spmv_csr(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64
 
   b200sp_cfg c = cfg ? *cfg : b200sp_cfg{};
   csr_defaults(c, rows, nnz, sizeof(T));
+  if (c.kernel == B200SP_K_CSR_BALANCED) {
+    if (dotv) return set_error(h, B200SP_INVALID_INPUT, "csr balanced: no fused dot epilogue");
+    return spmv_csr_balanced<T>(h, st, rows, cols, nnz, Ap, Aj, Ax, x, y, accumulate, c.block_size, c.unroll);
+  }
   if (c.kernel != B200SP_K_CSR_VECTOR && c.kernel != B200SP_K_CSR_STREAM && c.kernel != B200SP_K_CSR_RING)
     return set_error(h, B200SP_INVALID_INPUT, "csr: unknown kernel id %d", c.kernel);
   if (c.kernel == B200SP_K_CSR_RING && !(aligned16(Aj) && aligned16(Ax))) {

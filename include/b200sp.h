@@ -81,6 +81,10 @@ enum {
   B200SP_K_CSR_STREAM = 2, /* CTA streams a row block's nnz through smem        */
   B200SP_K_CSR_RING = 3,   /* persistent CTAs, producer warp + mbarrier ring of
                               bulk-async staged row blocks (default)            */
+  B200SP_K_CSR_BALANCED = 4, /* nnz-balanced tiles + segmented scan, rows rebuilt per
+                              tile from row_offsets: power-law rows; replaces KTT's
+                              DYNAMIC=2 kernel + gpu_compute_row_starts
+                              (cuda/ktt/csr_multiply.h:64-133), no atomics        */
   /* ELL  (replaces spmv_ell_kernel ell_spmv.h:47-93, ktt_ell_kernel)          */
   B200SP_K_ELL_LDG = 1,  /* thread per row, coalesced loads, deep unroll      */
   B200SP_K_ELL_BULK = 2, /* slabs staged by cp.async.bulk + mbarrier pipeline  */

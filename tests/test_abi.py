@@ -52,12 +52,15 @@ def test_version_and_strings():
 
 def test_cfg_spaces_enumerate():
     sizes = {f: len(capi.Handle.cfg_space(f, capi.F32)) for f in range(6)}
-    assert sizes[capi.FMT_CSR] == 62 + 45 and sizes[capi.FMT_COO] == 10
+    assert sizes[capi.FMT_CSR] == 62 + 45 + 4 and sizes[capi.FMT_COO] == 10
     assert sizes[capi.FMT_ELL] == sizes[capi.FMT_DIA] == sizes[capi.FMT_ELLR] == 63
     for c in capi.Handle.cfg_space(capi.FMT_CSR, capi.F64):
-        assert c.kernel in (capi.K_CSR_VECTOR, capi.K_CSR_STREAM, capi.K_CSR_RING) and c.block_size in (128, 256, 512)
+        assert c.kernel in (capi.K_CSR_VECTOR, capi.K_CSR_STREAM, capi.K_CSR_RING, capi.K_CSR_BALANCED)
+        assert c.block_size in (128, 256, 512)
         if c.kernel == capi.K_CSR_VECTOR:
             assert c.threads_per_row in (1, 2, 4, 8, 16, 32) and c.unroll in (1, 2, 4)
+        elif c.kernel == capi.K_CSR_BALANCED:
+            assert c.unroll in (5, 7, 9)
         elif c.kernel == capi.K_CSR_RING:
             assert c.unroll in (4, 8, 16) and c.stages in (2, 3, 4) and c.ctas_per_sm in (2, 4, 6)
         else:

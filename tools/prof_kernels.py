@@ -14,6 +14,13 @@ for fmt in which:
     if fmt in ("dia", "ell", "csr"):
         A = gallery.poisson(fmt, 7, (n, n, n), dtype=torch.float64)
         x = ((torch.arange(A.num_cols, device=dev) % 21) - 10).double()
+    elif fmt == "coop":  # COO on the stencil operator: coalesced gathers, isolates the segmented scan
+        from cusp_autotuned_b200.matrix import coo_matrix
+        C = gallery.poisson("csr", 7, (n, n, n), dtype=torch.float64)
+        lens = (C.row_offsets[1:] - C.row_offsets[:-1]).to(torch.int64)
+        ri = torch.repeat_interleave(torch.arange(C.num_rows, device=dev, dtype=torch.int32), lens)
+        A = coo_matrix(C.num_rows, C.num_cols, ri, C.column_indices, C.values)
+        x = ((torch.arange(A.num_cols, device=dev) % 21) - 10).double()
     else:
         A = convert.rmat(22, 16, seed=42, dtype=torch.float32)
         x = torch.rand(A.num_cols, device=dev) + 0.5
