@@ -360,10 +360,18 @@ __global__ void __launch_bounds__(CG_BLOCK) cg_direction_p2p_kernel(i64 n, const
                                                                     unsigned int *ticket, double *residuals,
                                                                     P2PView c, unsigned tag,
                                                                     unsigned long long epoch, i64 halo_lo,
-                                                                    i64 halo_hi, T *dst_lo, T *dst_hi) {
+                                                                    i64 halo_hi, T *dst_lo, T *dst_hi,
+                                                                    int defer_wait) {
   __shared__ T s_rz;
   __shared__ bool is_last;
-  if (S->done) return;
+  if (S->done) {
+    // the solve is over, but a next K1 that waits for this epoch may already be queued on a neighbour
+    if (defer_wait && blockIdx.x == 0 && threadIdx.x == 0) {
+      if (dst_lo) st_release_sys(&c.peer[c.rank - 1]->halo_flag[1], epoch);
+      if (dst_hi) st_release_sys(&c.peer[c.rank + 1]->halo_flag[0], epoch);
+    }
+    return;
+  }
   if (threadIdx.x < 32) {
     const T t = p2p_sum_warp<T>(c, 1, tag);
     if (threadIdx.x == 0) s_rz = t;
@@ -426,11 +434,13 @@ __global__ void __launch_bounds__(CG_BLOCK) cg_direction_p2p_kernel(i64 n, const
     S->rz = rz_new;
     S->iter += 1;
     monitor_step(S, residuals);
+    // defer_wait: the next K1 (DIA bulk kernel) visits its halo-reading tiles last and waits
+    // for these flags there, so the arrival latency hides behind its interior tiles
     SpinGuard guard;
-    if (dst_lo)
+    if (dst_lo && !defer_wait)
       while (ld_acquire_sys(&c.mine->halo_flag[0]) < epoch && !guard.expired(c.mine)) {
       }
-    if (dst_hi)
+    if (dst_hi && !defer_wait)
       while (ld_acquire_sys(&c.mine->halo_flag[1]) < epoch && !guard.expired(c.mine)) {
       }
     *ticket = 0;
@@ -564,6 +574,15 @@ static b200sp_status cg_impl(b200sp_handle h, cudaStream_t st, const b200sp_matr
   P2PView view;
   T *dst_lo = nullptr, *dst_hi = nullptr;
   unsigned long long solve = 0, kiter = 0;
+  // DIA through the bulk kernel: K3 does not wait for the neighbours' planes; the next K1 does,
+  // just before the tiles that read them (visited last)
+  b200sp_cfg cached_cfg;
+  const b200sp_cfg *use_cfg = cfg;
+  if (!use_cfg && b200sp_tune_lookup(h, A, &cached_cfg)) use_cfg = &cached_cfg;
+  const bool defer = p2p && A->format == B200SP_FMT_DIA &&
+                     dia_can_fuse_xchg(A->num_rows, A->num_cols_per_row, A->pitch, A->values, sizeof(T), use_cfg) &&
+                     ((size_t)halo_lo * sizeof(T)) % 128 == 0 && ((size_t)(halo_lo + n) * sizeof(T)) % 128 == 0 &&
+                     (reinterpret_cast<uintptr_t>(pwin) & 127) == 0;
   if (p2p) {
     void *dl = nullptr, *dh = nullptr;
     s = comm_p2p_map_windows(h, st, h->cg_ws, (size_t)((char *)pwin - (char *)h->cg_ws), n, halo_lo, halo_hi,
@@ -580,14 +599,32 @@ static b200sp_status cg_impl(b200sp_handle h, cudaStream_t st, const b200sp_matr
   while (!hs->done) {
     for (int k = 0; k < prm.check_interval; ++k) {
       if (p2p) {
+        const unsigned long long prev_epoch = (solve << 32) | kiter;
         const unsigned long long epoch = (solve << 32) | (++kiter);
         const unsigned tag = (unsigned)((solve << 20) + kiter);  // differs from whatever the slot held before
-        s = spmv_any<T>(h, st, A, pwin, y, 0, cfg, p, &S->yp);
+        if (defer && kiter > 1) {
+          // K1 waits for the planes of p that the neighbours' previous K3 stored here
+          FusedXchg xw;
+          memset(&xw, 0, sizeof(xw));
+          xw.enabled = 2;
+          xw.mine = view.mine;
+          xw.lo_bytes = dst_lo ? (size_t)halo_lo * sizeof(T) : 0;
+          xw.hi_bytes = dst_hi ? (size_t)halo_hi * sizeof(T) : 0;
+          xw.wait_lo = &view.mine->halo_flag[0];
+          xw.wait_hi = &view.mine->halo_flag[1];
+          xw.wait_epoch = prev_epoch;
+          int fused = 0;
+          s = spmv_dia_xchg<T>(h, st, A->num_rows, A->num_cols, A->num_cols_per_row, A->pitch, A->diagonal_offsets,
+                               reinterpret_cast<const T *>(A->values), pwin, y, 0, use_cfg, p, &S->yp, &xw, &fused);
+          if (s == B200SP_OK && !fused) s = set_error(h, B200SP_COMM_ERROR, "cg_dist: deferred halo wait was not launched");
+        } else {
+          s = spmv_any<T>(h, st, A, pwin, y, 0, cfg, p, &S->yp);
+        }
         if (s != B200SP_OK) return s;
         cg_update_p2p_kernel<T><<<(unsigned)g, CG_BLOCK, 0, st>>>(n, p, y, x, r, S, partials, ticket, view, tag);
         B200SP_LAUNCH_CHECK(h, "cg_update_p2p_kernel");
         cg_direction_p2p_kernel<T><<<(unsigned)g, CG_BLOCK, 0, st>>>(n, r, p, S, ticket + 1, res, view, tag, epoch,
-                                                                     halo_lo, halo_hi, dst_lo, dst_hi);
+                                                                     halo_lo, halo_hi, dst_lo, dst_hi, defer ? 1 : 0);
         B200SP_LAUNCH_CHECK(h, "cg_direction_p2p_kernel");
         continue;
       }

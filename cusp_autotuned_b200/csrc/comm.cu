@@ -344,6 +344,8 @@ bool comm_fused_xchg_prepare(b200sp_handle h, void *window, i64 n, i64 halo_lo, 
   xc->mail_hi_nbr = has_hi ? reinterpret_cast<Mailbox *>(h->peer_mail[h->rank + 1]) : nullptr;
   xc->tickets = h->red_counters + 4;
   xc->epoch = ++h->xchg_epoch;
+  xc->wait_lo = xc->wait_hi = &xc->mine->xchg_go;  // raised locally when both planes are in the window
+  xc->wait_epoch = xc->epoch;
   return true;
 }
 

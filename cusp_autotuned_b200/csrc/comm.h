@@ -79,7 +79,10 @@ b200sp_status comm_p2p_map_windows(b200sp_handle h, cudaStream_t st, void *ws_ba
 // are visited in rotated order so that the tiles which read halo columns come last;
 // their consumers wait on a local flag that is raised when the copy-out is complete.
 struct FusedXchg {
-  int enabled;
+  int enabled;  // 0: off   1: exchange inside the kernel   2: only wait for flags raised by someone else
+  // consumers of tiles that read the lower / upper halo wait until *wait_lo / *wait_hi >= wait_epoch
+  const unsigned long long *wait_lo, *wait_hi;
+  unsigned long long wait_epoch;
   char *window;        // x window base [halo_lo | local | halo_hi]
   size_t local_off, n_bytes, lo_bytes, hi_bytes;
   char *stage_mine, *stage_lo_nbr, *stage_hi_nbr;  // nullptr where there is no neighbour

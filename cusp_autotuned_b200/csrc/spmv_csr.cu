@@ -39,6 +39,9 @@ template <typename T>
 b200sp_status spmv_csr_balanced(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64 nnz, const int *Ap,
                                 const int *Aj, const T *Ax, const T *x, T *y, int accumulate, int block, int vpt);
 
+template <typename T, int MODE>
+b200sp_status reduce(b200sp_handle, cudaStream_t, i64, const T *, const T *, T *, T *);  // blas1.cu
+
 template <typename T>
 struct CsrArgs {
   i64 rows, cols, nnz;
@@ -618,8 +621,9 @@ b200sp_status spmv_csr(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64
   b200sp_cfg c = cfg ? *cfg : b200sp_cfg{};
   csr_defaults(c, rows, nnz, sizeof(T));
   if (c.kernel == B200SP_K_CSR_BALANCED) {
-    if (dotv) return set_error(h, B200SP_INVALID_INPUT, "csr balanced: no fused dot epilogue");
-    return spmv_csr_balanced<T>(h, st, rows, cols, nnz, Ap, Aj, Ax, x, y, accumulate, c.block_size, c.unroll);
+    b200sp_status bs = spmv_csr_balanced<T>(h, st, rows, cols, nnz, Ap, Aj, Ax, x, y, accumulate, c.block_size, c.unroll);
+    if (bs != B200SP_OK || !dotv) return bs;
+    return reduce<T, 0>(h, st, rows, y, dotv, dot_result, nullptr);  // no fused epilogue: separate deterministic dot
   }
   if (c.kernel != B200SP_K_CSR_VECTOR && c.kernel != B200SP_K_CSR_STREAM && c.kernel != B200SP_K_CSR_RING)
     return set_error(h, B200SP_INVALID_INPUT, "csr: unknown kernel id %d", c.kernel);

@@ -152,6 +152,12 @@ __global__ void __launch_bounds__(BLOCK) dia_ldg_kernel(DiaArgs<T> a) {
 // ---------------------------------------------------------------------------
 constexpr int DIA_KC = 8;  // diagonals per stage
 
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ void xchg_copy16(char *dst, const char *src, size_t bytes, size_t tid, size_t nthreads) {
   const size_t n16 = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) ? 0 : bytes / 16;
   const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
@@ -255,7 +261,7 @@ __global__ void __launch_bounds__(BLOCK + 32) dia_bulk_kernel(DiaArgs<T> a, int 
           }
         }
       }
-    } else if (a.xc.enabled) {
+    } else if (a.xc.enabled == 1) {
       dia_xchg_aux(a.xc, tid - BLOCK);
     }
   } else {
@@ -263,21 +269,28 @@ __global__ void __launch_bounds__(BLOCK + 32) dia_bulk_kernel(DiaArgs<T> a, int 
     int s = 0;
     uint32_t ph = 0;
     const int lane = tid & 31;
-    bool halo_ready = !a.xc.enabled;
+    bool ready_lo = !a.xc.enabled, ready_hi = !a.xc.enabled;
     for (i64 seq = blockIdx.x; seq < num_tiles; seq += gridDim.x) {
       i64 tile = seq + a.xc.rot;
       if (tile >= num_tiles) tile -= num_tiles;
-      if (!halo_ready && (tile < a.xc.lo_tiles || tile >= a.xc.hi_tile_begin)) {
-        // first tile of this warp that reads halo columns: the copy-out must be complete
+      // first tile of this warp that reads halo columns: the planes must have landed
+      if (!ready_lo && tile < a.xc.lo_tiles) {
         if (lane == 0) {
-          unsigned long long v;
           SpinGuard guard;
-          do {
-            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(&a.xc.mine->xchg_go) : "memory");
-          } while (v < a.xc.epoch && !guard.expired(a.xc.mine));
+          while (ld_acquire_sys_u64(a.xc.wait_lo) < a.xc.wait_epoch && !guard.expired(a.xc.mine)) {
+          }
         }
         __syncwarp();
-        halo_ready = true;
+        ready_lo = true;
+      }
+      if (!ready_hi && tile >= a.xc.hi_tile_begin) {
+        if (lane == 0) {
+          SpinGuard guard;
+          while (ld_acquire_sys_u64(a.xc.wait_hi) < a.xc.wait_epoch && !guard.expired(a.xc.mine)) {
+          }
+        }
+        __syncwarp();
+        ready_hi = true;
       }
       const unsigned r0 = (unsigned)(a.row_begin + tile * R);
       T acc[RPT];
@@ -479,10 +492,10 @@ b200sp_status spmv_dia_xchg(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols
     if (ok && xchg && xchg->enabled) {
       // fused halo exchange: the tiles that read halo columns are visited last
       a.xc = *xchg;
-      const i64 lo_rows = (i64)(a.xc.mail_lo_nbr ? a.xc.lo_bytes / sizeof(T) : 0);
-      const i64 hi_rows = (i64)(a.xc.mail_hi_nbr ? a.xc.hi_bytes / sizeof(T) : 0);
+      const i64 lo_rows = (i64)(a.xc.lo_bytes / sizeof(T));  // 0 where there is no neighbour
+      const i64 hi_rows = (i64)(a.xc.hi_bytes / sizeof(T));
       a.xc.lo_tiles = ceil_div(lo_rows, (i64)R);
-      a.xc.hi_tile_begin = (rows - hi_rows) / R;
+      a.xc.hi_tile_begin = hi_rows > 0 ? (rows - hi_rows) / R : tiles;
       a.xc.rot = a.xc.lo_tiles;
       if (a.xc.lo_tiles + (tiles - a.xc.hi_tile_begin) >= tiles) a.xc.rot = 0;  // no interior to hide behind
       *xchg_fused = 1;

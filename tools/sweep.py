@@ -2,6 +2,7 @@
 
   python tools/sweep.py csr256        CSR cfg space on poisson7pt 256^3, fp32+fp64
   python tools/sweep.py coo256        COO / HYB cfg spaces on poisson7pt 256^3 (coalesced gathers)
+  python tools/sweep.py csr512sq      CSR cfg space on poisson5pt 512^2 (BASELINE configs[0], L2-resident)
   python tools/sweep.py rmat [scale]  CSR / COO / HYB on the R-MAT graph (power-law rows, random gathers)
   python tools/sweep.py random        BASELINE configs[3]: CSR space over random matrices, 2^20 rows,
                                       4..256 nnz/row (the csr_vector threads-per-row sweep of
@@ -24,7 +25,7 @@ dev = torch.device("cuda", 0)
 h = cusp.default_handle()
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 REPS = int(os.environ.get("SWEEP_REPS", "10"))
-KNAME = {capi.FMT_CSR: {1: "vector", 2: "stream", 3: "ring"}, capi.FMT_COO: {1: "segscan"},
+KNAME = {capi.FMT_CSR: {1: "vector", 2: "stream", 3: "ring", 4: "balanced"}, capi.FMT_COO: {1: "segscan"},
          capi.FMT_HYB: {1: "ldg", 2: "bulk"}}
 
 
@@ -115,6 +116,11 @@ def main():
                 H = convert.csr_to_hyb(A, num_entries_per_row=6)  # force a COO tail of one entry per interior row
                 sweep(f"hyb(K=6) poisson7pt {n}^3 {dtype}", H, x, space=[], out=out)
             del A, x
+    elif what == "csr512sq":  # BASELINE configs[0]: L2-resident, launch-latency territory
+        for dtype in (torch.float32, torch.float64):
+            A = gallery.poisson5pt(512, 512, fmt="csr", dtype=dtype)
+            x = torch.rand(A.num_cols, dtype=dtype, device=dev) + 0.5
+            sweep(f"csr poisson5pt 512^2 {dtype}", A, x, out=out)
     elif what == "rmat":
         scale = int(sys.argv[2]) if len(sys.argv) > 2 else 24
         C = convert.rmat(scale, 16, seed=42, dtype=torch.float32)
