@@ -121,6 +121,22 @@ def main():
             A = gallery.poisson5pt(512, 512, fmt="csr", dtype=dtype)
             x = torch.rand(A.num_cols, dtype=dtype, device=dev) + 0.5
             sweep(f"csr poisson5pt 512^2 {dtype}", A, x, out=out)
+    elif what == "gather":
+        # how fast can this GPU gather 4-byte words at all?  (library kernel, not ours: torch.index_select)
+        # R-MAT column stream vs uniformly random indices vs a sorted (coalescable) stream, 2^24-entry table
+        C = convert.rmat(24, 16, seed=42, dtype=torch.float32)
+        x = torch.rand(C.num_cols, dtype=torch.float32, device=dev)
+        n = C.num_entries
+        streams = {"rmat_columns": C.column_indices,
+                   "uniform_random": torch.randint(0, C.num_cols, (n,), device=dev, dtype=torch.int32),
+                   "sorted": torch.sort(torch.randint(0, C.num_cols, (n,), device=dev, dtype=torch.int32))[0]}
+        for name, idx in streams.items():
+            ms = timeit(lambda: torch.index_select(x, 0, idx))
+            rec = dict(label=f"gather {name}", n=n, ms=ms, gathers_per_s=n / ms * 1e3,
+                       gathers_per_clk_per_sm=n / (ms * 1e-3) / 148 / 1.965e9)
+            out.append(rec)
+            print(f"## gather {name}: {n} x 4 B from a 64 MiB table  {ms:.4f} ms  {rec['gathers_per_s'] / 1e9:.1f} G/s  "
+                  f"{rec['gathers_per_clk_per_sm']:.2f} per clk per SM", flush=True)
     elif what == "rmat":
         scale = int(sys.argv[2]) if len(sys.argv) > 2 else 24
         C = convert.rmat(scale, 16, seed=42, dtype=torch.float32)
