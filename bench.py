@@ -37,6 +37,9 @@ sys.path.insert(0, ROOT)
 GRID = (256, 256, 256)        # BASELINE configs[1]
 CG_GRID = (512, 512, 512)     # BASELINE configs[4]
 HEAD_FMT, HEAD_DT = "dia", "f64"
+# the same string in both arms (ours and --impl reference)
+WORKLOAD = ("cusp::gallery::poisson7pt 256^3 per GPU, DIA fp64, y = A x (BASELINE configs[1]); "
+            "N>1: blocks stacked along z, halo exchange per step")
 
 
 def peaks():
@@ -163,8 +166,7 @@ def run_reference(args):
         "impl": "reference", "metric": "spmv_gflops", "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cusp::gallery::poisson7pt 256^3 DIA fp64 SpMV (BASELINE configs[1])",
-                   "format": "dia", "rows": rows, "nnz": nnz, "sample_rows": srows,
+        "config": {"workload": WORKLOAD, "format": "dia", "rows": rows, "nnz": nnz, "sample_rows": srows,
                    "path": "cusp/system/detail/sequential/multiply/dia_spmv.h over row blocks, std::thread"},
         "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -435,9 +437,7 @@ def main():
             "metric": "spmv_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cusp::gallery::poisson7pt 256^3 per GPU, DIA fp64, y = A x "
-                                   "(BASELINE configs[1]); N>1: blocks stacked along z, halo exchange per step",
-                       "format": "dia", "rows_per_gpu": blk.num_rows, "nnz_total": nnz_total,
+            "config": {"workload": WORKLOAD, "format": "dia", "rows_per_gpu": blk.num_rows, "nnz_total": nnz_total,
                        "x": "x_i = (i mod 21) - 10 (performance/spmv/benchmark.h convention)",
                        "l2": "per-step inputs (1.21 GB) exceed the 126 MB L2, no flush needed",
                        "parallelism": f"rowblock{world}", "api": "b200sp_spmv / b200sp_spmv_dist (C ABI)"},

@@ -73,6 +73,19 @@ struct b200sp_context {
   size_t cg_residuals_cap = 0;
 
   std::map<b200sp_tune_key, b200sp_tune_entry> tune_cache;
+  // CSR structure analysis (longest row) per (row_offsets pointer, rows, nnz): decides between the
+  // row-split kernels and the nnz-balanced one when the caller gives no configuration.  Only a
+  // performance hint — every kernel is correct for every matrix — so a stale entry is harmless.
+  struct CsrKey {
+    const void *ap;
+    int64_t rows, nnz;
+    bool operator<(const CsrKey &o) const {
+      if (ap != o.ap) return ap < o.ap;
+      if (rows != o.rows) return rows < o.rows;
+      return nnz < o.nnz;
+    }
+  };
+  std::map<CsrKey, int> csr_max_row;
   std::vector<void *> tune_events;  // cudaEvent_t pair
 
   // multi-GPU

@@ -557,8 +557,43 @@ static b200sp_status dispatch_tpr(b200sp_handle h, cudaStream_t st, const CsrArg
   return set_error(h, B200SP_INVALID_INPUT, "csr: unsupported threads_per_row=%d unroll=%d", tpr, rpt);
 }
 
-static void csr_defaults(b200sp_cfg &c, i64 rows, i64 nnz, size_t elem) {
+// longest row of the matrix (one pass over row_offsets, result cached in the handle)
+__global__ void csr_max_row_kernel(i64 rows, const int *Ap, int *out) {
+  int m = 0;
+  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (i64)gridDim.x * blockDim.x)
+    m = max(m, Ap[r + 1] - Ap[r]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+static int csr_longest_row(b200sp_handle h, cudaStream_t st, i64 rows, i64 nnz, const int *Ap) {
+  const b200sp_context::CsrKey key{Ap, rows, nnz};
+  auto it = h->csr_max_row.find(key);
+  if (it != h->csr_max_row.end()) return it->second;
+  int *d = reinterpret_cast<int *>(h->dev_scalars + 60);
+  int *p = reinterpret_cast<int *>(h->pinned_scalars + 60);
+  int longest = -1;
+  if (cudaMemsetAsync(d, 0, sizeof(int), st) == cudaSuccess) {
+    i64 g = ceil_div(rows, 256);
+    if (g > (i64)h->num_sms * 16) g = (i64)h->num_sms * 16;
+    csr_max_row_kernel<<<(unsigned)g, 256, 0, st>>>(rows, Ap, d);
+    h->launches++;
+    if (cudaMemcpyAsync(p, d, sizeof(int), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+        cudaStreamSynchronize(st) == cudaSuccess)
+      longest = *p;
+  }
+  cudaGetLastError();
+  if (h->csr_max_row.size() > 256) h->csr_max_row.clear();
+  if (longest >= 0) h->csr_max_row[key] = longest;
+  return longest;
+}
+
+static void csr_defaults(b200sp_cfg &c, i64 rows, i64 nnz, size_t elem, int longest_row) {
   const double mean = rows > 0 ? (double)nnz / (double)rows : 0.0;
+  // skewed row lengths (power-law graphs): one hub row would serialise a row-split kernel
+  if (c.kernel == 0 && longest_row > 2048 && (double)longest_row > 64.0 * (mean > 1.0 ? mean : 1.0))
+    c.kernel = B200SP_K_CSR_BALANCED;
   if (c.kernel == 0) {
     // round-1 sweeps on B200 (profiles/r01_sweep_*.md): short rows -> thread-per-row from a
     // TMA-staged ring (RING; STREAM when the matrix is too small to fill persistent CTAs);
@@ -619,7 +654,8 @@ b200sp_status spmv_csr(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64
   B200SP_REQUIRE(h, cols > 0, "csr: num_cols == 0 with stored entries");
 
   b200sp_cfg c = cfg ? *cfg : b200sp_cfg{};
-  csr_defaults(c, rows, nnz, sizeof(T));
+  const int longest = (c.kernel == 0) ? csr_longest_row(h, st, rows, nnz, Ap) : -1;
+  csr_defaults(c, rows, nnz, sizeof(T), longest);
   if (c.kernel == B200SP_K_CSR_BALANCED) {
     b200sp_status bs = spmv_csr_balanced<T>(h, st, rows, cols, nnz, Ap, Aj, Ax, x, y, accumulate, c.block_size, c.unroll);
     if (bs != B200SP_OK || !dotv) return bs;
