@@ -7,6 +7,9 @@
 // JIT-compiles every configuration with NVRTC; here every point of the space is
 // a precompiled template instantiation, so a tuning step costs one launch.
 #include <stdarg.h>
+#include <stdlib.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -393,6 +396,9 @@ b200sp_status b200sp_destroy(b200sp_handle h) {
   if (h->red_counters) cudaFree(h->red_counters);
   if (h->dev_scalars) cudaFree(h->dev_scalars);
   if (h->pinned_scalars) cudaFreeHost(h->pinned_scalars);
+  for (void *e : h->pipe_events) cudaEventDestroy((cudaEvent_t)e);
+  if (h->copy_in_stream) cudaStreamDestroy((cudaStream_t)h->copy_in_stream);
+  if (h->copy_out_stream) cudaStreamDestroy((cudaStream_t)h->copy_out_stream);
   if (h->stage_x) cudaFree(h->stage_x);
   if (h->stage_y) cudaFree(h->stage_y);
   if (h->cg_ws) cudaFree(h->cg_ws);
@@ -430,6 +436,109 @@ b200sp_status b200sp_set_l2_persist(b200sp_handle h, b200sp_stream stream, const
   B200SP_CUDA(h, cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &attr));
   return B200SP_OK;
 }
+}  // extern "C"
+
+namespace b200sp {
+
+// DIA matrices are banded: rows [r0, r1) only read x[r0 + min_off, r1 + max_off).  The host
+// path therefore runs as a pipeline over row chunks — x pieces go up on one copy stream, the
+// chunk products run on the caller's stream as soon as their columns have landed, y chunks go
+// down on a second copy stream — so the two PCIe directions and the kernels overlap instead of
+// running back to back.  Same kernels, same per-row arithmetic: results are bit-identical to
+// the one-shot path.  *done = 0 when the matrix does not qualify (caller falls back).
+static b200sp_status spmv_host_pipelined_dia(b200sp_handle h, cudaStream_t st, const b200sp_matrix *A,
+                                             const void *x_host, void *y_host, const b200sp_cfg *cfg, int *done) {
+  *done = 0;
+  const i64 K = A->num_cols_per_row, rows = A->num_rows, cols = A->num_cols;
+  const size_t elem = A->dtype == B200SP_F64 ? 8 : 4;
+  if (K <= 0 || K > 1024 || rows < (1 << 20)) return B200SP_OK;
+  std::vector<int> off((size_t)K);
+  B200SP_CUDA(h, cudaMemcpyAsync(off.data(), A->diagonal_offsets, (size_t)K * sizeof(int), cudaMemcpyDeviceToHost, st));
+  B200SP_CUDA(h, cudaStreamSynchronize(st));
+  i64 lo = 0, up = 0;
+  for (int o : off) {
+    lo = o < -lo ? -(i64)o : lo;  // lo = max(0, -min_off)
+    up = o > up ? (i64)o : up;    // up = max(0, max_off)
+  }
+  const int want_chunks = 16;
+  i64 chunk = ((ceil_div(rows, (i64)want_chunks) + 1023) / 1024) * 1024;
+  if (chunk < lo + 1024 || chunk < up + 1024) return B200SP_OK;  // band wider than a chunk: nothing to overlap
+  const int nch = (int)ceil_div(rows, chunk);
+  if (nch < 3) return B200SP_OK;
+  const int npieces = nch;  // x piece p = columns [p*chunk, (p+1)*chunk), the last one runs to `cols`
+
+  if (!h->copy_in_stream) {
+    cudaStream_t a, b;
+    B200SP_CUDA(h, cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+    B200SP_CUDA(h, cudaStreamCreateWithFlags(&b, cudaStreamNonBlocking));
+    h->copy_in_stream = a;
+    h->copy_out_stream = b;
+  }
+  const size_t need_events = (size_t)2 * nch + 2;
+  while (h->pipe_events.size() < need_events) {
+    cudaEvent_t e;
+    B200SP_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->pipe_events.push_back(e);
+  }
+  cudaStream_t cin = (cudaStream_t)h->copy_in_stream, cout = (cudaStream_t)h->copy_out_stream;
+  auto ev = [&](size_t i) { return (cudaEvent_t)h->pipe_events[i]; };
+
+  // diagonal offsets shifted by `lo` for chunks that address x through a window starting at r0 - lo
+  b200sp_status s = ensure_scratch(h, (size_t)K * sizeof(int));
+  if (s != B200SP_OK) return s;
+  std::vector<int> off_shift((size_t)K);
+  for (i64 k = 0; k < K; ++k) off_shift[(size_t)k] = off[(size_t)k] + (int)lo;
+  int *d_off_shift = reinterpret_cast<int *>(h->scratch);
+  B200SP_CUDA(h, cudaMemcpyAsync(d_off_shift, off_shift.data(), (size_t)K * sizeof(int), cudaMemcpyHostToDevice, st));
+
+  char *dx = reinterpret_cast<char *>(h->stage_x), *dy = reinterpret_cast<char *>(h->stage_y);
+  const char *hx = reinterpret_cast<const char *>(x_host);
+  char *hy = reinterpret_cast<char *>(y_host);
+  B200SP_CUDA(h, cudaEventRecord(ev(0), st));  // staging buffers are free once prior work on `st` is done
+  B200SP_CUDA(h, cudaStreamWaitEvent(cin, ev(0), 0));
+  B200SP_CUDA(h, cudaStreamWaitEvent(cout, ev(0), 0));
+  for (int p = 0; p < npieces; ++p) {
+    const i64 c0 = (i64)p * chunk, c1 = (p == npieces - 1) ? cols : std::min(cols, c0 + chunk);
+    if (c1 > c0)
+      B200SP_CUDA(h, cudaMemcpyAsync(dx + (size_t)c0 * elem, hx + (size_t)c0 * elem, (size_t)(c1 - c0) * elem,
+                                     cudaMemcpyHostToDevice, cin));
+    B200SP_CUDA(h, cudaEventRecord(ev(1 + (size_t)p), cin));
+  }
+  for (int c = 0; c < nch; ++c) {
+    const i64 r0 = (i64)c * chunk, r1 = std::min(rows, r0 + chunk);
+    const i64 last_col = std::min(cols, r1 + up) - 1;
+    int p = (int)(last_col / chunk);
+    if (p > npieces - 1) p = npieces - 1;
+    B200SP_CUDA(h, cudaStreamWaitEvent(st, ev(1 + (size_t)p), 0));
+    b200sp_matrix sub = *A;
+    sub.num_rows = r1 - r0;
+    sub.values = reinterpret_cast<const char *>(A->values) + (size_t)r0 * elem;
+    const void *xp;
+    if (c == 0) {
+      xp = dx;  // original offsets, x from column 0
+    } else {
+      sub.diagonal_offsets = d_off_shift;
+      sub.num_cols = cols - (r0 - lo);
+      xp = dx + (size_t)(r0 - lo) * elem;
+    }
+    sub.num_entries = 0;
+    s = b200sp_spmv(h, (b200sp_stream)st, &sub, xp, dy + (size_t)r0 * elem, 0, cfg);
+    if (s != B200SP_OK) return s;
+    B200SP_CUDA(h, cudaEventRecord(ev(1 + (size_t)nch + (size_t)c), st));
+    B200SP_CUDA(h, cudaStreamWaitEvent(cout, ev(1 + (size_t)nch + (size_t)c), 0));
+    B200SP_CUDA(h, cudaMemcpyAsync(hy + (size_t)r0 * elem, dy + (size_t)r0 * elem, (size_t)(r1 - r0) * elem,
+                                   cudaMemcpyDeviceToHost, cout));
+  }
+  B200SP_CUDA(h, cudaEventRecord(ev(1 + 2 * (size_t)nch), cout));
+  B200SP_CUDA(h, cudaStreamWaitEvent(st, ev(1 + 2 * (size_t)nch), 0));
+  B200SP_CUDA(h, cudaStreamSynchronize(st));
+  *done = 1;
+  return B200SP_OK;
+}
+
+}  // namespace b200sp
+
+extern "C" {
 
 b200sp_status b200sp_spmv_host(b200sp_handle h, b200sp_stream stream, const b200sp_matrix *A,
                                const void *x_host, void *y_host, int accumulate, const b200sp_cfg *cfg) {
@@ -457,6 +566,11 @@ b200sp_status b200sp_spmv_host(b200sp_handle h, b200sp_stream stream, const b200
       return b200sp::set_error(h, B200SP_ALLOC_FAILED, "spmv_host: cannot stage y (%zu B)", yb);
     }
     h->stage_y_bytes = yb;
+  }
+  if (!accumulate && A->format == B200SP_FMT_DIA && !getenv("B200SP_HOST_ONE_SHOT")) {
+    int done = 0;
+    b200sp_status ps = b200sp::spmv_host_pipelined_dia(h, st, A, x_host, y_host, cfg, &done);
+    if (ps != B200SP_OK || done) return ps;
   }
   B200SP_CUDA(h, cudaMemcpyAsync(h->stage_x, x_host, xb, cudaMemcpyHostToDevice, st));
   if (accumulate) B200SP_CUDA(h, cudaMemcpyAsync(h->stage_y, y_host, yb, cudaMemcpyHostToDevice, st));

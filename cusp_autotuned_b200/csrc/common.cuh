@@ -66,6 +66,9 @@ struct b200sp_context {
   // host-buffer entry points
   void *stage_x = nullptr, *stage_y = nullptr;
   size_t stage_x_bytes = 0, stage_y_bytes = 0;
+  // pipelined host path (b200sp_spmv_host on banded matrices): copy streams + events
+  void *copy_in_stream = nullptr, *copy_out_stream = nullptr;
+  std::vector<void *> pipe_events;
   // CG workspace
   void *cg_ws = nullptr;
   size_t cg_ws_bytes = 0;

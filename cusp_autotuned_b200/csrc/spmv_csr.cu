@@ -557,39 +557,68 @@ static b200sp_status dispatch_tpr(b200sp_handle h, cudaStream_t st, const CsrArg
   return set_error(h, B200SP_INVALID_INPUT, "csr: unsupported threads_per_row=%d unroll=%d", tpr, rpt);
 }
 
-// longest row of the matrix (one pass over row_offsets, result cached in the handle)
-__global__ void csr_max_row_kernel(i64 rows, const int *Ap, int *out) {
-  int m = 0;
-  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (i64)gridDim.x * blockDim.x)
-    m = max(m, Ap[r + 1] - Ap[r]);
+// structure analysis, one pass over row_offsets (+ a 1/16 sample of column_indices), cached in
+// the handle: out[0] = longest row, out[1] = sampled row pairs, out[2] = pairs whose first
+// columns are within 32 of each other ("adjacent rows read adjacent x": stencils, banded
+// matrices — the case where thread-per-row gathers coalesce)
+__global__ void csr_analyze_kernel(i64 rows, const int *Ap, const int *Aj, int *out) {
+  int m = 0, pairs = 0, close = 0;
+  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (i64)gridDim.x * blockDim.x) {
+    const int lo = Ap[r], hi = Ap[r + 1];
+    m = max(m, hi - lo);
+    if ((r & 15) == 0 && r + 1 < rows && hi > lo) {
+      const int hi2 = Ap[r + 2];
+      if (hi2 > hi) {
+        ++pairs;
+        const int d = Aj[hi] - Aj[lo];
+        close += (d >= -32 && d <= 32) ? 1 : 0;
+      }
+    }
+  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+  for (int o = 16; o > 0; o >>= 1) {
+    m = max(m, __shfl_down_sync(0xffffffffu, m, o));
+    pairs += __shfl_down_sync(0xffffffffu, pairs, o);
+    close += __shfl_down_sync(0xffffffffu, close, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(out, m);
+    if (pairs) atomicAdd(out + 1, pairs);
+    if (close) atomicAdd(out + 2, close);
+  }
 }
 
-static int csr_longest_row(b200sp_handle h, cudaStream_t st, i64 rows, i64 nnz, const int *Ap) {
+struct CsrStructure {
+  int longest_row;  // -1: unknown
+  bool banded;      // most adjacent rows start at adjacent columns
+};
+
+static CsrStructure csr_structure(b200sp_handle h, cudaStream_t st, i64 rows, i64 nnz, const int *Ap, const int *Aj) {
   const b200sp_context::CsrKey key{Ap, rows, nnz};
   auto it = h->csr_max_row.find(key);
-  if (it != h->csr_max_row.end()) return it->second;
-  int *d = reinterpret_cast<int *>(h->dev_scalars + 60);
-  int *p = reinterpret_cast<int *>(h->pinned_scalars + 60);
-  int longest = -1;
-  if (cudaMemsetAsync(d, 0, sizeof(int), st) == cudaSuccess) {
+  if (it != h->csr_max_row.end()) return CsrStructure{it->second >> 1, (it->second & 1) != 0};
+  int *d = reinterpret_cast<int *>(h->dev_scalars + 58);  // 3 ints
+  int *p = reinterpret_cast<int *>(h->pinned_scalars + 58);
+  CsrStructure r{-1, true};
+  if (cudaMemsetAsync(d, 0, 3 * sizeof(int), st) == cudaSuccess) {
     i64 g = ceil_div(rows, 256);
     if (g > (i64)h->num_sms * 16) g = (i64)h->num_sms * 16;
-    csr_max_row_kernel<<<(unsigned)g, 256, 0, st>>>(rows, Ap, d);
+    csr_analyze_kernel<<<(unsigned)g, 256, 0, st>>>(rows, Ap, Aj, d);
     h->launches++;
-    if (cudaMemcpyAsync(p, d, sizeof(int), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
-        cudaStreamSynchronize(st) == cudaSuccess)
-      longest = *p;
+    if (cudaMemcpyAsync(p, d, 3 * sizeof(int), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+        cudaStreamSynchronize(st) == cudaSuccess) {
+      r.longest_row = p[0];
+      r.banded = p[1] == 0 || 2 * (i64)p[2] >= (i64)p[1];
+    }
   }
   cudaGetLastError();
   if (h->csr_max_row.size() > 256) h->csr_max_row.clear();
-  if (longest >= 0) h->csr_max_row[key] = longest;
-  return longest;
+  if (r.longest_row >= 0) h->csr_max_row[key] = (r.longest_row << 1) | (r.banded ? 1 : 0);
+  return r;
 }
 
-static void csr_defaults(b200sp_cfg &c, i64 rows, i64 nnz, size_t elem, int longest_row) {
+static void csr_defaults(b200sp_cfg &c, i64 rows, i64 nnz, size_t elem, const CsrStructure &cs) {
+  const int longest_row = cs.longest_row;
   const double mean = rows > 0 ? (double)nnz / (double)rows : 0.0;
   // skewed row lengths (power-law graphs): one hub row would serialise a row-split kernel
   if (c.kernel == 0 && longest_row > 2048 && (double)longest_row > 64.0 * (mean > 1.0 ? mean : 1.0))
@@ -598,10 +627,10 @@ static void csr_defaults(b200sp_cfg &c, i64 rows, i64 nnz, size_t elem, int long
     // round-1 sweeps on B200 (profiles/r01_sweep_*.md): short rows -> thread-per-row from a
     // TMA-staged ring (RING; STREAM when the matrix is too small to fill persistent CTAs);
     // longer rows -> lane-per-entry sub-warps (VECTOR).  cusp::ktt::tune refines per matrix.
-    if (mean <= 12.0)
+    if (mean <= 12.0 && cs.banded)
       c.kernel = (rows >= (i64)B200SP_NUM_SMS_FALLBACK * 4 * 256 * 2) ? B200SP_K_CSR_RING : B200SP_K_CSR_STREAM;
     else
-      c.kernel = B200SP_K_CSR_VECTOR;
+      c.kernel = B200SP_K_CSR_VECTOR;  // scattered columns: lane-per-entry keeps the matrix stream coalesced
   }
   if (c.kernel == B200SP_K_CSR_RING) {
     if (c.block_size == 0) c.block_size = 256;
@@ -654,8 +683,8 @@ b200sp_status spmv_csr(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64
   B200SP_REQUIRE(h, cols > 0, "csr: num_cols == 0 with stored entries");
 
   b200sp_cfg c = cfg ? *cfg : b200sp_cfg{};
-  const int longest = (c.kernel == 0) ? csr_longest_row(h, st, rows, nnz, Ap) : -1;
-  csr_defaults(c, rows, nnz, sizeof(T), longest);
+  const CsrStructure cs = (c.kernel == 0) ? csr_structure(h, st, rows, nnz, Ap, Aj) : CsrStructure{-1, true};
+  csr_defaults(c, rows, nnz, sizeof(T), cs);
   if (c.kernel == B200SP_K_CSR_BALANCED) {
     b200sp_status bs = spmv_csr_balanced<T>(h, st, rows, cols, nnz, Ap, Aj, Ax, x, y, accumulate, c.block_size, c.unroll);
     if (bs != B200SP_OK || !dotv) return bs;

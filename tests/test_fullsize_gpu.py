@@ -142,3 +142,45 @@ def test_cg_512cubed_residual_history_properties(dev, handle):
     cusp.blas.axpby(b, r, r, 1.0, -1.0)
     true = cusp.blas.nrm2(r)
     assert abs(true - mon.residuals[-1]) <= 1e-8 * mon.residuals[0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tdt", (torch.float64, torch.float32))
+def test_host_buffer_pipeline_is_bit_identical_to_the_device_product(tdt, dev, handle):
+    """b200sp_spmv_host on a banded (DIA) operator runs as a chunked H2D / SpMV / D2H pipeline
+    (csrc/api.cu); every row is still computed by the same kernel in the same order, so the
+    host-side result equals the device product bit for bit — on generic data, for square and
+    rectangular operators, and after the staging buffers have been reused"""
+    import os
+    n = 160  # 4 096 000 rows: 16 chunks of 256 000 rows, band 25 600
+    A = gallery.poisson("dia", 7, (n, n, n), dtype=tdt)
+    N = A.num_rows
+    g = torch.Generator(device="cpu").manual_seed(5)
+    for rep in range(2):
+        xh = (torch.rand(N, generator=g, dtype=torch.float64) - 0.5).to(tdt).pin_memory()
+        yh = torch.full((N,), 7.0, dtype=tdt).pin_memory()
+        handle.spmv_host(A.descriptor(), xh, yh)
+        y = torch.empty(N, dtype=tdt, device=dev)
+        cusp.multiply(A, xh.to(dev), y)
+        assert torch.equal(yh, y.cpu()), rep
+    # the one-shot path (B200SP_HOST_ONE_SHOT) gives the same bits
+    os.environ["B200SP_HOST_ONE_SHOT"] = "1"
+    try:
+        y2 = torch.empty(N, dtype=tdt).pin_memory()
+        handle.spmv_host(A.descriptor(), xh, y2)
+    finally:
+        del os.environ["B200SP_HOST_ONE_SHOT"]
+    assert torch.equal(y2, yh)
+    # rectangular: more columns than rows (the last x piece runs to num_cols), offsets reaching past the rows
+    rows, cols = 3_000_000, 3_200_000
+    offs = torch.tensor([-70_000, -3, 0, 5, 150_000], dtype=torch.int32, device=dev)
+    vals = (torch.rand(5 * rows, generator=torch.Generator(device=dev).manual_seed(3), device=dev,
+                       dtype=torch.float64) + 0.5).to(tdt)
+    from cusp_autotuned_b200.matrix import dia_matrix
+    B = dia_matrix(rows, cols, 5 * rows, offs, rows, vals)
+    xh = (torch.rand(cols, generator=g, dtype=torch.float64) - 0.5).to(tdt).pin_memory()
+    yh = torch.empty(rows, dtype=tdt).pin_memory()
+    handle.spmv_host(B.descriptor(), xh, yh)
+    y = torch.empty(rows, dtype=tdt, device=dev)
+    cusp.multiply(B, xh.to(dev), y)
+    assert torch.equal(yh, y.cpu())
