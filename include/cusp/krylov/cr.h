@@ -1,0 +1,77 @@
+// cusp/krylov/cr.h — cusp::krylov::cr(A, x, b[, monitor[, M]]): conjugate residuals
+// (reference: cusp/krylov/cr.h, cusp/krylov/detail/cr.inl:35-128), for symmetric
+// (possibly indefinite) A.  SURVEY §8(f) row 3: same hot-path kernels, another
+// fusion pattern; operations are issued in the reference's order, including its
+// periodic recomputation of the true residual every 8 iterations.
+#pragma once
+#include "../array1d.h"
+#include "../blas/blas.h"
+#include "../linear_operator.h"
+#include "../monitor.h"
+#include "../multiply.h"
+
+namespace cusp {
+namespace krylov {
+
+template <typename LinearOperator, typename VectorType1, typename VectorType2, typename Monitor,
+          typename Preconditioner>
+void cr(const LinearOperator &A, VectorType1 &x, const VectorType2 &b, Monitor &monitor, Preconditioner &M) {
+  typedef typename LinearOperator::value_type ValueType;
+  typedef typename LinearOperator::memory_space Space;
+  if (A.num_rows != A.num_cols || x.size() != A.num_rows || b.size() != A.num_rows)
+    throw cusp::invalid_input_exception("cusp::krylov::cr: A must be square and match x, b");
+  const size_t N = A.num_rows;
+  const size_t recompute_r = 8;  // interval at which r is recomputed from b - A x
+  cusp::array1d<ValueType, Space> y(N), z(N), r(N), p(N), Az(N), Ax(N);
+
+  cusp::multiply(A, x, Ax);
+  cusp::blas::axpby(b, Ax, r, ValueType(1), ValueType(-1));  // r <- b - A x
+  cusp::multiply(M, r, z);                                   // z <- M r
+  cusp::blas::copy(z, p);
+  cusp::multiply(A, p, y);                                   // y <- A p
+  cusp::multiply(A, z, Az);
+  ValueType rz = cusp::blas::dotc(r, Az);
+
+  while (!monitor.finished(r)) {
+    const ValueType alpha = rz / cusp::blas::dotc(y, y);
+    cusp::blas::axpy(p, x, alpha);                           // x += alpha p
+    const size_t iter = monitor.iteration_count();
+    if ((iter % recompute_r) && (iter > 0)) {
+      cusp::blas::axpy(y, r, -alpha);                        // r -= alpha A p
+    } else {
+      cusp::multiply(A, x, Ax);
+      cusp::blas::axpby(b, Ax, r, ValueType(1), ValueType(-1));
+    }
+    cusp::multiply(M, r, z);
+    cusp::multiply(A, z, Az);
+    const ValueType rz_old = rz;
+    rz = cusp::blas::dotc(r, Az);
+    const ValueType beta = rz / rz_old;
+    cusp::blas::axpby(z, p, p, ValueType(1), beta);          // p <- z + beta p
+    cusp::blas::axpby(Az, y, y, ValueType(1), beta);         // y <- A z + beta y  (= A p)
+    ++monitor;
+  }
+}
+
+template <typename LinearOperator, typename VectorType1, typename VectorType2, typename Monitor>
+void cr(const LinearOperator &A, VectorType1 &x, const VectorType2 &b, Monitor &monitor) {
+  cusp::identity_operator<typename LinearOperator::value_type, typename LinearOperator::memory_space> M(A.num_rows,
+                                                                                                        A.num_cols);
+  cr(A, x, b, monitor, M);
+}
+
+template <typename LinearOperator, typename VectorType1, typename VectorType2>
+void cr(const LinearOperator &A, VectorType1 &x, const VectorType2 &b) {
+  cusp::monitor<typename LinearOperator::value_type> monitor(b);
+  cr(A, x, b, monitor);
+}
+
+template <typename P, typename LinearOperator, typename VectorType1, typename VectorType2, typename Monitor,
+          typename Preconditioner>
+void cr(const cusp::execution_policy<P> &, const LinearOperator &A, VectorType1 &x, const VectorType2 &b,
+        Monitor &monitor, Preconditioner &M) {
+  cr(A, x, b, monitor, M);
+}
+
+}  // namespace krylov
+}  // namespace cusp
