@@ -404,6 +404,11 @@ def main():
               "includes": "setup SpMV + ||b|| + residual init (1 extra SpMV over %d iterations)" % iters}
         del Ac, b, xs
         torch.cuda.empty_cache()
+        if world > 1:
+            # every rank: no cross-GPU wait may have given up (peer-memory path), else the numbers are void
+            bad = torch.tensor([h.comm_timeouts()], dtype=torch.int64, device=dev)
+            td.all_reduce(bad, op=td.ReduceOp.MAX)
+            assert int(bad.item()) == 0, f"{int(bad.item())} cross-GPU waits timed out: results invalid"
 
         # ---- CPU baseline: the reference's host loop on this box's cores (rank 0, N == 1) -----------
         if world == 1 and rank == 0:

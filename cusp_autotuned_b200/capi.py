@@ -118,7 +118,7 @@ EXPORTED_SYMBOLS = (
      "b200sp_status_string", "b200sp_launch_count", "b200sp_set_l2_persist",
      "b200sp_ell_row_lengths", "b200sp_spmv", "b200sp_spmv_host", "b200sp_cg",
      "b200sp_comm_unique_id", "b200sp_comm_init", "b200sp_comm_destroy", "b200sp_cg_dist",
-     "b200sp_spmv_dist", "b200sp_comm_p2p_enabled", "b200sp_cfg_space", "b200sp_tune", "b200sp_tune_step",
+     "b200sp_spmv_dist", "b200sp_comm_p2p_enabled", "b200sp_comm_timeouts", "b200sp_cfg_space", "b200sp_tune", "b200sp_tune_step",
      "b200sp_tune_reset", "b200sp_tune_lookup", "b200sp_tune_save", "b200sp_tune_load",
      "b200sp_poisson_num_entries", "b200sp_poisson_csr_offsets"]
     + [f"b200sp_spmv_{f}_{s}" for f in ("csr", "ell", "dia", "coo", "hyb", "ellr") for s in _SFX]
@@ -360,6 +360,11 @@ class Handle:
 
     def comm_destroy(self):
         self.check(self.lib.b200sp_comm_destroy(self._h))
+
+    def comm_timeouts(self) -> int:
+        """cross-GPU waits that gave up since comm_init (must be 0 for valid results)"""
+        self.lib.b200sp_comm_timeouts.restype = C.c_int64
+        return int(self.lib.b200sp_comm_timeouts(self._h, _stream()))
 
     def comm_p2p_enabled(self) -> bool:
         """True when cg_dist runs its exchanges as stores into NVLink peer memory"""

@@ -470,6 +470,18 @@ b200sp_status b200sp_comm_init(b200sp_handle h, const void *id128, int world_siz
 
 int b200sp_comm_p2p_enabled(b200sp_handle h) { return (h && h->p2p_ok) ? 1 : 0; }
 
+int64_t b200sp_comm_timeouts(b200sp_handle h, b200sp_stream stream) {
+  if (!h || !h->p2p_ok || !h->mail) return 0;
+  unsigned long long t = 0;
+  b200sp::Mailbox *m = reinterpret_cast<b200sp::Mailbox *>(h->mail);
+  if (cudaMemcpyAsync(&t, &m->timeouts, sizeof(t), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess ||
+      cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return (int64_t)t;
+}
+
 b200sp_status b200sp_comm_destroy(b200sp_handle h) {
   B200SP_CHECK_HANDLE(h);
   if (h->nccl_comm) {

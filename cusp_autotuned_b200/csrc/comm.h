@@ -36,7 +36,7 @@ struct Mailbox {
   unsigned long long timeouts;      // spin loops that gave up (a peer never arrived): results are invalid
 };
 #ifdef __CUDACC__
-// every cross-GPU spin is bounded (~4 s of SM clocks): a peer that died must not hang this GPU
+// every cross-GPU spin is bounded (~0.5 s of SM clocks): a peer that died must not hang this GPU
 struct SpinGuard {
   long long t0;
   __device__ SpinGuard() {
@@ -48,7 +48,11 @@ struct SpinGuard {
   }
   __device__ bool expired(Mailbox *mine) {
 #ifdef __CUDA_ARCH__
-    if (clock64() - t0 < (1ll << 33)) return false;
+    // ~0.5 s of SM clocks for the first failure; once one wait has failed the job is broken
+    // anyway (b200sp_comm_timeouts() != 0), so later waits give up at once instead of
+    // stretching a dead run by half a second per kernel
+    if (clock64() - t0 < (1ll << 30) && *reinterpret_cast<volatile unsigned long long *>(&mine->timeouts) == 0)
+      return false;
     atomicAdd(&mine->timeouts, 1ull);
 #endif
     return true;

@@ -380,6 +380,15 @@ b200sp_status spmv_hyb(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64
                        const T *cv, const T *x, T *y, int accumulate, const b200sp_cfg *ecfg,
                        const b200sp_cfg *ccfg) {
   B200SP_CHECK_HANDLE(h);
+  if (!accumulate && cnnz > 0 && K == 1 && rows > 0) {
+    // y = A x with a one-column ELL part (what the reference's split rule gives power-law graphs):
+    // tail first (y zeroed, complete rows stored without reading y), then the ELL column
+    // accumulating with coalesced y reads.  Per row the only add is tail + ell instead of
+    // ell + tail (commutative), so the bits equal the ELL-then-COO order.
+    b200sp_status s = spmv_coo<T>(h, st, rows, cols, cnnz, ci, cj, cv, x, y, 0, ccfg);
+    if (s != B200SP_OK) return s;
+    return spmv_ell<T>(h, st, rows, cols, K, pitch, ecidx, evals, nullptr, x, y, 1, ecfg, nullptr, nullptr);
+  }
   b200sp_status s = spmv_ell<T>(h, st, rows, cols, K, pitch, ecidx, evals, nullptr, x, y, accumulate, ecfg,
                                 nullptr, nullptr);
   if (s != B200SP_OK) return s;

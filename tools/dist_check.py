@@ -121,6 +121,11 @@ def main():
         td.all_reduce(flags, op=td.ReduceOp.MIN)
         out["skew_stress_ok"] = int(flags.item())
         ok = ok and bool(out["skew_stress_ok"])
+    if world > 1:
+        bad = torch.tensor([h.comm_timeouts()], dtype=torch.int64, device=dev)
+        td.all_reduce(bad, op=td.ReduceOp.MAX)
+        out["comm_timeouts"] = int(bad.item())
+        ok = ok and out["comm_timeouts"] == 0
     out["ok"] = ok
     if rank == 0:
         print(json.dumps(out), flush=True)
