@@ -94,6 +94,12 @@ class Halo(C.Structure):
     _fields_ = [("halo_lo", C.c_int64), ("halo_hi", C.c_int64)]
 
 
+class ConvertInfo(C.Structure):
+    """b200sp_convert_info"""
+    _fields_ = [("max_entries_per_row", C.c_int64), ("hyb_entries_per_row", C.c_int64),
+                ("hyb_coo_entries", C.c_int64), ("num_diagonals", C.c_int64)]
+
+
 class TuneResult(C.Structure):
     _fields_ = [
         ("cfg", Cfg),
@@ -120,7 +126,9 @@ EXPORTED_SYMBOLS = (
      "b200sp_comm_unique_id", "b200sp_comm_init", "b200sp_comm_destroy", "b200sp_cg_dist",
      "b200sp_spmv_dist", "b200sp_comm_p2p_enabled", "b200sp_comm_timeouts", "b200sp_cfg_space", "b200sp_tune", "b200sp_tune_step",
      "b200sp_tune_reset", "b200sp_tune_lookup", "b200sp_tune_save", "b200sp_tune_load",
-     "b200sp_poisson_num_entries", "b200sp_poisson_csr_offsets"]
+     "b200sp_poisson_num_entries", "b200sp_poisson_csr_offsets",
+     "b200sp_offsets_to_indices", "b200sp_indices_to_offsets", "b200sp_csr_convert_query"]
+    + [f"b200sp_{op}_{s}" for op in ("csr_to_ell", "csr_to_coo_tail", "csr_to_dia", "count_zeros") for s in _SFX]
     + [f"b200sp_spmv_{f}_{s}" for f in ("csr", "ell", "dia", "coo", "hyb", "ellr") for s in _SFX]
     + [f"b200sp_{op}_{s}" for op in ("axpy", "axpby", "axpbypcz", "xmy", "copy", "fill", "scal", "dot", "nrm2", "asum", "nrmmax",
                                        "amax") for s in _SFX]
@@ -423,6 +431,48 @@ class Handle:
         self.check(f(self._h, _stream(), C.c_int(stencil), C.c_int64(nx), C.c_int64(ny), C.c_int64(nz),
                      C.c_int64(row_begin), C.c_int64(num_rows), C.c_int64(col_shift), C.c_int64(pitch),
                      _ptr(cidx), _ptr(values)))
+
+    # -- conversions on the device (csrc/convert.cu) ------------------------------------
+    def offsets_to_indices(self, row_offsets, row_indices):
+        self.check(self.lib.b200sp_offsets_to_indices(self._h, _stream(), C.c_int64(row_offsets.numel() - 1),
+                                                      _ptr(row_offsets), _ptr(row_indices)))
+
+    def indices_to_offsets(self, row_indices, row_offsets):
+        self.check(self.lib.b200sp_indices_to_offsets(self._h, _stream(), C.c_int64(row_offsets.numel() - 1),
+                                                      C.c_int64(row_indices.numel()), _ptr(row_indices),
+                                                      _ptr(row_offsets)))
+
+    def csr_convert_query(self, num_rows, num_cols, num_entries, row_offsets, column_indices=None,
+                          relative_speed=3.0, breakeven_threshold=4096) -> "ConvertInfo":
+        info = ConvertInfo()
+        self.check(self.lib.b200sp_csr_convert_query(self._h, _stream(), C.c_int64(num_rows), C.c_int64(num_cols),
+                                                     C.c_int64(num_entries), _ptr(row_offsets), _ptr(column_indices),
+                                                     C.c_float(relative_speed), C.c_int64(breakeven_threshold),
+                                                     C.byref(info)))
+        return info
+
+    def csr_to_ell(self, num_rows, K, pitch, row_offsets, column_indices, values, ell_cidx, ell_vals):
+        f = getattr(self.lib, "b200sp_csr_to_ell_" + _sfx(values.dtype))
+        self.check(f(self._h, _stream(), C.c_int64(num_rows), C.c_int64(K), C.c_int64(pitch), _ptr(row_offsets),
+                     _ptr(column_indices), _ptr(values), _ptr(ell_cidx), _ptr(ell_vals)))
+
+    def csr_to_coo_tail(self, num_rows, K, row_offsets, column_indices, values, coo_ri, coo_ci, coo_v):
+        f = getattr(self.lib, "b200sp_csr_to_coo_tail_" + _sfx(values.dtype))
+        self.check(f(self._h, _stream(), C.c_int64(num_rows), C.c_int64(K), _ptr(row_offsets), _ptr(column_indices),
+                     _ptr(values), _ptr(coo_ri), _ptr(coo_ci), _ptr(coo_v)))
+
+    def csr_to_dia(self, num_rows, num_cols, num_diagonals, pitch, row_offsets, column_indices, values,
+                   diagonal_offsets, dia_values):
+        f = getattr(self.lib, "b200sp_csr_to_dia_" + _sfx(values.dtype))
+        self.check(f(self._h, _stream(), C.c_int64(num_rows), C.c_int64(num_cols), C.c_int64(num_diagonals),
+                     C.c_int64(pitch), _ptr(row_offsets), _ptr(column_indices), _ptr(values),
+                     _ptr(diagonal_offsets), _ptr(dia_values)))
+
+    def count_zeros(self, values) -> int:
+        f = getattr(self.lib, "b200sp_count_zeros_" + _sfx(values.dtype))
+        out = C.c_int64()
+        self.check(f(self._h, _stream(), C.c_int64(values.numel()), _ptr(values), C.byref(out)))
+        return out.value
 
     def poisson_csr_offsets(self, stencil, nx, ny, nz, row_begin, num_rows, row_offsets):
         self.check(self.lib.b200sp_poisson_csr_offsets(self._h, _stream(), C.c_int(stencil), C.c_int64(nx),

@@ -1,20 +1,19 @@
-"""Device-side input construction for the bench configurations that the
-reference builds with cusp::convert / has no generator for:
+"""cusp::convert on the device, plus the R-MAT generator of the bench configurations.
 
-  * rmat(): R-MAT power-law graph (SURVEY §8d cfg 3; not in the reference gallery)
-  * coo_to_csr / csr_to_hyb / csr_to_ell: the reference's conversion RULES
-    (cusp/system/detail/generic/conversions/csr_to_other.h:155-306,
-    generic/format_utils.inl:281-321) evaluated with torch tensor ops on the GPU.
+  * rmat(): R-MAT power-law graph (SURVEY §8d cfg 3; not in the reference gallery), torch ops
+  * coo_to_csr / csr_to_coo / csr_to_ell / csr_to_hyb / csr_to_dia / optimal_entries_per_row:
+    the reference's conversion rules (cusp/system/detail/generic/conversions/csr_to_other.h:73-306,
+    generic/format_utils.inl:36-110,281-321) through the engine's conversion kernels
+    (csrc/convert.cu, b200sp_csr_to_* / b200sp_csr_convert_query).
 
-This is input plumbing (sort / scan / scatter through PyTorch), not the SpMV hot
-path; results are bit-identical to the oracle's restatement of the same rules
-(tests/test_convert_gpu.py).  Hand-written conversion kernels are a "next" row
-(SURVEY §8f-1)."""
+Results are bit-identical to the oracle's restatement of the same rules
+(tests/test_gallery_gpu.py, tests/test_convert_gpu.py)."""
 from __future__ import annotations
 
 import torch
 
-from .matrix import coo_matrix, csr_matrix, ell_matrix, hyb_matrix
+from . import capi
+from .matrix import coo_matrix, csr_matrix, default_handle, dia_matrix, ell_matrix, hyb_matrix
 
 
 def round_up(n: int, k: int) -> int:
@@ -54,70 +53,83 @@ def rmat(scale: int, edge_factor: int = 16, a=0.57, b=0.19, c=0.19, seed: int = 
 
 
 def coo_to_csr(A: coo_matrix) -> csr_matrix:
-    """indices_to_offsets (cusp/format_utils.h): offsets[i] = #entries with row < i"""
-    counts = torch.bincount(A.row_indices.to(torch.int64), minlength=A.num_rows)
-    offs = torch.zeros(A.num_rows + 1, dtype=torch.int64, device=A.values.device)
-    torch.cumsum(counts, 0, out=offs[1:])
-    return csr_matrix(A.num_rows, A.num_cols, offs.to(torch.int32), A.column_indices, A.values)
+    """indices_to_offsets (cusp/format_utils.h): offsets[i] = #entries with row < i (b200sp_indices_to_offsets)"""
+    offs = torch.empty(A.num_rows + 1, dtype=torch.int32, device=A.values.device)
+    default_handle().indices_to_offsets(A.row_indices, offs)
+    return csr_matrix(A.num_rows, A.num_cols, offs, A.column_indices, A.values)
+
+
+def csr_to_coo(A: csr_matrix) -> coo_matrix:
+    """offsets_to_indices (b200sp_offsets_to_indices)"""
+    ri = torch.empty(max(A.num_entries, 1), dtype=torch.int32, device=A.values.device)[:A.num_entries]
+    default_handle().offsets_to_indices(A.row_offsets, ri)
+    return coo_matrix(A.num_rows, A.num_cols, ri, A.column_indices, A.values)
 
 
 def optimal_entries_per_row(row_offsets: torch.Tensor, relative_speed: float = 3.0,
                             breakeven_threshold: int = 4096) -> int:
     """compute_optimal_entries_per_row (generic/format_utils.inl:281-321) +
-    speed_threshold_functor (cusp/detail/functional.inl:114-132)"""
-    lens = (row_offsets[1:] - row_offsets[:-1]).to(torch.int64)
-    num_rows = lens.numel()
-    maxc = int(lens.max().item()) if num_rows else 0
-    hist = torch.bincount(lens, minlength=maxc + 1)
-    cum = torch.cumsum(hist, 0).cpu().tolist()  # cum[k] = #rows with length <= k
-    import numpy as np
-    for k in range(maxc):
-        longer = num_rows - cum[k]
-        # float32 arithmetic like the functor: relative_speed * (num_rows-rows) < num_rows
-        if np.float32(relative_speed) * np.float32(longer) < np.float32(num_rows) or longer < breakeven_threshold:
-            return k
-    return maxc
-
-
-def _slot_index(row_offsets: torch.Tensor, nnz: int):
-    """position of every entry inside its row, and its row"""
-    dev = row_offsets.device
-    lens = (row_offsets[1:] - row_offsets[:-1]).to(torch.int64)
-    rows = torch.repeat_interleave(torch.arange(lens.numel(), device=dev, dtype=torch.int64), lens)
-    k = torch.arange(nnz, device=dev, dtype=torch.int64) - row_offsets.to(torch.int64)[rows]
-    return rows, k
+    speed_threshold_functor (cusp/detail/functional.inl:114-132), b200sp_csr_convert_query"""
+    rows = row_offsets.numel() - 1
+    if rows <= 0:
+        return 0
+    nnz = int(row_offsets[-1].item())
+    info = default_handle().csr_convert_query(rows, rows, nnz, row_offsets, None, relative_speed, breakeven_threshold)
+    return int(info.hyb_entries_per_row)
 
 
 def csr_to_ell(A: csr_matrix, num_entries_per_row: int = 0, alignment: int = 32) -> ell_matrix:
-    """csr_to_other.h:155-227"""
+    """csr_to_other.h:155-227 (b200sp_csr_to_ell)"""
+    h = default_handle()
     dev = A.values.device
-    rows, k = _slot_index(A.row_offsets, A.num_entries)
-    K = num_entries_per_row or (int(k.max().item()) + 1 if A.num_entries else 0)
+    K = num_entries_per_row
+    if not K and A.num_entries:
+        K = int(h.csr_convert_query(A.num_rows, A.num_cols, A.num_entries, A.row_offsets).max_entries_per_row)
     pitch = round_up(A.num_rows, alignment)
-    cidx = torch.full((K * pitch,), -1, dtype=torch.int32, device=dev)
-    vals = torch.zeros(K * pitch, dtype=A.values.dtype, device=dev)
-    keep = k < K
-    pos = (k * pitch + rows)[keep]
-    cidx[pos] = A.column_indices[keep]
-    vals[pos] = A.values[keep]
-    ne = A.num_entries - int((A.values == 0).sum().item())
+    cidx = torch.empty(max(K * pitch, 1), dtype=torch.int32, device=dev)[:K * pitch]
+    vals = torch.empty(max(K * pitch, 1), dtype=A.values.dtype, device=dev)[:K * pitch]
+    h.csr_to_ell(A.num_rows, K, pitch, A.row_offsets, A.column_indices, A.values, cidx, vals)
+    ne = A.num_entries - h.count_zeros(A.values)
     return ell_matrix(A.num_rows, A.num_cols, ne, K, pitch, cidx, vals)
 
 
 def csr_to_hyb(A: csr_matrix, num_entries_per_row: int | None = None, alignment: int = 32) -> hyb_matrix:
-    """csr_to_other.h:229-306: first K entries of each row -> ELL, the rest -> COO"""
+    """csr_to_other.h:229-306: first K entries of each row -> ELL, the rest -> COO in CSR order
+    (b200sp_csr_convert_query + b200sp_csr_to_ell + b200sp_csr_to_coo_tail)"""
+    h = default_handle()
     dev = A.values.device
-    K = optimal_entries_per_row(A.row_offsets) if num_entries_per_row is None else num_entries_per_row
-    rows, k = _slot_index(A.row_offsets, A.num_entries)
+    if num_entries_per_row is None:
+        info = h.csr_convert_query(A.num_rows, A.num_cols, A.num_entries, A.row_offsets)
+        K, tail = int(info.hyb_entries_per_row), int(info.hyb_coo_entries)
+    else:
+        K = int(num_entries_per_row)
+        lens = (A.row_offsets[1:] - A.row_offsets[:-1]).to(torch.int64)
+        tail = int(torch.clamp(lens - K, min=0).sum().item())
     pitch = round_up(A.num_rows, alignment)
-    cidx = torch.full((K * pitch,), -1, dtype=torch.int32, device=dev)
-    vals = torch.zeros(K * pitch, dtype=A.values.dtype, device=dev)
-    in_ell = k < K
-    pos = (k * pitch + rows)[in_ell]
-    cidx[pos] = A.column_indices[in_ell]
-    vals[pos] = A.values[in_ell]
-    tail = ~in_ell
-    coo = coo_matrix(A.num_rows, A.num_cols, rows[tail].to(torch.int32), A.column_indices[tail].contiguous(),
-                     A.values[tail].contiguous())
-    ell = ell_matrix(A.num_rows, A.num_cols, int(in_ell.sum().item()), K, pitch, cidx, vals)
+    cidx = torch.empty(max(K * pitch, 1), dtype=torch.int32, device=dev)[:K * pitch]
+    vals = torch.empty(max(K * pitch, 1), dtype=A.values.dtype, device=dev)[:K * pitch]
+    h.csr_to_ell(A.num_rows, K, pitch, A.row_offsets, A.column_indices, A.values, cidx, vals)
+    ri = torch.empty(max(tail, 1), dtype=torch.int32, device=dev)[:tail]
+    ci = torch.empty(max(tail, 1), dtype=torch.int32, device=dev)[:tail]
+    cv = torch.empty(max(tail, 1), dtype=A.values.dtype, device=dev)[:tail]
+    h.csr_to_coo_tail(A.num_rows, K, A.row_offsets, A.column_indices, A.values, ri, ci, cv)
+    coo = coo_matrix(A.num_rows, A.num_cols, ri, ci, cv)
+    ell = ell_matrix(A.num_rows, A.num_cols, A.num_entries - tail, K, pitch, cidx, vals)
     return hyb_matrix(ell, coo)
+
+
+def csr_to_dia(A: csr_matrix, alignment: int = 32) -> dia_matrix:
+    """csr_to_other.h:73-153: occupied diagonals ascending, pitch = round_up(rows, alignment),
+    refuses a fill-in > 3x on slabs > 1e6 slots (b200sp_csr_convert_query + b200sp_csr_to_dia)"""
+    h = default_handle()
+    dev = A.values.device
+    info = h.csr_convert_query(A.num_rows, A.num_cols, A.num_entries, A.row_offsets, A.column_indices)
+    nd = int(info.num_diagonals)
+    size = float(nd) * float(A.num_rows)
+    if 3.0 < size / max(1.0, float(A.num_entries)) and size > 1e6:
+        raise capi.B200spError(capi.ST_INVALID_INPUT, "dia_matrix fill-in would exceed maximum tolerance")
+    pitch = round_up(A.num_rows, alignment)
+    offs = torch.empty(max(nd, 1), dtype=torch.int32, device=dev)[:nd]
+    vals = torch.empty(max(nd * pitch, 1), dtype=A.values.dtype, device=dev)[:nd * pitch]
+    h.csr_to_dia(A.num_rows, A.num_cols, nd, pitch, A.row_offsets, A.column_indices, A.values, offs, vals)
+    return dia_matrix(A.num_rows, A.num_cols, A.num_entries, offs, pitch, vals)

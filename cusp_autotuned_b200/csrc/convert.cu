@@ -1,0 +1,439 @@
+// convert.cu — format conversions on the device.
+//
+// The reference converts through multi-pass Thrust pipelines with host loops in the middle
+// (cusp/system/detail/generic/conversions/csr_to_other.h:73-306: one thrust::replace per
+// diagonal, :138-140; dia_to_other.h:227-251: two stable_partitions per ROW), which dominate
+// set-up time at 10^8 rows.  Here every conversion is a handful of flat kernels; the
+// layouts are the reference's, bit for bit:
+//   CSR -> COO   offsets_to_indices                             (format_utils.inl:36-75)
+//   COO -> CSR   indices_to_offsets (row indices sorted)        (format_utils.inl:77-110)
+//   CSR -> ELL   k-th entry of row i -> slot [k*pitch + i], padding column -1 / value 0,
+//                entries beyond K dropped                       (csr_to_other.h:155-227)
+//   CSR -> HYB   ELL part as above with K from the reference's split rule
+//                (format_utils.inl:281-321, functional.inl:114-132), the rest to COO in
+//                CSR order                                      (csr_to_other.h:229-306)
+//   CSR -> DIA   occupied diagonals ascending, values[d*pitch + i], zero fill
+//                                                               (csr_to_other.h:73-153)
+// Callers size the outputs from the query calls (max row length, HYB width + tail size,
+// number of diagonals); those return scalars to the host and synchronise the stream.
+#include "common.cuh"
+
+namespace b200sp {
+
+// ---------------------------------------------------------------------------
+// exclusive scan of int32 (three-level, deterministic); n < 2^31
+// ---------------------------------------------------------------------------
+constexpr int SCAN_BLOCK = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_tile_kernel(i64 n, const int *in, int *out, int *tile_sums) {
+  __shared__ int s_warp[SCAN_BLOCK / 32];
+  const i64 base = (i64)blockIdx.x * SCAN_TILE + (i64)threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    v[k] = (base + k < n) ? in[base + k] : 0;
+    sum += v[k];
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += u;
+  }
+  if (lane == 31) s_warp[w] = incl;
+  __syncthreads();
+  int warp_off = 0;
+  for (int k = 0; k < w; ++k) warp_off += s_warp[k];
+  int run = warp_off + incl - sum;  // exclusive prefix of this thread inside the tile
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    if (base + k < n) out[base + k] = run;
+    run += v[k];
+  }
+  if (threadIdx.x == SCAN_BLOCK - 1 && tile_sums) tile_sums[blockIdx.x] = warp_off + incl;
+}
+
+__global__ void scan_add_kernel(i64 n, int *out, const int *tile_offsets) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] += tile_offsets[i / SCAN_TILE];
+}
+
+// out[i] = sum_{j<i} in[j]; in == out allowed.  tmp: scratch of >= scan_tmp_ints(n) ints.
+static i64 scan_tmp_ints(i64 n) {
+  i64 t = 0;
+  while (n > SCAN_TILE) {
+    n = ceil_div(n, (i64)SCAN_TILE);
+    t += n;
+  }
+  return t + 1;
+}
+static b200sp_status scan_exclusive(b200sp_handle h, cudaStream_t st, i64 n, const int *in, int *out, int *tmp) {
+  if (n <= 0) return B200SP_OK;
+  const i64 tiles = ceil_div(n, (i64)SCAN_TILE);
+  scan_tile_kernel<<<(unsigned)tiles, SCAN_BLOCK, 0, st>>>(n, in, out, tiles > 1 ? tmp : nullptr);
+  B200SP_LAUNCH_CHECK(h, "scan_tile_kernel");
+  if (tiles > 1) {
+    b200sp_status s = scan_exclusive(h, st, tiles, tmp, tmp, tmp + tiles);
+    if (s != B200SP_OK) return s;
+    scan_add_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(n, out, tmp);
+    B200SP_LAUNCH_CHECK(h, "scan_add_kernel");
+  }
+  return B200SP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// CSR <-> COO
+// ---------------------------------------------------------------------------
+__global__ void offsets_to_indices_kernel(i64 rows, const int *Ap, int *Ai) {
+  // one warp per row: rows of any length are written coalesced
+  const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (i64 r = warp; r < rows; r += ((i64)gridDim.x * blockDim.x) >> 5) {
+    const int lo = Ap[r], hi = Ap[r + 1];
+    for (int j = lo + lane; j < hi; j += 32) Ai[j] = (int)r;
+  }
+}
+
+// offsets[i] = number of (sorted) indices < i  == lower_bound(indices, i)
+__global__ void indices_to_offsets_kernel(i64 rows, i64 nnz, const int *Ai, int *Ap) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > rows) return;
+  i64 lo = 0, hi = nnz;
+  while (lo < hi) {
+    const i64 mid = (lo + hi) >> 1;
+    if (Ai[mid] < (int)i) lo = mid + 1; else hi = mid;
+  }
+  Ap[i] = (int)lo;
+}
+
+// ---------------------------------------------------------------------------
+// queries
+// ---------------------------------------------------------------------------
+__global__ void row_length_stats_kernel(i64 rows, const int *Ap, int *max_len, unsigned int *hist, int hist_len) {
+  int m = 0;
+  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (i64)gridDim.x * blockDim.x) {
+    const int len = Ap[r + 1] - Ap[r];
+    m = max(m, len);
+    if (hist && len < hist_len) atomicAdd(hist + len, 1u);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(max_len, m);
+}
+
+__global__ void tail_lengths_kernel(i64 rows, const int *Ap, int K, int *tail) {
+  const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r <= rows) tail[r] = (r < rows) ? max(Ap[r + 1] - Ap[r] - K, 0) : 0;
+}
+
+template <typename T>
+__global__ void count_zeros_kernel(i64 n, const T *v, unsigned long long *out) {
+  unsigned long long c = 0;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+    c += (v[i] == T(0)) ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+// ---------------------------------------------------------------------------
+// CSR -> ELL (+ COO tail)
+// ---------------------------------------------------------------------------
+// slot-major: thread (row, k) for k < K; consecutive threads -> consecutive rows of one slot,
+// so the slab writes are coalesced
+template <typename T>
+__global__ void csr_to_ell_kernel(i64 rows, int K, i64 pitch, const int *Ap, const int *Aj, const T *Ax, int *cidx,
+                                  T *vals) {
+  const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  if (r >= pitch || k >= K) return;
+  int c = -1;
+  T v = T(0);
+  if (r < rows) {
+    const int lo = Ap[r], len = Ap[r + 1] - lo;
+    if (k < len) {
+      c = Aj[lo + k];
+      v = Ax[lo + k];
+    }
+  }
+  cidx[(i64)k * pitch + r] = c;
+  vals[(i64)k * pitch + r] = v;
+}
+
+template <typename T>
+__global__ void csr_tail_to_coo_kernel(i64 rows, int K, const int *Ap, const int *Aj, const T *Ax, const int *tail_off,
+                                       int *ri, int *ci, T *cv) {
+  const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (i64 r = warp; r < rows; r += ((i64)gridDim.x * blockDim.x) >> 5) {
+    const int lo = Ap[r] + K, hi = Ap[r + 1];
+    const int dst = tail_off[r];
+    for (int j = lo + lane; j < hi; j += 32) {
+      ri[dst + (j - lo)] = (int)r;
+      ci[dst + (j - lo)] = Aj[j];
+      cv[dst + (j - lo)] = Ax[j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// CSR -> DIA
+// ---------------------------------------------------------------------------
+__global__ void mark_diagonals_kernel(i64 rows, const int *Ap, const int *Aj, int *flags) {
+  const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (i64 r = warp; r < rows; r += ((i64)gridDim.x * blockDim.x) >> 5) {
+    const int lo = Ap[r], hi = Ap[r + 1];
+    for (int j = lo + lane; j < hi; j += 32) flags[(i64)Aj[j] - r + rows] = 1;  // benign race: all writers store 1
+  }
+}
+__global__ void compact_diagonals_kernel(i64 n, i64 rows, const int *flags, const int *pos, int *offsets) {
+  const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n && flags[k]) offsets[pos[k]] = (int)(k - rows);
+}
+template <typename T>
+__global__ void csr_to_dia_fill_kernel(i64 rows, i64 pitch, const int *Ap, const int *Aj, const T *Ax, const int *pos,
+                                       T *vals) {
+  const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (i64 r = warp; r < rows; r += ((i64)gridDim.x * blockDim.x) >> 5) {
+    const int lo = Ap[r], hi = Ap[r + 1];
+    // duplicates inside a row: the last one in CSR order wins, like thrust::scatter in the reference
+    for (int j = lo + lane; j < hi; j += 32) vals[(i64)pos[(i64)Aj[j] - r + rows] * pitch + r] = Ax[j];
+  }
+}
+
+static inline unsigned warp_grid(b200sp_handle h, i64 rows) {
+  i64 g = ceil_div(rows, 8);  // 8 warps (rows) per 256-thread block
+  const i64 cap = (i64)h->num_sms * 32;
+  if (g > cap) g = cap;
+  return (unsigned)(g < 1 ? 1 : g);
+}
+
+struct DevTemp {  // cudaMalloc'd scratch freed on scope exit (set-up time code)
+  void *p = nullptr;
+  ~DevTemp() {
+    if (p) cudaFree(p);
+  }
+  b200sp_status alloc(b200sp_handle h, size_t bytes) {
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+      return set_error(h, B200SP_ALLOC_FAILED, "convert: cannot allocate %zu B of scratch", bytes);
+    }
+    return B200SP_OK;
+  }
+};
+
+template <typename T>
+static b200sp_status csr_to_ell_impl(b200sp_handle h, cudaStream_t st, i64 rows, i64 K, i64 pitch, const int *Ap,
+                                     const int *Aj, const T *Ax, int *cidx, T *vals) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, rows >= 0 && K >= 0 && pitch >= rows && K < 65536, "csr_to_ell: bad dimensions");
+  if (K == 0 || pitch == 0) return B200SP_OK;
+  B200SP_REQUIRE(h, Ap && cidx && vals, "csr_to_ell: null pointer");
+  const dim3 grid((unsigned)ceil_div(pitch, 256), (unsigned)K);
+  csr_to_ell_kernel<T><<<grid, 256, 0, st>>>(rows, (int)K, pitch, Ap, Aj, Ax, cidx, vals);
+  B200SP_LAUNCH_CHECK(h, "csr_to_ell_kernel");
+  return B200SP_OK;
+}
+
+template <typename T>
+static b200sp_status csr_tail_impl(b200sp_handle h, cudaStream_t st, i64 rows, i64 K, const int *Ap, const int *Aj,
+                                   const T *Ax, int *ri, int *ci, T *cv) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, rows >= 0 && K >= 0, "csr_to_coo_tail: bad dimensions");
+  if (rows == 0) return B200SP_OK;
+  DevTemp off, tmp;
+  b200sp_status s = off.alloc(h, (size_t)(rows + 1) * sizeof(int));
+  if (s != B200SP_OK) return s;
+  s = tmp.alloc(h, (size_t)scan_tmp_ints(rows + 1) * sizeof(int));
+  if (s != B200SP_OK) return s;
+  int *tail_off = reinterpret_cast<int *>(off.p);
+  tail_lengths_kernel<<<(unsigned)ceil_div(rows + 1, 256), 256, 0, st>>>(rows, Ap, (int)K, tail_off);
+  B200SP_LAUNCH_CHECK(h, "tail_lengths_kernel");
+  s = scan_exclusive(h, st, rows + 1, tail_off, tail_off, reinterpret_cast<int *>(tmp.p));
+  if (s != B200SP_OK) return s;
+  csr_tail_to_coo_kernel<T><<<warp_grid(h, rows), 256, 0, st>>>(rows, (int)K, Ap, Aj, Ax, tail_off, ri, ci, cv);
+  B200SP_LAUNCH_CHECK(h, "csr_tail_to_coo_kernel");
+  B200SP_CUDA(h, cudaStreamSynchronize(st));  // the temporaries die with this frame
+  return B200SP_OK;
+}
+
+template <typename T>
+static b200sp_status csr_to_dia_impl(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64 ndiag, i64 pitch,
+                                     const int *Ap, const int *Aj, const T *Ax, int *offsets, T *vals) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, rows >= 0 && cols >= 0 && ndiag >= 0 && pitch >= rows, "csr_to_dia: bad dimensions");
+  if (rows == 0 || ndiag == 0) return B200SP_OK;
+  B200SP_REQUIRE(h, Ap && Aj && Ax && offsets && vals, "csr_to_dia: null pointer");
+  const i64 n = rows + cols;
+  DevTemp flags, pos, tmp;
+  b200sp_status s = flags.alloc(h, (size_t)n * sizeof(int));
+  if (s == B200SP_OK) s = pos.alloc(h, (size_t)n * sizeof(int));
+  if (s == B200SP_OK) s = tmp.alloc(h, (size_t)scan_tmp_ints(n) * sizeof(int));
+  if (s != B200SP_OK) return s;
+  B200SP_CUDA(h, cudaMemsetAsync(flags.p, 0, (size_t)n * sizeof(int), st));
+  mark_diagonals_kernel<<<warp_grid(h, rows), 256, 0, st>>>(rows, Ap, Aj, reinterpret_cast<int *>(flags.p));
+  B200SP_LAUNCH_CHECK(h, "mark_diagonals_kernel");
+  s = scan_exclusive(h, st, n, reinterpret_cast<int *>(flags.p), reinterpret_cast<int *>(pos.p),
+                     reinterpret_cast<int *>(tmp.p));
+  if (s != B200SP_OK) return s;
+  compact_diagonals_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(n, rows, reinterpret_cast<int *>(flags.p),
+                                                                        reinterpret_cast<int *>(pos.p), offsets);
+  B200SP_LAUNCH_CHECK(h, "compact_diagonals_kernel");
+  B200SP_CUDA(h, cudaMemsetAsync(vals, 0, (size_t)pitch * (size_t)ndiag * sizeof(T), st));
+  csr_to_dia_fill_kernel<T><<<warp_grid(h, rows), 256, 0, st>>>(rows, pitch, Ap, Aj, Ax, reinterpret_cast<int *>(pos.p),
+                                                                vals);
+  B200SP_LAUNCH_CHECK(h, "csr_to_dia_fill_kernel");
+  B200SP_CUDA(h, cudaStreamSynchronize(st));
+  return B200SP_OK;
+}
+
+}  // namespace b200sp
+
+extern "C" {
+
+b200sp_status b200sp_offsets_to_indices(b200sp_handle h, b200sp_stream stream, int64_t num_rows,
+                                        const int32_t *row_offsets, int32_t *row_indices) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, num_rows >= 0, "offsets_to_indices: negative size");
+  if (num_rows == 0) return B200SP_OK;
+  B200SP_REQUIRE(h, row_offsets && row_indices, "offsets_to_indices: null pointer");
+  b200sp::offsets_to_indices_kernel<<<b200sp::warp_grid(h, num_rows), 256, 0, (cudaStream_t)stream>>>(
+      num_rows, row_offsets, row_indices);
+  B200SP_LAUNCH_CHECK(h, "offsets_to_indices_kernel");
+  return B200SP_OK;
+}
+
+b200sp_status b200sp_indices_to_offsets(b200sp_handle h, b200sp_stream stream, int64_t num_rows, int64_t num_entries,
+                                        const int32_t *row_indices, int32_t *row_offsets) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, num_rows >= 0 && num_entries >= 0 && row_offsets, "indices_to_offsets: bad arguments");
+  B200SP_REQUIRE(h, num_entries == 0 || row_indices, "indices_to_offsets: null pointer");
+  b200sp::indices_to_offsets_kernel<<<(unsigned)b200sp::ceil_div(num_rows + 1, 256), 256, 0, (cudaStream_t)stream>>>(
+      num_rows, num_entries, row_indices, row_offsets);
+  B200SP_LAUNCH_CHECK(h, "indices_to_offsets_kernel");
+  return B200SP_OK;
+}
+
+b200sp_status b200sp_csr_convert_query(b200sp_handle h, b200sp_stream stream, int64_t num_rows, int64_t num_cols,
+                                       int64_t num_entries, const int32_t *row_offsets,
+                                       const int32_t *column_indices, float relative_speed,
+                                       int64_t breakeven_threshold, b200sp_convert_info *info) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, info && num_rows >= 0 && num_cols >= 0 && num_entries >= 0, "csr_convert_query: bad arguments");
+  memset(info, 0, sizeof(*info));
+  if (num_rows == 0 || num_entries == 0) return B200SP_OK;
+  B200SP_REQUIRE(h, row_offsets, "csr_convert_query: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  // pass 1: longest row
+  int *d_max = reinterpret_cast<int *>(h->dev_scalars + 56);
+  B200SP_CUDA(h, cudaMemsetAsync(d_max, 0, sizeof(int), st));
+  i64 g = b200sp::ceil_div(num_rows, 256);
+  if (g > (i64)h->num_sms * 16) g = (i64)h->num_sms * 16;
+  b200sp::row_length_stats_kernel<<<(unsigned)g, 256, 0, st>>>(num_rows, row_offsets, d_max, nullptr, 0);
+  B200SP_LAUNCH_CHECK(h, "row_length_stats_kernel");
+  int max_len = 0;
+  B200SP_CUDA(h, cudaMemcpyAsync(&max_len, d_max, sizeof(int), cudaMemcpyDeviceToHost, st));
+  B200SP_CUDA(h, cudaStreamSynchronize(st));
+  info->max_entries_per_row = max_len;
+  // pass 2: histogram of row lengths -> the reference's HYB split rule, evaluated on the host
+  // (compute_optimal_entries_per_row, format_utils.inl:281-321 with speed_threshold_functor,
+  // functional.inl:114-132): smallest K with  relative_speed * #rows(len > K) < rows  or
+  // #rows(len > K) < breakeven_threshold
+  {
+    b200sp::DevTemp hist;
+    b200sp_status s = hist.alloc(h, (size_t)(max_len + 1) * sizeof(unsigned int));
+    if (s != B200SP_OK) return s;
+    B200SP_CUDA(h, cudaMemsetAsync(hist.p, 0, (size_t)(max_len + 1) * sizeof(unsigned int), st));
+    B200SP_CUDA(h, cudaMemsetAsync(d_max, 0, sizeof(int), st));
+    b200sp::row_length_stats_kernel<<<(unsigned)g, 256, 0, st>>>(num_rows, row_offsets, d_max,
+                                                                 reinterpret_cast<unsigned int *>(hist.p), max_len + 1);
+    B200SP_LAUNCH_CHECK(h, "row_length_stats_kernel");
+    std::vector<unsigned int> hh((size_t)max_len + 1);
+    B200SP_CUDA(h, cudaMemcpyAsync(hh.data(), hist.p, hh.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    B200SP_CUDA(h, cudaStreamSynchronize(st));
+    i64 cum = 0, K = max_len, tail = 0;
+    for (i64 k = 0; k < max_len; ++k) {
+      cum += hh[(size_t)k];  // rows with length <= k
+      const i64 longer = num_rows - cum;
+      if (relative_speed * (float)longer < (float)num_rows || longer < breakeven_threshold) {
+        K = k;
+        break;
+      }
+    }
+    for (i64 len = K + 1; len <= max_len; ++len) tail += (len - K) * (i64)hh[(size_t)len];
+    info->hyb_entries_per_row = K;
+    info->hyb_coo_entries = tail;
+  }
+  // pass 3: occupied diagonals
+  if (column_indices) {
+    const i64 n = num_rows + num_cols;
+    b200sp::DevTemp flags, tmp;
+    b200sp_status s = flags.alloc(h, (size_t)(n + 1) * sizeof(int));
+    if (s == B200SP_OK) s = tmp.alloc(h, (size_t)b200sp::scan_tmp_ints(n + 1) * sizeof(int));
+    if (s != B200SP_OK) return s;
+    int *f = reinterpret_cast<int *>(flags.p);
+    B200SP_CUDA(h, cudaMemsetAsync(f, 0, (size_t)(n + 1) * sizeof(int), st));
+    b200sp::mark_diagonals_kernel<<<b200sp::warp_grid(h, num_rows), 256, 0, st>>>(num_rows, row_offsets,
+                                                                                  column_indices, f);
+    B200SP_LAUNCH_CHECK(h, "mark_diagonals_kernel");
+    s = b200sp::scan_exclusive(h, st, n + 1, f, f, reinterpret_cast<int *>(tmp.p));  // f[n] = total
+    if (s != B200SP_OK) return s;
+    int nd = 0;
+    B200SP_CUDA(h, cudaMemcpyAsync(&nd, f + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    B200SP_CUDA(h, cudaStreamSynchronize(st));
+    info->num_diagonals = nd;
+  }
+  return B200SP_OK;
+}
+
+#define DEF(T, sfx)                                                                                        \
+  b200sp_status b200sp_csr_to_ell_##sfx(b200sp_handle h, b200sp_stream s, int64_t num_rows,                \
+                                        int64_t num_cols_per_row, int64_t pitch, const int32_t *row_offsets, \
+                                        const int32_t *column_indices, const T *values,                    \
+                                        int32_t *ell_column_indices, T *ell_values) {                      \
+    return b200sp::csr_to_ell_impl<T>(h, (cudaStream_t)s, num_rows, num_cols_per_row, pitch, row_offsets,  \
+                                      column_indices, values, ell_column_indices, ell_values);             \
+  }                                                                                                        \
+  b200sp_status b200sp_csr_to_coo_tail_##sfx(b200sp_handle h, b200sp_stream s, int64_t num_rows,           \
+                                             int64_t num_cols_per_row, const int32_t *row_offsets,         \
+                                             const int32_t *column_indices, const T *values,               \
+                                             int32_t *coo_row_indices, int32_t *coo_column_indices,        \
+                                             T *coo_values) {                                              \
+    return b200sp::csr_tail_impl<T>(h, (cudaStream_t)s, num_rows, num_cols_per_row, row_offsets,           \
+                                    column_indices, values, coo_row_indices, coo_column_indices, coo_values); \
+  }                                                                                                        \
+  b200sp_status b200sp_csr_to_dia_##sfx(b200sp_handle h, b200sp_stream s, int64_t num_rows, int64_t num_cols, \
+                                        int64_t num_diagonals, int64_t pitch, const int32_t *row_offsets,  \
+                                        const int32_t *column_indices, const T *values,                    \
+                                        int32_t *diagonal_offsets, T *dia_values) {                        \
+    return b200sp::csr_to_dia_impl<T>(h, (cudaStream_t)s, num_rows, num_cols, num_diagonals, pitch,        \
+                                      row_offsets, column_indices, values, diagonal_offsets, dia_values);  \
+  }                                                                                                        \
+  b200sp_status b200sp_count_zeros_##sfx(b200sp_handle h, b200sp_stream s, int64_t n, const T *values,     \
+                                         int64_t *count_host) {                                            \
+    B200SP_CHECK_HANDLE(h);                                                                                \
+    B200SP_REQUIRE(h, n >= 0 && count_host, "count_zeros: bad arguments");                                 \
+    *count_host = 0;                                                                                       \
+    if (n == 0) return B200SP_OK;                                                                          \
+    unsigned long long *d = reinterpret_cast<unsigned long long *>(h->dev_scalars + 57);                   \
+    B200SP_CUDA(h, cudaMemsetAsync(d, 0, sizeof(*d), (cudaStream_t)s));                                    \
+    i64 g = b200sp::ceil_div(n, 1024);                                                                     \
+    if (g > (i64)h->num_sms * 16) g = (i64)h->num_sms * 16;                                                \
+    b200sp::count_zeros_kernel<T><<<(unsigned)g, 256, 0, (cudaStream_t)s>>>(n, values, d);                 \
+    B200SP_LAUNCH_CHECK(h, "count_zeros_kernel");                                                          \
+    unsigned long long c = 0;                                                                              \
+    B200SP_CUDA(h, cudaMemcpyAsync(&c, d, sizeof(c), cudaMemcpyDeviceToHost, (cudaStream_t)s));            \
+    B200SP_CUDA(h, cudaStreamSynchronize((cudaStream_t)s));                                                \
+    *count_host = (int64_t)c;                                                                              \
+    return B200SP_OK;                                                                                      \
+  }
+DEF(float, f32)
+DEF(double, f64)
+#undef DEF
+}

@@ -395,6 +395,61 @@ int b200sp_tune_lookup(b200sp_handle h, const b200sp_matrix *A, b200sp_cfg *cfg)
 b200sp_status b200sp_tune_save(b200sp_handle h, const char *path);
 b200sp_status b200sp_tune_load(b200sp_handle h, const char *path);
 
+/* ---- format conversions on the device (cusp::convert) ----------------
+ * Layouts are the reference's, bit for bit (cusp/system/detail/generic/conversions/
+ * csr_to_other.h:73-306, cusp/system/detail/generic/format_utils.inl:36-110,281-321).
+ * The caller sizes the outputs from b200sp_csr_convert_query. */
+typedef struct {
+  int64_t max_entries_per_row; /* cusp::compute_max_entries_per_row                      */
+  int64_t hyb_entries_per_row; /* cusp::compute_optimal_entries_per_row(relative_speed,
+                                  breakeven_threshold): ELL width of the HYB split        */
+  int64_t hyb_coo_entries;     /* entries left for the COO part at that width            */
+  int64_t num_diagonals;       /* cusp::count_diagonals (0 if column_indices == NULL)    */
+} b200sp_convert_info;
+
+/* row_indices[k] = i for row_offsets[i] <= k < row_offsets[i+1]   (CSR -> COO) */
+b200sp_status b200sp_offsets_to_indices(b200sp_handle h, b200sp_stream stream, int64_t num_rows,
+                                        const int32_t *row_offsets, int32_t *row_indices);
+/* row_offsets[i] = #(row_indices < i), i = 0..num_rows; row_indices sorted  (COO -> CSR) */
+b200sp_status b200sp_indices_to_offsets(b200sp_handle h, b200sp_stream stream, int64_t num_rows,
+                                        int64_t num_entries, const int32_t *row_indices,
+                                        int32_t *row_offsets);
+/* structure of a CSR matrix that the conversions need; the reference's defaults are
+ * relative_speed = 3, breakeven_threshold = 4096 (csr_to_other.h:250-253).
+ * Returns scalars to the host: synchronises `stream`. */
+b200sp_status b200sp_csr_convert_query(b200sp_handle h, b200sp_stream stream, int64_t num_rows,
+                                       int64_t num_cols, int64_t num_entries,
+                                       const int32_t *row_offsets, const int32_t *column_indices,
+                                       float relative_speed, int64_t breakeven_threshold,
+                                       b200sp_convert_info *info_host);
+
+#define B200SP_DECL_CONVERT(T, sfx)                                                       \
+  /* k-th entry of row i -> slot [k*pitch + i] for k < num_cols_per_row; padding column   \
+   * -1 / value 0, rows [num_rows, pitch) padded too          csr_to_other.h:155-227 */   \
+  b200sp_status b200sp_csr_to_ell_##sfx(                                                  \
+      b200sp_handle h, b200sp_stream s, int64_t num_rows, int64_t num_cols_per_row,       \
+      int64_t pitch, const int32_t *row_offsets, const int32_t *column_indices,           \
+      const T *values, int32_t *ell_column_indices, T *ell_values);                       \
+  /* entries k >= num_cols_per_row of every row, in CSR order, as COO (the tail of the    \
+   * HYB split)                                               csr_to_other.h:229-306 */   \
+  b200sp_status b200sp_csr_to_coo_tail_##sfx(                                             \
+      b200sp_handle h, b200sp_stream s, int64_t num_rows, int64_t num_cols_per_row,       \
+      const int32_t *row_offsets, const int32_t *column_indices, const T *values,         \
+      int32_t *coo_row_indices, int32_t *coo_column_indices, T *coo_values);              \
+  /* occupied diagonals ascending in diagonal_offsets[num_diagonals]; values[d*pitch+i],  \
+   * zero elsewhere                                           csr_to_other.h:73-153 */    \
+  b200sp_status b200sp_csr_to_dia_##sfx(                                                  \
+      b200sp_handle h, b200sp_stream s, int64_t num_rows, int64_t num_cols,               \
+      int64_t num_diagonals, int64_t pitch, const int32_t *row_offsets,                   \
+      const int32_t *column_indices, const T *values, int32_t *diagonal_offsets,          \
+      T *dia_values);                                                                     \
+  /* number of stored values equal to 0 (ELL num_entries = nnz - zeros, :205-212) */      \
+  b200sp_status b200sp_count_zeros_##sfx(b200sp_handle h, b200sp_stream s, int64_t n,     \
+                                         const T *values, int64_t *count_host);
+B200SP_DECL_CONVERT(float, f32)
+B200SP_DECL_CONVERT(double, f64)
+#undef B200SP_DECL_CONVERT
+
 /* ---- device-side input builders (cusp::gallery::poisson5pt/7pt via
  *      generate_matrix_from_stencil, gallery/detail/stencil.inl:143-206, then
  *      cusp::convert; produce bit-identical arrays to that pipeline without

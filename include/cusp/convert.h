@@ -20,15 +20,19 @@
 //                COO in CSR order   (csr_to_other.h:229-306, format_utils.inl:281-321,
 //                                    detail/functional.inl:114-132)
 //   anything else goes through COO/CSR                     (convert.inl:53-70)
-// Conversions are setup-time operations: they run on the host and the result is
-// uploaded (SURVEY 8f-1 ranks device conversions "next").  The device builders
-// for the benchmark operators are in cusp/gallery/poisson.h.
+// Conversions are setup-time operations.  Device CSR / COO sources with 32-bit indices and
+// float / double values convert on the device through the engine's conversion kernels
+// (b200sp_csr_to_{ell,coo_tail,dia}, b200sp_{offsets_to_indices,indices_to_offsets},
+// b200sp_csr_convert_query — csrc/convert.cu), same layouts bit for bit;
+// every other pair runs on the host and the result is uploaded.  The device builders for
+// the benchmark operators are in cusp/gallery/poisson.h.
 #pragma once
 #include <algorithm>
 #include <vector>
 
 #include "coo_matrix.h"
 #include "csr_matrix.h"
+#include "detail/descriptor.h"
 #include "dia_matrix.h"
 #include "ell_matrix.h"
 #include "hyb_matrix.h"
@@ -369,8 +373,168 @@ void convert_dispatch(const S &src, D &dst, dia_format, ell_format) {
   upload(ci, dst.column_indices.values);
   upload(ev, dst.values.values);
 }
+// ---- device -> device through the conversion kernels ---------------------------------
+inline b200sp_status csr_to_ell_(int64_t r, int64_t K, int64_t p, const int *ro, const int *ci, const float *v, int *ec,
+                                 float *ev) {
+  return b200sp_csr_to_ell_f32(engine(), current_stream(), r, K, p, ro, ci, v, ec, ev);
+}
+inline b200sp_status csr_to_ell_(int64_t r, int64_t K, int64_t p, const int *ro, const int *ci, const double *v,
+                                 int *ec, double *ev) {
+  return b200sp_csr_to_ell_f64(engine(), current_stream(), r, K, p, ro, ci, v, ec, ev);
+}
+inline b200sp_status csr_to_tail_(int64_t r, int64_t K, const int *ro, const int *ci, const float *v, int *tr, int *tc,
+                                  float *tv) {
+  return b200sp_csr_to_coo_tail_f32(engine(), current_stream(), r, K, ro, ci, v, tr, tc, tv);
+}
+inline b200sp_status csr_to_tail_(int64_t r, int64_t K, const int *ro, const int *ci, const double *v, int *tr,
+                                  int *tc, double *tv) {
+  return b200sp_csr_to_coo_tail_f64(engine(), current_stream(), r, K, ro, ci, v, tr, tc, tv);
+}
+inline b200sp_status csr_to_dia_(int64_t r, int64_t c, int64_t nd, int64_t p, const int *ro, const int *ci,
+                                 const float *v, int *off, float *dv) {
+  return b200sp_csr_to_dia_f32(engine(), current_stream(), r, c, nd, p, ro, ci, v, off, dv);
+}
+inline b200sp_status csr_to_dia_(int64_t r, int64_t c, int64_t nd, int64_t p, const int *ro, const int *ci,
+                                 const double *v, int *off, double *dv) {
+  return b200sp_csr_to_dia_f64(engine(), current_stream(), r, c, nd, p, ro, ci, v, off, dv);
+}
+inline b200sp_status count_zeros_(int64_t n, const float *v, int64_t *c) {
+  return b200sp_count_zeros_f32(engine(), current_stream(), n, v, c);
+}
+inline b200sp_status count_zeros_(int64_t n, const double *v, int64_t *c) {
+  return b200sp_count_zeros_f64(engine(), current_stream(), n, v, c);
+}
+
+// both ends live on the device, same value type, the ABI's index / value types
+template <typename S, typename D>
+struct device_convertible
+    : std::integral_constant<bool, abi_matrix<S>::value && abi_matrix<D>::value &&
+                                       std::is_same<typename S::value_type, typename D::value_type>::value> {};
+
+template <typename S>
+b200sp_convert_info csr_query(const S &src, bool diagonals) {
+  b200sp_convert_info info;
+  check(b200sp_csr_convert_query(engine(), current_stream(), (int64_t)src.num_rows, (int64_t)src.num_cols,
+                                 (int64_t)src.num_entries, raw_ptr(src.row_offsets),
+                                 diagonals ? raw_ptr(src.column_indices) : nullptr, 3.0f, 4096, &info));
+  return info;
+}
+
+template <typename S, typename D>
+void device_convert(const S &src, D &dst, csr_format, coo_format) {
+  dst.resize(src.num_rows, src.num_cols, src.num_entries);
+  check(b200sp_offsets_to_indices(engine(), current_stream(), (int64_t)src.num_rows, raw_ptr(src.row_offsets),
+                                  raw_ptr(dst.row_indices)));
+  dst.column_indices = src.column_indices;
+  dst.values = src.values;
+}
+template <typename S, typename D>
+void device_convert(const S &src, D &dst, coo_format, csr_format) {
+  dst.resize(src.num_rows, src.num_cols, src.num_entries);
+  check(b200sp_indices_to_offsets(engine(), current_stream(), (int64_t)src.num_rows, (int64_t)src.num_entries,
+                                  raw_ptr(src.row_indices), raw_ptr(dst.row_offsets)));
+  dst.column_indices = src.column_indices;
+  dst.values = src.values;
+}
+template <typename S, typename D>
+void device_convert(const S &src, D &dst, csr_format, ell_format, size_t K = 0, size_t alignment = 32) {
+  if (src.num_entries == 0) {
+    dst.resize(src.num_rows, src.num_cols, 0, K);
+    return;
+  }
+  if (K == 0) {
+    K = (size_t)csr_query(src, false).max_entries_per_row;
+    fill_guard(K, src.num_rows, src.num_entries, "ell_matrix fill-in would exceed maximum tolerance");
+  }
+  int64_t zeros = 0;
+  check(count_zeros_((int64_t)src.num_entries, raw_ptr(src.values), &zeros));
+  dst.resize(src.num_rows, src.num_cols, src.num_entries - (size_t)zeros, K, alignment);
+  check(csr_to_ell_((int64_t)src.num_rows, (int64_t)K, (int64_t)dst.column_indices.pitch, raw_ptr(src.row_offsets),
+                    raw_ptr(src.column_indices), raw_ptr(src.values), raw_ptr(dst.column_indices.values),
+                    raw_ptr(dst.values.values)));
+}
+template <typename S, typename D>
+void device_convert(const S &src, D &dst, csr_format, hyb_format, size_t K = (size_t)-1, size_t alignment = 32) {
+  if (src.num_entries == 0) {
+    dst.resize(src.num_rows, src.num_cols, 0, 0, K == (size_t)-1 ? 0 : K);
+    return;
+  }
+  size_t tail;
+  if (K == (size_t)-1) {
+    const b200sp_convert_info info = csr_query(src, false);
+    K = (size_t)info.hyb_entries_per_row;
+    tail = (size_t)info.hyb_coo_entries;
+  } else {  // explicit width: count the tail on the host side of the offsets (set-up time)
+    auto ro = to_host_vector(src.row_offsets);
+    tail = 0;
+    for (size_t i = 0; i + 1 < ro.size(); ++i) tail += (size_t)std::max<long long>((long long)ro[i + 1] - ro[i] - (long long)K, 0);
+  }
+  dst.resize(src.num_rows, src.num_cols, src.num_entries - tail, tail, K, alignment);
+  check(csr_to_ell_((int64_t)src.num_rows, (int64_t)K, (int64_t)dst.ell.column_indices.pitch, raw_ptr(src.row_offsets),
+                    raw_ptr(src.column_indices), raw_ptr(src.values), raw_ptr(dst.ell.column_indices.values),
+                    raw_ptr(dst.ell.values.values)));
+  check(csr_to_tail_((int64_t)src.num_rows, (int64_t)K, raw_ptr(src.row_offsets), raw_ptr(src.column_indices),
+                     raw_ptr(src.values), raw_ptr(dst.coo.row_indices), raw_ptr(dst.coo.column_indices),
+                     raw_ptr(dst.coo.values)));
+}
+template <typename S, typename D>
+void device_convert(const S &src, D &dst, csr_format, dia_format, size_t alignment = 32) {
+  if (src.num_entries == 0) {
+    dst.resize(src.num_rows, src.num_cols, 0, 0);
+    return;
+  }
+  const size_t nd = (size_t)csr_query(src, true).num_diagonals;
+  fill_guard(nd, src.num_rows, src.num_entries, "dia_matrix fill-in would exceed maximum tolerance");
+  dst.resize(src.num_rows, src.num_cols, src.num_entries, nd, alignment);
+  check(csr_to_dia_((int64_t)src.num_rows, (int64_t)src.num_cols, (int64_t)nd, (int64_t)dst.values.pitch,
+                    raw_ptr(src.row_offsets), raw_ptr(src.column_indices), raw_ptr(src.values),
+                    raw_ptr(dst.diagonal_offsets), raw_ptr(dst.values.values)));
+}
+// COO source: to CSR on the device, then as above
+template <typename S, typename D, typename F2>
+void device_convert(const S &src, D &dst, coo_format, F2) {
+  cusp::csr_matrix<typename S::index_type, typename S::value_type, device_memory> csr;
+  device_convert(src, csr, coo_format(), csr_format());
+  device_convert(csr, dst, csr_format(), F2());
+}
+
+template <typename F1, typename F2>
+struct device_path : std::false_type {};
+template <>
+struct device_path<csr_format, coo_format> : std::true_type {};
+template <>
+struct device_path<csr_format, ell_format> : std::true_type {};
+template <>
+struct device_path<csr_format, hyb_format> : std::true_type {};
+template <>
+struct device_path<csr_format, dia_format> : std::true_type {};
+template <>
+struct device_path<coo_format, csr_format> : std::true_type {};
+template <>
+struct device_path<coo_format, ell_format> : std::true_type {};
+template <>
+struct device_path<coo_format, hyb_format> : std::true_type {};
+template <>
+struct device_path<coo_format, dia_format> : std::true_type {};
+
+template <typename S, typename D, typename F1, typename F2>
+void convert_generic(const S &src, D &dst, F1, F2, std::true_type) {
+  device_convert(src, dst, F1(), F2());
+}
+template <typename S, typename D, typename F1, typename F2>
+void convert_generic(const S &src, D &dst, F1, F2, std::false_type) {
+  host_csr<typename D::index_type, typename D::value_type> H;
+  gather(src, H, F1());
+  scatter(H, dst, F2());
+}
+
 template <typename S, typename D, typename F1, typename F2>
 void convert_dispatch(const S &src, D &dst, F1, F2) {
+  convert_generic(src, dst, F1(), F2(),
+                  std::integral_constant<bool, device_path<F1, F2>::value && device_convertible<S, D>::value>());
+}
+template <typename S, typename D, typename F1, typename F2>
+void convert_dispatch_host_only(const S &src, D &dst, F1, F2) {
   host_csr<typename D::index_type, typename D::value_type> H;
   gather(src, H, F1());
   scatter(H, dst, F2());
