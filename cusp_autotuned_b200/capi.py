@@ -114,7 +114,7 @@ F32, F64 = 0, 1
 K_CSR_VECTOR, K_CSR_STREAM, K_CSR_RING, K_CSR_BALANCED = 1, 2, 3, 4
 K_ELL_LDG, K_ELL_BULK = 1, 2
 K_DIA_LDG, K_DIA_BULK = 1, 2
-K_COO_SEGSCAN = 1
+K_COO_SEGSCAN, K_COO_RING = 1, 2
 ST_OK, ST_INVALID_INPUT, ST_CUDA_ERROR, ST_NOT_IMPLEMENTED, ST_ALLOC_FAILED, ST_COMM_ERROR = range(6)
 
 # every symbol include/b200sp.h declares (checked by tests/test_abi.py)

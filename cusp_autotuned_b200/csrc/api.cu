@@ -132,6 +132,12 @@ static std::vector<b200sp_cfg> cfg_space_vec(b200sp_format f, b200sp_dtype) {
           if (b == 512 && u > 7) continue;
           push(v, B200SP_K_COO_SEGSCAN, b, 0, u, 0, 0);
         }
+      {
+        const int bu[8][2] = {{128, 7}, {128, 9}, {128, 11}, {256, 5}, {256, 7}, {256, 9}, {512, 5}, {512, 7}};
+        for (auto &p : bu)
+          for (int st : {2, 3})
+            for (int cps : {2, 4, 6}) push(v, B200SP_K_COO_RING, p[0], 0, p[1], st, cps);
+      }
       break;
   }
   return v;

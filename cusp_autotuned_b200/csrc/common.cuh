@@ -89,6 +89,8 @@ struct b200sp_context {
     }
   };
   std::map<CsrKey, int> csr_max_row;
+  // COO gather-order probe per (column_indices pointer, element size, nnz): 1 = ring kernel
+  std::map<CsrKey, int> coo_gather_order;
   std::vector<void *> tune_events;  // cudaEvent_t pair
 
   // multi-GPU

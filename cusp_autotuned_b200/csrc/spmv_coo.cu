@@ -265,6 +265,236 @@ __global__ void coo_fixup_kernel(i64 num_tiles, const CooCarry<T> *carry, T *y, 
   y[row] = accumulate ? y[row] + total : total;  // !accumulate: y[row] still holds the memset zero
 }
 
+// ---------------------------------------------------------------------------
+// K_COO_RING — the same tiles and the same summation order as K_COO_SEGSCAN, but the three
+// entry streams never touch the LSU/L1TEX path: persistent CTAs, one producer lane stages
+// each tile's row / column / value ranges with three bulk copies (TMA engine, L2
+// evict-first) into an mbarrier ring; the consumers read their VPT consecutive entries
+// straight from shared memory (VPT odd -> conflict-free, no transposition buffer), gather
+// x, run the serial + shuffle segmented scan and release the stage.  L1TEX then carries only
+// the x gathers, which is what bounds COO on coalesced inputs (ncu: l1tex 80 % with the
+// LDG kernel).  One named barrier per tile (the cross-warp carry arrays are double
+// buffered by tile parity).  Needs 16-byte aligned array bases; spmv_coo falls back to
+// K_COO_SEGSCAN otherwise.  Bit-identical to K_COO_SEGSCAN for equal (BLOCK, VPT).
+// ---------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void consumer_bar() {
+  asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory");
+}
+
+template <typename T, int BLOCK, int VPT>
+__global__ void __launch_bounds__(BLOCK + 32) coo_ring_kernel(CooArgs<T> a, int stages, i64 num_tiles) {
+  constexpr int TILE = BLOCK * VPT;
+  constexpr int NW = BLOCK / 32;
+  constexpr int RSTR = TILE + 8;  // rows of entries [start-4, start+TILE+4): previous and next row ride along
+  constexpr int EPV = 16 / (int)sizeof(T);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T *s_val = reinterpret_cast<T *>(smem_raw);
+  int *s_col = reinterpret_cast<int *>(smem_raw + (size_t)stages * TILE * sizeof(T));
+  int *s_row = s_col + (size_t)stages * TILE;
+  uint64_t *full = reinterpret_cast<uint64_t *>(s_row + (size_t)stages * RSTR);
+  uint64_t *empty = full + stages;
+  __shared__ T s_wv[2][NW];
+  __shared__ int s_wf[2][NW];
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NW);
+    }
+    mbar_fence_init();
+  }
+  for (int i = tid; i < stages * TILE; i += BLOCK + 32) s_col[i] = 0;
+  __syncthreads();
+
+  const i64 nnz = a.nnz;
+  if (tid >= BLOCK) {
+    // ------------------------------ producer --------------------------------
+    if (tid == BLOCK) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const uint64_t pol = l2_policy_evict_first();
+      int s = 0;
+      uint32_t ph = 0;
+      for (i64 tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const i64 start = tile * TILE;
+        const int n = (int)min((i64)TILE, nnz - start);
+        mbar_wait(&empty[s], ph ^ 1);
+        T *dv = s_val + (size_t)s * TILE;
+        int *dc = s_col + (size_t)s * TILE;
+        int *dr = s_row + (size_t)s * RSTR + (start > 0 ? 0 : 4);
+        const i64 g0 = start > 0 ? start - 4 : 0;
+        const int nr = (int)(min(start + TILE + 4, nnz) - g0);
+        const int bv = n & ~(EPV - 1), bc = n & ~3, br = nr & ~3;
+        // the (at most 3) entries after the last complete 16 bytes of the arrays
+        for (int j = bv; j < n; ++j) dv[j] = a.Ax[start + j];
+        for (int j = bc; j < n; ++j) dc[j] = a.Aj[start + j];
+        for (int j = br; j < nr; ++j) dr[j] = a.Ai[g0 + j];
+        mbar_expect_tx(&full[s], (uint32_t)(bv * sizeof(T) + (bc + br) * sizeof(int)));
+        if (br > 0) bulk_g2s(dr, a.Ai + g0, (uint32_t)(br * sizeof(int)), &full[s], pol);
+        if (bc > 0) bulk_g2s(dc, a.Aj + start, (uint32_t)(bc * sizeof(int)), &full[s], pol);
+        if (bv > 0) bulk_g2s(dv, a.Ax + start, (uint32_t)(bv * sizeof(T)), &full[s], pol);
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+    return;
+  }
+  // ------------------------------ consumers -------------------------------
+  const int lane = tid & 31, w = tid >> 5;
+  const unsigned cols = (unsigned)a.cols;
+  int s = 0, par = 0;
+  uint32_t ph = 0;
+  for (i64 tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, par ^= 1) {
+    const i64 start = tile * TILE;
+    const int n = (int)min((i64)TILE, nnz - start);
+    const int n_rows = (start + TILE < nnz) ? TILE + 1 : n;  // entries whose row index was staged
+    mbar_wait(&full[s], ph);
+    const int *pr = s_row + (size_t)s * RSTR + 4;  // pr[j]: row of entry start + j
+    const int *pc = s_col + (size_t)s * TILE;
+    const T *pv_ = s_val + (size_t)s * TILE;
+    int rr[VPT + 1], c[VPT];
+    T v[VPT], xv[VPT];
+    const int prev_row = (start > 0) ? pr[-1] : -1;
+#pragma unroll
+    for (int q = 0; q < VPT; ++q) {
+      const int idx = tid * VPT + q;
+      rr[q] = (idx < n) ? pr[idx] : -1;
+      c[q] = pc[idx];
+      v[q] = pv_[idx];
+    }
+    rr[VPT] = (tid * VPT + VPT < n_rows) ? pr[tid * VPT + VPT] : -1;
+    const int s_used = s;  // released after the products are formed (see below)
+    if (++s == stages) {
+      s = 0;
+      ph ^= 1;
+    }
+#pragma unroll
+    for (int q = 0; q < VPT; ++q) xv[q] = ld_ro(a.x + min((unsigned)c[q], cols - 1));
+
+    // ---- per-thread serial segmented reduction over VPT consecutive entries ----
+    T run = T(0), head = T(0);
+    int head_row = -1;
+    bool has_b = false;
+#pragma unroll
+    for (int q = 0; q < VPT; ++q) {
+      pin(xv[q]);
+      const T p = (tid * VPT + q < n) ? v[q] * xv[q] : T(0);
+      run = run + p;
+      if (rr[q] != rr[q + 1]) {  // row rr[q] ends at this entry
+        if (!has_b) {
+          head = run;
+          head_row = rr[q];
+          has_b = true;
+        } else if (rr[q] >= 0) {
+          a.y[rr[q]] = a.accumulate ? a.y[rr[q]] + run : run;  // began and ended inside this thread
+        }
+        run = T(0);
+      }
+    }
+
+    // ---- block-wide segmented scan of (has_b, tail) ---------------------------
+    T vi = run;
+    int fi = has_b ? 1 : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const T vu = __shfl_up_sync(0xffffffffu, vi, d);
+      const int fu = __shfl_up_sync(0xffffffffu, fi, d);
+      if (lane >= d) {
+        if (!fi) vi = vu + vi;
+        fi |= fu;
+      }
+    }
+    if (lane == 31) {
+      s_wv[par][w] = vi;
+      s_wf[par][w] = fi;
+    }
+    consumer_bar<BLOCK>();
+    T VW = T(0);
+    int FW = 0;  // a row ended in an earlier warp of this tile
+    for (int k = 0; k < w; ++k) {
+      VW = s_wf[par][k] ? s_wv[par][k] : VW + s_wv[par][k];
+      FW |= s_wf[par][k];
+    }
+    const T Vi = fi ? vi : VW + vi;  // block-inclusive tail sum
+    T carry_in = __shfl_up_sync(0xffffffffu, Vi, 1);
+    int f_before = __shfl_up_sync(0xffffffffu, fi, 1);
+    if (lane == 0) {
+      carry_in = VW;
+      f_before = 0;
+    }
+    f_before |= FW;
+
+    CooCarry<T> *cr = a.carry + tile;
+    if (has_b && head_row >= 0) {
+      const T total = carry_in + head;
+      const bool continued = (head_row == prev_row);  // only the first row end of a tile can be
+      if (continued) {
+        cr->head_row = head_row;
+        cr->head_val = total;
+      } else {
+        a.y[head_row] = a.accumulate ? a.y[head_row] + total : total;
+        if (!f_before) {
+          cr->head_row = -1;
+          cr->head_val = T(0);
+        }
+      }
+    }
+    if (tid == BLOCK - 1) {
+      if (!(fi | FW)) {  // no row ends inside this tile
+        cr->head_row = -1;
+        cr->head_val = T(0);
+      }
+      cr->pad = 0;
+      const int last_row = rr[VPT - 1];
+      if (last_row >= 0 && last_row == rr[VPT]) {
+        cr->tail_row = last_row;
+        cr->tail_val = Vi;
+        cr->leader = (last_row != prev_row) ? 1 : 0;
+      } else {
+        cr->tail_row = -1;
+        cr->tail_val = T(0);
+        cr->leader = 0;
+      }
+    }
+    // Release the stage only at the end of the tile.  Every staged value has by now been
+    // consumed by a later instruction, so the shared-memory loads have returned.  An arrive
+    // issued right after the loads is NOT ordered behind them by the hardware (ptxas puts no
+    // scoreboard wait on SYNCS.ARRIVE): the producer's next bulk copy then raced with loads
+    // still queued in the MIO pipe — seen on hardware as one warp of a tile reading a
+    // half-overwritten stage.
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s_used]);
+  }
+}
+
+template <typename T, int BLOCK, int VPT>
+static b200sp_status launch_coo_ring(b200sp_handle h, cudaStream_t st, CooArgs<T> a, int stages, int ctas_per_sm) {
+  constexpr int TILE = BLOCK * VPT;
+  const i64 tiles = ceil_div(a.nnz, (i64)TILE);
+  b200sp_status s = ensure_scratch(h, (size_t)tiles * sizeof(CooCarry<T>));
+  if (s != B200SP_OK) return s;
+  a.carry = reinterpret_cast<CooCarry<T> *>(h->scratch);
+  const size_t smem = (size_t)stages * ((size_t)TILE * (sizeof(T) + sizeof(int)) + (size_t)(TILE + 8) * sizeof(int)) +
+                      2 * (size_t)stages * sizeof(uint64_t);
+  if (smem > (size_t)h->max_smem_optin)
+    return set_error(h, B200SP_INVALID_INPUT, "coo ring: %zu B smem exceeds %d", smem, h->max_smem_optin);
+  auto kern = coo_ring_kernel<T, BLOCK, VPT>;
+  B200SP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int resident = 0;
+  B200SP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, BLOCK + 32, smem));
+  if (resident < 1) return set_error(h, B200SP_INVALID_INPUT, "coo ring: configuration does not fit on an SM");
+  i64 grid = (i64)h->num_sms * (ctas_per_sm < resident ? ctas_per_sm : resident);
+  if (grid > tiles) grid = tiles;
+  kern<<<(unsigned)grid, BLOCK + 32, smem, st>>>(a, stages, tiles);
+  B200SP_LAUNCH_CHECK(h, "coo_ring_kernel");
+  coo_fixup_kernel<T><<<(unsigned)ceil_div(tiles, 256), 256, 0, st>>>(tiles, a.carry, a.y, a.accumulate);
+  B200SP_LAUNCH_CHECK(h, "coo_fixup_kernel");
+  return B200SP_OK;
+}
+
 template <typename T, int BLOCK, int VPT>
 static b200sp_status launch_coo(b200sp_handle h, cudaStream_t st, CooArgs<T> a) {
   constexpr int TILE = BLOCK * VPT;
@@ -321,10 +551,81 @@ template b200sp_status spmv_csr_balanced<float>(b200sp_handle, cudaStream_t, i64
 template b200sp_status spmv_csr_balanced<double>(b200sp_handle, cudaStream_t, i64, i64, i64, const int *, const int *,
                                                  const double *, const double *, double *, int, int, int);
 
-static void coo_defaults(b200sp_cfg &c) {
-  if (c.kernel == 0) c.kernel = B200SP_K_COO_SEGSCAN;
+// Gather-locality probe for the default kernel choice.  The two COO kernels issue their x
+// gathers in different lane orders: K_COO_SEGSCAN lane l of a warp reads entry 32k + l
+// (consecutive entries), K_COO_RING lane l reads entry 7l + q (its own 7 consecutive entries).
+// What a gather costs in L1TEX is the number of distinct 128-byte lines per instruction, so
+// the probe counts exactly that for both orders on `samples` windows of 224 entries spread
+// over the matrix (one warp per window, __match_any_sync on the line id).
+// out[0] = lines in consecutive-entry order, out[1] = lines in 7-strided order.
+__global__ void coo_analyze_kernel(i64 nnz, const int *Aj, int line_shift, int samples, int *out) {
+  const int lane = threadIdx.x & 31;
+  const int wid = (int)(((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (wid >= samples) return;
+  const i64 windows = nnz / 224;
+  const i64 base = (windows * wid / samples) * 224;
+  int la = 0, lb = 0;
+  for (int q = 0; q < 7; ++q) {
+    const int ca = Aj[base + q * 32 + lane] >> line_shift;
+    const int cb = Aj[base + lane * 7 + q] >> line_shift;
+    const unsigned ma = __match_any_sync(0xffffffffu, ca), mb = __match_any_sync(0xffffffffu, cb);
+    la += (__ffs(ma) - 1 == lane) ? 1 : 0;
+    lb += (__ffs(mb) - 1 == lane) ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    la += __shfl_down_sync(0xffffffffu, la, o);
+    lb += __shfl_down_sync(0xffffffffu, lb, o);
+  }
+  if (lane == 0) {
+    atomicAdd(out, la);
+    atomicAdd(out + 1, lb);
+  }
+}
+
+// true: the ring kernel's gather order coalesces (few lines per instruction, and no worse than
+// the consecutive order).  Cached per (column_indices, nnz, element size); a hint only — both
+// kernels are correct on every matrix and produce the same bits.
+static bool coo_prefers_ring(b200sp_handle h, cudaStream_t st, i64 nnz, const int *Aj, size_t elem) {
+  const b200sp_context::CsrKey key{Aj, (int64_t)elem, nnz};
+  auto it = h->coo_gather_order.find(key);
+  if (it != h->coo_gather_order.end()) return it->second != 0;
+  const int samples = 2048;
+  int *d = reinterpret_cast<int *>(h->dev_scalars + 54);  // 2 ints
+  int *p = reinterpret_cast<int *>(h->pinned_scalars + 54);
+  int ring = 0;
+  if (cudaMemsetAsync(d, 0, 2 * sizeof(int), st) == cudaSuccess) {
+    coo_analyze_kernel<<<samples / 8, 256, 0, st>>>(nnz, Aj, elem == 4 ? 5 : 4, samples, d);
+    h->launches++;
+    if (cudaMemcpyAsync(p, d, 2 * sizeof(int), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+        cudaStreamSynchronize(st) == cudaSuccess) {
+      const double per_instr_seq = (double)p[0] / (7.0 * samples), per_instr_str = (double)p[1] / (7.0 * samples);
+      ring = (per_instr_str <= 4.0 && per_instr_str <= per_instr_seq) ? 1 : 0;
+    }
+  }
+  cudaGetLastError();
+  if (h->coo_gather_order.size() > 256) h->coo_gather_order.clear();
+  h->coo_gather_order[key] = ring;
+  return ring != 0;
+}
+
+static void coo_defaults(b200sp_cfg &c, b200sp_handle h, cudaStream_t st, i64 nnz, const int *Aj, size_t elem,
+                         bool tma_ok) {
+  const bool no_shape = c.block_size == 0 && c.unroll == 0;
   if (c.block_size == 0) c.block_size = 256;
   if (c.unroll == 0) c.unroll = 7;
+  // The persistent ring needs a few tiles per resident CTA to be worth its prologue, and its
+  // gather order must coalesce (stencils, banded operators); scattered or consecutive-column
+  // streams (graphs, one entry per row) run the LDG kernel with its 2048 threads per SM.
+  if (c.kernel == 0)
+    c.kernel = (tma_ok && nnz >= (i64)h->num_sms * 8 * c.block_size * c.unroll && coo_prefers_ring(h, st, nnz, Aj, elem))
+                   ? B200SP_K_COO_RING
+                   : B200SP_K_COO_SEGSCAN;
+  if (c.kernel == B200SP_K_COO_RING && no_shape && elem == 8) c.block_size = 512;  // sweep: 512x7 for fp64
+  if (c.kernel == B200SP_K_COO_RING) {
+    if (c.stages == 0) c.stages = 2;
+    if (c.ctas_per_sm == 0) c.ctas_per_sm = 4;
+  }
 }
 
 template <typename T>
@@ -342,8 +643,11 @@ b200sp_status spmv_coo(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64
   B200SP_REQUIRE(h, cols > 0, "coo: num_cols == 0 with stored entries");
 
   b200sp_cfg c = cfg ? *cfg : b200sp_cfg{};
-  coo_defaults(c);
-  if (c.kernel != B200SP_K_COO_SEGSCAN) return set_error(h, B200SP_INVALID_INPUT, "coo: unknown kernel id %d", c.kernel);
+  const bool tma_ok = aligned16(Ai) && aligned16(Aj) && aligned16(Ax);
+  coo_defaults(c, h, st, nnz, Aj, sizeof(T), tma_ok);
+  if (c.kernel == B200SP_K_COO_RING && !tma_ok) c.kernel = B200SP_K_COO_SEGSCAN;  // bulk copies need 16-byte bases
+  if (c.kernel != B200SP_K_COO_SEGSCAN && c.kernel != B200SP_K_COO_RING)
+    return set_error(h, B200SP_INVALID_INPUT, "coo: unknown kernel id %d", c.kernel);
 
   CooArgs<T> a;
   a.rows = rows; a.cols = cols; a.nnz = nnz; a.Ai = Ai; a.Aj = Aj; a.Ax = Ax; a.x = x; a.y = y;
@@ -352,6 +656,18 @@ b200sp_status spmv_coo(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64
   a.carry = nullptr;
   a.Ap = nullptr;
   a.tile_first_row = nullptr;
+  if (c.kernel == B200SP_K_COO_RING) {
+    if (c.stages < 2 || c.stages > 8 || c.ctas_per_sm < 1 || c.ctas_per_sm > 16)
+      return set_error(h, B200SP_INVALID_INPUT, "coo ring: unsupported stages=%d ctas_per_sm=%d", c.stages,
+                       c.ctas_per_sm);
+#define CASE(B, V) \
+  if (c.block_size == B && c.unroll == V) return launch_coo_ring<T, B, V>(h, st, a, c.stages, c.ctas_per_sm);
+    CASE(128, 7) CASE(128, 9) CASE(128, 11)
+    CASE(256, 5) CASE(256, 7) CASE(256, 9)
+    CASE(512, 5) CASE(512, 7)
+#undef CASE
+    return set_error(h, B200SP_INVALID_INPUT, "coo ring: unsupported block_size=%d unroll=%d", c.block_size, c.unroll);
+  }
 #define CASE(B, V) \
   if (c.block_size == B && c.unroll == V) return launch_coo<T, B, V>(h, st, a);
   CASE(128, 5) CASE(128, 7) CASE(128, 9) CASE(128, 11)

@@ -93,7 +93,10 @@ enum {
   B200SP_K_DIA_BULK = 2,
   /* COO  (replaces thrust reduce_by_key generic/multiply/spmv.h:182-238,
    *       spmv_coo_flat_kernel coo_flat_spmv.h:225-463, KTT coo_spmv)         */
-  B200SP_K_COO_SEGSCAN = 1 /* nnz-balanced tiles, smem segmented scan, no atomics */
+  B200SP_K_COO_SEGSCAN = 1, /* nnz-balanced tiles, smem segmented scan, no atomics */
+  B200SP_K_COO_RING = 2     /* same tiles and summation order; persistent CTAs, entry streams
+                               staged by cp.async.bulk into an mbarrier ring (default for
+                               16-byte aligned arrays with enough tiles)                     */
 };
 
 /* ---- lifecycle ---------------------------------------------------------- */

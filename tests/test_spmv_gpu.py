@@ -274,7 +274,67 @@ def test_coo_tile_boundary_cases(ndt, tdt, dev):
         A = dict(format="coo", num_rows=n, num_cols=n, num_entries=len(rows), row_indices=rows,
                  column_indices=cols, values=vals)
         x = (np.arange(n) % 3 + 1).astype(ndt)
-        assert np.array_equal(gpu_multiply("coo", A, x, dev, cfg=capi.Cfg(block_size=256, unroll=7)), O.spmv(A, x))
+        for kern in (capi.K_COO_SEGSCAN, capi.K_COO_RING):
+            cfg = capi.Cfg(kernel=kern, block_size=256, unroll=7)
+            assert np.array_equal(gpu_multiply("coo", A, x, dev, cfg=cfg), O.spmv(A, x)), (lens[:3], kern)
+
+
+@pytest.mark.parametrize("ndt,tdt", DTYPES)
+def test_coo_ring_matches_segscan_bitwise(ndt, tdt, dev):
+    """K_COO_RING keeps K_COO_SEGSCAN's tiles and summation order: identical bits on any data.
+    Sizes: every residue of nnz mod 4 (the producer's scalar tail), far more tiles than the
+    persistent grid x stages (ring wrap-around), hub rows across many tiles, accumulate."""
+    rng = np.random.default_rng(11)
+    n = 40000
+    for nnz in (1, 2, 3, 5, 1791, 1792, 1793, 1792 * 3 + 2, 1792 * 1500 + 3, 1792 * 2600 + 1):
+        rows = np.sort(rng.integers(0, n, nnz)).astype(np.int32)
+        if nnz > 100000:
+            rows[1000:60000] = rows[1000]  # a hub row spanning ~33 tiles
+            rows = np.sort(rows)
+        cols = rng.integers(0, n, nnz).astype(np.int32)
+        vals = rng.uniform(0.5, 1.5, nnz).astype(ndt)
+        A = dict(format="coo", num_rows=n, num_cols=n, num_entries=nnz, row_indices=rows,
+                 column_indices=cols, values=vals)
+        x = rng.uniform(0.5, 1.5, n).astype(ndt)
+        y0 = rng.uniform(-1, 1, n).astype(ndt)
+        want = O.spmv(A, x)
+        for b, u in ((256, 7), (128, 9), (512, 5)):
+            seg = gpu_multiply("coo", A, x, dev, cfg=capi.Cfg(kernel=capi.K_COO_SEGSCAN, block_size=b, unroll=u))
+            for st, cps in ((2, 4), (3, 1)):
+                ring = gpu_multiply("coo", A, x, dev,
+                                    cfg=capi.Cfg(kernel=capi.K_COO_RING, block_size=b, unroll=u, stages=st,
+                                                 ctas_per_sm=cps))
+                assert np.array_equal(ring, seg), (nnz, b, u, st, cps)
+            assert rel_err(seg, want) <= TOL[np.dtype(ndt)], (nnz, b, u)
+        shape = dict(block_size=256, unroll=7)  # same tiles -> same grouping of the sums
+        assert np.array_equal(gpu_multiply("coo", A, x, dev, y0=y0, accumulate=True,
+                                           cfg=capi.Cfg(kernel=capi.K_COO_RING, **shape)),
+                              gpu_multiply("coo", A, x, dev, y0=y0, accumulate=True,
+                                           cfg=capi.Cfg(kernel=capi.K_COO_SEGSCAN, **shape)))
+        got = gpu_multiply("coo", A, x, dev, y0=y0, accumulate=True, cfg=capi.Cfg(kernel=capi.K_COO_RING))
+        assert scaled_err(got, O.spmv(A, x, y0, accumulate=True), np.abs(y0) + want) <= TOL[np.dtype(ndt)]
+
+
+@pytest.mark.parametrize("ndt,tdt", DTYPES)
+def test_coo_unaligned_bases_fall_back(ndt, tdt, dev):
+    """array bases that are not 16-byte aligned cannot be bulk-copied: K_COO_RING requests run
+    the LDG kernel with the same result"""
+    rng = np.random.default_rng(12)
+    n, nnz = 3000, 1792 * 700 + 5
+    rows = np.sort(rng.integers(0, n, nnz)).astype(np.int32)
+    cols = rng.integers(0, n, nnz).astype(np.int32)
+    vals = rng.integers(1, 4, nnz).astype(ndt)
+    x = rng.integers(-3, 4, n).astype(ndt)
+    A = dict(format="coo", num_rows=n, num_cols=n, num_entries=nnz, row_indices=rows,
+             column_indices=cols, values=vals)
+    want = O.spmv(A, x)
+    pad = lambda a: tdev(np.concatenate([a[:1], a]), dev)[1:]  # base shifted by one element
+    Ad = cusp.coo_matrix(n, n, pad(rows), pad(cols), pad(vals))
+    assert Ad.values.data_ptr() % 16 != 0
+    for kern in (0, capi.K_COO_RING):
+        y = torch.full((n,), 5, dtype=tdt, device=dev)
+        cusp.multiply(Ad, tdev(x, dev), y, cfg=capi.Cfg(kernel=kern))
+        assert np.array_equal(y.cpu().numpy(), want)
 
 
 def test_empty_and_degenerate(dev, handle):

@@ -25,7 +25,7 @@ dev = torch.device("cuda", 0)
 h = cusp.default_handle()
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 REPS = int(os.environ.get("SWEEP_REPS", "10"))
-KNAME = {capi.FMT_CSR: {1: "vector", 2: "stream", 3: "ring", 4: "balanced"}, capi.FMT_COO: {1: "segscan"},
+KNAME = {capi.FMT_CSR: {1: "vector", 2: "stream", 3: "ring", 4: "balanced"}, capi.FMT_COO: {1: "segscan", 2: "ring"},
          capi.FMT_HYB: {1: "ldg", 2: "bulk"}}
 
 
@@ -69,7 +69,8 @@ def sweep(label, A, x, space=None, out=None, check=True):
     y = torch.empty(A.num_rows, dtype=x.dtype, device=dev)
     d = A.descriptor()
     B = comp_bytes(A, es)
-    h.spmv(d, x, y)
+    # reference output: for COO the LDG kernel (the ring kernel must reproduce its bits)
+    h.spmv(d, x, y, cfg=capi.Cfg(kernel=capi.K_COO_SEGSCAN) if A.format == capi.FMT_COO else None)
     yref = y.clone()
     scale = float(yref.abs().max().item()) or 1.0
     recs = []
@@ -142,6 +143,9 @@ def main():
         C = convert.rmat(scale, 16, seed=42, dtype=torch.float32)
         x = torch.rand(C.num_cols, dtype=torch.float32, device=dev) + 0.5
         sweep(f"coo rmat s{scale}", C, x, out=out)
+        if os.environ.get("SWEEP_ONLY") == "coo":
+            json.dump(out, open(f"gpurun_out/sweep_{what}_coo.json", "w"))
+            return
         A = convert.coo_to_csr(C)
         sweep(f"csr rmat s{scale}", A, x, out=out)
         H = convert.csr_to_hyb(A)
