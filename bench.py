@@ -341,7 +341,7 @@ def main():
                                                  "frac_of_8TBs": roof["frac_of_nominal_8TBs"]}
             del A, xw, y
             torch.cuda.empty_cache()
-            for fmt in ("dia", "ell", "csr"):
+            for fmt in ("dia", "ell", "csr", "coo"):
                 for tt, nm in ((torch.float32, "f32"), (torch.float64, "f64")):
                     if fmt == "dia" and nm == "f64":
                         continue

@@ -301,6 +301,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Releasing a ring stage: the consumer's `mbarrier.arrive` on the stage's `empty` barrier
+// must not be issued while shared-memory loads of that stage are still outstanding.  On
+// sm_100a nothing orders it behind them: ptxas puts no scoreboard wait on SYNCS.ARRIVE, the
+// arrive overtakes LDS instructions still queued in the MIO pipe, the producer's next bulk
+// copy lands, and the late LDS reads the NEW tile (measured with the COO ring kernel:
+// arrive right after the loads -> a few warps per launch read a half-overwritten stage;
+// membar.cta in between does not help; consuming every loaded register first does).
+// consume_before_release(acc) is that consumption for a value every staged load flows
+// into: a real compare-and-branch on it (taken only for one NaN bit pattern, and then it
+// only executes `nanosleep 0`) that the scheduler cannot move behind the arrive.
+__device__ __forceinline__ int hi_bits(float v) { return __float_as_int(v); }
+__device__ __forceinline__ int hi_bits(double v) { return __double2hiint(v); }
+template <typename T>
+__device__ __forceinline__ void consume_before_release(T acc) {
+  if (hi_bits(acc) == (int)0x7ff4dead) asm volatile("nanosleep.u32 0;");
+}
+
 // L2 eviction policy for slabs that are read exactly once
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   uint64_t pol;

@@ -431,6 +431,7 @@ __global__ void __launch_bounds__(BLOCK + 32) csr_ring_kernel(CsrArgs<T> a, int 
           part = __shfl_sync(0xffffffffu, part, 0);
           if (lane == src) acc = acc + part;
         }
+        consume_before_release(acc);  // every staged value of this piece has flowed into acc
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
         if (++s == stages) {

@@ -336,6 +336,8 @@ __global__ void __launch_bounds__(BLOCK + 32) dia_bulk_kernel(DiaArgs<T> a, int 
             const T t = acc[i] + sv[u * R + tid + i * BLOCK] * xv[u][i];
             acc[i] = (u < kc && r0 + tid + i * BLOCK + off[u] < cols) ? t : acc[i];
           }
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) consume_before_release(acc[i]);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
         if (++s == stages) {

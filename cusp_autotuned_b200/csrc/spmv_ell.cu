@@ -231,6 +231,8 @@ __global__ void __launch_bounds__(BLOCK + 32) ell_bulk_kernel(EllArgs<T> a, int 
             const T t = acc[i] + vv * xv[u][i];
             acc[i] = (cc[u][i] != -1 && k0 + u < len[i]) ? t : acc[i];
           }
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) consume_before_release(acc[i]);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
         if (++s == stages) {

@@ -20,7 +20,7 @@ def _grid(stencil, dims):
 def poisson(fmt: str, stencil: int, dims, dtype=torch.float64, device=None, row_begin=0, num_rows=None,
             halo_lo=0, halo_hi=0, handle=None):
     """Rows [row_begin, row_begin+num_rows) of the stencil operator in `fmt`
-    ("dia" | "ell" | "csr").  With halos, column indices are relative to the
+    ("dia" | "ell" | "csr" | "coo").  With halos, column indices are relative to the
     window [halo_lo | local | halo_hi] (row-partitioned operators)."""
     h = handle or default_handle()
     device = device or torch.device("cuda", torch.cuda.current_device())
@@ -44,6 +44,12 @@ def poisson(fmt: str, stencil: int, dims, dtype=torch.float64, device=None, row_
         vals = torch.empty(stencil * pitch, dtype=dtype, device=device)
         h.poisson_ell(stencil, nx, ny, nz, row_begin, num_rows, col_shift, pitch, cidx, vals)
         return ell_matrix(num_rows, num_cols, nnz, stencil, pitch, cidx, vals)
+    if fmt == "coo":  # DIA -> COO: same entries and order as CSR (dia_to_other.h:61-161), rows expanded
+        A = poisson("csr", stencil, dims, dtype=dtype, device=device, row_begin=row_begin, num_rows=num_rows,
+                    halo_lo=halo_lo, halo_hi=halo_hi, handle=h)
+        ri = torch.empty(max(nnz, 1), dtype=torch.int32, device=device)[:nnz]
+        h.offsets_to_indices(A.row_offsets, ri)
+        return coo_matrix(A.num_rows, A.num_cols, ri, A.column_indices, A.values)
     if fmt == "csr":
         Ap = torch.empty(num_rows + 1, dtype=torch.int32, device=device)
         Aj = torch.empty(max(nnz, 1), dtype=torch.int32, device=device)[:nnz]

@@ -111,3 +111,15 @@ def test_only_sm100a_code_in_the_library():
     out = subprocess.check_output(["/usr/local/cuda/bin/cuobjdump", "-lelf", capi.LIB_PATH], text=True)
     archs = set(re.findall(r"sm_\d+a?", out))
     assert archs == {"sm_100a"}, archs
+
+
+def test_ring_stages_are_released_after_their_loads_are_consumed():
+    """SASS check (tools/check_release_order.py): no consumer-side mbarrier arrive with an
+    unconsumed shared-memory load in front of it — the hardware does not order the two"""
+    if not os.path.exists("/usr/local/cuda/bin/cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import check_release_order
+    sites, flagged = check_release_order.scan(capi.LIB_PATH)
+    assert sites >= 40 and not flagged, flagged

@@ -34,6 +34,10 @@ def test_poisson_builders_bit_identical(stencil, dims, ndt, tdt, dev):
     Cm = gallery.poisson("csr", stencil, dims, dtype=tdt)
     assert _eq(Cm.row_offsets, c["row_offsets"]) and _eq(Cm.column_indices, c["column_indices"])
     assert _eq(Cm.values, c["values"])
+    o = O.convert(ref, "coo")
+    Om = gallery.poisson("coo", stencil, dims, dtype=tdt)
+    assert _eq(Om.row_indices, o["row_indices"]) and _eq(Om.column_indices, o["column_indices"])
+    assert _eq(Om.values, o["values"])
     assert capi.poisson_num_entries(stencil, *(dims if stencil == 7 else (*dims, 1)), 0, ref["num_rows"]) == ref["num_entries"]
 
 
