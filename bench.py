@@ -329,7 +329,7 @@ def main():
            "note": "matrix device-resident (cusp::dia_matrix<..,device_memory>), x from / y to pinned host memory"}
     y_check = float(y.double().abs().sum().item())
 
-    formats, cg, cpu = {}, None, None
+    formats, cg, cpu, graph = {}, None, None, None
     if not args.quick:
         del xh, yh
         # ---- per-format SpMV at the BASELINE configs (rank 0 of a single-GPU run) -----------------
@@ -404,6 +404,48 @@ def main():
               "includes": "setup SpMV + ||b|| + residual init (1 extra SpMV over %d iterations)" % iters}
         del Ac, b, xs
         torch.cuda.empty_cache()
+        # ---- graph operator: R-MAT, contiguous row blocks, x all-gathered before every product -----
+        if world > 1:
+            try:
+                from cusp_autotuned_b200.matrix import coo_matrix
+                from cusp_autotuned_b200.partition import nnz_balanced_offsets
+                Cg = convert.rmat(args.rmat_scale, 16, seed=42, dtype=torch.float32)  # same graph on every GPU
+                n = Cg.num_rows
+                offs = nnz_balanced_offsets(Cg.row_indices, n, world)
+                bounds = torch.searchsorted(Cg.row_indices, torch.tensor(offs, dtype=torch.int32, device=dev))
+                g0, g1 = int(bounds[rank]), int(bounds[rank + 1])
+                nloc = offs[rank + 1] - offs[rank]
+                loc = coo_matrix(nloc, n, (Cg.row_indices[g0:g1] - offs[rank]).contiguous(),
+                                 Cg.column_indices[g0:g1].clone(), Cg.values[g0:g1].clone())
+                nnz_graph = Cg.num_entries
+                del Cg
+                torch.cuda.empty_cache()
+                xf = torch.rand(n, dtype=torch.float32, device=dev) + 0.5
+                yl = torch.empty(nloc, dtype=torch.float32, device=dev)
+                gd = loc.descriptor()
+                gsteps = max(10, min(args.steps, 50))
+                for _ in range(3):
+                    h.spmv_dist_gather(gd, offs, xf, yl)
+                barrier()
+                g_e0 = torch.cuda.Event(enable_timing=True)
+                g_e1 = torch.cuda.Event(enable_timing=True)
+                g_e0.record()
+                for _ in range(gsteps):
+                    h.spmv_dist_gather(gd, offs, xf, yl)
+                g_e1.record()
+                barrier()
+                g_ms = max_over_ranks(g_e0.elapsed_time(g_e1) / gsteps)
+                nnz_max = max_over_ranks(float(loc.num_entries))
+                graph = {"workload": f"COO fp32 R-MAT scale {args.rmat_scale} ef 16, nnz-balanced row blocks over {world} GPUs, "
+                                     "x all-gathered every step (b200sp_spmv_dist_gather)",
+                         "scaling": "strong", "ms_per_step": g_ms, "gflops": 2.0 * nnz_graph / g_ms / 1e6,
+                         "nnz_total": int(nnz_graph), "nnz_max_per_gpu": int(nnz_max),
+                         "gathered_bytes_per_gpu": int((n - nloc) * 4), "row_offsets": offs,
+                         "comm": "nvlink-p2p pull from IPC staging" if h.comm_p2p_enabled() else "nccl send/recv"}
+                del loc, xf, yl
+                torch.cuda.empty_cache()
+            except Exception as ex:
+                graph = {"error": repr(ex)}
         if world > 1:
             # every rank: no cross-GPU wait may have given up (peer-memory path), else the numbers are void
             bad = torch.tensor([h.comm_timeouts()], dtype=torch.int64, device=dev)
@@ -447,7 +489,7 @@ def main():
                        "l2": "per-step inputs (1.21 GB) exceed the 126 MB L2, no flush needed",
                        "parallelism": f"rowblock{world}", "api": "b200sp_spmv / b200sp_spmv_dist (C ABI)"},
             "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "cpu_baseline": cpu, "formats": formats, "cg": cg,
+            "cpu_baseline": cpu, "formats": formats, "cg": cg, "graph": graph,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

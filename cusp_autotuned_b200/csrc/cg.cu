@@ -759,4 +759,18 @@ b200sp_status b200sp_spmv_dist(b200sp_handle h, b200sp_stream stream, const b200
   if (s != B200SP_OK) return s;
   return b200sp_spmv(h, stream, A_local, x_window, y_local, 0, cfg);
 }
+
+b200sp_status b200sp_spmv_dist_gather(b200sp_handle h, b200sp_stream stream, const b200sp_matrix *A_local,
+                                      const int64_t *slice_offsets, void *x_full, void *y_local,
+                                      const b200sp_cfg *cfg) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, A_local && slice_offsets && x_full && y_local, "spmv_dist_gather: null argument");
+  B200SP_REQUIRE(h, h->nccl_comm || h->world == 1, "spmv_dist_gather: b200sp_comm_init has not been called");
+  B200SP_REQUIRE(h, slice_offsets[0] == 0 && slice_offsets[h->world] == A_local->num_cols,
+                 "spmv_dist_gather: slice offsets must cover [0, num_cols)");
+  const size_t elem = A_local->dtype == B200SP_F64 ? 8 : 4;
+  b200sp_status s = b200sp::comm_allgather_slices(h, (cudaStream_t)stream, x_full, slice_offsets, elem);
+  if (s != B200SP_OK) return s;
+  return b200sp_spmv(h, stream, A_local, x_full, y_local, 0, cfg);
+}
 }

@@ -149,6 +149,14 @@ static void p2p_teardown(b200sp_handle h) {
     if (h->nbr_stage[k]) cudaIpcCloseMemHandle(h->nbr_stage[k]);
     h->nbr_stage[k] = nullptr;
   }
+  for (int r = 0; r < P2P_MAX_WORLD; ++r) {
+    if (h->peer_gather[r] && h->peer_gather[r] != h->gather_stage) cudaIpcCloseMemHandle(h->peer_gather[r]);
+    h->peer_gather[r] = nullptr;
+  }
+  if (h->gather_stage) cudaFree(h->gather_stage);
+  h->gather_stage = nullptr;
+  h->gather_slice_cap = 0;
+  h->gather_epoch = 0;
   if (h->halo_stage) cudaFree(h->halo_stage);
   h->halo_stage = nullptr;
   if (h->mail) cudaFree(h->mail);
@@ -347,6 +355,177 @@ bool comm_fused_xchg_prepare(b200sp_handle h, void *window, i64 n, i64 halo_lo, 
   xc->wait_lo = xc->wait_hi = &xc->mine->xchg_go;  // raised locally when both planes are in the window
   xc->wait_epoch = xc->epoch;
   return true;
+}
+
+// ---- all-gather of x slices through peer memory ------------------------------------
+// copy with congruent misalignment: dst and src have the same address modulo 16
+__device__ __forceinline__ void copy_congruent(char *dst, const char *src, size_t bytes, size_t tid, size_t nth) {
+  size_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+  if (head > bytes) head = bytes;
+  for (size_t i = tid; i < head; i += nth) dst[i] = src[i];
+  const size_t n16 = (bytes - head) / 16;
+  const uint4 *s4 = reinterpret_cast<const uint4 *>(src + head);
+  uint4 *d4 = reinterpret_cast<uint4 *>(dst + head);
+  // 4 independent 16-byte loads in flight per thread: a peer read over NVLink takes microseconds
+  size_t i = tid;
+  for (; i + 3 * nth < n16; i += 4 * nth) {
+    const uint4 a = s4[i], b = s4[i + nth], c = s4[i + 2 * nth], d = s4[i + 3 * nth];
+    d4[i] = a;
+    d4[i + nth] = b;
+    d4[i + 2 * nth] = c;
+    d4[i + 3 * nth] = d;
+  }
+  for (; i < n16; i += nth) d4[i] = s4[i];
+  for (size_t j = head + n16 * 16 + tid; j < bytes; j += nth) dst[j] = src[j];
+}
+
+struct GatherArgs {
+  char *x_full;
+  char *stage_mine;
+  const char *stage_peer[P2P_MAX_WORLD];
+  Mailbox *mail[P2P_MAX_WORLD];
+  unsigned long long off[P2P_MAX_WORLD + 1];  // byte offsets of the slices in x_full
+  size_t par_off;                             // byte offset of this epoch's half of a staging buffer
+  unsigned int *ticket;
+  unsigned long long epoch;
+  int world, rank;
+};
+
+constexpr int GATHER_BLOCK = 256;
+
+// Grid: at most 2 CTAs per SM (co-resident: CTAs spin on flags raised by other GPUs).
+//   A  my slice -> my staging buffer (same misalignment as in x_full); the CTA that finishes last
+//      publishes gather_flag[rank] = epoch in every peer's mailbox;
+//   B  for each peer in rotated order: wait for its flag here, pull its slice into x_full.
+__global__ void __launch_bounds__(GATHER_BLOCK) allgather_pull_kernel(GatherArgs g) {
+  const size_t tid = (size_t)blockIdx.x * GATHER_BLOCK + threadIdx.x, nth = (size_t)gridDim.x * GATHER_BLOCK;
+  {
+    const size_t o = g.off[g.rank], b = g.off[g.rank + 1] - o;
+    copy_congruent(g.stage_mine + g.par_off + (o & 15), g.x_full + o, b, tid, nth);
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) is_last = (atomicAdd(g.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last && threadIdx.x < g.world && (int)threadIdx.x != g.rank) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&g.mail[threadIdx.x]->gather_flag[g.rank]), "l"(g.epoch)
+                 : "memory");
+  }
+  if (is_last && threadIdx.x == 0) *g.ticket = 0;
+  Mailbox *mine = g.mail[g.rank];
+  for (int k = 1; k < g.world; ++k) {
+    const int r = (g.rank + k) % g.world;
+    if (threadIdx.x == 0) {
+      unsigned long long v;
+      SpinGuard guard;
+      do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(&mine->gather_flag[r]) : "memory");
+      } while (v < g.epoch && !guard.expired(mine));
+    }
+    __syncthreads();
+    const size_t o = g.off[r], b = g.off[r + 1] - o;
+    copy_congruent(g.x_full + o, g.stage_peer[r] + g.par_off + (o & 15), b, tid, nth);
+  }
+}
+
+// (re)allocate and IPC-share the staging buffers so that a slice of `need` bytes fits; collective
+static b200sp_status gather_stage_ensure(b200sp_handle h, cudaStream_t st, size_t need) {
+  if (h->gather_stage && h->gather_slice_cap >= need) return B200SP_OK;
+  B200SP_CUDA(h, cudaStreamSynchronize(st));
+  for (int r = 0; r < P2P_MAX_WORLD; ++r) {
+    if (h->peer_gather[r] && h->peer_gather[r] != h->gather_stage) cudaIpcCloseMemHandle(h->peer_gather[r]);
+    h->peer_gather[r] = nullptr;
+  }
+  struct Info {
+    unsigned char handle[64];
+    int ok, pad;
+  } mine, all[P2P_MAX_WORLD];
+  memset(&mine, 0, sizeof(mine));
+  // every rank must have closed its mappings of the old buffers before anybody frees one
+  if (!all_ranks_ok(h, st, 1)) return set_error(h, B200SP_COMM_ERROR, "allgather: staging re-allocation handshake failed");
+  if (h->gather_stage) cudaFree(h->gather_stage);
+  h->gather_stage = nullptr;
+  const size_t cap = ((need + 16 + 255) & ~(size_t)255);
+  if (cudaMalloc(&h->gather_stage, 2 * cap) == cudaSuccess) {
+    cudaIpcMemHandle_t hd;
+    if (cudaIpcGetMemHandle(&hd, h->gather_stage) == cudaSuccess) {
+      memcpy(mine.handle, &hd, 64);
+      mine.ok = 1;
+    }
+  }
+  cudaGetLastError();
+  b200sp_status s = comm_allgather_host(h, st, &mine, sizeof(Info), all);
+  if (s != B200SP_OK) return s;
+  int ok = 1;
+  for (int r = 0; r < h->world; ++r) ok = ok && all[r].ok;
+  for (int r = 0; r < h->world && ok; ++r) {
+    if (r == h->rank) {
+      h->peer_gather[r] = h->gather_stage;
+      continue;
+    }
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, all[r].handle, 64);
+    if (cudaIpcOpenMemHandle(&h->peer_gather[r], hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      h->peer_gather[r] = nullptr;
+      ok = 0;
+      cudaGetLastError();
+    }
+  }
+  if (!all_ranks_ok(h, st, ok)) {
+    h->gather_slice_cap = 0;
+    return set_error(h, B200SP_COMM_ERROR, "allgather: mapping the peers' staging buffers failed on some rank");
+  }
+  h->gather_slice_cap = cap - 16;
+  return B200SP_OK;
+}
+
+b200sp_status comm_allgather_slices(b200sp_handle h, cudaStream_t st, void *x_full, const int64_t *slice_offsets,
+                                    size_t elem) {
+  if (h->world <= 1) return B200SP_OK;
+  B200SP_REQUIRE(h, x_full && slice_offsets, "allgather: null argument");
+  size_t max_slice = 0;
+  for (int r = 0; r < h->world; ++r) {
+    B200SP_REQUIRE(h, slice_offsets[r + 1] >= slice_offsets[r], "allgather: slice offsets must ascend");
+    const size_t b = (size_t)(slice_offsets[r + 1] - slice_offsets[r]) * elem;
+    max_slice = b > max_slice ? b : max_slice;
+  }
+  char *x = reinterpret_cast<char *>(x_full);
+  if (h->p2p_ok) {
+    b200sp_status s = gather_stage_ensure(h, st, max_slice);
+    if (s != B200SP_OK) return s;
+    GatherArgs g;
+    memset(&g, 0, sizeof(g));
+    g.x_full = x;
+    g.stage_mine = reinterpret_cast<char *>(h->gather_stage);
+    for (int r = 0; r < h->world; ++r) {
+      g.stage_peer[r] = reinterpret_cast<const char *>(h->peer_gather[r]);
+      g.mail[r] = reinterpret_cast<Mailbox *>(h->peer_mail[r]);
+      g.off[r] = (unsigned long long)slice_offsets[r] * elem;
+    }
+    g.off[h->world] = (unsigned long long)slice_offsets[h->world] * elem;
+    g.epoch = ++h->gather_epoch;
+    g.par_off = (size_t)(g.epoch & 1) * (h->gather_slice_cap + 16);
+    g.ticket = h->red_counters + 6;
+    g.world = h->world;
+    g.rank = h->rank;
+    allgather_pull_kernel<<<h->num_sms * 2, GATHER_BLOCK, 0, st>>>(g);
+    B200SP_LAUNCH_CHECK(h, "allgather_pull_kernel");
+    return B200SP_OK;
+  }
+  ncclComm_t comm = (ncclComm_t)h->nccl_comm;
+  const size_t mine_b = (size_t)(slice_offsets[h->rank + 1] - slice_offsets[h->rank]) * elem;
+  B200SP_NCCL(h, nccl().GroupStart());
+  for (int r = 0; r < h->world; ++r) {
+    if (r == h->rank) continue;
+    const size_t b = (size_t)(slice_offsets[r + 1] - slice_offsets[r]) * elem;
+    if (mine_b) B200SP_NCCL(h, nccl().Send(x + (size_t)slice_offsets[h->rank] * elem, mine_b, ncclChar, r, comm, st));
+    if (b) B200SP_NCCL(h, nccl().Recv(x + (size_t)slice_offsets[r] * elem, b, ncclChar, r, comm, st));
+  }
+  B200SP_NCCL(h, nccl().GroupEnd());
+  h->launches++;
+  return B200SP_OK;
 }
 
 P2PView comm_p2p_view(b200sp_handle h) {

@@ -34,6 +34,7 @@ struct Mailbox {
   unsigned long long xchg_flag[2];  // spmv_dist: epoch of the last staged plane from rank-1 / rank+1
   unsigned long long xchg_go;       // spmv_dist: local "both planes have landed" signal
   unsigned long long timeouts;      // spin loops that gave up (a peer never arrived): results are invalid
+  unsigned long long gather_flag[P2P_MAX_WORLD];  // spmv_dist_gather: epoch of rank r's last staged x slice
 };
 #ifdef __CUDACC__
 // every cross-GPU spin is bounded (~0.5 s of SM clocks): a peer that died must not hang this GPU
@@ -110,6 +111,15 @@ P2PView comm_p2p_view(b200sp_handle h);
 // P2P_STAGE_SIDE.  Same contract as comm_halo_exchange.
 b200sp_status comm_halo_exchange_auto(b200sp_handle h, cudaStream_t st, void *window, i64 n, i64 halo_lo,
                                       i64 halo_hi, size_t elem);
+// All-gather of a row-block partitioned vector (graph operators: every rank's rows read the
+// whole of x).  x_full holds `slice_offsets[world]` elements; this rank's slice
+// [slice_offsets[rank], slice_offsets[rank+1]) is valid on entry, all slices on return.
+// Peer-memory path: one kernel copies the own slice into an IPC-shared staging buffer,
+// publishes an epoch flag in every peer's mailbox, and pulls the other ranks' slices straight
+// from their staging buffers over NVLink (rotated peer order, staging double-buffered by
+// epoch parity).  Without CUDA IPC: grouped ncclSend / ncclRecv.  Collective.
+b200sp_status comm_allgather_slices(b200sp_handle h, cudaStream_t st, void *x_full, const int64_t *slice_offsets,
+                                    size_t elem);
 // agree on a fresh solve id (max over ranks + 1): epochs never repeat across solves
 b200sp_status comm_next_solve_id(b200sp_handle h, cudaStream_t st, unsigned long long *id);
 }  // namespace b200sp

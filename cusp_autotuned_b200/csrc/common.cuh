@@ -110,6 +110,12 @@ struct b200sp_context {
   void *halo_stage = nullptr;
   void *nbr_stage[2] = {nullptr, nullptr};
   unsigned long long xchg_epoch = 0;
+  // staging for the peer-memory all-gather of b200sp_spmv_dist_gather: 2 parities x gather_slice_cap
+  // bytes, IPC-exported; every peer's buffer mapped here
+  void *gather_stage = nullptr;
+  void *peer_gather[16] = {nullptr};
+  size_t gather_slice_cap = 0;
+  unsigned long long gather_epoch = 0;
 };
 
 enum { RED_MAX_PARTIALS = 1 << 16 };

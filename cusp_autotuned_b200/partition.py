@@ -56,3 +56,40 @@ def halo_plan(blk: RowBlock):
         hi = blk.halo_hi
         plan.append((blk.rank + 1, slice(lo + n - hi, lo + n), slice(lo + n, lo + n + hi)))
     return plan
+
+
+def row_block_offsets(num_rows: int, world: int):
+    """contiguous row blocks for operators without grid structure (graphs): world+1 offsets,
+    block r = [offsets[r], offsets[r+1]); sizes differ by at most one row and are multiples
+    of 32 rows where possible (16-byte aligned fp32 slices for the peer-memory all-gather)"""
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    units, rem = divmod(int(num_rows), 32)
+    base, extra = divmod(units, world)
+    offs = [0]
+    for r in range(world):
+        offs.append(offs[-1] + 32 * (base + (1 if r < extra else 0)))
+    offs[-1] += rem
+    return offs
+
+
+def coo_row_block(row_indices, offsets, rank: int):
+    """entry range [e0, e1) of a row-sorted COO matrix whose rows fall into block `rank`
+    (row_indices: any sorted sequence supporting searchsorted-style bisect)"""
+    import bisect
+    return bisect.bisect_left(row_indices, offsets[rank]), bisect.bisect_left(row_indices, offsets[rank + 1])
+
+
+def nnz_balanced_offsets(row_indices, num_rows: int, world: int, align: int = 32):
+    """row blocks with about nnz/world stored entries each (power-law graphs: equal row counts
+    would give the block holding the hub rows most of the matrix).  `row_indices` is the
+    row-sorted COO row array (anything indexable: list, numpy, torch); block boundaries are
+    rounded to a multiple of `align` rows and kept ascending."""
+    nnz = len(row_indices)
+    offs = [0]
+    for r in range(1, world):
+        cut = int(row_indices[(nnz * r) // world]) if nnz else 0
+        cut = ((cut + align // 2) // align) * align  # nearest multiple of `align`
+        offs.append(min(max(cut, offs[-1]), int(num_rows)))
+    offs.append(int(num_rows))
+    return offs

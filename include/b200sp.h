@@ -348,6 +348,17 @@ b200sp_status b200sp_spmv_dist(b200sp_handle h, b200sp_stream stream,
                                void *x_window, void *y_local,
                                const b200sp_cfg *cfg);
 
+/* Partitioned SpMV for operators whose rows read the whole of x (graphs): the rank's
+ * block of rows keeps GLOBAL column indices (num_cols = global size); x is partitioned like the
+ * rows, slice r = [slice_offsets[r], slice_offsets[r+1]) (host array of world_size+1 entries,
+ * slice_offsets[0] = 0, slice_offsets[world_size] = num_cols).  x_full has room for num_cols
+ * elements with this rank's slice in place; the call gathers the other slices (one kernel
+ * pulling them from the peers' IPC-shared staging buffers over NVLink, or grouped NCCL
+ * send/recv) and then runs the local product.  Every y entry is computed by exactly one rank. */
+b200sp_status b200sp_spmv_dist_gather(b200sp_handle h, b200sp_stream stream,
+                                      const b200sp_matrix *A_local, const int64_t *slice_offsets,
+                                      void *x_full, void *y_local, const b200sp_cfg *cfg);
+
 /* ---- autotuning (cusp::ktt::{multiply,tune,reset_tuning},
  *      cusp/ktt/detail/ktt.inl:83-142, cuda/ktt/multiply.h:56-153) ----------- */
 typedef enum {

@@ -114,3 +114,75 @@ def test_partitioned_spmv_and_cg_match_single_process(world):
     xo, it, conv, hist = O.cg(full, np.zeros(full["num_rows"]), np.ones(full["num_rows"]), 12, 0.0)
     assert np.allclose(parts[0][3], hist, rtol=1e-10)  # only the dot-product grouping differs
     assert np.allclose(xs, xo, rtol=1e-9, atol=1e-13)
+
+
+# ---------------------------------------------------------------------------
+# graph operators: contiguous row blocks, global column indices, x all-gathered
+# (the plan b200sp_spmv_dist_gather executes over NVLink peer memory / NCCL)
+# ---------------------------------------------------------------------------
+def test_row_block_offsets_properties():
+    from cusp_autotuned_b200.partition import row_block_offsets
+    for n in (0, 1, 31, 32, 33, 1000, 65531, 1 << 24):
+        for world in (1, 2, 3, 8):
+            offs = row_block_offsets(n, world)
+            assert len(offs) == world + 1 and offs[0] == 0 and offs[-1] == n
+            sizes = np.diff(offs)
+            assert (sizes >= 0).all()
+            assert all(o % 32 == 0 for o in offs[:-1])  # 16-byte aligned fp32 slices
+            if n >= 32 * world:
+                assert sizes.max() - sizes.min() <= 32 + 31
+
+
+def test_nnz_balanced_offsets_split_the_entries_evenly():
+    from cusp_autotuned_b200.partition import nnz_balanced_offsets
+    rng = np.random.default_rng(5)
+    n = 5000
+    deg = (rng.pareto(1.2, n) * 3).astype(np.int64) + (np.arange(n) % 400 == 0) * 3000 * (np.arange(n) < 2000)  # hubs early
+    rows = np.repeat(np.arange(n), deg)
+    for world in (1, 2, 4, 8):
+        offs = nnz_balanced_offsets(rows, n, world)
+        assert offs[0] == 0 and offs[-1] == n and all(a <= b for a, b in zip(offs, offs[1:]))
+        assert all(o % 32 == 0 for o in offs[:-1])
+        per = np.diff(np.searchsorted(rows, offs))
+        assert per.sum() == len(rows)
+        window = np.convolve(deg, np.ones(32, np.int64), mode="full").max()  # entries of any 32 consecutive rows
+        assert per.max() <= len(rows) / world + 2 * window
+    assert nnz_balanced_offsets([], 7, 3) == [0, 0, 0, 7]
+
+
+def _graph_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cusp_autotuned_b200.partition import coo_row_block, row_block_offsets
+        A = O.gallery_random(700, 700, 9000, np.float64, "coo")  # same matrix on every rank
+        offs = row_block_offsets(A["num_rows"], world)
+        e0, e1 = coo_row_block(A["row_indices"].tolist(), offs, rank)
+        loc = dict(format="coo", num_rows=offs[rank + 1] - offs[rank], num_cols=A["num_cols"], num_entries=e1 - e0,
+                   row_indices=(A["row_indices"][e0:e1] - offs[rank]).astype(np.int32),
+                   column_indices=A["column_indices"][e0:e1].copy(), values=A["values"][e0:e1].copy())
+        xg = np.random.default_rng(3).uniform(-1, 1, A["num_cols"])
+        # all-gather of the x slices (slices are ragged: all_gather on padded tensors)
+        m = max(np.diff(offs))
+        mine = torch.zeros(m, dtype=torch.float64)
+        mine[: offs[rank + 1] - offs[rank]] = torch.from_numpy(xg[offs[rank]:offs[rank + 1]])
+        parts = [torch.zeros(m, dtype=torch.float64) for _ in range(world)]
+        td.all_gather(parts, mine)
+        xf = np.concatenate([parts[r][: offs[r + 1] - offs[r]].numpy() for r in range(world)])
+        out[rank] = (xf, O.spmv(loc, xf))
+    finally:
+        td.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_graph_row_blocks_with_gathered_x_match_single_process(world):
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_graph_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    A = O.gallery_random(700, 700, 9000, np.float64, "coo")
+    xg = np.random.default_rng(3).uniform(-1, 1, A["num_cols"])
+    for r in range(world):
+        assert np.array_equal(out[r][0], xg)
+    y = np.concatenate([out[r][1] for r in range(world)])
+    assert np.array_equal(y, O.spmv(A, xg))  # rows are never split across ranks: same sums, same order

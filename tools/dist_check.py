@@ -121,6 +121,48 @@ def main():
         td.all_reduce(flags, op=td.ReduceOp.MIN)
         out["skew_stress_ok"] = int(flags.item())
         ok = ok and bool(out["skew_stress_ok"])
+    # graph operator (R-MAT): rows partitioned in contiguous blocks, global column indices, x gathered
+    # from all ranks (b200sp_spmv_dist_gather).  Integer-valued data: y must equal the single-GPU
+    # product of the whole matrix bit for bit; ranks take turns being late (staging parity).
+    if world > 1:
+        from cusp_autotuned_b200 import convert
+        from cusp_autotuned_b200.matrix import coo_matrix
+        from cusp_autotuned_b200.partition import row_block_offsets
+        scale = 16
+        C = convert.rmat(scale, 16, seed=7, dtype=torch.float32, values="ones")  # same stream on every GPU
+        n = C.num_rows
+        from cusp_autotuned_b200.partition import nnz_balanced_offsets
+        graph_ok = 1
+        # equal row counts, and nnz-balanced blocks cut at arbitrary rows (slices not 16-byte aligned)
+        for offs, tdt in [(o, t) for o in (row_block_offsets(n, world), nnz_balanced_offsets(C.row_indices, n, world, align=1))
+                          for t in (torch.float32, torch.float64)]:
+            bounds = torch.searchsorted(C.row_indices, torch.tensor(offs, dtype=torch.int32, device=dev))
+            e0, e1 = int(bounds[rank]), int(bounds[rank + 1])
+            nloc = offs[rank + 1] - offs[rank]
+            vals = C.values.to(tdt)
+            Cg = coo_matrix(n, n, C.row_indices, C.column_indices, vals)
+            loc = coo_matrix(nloc, n, (C.row_indices[e0:e1] - offs[rank]).contiguous(),
+                             C.column_indices[e0:e1].clone(), vals[e0:e1].clone())
+            mats = {"coo": loc, "csr": convert.coo_to_csr(loc)}
+            mats["hyb"] = convert.csr_to_hyb(mats["csr"])
+            for it in range(8):
+                xg = ((torch.arange(n, device=dev) * (it + 3)) % 17 - 8).to(tdt)
+                yref = torch.empty(n, dtype=tdt, device=dev)
+                h.spmv(Cg.descriptor(), xg, yref)
+                for fmt, M in mats.items():
+                    xf = torch.full((n,), float("nan"), dtype=tdt, device=dev)
+                    xf[offs[rank]:offs[rank + 1]] = xg[offs[rank]:offs[rank + 1]]
+                    y = torch.empty(nloc, dtype=tdt, device=dev)
+                    if (it + len(fmt)) % world == rank:
+                        torch.cuda._sleep(2_000_000)
+                    h.spmv_dist_gather(M.descriptor(), offs, xf, y)
+                    if not (torch.equal(xf, xg) and torch.equal(y, yref[offs[rank]:offs[rank + 1]])):
+                        graph_ok = 0
+        flags = torch.tensor([graph_ok], device=dev)
+        td.all_reduce(flags, op=td.ReduceOp.MIN)
+        out["graph_gather_ok"] = int(flags.item())
+        out["graph"] = {"matrix": f"R-MAT scale {scale} ef 16 (ones)", "nnz": int(C.num_entries), "offsets": offs}
+        ok = ok and bool(out["graph_gather_ok"])
     if world > 1:
         bad = torch.tensor([h.comm_timeouts()], dtype=torch.int64, device=dev)
         td.all_reduce(bad, op=td.ReduceOp.MAX)
