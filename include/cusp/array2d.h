@@ -107,6 +107,20 @@ class array2d {
     return values[detail::orient<Orientation>::index(i, j, pitch)];
   }
   T operator()(size_t i, size_t j) const { return values[detail::orient<Orientation>::index(i, j, pitch)]; }
+
+  // contiguous lines of the storage order as array1d views (cusp/array2d.h: row(i) of a row_major,
+  // column(j) of a column_major array; the strided direction is not provided here)
+  typedef typename values_array_type::view row_view;
+  typedef typename values_array_type::view column_view;
+  row_view row(size_t i) {
+    static_assert(std::is_same<Orientation, row_major>::value, "array2d::row(): contiguous only for row_major");
+    return values.subarray(i * pitch, num_cols);
+  }
+  column_view column(size_t j) {
+    static_assert(std::is_same<Orientation, column_major>::value,
+                  "array2d::column(): contiguous only for column_major");
+    return values.subarray(j * pitch, num_rows);
+  }
 };
 
 template <typename ArrayView, typename Orientation = row_major>

@@ -9,6 +9,7 @@
 #include <cusp/krylov/bicgstab.h>
 #include <cusp/krylov/cg.h>
 #include <cusp/krylov/cr.h>
+#include <cusp/krylov/gmres.h>
 #include <cusp/monitor.h>
 #include <cusp/multiply.h>
 #include <cusp/precond/diagonal.h>
@@ -113,3 +114,59 @@ void TestKrylovDeviceVsHost() {
   compare_device_and_host([](auto &A, auto &x, auto &b, auto &m) { cusp::krylov::bicgstab(A, x, b, m); });
 }
 TEST_DEVICE(TestKrylovDeviceVsHost)
+
+
+// testing/gmres.cu:39-62
+template <class MemorySpace>
+void TestGeneralizedMinRes() {
+  const size_t restart = 20;
+  cusp::csr_matrix<int, float, MemorySpace> A;
+  cusp::gallery::poisson5pt(A, 10, 10);
+  cusp::array1d<float, MemorySpace> x(A.num_rows, 0.0f), b(A.num_rows, 1.0f);
+  cusp::monitor<float> monitor(b, 20, 1e-4);
+  cusp::krylov::gmres(A, x, b, restart, monitor);
+  cusp::array1d<float, MemorySpace> residual(A.num_rows, 0.0f);
+  cusp::multiply(A, x, residual);
+  cusp::blas::axpby(residual, b, residual, -1.0f, 1.0f);
+  ASSERT_EQUAL(cusp::blas::nrm2(residual) < 1e-4 * cusp::blas::nrm2(b), true);
+}
+TEST_HOST_DEVICE(TestGeneralizedMinRes)
+
+// restarts (restart < iterations needed), fp64, non-symmetric operator, Jacobi preconditioner
+template <class MemorySpace>
+void TestGeneralizedMinResRestartedNonSymmetric() {
+  cusp::csr_matrix<int, double, cusp::host_memory> P;
+  cusp::gallery::poisson5pt(P, 12, 9);
+  for (size_t r = 0; r < P.num_rows; ++r)
+    for (int e = P.row_offsets[r]; e < P.row_offsets[r + 1]; ++e) {
+      if ((size_t)P.column_indices[e] == r + 1) P.values[e] = -1.5;  // convection-like skew, rows stay dominant
+      if ((size_t)P.column_indices[e] + 1 == r) P.values[e] = -0.5;
+      if ((size_t)P.column_indices[e] == r) P.values[e] = 4.0 + 0.01 * (double)(r % 7);
+    }
+  cusp::csr_matrix<int, double, MemorySpace> A(P);
+  cusp::array1d<double, MemorySpace> x(A.num_rows, 0.0), b(A.num_rows, 1.0);
+  cusp::monitor<double> monitor(b, 400, 1e-10);
+  cusp::precond::diagonal<double, MemorySpace> M(A);
+  cusp::krylov::gmres(A, x, b, 7, monitor, M);
+  ASSERT_TRUE(monitor.converged());
+  ASSERT_TRUE(monitor.iteration_count() > 7);  // restarted at least once
+  cusp::array1d<double, MemorySpace> residual(A.num_rows, 0.0);
+  cusp::multiply(A, x, residual);
+  cusp::blas::axpby(residual, b, residual, -1.0, 1.0);
+  ASSERT_TRUE(cusp::blas::nrm2(residual) < 1e-8 * cusp::blas::nrm2(b));
+}
+TEST_HOST_DEVICE(TestGeneralizedMinResRestartedNonSymmetric)
+
+// array2d::column / row views alias the storage
+void TestArray2dLines() {
+  cusp::array2d<float, cusp::host_memory, cusp::column_major> C(3, 2, 0.0f);
+  auto c1 = C.column(1);
+  c1[2] = 5.0f;
+  ASSERT_EQUAL(C(2, 1), 5.0f);
+  ASSERT_EQUAL(c1.size(), (size_t)3);
+  cusp::array2d<float, cusp::host_memory> Rm(2, 4, 0.0f);
+  auto r1 = Rm.row(1);
+  r1[3] = 7.0f;
+  ASSERT_EQUAL(Rm(1, 3), 7.0f);
+}
+TEST_HOST(TestArray2dLines)
