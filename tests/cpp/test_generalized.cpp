@@ -1,0 +1,80 @@
+// cusp::generalized_spmv — testing/generalized_spmv.cu:13-180 restated: z = y + A x with
+// (multiplies, plus) for {coo,csr,dia,ell,hyb} x {host_memory,device_memory}: the known-answer
+// 5x4 matrix, then poisson5pt / gallery::random matrices against cusp::multiply + y (exact:
+// integer-valued data).  On device_memory the call is cusp::blas::copy + b200sp_spmv(accumulate).
+#include <cusp/array2d.h>
+#include <cusp/coo_matrix.h>
+#include <cusp/csr_matrix.h>
+#include <cusp/dia_matrix.h>
+#include <cusp/ell_matrix.h>
+#include <cusp/gallery/poisson.h>
+#include <cusp/gallery/random.h>
+#include <cusp/hyb_matrix.h>
+#include <cusp/multiply.h>
+
+#include <vector>
+
+#include "check.h"
+
+template <typename TestMatrix>
+void GeneralizedSpMV() {
+  typedef typename TestMatrix::value_type ValueType;
+  typedef typename TestMatrix::memory_space MemorySpace;
+  const bool is_dia = std::is_same<typename TestMatrix::format, cusp::dia_format>::value;
+  {
+    cusp::array2d<ValueType, cusp::host_memory> A(5, 4, ValueType(0));
+    A(0, 0) = 13; A(0, 1) = 80; A(1, 1) = 27; A(2, 0) = 55; A(2, 2) = 24; A(2, 3) = 42;
+    A(3, 1) = 69; A(3, 3) = 83; A(4, 2) = 27;
+    TestMatrix test_matrix(A);
+    cusp::array1d<ValueType, MemorySpace> x(4), y(5), z(5, -1);
+    x[0] = 1; x[1] = 2; x[2] = 3; x[3] = 4;
+    y[0] = 10; y[1] = 20; y[2] = 30; y[3] = 40; y[4] = 50;
+    cusp::generalized_spmv(test_matrix, x, y, z, cusp::multiplies_function<ValueType>(),
+                           cusp::plus_function<ValueType>());
+    ASSERT_EQUAL((ValueType)z[0], (ValueType)183);
+    ASSERT_EQUAL((ValueType)z[1], (ValueType)74);
+    ASSERT_EQUAL((ValueType)z[2], (ValueType)325);
+    ASSERT_EQUAL((ValueType)z[3], (ValueType)510);
+    ASSERT_EQUAL((ValueType)z[4], (ValueType)131);
+  }
+  typedef cusp::coo_matrix<int, ValueType, cusp::host_memory> HostMatrix;
+  std::vector<HostMatrix> matrices;
+  const int grids[5][2] = {{5, 5}, {10, 10}, {117, 113}, {313, 444}, {876, 321}};
+  for (auto &g : grids) {
+    HostMatrix M;
+    cusp::gallery::poisson5pt(M, g[0], g[1]);
+    matrices.push_back(M);
+  }
+  if (!is_dia) {  // random patterns have no diagonal structure (the reference's DIA conversion refuses them)
+    const int rnd[5][3] = {{21, 23, 5}, {45, 37, 15}, {129, 127, 40}, {355, 378, 234}, {512, 512, 276}};
+    for (auto &r : rnd) {
+      HostMatrix M;
+      cusp::gallery::random(M, r[0], r[1], r[2]);
+      matrices.push_back(M);
+    }
+  }
+  for (size_t i = 0; i < matrices.size(); i++) {
+    TestMatrix M(matrices[i]);
+    cusp::array1d<ValueType, cusp::host_memory> xh(M.num_cols), yh(M.num_rows);
+    for (size_t k = 0; k < xh.size(); ++k) xh[k] = (ValueType)((k * 7 + i) % 2);          // random_integers<bool>
+    for (size_t k = 0; k < yh.size(); ++k) yh[k] = (ValueType)((int)((k * 13 + i) % 256) - 128);  // <char>
+    cusp::array1d<ValueType, MemorySpace> x(xh), y(yh), z(M.num_rows, ValueType(-7));
+    cusp::generalized_spmv(M, x, y, z, cusp::multiplies_function<ValueType>(), cusp::plus_function<ValueType>());
+    cusp::array1d<ValueType, MemorySpace> reference(M.num_rows, ValueType(0));
+    cusp::multiply(M, x, reference);
+    cusp::blas::axpy(y, reference, ValueType(1));
+    ASSERT_EQUAL(z, reference);
+  }
+}
+
+template <class MemorySpace>
+void TestGeneralizedSpMV() {
+  GeneralizedSpMV<cusp::coo_matrix<int, float, MemorySpace>>();
+  GeneralizedSpMV<cusp::csr_matrix<int, float, MemorySpace>>();
+  GeneralizedSpMV<cusp::dia_matrix<int, float, MemorySpace>>();
+  GeneralizedSpMV<cusp::ell_matrix<int, float, MemorySpace>>();
+  GeneralizedSpMV<cusp::hyb_matrix<int, float, MemorySpace>>();
+  GeneralizedSpMV<cusp::csr_matrix<int, double, MemorySpace>>();
+  GeneralizedSpMV<cusp::hyb_matrix<int, double, MemorySpace>>();
+}
+TEST_HOST_DEVICE(TestGeneralizedSpMV)
