@@ -9,10 +9,10 @@ runs in hand-written sm_100a kernels (csrc/).  No CPU fallback.
 from . import capi
 from .capi import B200spError, InvalidInput, Cfg, Handle
 from .matrix import (coo_matrix, csr_matrix, dia_matrix, ell_matrix, ellr_matrix, hyb_matrix,
-                     default_handle, multiply)
+                     default_handle, multiply, multiply_block)
 from . import blas, gallery, krylov, ktt
 from .krylov import monitor
 
 __all__ = ["capi", "B200spError", "InvalidInput", "Cfg", "Handle", "coo_matrix", "csr_matrix",
-           "dia_matrix", "ell_matrix", "ellr_matrix", "hyb_matrix", "default_handle", "multiply",
+           "dia_matrix", "ell_matrix", "ellr_matrix", "hyb_matrix", "default_handle", "multiply", "multiply_block",
            "blas", "gallery", "krylov", "ktt", "monitor"]

@@ -133,6 +133,7 @@ EXPORTED_SYMBOLS = (
     + [f"b200sp_{op}_{s}" for op in ("axpy", "axpby", "axpbypcz", "xmy", "copy", "fill", "scal", "dot", "nrm2", "asum", "nrmmax",
                                        "amax") for s in _SFX]
     + [f"b200sp_poisson_{f}_{s}" for f in ("dia", "ell", "csr") for s in _SFX]
+    + [f"b200sp_spmm_csr_{s}" for s in _SFX]
 )
 
 _lib: Optional[C.CDLL] = None
@@ -227,6 +228,13 @@ class Handle:
         f = getattr(self.lib, "b200sp_spmv_csr_" + _sfx(y.dtype))
         self.check(f(self._h, _stream(), C.c_int64(rows), C.c_int64(cols), C.c_int64(nnz), _ptr(Ap), _ptr(Aj),
                      _ptr(Ax), _ptr(x), _ptr(y), C.c_int(int(accumulate)), C.byref(cfg) if cfg else None))
+
+    def spmm_csr(self, rows, cols, nnz, Ap, Aj, Ax, k, X, ldx, Y, ldy, accumulate=False):
+        """Y[rows x k] = (accumulate ? Y : 0) + A X[cols x k], X / Y row-major (cusp::multiply(csr, array2d, array2d))"""
+        f = getattr(self.lib, "b200sp_spmm_csr_" + _sfx(Y.dtype))
+        self.check(f(self._h, _stream(), C.c_int64(rows), C.c_int64(cols), C.c_int64(nnz), _ptr(Ap), _ptr(Aj),
+                     _ptr(Ax), C.c_int64(k), _ptr(X), C.c_int64(ldx), _ptr(Y), C.c_int64(ldy),
+                     C.c_int(int(accumulate))))
 
     def spmv_ell(self, rows, cols, K, pitch, cidx, vals, x, y, accumulate=False, cfg: Optional[Cfg] = None):
         f = getattr(self.lib, "b200sp_spmv_ell_" + _sfx(y.dtype))

@@ -189,6 +189,24 @@ def multiply(A: _Base, x: torch.Tensor, y: torch.Tensor, *, accumulate: bool = F
     return y
 
 
+def multiply_block(A: "csr_matrix", X: torch.Tensor, Y: torch.Tensor, *, accumulate: bool = False,
+                   handle: Optional[capi.Handle] = None) -> torch.Tensor:
+    """cusp::multiply(A, X, Y) for a csr_matrix and row-major dense blocks X [num_cols x k],
+    Y [num_rows x k] (cusp/system/cuda/detail/multiply/csr_block_spmv.h:181-222)."""
+    if not isinstance(A, csr_matrix):
+        raise capi.InvalidInput(capi.ST_NOT_IMPLEMENTED, "multiply_block: csr_matrix only (like the reference)")
+    if X.dim() != 2 or Y.dim() != 2 or X.shape[0] != A.num_cols or Y.shape[0] != A.num_rows or X.shape[1] != Y.shape[1]:
+        raise capi.InvalidInput(capi.ST_INVALID_INPUT, "multiply_block: shapes do not match")
+    if not (X.is_cuda and Y.is_cuda):
+        raise capi.InvalidInput(capi.ST_INVALID_INPUT, "device_memory container given a host tensor")
+    if X.dtype != Y.dtype or X.dtype != A.values.dtype or X.stride(1) != 1 or Y.stride(1) != 1:
+        raise capi.InvalidInput(capi.ST_INVALID_INPUT, "multiply_block: one value type, row-major blocks")
+    h = handle or default_handle()
+    h.spmm_csr(A.num_rows, A.num_cols, A.num_entries, A.row_offsets, A.column_indices, A.values, X.shape[1],
+               X, X.stride(0), Y, Y.stride(0), accumulate=accumulate)
+    return Y
+
+
 def _descriptor_dtype(self):
     v = self.ell.values if isinstance(self, hyb_matrix) else self.values
     return v.dtype

@@ -298,6 +298,25 @@ b200sp_status b200sp_cg(b200sp_handle h, b200sp_stream stream,
                         const b200sp_cg_params *params, const b200sp_cfg *spmv_cfg,
                         b200sp_cg_result *result, double *residuals_host);
 
+/* ---- CSR x dense block ("block SpMV", cusp::multiply(csr_matrix, array2d, array2d)) ----------
+ * Y[num_rows x block_cols] = (accumulate ? Y : 0) + A * X[num_cols x block_cols]; X and Y are
+ * row-major with leading dimensions ldx, ldy (elements).  Replaces BlockSpmvKernel /
+ * __spmv_csr_block (cusp/system/cuda/detail/multiply/csr_block_spmv.h:36-222); per (row, column)
+ * the entries are added in storage order like the host loop
+ * (cusp/system/detail/sequential/multiply/csr_block_spmv.h:52-77), so results are bit-identical
+ * to it (a single contiguous column, block_cols == ldx == ldy == 1, is handed to b200sp_spmv_csr and
+ * follows its parity rule).  Any block width (the reference's kernel handles at most 32 columns). */
+b200sp_status b200sp_spmm_csr_f32(b200sp_handle h, b200sp_stream stream, int64_t num_rows,
+                                  int64_t num_cols, int64_t num_entries,
+                                  const int32_t *row_offsets, const int32_t *column_indices,
+                                  const float *values, int64_t block_cols, const float *X,
+                                  int64_t ldx, float *Y, int64_t ldy, int accumulate);
+b200sp_status b200sp_spmm_csr_f64(b200sp_handle h, b200sp_stream stream, int64_t num_rows,
+                                  int64_t num_cols, int64_t num_entries,
+                                  const int32_t *row_offsets, const int32_t *column_indices,
+                                  const double *values, int64_t block_cols, const double *X,
+                                  int64_t ldx, double *Y, int64_t ldy, int accumulate);
+
 /* ---- multi-GPU: row-block partitioned operator ---------------------------
  * One process per GPU.  Each rank owns a contiguous block of rows of A and the
  * matching slices of x, b.  Column j of the global matrix is owned by the rank

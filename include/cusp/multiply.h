@@ -20,6 +20,7 @@
 //     cusp::not_implemented_exception — there is no silent fallback.
 #pragma once
 #include <algorithm>
+#include <vector>
 
 #include "array1d.h"
 #include "array2d.h"
@@ -144,6 +145,69 @@ void multiply_in(device_memory, const M &A, const V1 &x, V2 &y, F0 initialize, F
   device_spmv(A, x, y, acc, allow_dynamic_tuning, std::integral_constant<bool, abi_matrix<M>::value>());
 }
 
+// ---------------------------------------------------------------------------
+// CSR x dense block: C = (init C) + A B for array2d B, C
+// (host: sequential/multiply/csr_block_spmv.h:52-77; device: cuda/detail/multiply/csr_block_spmv.h:181-222
+//  -> b200sp_spmm_csr_<t>).  Like the reference, only csr_matrix takes dense right-hand sides.
+// ---------------------------------------------------------------------------
+template <typename V>
+struct is_array2d : std::is_same<typename V::format, array2d_format> {};
+
+inline b200sp_status spmm_(int64_t r, int64_t c, int64_t n, const int *Ap, const int *Aj, const float *Ax, int64_t k,
+                           const float *X, int64_t ldx, float *Y, int64_t ldy, int acc) {
+  return b200sp_spmm_csr_f32(engine(), current_stream(), r, c, n, Ap, Aj, Ax, k, X, ldx, Y, ldy, acc);
+}
+inline b200sp_status spmm_(int64_t r, int64_t c, int64_t n, const int *Ap, const int *Aj, const double *Ax, int64_t k,
+                           const double *X, int64_t ldx, double *Y, int64_t ldy, int acc) {
+  return b200sp_spmm_csr_f64(engine(), current_stream(), r, c, n, Ap, Aj, Ax, k, X, ldx, Y, ldy, acc);
+}
+
+template <typename M, typename B, typename C, typename F0, typename F1, typename F2>
+void block_multiply_in(host_memory, const M &A, const B &X, C &Y, F0 initialize, F1 combine, F2 reduce) {
+  typedef typename C::value_type T;
+  std::vector<T> acc(X.num_cols);
+  for (size_t i = 0; i < A.num_rows; ++i) {
+    for (size_t k = 0; k < X.num_cols; ++k) acc[k] = initialize((T)Y(i, k));
+    const size_t lo = (size_t)A.row_offsets[i], hi = (size_t)A.row_offsets[i + 1];
+    for (size_t jj = lo; jj < hi; ++jj) {
+      const size_t j = (size_t)A.column_indices[jj];
+      const T a = (T)A.values[jj];
+      for (size_t k = 0; k < X.num_cols; ++k) acc[k] = reduce(acc[k], combine(a, (T)X(j, k)));
+    }
+    for (size_t k = 0; k < X.num_cols; ++k) Y(i, k) = acc[k];
+  }
+}
+template <typename M, typename B, typename C, typename F0, typename F1, typename F2>
+void block_multiply_in(device_memory, const M &A, const B &X, C &Y, F0 initialize, F1, F2) {
+  typedef typename M::value_type T;
+  const int acc = init_kind<F0>::of(initialize);
+  constexpr bool abi = std::is_same<typename M::index_type, int>::value &&
+                       (std::is_same<T, float>::value || std::is_same<T, double>::value) &&
+                       std::is_same<typename B::value_type, T>::value && std::is_same<typename C::value_type, T>::value &&
+                       std::is_same<typename B::orientation, row_major>::value &&
+                       std::is_same<typename C::orientation, row_major>::value;
+  if (acc < 0 || !is_multiplies<F1>::value || !is_plus<F2>::value || !abi)
+    throw cusp::not_implemented_exception(
+        "cusp::multiply(csr, array2d, array2d) on device_memory: int32 indices, one float/double value type, row-major "
+        "blocks and (constant_functor(0) | identity, multiplies, plus)");
+  if constexpr (abi)
+    check(spmm_((int64_t)A.num_rows, (int64_t)A.num_cols, (int64_t)A.num_entries, raw_ptr(A.row_offsets),
+                raw_ptr(A.column_indices), raw_ptr(A.values), (int64_t)X.num_cols, raw_ptr(X.values), (int64_t)X.pitch,
+                raw_ptr(Y.values), (int64_t)Y.pitch, acc));
+}
+template <typename M, typename B, typename C, typename F0, typename F1, typename F2>
+void block_multiply(const M &A, const B &X, C &Y, F0 initialize, F1 combine, F2 reduce) {
+  static_assert(std::is_same<typename M::memory_space, typename B::memory_space>::value &&
+                    std::is_same<typename M::memory_space, typename C::memory_space>::value,
+                "cusp::multiply: A, B and C must live in the same memory space");
+  if (!std::is_same<typename M::format, csr_format>::value)
+    throw cusp::not_implemented_exception("cusp::multiply(sparse, array2d, array2d): csr_matrix only");
+  if (A.num_cols != X.num_rows || A.num_rows != Y.num_rows || X.num_cols != Y.num_cols)
+    throw cusp::invalid_input_exception("cusp::multiply: matrix and block dimensions do not match");
+  if constexpr (std::is_same<typename M::format, csr_format>::value)
+    block_multiply_in(typename M::memory_space(), A, X, Y, initialize, combine, reduce);
+}
+
 }  // namespace detail
 
 // ---- 7-argument form (cusp/multiply.h:163-195) ------------------------------
@@ -152,11 +216,15 @@ template <typename P, typename LinearOperator, typename MatrixOrVector1, typenam
 void multiply(const execution_policy<P> &, const LinearOperator &A, const MatrixOrVector1 &B, MatrixOrVector2 &&C,
               UnaryFunction initialize, BinaryFunction1 combine, BinaryFunction2 reduce) {
   typedef typename std::decay<MatrixOrVector2>::type V2;
-  static_assert(std::is_same<typename LinearOperator::memory_space, typename MatrixOrVector1::memory_space>::value &&
-                    std::is_same<typename LinearOperator::memory_space, typename V2::memory_space>::value,
-                "cusp::multiply: A, x and y must live in the same memory space");
-  detail::check_shapes(A, B, C);
-  detail::multiply_in(typename LinearOperator::memory_space(), A, B, C, initialize, combine, reduce, false);
+  if constexpr (detail::is_array2d<MatrixOrVector1>::value && std::is_base_of<sparse_format, typename LinearOperator::format>::value) {
+    detail::block_multiply(A, B, C, initialize, combine, reduce);
+  } else {
+    static_assert(std::is_same<typename LinearOperator::memory_space, typename MatrixOrVector1::memory_space>::value &&
+                      std::is_same<typename LinearOperator::memory_space, typename V2::memory_space>::value,
+                  "cusp::multiply: A, x and y must live in the same memory space");
+    detail::check_shapes(A, B, C);
+    detail::multiply_in(typename LinearOperator::memory_space(), A, B, C, initialize, combine, reduce, false);
+  }
 }
 template <typename LinearOperator, typename MatrixOrVector1, typename MatrixOrVector2, typename UnaryFunction,
           typename BinaryFunction1, typename BinaryFunction2>
@@ -176,12 +244,17 @@ void multiply3(const LinearOperator &A, const V1 &x, V2 &y, unknown_format) {
 template <typename LinearOperator, typename V1, typename V2>
 void multiply3(const LinearOperator &A, const V1 &x, V2 &y, known_format) {
   typedef typename V2::value_type T;
+  if constexpr (is_array2d<V1>::value && std::is_base_of<sparse_format, typename LinearOperator::format>::value) {
+    block_multiply(A, x, y, constant_functor<T>(T(0)), multiplies_function<T>(), plus_function<T>());
+    return;
+  } else {
   static_assert(std::is_same<typename LinearOperator::memory_space, typename V1::memory_space>::value &&
                     std::is_same<typename LinearOperator::memory_space, typename V2::memory_space>::value,
                 "cusp::multiply: A, x and y must live in the same memory space");
   check_shapes(A, x, y);
   multiply_in(typename LinearOperator::memory_space(), A, x, y, constant_functor<T>(T(0)), multiplies_function<T>(),
               plus_function<T>(), true);
+  }
 }
 }  // namespace detail
 

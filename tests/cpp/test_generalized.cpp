@@ -78,3 +78,43 @@ void TestGeneralizedSpMV() {
   GeneralizedSpMV<cusp::hyb_matrix<int, double, MemorySpace>>();
 }
 TEST_HOST_DEVICE(TestGeneralizedSpMV)
+
+// cusp::multiply(csr_matrix, array2d, array2d): CSR x dense block
+// (cuda/detail/multiply/csr_block_spmv.h:181-222, sequential/multiply/csr_block_spmv.h:52-77).
+// Column j of the result must equal cusp::multiply(A, column j) exactly (same order of additions).
+template <class MemorySpace>
+void TestCsrBlockMultiply() {
+  cusp::csr_matrix<int, double, cusp::host_memory> Ah;
+  cusp::gallery::poisson5pt(Ah, 23, 17);
+  for (size_t n = 0; n < Ah.num_entries; ++n) Ah.values[n] = (double)Ah.values[n] * (0.5 + 0.001 * (double)(n % 97));
+  cusp::csr_matrix<int, double, MemorySpace> A(Ah);
+  for (size_t k : {1u, 2u, 3u, 5u, 8u, 16u, 20u, 32u, 40u}) {
+    cusp::array2d<double, cusp::host_memory> Xh(A.num_cols, k), Y0(A.num_rows, k, 3.0);
+    for (size_t i = 0; i < A.num_cols; ++i)
+      for (size_t j = 0; j < k; ++j) Xh(i, j) = 0.125 * (double)((i * 7 + j * 3) % 19) - 1.0;
+    cusp::array2d<double, MemorySpace> X(Xh), Y(Y0);
+    cusp::multiply(A, X, Y);
+    cusp::array2d<double, cusp::host_memory> Yh(Y);
+    for (size_t j = 0; j < k; ++j) {
+      cusp::array1d<double, cusp::host_memory> xj(A.num_cols), yj(A.num_rows);
+      for (size_t i = 0; i < A.num_cols; ++i) xj[i] = Xh(i, j);
+      cusp::multiply(Ah, xj, yj);
+      for (size_t i = 0; i < A.num_rows; ++i) ASSERT_EQUAL((double)Yh(i, j), (double)yj[i]);
+    }
+    // y += A x  (initialize = identity)
+    cusp::array2d<double, MemorySpace> Z(Y0);
+    cusp::multiply(A, X, Z, cusp::identity_function<double>(), cusp::multiplies_function<double>(),
+                   cusp::plus_function<double>());
+    cusp::array2d<double, cusp::host_memory> Zh(Z);
+    cusp::array2d<double, cusp::host_memory> Wh(Y0);
+    cusp::multiply(Ah, Xh, Wh, cusp::identity_function<double>(), cusp::multiplies_function<double>(),
+                   cusp::plus_function<double>());
+    ASSERT_EQUAL(Zh == Wh, true);
+  }
+  cusp::array2d<double, MemorySpace> Xbad(A.num_cols + 1, 2), Ybad(A.num_rows, 2);
+  ASSERT_THROWS(cusp::multiply(A, Xbad, Ybad), cusp::invalid_input_exception);
+  cusp::coo_matrix<int, double, MemorySpace> C(Ah);
+  cusp::array2d<double, MemorySpace> X2(A.num_cols, 2), Y2(A.num_rows, 2);
+  ASSERT_THROWS(cusp::multiply(C, X2, Y2), cusp::not_implemented_exception);
+}
+TEST_HOST_DEVICE(TestCsrBlockMultiply)

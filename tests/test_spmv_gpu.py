@@ -401,3 +401,56 @@ def test_native_library_is_the_one_running(handle):
     x = torch.ones(1000, dtype=torch.float32, device="cuda")
     handle.axpy(2.0, x, x.clone())
     assert handle.launch_count == before + 1
+
+
+# ---------------------------------------------------------------------------
+# CSR x dense block (cusp::multiply(csr_matrix, array2d, array2d), csr_block_spmv.h)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("ndt,tdt", DTYPES)
+def test_csr_block_multiply_bit_exact(ndt, tdt, dev):
+    """per (row, column) the entries are added in storage order like the host loop
+    (sequential/multiply/csr_block_spmv.h:52-77): column j of Y == the sequential SpMV with
+    column j of X, bit for bit, for every block width (sub-warp widths 1..32, chunks beyond 32),
+    padded leading dimensions, ragged / empty / hub rows, accumulate"""
+    rng = np.random.default_rng(21)
+    mats = {"p7": O.poisson(7, (11, 9, 7), ndt, "csr"), "rand": O.convert(O.gallery_random(700, 500, 9000, ndt, "coo"), "csr")}
+    hub = O.gallery_random(300, 300, 2500, ndt, "coo")
+    hub_rows = np.concatenate([hub["row_indices"], np.full(5000, 150, np.int32)])
+    order = np.argsort(hub_rows, kind="stable")
+    hubm = dict(format="coo", num_rows=300, num_cols=300, num_entries=len(hub_rows), row_indices=hub_rows[order],
+                column_indices=np.concatenate([hub["column_indices"], rng.integers(0, 300, 5000).astype(np.int32)])[order],
+                values=np.ones(len(hub_rows), ndt))
+    mats["hub"] = O.convert(hubm, "csr")
+    for name, A in mats.items():
+        A = dict(A)
+        A["values"] = (A["values"] * rng.uniform(0.5, 1.5, A["num_entries"])).astype(ndt)
+        Ad = upload("csr", A, dev)
+        for k in (1, 2, 3, 4, 7, 8, 16, 31, 32, 33, 70):
+            pad = 0 if k % 2 else 3
+            Xh = rng.uniform(-1, 1, (A["num_cols"], k + pad)).astype(ndt)
+            Y0 = rng.uniform(-1, 1, (A["num_rows"], k + pad)).astype(ndt)
+            X = tdev(Xh, dev)[:, :k]
+            for acc in (False, True):
+                Yfull = tdev(Y0, dev)
+                Y = Yfull[:, :k]
+                cusp.multiply_block(Ad, X, Y, accumulate=acc)
+                got = Y.cpu().numpy()
+                assert np.array_equal(Yfull[:, k:].cpu().numpy(), Y0[:, k:])  # padding columns untouched
+                for j in range(k):
+                    want = O.spmv(A, np.ascontiguousarray(Xh[:, j]), np.ascontiguousarray(Y0[:, j]) if acc else None,
+                                  accumulate=acc)
+                    if k == 1 and pad == 0:
+                        # one contiguous column is handed to the SpMV kernels (csr_block_spmv.h:198-201), whose
+                        # row-split variants regroup the sums: tolerance bar against sum_j |a_ij x_j|
+                        scale = O.spmv(abs_matrix(A), np.abs(Xh[:, j])) + (np.abs(Y0[:, j]) if acc else 0)
+                        assert scaled_err(got[:, j], want, scale) <= TOL[np.dtype(ndt)], (name, k, j, acc)
+                    else:
+                        assert np.array_equal(got[:, j], want), (name, k, j, acc)
+    # degenerate shapes
+    e = torch.zeros(0, dtype=tdt, device=dev)
+    A0 = cusp.csr_matrix(4, 5, torch.zeros(5, dtype=torch.int32, device=dev), torch.zeros(0, dtype=torch.int32, device=dev), e)
+    Y = torch.full((4, 3), 7, dtype=tdt, device=dev)
+    cusp.multiply_block(A0, torch.ones(5, 3, dtype=tdt, device=dev), Y)
+    assert torch.equal(Y, torch.zeros_like(Y))
+    with pytest.raises(capi.InvalidInput):
+        cusp.multiply_block(A0, torch.ones(4, 3, dtype=tdt, device=dev), Y)

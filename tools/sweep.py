@@ -150,6 +150,22 @@ def main():
         sweep(f"csr rmat s{scale}", A, x, out=out)
         H = convert.csr_to_hyb(A)
         sweep(f"hyb rmat s{scale} (K={H.ell.num_cols_per_row})", H, x, space=[], out=out)
+    elif what == "spmm":  # CSR x dense block (cusp::multiply(csr, array2d, array2d)), poisson7pt 256^3
+        n = int(os.environ.get("SWEEP_N", "256"))
+        for dtype in (torch.float32, torch.float64):
+            A = gallery.poisson7pt(n, n, n, fmt="csr", dtype=dtype)
+            es = torch.empty(0, dtype=dtype).element_size()
+            for k in (1, 2, 4, 8, 16, 32):
+                X = torch.rand(A.num_cols, k, dtype=dtype, device=dev) + 0.5
+                Y = torch.empty(A.num_rows, k, dtype=dtype, device=dev)
+                ms = timeit(lambda: cusp.multiply_block(A, X, Y))
+                B = (A.num_rows + 1) * 4 + A.num_entries * (4 + es) + (A.num_cols + A.num_rows) * k * es
+                rec = dict(label=f"spmm csr poisson7pt {n}^3 {dtype} k={k}", ms=ms, gbs=B / ms / 1e6, bytes=B,
+                           gflops=2.0 * A.num_entries * k / ms / 1e6)
+                out.append(rec)
+                print(f"## {rec['label']}: bytes={B}  {ms:.4f} ms  {rec['gbs']:.0f} GB/s  {rec['gflops']:.0f} GFLOP/s", flush=True)
+                del X, Y
+            del A
     elif what == "random":
         rows = 1 << 20
         for k in (4, 8, 16, 32, 64, 128, 256):
