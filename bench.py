@@ -194,7 +194,7 @@ def time_launches(fn, steps, warmup, sync):
     return e0.elapsed_time(e1) / steps  # ms per step
 
 
-def bench_format(h, A, tdt, steps, warmup, peak, cfg=None, label=None):
+def bench_format(h, A, tdt, steps, warmup, peak, cfg=None, label=None, graph=False):
     import torch
     es = 4 if tdt == torch.float32 else 8
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -204,8 +204,33 @@ def bench_format(h, A, tdt, steps, warmup, peak, cfg=None, label=None):
     ms = time_launches(lambda: h.spmv(d, x, y, cfg=cfg), steps, warmup, torch.cuda.synchronize)
     B = compulsory_bytes(A, es)
     nnz = A.num_entries
-    return {"label": label, "rows": A.num_rows, "nnz": nnz, "ms": ms, "gflops": 2.0 * nnz / ms / 1e6,
-            "bytes": B, "gbs": B / ms / 1e6, "frac": B / ms / 1e6 / peak, "frac_of_8TBs": B / ms / 1e6 / 8000.0}
+    out = {"label": label, "rows": A.num_rows, "nnz": nnz, "ms": ms, "gflops": 2.0 * nnz / ms / 1e6,
+           "bytes": B, "gbs": B / ms / 1e6, "frac": B / ms / 1e6 / peak, "frac_of_8TBs": B / ms / 1e6 / 8000.0}
+    if graph:
+        # launch-bound size: one python -> ctypes -> cudaLaunch round trip costs more than the kernel.
+        # The same `steps` launches captured once in a CUDA graph and replayed (what a solver loop does)
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            h.spmv(d, x, y, cfg=cfg)
+            with torch.cuda.graph(g, stream=side):
+                for _ in range(steps):
+                    h.spmv(d, x, y, cfg=cfg)
+        torch.cuda.current_stream().wait_stream(side)
+        g.replay()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        gms = e0.elapsed_time(e1) / steps
+        out.update({"ms_cuda_graph": gms, "gbs_cuda_graph": B / gms / 1e6, "frac_cuda_graph": B / gms / 1e6 / peak,
+                    "note": "ms = one host call per launch (host-bound at this size); ms_cuda_graph = the same "
+                            f"{steps} launches replayed from one CUDA graph"})
+    return out
 
 
 def main():
@@ -351,7 +376,7 @@ def main():
                     del M
             M = gallery.poisson("csr", 5, (512, 512), dtype=torch.float64)
             formats["csr_f64_poisson5pt_512"] = bench_format(h, M, torch.float64, 200, 20, peak,
-                                                             label="CSR fp64 poisson5pt 512^2 (L2-resident)")
+                                                             label="CSR fp64 poisson5pt 512^2 (L2-resident)", graph=True)
             del M
             try:
                 coo = convert.rmat(args.rmat_scale, 16, seed=42, dtype=torch.float32)

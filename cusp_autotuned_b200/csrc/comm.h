@@ -37,7 +37,7 @@ struct Mailbox {
   unsigned long long gather_flag[P2P_MAX_WORLD];  // spmv_dist_gather: epoch of rank r's last staged x slice
 };
 #ifdef __CUDACC__
-// every cross-GPU spin is bounded (~0.5 s of SM clocks): a peer that died must not hang this GPU
+// every cross-GPU spin is bounded (~4 s of SM clocks): a peer that died must not hang this GPU
 struct SpinGuard {
   long long t0;
   __device__ SpinGuard() {
@@ -49,10 +49,10 @@ struct SpinGuard {
   }
   __device__ bool expired(Mailbox *mine) {
 #ifdef __CUDA_ARCH__
-    // ~0.5 s of SM clocks for the first failure; once one wait has failed the job is broken
+    // ~4 s of SM clocks (ranks of a real job arrive seconds apart after host-side work) for the first failure; once one wait has failed the job is broken
     // anyway (b200sp_comm_timeouts() != 0), so later waits give up at once instead of
     // stretching a dead run by half a second per kernel
-    if (clock64() - t0 < (1ll << 30) && *reinterpret_cast<volatile unsigned long long *>(&mine->timeouts) == 0)
+    if (clock64() - t0 < (1ll << 33) && *reinterpret_cast<volatile unsigned long long *>(&mine->timeouts) == 0)
       return false;
     atomicAdd(&mine->timeouts, 1ull);
 #endif

@@ -342,7 +342,7 @@ b200sp_status b200sp_comm_destroy(b200sp_handle h);
  * environment variable B200SP_DISABLE_P2P=1). */
 int b200sp_comm_p2p_enabled(b200sp_handle h);
 /* Number of cross-GPU waits of the peer-memory path that gave up (a peer never published
- * its data within ~0.5 s).  Non-zero means results of `_dist` calls since b200sp_comm_init
+ * its data within ~4 s).  Non-zero means results of `_dist` calls since b200sp_comm_init
  * are invalid; b200sp_cg_dist checks it itself and returns B200SP_COMM_ERROR.  Synchronises
  * `stream`.  Always 0 on the NCCL path. */
 int64_t b200sp_comm_timeouts(b200sp_handle h, b200sp_stream stream);

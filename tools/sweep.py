@@ -33,15 +33,18 @@ def timeit(fn):
     fn()
     torch.cuda.synchronize()
     ts = []
+    inner = int(os.environ.get("SWEEP_WARM_LAUNCHES", "0"))  # > 0: L2-resident timing, mean of back-to-back launches
     for _ in range(REPS):
-        flush.zero_()
+        if not inner:
+            flush.zero_()
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        for _ in range(max(1, inner)):
+            fn()
         e1.record()
         e1.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        ts.append(e0.elapsed_time(e1) / max(1, inner))
     ts.sort()
     return ts[len(ts) // 2]
 
