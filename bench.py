@@ -433,13 +433,17 @@ def main():
         if world > 1:
             try:
                 from cusp_autotuned_b200.matrix import coo_matrix
-                from cusp_autotuned_b200.partition import nnz_balanced_offsets
+                from cusp_autotuned_b200.partition import nnz_balanced_offsets, row_block_offsets
                 Cg = convert.rmat(args.rmat_scale, 16, seed=42, dtype=torch.float32)  # same graph on every GPU
                 n = Cg.num_rows
                 offs = nnz_balanced_offsets(Cg.row_indices, n, world)
                 bounds = torch.searchsorted(Cg.row_indices, torch.tensor(offs, dtype=torch.int32, device=dev))
                 g0, g1 = int(bounds[rank]), int(bounds[rank + 1])
                 nloc = offs[rank + 1] - offs[rank]
+                # x in equal slices, independent of the row blocks: with x partitioned like the nnz-balanced rows
+                # the rank owning the long tail of short rows owns 43 % of x and has to serve it to 7 peers
+                # (0.26 ms of NVLink egress at 8 GPUs); equal slices cost every rank the same 7/8 of x / 8
+                xoffs = row_block_offsets(n, world)
                 loc = coo_matrix(nloc, n, (Cg.row_indices[g0:g1] - offs[rank]).contiguous(),
                                  Cg.column_indices[g0:g1].clone(), Cg.values[g0:g1].clone())
                 nnz_graph = Cg.num_entries
@@ -450,22 +454,23 @@ def main():
                 gd = loc.descriptor()
                 gsteps = max(10, min(args.steps, 50))
                 for _ in range(3):
-                    h.spmv_dist_gather(gd, offs, xf, yl)
+                    h.spmv_dist_gather(gd, xoffs, xf, yl)
                 barrier()
                 g_e0 = torch.cuda.Event(enable_timing=True)
                 g_e1 = torch.cuda.Event(enable_timing=True)
                 g_e0.record()
                 for _ in range(gsteps):
-                    h.spmv_dist_gather(gd, offs, xf, yl)
+                    h.spmv_dist_gather(gd, xoffs, xf, yl)
                 g_e1.record()
                 barrier()
                 g_ms = max_over_ranks(g_e0.elapsed_time(g_e1) / gsteps)
                 nnz_max = max_over_ranks(float(loc.num_entries))
-                graph = {"workload": f"COO fp32 R-MAT scale {args.rmat_scale} ef 16, nnz-balanced row blocks over {world} GPUs, "
+                graph = {"workload": f"COO fp32 R-MAT scale {args.rmat_scale} ef 16, nnz-balanced row blocks over {world} GPUs, x in equal slices, "
                                      "x all-gathered every step (b200sp_spmv_dist_gather)",
                          "scaling": "strong", "ms_per_step": g_ms, "gflops": 2.0 * nnz_graph / g_ms / 1e6,
                          "nnz_total": int(nnz_graph), "nnz_max_per_gpu": int(nnz_max),
-                         "gathered_bytes_per_gpu": int((n - nloc) * 4), "row_offsets": offs,
+                         "gathered_bytes_per_gpu": int((n - (xoffs[rank + 1] - xoffs[rank])) * 4), "row_offsets": offs,
+                         "x_slice_offsets": xoffs,
                          "comm": "nvlink-p2p pull from IPC staging" if h.comm_p2p_enabled() else "nccl send/recv"}
                 del loc, xf, yl
                 torch.cuda.empty_cache()

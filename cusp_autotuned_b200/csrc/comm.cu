@@ -382,7 +382,7 @@ __device__ __forceinline__ void copy_congruent(char *dst, const char *src, size_
 struct GatherArgs {
   char *x_full;
   char *stage_mine;
-  const char *stage_peer[P2P_MAX_WORLD];
+  char *stage_peer[P2P_MAX_WORLD];
   Mailbox *mail[P2P_MAX_WORLD];
   unsigned long long off[P2P_MAX_WORLD + 1];  // byte offsets of the slices in x_full
   size_t par_off;                             // byte offset of this epoch's half of a staging buffer
@@ -427,6 +427,51 @@ __global__ void __launch_bounds__(GATHER_BLOCK) allgather_pull_kernel(GatherArgs
     __syncthreads();
     const size_t o = g.off[r], b = g.off[r + 1] - o;
     copy_congruent(g.x_full + o, g.stage_peer[r] + g.par_off + (o & 15), b, tid, nth);
+  }
+}
+
+// Push variant (default): NVLink stores are posted, loads pay a round trip per request, so the
+// slices travel as stores.  Every staging buffer mirrors the whole of x (same byte offsets).
+//   A  my slice -> every peer's staging buffer, rotated peer order; the CTA that finishes last
+//      publishes gather_flag[rank] = epoch in every peer's mailbox;
+//   B  for each peer: wait for its flag here, copy its slice from MY staging buffer into x_full
+//      (local copy).
+// Reuse of a staging half two epochs later is safe: to get there a rank has passed B of the epoch in
+// between, i.e. has seen every peer's flag of that epoch, which a peer raises only after its
+// previous kernel (and with it its copy-out of the older data) has completed.
+__global__ void __launch_bounds__(GATHER_BLOCK) allgather_push_kernel(GatherArgs g) {
+  const size_t tid = (size_t)blockIdx.x * GATHER_BLOCK + threadIdx.x, nth = (size_t)gridDim.x * GATHER_BLOCK;
+  {
+    const size_t o = g.off[g.rank], b = g.off[g.rank + 1] - o;
+    for (int k = 1; k < g.world; ++k) {
+      const int r = (g.rank + k) % g.world;
+      copy_congruent(g.stage_peer[r] + g.par_off + o, g.x_full + o, b, tid, nth);
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) is_last = (atomicAdd(g.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last && threadIdx.x < g.world && (int)threadIdx.x != g.rank) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&g.mail[threadIdx.x]->gather_flag[g.rank]), "l"(g.epoch)
+                 : "memory");
+  }
+  if (is_last && threadIdx.x == 0) *g.ticket = 0;
+  Mailbox *mine = g.mail[g.rank];
+  for (int k = 1; k < g.world; ++k) {
+    const int r = (g.rank + g.world - k) % g.world;  // the peer that pushed to me first comes first
+    if (threadIdx.x == 0) {
+      unsigned long long v;
+      SpinGuard guard;
+      do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(&mine->gather_flag[r]) : "memory");
+      } while (v < g.epoch && !guard.expired(mine));
+    }
+    __syncthreads();
+    const size_t o = g.off[r], b = g.off[r + 1] - o;
+    copy_congruent(g.x_full + o, g.stage_mine + g.par_off + o, b, tid, nth);
   }
 }
 
@@ -493,14 +538,20 @@ b200sp_status comm_allgather_slices(b200sp_handle h, cudaStream_t st, void *x_fu
   }
   char *x = reinterpret_cast<char *>(x_full);
   if (h->p2p_ok) {
-    b200sp_status s = gather_stage_ensure(h, st, max_slice);
+    // B200SP_GATHER_PULL=1: the pull protocol (peers read each other's staged slice); default: push
+    static const bool pull = [] {
+      const char *e = getenv("B200SP_GATHER_PULL");
+      return e && e[0] && e[0] != '0';
+    }();
+    const size_t total = (size_t)slice_offsets[h->world] * elem;
+    b200sp_status s = gather_stage_ensure(h, st, pull ? max_slice : total);
     if (s != B200SP_OK) return s;
     GatherArgs g;
     memset(&g, 0, sizeof(g));
     g.x_full = x;
     g.stage_mine = reinterpret_cast<char *>(h->gather_stage);
     for (int r = 0; r < h->world; ++r) {
-      g.stage_peer[r] = reinterpret_cast<const char *>(h->peer_gather[r]);
+      g.stage_peer[r] = reinterpret_cast<char *>(h->peer_gather[r]);
       g.mail[r] = reinterpret_cast<Mailbox *>(h->peer_mail[r]);
       g.off[r] = (unsigned long long)slice_offsets[r] * elem;
     }
@@ -510,8 +561,13 @@ b200sp_status comm_allgather_slices(b200sp_handle h, cudaStream_t st, void *x_fu
     g.ticket = h->red_counters + 6;
     g.world = h->world;
     g.rank = h->rank;
-    allgather_pull_kernel<<<h->num_sms * 2, GATHER_BLOCK, 0, st>>>(g);
-    B200SP_LAUNCH_CHECK(h, "allgather_pull_kernel");
+    if (pull) {
+      allgather_pull_kernel<<<h->num_sms * 2, GATHER_BLOCK, 0, st>>>(g);
+      B200SP_LAUNCH_CHECK(h, "allgather_pull_kernel");
+    } else {
+      allgather_push_kernel<<<h->num_sms * 2, GATHER_BLOCK, 0, st>>>(g);
+      B200SP_LAUNCH_CHECK(h, "allgather_push_kernel");
+    }
     return B200SP_OK;
   }
   ncclComm_t comm = (ncclComm_t)h->nccl_comm;

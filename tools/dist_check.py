@@ -134,8 +134,12 @@ def main():
         from cusp_autotuned_b200.partition import nnz_balanced_offsets
         graph_ok = 1
         # equal row counts, and nnz-balanced blocks cut at arbitrary rows (slices not 16-byte aligned)
-        for offs, tdt in [(o, t) for o in (row_block_offsets(n, world), nnz_balanced_offsets(C.row_indices, n, world, align=1))
-                          for t in (torch.float32, torch.float64)]:
+        # (row blocks, x slices): equal row counts with x partitioned alike; nnz-balanced blocks cut at arbitrary
+        # rows (slices not 16-byte aligned) with x alike; nnz-balanced rows with x in equal slices (decoupled)
+        bal = nnz_balanced_offsets(C.row_indices, n, world, align=1)
+        eq = row_block_offsets(n, world)
+        for offs, xoffs, tdt in [(o, xo, t) for o, xo in ((eq, eq), (bal, bal), (bal, eq))
+                                 for t in (torch.float32, torch.float64)]:
             bounds = torch.searchsorted(C.row_indices, torch.tensor(offs, dtype=torch.int32, device=dev))
             e0, e1 = int(bounds[rank]), int(bounds[rank + 1])
             nloc = offs[rank + 1] - offs[rank]
@@ -145,17 +149,17 @@ def main():
                              C.column_indices[e0:e1].clone(), vals[e0:e1].clone())
             mats = {"coo": loc, "csr": convert.coo_to_csr(loc)}
             mats["hyb"] = convert.csr_to_hyb(mats["csr"])
-            for it in range(8):
+            for it in range(6):
                 xg = ((torch.arange(n, device=dev) * (it + 3)) % 17 - 8).to(tdt)
                 yref = torch.empty(n, dtype=tdt, device=dev)
                 h.spmv(Cg.descriptor(), xg, yref)
                 for fmt, M in mats.items():
                     xf = torch.full((n,), float("nan"), dtype=tdt, device=dev)
-                    xf[offs[rank]:offs[rank + 1]] = xg[offs[rank]:offs[rank + 1]]
+                    xf[xoffs[rank]:xoffs[rank + 1]] = xg[xoffs[rank]:xoffs[rank + 1]]
                     y = torch.empty(nloc, dtype=tdt, device=dev)
                     if (it + len(fmt)) % world == rank:
                         torch.cuda._sleep(2_000_000)
-                    h.spmv_dist_gather(M.descriptor(), offs, xf, y)
+                    h.spmv_dist_gather(M.descriptor(), xoffs, xf, y)
                     if not (torch.equal(xf, xg) and torch.equal(y, yref[offs[rank]:offs[rank + 1]])):
                         graph_ok = 0
         flags = torch.tensor([graph_ok], device=dev)
