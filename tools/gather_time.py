@@ -1,4 +1,6 @@
-"""Times the all-gather of b200sp_spmv_dist_gather alone (empty operator, x of 2^24 fp32 in equal slices):\n  python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/gather_time.py\nB200SP_GATHER_PULL=1 selects the pull protocol."""
+"""Times the all-gather of b200sp_spmv_dist_gather alone (empty operator, x of 2^24 fp32 in equal slices):
+  python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/gather_time.py
+B200SP_GATHER_PULL=1 selects the pull protocol."""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as td
