@@ -533,4 +533,72 @@ bool operator==(const array1d_view<It1> &a, const array1d_view<It2> &b) {
   return detail::arrays_equal(a, b);
 }
 
+// ---------------------------------------------------------------------------
+// generator arrays (cusp/array1d.h:564-662: array1d_views over thrust::counting_iterator,
+// thrust::constant_iterator and cusp::random_iterator).  Here they are host arrays filled at
+// construction with the same element values — usable wherever an array1d is (copy into either
+// memory space, cusp::copy, blas, operator==); O(n) memory instead of a fancy iterator.
+// ---------------------------------------------------------------------------
+template <typename ValueType>
+class counting_array : public array1d<ValueType, host_memory> {
+ public:
+  typedef size_t size_type;
+  counting_array(size_type size, ValueType init = ValueType(0)) : array1d<ValueType, host_memory>(size) {
+    for (size_type i = 0; i < size; ++i) (*this)[i] = (ValueType)(init + (ValueType)i);
+  }
+};
+
+template <typename ValueType>
+class constant_array : public array1d<ValueType, host_memory> {
+ public:
+  typedef size_t size_type;
+  constant_array(size_type size, ValueType value) : array1d<ValueType, host_memory>(size, value) {}
+};
+
+namespace detail {
+// element i of cusp::random_iterator<T>(seed)  (cusp/iterator/detail/random_iterator.inl:30-128):
+// a 64-bit integer hash of (i ^ seed) (the index type is ptrdiff_t, so the 64-bit variant is the one
+// taken on LP64), truncated to 32 bits for value types of at most 4 bytes; integers take the hash
+// as is, reals divide it by 2^32 resp. 2^64 -> [0, 1).
+inline unsigned long long random_hash64(unsigned long long i, unsigned long long seed) {
+  unsigned long long h = i ^ seed;
+  h = ~h + (h << 21);
+  h = h ^ (h >> 24);
+  h = (h + (h << 3)) + (h << 8);
+  h = h ^ (h >> 14);
+  h = (h + (h << 2)) + (h << 4);
+  h = h ^ (h >> 28);
+  h = h + (h << 31);
+  return h;
+}
+template <typename T, bool IsFloat = std::is_floating_point<T>::value, bool Wide = (sizeof(T) > 4)>
+struct random_value;
+template <typename T>
+struct random_value<T, false, false> {
+  static T of(unsigned long long h) { return (T)(unsigned int)h; }
+};
+template <typename T>
+struct random_value<T, false, true> {
+  static T of(unsigned long long h) { return (T)h; }
+};
+template <typename T>
+struct random_value<T, true, false> {
+  static T of(unsigned long long h) { return T((unsigned int)h) / (T(1u << 16) * T(1u << 16)); }
+};
+template <typename T>
+struct random_value<T, true, true> {
+  static T of(unsigned long long h) { return T(h) / (T(1ull << 32) * T(1ull << 32)); }
+};
+}  // namespace detail
+
+template <typename ValueType>
+class random_array : public array1d<ValueType, host_memory> {
+ public:
+  typedef size_t size_type;
+  random_array(size_type size, size_type seed = 0) : array1d<ValueType, host_memory>(size) {
+    for (size_type i = 0; i < size; ++i)
+      (*this)[i] = detail::random_value<ValueType>::of(detail::random_hash64((unsigned long long)i, (unsigned long long)seed));
+  }
+};
+
 }  // namespace cusp

@@ -89,3 +89,62 @@ void TestMakeViewsAndStream() {
   ASSERT_EQUAL(h[10], 0.0);  // interior row
 }
 TEST_DEVICE(TestMakeViewsAndStream)
+
+// generator arrays: testing/array1d_view.cu:449-458 and testing/random.cu:13-112
+template <class MemorySpace>
+void TestGeneratorArrays() {
+  cusp::counting_array<int> W(4, 5);
+  ASSERT_EQUAL(W.size(), (size_t)4);
+  ASSERT_EQUAL((int)W[0], 5);
+  ASSERT_EQUAL((int)W[3], 8);
+  cusp::constant_array<int> X(200, 5);
+  ASSERT_EQUAL((int)X[0], 5);
+  ASSERT_EQUAL((int)X[3], 5);
+  ASSERT_EQUAL((int)X[199], 5);
+  cusp::array1d<int, MemorySpace> Wd(W);
+  ASSERT_EQUAL(Wd == W, true);
+  // random integers: every nibble of the raw value is uniform within 5 %
+  const size_t n = 123456;
+  {
+    cusp::random_array<int> random(n);
+    size_t counts[8][16] = {{0}};
+    for (size_t i = 0; i < n; i++) {
+      const unsigned long long raw = (unsigned int)(int)random[i];
+      for (size_t nibble = 0; nibble < 8; nibble++) counts[nibble][(raw >> (4 * nibble)) % 16]++;
+    }
+    size_t lo = n, hi = 0;
+    for (auto &row : counts)
+      for (size_t c : row) {
+        lo = std::min(lo, c);
+        hi = std::max(hi, c);
+      }
+    ASSERT_TRUE(lo >= (size_t)(0.95 * (n / 16)) && hi <= (size_t)(1.05 * (n / 16)));
+    cusp::array1d<int, cusp::host_memory> h(random);
+    cusp::array1d<int, MemorySpace> d(random);
+    ASSERT_EQUAL(h == d, true);
+  }
+  // random reals: in [0, 1), 32 buckets uniform within 5 %
+  {
+    cusp::random_array<double> random(n);
+    cusp::random_array<float> randomf(n);
+    size_t b64[32] = {0}, b32[32] = {0};
+    for (size_t i = 0; i < n; i++) {
+      const double v = random[i];
+      const float f = randomf[i];
+      ASSERT_TRUE(0.0 <= v && v < 1.0 && 0.0f <= f && f <= 1.0f);
+      b64[(size_t)(v * 32.0)]++;
+      b32[std::min<size_t>(31, (size_t)(f * 32.0f))]++;
+    }
+    for (int k = 0; k < 32; ++k) {
+      ASSERT_TRUE(b64[k] >= (size_t)(0.95 * (n / 32)) && b64[k] <= (size_t)(1.05 * (n / 32)));
+      ASSERT_TRUE(b32[k] >= (size_t)(0.95 * (n / 32)) && b32[k] <= (size_t)(1.05 * (n / 32)));
+    }
+    cusp::array1d<double, MemorySpace> d(random);
+    ASSERT_EQUAL(d == random, true);
+    ASSERT_TRUE(!(cusp::random_array<double>(16, 1) == cusp::random_array<double>(16, 2)));  // the seed matters
+  }
+  // known answers of the published 64-bit integer hash (T. Wang), seed 0
+  ASSERT_EQUAL(cusp::detail::random_hash64(0, 0), 0x77cfa1eef01bca90ull);
+  ASSERT_EQUAL(cusp::detail::random_hash64(1, 0), 0x5bca7c69b794f8ceull);
+}
+TEST_HOST_DEVICE(TestGeneratorArrays)
