@@ -522,6 +522,27 @@ def main():
                    "checksum_matches_gpu": bool(abs(float(np.abs(yc).sum()) - y_check) <= 1e-9 * max(1.0, y_check))}
             del Ah, xv, yc
 
+    # ---- the reference's own CUDA kernel on this GPU (separate process: it cannot disturb anything above) ------
+    ref_gpu = None
+    if not args.quick and world == 1 and rank == 0:
+        try:
+            import subprocess
+            p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_gpu_kernels.py")], capture_output=True,
+                               text=True, timeout=240)
+            last = [ln for ln in p.stdout.strip().splitlines() if ln.startswith("{")]
+            if p.returncode != 0 or not last:
+                ref_gpu = {"error": f"rc={p.returncode}: {(p.stderr or p.stdout)[-300:]}"}
+            else:
+                full = json.loads(last[-1])
+                ref_gpu = {k: full[k] for k in ("workload", "kernel", "configs", "reps", "unavailable") if k in full}
+                for name, dct in full.get("dtypes", {}).items():
+                    ref_gpu[name] = {k: dct[k] for k in ("bytes", "engine_ms", "engine_gbs", "reference_best",
+                                                         "reference_first_config", "engine_speedup_over_reference_best",
+                                                         "valid_configs")}
+                    ref_gpu[name]["all_ms"] = [round(r["ms"], 4) if "ms" in r else None for r in dct["all"]]
+        except Exception as ex:
+            ref_gpu = {"error": repr(ex)}
+
     clocks = sampler.stop()
     if rank == 0:
         line = {
@@ -534,6 +555,7 @@ def main():
                        "parallelism": f"rowblock{world}", "api": "b200sp_spmv / b200sp_spmv_dist (C ABI)"},
             "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "cpu_baseline": cpu, "formats": formats, "cg": cg, "graph": graph,
+            "reference_cuda_kernel": ref_gpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -5,6 +5,8 @@
     committed outputs tests/golden/ref_spmv.npz, and live when _ref is present,
   * scipy as an independent cross-check.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -219,3 +221,30 @@ def test_make_diagonal_symmetric():
     for rows, cols, step, cnt in G.KTT_BANDED:
         B = O.make_diagonal_symmetric(rows, cols, step, cnt)
         assert B["diagonal_offsets"][0] == -512 and len(B["diagonal_offsets"]) == 1024
+
+
+def test_reference_gpu_kernel_harness_enumerates_the_ktt_dia_space():
+    """oracle/_ref/libcuspref_gpu.so (the reference's KTT DIA kernel compiled unmodified, measurement
+    infrastructure for bench.py's reference_cuda_kernel leg): loads without a GPU, exports its C ABI and
+    lists the 42 points of cusp/system/cuda/ktt/dia_multiply.h:24-55; only sm_100a code inside"""
+    import ctypes as C
+    import re
+    import subprocess
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libcuspref_gpu.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libcuspref_gpu.so not built (needs /root/reference)")
+    lib = C.CDLL(path)
+    assert lib.cuspref_dia_num_configs() == 42
+    p = (C.c_int * 4)()
+    seen = set()
+    for k in range(42):
+        assert lib.cuspref_dia_config(k, p) == 0
+        bs, pf, pt, sl = tuple(p)
+        assert bs in (128, 256, 512) and pf in (0, 2, 3, 4) and pt in (0, 1) and sl in (0, 1)
+        assert pf > 0 or pt == 0  # the KTT constraint
+        seen.add((bs, pf, pt, sl))
+    assert len(seen) == 42 and lib.cuspref_dia_config(42, p) != 0
+    assert hasattr(lib, "cuspref_dia_spmv")
+    if os.path.exists("/usr/local/cuda/bin/cuobjdump"):
+        out = subprocess.check_output(["/usr/local/cuda/bin/cuobjdump", "-res-usage", path], text=True)
+        assert len(re.findall(r"ktt_dia_vector_kernel", out)) == 84  # 42 points x {float, double}
