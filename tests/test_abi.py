@@ -123,3 +123,22 @@ def test_ring_stages_are_released_after_their_loads_are_consumed():
     import check_release_order
     sites, flagged = check_release_order.scan(capi.LIB_PATH)
     assert sites >= 40 and not flagged, flagged
+
+
+def test_release_order_checker_flags_an_unconsumed_load():
+    """the checker itself: an arrive right after an LDS whose register nobody read is flagged, the same
+    listing with a consumer in between is not"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import check_release_order
+    head = "\n\tFunction : _ZN6b200sp15coo_ring_kernelIfLi256ELi7EEEvNS_7CooArgsIT_EEix\n"
+    lds = "        /*0010*/                   LDS R4, [R2] ;\n        /*0020*/                   LDS.64 R6, [R2+0x8] ;\n"
+    use = "        /*0030*/                   FADD R9, R4, R6 ;\n        /*0040*/                   FADD R9, R9, R7 ;\n"
+    arrive = "        /*0050*/              @!P2 SYNCS.ARRIVE.TRANS64.A1T0 RZ, [R18+URZ], RZ ;\n"
+    producer = "        /*0060*/                   SYNCS.ARRIVE.TRANS64 RZ, [UR9], R16 ;\n"  # expect_tx arrive: not a release
+    sites, flagged = check_release_order.scan_text(head + lds + arrive + producer)
+    assert sites == 1 and len(flagged) == 1 and flagged[0][2] == ["R4", "R6", "R7"]
+    sites, flagged = check_release_order.scan_text(head + lds + use + arrive + producer)
+    assert sites == 1 and not flagged
+    other = "\n\tFunction : _ZN6b200sp11dot_kernelIfEEvv\n" + lds + arrive  # not a ring kernel: ignored
+    assert check_release_order.scan_text(other) == (0, [])

@@ -17,7 +17,11 @@ WINDOW = 300  # instructions scanned before each arrive
 
 
 def scan(lib):
-    txt = subprocess.check_output(["cuobjdump", "-sass", lib], text=True)
+    return scan_text(subprocess.check_output(["cuobjdump", "-sass", lib], text=True))
+
+
+def scan_text(txt):
+    """(release sites, flagged sites) of a `cuobjdump -sass` listing"""
     sites, flagged = 0, []
     for f in re.split(r"\n\s*Function : ", txt)[1:]:
         name = f.split("\n", 1)[0]
