@@ -385,10 +385,61 @@ int amax(const Array &x) {
 }
 
 // ---- overloads with a leading execution policy ------------------------------
+// Dispatched on the derived policy (cusp/memory.h: derived_cast): a user policy's own overload
+// `void axpy(my_system&, ...)` is found by argument-dependent lookup (testing/blas.cu:700-1208,
+// TestBlasDispatch); otherwise the call lands on adl_default::<name>, which forwards to the
+// policy-free function above.
+namespace detail {
+namespace adl_default {
+#define CUSP_B200_POLICY_DEFAULT_VOID(name)                                   \
+  template <typename P, typename... Args>                                     \
+  void name(cusp::execution_policy<P> &, Args &&... args) {                   \
+    cusp::blas::name(std::forward<Args>(args)...);                            \
+  }
+CUSP_B200_POLICY_DEFAULT_VOID(axpy)
+CUSP_B200_POLICY_DEFAULT_VOID(axpby)
+CUSP_B200_POLICY_DEFAULT_VOID(axpbypcz)
+CUSP_B200_POLICY_DEFAULT_VOID(xmy)
+CUSP_B200_POLICY_DEFAULT_VOID(copy)
+CUSP_B200_POLICY_DEFAULT_VOID(fill)
+CUSP_B200_POLICY_DEFAULT_VOID(scal)
+#undef CUSP_B200_POLICY_DEFAULT_VOID
+template <typename P, typename Array1, typename Array2>
+typename Array1::value_type dot(cusp::execution_policy<P> &, const Array1 &x, const Array2 &y) {
+  return cusp::blas::dot(x, y);
+}
+template <typename P, typename Array1, typename Array2>
+typename Array1::value_type dotc(cusp::execution_policy<P> &, const Array1 &x, const Array2 &y) {
+  return cusp::blas::dot(x, y);
+}
+template <typename P, typename Array>
+typename Array::value_type nrm2(cusp::execution_policy<P> &, const Array &x) {
+  return cusp::blas::nrm2(x);
+}
+template <typename P, typename Array>
+typename Array::value_type nrm1(cusp::execution_policy<P> &, const Array &x) {
+  return cusp::blas::asum(x);
+}
+template <typename P, typename Array>
+typename Array::value_type asum(cusp::execution_policy<P> &, const Array &x) {
+  return cusp::blas::asum(x);
+}
+template <typename P, typename Array>
+typename Array::value_type nrmmax(cusp::execution_policy<P> &, const Array &x) {
+  return cusp::blas::nrmmax(x);
+}
+template <typename P, typename Array>
+int amax(cusp::execution_policy<P> &, const Array &x) {
+  return cusp::blas::amax(x);
+}
+}  // namespace adl_default
+}  // namespace detail
+
 #define CUSP_B200_POLICY_VOID(name)                                           \
   template <typename P, typename... Args>                                     \
-  void name(const cusp::execution_policy<P> &, Args &&... args) {             \
-    name(std::forward<Args>(args)...);                                        \
+  void name(const cusp::execution_policy<P> &exec, Args &&... args) {         \
+    using detail::adl_default::name;                                          \
+    name(cusp::detail::derived_cast(exec), std::forward<Args>(args)...);      \
   }
 CUSP_B200_POLICY_VOID(axpy)
 CUSP_B200_POLICY_VOID(axpby)
@@ -399,34 +450,20 @@ CUSP_B200_POLICY_VOID(fill)
 CUSP_B200_POLICY_VOID(scal)
 #undef CUSP_B200_POLICY_VOID
 
-template <typename P, typename Array1, typename Array2>
-typename Array1::value_type dot(const cusp::execution_policy<P> &, const Array1 &x, const Array2 &y) {
-  return dot(x, y);
-}
-template <typename P, typename Array1, typename Array2>
-typename Array1::value_type dotc(const cusp::execution_policy<P> &, const Array1 &x, const Array2 &y) {
-  return dot(x, y);
-}
-template <typename P, typename Array>
-typename Array::value_type nrm2(const cusp::execution_policy<P> &, const Array &x) {
-  return nrm2(x);
-}
-template <typename P, typename Array>
-typename Array::value_type nrm1(const cusp::execution_policy<P> &, const Array &x) {
-  return asum(x);
-}
-template <typename P, typename Array>
-typename Array::value_type asum(const cusp::execution_policy<P> &, const Array &x) {
-  return asum(x);
-}
-template <typename P, typename Array>
-typename Array::value_type nrmmax(const cusp::execution_policy<P> &, const Array &x) {
-  return nrmmax(x);
-}
-template <typename P, typename Array>
-int amax(const cusp::execution_policy<P> &, const Array &x) {
-  return amax(x);
-}
+#define CUSP_B200_POLICY_VALUE(name)                                                          \
+  template <typename P, typename... Args>                                                     \
+  auto name(const cusp::execution_policy<P> &exec, Args &&... args) {                         \
+    using detail::adl_default::name;                                                          \
+    return name(cusp::detail::derived_cast(exec), std::forward<Args>(args)...);               \
+  }
+CUSP_B200_POLICY_VALUE(dot)
+CUSP_B200_POLICY_VALUE(dotc)
+CUSP_B200_POLICY_VALUE(nrm2)
+CUSP_B200_POLICY_VALUE(nrm1)
+CUSP_B200_POLICY_VALUE(asum)
+CUSP_B200_POLICY_VALUE(nrmmax)
+CUSP_B200_POLICY_VALUE(amax)
+#undef CUSP_B200_POLICY_VALUE
 
 // ---- BLAS-2/3: not provided by the generic back end either ------------------
 template <typename... Args>

@@ -557,9 +557,20 @@ template <typename SourceType, typename DestinationType>
 void convert(const SourceType &src, DestinationType &dst) {
   detail::convert_dispatch(src, dst, typename SourceType::format(), typename DestinationType::format());
 }
-template <typename Policy, typename SourceType, typename DestinationType>
-void convert(const Policy &, const SourceType &src, DestinationType &dst) {
-  convert(src, dst);
+namespace detail {
+namespace adl_default {
+template <typename P, typename SourceType, typename DestinationType>
+void convert(cusp::execution_policy<P> &, const SourceType &src, DestinationType &dst) {
+  cusp::convert(src, dst);
+}
+}  // namespace adl_default
+}  // namespace detail
+// leading execution policy: dispatched on the derived policy (cusp/memory.h: derived_cast;
+// testing/convert.cu:662-690, TestConvertDispatch)
+template <typename P, typename SourceType, typename DestinationType>
+void convert(const execution_policy<P> &exec, const SourceType &src, DestinationType &dst) {
+  using detail::adl_default::convert;
+  convert(detail::derived_cast(exec), src, dst);
 }
 
 // cusp::copy: same format, any memory spaces (cusp/copy.h)

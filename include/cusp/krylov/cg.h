@@ -116,11 +116,23 @@ void cg(const LinearOperator &A, VectorType1 &x, const VectorType2 &b) {
 }
 
 // leading execution policy (cg.h:43-70)
+namespace detail {
+namespace adl_default {
 template <typename P, typename LinearOperator, typename VectorType1, typename VectorType2, typename Monitor,
           typename Preconditioner>
-void cg(const cusp::execution_policy<P> &, const LinearOperator &A, VectorType1 &x, const VectorType2 &b,
+void cg(cusp::execution_policy<P> &, const LinearOperator &A, VectorType1 &x, const VectorType2 &b,
         Monitor &monitor, Preconditioner &M) {
-  cg(A, x, b, monitor, M);
+  cusp::krylov::cg(A, x, b, monitor, M);
+}
+}  // namespace adl_default
+}  // namespace detail
+// leading execution policy: dispatched on the derived policy (cusp/memory.h: derived_cast)
+template <typename P, typename LinearOperator, typename VectorType1, typename VectorType2, typename Monitor,
+          typename Preconditioner>
+void cg(const cusp::execution_policy<P> &exec, const LinearOperator &A, VectorType1 &x, const VectorType2 &b,
+        Monitor &monitor, Preconditioner &M) {
+  using detail::adl_default::cg;
+  cg(cusp::detail::derived_cast(exec), A, x, b, monitor, M);
 }
 
 }  // namespace krylov

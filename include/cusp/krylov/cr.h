@@ -66,11 +66,23 @@ void cr(const LinearOperator &A, VectorType1 &x, const VectorType2 &b) {
   cr(A, x, b, monitor);
 }
 
+namespace detail {
+namespace adl_default {
 template <typename P, typename LinearOperator, typename VectorType1, typename VectorType2, typename Monitor,
           typename Preconditioner>
-void cr(const cusp::execution_policy<P> &, const LinearOperator &A, VectorType1 &x, const VectorType2 &b,
+void cr(cusp::execution_policy<P> &, const LinearOperator &A, VectorType1 &x, const VectorType2 &b,
         Monitor &monitor, Preconditioner &M) {
-  cr(A, x, b, monitor, M);
+  cusp::krylov::cr(A, x, b, monitor, M);
+}
+}  // namespace adl_default
+}  // namespace detail
+// leading execution policy: dispatched on the derived policy (cusp/memory.h: derived_cast)
+template <typename P, typename LinearOperator, typename VectorType1, typename VectorType2, typename Monitor,
+          typename Preconditioner>
+void cr(const cusp::execution_policy<P> &exec, const LinearOperator &A, VectorType1 &x, const VectorType2 &b,
+        Monitor &monitor, Preconditioner &M) {
+  using detail::adl_default::cr;
+  cr(cusp::detail::derived_cast(exec), A, x, b, monitor, M);
 }
 
 }  // namespace krylov

@@ -148,11 +148,23 @@ void gmres(const LinearOperator &A, VectorType1 &x, const VectorType2 &b, const 
   gmres(A, x, b, restart, monitor);
 }
 
+namespace detail {
+namespace adl_default {
 template <typename P, typename LinearOperator, typename VectorType1, typename VectorType2, typename Monitor,
           typename Preconditioner>
-void gmres(const cusp::execution_policy<P> &, const LinearOperator &A, VectorType1 &x, const VectorType2 &b,
+void gmres(cusp::execution_policy<P> &, const LinearOperator &A, VectorType1 &x, const VectorType2 &b,
            const size_t restart, Monitor &monitor, Preconditioner &M) {
-  gmres(A, x, b, restart, monitor, M);
+  cusp::krylov::gmres(A, x, b, restart, monitor, M);
+}
+}  // namespace adl_default
+}  // namespace detail
+// leading execution policy: dispatched on the derived policy (cusp/memory.h: derived_cast)
+template <typename P, typename LinearOperator, typename VectorType1, typename VectorType2, typename Monitor,
+          typename Preconditioner>
+void gmres(const cusp::execution_policy<P> &exec, const LinearOperator &A, VectorType1 &x, const VectorType2 &b,
+           const size_t restart, Monitor &monitor, Preconditioner &M) {
+  using detail::adl_default::gmres;
+  gmres(cusp::detail::derived_cast(exec), A, x, b, restart, monitor, M);
 }
 
 }  // namespace krylov

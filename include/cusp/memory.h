@@ -13,6 +13,20 @@ struct execution_policy {};
 struct host_memory : execution_policy<host_memory> {};
 struct device_memory : execution_policy<device_memory> {};
 
+namespace detail {
+// Dispatch on the derived policy, as thrust/cusp do (cusp/detail/multiply.inl:27-46: the public
+// entry point calls `multiply(derived_cast(exec), ...)` unqualified): a user policy
+//     struct my_system : cusp::execution_policy<my_system> { ... };
+// with its own overload  `void multiply(my_system&, const A&, const B&, C&)`  in its namespace is
+// reached through argument-dependent lookup; without such an overload the call lands on the
+// library's implementation in `adl_default` (taken by `execution_policy<P>&`, a worse match than a
+// user's exact `my_system&`, a better one than the public `const execution_policy<P>&` entry).
+template <typename P>
+P &derived_cast(const execution_policy<P> &exec) {
+  return const_cast<P &>(static_cast<const P &>(exec));
+}
+}  // namespace detail
+
 struct known_format {};
 struct unknown_format {};
 struct dense_format : known_format {};

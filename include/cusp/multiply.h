@@ -211,11 +211,12 @@ void block_multiply(const M &A, const B &X, C &Y, F0 initialize, F1 combine, F2 
 }  // namespace detail
 
 // ---- 7-argument form (cusp/multiply.h:163-195) ------------------------------
-template <typename P, typename LinearOperator, typename MatrixOrVector1, typename MatrixOrVector2, typename UnaryFunction,
+namespace detail {
+namespace adl_default {
+template <typename P, typename LinearOperator, typename MatrixOrVector1, typename V2, typename UnaryFunction,
           typename BinaryFunction1, typename BinaryFunction2>
-void multiply(const execution_policy<P> &, const LinearOperator &A, const MatrixOrVector1 &B, MatrixOrVector2 &&C,
+void multiply(cusp::execution_policy<P> &, const LinearOperator &A, const MatrixOrVector1 &B, V2 &C,
               UnaryFunction initialize, BinaryFunction1 combine, BinaryFunction2 reduce) {
-  typedef typename std::decay<MatrixOrVector2>::type V2;
   if constexpr (detail::is_array2d<MatrixOrVector1>::value && std::is_base_of<sparse_format, typename LinearOperator::format>::value) {
     detail::block_multiply(A, B, C, initialize, combine, reduce);
   } else {
@@ -225,6 +226,15 @@ void multiply(const execution_policy<P> &, const LinearOperator &A, const Matrix
     detail::check_shapes(A, B, C);
     detail::multiply_in(typename LinearOperator::memory_space(), A, B, C, initialize, combine, reduce, false);
   }
+}
+}  // namespace adl_default
+}  // namespace detail
+template <typename P, typename LinearOperator, typename MatrixOrVector1, typename MatrixOrVector2, typename UnaryFunction,
+          typename BinaryFunction1, typename BinaryFunction2>
+void multiply(const execution_policy<P> &exec, const LinearOperator &A, const MatrixOrVector1 &B, MatrixOrVector2 &&C,
+              UnaryFunction initialize, BinaryFunction1 combine, BinaryFunction2 reduce) {
+  using detail::adl_default::multiply;
+  multiply(detail::derived_cast(exec), A, B, C, initialize, combine, reduce);
 }
 template <typename LinearOperator, typename MatrixOrVector1, typename MatrixOrVector2, typename UnaryFunction,
           typename BinaryFunction1, typename BinaryFunction2>
@@ -263,9 +273,18 @@ template <typename LinearOperator, typename MatrixOrVector1, typename MatrixOrVe
 void multiply(const LinearOperator &A, const MatrixOrVector1 &B, MatrixOrVector2 &&C) {
   detail::multiply3(A, B, C, typename LinearOperator::format());
 }
-template <typename P, typename LinearOperator, typename MatrixOrVector1, typename MatrixOrVector2>
-void multiply(const execution_policy<P> &, const LinearOperator &A, const MatrixOrVector1 &B, MatrixOrVector2 &&C) {
+namespace detail {
+namespace adl_default {
+template <typename P, typename LinearOperator, typename MatrixOrVector1, typename V2>
+void multiply(cusp::execution_policy<P> &, const LinearOperator &A, const MatrixOrVector1 &B, V2 &C) {
   detail::multiply3(A, B, C, typename LinearOperator::format());
+}
+}  // namespace adl_default
+}  // namespace detail
+template <typename P, typename LinearOperator, typename MatrixOrVector1, typename MatrixOrVector2>
+void multiply(const execution_policy<P> &exec, const LinearOperator &A, const MatrixOrVector1 &B, MatrixOrVector2 &&C) {
+  using detail::adl_default::multiply;
+  multiply(detail::derived_cast(exec), A, B, C);
 }
 
 // ---- generalized_spmv (cusp/multiply.h:197-280): z = reduce(y, A (combine) x)
