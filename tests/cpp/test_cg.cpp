@@ -136,3 +136,52 @@ void TestCgShapeErrors() {
   ASSERT_THROWS(cusp::krylov::cg(A, x, b), cusp::invalid_input_exception);
 }
 TEST_HOST_DEVICE(TestCgShapeErrors)
+
+// testing/monitor.cu:5-69 — the monitor on its own: tolerance = abs + rel * ||b||, finished() records the
+// residual norm, the iteration limit ends the run, reset() re-arms with a new right-hand side
+template <typename MemorySpace>
+void TestMonitorSimple() {
+  cusp::array1d<float, MemorySpace> b(2);
+  b[0] = 10;
+  b[1] = 0;
+  cusp::array1d<float, MemorySpace> r(2);
+  r[0] = 10;
+  r[1] = 0;
+  cusp::monitor<float> monitor(b, 5, 0.5, 1.0);
+  ASSERT_EQUAL(monitor.finished(r), false);
+  ASSERT_EQUAL(monitor.iteration_count(), (size_t)0);
+  ASSERT_EQUAL(monitor.iteration_limit(), (size_t)5);
+  ASSERT_EQUAL(monitor.relative_tolerance(), 0.5f);
+  ASSERT_EQUAL(monitor.absolute_tolerance(), 1.0f);
+  ASSERT_EQUAL(monitor.tolerance(), 6.0f);
+  ++monitor;
+  ASSERT_EQUAL(monitor.finished(r), false);
+  ASSERT_EQUAL(monitor.iteration_count(), (size_t)1);
+  ASSERT_EQUAL(monitor.residual_norm(), 10.0f);
+  r[0] = 2;
+  ASSERT_EQUAL(monitor.finished(r), true);
+  ASSERT_EQUAL(monitor.iteration_count(), (size_t)1);
+  ASSERT_EQUAL(monitor.residual_norm(), 2.0f);
+  ASSERT_EQUAL(monitor.converged(), true);
+  r[0] = 7;
+  ASSERT_EQUAL(monitor.finished(r), false);
+  ASSERT_EQUAL(monitor.residual_norm(), 7.0f);
+  ++monitor;
+  ASSERT_EQUAL(monitor.finished(r), false);
+  ASSERT_EQUAL(monitor.iteration_count(), (size_t)2);
+  ++monitor;
+  ++monitor;
+  ASSERT_EQUAL(monitor.finished(r), false);
+  ASSERT_EQUAL(monitor.iteration_count(), (size_t)4);
+  ++monitor;
+  ASSERT_EQUAL(monitor.finished(r), true);  // iteration limit
+  ASSERT_EQUAL(monitor.iteration_count(), (size_t)5);
+  ASSERT_EQUAL(monitor.residual_norm(), 7.0f);
+  ASSERT_EQUAL(monitor.converged(), false);
+  monitor.reset(r);
+  ASSERT_EQUAL(monitor.finished(r), false);
+  ASSERT_EQUAL(monitor.iteration_count(), (size_t)0);
+  ASSERT_EQUAL(monitor.residual_norm(), 7.0f);
+}
+static void TestMonitorSimpleHost() { TestMonitorSimple<cusp::host_memory>(); }
+TEST_HOST(TestMonitorSimpleHost)
