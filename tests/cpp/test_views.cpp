@@ -148,3 +148,40 @@ void TestGeneratorArrays() {
   ASSERT_EQUAL(cusp::detail::random_hash64(1, 0), 0x5bca7c69b794f8ceull);
 }
 TEST_HOST_DEVICE(TestGeneratorArrays)
+
+// testing/linear_operator.cu:5-47 — linear_operator carries shape and types; identity_operator copies;
+// a user operator (unknown_format) is applied through operator() by cusp::multiply and works as the A of cg
+template <class MemorySpace>
+struct scale_by_two : cusp::linear_operator<float, MemorySpace> {
+  scale_by_two(int n) : cusp::linear_operator<float, MemorySpace>(n, n) {}
+  template <typename V1, typename V2>
+  void operator()(const V1 &x, V2 &y) const {
+    cusp::blas::axpby(x, x, y, 1.0f, 1.0f);
+  }
+};
+template <class MemorySpace>
+void TestLinearOperators() {
+  typedef cusp::linear_operator<float, MemorySpace, long> LinearOperator;
+  LinearOperator A(4, 3);
+  ASSERT_EQUAL(A.num_rows, (size_t)4);
+  ASSERT_EQUAL(A.num_cols, (size_t)3);
+  static_assert(std::is_same<typename LinearOperator::value_type, float>::value, "value_type");
+  static_assert(std::is_same<typename LinearOperator::index_type, long>::value, "index_type");
+  cusp::array1d<float, MemorySpace> x(4), y(4);
+  x[0] = 7.0f; y[0] = 0.0f; x[1] = 5.0f; y[1] = -2.0f; x[2] = 4.0f; y[2] = 0.0f; x[3] = -3.0f; y[3] = 5.0f;
+  cusp::identity_operator<float, MemorySpace> I(4, 4);
+  I(x, y);
+  ASSERT_EQUAL((float)y[0], 7.0f);
+  ASSERT_EQUAL((float)y[3], -3.0f);
+  scale_by_two<MemorySpace> S(4);
+  cusp::multiply(S, x, y);  // generic/multiply.inl:59-73: unknown_format -> A(x, y)
+  ASSERT_EQUAL((float)y[0], 14.0f);
+  ASSERT_EQUAL((float)y[3], -6.0f);
+  cusp::array1d<float, MemorySpace> b(4, 3.0f), s(4, 0.0f);
+  cusp::monitor<float> monitor(b, 10, 1e-6);
+  cusp::krylov::cg(S, s, b, monitor);  // 2 s = b
+  ASSERT_TRUE(monitor.converged());
+  ASSERT_EQUAL((float)s[2], 1.5f);
+}
+static void TestLinearOperatorsHost() { TestLinearOperators<cusp::host_memory>(); }
+TEST_HOST(TestLinearOperatorsHost)
