@@ -238,6 +238,14 @@ class array1d<T, host_memory> {
   }
   template <typename It, typename = typename std::enable_if<!std::is_integral<It>::value>::type>
   array1d(It first, It last) : v_(first, last) {}
+  // std::vector interoperability (testing/array1d.cu:66-140)
+  template <typename U, typename Alloc>
+  array1d(const std::vector<U, Alloc> &v) : v_(v.begin(), v.end()) {}
+  template <typename U, typename Alloc>
+  array1d &operator=(const std::vector<U, Alloc> &v) {
+    v_.assign(v.begin(), v.end());
+    return *this;
+  }
 
   array1d &operator=(const array1d &o) {
     v_ = o.v_;
@@ -335,6 +343,20 @@ class array1d<T, device_memory> {
     std::vector<T> h(first, last);
     resize(h.size());
     detail::raw_copy<T, host_memory, device_memory>(h.data(), p_, n_);
+  }
+  // std::vector interoperability (testing/array1d.cu:66-140)
+  template <typename U, typename Alloc>
+  array1d(const std::vector<U, Alloc> &v) {
+    std::vector<T> h(v.begin(), v.end());
+    resize(h.size());
+    detail::raw_copy<T, host_memory, device_memory>(h.data(), p_, n_);
+  }
+  template <typename U, typename Alloc>
+  array1d &operator=(const std::vector<U, Alloc> &v) {
+    std::vector<T> h(v.begin(), v.end());
+    resize(h.size());
+    detail::raw_copy<T, host_memory, device_memory>(h.data(), p_, n_);
+    return *this;
   }
   ~array1d() { release(); }
 
@@ -519,6 +541,26 @@ bool operator==(const array1d<T1, S1> &a, const array1d<T2, S2> &b) {
 template <typename T1, typename S1, typename T2, typename S2>
 bool operator!=(const array1d<T1, S1> &a, const array1d<T2, S2> &b) {
   return !detail::arrays_equal(a, b);
+}
+template <typename T1, typename S1, typename U, typename Alloc>
+bool operator==(const array1d<T1, S1> &a, const std::vector<U, Alloc> &v) {
+  if (a.size() != v.size()) return false;
+  auto ha = detail::to_host_vector(a);
+  for (size_t i = 0; i < ha.size(); ++i)
+    if (!(ha[i] == v[i])) return false;
+  return true;
+}
+template <typename T1, typename S1, typename U, typename Alloc>
+bool operator==(const std::vector<U, Alloc> &v, const array1d<T1, S1> &a) {
+  return a == v;
+}
+template <typename T1, typename S1, typename U, typename Alloc>
+bool operator!=(const array1d<T1, S1> &a, const std::vector<U, Alloc> &v) {
+  return !(a == v);
+}
+template <typename T1, typename S1, typename U, typename Alloc>
+bool operator!=(const std::vector<U, Alloc> &v, const array1d<T1, S1> &a) {
+  return !(a == v);
 }
 template <typename T1, typename S1, typename It>
 bool operator==(const array1d<T1, S1> &a, const array1d_view<It> &b) {

@@ -185,3 +185,62 @@ void TestLinearOperators() {
 }
 static void TestLinearOperatorsHost() { TestLinearOperators<cusp::host_memory>(); }
 TEST_HOST(TestLinearOperatorsHost)
+
+// testing/array1d.cu:10-190 — array1d as a container: push_back, constructors (size, fill, other array /
+// std::vector / iterator range), assignment and equality across array types
+template <typename MemorySpace>
+void TestArray1dContainer() {
+  cusp::array1d<int, MemorySpace> a(4);
+  ASSERT_EQUAL(a.size(), (size_t)4);
+  for (int i = 0; i < 4; ++i) a[i] = i;
+  a.push_back(4);
+  ASSERT_EQUAL(a.size(), (size_t)5);
+  for (int i = 0; i < 5; ++i) ASSERT_EQUAL((int)a[i], i);
+
+  cusp::array1d<int, cusp::host_memory> h(a);
+  ASSERT_EQUAL(h.size(), (size_t)5);
+  ASSERT_EQUAL((int)h[4], 4);
+  const cusp::array1d<int, cusp::host_memory> ch(2, 10);
+  ASSERT_EQUAL((int)ch[1], 10);
+  cusp::array1d<int, MemorySpace> from_const(ch);
+  ASSERT_EQUAL((int)from_const[0], 10);
+
+  std::vector<int> v(2, 10);
+  cusp::array1d<int, MemorySpace> av(v);
+  ASSERT_EQUAL(av.size(), (size_t)2);
+  ASSERT_EQUAL((int)av[1], 10);
+  cusp::array1d<int, MemorySpace> ar(v.begin(), v.end());
+  ASSERT_EQUAL((int)ar[0], 10);
+  cusp::array1d<int, MemorySpace> assigned;
+  assigned = v;
+  ASSERT_EQUAL(assigned.size(), (size_t)2);
+  assigned = a;
+  ASSERT_EQUAL(assigned.size(), (size_t)5);
+  assigned = ch;
+  ASSERT_EQUAL((int)assigned[1], 10);
+
+  cusp::array1d<int, MemorySpace> A(2);
+  A[0] = 10;
+  A[1] = 20;
+  cusp::array1d<int, cusp::host_memory> hh(A.begin(), A.end());
+  std::vector<int> vv(2);
+  vv[0] = 10;
+  vv[1] = 20;
+  ASSERT_EQUAL(A == hh, true);
+  ASSERT_EQUAL(A == vv, true);
+  hh.push_back(30);
+  vv.push_back(30);
+  ASSERT_EQUAL(A != hh, true);
+  ASSERT_EQUAL(A != vv, true);
+  // resize / reserve / swap
+  A.resize(3);
+  ASSERT_EQUAL(A.size(), (size_t)3);
+  ASSERT_EQUAL((int)A[1], 20);
+  cusp::array1d<int, MemorySpace> B(1, 7);
+  A.swap(B);
+  ASSERT_EQUAL(A.size(), (size_t)1);
+  ASSERT_EQUAL((int)A[0], 7);
+  ASSERT_EQUAL(B.size(), (size_t)3);
+}
+static void TestArray1dContainerHost() { TestArray1dContainer<cusp::host_memory>(); }
+TEST_HOST(TestArray1dContainerHost)
