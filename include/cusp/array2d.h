@@ -86,6 +86,19 @@ class array2d {
     return *this;
   }
 
+  // the other storage order: entries are re-laid out (cusp/detail/array2d.inl, testing/array2d.cu:200-229)
+  template <typename U, typename Space, typename O2,
+            typename = typename std::enable_if<!std::is_same<O2, Orientation>::value>::type>
+  array2d(const array2d<U, Space, O2> &o) {
+    assign_reoriented(o);
+  }
+  template <typename U, typename Space, typename O2,
+            typename = typename std::enable_if<!std::is_same<O2, Orientation>::value>::type>
+  array2d &operator=(const array2d<U, Space, O2> &o) {
+    assign_reoriented(o);
+    return *this;
+  }
+
   void resize(size_t r, size_t c) { resize(r, c, detail::orient<Orientation>::minor(r, c)); }
   void resize(size_t r, size_t c, size_t p) {
     if (p < detail::orient<Orientation>::minor(r, c))
@@ -111,6 +124,7 @@ class array2d {
   // contiguous lines of the storage order as array1d views (cusp/array2d.h: row(i) of a row_major,
   // column(j) of a column_major array; the strided direction is not provided here)
   typedef typename values_array_type::view row_view;
+
   typedef typename values_array_type::view column_view;
   row_view row(size_t i) {
     static_assert(std::is_same<Orientation, row_major>::value, "array2d::row(): contiguous only for row_major");
@@ -120,6 +134,18 @@ class array2d {
     static_assert(std::is_same<Orientation, column_major>::value,
                   "array2d::column(): contiguous only for column_major");
     return values.subarray(j * pitch, num_rows);
+  }
+
+ private:
+  template <typename U, typename Space, typename O2>
+  void assign_reoriented(const array2d<U, Space, O2> &o) {
+    auto h = detail::to_host_vector(o.values);
+    resize(o.num_rows, o.num_cols);
+    std::vector<T> mine(values.size(), T(0));
+    for (size_t i = 0; i < o.num_rows; ++i)
+      for (size_t j = 0; j < o.num_cols; ++j)
+        mine[detail::orient<Orientation>::index(i, j, pitch)] = (T)h[detail::orient<O2>::index(i, j, o.pitch)];
+    detail::raw_copy<T, host_memory, MemorySpace>(mine.data(), detail::raw_ptr(values), mine.size());
   }
 };
 

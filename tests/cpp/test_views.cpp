@@ -244,3 +244,59 @@ void TestArray1dContainer() {
 }
 static void TestArray1dContainerHost() { TestArray1dContainer<cusp::host_memory>(); }
 TEST_HOST(TestArray1dContainerHost)
+
+// testing/array2d.cu:100-298 — storage order, pitch, resize, swap, mixed orientations
+template <class Space>
+void TestArray2dContainer() {
+  cusp::array2d<float, Space, cusp::row_major> A(2, 3);
+  const float vals[6] = {10, 20, 30, 40, 50, 60};
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 3; ++j) A(i, j) = vals[3 * i + j];
+  for (int n = 0; n < 6; ++n) ASSERT_EQUAL((float)A.values[n], vals[n]);
+  A.resize(2, 3, 4);  // non-trivial pitch
+  cusp::blas::fill(A.values, 0.0f);
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 3; ++j) A(i, j) = vals[3 * i + j];
+  const float padded[8] = {10, 20, 30, 0, 40, 50, 60, 0};
+  for (int n = 0; n < 8; ++n) ASSERT_EQUAL((float)A.values[n], padded[n]);
+
+  cusp::array2d<float, Space, cusp::column_major> C(2, 3);
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 3; ++j) C(i, j) = vals[3 * i + j];
+  const float cm[6] = {10, 40, 20, 50, 30, 60};
+  for (int n = 0; n < 6; ++n) ASSERT_EQUAL((float)C.values[n], cm[n]);
+
+  // mixed orientations: assignment converts the storage order (array2d.cu:200-229)
+  cusp::array2d<float, Space, cusp::row_major> R(2, 3);
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 3; ++j) R(i, j) = vals[3 * i + j];
+  cusp::array2d<float, Space, cusp::column_major> C2;
+  C2 = R;
+  cusp::array2d<float, Space, cusp::row_major> R2(C2);
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 3; ++j) {
+      ASSERT_EQUAL((float)C2(i, j), vals[3 * i + j]);
+      ASSERT_EQUAL((float)R2(i, j), vals[3 * i + j]);
+    }
+  ASSERT_EQUAL(C2 == R, true);
+
+  cusp::array2d<float, Space> Z;
+  Z.resize(3, 2);
+  ASSERT_EQUAL(Z.pitch, (size_t)2);
+  ASSERT_EQUAL(Z.num_entries, (size_t)6);
+  ASSERT_EQUAL(Z.values.size(), (size_t)6);
+  Z.resize(3, 2, 4);
+  ASSERT_EQUAL(Z.pitch, (size_t)4);
+  ASSERT_EQUAL(Z.values.size(), (size_t)12);
+  ASSERT_THROWS(Z.resize(3, 2, 1), cusp::invalid_input_exception);
+
+  cusp::array2d<float, Space> P(2, 2, 1.0f), Q(3, 1, 2.0f);
+  cusp::array2d<float, Space> P_copy(P), Q_copy(Q);
+  P.swap(Q);
+  ASSERT_EQUAL(P.num_rows, Q_copy.num_rows);
+  ASSERT_EQUAL(P.values == Q_copy.values, true);
+  ASSERT_EQUAL(Q.num_cols, P_copy.num_cols);
+  ASSERT_EQUAL(Q.values == P_copy.values, true);
+}
+static void TestArray2dContainerHost() { TestArray2dContainer<cusp::host_memory>(); }
+TEST_HOST(TestArray2dContainerHost)
