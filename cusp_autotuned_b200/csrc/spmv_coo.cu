@@ -619,7 +619,12 @@ static void coo_defaults(b200sp_cfg &c, b200sp_handle h, cudaStream_t st, i64 nn
     c.kernel = (tma_ok && nnz >= (i64)h->num_sms * 8 * c.block_size * c.unroll && coo_prefers_ring(h, st, nnz, Aj, elem))
                    ? B200SP_K_COO_RING
                    : B200SP_K_COO_SEGSCAN;
-  if (c.kernel == B200SP_K_COO_RING && no_shape && elem == 8) c.block_size = 512;  // sweep: 512x7 for fp64
+  if (c.kernel == B200SP_K_COO_RING && no_shape) {  // profiles/r02_results.md: 512x7 for fp64, 256x9 for fp32
+    if (elem == 8)
+      c.block_size = 512;
+    else
+      c.unroll = 9;
+  }
   if (c.kernel == B200SP_K_COO_RING) {
     if (c.stages == 0) c.stages = 2;
     if (c.ctas_per_sm == 0) c.ctas_per_sm = 4;
