@@ -134,6 +134,8 @@ EXPORTED_SYMBOLS = (
                                        "amax") for s in _SFX]
     + [f"b200sp_poisson_{f}_{s}" for f in ("dia", "ell", "csr") for s in _SFX]
     + [f"b200sp_spmm_csr_{s}" for s in _SFX]
+    + ["b200sp_coo_plan_create", "b200sp_coo_plan_destroy", "b200sp_coo_plan_info"]
+    + [f"b200sp_spmv_coo_plan_{s}" for s in _SFX]
 )
 
 _lib: Optional[C.CDLL] = None
@@ -235,6 +237,26 @@ class Handle:
         self.check(f(self._h, _stream(), C.c_int64(rows), C.c_int64(cols), C.c_int64(nnz), _ptr(Ap), _ptr(Aj),
                      _ptr(Ax), C.c_int64(k), _ptr(X), C.c_int64(ldx), _ptr(Y), C.c_int64(ldy),
                      C.c_int(int(accumulate))))
+
+    # -- experimental: inspector / executor COO product (hot columns of x in shared memory) -----------
+    def coo_plan_create(self, rows, cols, nnz, Ai, Aj, dtype: int, table_bytes: int = 0):
+        plan = C.c_void_p()
+        self.check(self.lib.b200sp_coo_plan_create(self._h, _stream(), C.c_int64(rows), C.c_int64(cols), C.c_int64(nnz),
+                                                   _ptr(Ai), _ptr(Aj), C.c_int(dtype), C.c_int64(table_bytes),
+                                                   C.byref(plan)))
+        return plan
+
+    def coo_plan_destroy(self, plan):
+        self.check(self.lib.b200sp_coo_plan_destroy(self._h, plan))
+
+    def coo_plan_info(self, plan):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self.check(self.lib.b200sp_coo_plan_info(plan, C.byref(a), C.byref(b), C.byref(c)))
+        return {"hot_columns": a.value, "hot_entries": b.value, "capacity": c.value}
+
+    def spmv_coo_plan(self, plan, Ax, x, y, accumulate=False):
+        f = getattr(self.lib, "b200sp_spmv_coo_plan_" + _sfx(y.dtype))
+        self.check(f(self._h, _stream(), plan, _ptr(Ax), _ptr(x), _ptr(y), C.c_int(int(accumulate))))
 
     def spmv_ell(self, rows, cols, K, pitch, cidx, vals, x, y, accumulate=False, cfg: Optional[Cfg] = None):
         f = getattr(self.lib, "b200sp_spmv_ell_" + _sfx(y.dtype))

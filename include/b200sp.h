@@ -317,6 +317,29 @@ b200sp_status b200sp_spmm_csr_f64(b200sp_handle h, b200sp_stream stream, int64_t
                                   const double *values, int64_t block_cols, const double *X,
                                   int64_t ldx, double *Y, int64_t ldy, int accumulate);
 
+/* ---- EXPERIMENTAL: inspector / executor COO product for gather-bound operators (power-law graphs) ----
+ * Not used by b200sp_spmv / cusp::multiply.  b200sp_coo_plan_create inspects the sparsity pattern once
+ * (column histogram -> the most frequent columns that fit a `table_bytes` shared-memory table, default
+ * 128 KiB -> a second copy of column_indices in which those columns are replaced by a table slot);
+ * b200sp_spmv_coo_plan_<t> keeps x of those columns in shared memory, so their gathers never reach the
+ * L1 / L2 path that bounds COO on an R-MAT.  Same tiles, summation order and carry
+ * fix-up as the 1024 x 7 shape of the segmented-scan kernel.  The plan borrows row_indices (caller keeps
+ * them alive and unchanged while the plan exists); values are passed per call and may change between
+ * calls.  dtype fixes the table's element size.  First hardware validation: tests/test_zz_plan_gpu.py. */
+typedef struct b200sp_coo_plan_s *b200sp_coo_plan;
+b200sp_status b200sp_coo_plan_create(b200sp_handle h, b200sp_stream stream, int64_t num_rows,
+                                     int64_t num_cols, int64_t num_entries,
+                                     const int32_t *row_indices, const int32_t *column_indices,
+                                     b200sp_dtype dtype, int64_t table_bytes, b200sp_coo_plan *out);
+b200sp_status b200sp_coo_plan_destroy(b200sp_handle h, b200sp_coo_plan plan);
+/* columns held in the table, stored entries they serve, table capacity in elements */
+b200sp_status b200sp_coo_plan_info(b200sp_coo_plan plan, int64_t *hot_columns, int64_t *hot_entries,
+                                   int64_t *capacity);
+b200sp_status b200sp_spmv_coo_plan_f32(b200sp_handle h, b200sp_stream stream, b200sp_coo_plan plan,
+                                       const float *values, const float *x, float *y, int accumulate);
+b200sp_status b200sp_spmv_coo_plan_f64(b200sp_handle h, b200sp_stream stream, b200sp_coo_plan plan,
+                                       const double *values, const double *x, double *y, int accumulate);
+
 /* ---- multi-GPU: row-block partitioned operator ---------------------------
  * One process per GPU.  Each rank owns a contiguous block of rows of A and the
  * matching slices of x, b.  Column j of the global matrix is owned by the rank
