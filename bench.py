@@ -485,7 +485,9 @@ def main():
                          "nnz_total": int(nnz_graph), "nnz_max_per_gpu": int(nnz_max),
                          "gathered_bytes_per_gpu": int((n - (xoffs[rank + 1] - xoffs[rank])) * 4), "row_offsets": offs,
                          "x_slice_offsets": xoffs,
-                         "comm": "nvlink-p2p pull from IPC staging" if h.comm_p2p_enabled() else "nccl send/recv"}
+                         "comm": (("nvlink-p2p pull from peers' IPC staging" if os.environ.get("B200SP_GATHER_PULL", "0") not in ("", "0")
+                                   else "nvlink-p2p stores into peers' IPC staging mirrors + local copy-out")
+                                  if h.comm_p2p_enabled() else "nccl send/recv")}
                 del loc, xf, yl
                 torch.cuda.empty_cache()
             except Exception as ex:
