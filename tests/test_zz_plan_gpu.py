@@ -23,4 +23,4 @@ def test_coo_plan_first_hardware_check():
     assert p.returncode == 0 and lines, (p.returncode, p.stderr[-2000:])
     out = json.loads(lines[-1])
     assert out["ok"] and len(out["cases"]) == 16
-    assert out["timing"].get("agree", False), out["timing"]
+    assert out["timing_agree"], out["timing"]

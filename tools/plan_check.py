@@ -81,34 +81,45 @@ def main():
                     h.coo_plan_destroy(plan)
                 out["cases"].append(rec)
                 out["ok"] = out["ok"] and rec.get("ok", False)
-    # timing beside the default kernel (information only)
-    try:
-        C = convert.rmat(scale, 16, seed=42, dtype=torch.float32)
-        x = torch.rand(C.num_cols, dtype=torch.float32, device=dev) + 0.5
-        y = torch.empty(C.num_rows, dtype=torch.float32, device=dev)
-        yp = torch.empty_like(y)
-        plan = h.coo_plan_create(C.num_rows, C.num_cols, C.num_entries, C.row_indices, C.column_indices, capi.F32, 0)
-
-        def timed(fn):
+    # timing beside the default kernel (information only): table sizes at `scale`, then the bench's scale 24
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
             fn()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(10):
-                fn()
-            e1.record()
-            torch.cuda.synchronize()
-            return e0.elapsed_time(e1) / 10
-        t_def = timed(lambda: cusp.multiply(C, x, y))
-        t_plan = timed(lambda: h.spmv_coo_plan(plan, C.values, x, yp))
-        info = h.coo_plan_info(plan)
-        out["timing"] = {"matrix": f"R-MAT scale {scale} ef 16 fp32", "nnz": int(C.num_entries), "default_ms": t_def,
-                         "plan_ms": t_plan, "hot_columns": info["hot_columns"],
-                         "gathers_served_by_table": info["hot_entries"] / C.num_entries,
-                         "agree": bool(torch.allclose(y, yp, rtol=1e-4, atol=1e-4))}
-        h.coo_plan_destroy(plan)
-    except Exception as ex:
-        out["timing"] = {"error": repr(ex)}
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 10
+
+    out["timing"] = []
+    out["timing_agree"] = True
+    for sc, tables in ((scale, (32 << 10, 64 << 10, 128 << 10, 160 << 10)), (24, (128 << 10,))):
+        try:
+            C = convert.rmat(sc, 16, seed=42, dtype=torch.float32)
+            x = torch.rand(C.num_cols, dtype=torch.float32, device=dev) + 0.5
+            y = torch.empty(C.num_rows, dtype=torch.float32, device=dev)
+            yp = torch.empty_like(y)
+            t_def = timed(lambda: cusp.multiply(C, x, y))
+            for tb in tables:
+                plan = h.coo_plan_create(C.num_rows, C.num_cols, C.num_entries, C.row_indices, C.column_indices, capi.F32, tb)
+                try:
+                    t_plan = timed(lambda: h.spmv_coo_plan(plan, C.values, x, yp))
+                    info = h.coo_plan_info(plan)
+                    agree = bool(torch.allclose(y, yp, rtol=1e-4, atol=1e-4))
+                    out["timing_agree"] = out["timing_agree"] and agree
+                    out["timing"].append({"matrix": f"R-MAT scale {sc} ef 16 fp32", "nnz": int(C.num_entries),
+                                          "table_bytes": tb, "default_ms": t_def, "plan_ms": t_plan,
+                                          "hot_columns": info["hot_columns"],
+                                          "gathers_served_by_table": info["hot_entries"] / C.num_entries, "agree": agree})
+                finally:
+                    h.coo_plan_destroy(plan)
+            del C, x, y, yp
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            out["timing"].append({"scale": sc, "error": repr(ex)})
+            out["timing_agree"] = False
     print(json.dumps(out), flush=True)
     return 0 if out["ok"] else 1
 
