@@ -263,6 +263,7 @@ class array1d<T, host_memory> {
   }
 
   size_t size() const { return v_.size(); }
+  size_t capacity() const { return v_.capacity(); }
   bool empty() const { return v_.empty(); }
   void resize(size_t n) { v_.resize(n); }
   void resize(size_t n, const T &value) { v_.resize(n, value); }
@@ -380,6 +381,7 @@ class array1d<T, device_memory> {
   }
 
   size_t size() const { return n_; }
+  size_t capacity() const { return cap_; }
   bool empty() const { return n_ == 0; }
   void reserve(size_t n) {
     if (n <= cap_) return;
@@ -474,7 +476,7 @@ class array1d_view {
   template <typename Array, typename = typename std::enable_if<
                                 std::is_convertible<decltype(std::declval<Array &>().begin()), Iterator>::value &&
                                 !std::is_same<typename std::decay<Array>::type, array1d_view>::value>::type>
-  array1d_view(Array &a) : first_(a.begin()), n_(a.size()), cap_(a.size()) {}
+  array1d_view(Array &a) : first_(a.begin()), n_(a.size()), cap_(a.capacity()) {}  // array1d_view.cu:414-435
 
   // views assign element-wise (like the reference: view = array copies data)
   array1d_view &operator=(const array1d_view &o) = default;
@@ -573,6 +575,18 @@ bool operator==(const array1d_view<It> &a, const array1d<T1, S1> &b) {
 template <typename It1, typename It2>
 bool operator==(const array1d_view<It1> &a, const array1d_view<It2> &b) {
   return detail::arrays_equal(a, b);
+}
+template <typename T1, typename S1, typename It>
+bool operator!=(const array1d<T1, S1> &a, const array1d_view<It> &b) {
+  return !detail::arrays_equal(a, b);
+}
+template <typename T1, typename S1, typename It>
+bool operator!=(const array1d_view<It> &a, const array1d<T1, S1> &b) {
+  return !detail::arrays_equal(a, b);
+}
+template <typename It1, typename It2>
+bool operator!=(const array1d_view<It1> &a, const array1d_view<It2> &b) {
+  return !detail::arrays_equal(a, b);
 }
 
 // ---------------------------------------------------------------------------

@@ -300,3 +300,86 @@ void TestArray2dContainer() {
 }
 static void TestArray2dContainerHost() { TestArray2dContainer<cusp::host_memory>(); }
 TEST_HOST(TestArray2dContainerHost)
+
+// testing/array1d_view.cu:12-564 — views over containers: aliasing, make_array1d_view, re-seating by
+// assignment, resize within the capacity, capacity taken from the container, equality, subarray
+template <typename MemorySpace>
+void TestArray1dViewSemantics() {
+  typedef cusp::array1d<int, MemorySpace> Array;
+  typedef typename Array::iterator Iterator;
+  typedef typename Array::const_iterator ConstIterator;
+  typedef cusp::array1d_view<Iterator> View;
+  {
+    Array A(4);
+    A[0] = 10; A[1] = 20; A[2] = 30; A[3] = 40;
+    View V(A.begin(), A.end());
+    ASSERT_EQUAL(V.size(), (size_t)4);
+    ASSERT_EQUAL(V.capacity(), (size_t)4);
+    ASSERT_EQUAL((int)V[2], 30);
+    ASSERT_TRUE(V.begin() == A.begin() && V.end() == A.end());
+    V[1] = 17;
+    ASSERT_EQUAL((int)A[1], 17);
+    const View CV(A);  // a const view still writes through
+    CV[2] = 33;
+    ASSERT_EQUAL((int)A[2], 33);
+    const Array CA(4, 10);
+    cusp::array1d_view<ConstIterator> R(CA.begin(), CA.end());
+    ASSERT_EQUAL((int)R[3], 10);
+    View M = cusp::make_array1d_view(A.begin(), A.end());
+    ASSERT_TRUE(M.begin() == A.begin());
+    View M2 = cusp::make_array1d_view(A);
+    M2[0] = 5;
+    ASSERT_EQUAL((int)A[0], 5);
+  }
+  {  // assignment re-seats the view (array1d_view.cu:305-343)
+    Array A(4), B(8);
+    View V(A.begin(), A.end());
+    V = View(B);
+    ASSERT_EQUAL(V.size(), (size_t)8);
+    ASSERT_TRUE(V.begin() == B.begin() && V.end() == B.end());
+    const View W = View(V);
+    ASSERT_EQUAL(W.capacity(), (size_t)8);
+  }
+  {  // resize within the capacity (array1d_view.cu:345-383)
+    Array A(4);
+    View V(A.begin(), A.end());
+    V.resize(3);
+    ASSERT_EQUAL(V.size(), (size_t)3);
+    ASSERT_EQUAL(V.capacity(), (size_t)4);
+    ASSERT_TRUE(V.end() == A.begin() + 3);
+    V.resize(4);
+    ASSERT_EQUAL(V.size(), (size_t)4);
+    ASSERT_THROWS(V.resize(5), cusp::not_implemented_exception);
+    View W = V;
+    V.resize(2);
+    ASSERT_EQUAL(W.size(), (size_t)4);
+  }
+  {  // the capacity comes from the container (array1d_view.cu:414-435)
+    Array A(4);
+    A.resize(2);
+    View V = View(A);
+    ASSERT_EQUAL(V.size(), (size_t)2);
+    ASSERT_EQUAL(V.capacity(), (size_t)4);
+  }
+  {  // equality (array1d_view.cu:490-530)
+    Array A(2), B(3);
+    A[0] = 10; A[1] = 20; B[0] = 10; B[1] = 20; B[2] = 30;
+    View V(A), W(B);
+    ASSERT_TRUE(A == V && V == A && V == V && !(A != V) && !(V != A));
+    ASSERT_TRUE(!(V == B) && !(B == V) && !(V == W) && V != B && B != V && V != W);
+    W.resize(2);
+    ASSERT_TRUE(V == W && !(V != W));
+  }
+  {  // subarray (array1d_view.cu:532-564)
+    Array A(4);
+    A[0] = 10; A[1] = 20; A[2] = 30; A[3] = 40;
+    View V = A.subarray(1, 3);
+    ASSERT_EQUAL(V.size(), (size_t)3);
+    ASSERT_TRUE(V.begin() == A.begin() + 1 && V.end() == A.begin() + 4);
+    View W = V.subarray(0, 1);
+    ASSERT_EQUAL(W.size(), (size_t)1);
+    ASSERT_EQUAL((int)W[0], 20);
+  }
+}
+static void TestArray1dViewSemanticsHost() { TestArray1dViewSemantics<cusp::host_memory>(); }
+TEST_HOST(TestArray1dViewSemanticsHost)
