@@ -145,6 +145,11 @@ template <typename I, typename V, typename S>
 typename coo_matrix<I, V, S>::const_view make_coo_matrix_view(const coo_matrix<I, V, S> &m) {
   return typename coo_matrix<I, V, S>::const_view(m);
 }
+// a view of a view is the same view (coo_matrix_view.cu: "construct view from view")
+template <typename A1, typename A2, typename A3, typename I, typename V, typename S>
+coo_matrix_view<A1, A2, A3, I, V, S> make_coo_matrix_view(const coo_matrix_view<A1, A2, A3, I, V, S> &v) {
+  return v;
+}
 
 }  // namespace cusp
 #include "convert.h"

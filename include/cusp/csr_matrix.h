@@ -103,6 +103,11 @@ template <typename I, typename V, typename S>
 typename csr_matrix<I, V, S>::const_view make_csr_matrix_view(const csr_matrix<I, V, S> &m) {
   return typename csr_matrix<I, V, S>::const_view(m);
 }
+// a view of a view is the same view (csr_matrix_view.cu: "construct view from view")
+template <typename A1, typename A2, typename A3, typename I, typename V, typename S>
+csr_matrix_view<A1, A2, A3, I, V, S> make_csr_matrix_view(const csr_matrix_view<A1, A2, A3, I, V, S> &v) {
+  return v;
+}
 
 }  // namespace cusp
 #include "convert.h"

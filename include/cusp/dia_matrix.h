@@ -102,6 +102,11 @@ template <typename I, typename V, typename S>
 typename dia_matrix<I, V, S>::const_view make_dia_matrix_view(const dia_matrix<I, V, S> &m) {
   return typename dia_matrix<I, V, S>::const_view(m);
 }
+// a view of a view is the same view (dia_matrix_view.cu: "construct view from view")
+template <typename A1, typename A2, typename I, typename V, typename S>
+dia_matrix_view<A1, A2, I, V, S> make_dia_matrix_view(const dia_matrix_view<A1, A2, I, V, S> &v) {
+  return v;
+}
 
 }  // namespace cusp
 #include "convert.h"

@@ -109,6 +109,11 @@ template <typename I, typename V, typename S>
 typename ell_matrix<I, V, S>::const_view make_ell_matrix_view(const ell_matrix<I, V, S> &m) {
   return typename ell_matrix<I, V, S>::const_view(m);
 }
+// a view of a view is the same view (ell_matrix_view.cu: "construct view from view")
+template <typename A1, typename A2, typename I, typename V, typename S>
+ell_matrix_view<A1, A2, I, V, S> make_ell_matrix_view(const ell_matrix_view<A1, A2, I, V, S> &v) {
+  return v;
+}
 
 }  // namespace cusp
 #include "convert.h"

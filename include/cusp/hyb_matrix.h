@@ -93,6 +93,11 @@ template <typename I, typename V, typename S>
 typename hyb_matrix<I, V, S>::const_view make_hyb_matrix_view(const hyb_matrix<I, V, S> &m) {
   return typename hyb_matrix<I, V, S>::const_view(m);
 }
+// a view of a view is the same view (hyb_matrix_view.cu: "construct view from view")
+template <typename E, typename C, typename I, typename V, typename S>
+hyb_matrix_view<E, C, I, V, S> make_hyb_matrix_view(const hyb_matrix_view<E, C, I, V, S> &v) {
+  return v;
+}
 
 }  // namespace cusp
 #include "convert.h"

@@ -198,3 +198,77 @@ void TestMatrixRebind() {
   ASSERT_EQUAL(d_hyb.num_entries, h_hyb.num_entries);
 }
 TEST_DEVICE(TestMatrixRebind)
+
+// testing/{csr,coo,ell,dia,hyb}_matrix_view.cu — views alias the container's arrays: built from parts, from a
+// matrix (View V = M; make_*_matrix_view(M)), from another view, from a const matrix; writes go through
+template <class Space>
+void TestMatrixViews() {
+  typedef typename cusp::array1d<int, Space>::iterator IndexIterator;
+  typedef typename cusp::array1d<float, Space>::iterator ValueIterator;
+  typedef cusp::array1d_view<IndexIterator> IndexView;
+  typedef cusp::array1d_view<ValueIterator> ValueView;
+  {  // csr_matrix_view.cu:7-194
+    typedef cusp::csr_matrix<int, float, Space> Matrix;
+    typedef cusp::csr_matrix_view<IndexView, IndexView, ValueView> View;
+    Matrix M(3, 2, 6);
+    View V(3, 2, 6, cusp::make_array1d_view(M.row_offsets.begin(), M.row_offsets.end()),
+           cusp::make_array1d_view(M.column_indices.begin(), M.column_indices.end()),
+           cusp::make_array1d_view(M.values.begin(), M.values.end()));
+    ASSERT_EQUAL(V.num_rows, (size_t)3);
+    ASSERT_EQUAL(V.num_entries, (size_t)6);
+    ASSERT_TRUE(V.row_offsets.begin() == M.row_offsets.begin() && V.values.end() == M.values.end());
+    View W(M);
+    ASSERT_TRUE(W.column_indices.begin() == M.column_indices.begin());
+    View A = M;  // assignment form
+    View B = A;
+    ASSERT_TRUE(B.values.begin() == M.values.begin() && B.num_cols == 2);
+    View P = cusp::make_csr_matrix_view(3, 2, 6, cusp::make_array1d_view(M.row_offsets),
+                                        cusp::make_array1d_view(M.column_indices), cusp::make_array1d_view(M.values));
+    P.row_offsets[0] = 0;
+    P.column_indices[0] = 1;
+    P.values[0] = 2;
+    ASSERT_EQUAL((int)M.column_indices[0], 1);
+    ASSERT_EQUAL((float)M.values[0], 2.0f);
+    View Q = cusp::make_csr_matrix_view(M);
+    View R = cusp::make_csr_matrix_view(Q);
+    ASSERT_TRUE(R.values.begin() == M.values.begin());
+    const Matrix CM(3, 2, 6);
+    ASSERT_EQUAL(cusp::make_csr_matrix_view(CM).num_entries, (size_t)6);
+    ASSERT_TRUE(cusp::make_csr_matrix_view(CM).values.begin() == CM.values.begin());
+  }
+  {  // coo_matrix_view.cu
+    typedef cusp::coo_matrix<int, float, Space> Matrix;
+    typedef cusp::coo_matrix_view<IndexView, IndexView, ValueView> View;
+    Matrix M(3, 2, 6);
+    View V(3, 2, 6, cusp::make_array1d_view(M.row_indices), cusp::make_array1d_view(M.column_indices),
+           cusp::make_array1d_view(M.values));
+    ASSERT_TRUE(V.row_indices.begin() == M.row_indices.begin() && V.num_entries == 6);
+    View W = cusp::make_coo_matrix_view(M);
+    W.values[5] = 9.0f;
+    ASSERT_EQUAL((float)M.values[5], 9.0f);
+    const Matrix CM(3, 2, 6);
+    ASSERT_TRUE(cusp::make_coo_matrix_view(CM).row_indices.begin() == CM.row_indices.begin());
+  }
+  {  // ell_matrix_view.cu / dia_matrix_view.cu / hyb_matrix_view.cu: from a matrix, writes alias
+    cusp::ell_matrix<int, float, Space> E(3, 2, 6, 2, 4);
+    auto EV = cusp::make_ell_matrix_view(E);
+    ASSERT_EQUAL(EV.num_entries, (size_t)6);
+    ASSERT_EQUAL(EV.values.pitch, (size_t)4);
+    EV.values.values[1] = 3.0f;
+    ASSERT_EQUAL((float)E.values.values[1], 3.0f);
+    cusp::dia_matrix<int, float, Space> D(4, 5, 7, 3, 8);
+    auto DV = cusp::make_dia_matrix_view(D);
+    DV.diagonal_offsets[2] = 1;
+    ASSERT_EQUAL((int)D.diagonal_offsets[2], 1);
+    ASSERT_EQUAL(DV.values.pitch, (size_t)8);
+    cusp::hyb_matrix<int, float, Space> H(10, 10, 42, 13, 5, 16);
+    auto HV = cusp::make_hyb_matrix_view(H);
+    ASSERT_EQUAL(HV.num_entries, (size_t)55);
+    HV.coo.values[12] = 4.0f;
+    ASSERT_EQUAL((float)H.coo.values[12], 4.0f);
+    typename cusp::hyb_matrix<int, float, Space>::view HV2(H);
+    ASSERT_EQUAL(HV2.ell.values.pitch, (size_t)16);
+  }
+}
+static void TestMatrixViewsHost() { TestMatrixViews<cusp::host_memory>(); }
+TEST_HOST(TestMatrixViewsHost)
