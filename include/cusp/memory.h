@@ -13,6 +13,26 @@ struct execution_policy {};
 struct host_memory : execution_policy<host_memory> {};
 struct device_memory : execution_policy<device_memory> {};
 
+// compatible with every space (cusp/memory.h: any_memory) and the combination rule used by algorithms
+// that mix operands (cusp/memory.h: minimum_space<T1,T2,T3>; mixing host and device has no type)
+struct any_memory : execution_policy<any_memory> {};
+namespace detail {
+template <typename T1, typename T2>
+struct minimum_space2 {};
+template <typename T>
+struct minimum_space2<T, T> { typedef T type; };
+template <typename T>
+struct minimum_space2<T, any_memory> { typedef T type; };
+template <typename T>
+struct minimum_space2<any_memory, T> { typedef T type; };
+template <>
+struct minimum_space2<any_memory, any_memory> { typedef any_memory type; };
+}  // namespace detail
+template <typename T1, typename T2 = any_memory, typename T3 = any_memory>
+struct minimum_space {
+  typedef typename detail::minimum_space2<typename detail::minimum_space2<T1, T2>::type, T3>::type type;
+};
+
 namespace detail {
 // Dispatch on the derived policy, as thrust/cusp do (cusp/detail/multiply.inl:27-46: the public
 // entry point calls `multiply(derived_cast(exec), ...)` unqualified): a user policy

@@ -272,3 +272,41 @@ void TestMatrixViews() {
 }
 static void TestMatrixViewsHost() { TestMatrixViews<cusp::host_memory>(); }
 TEST_HOST(TestMatrixViewsHost)
+
+// testing/format.cu and testing/memory.cu — compile-time traits
+void TestFormatAndMemoryTraits() {
+  typedef cusp::array1d<float, cusp::host_memory> A1D;
+  typedef cusp::array2d<float, cusp::host_memory> A2D;
+  typedef cusp::coo_matrix<int, float, cusp::host_memory> COO;
+  typedef cusp::csr_matrix<int, float, cusp::device_memory> CSR;
+  typedef cusp::dia_matrix<int, float, cusp::host_memory> DIA;
+  typedef cusp::ell_matrix<int, float, cusp::device_memory> ELL;
+  typedef cusp::hyb_matrix<int, float, cusp::host_memory> HYB;
+  static_assert(std::is_same<A1D::format, cusp::array1d_format>::value &&
+                    !std::is_convertible<A1D::format, cusp::sparse_format>::value &&
+                    std::is_convertible<A1D::format, cusp::dense_format>::value &&
+                    std::is_convertible<A1D::format, cusp::known_format>::value, "array1d format");
+  static_assert(std::is_same<A2D::format, cusp::array2d_format>::value &&
+                    std::is_convertible<A2D::format, cusp::dense_format>::value, "array2d format");
+  static_assert(std::is_same<COO::format, cusp::coo_format>::value && std::is_same<CSR::format, cusp::csr_format>::value &&
+                    std::is_same<DIA::format, cusp::dia_format>::value && std::is_same<ELL::format, cusp::ell_format>::value &&
+                    std::is_same<HYB::format, cusp::hyb_format>::value, "sparse formats");
+  static_assert(std::is_convertible<HYB::format, cusp::sparse_format>::value &&
+                    !std::is_convertible<HYB::format, cusp::dense_format>::value &&
+                    std::is_convertible<ELL::format, cusp::known_format>::value, "sparse format hierarchy");
+  static_assert(std::is_same<CSR::memory_space, cusp::device_memory>::value &&
+                    std::is_same<CSR::view::memory_space, cusp::device_memory>::value, "memory_space of containers and views");
+  typedef cusp::host_memory H;
+  typedef cusp::device_memory D;
+  typedef cusp::any_memory A;
+  static_assert(std::is_same<cusp::minimum_space<H, H>::type, H>::value && std::is_same<cusp::minimum_space<H, A>::type, H>::value &&
+                    std::is_same<cusp::minimum_space<A, H>::type, H>::value && std::is_same<cusp::minimum_space<D, D>::type, D>::value &&
+                    std::is_same<cusp::minimum_space<D, A>::type, D>::value && std::is_same<cusp::minimum_space<A, D>::type, D>::value &&
+                    std::is_same<cusp::minimum_space<A, A>::type, A>::value, "minimum_space of two");
+  static_assert(std::is_same<cusp::minimum_space<H, H, A>::type, H>::value && std::is_same<cusp::minimum_space<A, H, A>::type, H>::value &&
+                    std::is_same<cusp::minimum_space<D, A, A>::type, D>::value && std::is_same<cusp::minimum_space<A, A, A>::type, A>::value &&
+                    std::is_same<cusp::minimum_space<H, A, H>::type, H>::value && std::is_same<cusp::minimum_space<A, D, D>::type, D>::value,
+                "minimum_space of three");
+  ASSERT_TRUE(true);
+}
+TEST_HOST(TestFormatAndMemoryTraits)
