@@ -179,3 +179,30 @@ void TestMatrixMarketErrors() {  // matrix_market.inl:80-98, 203-227, 271-279
   ASSERT_THROWS(cusp::io::read_matrix_market_file(coo, "/nonexistent/dir/file.mtx"), cusp::io_exception);
 }
 TEST_HOST(TestMatrixMarketErrors)
+
+// cusp::print (cusp/detail/print.inl:33-140): same text as the reference for arrays and every sparse format
+#include <cusp/print.h>
+void TestPrint() {
+  cusp::array1d<float, cusp::host_memory> a(2);
+  a[0] = 1.5f;
+  a[1] = -2.0f;
+  std::ostringstream s1;
+  cusp::print(a, s1);
+  // " " + setw(8) of "(" + value + ")": eight blanks before the parenthesis (print.inl:36)
+  ASSERT_EQUAL(s1.str(), std::string("array1d <2>\n        (1.5)\n        (-2)\n"));
+  cusp::array2d<float, cusp::host_memory> D(2, 2, 0.0f);
+  D(0, 1) = 3.0f;
+  D(1, 0) = 4.25f;
+  cusp::csr_matrix<int, float, cusp::host_memory> A(D);
+  std::ostringstream s2, s3;
+  cusp::print(A, s2);
+  cusp::coo_matrix<int, float, cusp::host_memory> C(A);
+  cusp::print(C, s3);
+  ASSERT_EQUAL(s2.str(), s3.str());  // every sparse format prints through its COO image
+  ASSERT_TRUE(s2.str().find("sparse matrix <2, 2> with 2 entries\n") == 0);
+  ASSERT_TRUE(s2.str().find("(4.25)") != std::string::npos);
+  std::ostringstream s4;
+  cusp::print(D, s4);
+  ASSERT_TRUE(s4.str().find("array2d <2, 2>\n") == 0);
+}
+TEST_HOST(TestPrint)

@@ -76,3 +76,37 @@ def test_cpp_full_suite_on_gpu():
     passed, failed, skipped = _summary(out)
     assert rc == 0 and failed == 0 and skipped == 0, out[-6000:]
     assert passed >= 100
+
+
+REFERENCE_EXAMPLES = [  # the reference's own example programs that touch the hot path, compiled UNMODIFIED
+    "examples/Views/array1d.cu", "examples/Views/array2d_raw.cu", "examples/Views/cg_raw.cu", "examples/Views/csr_raw.cu",
+    "examples/Views/csr_view.cu", "examples/Solvers/cg.cu", "examples/Solvers/bicgstab.cu", "examples/Solvers/cr.cu",
+    "examples/MatrixFormats/coo.cu", "examples/MatrixFormats/csr.cu", "examples/MatrixFormats/dia.cu",
+    "examples/MatrixFormats/ell.cu", "examples/MatrixFormats/hyb.cu", "examples/Gallery/poisson.cu",
+    "examples/InputOutput/matrix_market.cu", "examples/Preconditioners/diagonal.cu",
+]
+
+
+def test_reference_examples_compile_unmodified_against_the_drop_in_headers(tmp_path):
+    """drop-in evidence: the reference's example sources (read where they lie under /root/reference, nothing copied)
+    compile with nvcc for sm_100a against include/cusp — Thrust's device_ptr, cusp::print, views over raw cudaMalloc
+    pointers, the solvers, MatrixMarket I/O included.  Known not to compile: Solvers/gmres.cu and LinearOperator/stencil.cu
+    (they run Thrust algorithms / raw_pointer_cast on the containers' own iterators), Gallery/diffusion.cu (off-path header)."""
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "examples")):
+        pytest.skip("reference sources not present (GPU box)")
+    import shutil
+    from concurrent.futures import ThreadPoolExecutor
+    if not shutil.which("nvcc"):
+        pytest.skip("nvcc not available")
+
+    def compile_one(rel):
+        obj = tmp_path / (rel.replace("/", "_") + ".o")
+        p = subprocess.run(["nvcc", "-std=c++17", "-x", "cu", "-w", "-c", "-gencode", "arch=compute_100a,code=sm_100a",
+                            "-I", os.path.join(ROOT, "include"), "-o", str(obj), os.path.join(ref, rel)],
+                           capture_output=True, text=True, timeout=600)
+        return rel, p.returncode, p.stderr[-600:]
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        results = list(ex.map(compile_one, REFERENCE_EXAMPLES))
+    bad = [(r, err) for r, rc, err in results if rc != 0]
+    assert not bad, bad
