@@ -20,6 +20,7 @@
 #if !defined(CUSP_B200_NO_THRUST) && defined(__has_include)
 #if __has_include(<thrust/device_ptr.h>) && defined(__CUDACC__)
 #include <thrust/device_ptr.h>
+#include <thrust/device_reference.h>
 #define CUSP_B200_HAVE_THRUST 1
 #endif
 #endif
@@ -30,6 +31,25 @@ template <typename T, typename MemorySpace>
 class array1d;
 template <typename Iterator>
 class array1d_view;
+
+#ifdef CUSP_B200_HAVE_THRUST
+// Compiled by nvcc with Thrust at hand (what a user of the reference has): device arrays iterate with
+// thrust::device_ptr and hand out thrust::device_reference, exactly like the reference's containers, so
+// user code that runs Thrust algorithms on them (thrust::fill(x.begin(), x.end(), v)) or takes
+// thrust::raw_pointer_cast(&x[0]) compiles unchanged (examples/Solvers/gmres.cu, LinearOperator/stencil.cu).
+template <typename T>
+using device_ptr = thrust::device_ptr<T>;
+using thrust::device_pointer_cast;
+using thrust::raw_pointer_cast;
+namespace detail {
+template <typename T>
+using device_reference = thrust::device_reference<T>;
+template <typename T>
+device_reference<T> make_device_reference(T *p) {
+  return device_reference<T>(thrust::device_ptr<T>(p));
+}
+}  // namespace detail
+#else
 template <typename T>
 class device_ptr;
 
@@ -110,6 +130,14 @@ template <typename T>
 device_ptr<T> device_reference<T>::operator&() const {
   return device_ptr<T>(p_);
 }
+template <typename T>
+device_reference<T> make_device_reference(T *p) {
+  return device_reference<T>(p);
+}
+}  // namespace detail
+#endif  // CUSP_B200_HAVE_THRUST
+
+namespace detail {
 
 // iterator -> (value type, memory space, raw pointer).  Raw pointers are host
 // iterators, exactly like in the reference (thrust's host system).
@@ -129,15 +157,8 @@ struct iter_traits<cusp::device_ptr<T>> {
   typedef device_memory memory_space;
   static T *raw(const cusp::device_ptr<T> &p) { return p.get(); }
 };
-#ifdef CUSP_B200_HAVE_THRUST
-template <typename T>
-struct iter_traits<thrust::device_ptr<T>> {
-  typedef typename std::remove_const<T>::type value_type;
-  typedef T element_type;
-  typedef device_memory memory_space;
-  static T *raw(const thrust::device_ptr<T> &p) { return thrust::raw_pointer_cast(p); }
-};
-#endif
+// (with Thrust, cusp::device_ptr IS thrust::device_ptr: the specialization above covers views over
+//  thrust::device_ptr built from raw cudaMalloc pointers, examples/Views/cg_raw.cu)
 
 template <typename Space1, typename Space2>
 struct copy_kind;
@@ -311,6 +332,11 @@ class array1d<T, device_memory> {
   typedef device_ptr<const T> const_iterator;
   typedef device_ptr<T> pointer;
   typedef detail::device_reference<T> reference;
+#ifdef CUSP_B200_HAVE_THRUST
+  typedef detail::device_reference<const T> const_reference;  // &x[0] of a const array is a device_ptr<const T>
+#else
+  typedef T const_reference;
+#endif
   typedef size_t size_type;
   typedef array1d container;
   typedef array1d_view<iterator> view;
@@ -416,8 +442,12 @@ class array1d<T, device_memory> {
     std::swap(n_, o.n_);
     std::swap(cap_, o.cap_);
   }
-  reference operator[](size_t i) { return reference(p_ + i); }
+  reference operator[](size_t i) { return detail::make_device_reference<T>(p_ + i); }
+#ifdef CUSP_B200_HAVE_THRUST
+  const_reference operator[](size_t i) const { return detail::make_device_reference<const T>(p_ + i); }
+#else
   T operator[](size_t i) const { return (T)detail::device_reference<const T>(p_ + i); }
+#endif
   pointer data() { return pointer(p_); }
   device_ptr<const T> data() const { return device_ptr<const T>(p_); }
   iterator begin() { return iterator(p_); }

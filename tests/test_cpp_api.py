@@ -84,14 +84,15 @@ REFERENCE_EXAMPLES = [  # the reference's own example programs that touch the ho
     "examples/MatrixFormats/coo.cu", "examples/MatrixFormats/csr.cu", "examples/MatrixFormats/dia.cu",
     "examples/MatrixFormats/ell.cu", "examples/MatrixFormats/hyb.cu", "examples/Gallery/poisson.cu",
     "examples/InputOutput/matrix_market.cu", "examples/Preconditioners/diagonal.cu",
+    "examples/Solvers/gmres.cu", "examples/LinearOperator/stencil.cu",  # thrust::fill / raw_pointer_cast on the containers
 ]
 
 
 def test_reference_examples_compile_unmodified_against_the_drop_in_headers(tmp_path):
     """drop-in evidence: the reference's example sources (read where they lie under /root/reference, nothing copied)
     compile with nvcc for sm_100a against include/cusp — Thrust's device_ptr, cusp::print, views over raw cudaMalloc
-    pointers, the solvers, MatrixMarket I/O included.  Known not to compile: Solvers/gmres.cu and LinearOperator/stencil.cu
-    (they run Thrust algorithms / raw_pointer_cast on the containers' own iterators), Gallery/diffusion.cu (off-path header)."""
+    pointers, Thrust algorithms and thrust::raw_pointer_cast on the containers' iterators (under nvcc they ARE
+    thrust::device_ptr), the solvers, MatrixMarket I/O included.  Not covered: Gallery/diffusion.cu (off-path header)."""
     ref = "/root/reference"
     if not os.path.isdir(os.path.join(ref, "examples")):
         pytest.skip("reference sources not present (GPU box)")
@@ -110,3 +111,33 @@ def test_reference_examples_compile_unmodified_against_the_drop_in_headers(tmp_p
         results = list(ex.map(compile_one, REFERENCE_EXAMPLES))
     bad = [(r, err) for r, rc, err in results if rc != 0]
     assert not bad, bad
+
+
+def test_cpp_suite_builds_with_nvcc_thrust_iterators(tmp_path):
+    """under nvcc the device containers iterate with thrust::device_ptr / thrust::device_reference (cusp/array1d.h):
+    the restated test programs must compile in that mode too (every device instantiation), and their host_memory half,
+    linked from the nvcc objects, must pass"""
+    import shutil
+    from concurrent.futures import ThreadPoolExecutor
+    if not shutil.which("nvcc"):
+        pytest.skip("nvcc not available")
+    srcs = ["main.cpp", "test_views.cpp", "test_containers.cpp", "test_multiply.cpp", "test_krylov.cpp", "test_blas.cpp",
+            "test_dispatch.cpp"]
+
+    def compile_one(name):
+        obj = tmp_path / (name + ".o")
+        p = subprocess.run(["nvcc", "-std=c++17", "-x", "cu", "-w", "-c", "-fmad=false", "-Xcompiler", "-ffp-contract=off",
+                            "-gencode", "arch=compute_100a,code=sm_100a", "-I", os.path.join(ROOT, "include"), "-I", CPP,
+                            "-o", str(obj), os.path.join(CPP, name)], capture_output=True, text=True, timeout=900)
+        return name, p.returncode, p.stderr[-800:], str(obj)
+    with ThreadPoolExecutor(max_workers=7) as ex:
+        results = list(ex.map(compile_one, srcs))
+    bad = [(n, err) for n, rc, err, _ in results if rc != 0]
+    assert not bad, bad
+    exe = tmp_path / "cusp_api_tests_nvcc"
+    libdir = os.path.join(ROOT, "cusp_autotuned_b200")
+    subprocess.check_call(["nvcc", "-o", str(exe)] + [o for *_, o in results] +
+                          ["-L", libdir, "-lb200sp", "-Xlinker", "-rpath," + libdir], stderr=subprocess.DEVNULL)
+    p = subprocess.run([str(exe), "--host-only"], capture_output=True, text=True, timeout=300)
+    passed, failed, skipped = _summary(p.stdout)
+    assert p.returncode == 0 and failed == 0 and passed >= 40, p.stdout[-3000:]
