@@ -62,7 +62,7 @@ def test_public_headers_are_self_contained(tmp_path):
                "cusp/linear_operator.h", "cusp/gallery/poisson.h", "cusp/gallery/random.h", "cusp/ktt/ktt.h",
                "cusp/ktt/ellr_matrix.h", "cusp/ktt/matrix_generation.h", "cusp/functional.h", "cusp/exception.h",
                "cusp/krylov/bicgstab.h", "cusp/krylov/cr.h", "cusp/krylov/gmres.h", "cusp/precond/diagonal.h",
-               "cusp/io/matrix_market.h"]
+               "cusp/io/matrix_market.h", "cusp/print.h", "cusp/complex.h"]
     for h in headers:
         src = tmp_path / "tu.cpp"
         src.write_text(f"#include <{h}>\nint main() {{ return 0; }}\n")
