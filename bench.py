@@ -545,25 +545,6 @@ def main():
         except Exception as ex:
             ref_gpu = {"error": repr(ex)}
 
-    # ---- experimental inspector / executor COO path: first hardware numbers (separate process, information only) ----
-    plan_info = None
-    if not args.quick and world == 1 and rank == 0:
-        try:
-            import subprocess
-            p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "plan_check.py"), "22"], capture_output=True,
-                               text=True, timeout=420)
-            last = [ln for ln in p.stdout.strip().splitlines() if ln.startswith("{")]
-            if not last:
-                plan_info = {"error": f"rc={p.returncode}: {(p.stderr or p.stdout)[-300:]}"}
-            else:
-                full = json.loads(last[-1])
-                plan_info = {"status": "experimental, not used by any product path (DESIGN.md 7b)", "parity_ok": full.get("ok"),
-                             "parity_cases": len(full.get("cases", [])),
-                             "failed_cases": [c for c in full.get("cases", []) if not c.get("ok")][:4],
-                             "timing": full.get("timing")}
-        except Exception as ex:
-            plan_info = {"error": repr(ex)}
-
     clocks = sampler.stop()
     if rank == 0:
         line = {
@@ -576,7 +557,7 @@ def main():
                        "parallelism": f"rowblock{world}", "api": "b200sp_spmv / b200sp_spmv_dist (C ABI)"},
             "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "cpu_baseline": cpu, "formats": formats, "cg": cg, "graph": graph,
-            "reference_cuda_kernel": ref_gpu, "experimental_coo_plan": plan_info,
+            "reference_cuda_kernel": ref_gpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -114,7 +114,7 @@ F32, F64 = 0, 1
 K_CSR_VECTOR, K_CSR_STREAM, K_CSR_RING, K_CSR_BALANCED = 1, 2, 3, 4
 K_ELL_LDG, K_ELL_BULK = 1, 2
 K_DIA_LDG, K_DIA_BULK = 1, 2
-K_COO_SEGSCAN, K_COO_RING = 1, 2
+K_COO_SEGSCAN, K_COO_RING, K_COO_WARP = 1, 2, 3
 ST_OK, ST_INVALID_INPUT, ST_CUDA_ERROR, ST_NOT_IMPLEMENTED, ST_ALLOC_FAILED, ST_COMM_ERROR = range(6)
 
 # every symbol include/b200sp.h declares (checked by tests/test_abi.py)
@@ -134,7 +134,8 @@ EXPORTED_SYMBOLS = (
                                        "amax") for s in _SFX]
     + [f"b200sp_poisson_{f}_{s}" for f in ("dia", "ell", "csr") for s in _SFX]
     + [f"b200sp_spmm_csr_{s}" for s in _SFX]
-    + ["b200sp_coo_plan_create", "b200sp_coo_plan_destroy", "b200sp_coo_plan_info"]
+    + ["b200sp_coo_plan_create", "b200sp_coo_plan_destroy", "b200sp_coo_plan_info", "b200sp_coo_plan_attach",
+       "b200sp_coo_plan_detach"]
     + [f"b200sp_spmv_coo_plan_{s}" for s in _SFX]
 )
 
@@ -238,7 +239,7 @@ class Handle:
                      _ptr(Ax), C.c_int64(k), _ptr(X), C.c_int64(ldx), _ptr(Y), C.c_int64(ldy),
                      C.c_int(int(accumulate))))
 
-    # -- experimental: inspector / executor COO product (hot columns of x in shared memory) -----------
+    # -- inspector / executor COO product (hot columns of x in shared memory) -------------------------
     def coo_plan_create(self, rows, cols, nnz, Ai, Aj, dtype: int, table_bytes: int = 0):
         plan = C.c_void_p()
         self.check(self.lib.b200sp_coo_plan_create(self._h, _stream(), C.c_int64(rows), C.c_int64(cols), C.c_int64(nnz),
@@ -254,9 +255,16 @@ class Handle:
         self.check(self.lib.b200sp_coo_plan_info(plan, C.byref(a), C.byref(b), C.byref(c)))
         return {"hot_columns": a.value, "hot_entries": b.value, "capacity": c.value}
 
-    def spmv_coo_plan(self, plan, Ax, x, y, accumulate=False):
+    def coo_plan_attach(self, plan):
+        self.check(self.lib.b200sp_coo_plan_attach(self._h, plan))
+
+    def coo_plan_detach(self, plan):
+        self.check(self.lib.b200sp_coo_plan_detach(self._h, plan))
+
+    def spmv_coo_plan(self, plan, Ax, x, y, accumulate=False, cfg: Optional[Cfg] = None):
         f = getattr(self.lib, "b200sp_spmv_coo_plan_" + _sfx(y.dtype))
-        self.check(f(self._h, _stream(), plan, _ptr(Ax), _ptr(x), _ptr(y), C.c_int(int(accumulate))))
+        self.check(f(self._h, _stream(), plan, _ptr(Ax), _ptr(x), _ptr(y), C.c_int(int(accumulate)),
+                     C.byref(cfg) if cfg else None))
 
     def spmv_ell(self, rows, cols, K, pitch, cidx, vals, x, y, accumulate=False, cfg: Optional[Cfg] = None):
         f = getattr(self.lib, "b200sp_spmv_ell_" + _sfx(y.dtype))

@@ -90,7 +90,7 @@ static void push(std::vector<b200sp_cfg> &v, int kernel, int block, int tpr, int
   v.push_back(c);
 }
 
-static std::vector<b200sp_cfg> cfg_space_vec(b200sp_format f, b200sp_dtype) {
+static std::vector<b200sp_cfg> cfg_space_vec(b200sp_format f, b200sp_dtype dt) {
   std::vector<b200sp_cfg> v;
   const int blocks[3] = {128, 256, 512};
   switch (f) {
@@ -138,6 +138,12 @@ static std::vector<b200sp_cfg> cfg_space_vec(b200sp_format f, b200sp_dtype) {
           for (int st : {2, 3})
             for (int cps : {2, 4, 6}) push(v, B200SP_K_COO_RING, p[0], 0, p[1], st, cps);
       }
+      for (int vw : {4, 8})  // K_COO_WARP: entries per lane per load x units per warp tile
+        for (int u : {1, 2, 4}) {
+          if (dt == B200SP_F64 && vw == 8 && u == 4) continue;
+          push(v, B200SP_K_COO_WARP, 256, 0, u, 0, 0);
+          v.back().vector_width = vw;
+        }
       break;
   }
   return v;

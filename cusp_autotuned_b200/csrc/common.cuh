@@ -92,6 +92,7 @@ struct b200sp_context {
   // COO gather-order probe per (column_indices pointer, element size, nnz): 1 = ring kernel
   std::map<CsrKey, int> coo_gather_order;
   std::vector<void *> tune_events;  // cudaEvent_t pair
+  std::vector<void *> coo_plans;    // attached b200sp_coo_plan (spmv_coo_plan.cu)
 
   // multi-GPU
   void *nccl_comm = nullptr;

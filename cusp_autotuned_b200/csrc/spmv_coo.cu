@@ -27,34 +27,9 @@
 //   Summation order is fixed by (nnz, BLOCK, VPT) -> bit-reproducible.
 //
 // Algorithmic bytes: nnz*(8+sizeof(T)) + cols*sizeof(T) + rows*sizeof(T).
-#include "common.cuh"
+#include "coo.cuh"
 
 namespace b200sp {
-
-template <typename T>
-struct CooCarry {
-  int head_row;  // row continued from the previous tile that ends here, or -1
-  int tail_row;  // row left open at the end of this tile, or -1
-  int leader;    // tail_row began inside this tile
-  int pad;
-  T head_val;
-  T tail_val;
-};
-
-template <typename T>
-struct CooArgs {
-  i64 rows, cols, nnz;
-  const int *Ai;
-  const int *Aj;
-  const T *Ax;
-  const T *x;
-  T *y;
-  int accumulate;
-  CooCarry<T> *carry;
-  // CSR source (K_CSR_BALANCED): row indices are rebuilt per tile from row_offsets
-  const int *Ap;
-  const int *tile_first_row;  // row that contains entry t*TILE, for every tile t
-};
 
 // first row of every nnz tile of a CSR matrix: tile t starts at entry t*TILE, which lies in
 // the row r with Ap[r] <= t*TILE < Ap[r+1].  Replaces gpu_compute_row_starts
@@ -242,28 +217,81 @@ __global__ void __launch_bounds__(BLOCK) coo_segscan_kernel(CooArgs<T> a) {
   }
 }
 
-// one thread per tile: leaders walk their carry chain in tile order
+// Second pass: one thread per tile.  A tile whose open tail row began inside it ("leader") owns
+// that row's total: its tail, then the tails of the following tiles that lie entirely inside the
+// row, then the head of the tile in which the row ends.  Most chains are one record long and are
+// finished by the leader's own lane; a chain that goes on (a hub row spanning many tiles) is
+// walked by the whole warp, 32 records per step, with a fixed shuffle tree per step — the order
+// of additions depends only on the tile shape, never on timing.
 template <typename T>
 __global__ void coo_fixup_kernel(i64 num_tiles, const CooCarry<T> *carry, T *y, int accumulate) {
+  constexpr unsigned FULL = 0xffffffffu;
   const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= num_tiles) return;
-  const CooCarry<T> me = carry[t];
-  if (me.tail_row < 0 || !me.leader) return;
-  const int row = me.tail_row;
-  T total = me.tail_val;
-  for (i64 u = t + 1; u < num_tiles; ++u) {
-    const CooCarry<T> nx = carry[u];
-    if (nx.head_row == row) {
-      total = total + nx.head_val;
-      break;
-    } else if (nx.tail_row == row && !nx.leader) {
-      total = total + nx.tail_val;
-    } else {
-      break;
+  const int lane = threadIdx.x & 31;
+  bool leader = false, walk = false;
+  int row = -1;
+  T total = T(0);
+  if (t < num_tiles) {
+    const CooCarry<T> me = carry[t];
+    if (me.tail_row >= 0 && me.leader) {
+      leader = true;
+      row = me.tail_row;
+      total = me.tail_val;
+      if (t + 1 < num_tiles) {
+        const CooCarry<T> nx = carry[t + 1];
+        if (nx.head_row == row) {
+          total = total + nx.head_val;
+        } else if (nx.tail_row == row && !nx.leader) {
+          total = total + nx.tail_val;
+          walk = true;
+        }
+      }
     }
   }
-  y[row] = accumulate ? y[row] + total : total;  // !accumulate: y[row] still holds the memset zero
+  unsigned walkers = __ballot_sync(FULL, walk);
+  while (walkers) {
+    const int src = __ffs(walkers) - 1;
+    walkers &= walkers - 1;
+    const i64 t0 = __shfl_sync(FULL, t, src);
+    const int wrow = __shfl_sync(FULL, row, src);
+    T wtot = __shfl_sync(FULL, total, src);
+    for (i64 base = t0 + 2;; base += 32) {
+      const i64 u = base + lane;
+      int cls = 2;  // 0: tile inside the row, 1: the row ends in this tile, 2: not part of the chain
+      T val = T(0);
+      if (u < num_tiles) {
+        const CooCarry<T> nx = carry[u];
+        if (nx.head_row == wrow) {
+          cls = 1;
+          val = nx.head_val;
+        } else if (nx.tail_row == wrow && !nx.leader) {
+          cls = 0;
+          val = nx.tail_val;
+        }
+      }
+      const unsigned stop = __ballot_sync(FULL, cls != 0);
+      const int first = stop ? __ffs(stop) - 1 : 32;
+      T contrib = (lane < first || (lane == first && cls == 1)) ? val : T(0);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) contrib = contrib + __shfl_xor_sync(FULL, contrib, o);
+      wtot = wtot + contrib;
+      if (stop) break;
+    }
+    if (lane == src) total = wtot;
+  }
+  if (leader) y[row] = accumulate ? y[row] + total : total;  // !accumulate: y[row] still holds the memset zero
 }
+
+template <typename T>
+b200sp_status launch_coo_fixup(b200sp_handle h, cudaStream_t st, i64 tiles, const CooCarry<T> *carry, T *y,
+                               int accumulate) {
+  coo_fixup_kernel<T><<<(unsigned)ceil_div(tiles, 256), 256, 0, st>>>(tiles, carry, y, accumulate);
+  B200SP_LAUNCH_CHECK(h, "coo_fixup_kernel");
+  return B200SP_OK;
+}
+template b200sp_status launch_coo_fixup<float>(b200sp_handle, cudaStream_t, i64, const CooCarry<float> *, float *, int);
+template b200sp_status launch_coo_fixup<double>(b200sp_handle, cudaStream_t, i64, const CooCarry<double> *, double *,
+                                                int);
 
 // ---------------------------------------------------------------------------
 // K_COO_RING — the same tiles and the same summation order as K_COO_SEGSCAN, but the three
@@ -488,9 +516,7 @@ static b200sp_status launch_coo_ring(b200sp_handle h, cudaStream_t st, CooArgs<T
   if (grid > tiles) grid = tiles;
   kern<<<(unsigned)grid, BLOCK + 32, smem, st>>>(a, stages, tiles);
   B200SP_LAUNCH_CHECK(h, "coo_ring_kernel");
-  coo_fixup_kernel<T><<<(unsigned)ceil_div(tiles, 256), 256, 0, st>>>(tiles, a.carry, a.y, a.accumulate);
-  B200SP_LAUNCH_CHECK(h, "coo_fixup_kernel");
-  return B200SP_OK;
+  return launch_coo_fixup<T>(h, st, tiles, a.carry, a.y, a.accumulate);
 }
 
 template <typename T, int BLOCK, int VPT>
@@ -502,9 +528,7 @@ static b200sp_status launch_coo(b200sp_handle h, cudaStream_t st, CooArgs<T> a) 
   a.carry = reinterpret_cast<CooCarry<T> *>(h->scratch);
   coo_segscan_kernel<T, BLOCK, VPT, false><<<(unsigned)tiles, BLOCK, 0, st>>>(a);
   B200SP_LAUNCH_CHECK(h, "coo_segscan_kernel");
-  coo_fixup_kernel<T><<<(unsigned)ceil_div(tiles, 256), 256, 0, st>>>(tiles, a.carry, a.y, a.accumulate);
-  B200SP_LAUNCH_CHECK(h, "coo_fixup_kernel");
-  return B200SP_OK;
+  return launch_coo_fixup<T>(h, st, tiles, a.carry, a.y, a.accumulate);
 }
 
 // CSR through the nnz-balanced segmented scan (K_CSR_BALANCED)
@@ -522,9 +546,7 @@ static b200sp_status launch_csr_balanced(b200sp_handle h, cudaStream_t st, CooAr
   B200SP_LAUNCH_CHECK(h, "csr_tile_rows_kernel");
   coo_segscan_kernel<T, BLOCK, VPT, true><<<(unsigned)tiles, BLOCK, 0, st>>>(a);
   B200SP_LAUNCH_CHECK(h, "coo_segscan_kernel<csr>");
-  coo_fixup_kernel<T><<<(unsigned)ceil_div(tiles, 256), 256, 0, st>>>(tiles, a.carry, a.y, a.accumulate);
-  B200SP_LAUNCH_CHECK(h, "coo_fixup_kernel");
-  return B200SP_OK;
+  return launch_coo_fixup<T>(h, st, tiles, a.carry, a.y, a.accumulate);
 }
 
 // entry used by spmv_csr (spmv_csr.cu) for cfg.kernel == B200SP_K_CSR_BALANCED
@@ -631,6 +653,13 @@ static void coo_defaults(b200sp_cfg &c, b200sp_handle h, cudaStream_t st, i64 nn
   }
 }
 
+// spmv_coo_plan.cu
+b200sp_coo_plan coo_attached_plan(b200sp_handle h, i64 rows, i64 cols, i64 nnz, const int *Ai, const int *Aj,
+                                  size_t elem);
+template <typename T>
+b200sp_status spmv_coo_attached(b200sp_handle h, cudaStream_t st, b200sp_coo_plan p, const T *Ax, const T *x, T *y,
+                                int accumulate, const b200sp_cfg *cfg);
+
 template <typename T>
 b200sp_status spmv_coo(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64 nnz, const int *Ai,
                        const int *Aj, const T *Ax, const T *x, T *y, int accumulate,
@@ -645,11 +674,16 @@ b200sp_status spmv_coo(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64
   B200SP_REQUIRE(h, Ai && Aj && Ax && x, "coo: null pointer");
   B200SP_REQUIRE(h, cols > 0, "coo: num_cols == 0 with stored entries");
 
+  if (!h->coo_plans.empty() && (!cfg || cfg->kernel == 0 || cfg->kernel == B200SP_K_COO_WARP)) {
+    // an attached plan for exactly these arrays (b200sp_coo_plan_attach): hot columns of x from shared memory
+    if (b200sp_coo_plan p = coo_attached_plan(h, rows, cols, nnz, Ai, Aj, sizeof(T)))
+      return spmv_coo_attached<T>(h, st, p, Ax, x, y, accumulate, cfg);
+  }
   b200sp_cfg c = cfg ? *cfg : b200sp_cfg{};
   const bool tma_ok = aligned16(Ai) && aligned16(Aj) && aligned16(Ax);
   coo_defaults(c, h, st, nnz, Aj, sizeof(T), tma_ok);
   if (c.kernel == B200SP_K_COO_RING && !tma_ok) c.kernel = B200SP_K_COO_SEGSCAN;  // bulk copies need 16-byte bases
-  if (c.kernel != B200SP_K_COO_SEGSCAN && c.kernel != B200SP_K_COO_RING)
+  if (c.kernel != B200SP_K_COO_SEGSCAN && c.kernel != B200SP_K_COO_RING && c.kernel != B200SP_K_COO_WARP)
     return set_error(h, B200SP_INVALID_INPUT, "coo: unknown kernel id %d", c.kernel);
 
   CooArgs<T> a;
@@ -659,6 +693,15 @@ b200sp_status spmv_coo(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64
   a.carry = nullptr;
   a.Ap = nullptr;
   a.tile_first_row = nullptr;
+  if (c.kernel == B200SP_K_COO_WARP) {
+    // vector loads need 16- / 32-byte aligned bases; otherwise the scalar-load kernel gives the same sums
+    const uintptr_t m = (uintptr_t)(c.vector_width == 8 ? 31 : 15);
+    if ((((uintptr_t)Ai | (uintptr_t)Aj | (uintptr_t)Ax) & m) == 0) return spmv_coo_warp<T>(h, st, a, c);
+    c = b200sp_cfg{};
+    c.kernel = B200SP_K_COO_SEGSCAN;
+    c.block_size = 256;
+    c.unroll = 7;
+  }
   if (c.kernel == B200SP_K_COO_RING) {
     if (c.stages < 2 || c.stages > 8 || c.ctas_per_sm < 1 || c.ctas_per_sm > 16)
       return set_error(h, B200SP_INVALID_INPUT, "coo ring: unsupported stages=%d ctas_per_sm=%d", c.stages,

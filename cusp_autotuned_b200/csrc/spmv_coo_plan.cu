@@ -1,34 +1,36 @@
-// spmv_coo_plan.cu — EXPERIMENTAL inspector / executor path for gather-bound COO products
-// (power-law graphs).  Not used by cusp::multiply or b200sp_spmv: reached only through the explicit
-// b200sp_coo_plan_* entry points.  Written after the round's GPU budget was spent — first hardware
-// validation is tests/test_zz_plan_gpu.py (expected-failure tolerant).
+// spmv_coo_plan.cu — inspector / executor COO product for gather-bound operators (power-law graphs).
 //
-// Why: on an R-MAT the product is bound by the x gathers (one L1TEX wavefront per distinct
-// 128-byte line, ~31 lines per 32-lane instruction), not by HBM.  The column stream is skewed: the 32 k
-// most frequent columns take 54 % of the gathers at scale 22.  The plan keeps x of the
-// most frequent columns in a per-CTA shared-memory table, and a second copy of the column array in
-// which those columns are replaced by (sign bit | table slot) — their gathers never reach L1TEX.
+// Why: on an R-MAT the product is bound by the x gathers (one L1TEX tag-stage cycle per
+// distinct 128-byte line, ~31 lines per 32-lane gather instruction, and one 32-byte sector from L2 per
+// gather), not by HBM.  The column stream is skewed: with the R-MAT parameters of BASELINE configs[2]
+// the 55 k columns whose index has at most five 1-bits take ~45 % of the gathers at scale 24.  The plan
+// keeps x of the most frequent columns in a per-CTA shared-memory table and a second copy of the column
+// array in which those columns are replaced by (sign bit | table slot): their gathers never reach
+// L1TEX or L2.
 //
 // Inspector (b200sp_coo_plan_create, device side, once per sparsity pattern):
 //   1. histogram of column_indices (atomicAdd per entry),
 //   2. the smallest count threshold t with #{c : count[c] >= t} <= table capacity (bisection, one count
-//      kernel + a 4-byte read-back per step),
-//   3. slot assignment of the selected columns (atomic counter; the order of slots has no effect on results),
+//      kernel + a 16-byte read-back per step),
+//   3. slot assignment of the selected columns, slots in ascending column order (the table is filled
+//      from x with mostly coalesced reads),
 //   4. the remapped column array.
-// Executor (b200sp_spmv_coo_plan_<t>): persistent CTAs, one per SM, 1024 threads; prologue loads
-// xs[slot] = x[hot_column[slot]]; then nnz-balanced tiles with the same per-thread serial + warp-shuffle
-// segmented scan, carry records and fix-up kernel as K_COO_SEGSCAN (spmv_coo.cu) — for equal
-// (BLOCK, VPT) the sums are grouped identically, so the result is bit-identical to that kernel's.
-// The plan borrows row_indices (caller keeps them alive and unchanged); values are passed per call.
+// Executor (b200sp_spmv_coo_plan_<t>, or b200sp_spmv_coo_<t> on the arrays of an attached plan):
+// K_COO_WARP with TABLE (coo_warp.cuh): one persistent 1024-thread CTA per SM, prologue
+// tab[slot] = x[hot_column[slot]], then the same warp tiles, summation order, carry records and
+// fix-up kernel as the plain kernel — for equal (vector_width, unroll) the result is bit-identical
+// to K_COO_WARP's.  The plan borrows row_indices (caller keeps them alive and unchanged); values are
+// passed per call.
 #include <algorithm>
 
-#include "common.cuh"
+#include "coo_warp.cuh"
 
 struct b200sp_coo_plan_s {
   i64 rows, cols, nnz;
   const int *Ai;       // borrowed
+  const int *Aj;       // borrowed: the original column array (identity of an attached plan)
   int *Aj_remapped;    // owned: column, or 0x80000000 | slot
-  int *hot_cols;       // owned: column of every slot
+  int *hot_cols;       // owned: column of every slot, ascending
   int hot;             // slots in use
   int capacity;        // slots the executor's table holds
   int elem;            // 4 / 8: value size the table was sized for
@@ -37,16 +39,7 @@ struct b200sp_coo_plan_s {
 
 namespace b200sp {
 
-constexpr int PLAN_BLOCK = 1024;
-constexpr int PLAN_VPT = 7;
-constexpr int PLAN_TILE = PLAN_BLOCK * PLAN_VPT;
-constexpr unsigned HOT_FLAG = 0x80000000u;
-
-template <typename T>
-struct CooCarryP {  // same layout as CooCarry<T> in spmv_coo.cu (the fix-up below mirrors coo_fixup_kernel)
-  int head_row, tail_row, leader, pad;
-  T head_val, tail_val;
-};
+constexpr unsigned HOT_FLAG = COO_HOT_FLAG;
 
 __global__ void plan_hist_kernel(i64 nnz, const int *Aj, int cols, int *cnt, int *bad) {
   for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (i64)gridDim.x * blockDim.x) {
@@ -101,210 +94,78 @@ __global__ void plan_remap_kernel(i64 nnz, const int *Aj, const int *slot_of, in
   }
 }
 
+
+// slot_of[hot_cols[s]] = s after the host put the selected columns in ascending order
+__global__ void plan_slots_kernel(int hot, const int *hot_cols, int *slot_of) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < hot) slot_of[hot_cols[s]] = s;
+}
+
 template <typename T>
-struct PlanArgs {
-  i64 rows, cols, nnz, tiles;
-  const int *Ai, *Aj2, *hot_cols;
-  const T *Ax, *x;
-  T *y;
-  int hot, accumulate;
-  CooCarryP<T> *carry;
-};
-
-// dynamic shared memory: xs[capacity] | s_val[TILE] | s_row[TILE + 1] (T first: 8-byte alignment)
-template <typename T>
-__global__ void __launch_bounds__(PLAN_BLOCK, 1) coo_hot_kernel(PlanArgs<T> a, int capacity) {
-  constexpr int BLOCK = PLAN_BLOCK, VPT = PLAN_VPT, TILE = PLAN_TILE, NW = BLOCK / 32;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T *xs = reinterpret_cast<T *>(smem_raw);
-  T *s_val = xs + capacity;
-  int *s_row = reinterpret_cast<int *>(s_val + TILE);
-  __shared__ T s_wv[NW];
-  __shared__ int s_wf[NW];
-  __shared__ int s_head_row;
-  __shared__ T s_head_val;
-
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const unsigned cols = (unsigned)a.cols;
-  for (int s = tid; s < a.hot; s += BLOCK) xs[s] = ld_ro(a.x + (unsigned)ld_ro(a.hot_cols + s));
-  __syncthreads();
-
-  for (i64 tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
-    const i64 start = tile * TILE;
-    const int n = (int)min((i64)TILE, a.nnz - start);
-    // ---- coalesced load + (table | global) gather + multiply -----------------------------
-    {
-      int r[VPT], c[VPT];
-      T v[VPT], xv[VPT];
-#pragma unroll
-      for (int i = 0; i < VPT; ++i) {
-        const i64 g = min(start + i * BLOCK + tid, a.nnz - 1);
-        r[i] = ld_stream(a.Ai + g);
-        c[i] = ld_stream(a.Aj2 + g);
-        v[i] = ld_stream(a.Ax + g);
-      }
-#pragma unroll
-      for (int i = 0; i < VPT; ++i) {
-        pin(c[i]);
-        if (c[i] < 0)
-          xv[i] = xs[min((unsigned)c[i] & ~HOT_FLAG, (unsigned)(a.hot - 1))];
-        else
-          xv[i] = ld_ro(a.x + min((unsigned)c[i], cols - 1));
-      }
-#pragma unroll
-      for (int i = 0; i < VPT; ++i) {
-        pin(xv[i]);
-        const int idx = i * BLOCK + tid;
-        const bool ok = idx < n;
-        s_row[idx] = ok ? r[i] : -1;
-        s_val[idx] = ok ? v[i] * xv[i] : T(0);
-      }
-    }
-    int prev_row = -1;
-    if (tid == 0) {
-      s_row[TILE] = (start + TILE < a.nnz) ? a.Ai[start + TILE] : -1;
-      s_head_row = -1;
-      s_head_val = T(0);
-    }
-    if (start > 0) prev_row = ld_ro(a.Ai + start - 1);
-    __syncthreads();
-
-    // ---- per-thread serial segmented reduction over VPT consecutive entries ----------------
-    int rr[VPT + 1];
-    T pv[VPT];
-#pragma unroll
-    for (int q = 0; q < VPT; ++q) {
-      rr[q] = s_row[tid * VPT + q];
-      pv[q] = s_val[tid * VPT + q];
-    }
-    rr[VPT] = s_row[tid * VPT + VPT];
-    T run = T(0), head = T(0);
-    int head_row = -1;
-    bool has_b = false;
-#pragma unroll
-    for (int q = 0; q < VPT; ++q) {
-      run = run + pv[q];
-      if (rr[q] != rr[q + 1]) {
-        if (!has_b) {
-          head = run;
-          head_row = rr[q];
-          has_b = true;
-        } else if (rr[q] >= 0) {
-          a.y[rr[q]] = a.accumulate ? a.y[rr[q]] + run : run;
-        }
-        run = T(0);
-      }
-    }
-    // ---- block-wide segmented scan of (has_b, tail) ----------------------------------------
-    T vi = run;
-    int fi = has_b ? 1 : 0;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const T vu = __shfl_up_sync(0xffffffffu, vi, d);
-      const int fu = __shfl_up_sync(0xffffffffu, fi, d);
-      if (lane >= d) {
-        if (!fi) vi = vu + vi;
-        fi |= fu;
-      }
-    }
-    if (lane == 31) {
-      s_wv[w] = vi;
-      s_wf[w] = fi;
-    }
-    __syncthreads();
-    T VW = T(0);
-    for (int k = 0; k < w; ++k) VW = s_wf[k] ? s_wv[k] : VW + s_wv[k];
-    const T Vi = fi ? vi : VW + vi;
-    T carry_in = __shfl_up_sync(0xffffffffu, Vi, 1);
-    if (lane == 0) carry_in = VW;
-    if (has_b && head_row >= 0) {
-      const T total = carry_in + head;
-      if (head_row == prev_row) {
-        s_head_row = head_row;
-        s_head_val = total;
-      } else {
-        a.y[head_row] = a.accumulate ? a.y[head_row] + total : total;
-      }
-    }
-    __syncthreads();
-    if (tid == BLOCK - 1) {
-      CooCarryP<T> cr;
-      cr.head_row = s_head_row;
-      cr.head_val = s_head_val;
-      cr.pad = 0;
-      const int last_row = rr[VPT - 1];
-      if (last_row >= 0 && last_row == rr[VPT]) {
-        cr.tail_row = last_row;
-        cr.tail_val = Vi;
-        cr.leader = (last_row != prev_row) ? 1 : 0;
-      } else {
-        cr.tail_row = -1;
-        cr.tail_val = T(0);
-        cr.leader = 0;
-      }
-      a.carry[tile] = cr;
-    }
-    __syncthreads();  // s_row / s_val / s_head_* / s_w* are rewritten by the next tile
+b200sp_status spmv_coo_hot(b200sp_handle h, cudaStream_t st, CooArgs<T> a, const b200sp_cfg &c, const int *hot_cols,
+                           int hot, int capacity) {
+  const int vpl = c.vector_width ? c.vector_width : 4, u = c.unroll ? c.unroll : 2;
+  const int xpol = c.stages & 3, spol = (c.stages >> 2) & 1;
+  const uintptr_t need_idx = (uintptr_t)(4 * vpl) - 1, need_val = (uintptr_t)(sizeof(T) * vpl > 32 ? 32 : sizeof(T) * vpl) - 1;
+  if (((uintptr_t)a.Ai & need_idx) || ((uintptr_t)a.Aj & need_idx) || ((uintptr_t)a.Ax & need_val))
+    return set_error(h, B200SP_INVALID_INPUT, "coo plan: arrays not aligned for %d-entry vector loads", vpl);
+#define CASE(V, UU, X, S)                              \
+  if (vpl == V && u == UU && xpol == X && spol == S) \
+    return launch_coo_warp<T, 1024, 1, V, UU, X, S, true>(h, st, a, 1, hot_cols, hot, capacity);
+#define CASES(V, UU) CASE(V, UU, 0, 0) CASE(V, UU, 1, 0) CASE(V, UU, 0, 1) CASE(V, UU, 1, 1)
+  if constexpr (sizeof(T) == 4) {
+    CASES(4, 1) CASES(4, 2) CASES(8, 1)
+  } else {
+    CASES(4, 1)
   }
+#undef CASES
+#undef CASE
+  return set_error(h, B200SP_INVALID_INPUT, "coo plan: unsupported vector_width=%d unroll=%d stages=%d", vpl, u,
+                   c.stages);
 }
-
-// one thread per tile: leaders walk their carry chain in tile order (as coo_fixup_kernel in spmv_coo.cu)
-template <typename T>
-__global__ void plan_fixup_kernel(i64 num_tiles, const CooCarryP<T> *carry, T *y, int accumulate) {
-  const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= num_tiles) return;
-  const CooCarryP<T> me = carry[t];
-  if (me.tail_row < 0 || !me.leader) return;
-  const int row = me.tail_row;
-  T total = me.tail_val;
-  for (i64 u = t + 1; u < num_tiles; ++u) {
-    const CooCarryP<T> nx = carry[u];
-    if (nx.head_row == row) {
-      total = total + nx.head_val;
-      break;
-    } else if (nx.tail_row == row && !nx.leader) {
-      total = total + nx.tail_val;
-    } else {
-      break;
-    }
-  }
-  y[row] = accumulate ? y[row] + total : total;
-}
-
-static size_t plan_smem_bytes(int capacity, size_t elem) {
-  return (size_t)capacity * elem + (size_t)PLAN_TILE * elem + (size_t)(PLAN_TILE + 1) * sizeof(int);
-}
+template b200sp_status spmv_coo_hot<float>(b200sp_handle, cudaStream_t, CooArgs<float>, const b200sp_cfg &, const int *,
+                                           int, int);
+template b200sp_status spmv_coo_hot<double>(b200sp_handle, cudaStream_t, CooArgs<double>, const b200sp_cfg &,
+                                            const int *, int, int);
 
 template <typename T>
 static b200sp_status spmv_coo_plan(b200sp_handle h, cudaStream_t st, b200sp_coo_plan p, const T *Ax, const T *x, T *y,
-                                   int accumulate) {
+                                   int accumulate, const b200sp_cfg *cfg) {
   B200SP_CHECK_HANDLE(h);
   B200SP_REQUIRE(h, p != nullptr, "coo plan: null plan");
-  B200SP_REQUIRE(h, p->elem == (int)sizeof(T), "coo plan: created for the other value type");
+  B200SP_REQUIRE(h, p->elem == (int)sizeof(T), "coo plan: the plan was created for the other value type");
   if (p->rows == 0) return B200SP_OK;
   B200SP_REQUIRE(h, y != nullptr, "coo plan: null pointer");
   if (!accumulate) B200SP_CUDA(h, cudaMemsetAsync(y, 0, (size_t)p->rows * sizeof(T), st));
   if (p->nnz == 0) return B200SP_OK;
   B200SP_REQUIRE(h, Ax && x, "coo plan: null pointer");
-  const i64 tiles = ceil_div(p->nnz, (i64)PLAN_TILE);
-  b200sp_status s = ensure_scratch(h, (size_t)tiles * sizeof(CooCarryP<T>));
-  if (s != B200SP_OK) return s;
-  PlanArgs<T> a;
-  a.rows = p->rows; a.cols = p->cols; a.nnz = p->nnz; a.tiles = tiles;
-  a.Ai = p->Ai; a.Aj2 = p->Aj_remapped; a.hot_cols = p->hot_cols; a.Ax = Ax; a.x = x; a.y = y;
-  a.hot = p->hot; a.accumulate = accumulate;
-  a.carry = reinterpret_cast<CooCarryP<T> *>(h->scratch);
-  const size_t smem = plan_smem_bytes(p->capacity, sizeof(T));
-  auto kern = coo_hot_kernel<T>;
-  B200SP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  i64 grid = h->num_sms;
-  if (grid > tiles) grid = tiles;
-  kern<<<(unsigned)grid, PLAN_BLOCK, smem, st>>>(a, p->capacity);
-  B200SP_LAUNCH_CHECK(h, "coo_hot_kernel");
-  plan_fixup_kernel<T><<<(unsigned)ceil_div(tiles, 256), 256, 0, st>>>(tiles, a.carry, y, accumulate);
-  B200SP_LAUNCH_CHECK(h, "plan_fixup_kernel");
-  return B200SP_OK;
+  CooArgs<T> a;
+  a.rows = p->rows; a.cols = p->cols; a.nnz = p->nnz; a.Ai = p->Ai; a.Aj = p->Aj_remapped; a.Ax = Ax; a.x = x; a.y = y;
+  a.accumulate = accumulate;
+  a.carry = nullptr; a.Ap = nullptr; a.tile_first_row = nullptr;
+  const b200sp_cfg c = cfg ? *cfg : b200sp_cfg{};
+  return spmv_coo_hot<T>(h, st, a, c, p->hot_cols, p->hot, p->capacity);
 }
+
+// the plan attached to this handle for exactly these arrays, or nullptr (spmv_coo.cu asks)
+b200sp_coo_plan coo_attached_plan(b200sp_handle h, i64 rows, i64 cols, i64 nnz, const int *Ai, const int *Aj,
+                                  size_t elem) {
+  for (void *q : h->coo_plans) {
+    b200sp_coo_plan p = reinterpret_cast<b200sp_coo_plan>(q);
+    if (p->Ai == Ai && p->Aj == Aj && p->nnz == nnz && p->rows == rows && p->cols == cols && p->elem == (int)elem)
+      return p;
+  }
+  return nullptr;
+}
+template <typename T>
+b200sp_status spmv_coo_attached(b200sp_handle h, cudaStream_t st, b200sp_coo_plan p, const T *Ax, const T *x, T *y,
+                                int accumulate, const b200sp_cfg *cfg) {
+  return spmv_coo_plan<T>(h, st, p, Ax, x, y, accumulate, cfg);
+}
+template b200sp_status spmv_coo_attached<float>(b200sp_handle, cudaStream_t, b200sp_coo_plan, const float *,
+                                                const float *, float *, int, const b200sp_cfg *);
+template b200sp_status spmv_coo_attached<double>(b200sp_handle, cudaStream_t, b200sp_coo_plan, const double *,
+                                                 const double *, double *, int, const b200sp_cfg *);
 
 }  // namespace b200sp
 
@@ -323,14 +184,15 @@ b200sp_status b200sp_coo_plan_create(b200sp_handle h, b200sp_stream stream, int6
   B200SP_REQUIRE(h, num_entries == 0 || (row_indices && column_indices && num_cols > 0), "coo plan: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t elem = dtype == B200SP_F64 ? 8 : 4;
-  if (table_bytes <= 0) table_bytes = 128 << 10;
+  // default: everything an SM's shared memory can hold next to the kernel's static needs
+  if (table_bytes <= 0) table_bytes = ((int64_t)h->max_smem_optin - 1024) & ~(int64_t)1023;
   int capacity = (int)std::min<int64_t>(table_bytes / (int64_t)elem, num_cols > 0 ? num_cols : 1);
   if (capacity < 1) capacity = 1;
-  if (plan_smem_bytes(capacity, elem) + 2048 > (size_t)h->max_smem_optin)
-    return set_error(h, B200SP_INVALID_INPUT, "coo plan: a %lld-byte table does not fit beside the tile buffers (%d B shared memory)",
+  if ((size_t)capacity * elem > (size_t)h->max_smem_optin)
+    return set_error(h, B200SP_INVALID_INPUT, "coo plan: a %lld-byte table does not fit in %d B of shared memory",
                      (long long)table_bytes, h->max_smem_optin);
   b200sp_coo_plan p = new b200sp_coo_plan_s();
-  p->rows = num_rows; p->cols = num_cols; p->nnz = num_entries; p->Ai = row_indices;
+  p->rows = num_rows; p->cols = num_cols; p->nnz = num_entries; p->Ai = row_indices; p->Aj = column_indices;
   p->Aj_remapped = nullptr; p->hot_cols = nullptr; p->hot = 0; p->capacity = capacity; p->elem = (int)elem;
   p->hot_entries = 0;
   int *cnt = nullptr, *slot_of = nullptr, *scal = nullptr;
@@ -398,8 +260,7 @@ b200sp_status b200sp_coo_plan_create(b200sp_handle h, b200sp_stream stream, int6
   if (ok) {
     plan_assign_kernel<<<g_col, 256, 0, st>>>((int)num_cols, cnt, t, capacity, slot_of, p->hot_cols, scal,
                                               reinterpret_cast<unsigned long long *>(scal + 4));
-    plan_remap_kernel<<<g_nnz, 256, 0, st>>>(num_entries, column_indices, slot_of, p->Aj_remapped);
-    h->launches += 2;
+    h->launches++;
     int h8[8];
     ok = cudaMemcpyAsync(h8, scal, 8 * sizeof(int), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
          cudaStreamSynchronize(st) == cudaSuccess;
@@ -408,6 +269,24 @@ b200sp_status b200sp_coo_plan_create(b200sp_handle h, b200sp_stream stream, int6
       unsigned long long he;
       memcpy(&he, h8 + 4, sizeof(he));
       p->hot_entries = (i64)he;
+      // slots in ascending column order: the atomic counter handed them out in arrival order
+      std::vector<int> hc((size_t)std::max(p->hot, 1));
+      ok = cudaMemcpyAsync(hc.data(), p->hot_cols, (size_t)p->hot * sizeof(int), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+           cudaStreamSynchronize(st) == cudaSuccess;
+      if (ok && p->hot > 0) {
+        std::sort(hc.begin(), hc.begin() + p->hot);
+        ok = cudaMemcpyAsync(p->hot_cols, hc.data(), (size_t)p->hot * sizeof(int), cudaMemcpyHostToDevice, st) == cudaSuccess;
+        if (ok) {
+          plan_slots_kernel<<<(unsigned)ceil_div(p->hot, 256), 256, 0, st>>>(p->hot, p->hot_cols, slot_of);
+          h->launches++;
+          ok = cudaStreamSynchronize(st) == cudaSuccess;  // hc goes out of scope
+        }
+      }
+    }
+    if (ok) {
+      plan_remap_kernel<<<g_nnz, 256, 0, st>>>(num_entries, column_indices, slot_of, p->Aj_remapped);
+      h->launches++;
+      ok = cudaStreamSynchronize(st) == cudaSuccess;
     }
   }
   if (!ok) return fail(set_error(h, B200SP_CUDA_ERROR, "coo plan: remapping failed: %s", cudaGetErrorString(cudaGetLastError())));
@@ -421,9 +300,29 @@ b200sp_status b200sp_coo_plan_create(b200sp_handle h, b200sp_stream stream, int6
 b200sp_status b200sp_coo_plan_destroy(b200sp_handle h, b200sp_coo_plan plan) {
   B200SP_CHECK_HANDLE(h);
   if (!plan) return B200SP_OK;
+  b200sp_coo_plan_detach(h, plan);
   cudaFree(plan->Aj_remapped);
   cudaFree(plan->hot_cols);
   delete plan;
+  return B200SP_OK;
+}
+
+b200sp_status b200sp_coo_plan_attach(b200sp_handle h, b200sp_coo_plan plan) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, plan != nullptr, "coo plan: null plan");
+  for (void *q : h->coo_plans)
+    if (q == plan) return B200SP_OK;
+  h->coo_plans.push_back(plan);
+  return B200SP_OK;
+}
+
+b200sp_status b200sp_coo_plan_detach(b200sp_handle h, b200sp_coo_plan plan) {
+  B200SP_CHECK_HANDLE(h);
+  for (size_t i = 0; i < h->coo_plans.size(); ++i)
+    if (h->coo_plans[i] == plan) {
+      h->coo_plans.erase(h->coo_plans.begin() + (long)i);
+      break;
+    }
   return B200SP_OK;
 }
 
@@ -436,11 +335,11 @@ b200sp_status b200sp_coo_plan_info(b200sp_coo_plan plan, int64_t *hot_columns, i
 }
 
 b200sp_status b200sp_spmv_coo_plan_f32(b200sp_handle h, b200sp_stream stream, b200sp_coo_plan plan, const float *values,
-                                       const float *x, float *y, int accumulate) {
-  return b200sp::spmv_coo_plan<float>(h, (cudaStream_t)stream, plan, values, x, y, accumulate);
+                                       const float *x, float *y, int accumulate, const b200sp_cfg *cfg) {
+  return b200sp::spmv_coo_plan<float>(h, (cudaStream_t)stream, plan, values, x, y, accumulate, cfg);
 }
 b200sp_status b200sp_spmv_coo_plan_f64(b200sp_handle h, b200sp_stream stream, b200sp_coo_plan plan, const double *values,
-                                       const double *x, double *y, int accumulate) {
-  return b200sp::spmv_coo_plan<double>(h, (cudaStream_t)stream, plan, values, x, y, accumulate);
+                                       const double *x, double *y, int accumulate, const b200sp_cfg *cfg) {
+  return b200sp::spmv_coo_plan<double>(h, (cudaStream_t)stream, plan, values, x, y, accumulate, cfg);
 }
 }

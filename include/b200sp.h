@@ -66,7 +66,8 @@ typedef struct {
   int block_size;      /* threads per CTA: 128, 256, 512                        */
   int threads_per_row; /* CSR row-split width 1,2,4,8,16,32 (1 = scalar)        */
   int unroll;          /* independent rows (CSR/ELL/DIA) or nnz (COO) per thread */
-  int vector_width;    /* elements per global load (1,2,4); slab kernels: unused */
+  int vector_width;    /* consecutive entries per lane per global load: K_COO_WARP 4 (128-bit
+                          loads) or 8 (256-bit loads); other kernels: 1                  */
   int tile_rows;       /* rows per staged slab tile (bulk-async kernels)         */
   int stages;          /* smem pipeline depth (bulk-async kernels)               */
   int ctas_per_sm;     /* persistent-grid multiplier (bulk-async kernels)        */
@@ -94,9 +95,13 @@ enum {
   /* COO  (replaces thrust reduce_by_key generic/multiply/spmv.h:182-238,
    *       spmv_coo_flat_kernel coo_flat_spmv.h:225-463, KTT coo_spmv)         */
   B200SP_K_COO_SEGSCAN = 1, /* nnz-balanced tiles, smem segmented scan, no atomics */
-  B200SP_K_COO_RING = 2     /* same tiles and summation order; persistent CTAs, entry streams
+  B200SP_K_COO_RING = 2,    /* same tiles and summation order; persistent CTAs, entry streams
                                staged by cp.async.bulk into an mbarrier ring (default for
                                16-byte aligned arrays with enough tiles)                     */
+  B200SP_K_COO_WARP = 3     /* warp-autonomous tiles: 128- / 256-bit loads of vector_width
+                               consecutive entries per lane, products in registers, shuffle
+                               segmented scan, no shared memory or CTA barrier (default for
+                               scattered column streams: power-law graphs)                   */
 };
 
 /* ---- lifecycle ---------------------------------------------------------- */
@@ -317,28 +322,40 @@ b200sp_status b200sp_spmm_csr_f64(b200sp_handle h, b200sp_stream stream, int64_t
                                   const double *values, int64_t block_cols, const double *X,
                                   int64_t ldx, double *Y, int64_t ldy, int accumulate);
 
-/* ---- EXPERIMENTAL: inspector / executor COO product for gather-bound operators (power-law graphs) ----
- * Not used by b200sp_spmv / cusp::multiply.  b200sp_coo_plan_create inspects the sparsity pattern once
- * (column histogram -> the most frequent columns that fit a `table_bytes` shared-memory table, default
- * 128 KiB -> a second copy of column_indices in which those columns are replaced by a table slot);
- * b200sp_spmv_coo_plan_<t> keeps x of those columns in shared memory, so their gathers never reach the
- * L1 / L2 path that bounds COO on an R-MAT.  Same tiles, summation order and carry
- * fix-up as the 1024 x 7 shape of the segmented-scan kernel.  The plan borrows row_indices (caller keeps
- * them alive and unchanged while the plan exists); values are passed per call and may change between
- * calls.  dtype fixes the table's element size.  First hardware validation: tests/test_zz_plan_gpu.py. */
+/* ---- inspector / executor COO product for gather-bound operators (power-law graphs) ----------------
+ * The analogue of tuning tied to one matrix (cusp::ktt::tune(A, x, y) keeps its results per kernel and
+ * matrix, cusp/ktt/detail/ktt.inl:108-142).  b200sp_coo_plan_create inspects the sparsity pattern once
+ * (column histogram -> the most frequent columns that fit a `table_bytes` shared-memory table, default:
+ * all of an SM's shared memory -> a second copy of column_indices in which those columns are replaced by
+ * a table slot); the executor keeps x of those columns in shared memory, so their gathers never reach
+ * the L1 / L2 path that bounds COO on an R-MAT.  Same tiles, summation order and carry
+ * fix-up as K_COO_WARP with equal (vector_width, unroll): identical bits.  The plan borrows row_indices
+ * and remembers column_indices by address (caller keeps both alive and unchanged while the plan exists);
+ * values are passed per call and may change between calls.  dtype fixes the table's element size.
+ *
+ * b200sp_coo_plan_attach registers the plan with the handle: from then on b200sp_spmv_coo_<t> /
+ * b200sp_spmv (COO, and the COO part of HYB) called with exactly the plan's (row_indices, column_indices,
+ * num_entries, shape) runs the executor; any other arrays take the default kernels.  Detach (or destroy)
+ * before changing the matrix's structure in place.  cusp::ktt::tune on a device coo_matrix attaches a
+ * plan, cusp::ktt::reset_tuning drops it (include/cusp/ktt/ktt.h). */
 typedef struct b200sp_coo_plan_s *b200sp_coo_plan;
 b200sp_status b200sp_coo_plan_create(b200sp_handle h, b200sp_stream stream, int64_t num_rows,
                                      int64_t num_cols, int64_t num_entries,
                                      const int32_t *row_indices, const int32_t *column_indices,
                                      b200sp_dtype dtype, int64_t table_bytes, b200sp_coo_plan *out);
 b200sp_status b200sp_coo_plan_destroy(b200sp_handle h, b200sp_coo_plan plan);
+b200sp_status b200sp_coo_plan_attach(b200sp_handle h, b200sp_coo_plan plan);
+b200sp_status b200sp_coo_plan_detach(b200sp_handle h, b200sp_coo_plan plan);
 /* columns held in the table, stored entries they serve, table capacity in elements */
 b200sp_status b200sp_coo_plan_info(b200sp_coo_plan plan, int64_t *hot_columns, int64_t *hot_entries,
                                    int64_t *capacity);
+/* cfg: NULL or a K_COO_WARP shape (vector_width, unroll, stages) */
 b200sp_status b200sp_spmv_coo_plan_f32(b200sp_handle h, b200sp_stream stream, b200sp_coo_plan plan,
-                                       const float *values, const float *x, float *y, int accumulate);
+                                       const float *values, const float *x, float *y, int accumulate,
+                                       const b200sp_cfg *cfg);
 b200sp_status b200sp_spmv_coo_plan_f64(b200sp_handle h, b200sp_stream stream, b200sp_coo_plan plan,
-                                       const double *values, const double *x, double *y, int accumulate);
+                                       const double *values, const double *x, double *y, int accumulate,
+                                       const b200sp_cfg *cfg);
 
 /* ---- multi-GPU: row-block partitioned operator ---------------------------
  * One process per GPU.  Each rank owns a contiguous block of rows of A and the

@@ -52,7 +52,7 @@ def test_version_and_strings():
 
 def test_cfg_spaces_enumerate():
     sizes = {f: len(capi.Handle.cfg_space(f, capi.F32)) for f in range(6)}
-    assert sizes[capi.FMT_CSR] == 62 + 45 + 4 and sizes[capi.FMT_COO] == 10 + 48  # segscan + ring (8 shapes x 2 stages x 3 ctas/sm)
+    assert sizes[capi.FMT_CSR] == 62 + 45 + 4 and sizes[capi.FMT_COO] == 10 + 48 + 6  # segscan + ring (8 shapes x 2 stages x 3 ctas/sm) + warp (2 widths x 3 unrolls)
     assert sizes[capi.FMT_ELL] == sizes[capi.FMT_DIA] == sizes[capi.FMT_ELLR] == 63
     for c in capi.Handle.cfg_space(capi.FMT_CSR, capi.F64):
         assert c.kernel in (capi.K_CSR_VECTOR, capi.K_CSR_STREAM, capi.K_CSR_RING, capi.K_CSR_BALANCED)

@@ -315,6 +315,119 @@ def test_coo_ring_matches_segscan_bitwise(ndt, tdt, dev):
         assert scaled_err(got, O.spmv(A, x, y0, accumulate=True), np.abs(y0) + want) <= TOL[np.dtype(ndt)]
 
 
+WARP_SHAPES = [(4, 1), (4, 2), (4, 4), (8, 1), (8, 2)]
+
+
+@pytest.mark.parametrize("ndt,tdt", DTYPES)
+def test_coo_warp_tile_boundaries_and_hubs(ndt, tdt, dev):
+    """K_COO_WARP: rows that start / end exactly on lane, unit and warp-tile boundaries, a matrix that is one row,
+    hub rows spanning > 64 tiles (the fix-up kernel's warp-parallel chain walk), ragged last tile, duplicates,
+    accumulate — integer data, exact against the host loop."""
+    rng = np.random.default_rng(21)
+    for vw, u in WARP_SHAPES:
+        wt = 32 * vw * u
+        cfg = capi.Cfg(kernel=capi.K_COO_WARP, vector_width=vw, unroll=u)
+        cases = ([wt, wt, wt], [wt - 1, 1, wt], [1, 2 * wt + 5, 3], [3 * wt], [vw] * 500, [vw - 1, vw + 1] * 300,
+                 [5] * 1000, [1] * 777, [70 * wt + 3, 2, 40 * wt], [1, 130 * wt])
+        for lens in cases:
+            rows = np.repeat(np.arange(len(lens)) * 2, lens).astype(np.int32)  # odd rows empty
+            n = 2 * len(lens)
+            cols = rng.integers(0, n, len(rows)).astype(np.int32)
+            vals = rng.integers(-2, 3, len(rows)).astype(ndt)
+            A = dict(format="coo", num_rows=n, num_cols=n, num_entries=len(rows), row_indices=rows,
+                     column_indices=cols, values=vals)
+            x = rng.integers(-3, 4, n).astype(ndt)
+            assert np.array_equal(gpu_multiply("coo", A, x, dev, cfg=cfg), O.spmv(A, x)), (vw, u, lens[:3])
+            y0 = rng.integers(-5, 5, n).astype(ndt)
+            assert np.array_equal(gpu_multiply("coo", A, x, dev, y0=y0, accumulate=True, cfg=cfg),
+                                  O.spmv(A, x, y0, accumulate=True)), (vw, u, lens[:3], "accumulate")
+        # persistent grid: more tiles than resident warps
+        nnz = wt * 9000 + 17
+        n = 50000
+        rows = np.sort(rng.integers(0, n, nnz)).astype(np.int32)
+        cols = rng.integers(0, n, nnz).astype(np.int32)
+        vals = rng.integers(-2, 3, nnz).astype(ndt)
+        A = dict(format="coo", num_rows=n, num_cols=n, num_entries=nnz, row_indices=rows, column_indices=cols,
+                 values=vals)
+        x = rng.integers(-3, 4, n).astype(ndt)
+        want = O.spmv(A, x)
+        for cps in (0, 1, 3):
+            c2 = capi.Cfg(kernel=capi.K_COO_WARP, vector_width=vw, unroll=u, ctas_per_sm=cps)
+            assert np.array_equal(gpu_multiply("coo", A, x, dev, cfg=c2), want), (vw, u, cps)
+
+
+@pytest.mark.parametrize("ndt,tdt", DTYPES)
+def test_coo_warp_tolerance_and_policies(ndt, tdt, dev):
+    """non-integer data: every shape within the north-star bound of the host loop; the cache-policy variants and the
+    persistent grid change no bit (same tiles, same order)"""
+    rng = np.random.default_rng(22)
+    n, nnz = 30000, 128 * 3000 + 77
+    rows = np.sort(rng.integers(0, n, nnz)).astype(np.int32)
+    rows[5000:90000] = rows[5000]
+    rows = np.sort(rows)
+    cols = rng.integers(0, n, nnz).astype(np.int32)
+    vals = rng.uniform(0.5, 1.5, nnz).astype(ndt)
+    A = dict(format="coo", num_rows=n, num_cols=n, num_entries=nnz, row_indices=rows, column_indices=cols, values=vals)
+    x = rng.uniform(0.5, 1.5, n).astype(ndt)
+    want = O.spmv(A, x)
+    for vw, u in WARP_SHAPES:
+        base = gpu_multiply("coo", A, x, dev, cfg=capi.Cfg(kernel=capi.K_COO_WARP, vector_width=vw, unroll=u))
+        assert rel_err(base, want) <= TOL[np.dtype(ndt)], (vw, u)
+        for pol, cps in ((1, 0), (2, 0), (4, 0), (5, 2), (6, 0)):
+            got = gpu_multiply("coo", A, x, dev, cfg=capi.Cfg(kernel=capi.K_COO_WARP, vector_width=vw, unroll=u,
+                                                              stages=pol, ctas_per_sm=cps))
+            assert np.array_equal(got, base), (vw, u, pol, cps)
+
+
+@pytest.mark.parametrize("ndt,tdt", DTYPES)
+def test_coo_plan_matches_warp_kernel_bitwise(ndt, tdt, dev, handle):
+    """b200sp_coo_plan_*: hot columns of x served from the shared-memory table — same tiles and order as K_COO_WARP,
+    so identical bits; table smaller than / equal to / larger than the number of distinct columns; skewed column
+    stream; attached plans are used by b200sp_spmv_coo for exactly their arrays and for nothing else."""
+    rng = np.random.default_rng(23)
+    n, nnz = 20000, 128 * 2500 + 5
+    rows = np.sort(rng.integers(0, n, nnz)).astype(np.int32)
+    cols = np.minimum((rng.pareto(1.2, nnz) * 40).astype(np.int64), n - 1).astype(np.int32)  # power-law columns
+    vals = rng.uniform(0.5, 1.5, nnz).astype(ndt)
+    x = rng.uniform(0.5, 1.5, n).astype(ndt)
+    ri, ci, va, xd = tdev(rows, dev), tdev(cols, dev), tdev(vals, dev), tdev(x, dev)
+    dt = capi.F32 if ndt == np.float32 else capi.F64
+    es = np.dtype(ndt).itemsize
+    for table_bytes in (16 * es, 4096, 0):
+        plan = handle.coo_plan_create(n, n, nnz, ri, ci, dt, table_bytes)
+        info = handle.coo_plan_info(plan)
+        assert 0 < info["hot_columns"] <= info["capacity"]
+        if table_bytes:
+            assert info["capacity"] == table_bytes // es
+        assert 0 < info["hot_entries"] <= nnz
+        for vw, u in ((4, 1), (4, 2), (8, 1)) if ndt == np.float32 else ((4, 1),):
+            cfg = capi.Cfg(kernel=capi.K_COO_WARP, vector_width=vw, unroll=u)
+            yw = torch.full((n,), 9, dtype=tdt, device=dev)
+            handle.spmv_coo(n, n, nnz, ri, ci, va, xd, yw, cfg=cfg)
+            yp = torch.full((n,), 5, dtype=tdt, device=dev)
+            handle.spmv_coo_plan(plan, va, xd, yp, cfg=cfg)
+            assert torch.equal(yw, yp), (table_bytes, vw, u)
+            handle.spmv_coo(n, n, nnz, ri, ci, va, xd, yw, accumulate=True, cfg=cfg)
+            handle.spmv_coo_plan(plan, va, xd, yp, accumulate=True, cfg=cfg)
+            assert torch.equal(yw, yp), (table_bytes, vw, u, "accumulate")
+        # attached: the plain entry point takes the executor for these arrays only
+        y_plain = torch.empty(n, dtype=tdt, device=dev)
+        handle.spmv_coo(n, n, nnz, ri, ci, va, xd, y_plain, cfg=capi.Cfg(kernel=capi.K_COO_WARP))
+        handle.coo_plan_attach(plan)
+        y_att = torch.empty(n, dtype=tdt, device=dev)
+        handle.spmv_coo(n, n, nnz, ri, ci, va, xd, y_att)
+        assert torch.equal(y_att, y_plain)
+        ci2 = ci.clone()  # same contents, different array: not the plan's matrix
+        y_other = torch.empty(n, dtype=tdt, device=dev)
+        handle.spmv_coo(n, n, nnz, ri, ci2, va, xd, y_other)
+        assert rel_err(y_other.cpu().numpy(), y_plain.cpu().numpy()) <= TOL[np.dtype(ndt)]
+        handle.coo_plan_detach(plan)
+        handle.coo_plan_destroy(plan)
+    want = O.spmv(dict(format="coo", num_rows=n, num_cols=n, num_entries=nnz, row_indices=rows, column_indices=cols,
+                       values=vals), x)
+    assert rel_err(y_att.cpu().numpy(), want) <= TOL[np.dtype(ndt)]
+
+
 @pytest.mark.parametrize("ndt,tdt", DTYPES)
 def test_coo_unaligned_bases_fall_back(ndt, tdt, dev):
     """array bases that are not 16-byte aligned cannot be bulk-copied: K_COO_RING requests run
