@@ -124,7 +124,7 @@ EXPORTED_SYMBOLS = (
      "b200sp_status_string", "b200sp_launch_count", "b200sp_set_l2_persist",
      "b200sp_ell_row_lengths", "b200sp_spmv", "b200sp_spmv_host", "b200sp_cg",
      "b200sp_comm_unique_id", "b200sp_comm_init", "b200sp_comm_destroy", "b200sp_cg_dist",
-     "b200sp_spmv_dist", "b200sp_spmv_dist_gather", "b200sp_comm_p2p_enabled", "b200sp_comm_timeouts", "b200sp_cfg_space", "b200sp_tune", "b200sp_tune_step",
+     "b200sp_spmv_dist", "b200sp_spmv_dist_host", "b200sp_spmv_dist_gather", "b200sp_comm_p2p_enabled", "b200sp_comm_timeouts", "b200sp_cfg_space", "b200sp_tune", "b200sp_tune_step",
      "b200sp_tune_reset", "b200sp_tune_lookup", "b200sp_tune_save", "b200sp_tune_load",
      "b200sp_poisson_num_entries", "b200sp_poisson_csr_offsets",
      "b200sp_offsets_to_indices", "b200sp_indices_to_offsets", "b200sp_csr_convert_query"]
@@ -419,6 +419,11 @@ class Handle:
     def spmv_dist(self, A: Matrix, halo: Halo, x_window, y, cfg: Optional[Cfg] = None):
         self.check(self.lib.b200sp_spmv_dist(self._h, _stream(), C.byref(A), C.byref(halo), _ptr(x_window),
                                              _ptr(y), C.byref(cfg) if cfg else None))
+
+    def spmv_dist_host(self, A: Matrix, halo: Halo, x_host_local, y_host_local, cfg: Optional[Cfg] = None):
+        """this rank's slices of x / y in (pinned) host memory; halo planes exchanged between the GPUs"""
+        self.check(self.lib.b200sp_spmv_dist_host(self._h, _stream(), C.byref(A), C.byref(halo), _ptr(x_host_local),
+                                                  _ptr(y_host_local), C.byref(cfg) if cfg else None))
 
     def spmv_dist_gather(self, A: Matrix, slice_offsets, x_full, y, cfg: Optional[Cfg] = None):
         """row block with global column indices; gathers the other ranks' x slices, then multiplies"""

@@ -12,6 +12,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "comm.h"
 
 static char g_global_err[1024] = "no error";
 
@@ -458,11 +459,19 @@ namespace b200sp {
 // down on a second copy stream — so the two PCIe directions and the kernels overlap instead of
 // running back to back.  Same kernels, same per-row arithmetic: results are bit-identical to
 // the one-shot path.  *done = 0 when the matrix does not qualify (caller falls back).
+//
+// Partitioned form (halo != nullptr, b200sp_spmv_dist_host): A is a rank's row block in window
+// coordinates [halo_lo | local | halo_hi], x_host is the rank's LOCAL slice.  The two edge pieces
+// go up first, the halo planes are exchanged with the neighbours (peer memory / NCCL) while the
+// interior pieces are still in flight, and every chunk waits only for the pieces it reads.
 static b200sp_status spmv_host_pipelined_dia(b200sp_handle h, cudaStream_t st, const b200sp_matrix *A,
-                                             const void *x_host, void *y_host, const b200sp_cfg *cfg, int *done) {
+                                             const void *x_host, void *y_host, const b200sp_cfg *cfg,
+                                             const b200sp_halo *halo, int *done) {
   *done = 0;
   const i64 K = A->num_cols_per_row, rows = A->num_rows, cols = A->num_cols;
   const size_t elem = A->dtype == B200SP_F64 ? 8 : 4;
+  const i64 hlo = halo ? halo->halo_lo : 0;
+  const i64 local_cols = halo ? rows : cols;  // columns that come from x_host, window columns [hlo, hlo + local_cols)
   if (K <= 0 || K > 1024 || rows < (1 << 20)) return B200SP_OK;
   std::vector<int> off((size_t)K);
   B200SP_CUDA(h, cudaMemcpyAsync(off.data(), A->diagonal_offsets, (size_t)K * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -477,7 +486,7 @@ static b200sp_status spmv_host_pipelined_dia(b200sp_handle h, cudaStream_t st, c
   if (chunk < lo + 1024 || chunk < up + 1024) return B200SP_OK;  // band wider than a chunk: nothing to overlap
   const int nch = (int)ceil_div(rows, chunk);
   if (nch < 3) return B200SP_OK;
-  const int npieces = nch;  // x piece p = columns [p*chunk, (p+1)*chunk), the last one runs to `cols`
+  const int npieces = nch;  // piece p = local columns [p*chunk, (p+1)*chunk), the last one runs to local_cols
 
   if (!h->copy_in_stream) {
     cudaStream_t a, b;
@@ -509,19 +518,38 @@ static b200sp_status spmv_host_pipelined_dia(b200sp_handle h, cudaStream_t st, c
   B200SP_CUDA(h, cudaEventRecord(ev(0), st));  // staging buffers are free once prior work on `st` is done
   B200SP_CUDA(h, cudaStreamWaitEvent(cin, ev(0), 0));
   B200SP_CUDA(h, cudaStreamWaitEvent(cout, ev(0), 0));
-  for (int p = 0; p < npieces; ++p) {
-    const i64 c0 = (i64)p * chunk, c1 = (p == npieces - 1) ? cols : std::min(cols, c0 + chunk);
+  // upload order: partitioned -> both edge pieces first (the neighbours need them), then the interior
+  std::vector<int> order, ord_of((size_t)npieces);
+  order.push_back(0);
+  if (halo) order.push_back(npieces - 1);
+  for (int p = 1; p < npieces; ++p)
+    if (!(halo && p == npieces - 1)) order.push_back(p);
+  for (int k = 0; k < npieces; ++k) {
+    const int p = order[(size_t)k];
+    ord_of[(size_t)p] = k;
+    const i64 c0 = (i64)p * chunk, c1 = (p == npieces - 1) ? local_cols : std::min(local_cols, c0 + chunk);
     if (c1 > c0)
-      B200SP_CUDA(h, cudaMemcpyAsync(dx + (size_t)c0 * elem, hx + (size_t)c0 * elem, (size_t)(c1 - c0) * elem,
+      B200SP_CUDA(h, cudaMemcpyAsync(dx + (size_t)(hlo + c0) * elem, hx + (size_t)c0 * elem, (size_t)(c1 - c0) * elem,
                                      cudaMemcpyHostToDevice, cin));
-    B200SP_CUDA(h, cudaEventRecord(ev(1 + (size_t)p), cin));
+    B200SP_CUDA(h, cudaEventRecord(ev(1 + (size_t)k), cin));
+  }
+  if (halo) {
+    B200SP_CUDA(h, cudaStreamWaitEvent(st, ev(1 + 1), 0));  // both edge pieces (stream order: piece 0, then the last)
+    s = comm_halo_exchange_auto(h, st, dx, rows, halo->halo_lo, halo->halo_hi, elem);
+    if (s != B200SP_OK) return s;
   }
   for (int c = 0; c < nch; ++c) {
     const i64 r0 = (i64)c * chunk, r1 = std::min(rows, r0 + chunk);
-    const i64 last_col = std::min(cols, r1 + up) - 1;
-    int p = (int)(last_col / chunk);
-    if (p > npieces - 1) p = npieces - 1;
-    B200SP_CUDA(h, cudaStreamWaitEvent(st, ev(1 + (size_t)p), 0));
+    // window columns the chunk reads -> local pieces -> the one uploaded last
+    i64 first_col = r0 - lo - hlo, last_col = std::min(cols, r1 + up) - 1 - hlo;  // in local coordinates
+    if (first_col < 0) first_col = 0;
+    if (last_col > local_cols - 1) last_col = local_cols - 1;
+    int p_lo = (int)(first_col / chunk), p_hi = (int)(last_col / chunk);
+    if (p_hi > npieces - 1) p_hi = npieces - 1;
+    if (p_lo > p_hi) p_lo = p_hi;
+    int wait_ord = 0;
+    for (int p = p_lo; p <= p_hi; ++p) wait_ord = std::max(wait_ord, ord_of[(size_t)p]);
+    B200SP_CUDA(h, cudaStreamWaitEvent(st, ev(1 + (size_t)wait_ord), 0));
     b200sp_matrix sub = *A;
     sub.num_rows = r1 - r0;
     sub.values = reinterpret_cast<const char *>(A->values) + (size_t)r0 * elem;
@@ -548,6 +576,30 @@ static b200sp_status spmv_host_pipelined_dia(b200sp_handle h, cudaStream_t st, c
   return B200SP_OK;
 }
 
+static b200sp_status ensure_host_staging(b200sp_handle h, size_t xb, size_t yb) {
+  if (h->stage_x_bytes < xb) {
+    if (h->stage_x) cudaFree(h->stage_x);
+    h->stage_x = nullptr;
+    h->stage_x_bytes = 0;
+    if (cudaMalloc(&h->stage_x, xb ? xb : 1) != cudaSuccess) {
+      cudaGetLastError();
+      return set_error(h, B200SP_ALLOC_FAILED, "spmv_host: cannot stage x (%zu B)", xb);
+    }
+    h->stage_x_bytes = xb;
+  }
+  if (h->stage_y_bytes < yb) {
+    if (h->stage_y) cudaFree(h->stage_y);
+    h->stage_y = nullptr;
+    h->stage_y_bytes = 0;
+    if (cudaMalloc(&h->stage_y, yb ? yb : 1) != cudaSuccess) {
+      cudaGetLastError();
+      return set_error(h, B200SP_ALLOC_FAILED, "spmv_host: cannot stage y (%zu B)", yb);
+    }
+    h->stage_y_bytes = yb;
+  }
+  return B200SP_OK;
+}
+
 }  // namespace b200sp
 
 extern "C" {
@@ -559,36 +611,49 @@ b200sp_status b200sp_spmv_host(b200sp_handle h, b200sp_stream stream, const b200
   const size_t elem = A->dtype == B200SP_F64 ? 8 : 4;
   const size_t xb = (size_t)A->num_cols * elem, yb = (size_t)A->num_rows * elem;
   cudaStream_t st = (cudaStream_t)stream;
-  if (h->stage_x_bytes < xb) {
-    if (h->stage_x) cudaFree(h->stage_x);
-    h->stage_x = nullptr;
-    h->stage_x_bytes = 0;
-    if (cudaMalloc(&h->stage_x, xb ? xb : 1) != cudaSuccess) {
-      cudaGetLastError();
-      return b200sp::set_error(h, B200SP_ALLOC_FAILED, "spmv_host: cannot stage x (%zu B)", xb);
-    }
-    h->stage_x_bytes = xb;
-  }
-  if (h->stage_y_bytes < yb) {
-    if (h->stage_y) cudaFree(h->stage_y);
-    h->stage_y = nullptr;
-    h->stage_y_bytes = 0;
-    if (cudaMalloc(&h->stage_y, yb ? yb : 1) != cudaSuccess) {
-      cudaGetLastError();
-      return b200sp::set_error(h, B200SP_ALLOC_FAILED, "spmv_host: cannot stage y (%zu B)", yb);
-    }
-    h->stage_y_bytes = yb;
-  }
+  b200sp_status s = b200sp::ensure_host_staging(h, xb, yb);
+  if (s != B200SP_OK) return s;
   if (!accumulate && A->format == B200SP_FMT_DIA && !getenv("B200SP_HOST_ONE_SHOT")) {
     int done = 0;
-    b200sp_status ps = b200sp::spmv_host_pipelined_dia(h, st, A, x_host, y_host, cfg, &done);
+    b200sp_status ps = b200sp::spmv_host_pipelined_dia(h, st, A, x_host, y_host, cfg, nullptr, &done);
     if (ps != B200SP_OK || done) return ps;
   }
   B200SP_CUDA(h, cudaMemcpyAsync(h->stage_x, x_host, xb, cudaMemcpyHostToDevice, st));
   if (accumulate) B200SP_CUDA(h, cudaMemcpyAsync(h->stage_y, y_host, yb, cudaMemcpyHostToDevice, st));
-  b200sp_status s = b200sp_spmv(h, stream, A, h->stage_x, h->stage_y, accumulate, cfg);
+  s = b200sp_spmv(h, stream, A, h->stage_x, h->stage_y, accumulate, cfg);
   if (s != B200SP_OK) return s;
   B200SP_CUDA(h, cudaMemcpyAsync(y_host, h->stage_y, yb, cudaMemcpyDeviceToHost, st));
+  B200SP_CUDA(h, cudaStreamSynchronize(st));
+  return B200SP_OK;
+}
+
+b200sp_status b200sp_spmv_dist_host(b200sp_handle h, b200sp_stream stream, const b200sp_matrix *A_local,
+                                    const b200sp_halo *halo, const void *x_host_local, void *y_host_local,
+                                    const b200sp_cfg *cfg) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, A_local && halo && x_host_local && y_host_local, "spmv_dist_host: null argument");
+  B200SP_REQUIRE(h, h->nccl_comm, "spmv_dist_host: b200sp_comm_init has not been called");
+  B200SP_REQUIRE(h, A_local->num_cols == A_local->num_rows + halo->halo_lo + halo->halo_hi,
+                 "spmv_dist_host: num_cols != halo_lo + local + halo_hi");
+  const size_t elem = A_local->dtype == B200SP_F64 ? 8 : 4;
+  const size_t xb = (size_t)A_local->num_cols * elem, yb = (size_t)A_local->num_rows * elem;
+  cudaStream_t st = (cudaStream_t)stream;
+  b200sp_status s = b200sp::ensure_host_staging(h, xb, yb);
+  if (s != B200SP_OK) return s;
+  // Both paths exchange the halos with comm_halo_exchange_auto exactly once, so ranks whose blocks
+  // qualify for the pipeline and ranks whose blocks do not still pair up.
+  if (A_local->format == B200SP_FMT_DIA && !getenv("B200SP_HOST_ONE_SHOT")) {
+    int done = 0;
+    b200sp_status ps = b200sp::spmv_host_pipelined_dia(h, st, A_local, x_host_local, y_host_local, cfg, halo, &done);
+    if (ps != B200SP_OK || done) return ps;
+  }
+  char *dx = reinterpret_cast<char *>(h->stage_x);
+  B200SP_CUDA(h, cudaMemcpyAsync(dx + (size_t)halo->halo_lo * elem, x_host_local, yb, cudaMemcpyHostToDevice, st));
+  s = b200sp::comm_halo_exchange_auto(h, st, dx, A_local->num_rows, halo->halo_lo, halo->halo_hi, elem);
+  if (s != B200SP_OK) return s;
+  s = b200sp_spmv(h, stream, A_local, dx, h->stage_y, 0, cfg);
+  if (s != B200SP_OK) return s;
+  B200SP_CUDA(h, cudaMemcpyAsync(y_host_local, h->stage_y, yb, cudaMemcpyDeviceToHost, st));
   B200SP_CUDA(h, cudaStreamSynchronize(st));
   return B200SP_OK;
 }

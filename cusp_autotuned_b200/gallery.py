@@ -90,3 +90,28 @@ def from_host(fmt: str, arrays: dict, device=None):
         from .matrix import hyb_matrix
         return hyb_matrix(from_host("ell", arrays["ell"], device), from_host("coo", arrays["coo"], device))
     raise capi.InvalidInput(capi.ST_INVALID_INPUT, f"unknown format {fmt!r}")
+
+
+def poisson7pt_benchmark_product(dims, row_begin, num_rows, dtype, device=None):
+    """y = A x of the 7-point Poisson operator on grid `dims` for the benchmark vector x_j = (j mod 21) - 10
+    (performance/spmv/benchmark.h:27-46), rows [row_begin, row_begin + num_rows), from index arithmetic alone: no
+    matrix, no engine call.  Integer-valued, hence exact in fp32 / fp64 in any summation order — the independent
+    check bench.py and tools/dist_check.py hold every timed product against.
+    gallery/detail/poisson.inl:75-96: 6 on the diagonal, -1 per neighbour inside the grid, dimension 0 fastest."""
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    nx, ny, nz = dims
+    g = torch.arange(row_begin, row_begin + num_rows, device=device, dtype=torch.int64)
+    xv = lambda j: (j % 21) - 10
+    y = 6 * xv(g)
+    ix = g % nx
+    y -= torch.where(ix > 0, xv(g - 1), 0)
+    y -= torch.where(ix < nx - 1, xv(g + 1), 0)
+    del ix
+    iy = (g // nx) % ny
+    y -= torch.where(iy > 0, xv(g - nx), 0)
+    y -= torch.where(iy < ny - 1, xv(g + nx), 0)
+    del iy
+    iz = g // (nx * ny)
+    y -= torch.where(iz > 0, xv(g - nx * ny), 0)
+    y -= torch.where(iz < nz - 1, xv(g + nx * ny), 0)
+    return y.to(dtype)

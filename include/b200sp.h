@@ -407,6 +407,16 @@ b200sp_status b200sp_spmv_dist(b200sp_handle h, b200sp_stream stream,
                                void *x_window, void *y_local,
                                const b200sp_cfg *cfg);
 
+/* b200sp_spmv_dist through HOST buffers: this rank's slice of x (num_rows elements) goes up, the halo
+ * planes are exchanged between the GPUs, this rank's slice of y comes down.  For DIA blocks the call is
+ * a pipeline over row chunks (edge pieces first, halo exchange and interior uploads overlapped, both
+ * PCIe directions busy at once), bit-identical to upload + b200sp_spmv_dist + download.  Collective:
+ * every rank of the communicator calls it.  Synchronises `stream`. */
+b200sp_status b200sp_spmv_dist_host(b200sp_handle h, b200sp_stream stream,
+                                    const b200sp_matrix *A_local, const b200sp_halo *halo,
+                                    const void *x_host_local, void *y_host_local,
+                                    const b200sp_cfg *cfg);
+
 /* Partitioned SpMV for operators whose rows read the whole of x (graphs): the rank's
  * block of rows keeps GLOBAL column indices (num_cols = global size); x is partitioned like the
  * rows, slice r = [slice_offsets[r], slice_offsets[r+1]) (host array of world_size+1 entries,

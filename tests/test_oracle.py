@@ -248,3 +248,20 @@ def test_reference_gpu_kernel_harness_enumerates_the_ktt_dia_space():
     if os.path.exists("/usr/local/cuda/bin/cuobjdump"):
         out = subprocess.check_output(["/usr/local/cuda/bin/cuobjdump", "-res-usage", path], text=True)
         assert len(re.findall(r"ktt_dia_vector_kernel", out)) == 84  # 42 points x {float, double}
+
+
+def test_committed_cg_history_is_the_oracles():
+    """tests/golden/cg_poisson7pt_f64.json (what bench.py and the full-size GPU test compare the solver's residual
+    history with) is reproduced by the oracle CG on the grid that finishes in a blink; the 512^3 entry has the
+    shape BASELINE configs[4] names"""
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cg_poisson7pt_f64.json")))
+    g = gold["64x64x64"]
+    A = O.poisson(7, (64, 64, 64), np.float64, "csr")
+    n = A["num_rows"]
+    x, it, conv, hist = O.cg(A, np.zeros(n), np.ones(n), g["iterations"], 0.0, 0.0)
+    assert it == g["iterations"] and np.array_equal(hist, np.asarray(g["residuals"]))
+    big = gold["512x512x512"]
+    assert big["rows"] == 512 ** 3 and big["nnz"] == 937951232 and len(big["residuals"]) == big["iterations"] + 1 == 51
+    assert abs(big["residuals"][0] - np.sqrt(512 ** 3)) < 1e-6

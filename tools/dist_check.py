@@ -95,6 +95,62 @@ def main():
                                      "cg_same_iters": f[1], "cg_hist": f[2], "cg_x": f[3], "hist_dev": hist_dev,
                                      "iters": int(res.iteration_count)})
                 ok = ok and all(f)
+    # production-shaped case (--production / DIST_CHECK_PRODUCTION=1): 32 planes of 256^2 per rank, the shape of the
+    # benchmarked jobs (bench.py: 256 planes per rank for the product, 64 for CG at 8 GPUs) rather than 2-8 planes.
+    # Product: every bit against the closed form (index arithmetic, gallery.poisson7pt_benchmark_product), through the
+    # device entry point and through host buffers (b200sp_spmv_dist_host).  CG: 40 iterations against the oracle CG of
+    # the whole operator, history within 1e-10.
+    if world > 1 and ("--production" in sys.argv or os.environ.get("DIST_CHECK_PRODUCTION") == "1"):
+        grid = (256, 256, 32 * world)
+        blk = plane_partition(grid, world, rank)
+        prod = {"grid": list(grid), "planes_per_rank": 32}
+        for fmt, tdt in (("dia", torch.float64), ("dia", torch.float32), ("ell", torch.float64), ("csr", torch.float64)):
+            A = gallery.poisson(fmt, 7, grid, dtype=tdt, row_begin=blk.row_begin, num_rows=blk.num_rows,
+                                halo_lo=blk.halo_lo, halo_hi=blk.halo_hi)
+            halo = capi.Halo(blk.halo_lo, blk.halo_hi)
+            xw = ((torch.arange(blk.window, device=dev) + blk.col_shift) % 21 - 10).to(tdt)
+            xw[:blk.halo_lo] = float("nan")
+            xw[blk.halo_lo + blk.num_rows:] = float("nan")
+            y = torch.empty(blk.num_rows, dtype=tdt, device=dev)
+            want = gallery.poisson7pt_benchmark_product(grid, blk.row_begin, blk.num_rows, tdt, dev)
+            good = 1
+            for rep in range(3):
+                if rep % world == rank:
+                    torch.cuda._sleep(2_000_000)
+                y.fill_(float("nan"))
+                h.spmv_dist(A.descriptor(), halo, xw, y)
+                good &= int(torch.equal(y, want))
+            xh = xw[blk.halo_lo:blk.halo_lo + blk.num_rows].cpu().pin_memory()
+            yh = torch.empty(blk.num_rows, dtype=tdt).pin_memory()
+            for rep in range(2):
+                yh.fill_(float("nan"))
+                h.spmv_dist_host(A.descriptor(), halo, xh, yh)
+                good &= int(torch.equal(yh, want.cpu()))
+            flags = torch.tensor([good], device=dev)
+            td.all_reduce(flags, op=td.ReduceOp.MIN)
+            prod[f"spmv_{fmt}_{'f64' if tdt == torch.float64 else 'f32'}_exact"] = int(flags.item())
+            ok = ok and bool(flags.item())
+            if fmt == "dia" and tdt == torch.float64:
+                ref = O.poisson(7, grid, np.float64, "csr")
+                nall = ref["num_rows"]
+                xo, it_o, conv_o, hist_o = O.cg(ref, np.zeros(nall), np.ones(nall), 40, 0.0)
+                del ref
+                xl = torch.zeros(blk.num_rows, dtype=tdt, device=dev)
+                bl = torch.ones(blk.num_rows, dtype=tdt, device=dev)
+                res, hist = h.cg(A.descriptor(), xl, bl, iteration_limit=40, relative_tolerance=0.0, check_interval=8,
+                                 halo=halo)
+                m = min(len(hist), len(hist_o))
+                devmax = float(np.max(np.abs(np.asarray(hist[:m]) - hist_o[:m]) / hist_o[:m]))
+                x_ok = bool(np.allclose(xl.cpu().numpy(), xo[blk.row_begin: blk.row_begin + blk.num_rows], rtol=1e-9, atol=1e-12))
+                flags = torch.tensor([int(devmax <= 1e-10 and len(hist) == len(hist_o) and int(res.iteration_count) == it_o), int(x_ok)],
+                                     device=dev)
+                td.all_reduce(flags, op=td.ReduceOp.MIN)
+                prod["cg_hist_max_rel_dev"] = devmax
+                prod["cg_hist_ok"], prod["cg_x_ok"] = int(flags[0].item()), int(flags[1].item())
+                ok = ok and bool(flags[0].item()) and bool(flags[1].item())
+            del A, xw, y, want
+            torch.cuda.empty_cache()
+        out["production"] = prod
     # skew stress: ranks take turns being late by ~1 ms before an exchange, so neighbours run one
     # exchange ahead of each other (epoch waits must be monotonic, staging double-buffered)
     if world > 1:
