@@ -48,6 +48,17 @@ class Cfg(C.Structure):
         return "Cfg(" + ", ".join(f"{k}={v}" for k, v in self.as_dict().items() if v) + ")"
 
 
+class Functors(C.Structure):
+    """b200sp_functors — (initialize, combine, reduce) of the generalized product, by code"""
+
+    _fields_ = [("initialize", C.c_int), ("init_value", C.c_double), ("combine", C.c_int), ("reduce", C.c_int)]
+
+
+INIT_CONSTANT, INIT_IDENTITY = 0, 1
+COMBINE = {"multiplies": 0, "plus": 1, "minimum": 2, "maximum": 3, "project2nd": 4}
+REDUCE = {"plus": 0, "minimum": 1, "maximum": 2}
+
+
 class Matrix(C.Structure):
     """b200sp_matrix — non-owning device matrix descriptor."""
 
@@ -122,7 +133,7 @@ _SFX = ("f32", "f64")
 EXPORTED_SYMBOLS = (
     ["b200sp_version", "b200sp_create", "b200sp_destroy", "b200sp_last_error_string",
      "b200sp_status_string", "b200sp_launch_count", "b200sp_set_l2_persist",
-     "b200sp_ell_row_lengths", "b200sp_spmv", "b200sp_spmv_host", "b200sp_cg",
+     "b200sp_ell_row_lengths", "b200sp_spmv", "b200sp_spmv_generalized", "b200sp_spmv_host", "b200sp_cg",
      "b200sp_comm_unique_id", "b200sp_comm_init", "b200sp_comm_destroy", "b200sp_cg_dist",
      "b200sp_spmv_dist", "b200sp_spmv_dist_host", "b200sp_spmv_dist_gather", "b200sp_comm_p2p_enabled", "b200sp_comm_timeouts", "b200sp_cfg_space", "b200sp_tune", "b200sp_tune_step",
      "b200sp_tune_reset", "b200sp_tune_lookup", "b200sp_tune_save", "b200sp_tune_load",
@@ -306,6 +317,13 @@ class Handle:
     def spmv(self, A: Matrix, x, y, accumulate=False, cfg: Optional[Cfg] = None):
         self.check(self.lib.b200sp_spmv(self._h, _stream(), C.byref(A), _ptr(x), _ptr(y),
                                         C.c_int(int(accumulate)), C.byref(cfg) if cfg else None))
+
+    def spmv_generalized(self, A: Matrix, x, y, initialize="constant", init_value=0.0, combine="multiplies",
+                         reduce="plus"):
+        """y[i] = reduce(initialize(y[i]), combine(a_ij, x_j) ...): cusp::multiply's 7-argument form by functor code"""
+        f = Functors(INIT_IDENTITY if initialize == "identity" else INIT_CONSTANT, float(init_value), COMBINE[combine],
+                     REDUCE[reduce])
+        self.check(self.lib.b200sp_spmv_generalized(self._h, _stream(), C.byref(A), _ptr(x), _ptr(y), C.byref(f)))
 
     def spmv_host(self, A: Matrix, x_host, y_host, accumulate=False, cfg: Optional[Cfg] = None):
         self.check(self.lib.b200sp_spmv_host(self._h, _stream(), C.byref(A), _ptr(x_host), _ptr(y_host),

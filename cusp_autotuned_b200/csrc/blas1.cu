@@ -213,7 +213,9 @@ static b200sp_status amax(b200sp_handle h, cudaStream_t st, i64 n, const T *x, i
   int *pin = reinterpret_cast<int *>(h->pinned_scalars);
   B200SP_CUDA(h, cudaMemcpyAsync(pin, idx, sizeof(int), cudaMemcpyDeviceToHost, st));
   B200SP_CUDA(h, cudaStreamSynchronize(st));
-  *index_host = *pin;
+  // all-NaN input: fmax drops NaN, no element compares equal, the index keeps its memset value;
+  // thrust::max_element returns the first element then
+  *index_host = (*pin >= 0 && (i64)*pin < n) ? *pin : 0;
   return B200SP_OK;
 }
 

@@ -530,6 +530,9 @@ b200sp_status comm_allgather_slices(b200sp_handle h, cudaStream_t st, void *x_fu
                                     size_t elem) {
   if (h->world <= 1) return B200SP_OK;
   B200SP_REQUIRE(h, x_full && slice_offsets, "allgather: null argument");
+  // the peer-memory kernels move 16-byte words relative to x_full; refusing here (on every path, so that
+  // all ranks agree) beats a misaligned-address fault inside the kernel
+  B200SP_REQUIRE(h, aligned16(x_full), "allgather: x_full must be 16-byte aligned");
   size_t max_slice = 0;
   for (int r = 0; r < h->world; ++r) {
     B200SP_REQUIRE(h, slice_offsets[r + 1] >= slice_offsets[r], "allgather: slice offsets must ascend");
@@ -685,6 +688,7 @@ b200sp_status b200sp_comm_unique_id(void *id128) {
 b200sp_status b200sp_comm_init(b200sp_handle h, const void *id128, int world_size, int rank) {
   B200SP_CHECK_HANDLE(h);
   B200SP_REQUIRE(h, id128 && world_size >= 1 && rank >= 0 && rank < world_size, "comm_init: bad arguments");
+  B200SP_REQUIRE(h, world_size <= b200sp::P2P_MAX_WORLD, "comm_init: at most 16 ranks (the GPUs of one node)");
   auto &api = b200sp::nccl();
   if (!api.ok) return b200sp::set_error(h, B200SP_COMM_ERROR, "NCCL library not found (libnccl.so.2)");
   if (h->nccl_comm) {

@@ -85,13 +85,13 @@ __device__ __forceinline__ double ld_x(const double *p) {
 
 constexpr unsigned COO_HOT_FLAG = 0x80000000u;  // remapped column: sign bit | table slot
 
-template <typename T>
+template <typename T, typename Ops>
 __device__ __forceinline__ void coo_store_y(T *y, int row, T val, int accumulate) {
-  y[row] = accumulate ? y[row] + val : val;
+  y[row] = accumulate ? Ops::reduce(y[row], val) : val;
 }
 
 // One warp, one tile of U * 32 * VPL consecutive entries.
-template <typename T, int VPL, int U, int XPOL, int SPOL, bool TABLE>
+template <typename T, int VPL, int U, int XPOL, int SPOL, bool TABLE, typename Ops>
 __device__ __forceinline__ void coo_warp_tile(const CooArgs<T> &a, const i64 tile, const int lane, const T *tab,
                                               const uint64_t pol) {
   constexpr unsigned FULL = 0xffffffffu;
@@ -103,7 +103,7 @@ __device__ __forceinline__ void coo_warp_tile(const CooArgs<T> &a, const i64 til
 
   int r[U][VPL], c[U][VPL];
   T v[U][VPL];
-  if (n == WT) {
+  if (n == WT && !a.scalar_loads) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const i64 e0 = start + u * UNIT + lane * VPL;
@@ -118,7 +118,7 @@ __device__ __forceinline__ void coo_warp_tile(const CooArgs<T> &a, const i64 til
         v[u][q] = from_words(wv + q * ((int)sizeof(T) / 4), T());
       }
     }
-  } else {  // the last tile of the matrix: guarded scalar loads, absent entries get row -1
+  } else {  // the last tile of the matrix (or unaligned arrays): guarded scalar loads, absent entries get row -1
 #pragma unroll
     for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -147,7 +147,7 @@ __device__ __forceinline__ void coo_warp_tile(const CooArgs<T> &a, const i64 til
         xv[u][q] = ld_x<XPOL>(a.x + min((unsigned)cc, cols - 1));
     }
 
-  T wcarry = T(0);        // the open row's sum since its last row end in earlier units of this tile
+  T wcarry = Ops::identity();  // the open row's sum since its last row end in earlier units of this tile
   bool seen_end = false;  // a row ended earlier in this tile (warp-uniform)
   CooCarry<T> *rec = a.carry + tile;
 #pragma unroll
@@ -158,13 +158,13 @@ __device__ __forceinline__ void coo_warp_tile(const CooArgs<T> &a, const i64 til
     if (lane == 31) rn = r_after;
 
     // serial segmented reduction over the lane's VPL consecutive entries
-    T run = T(0), head = T(0);
+    T run = Ops::identity(), head = Ops::identity();
     int head_row = -1;
     bool has_b = false;
 #pragma unroll
     for (int q = 0; q < VPL; ++q) {
-      const T p = (r[u][q] >= 0) ? v[u][q] * xv[u][q] : T(0);
-      run = run + p;
+      const T p = (r[u][q] >= 0) ? Ops::combine(v[u][q], xv[u][q]) : Ops::identity();
+      run = Ops::reduce(run, p);
       const int nxt = (q + 1 < VPL) ? r[u][(q + 1 < VPL) ? q + 1 : q] : rn;
       if (r[u][q] != nxt) {  // row r[u][q] ends at this entry
         if (!has_b) {
@@ -172,9 +172,9 @@ __device__ __forceinline__ void coo_warp_tile(const CooArgs<T> &a, const i64 til
           head_row = r[u][q];
           has_b = true;
         } else {
-          coo_store_y(a.y, r[u][q], run, a.accumulate);  // began and ended inside this lane
+          coo_store_y<T, Ops>(a.y, r[u][q], run, a.accumulate);  // began and ended inside this lane
         }
-        run = T(0);
+        run = Ops::identity();
       }
     }
 
@@ -186,21 +186,21 @@ __device__ __forceinline__ void coo_warp_tile(const CooArgs<T> &a, const i64 til
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const T up = __shfl_up_sync(FULL, vi, d);
-      if (lane - d >= j) vi = up + vi;
+      if (lane - d >= j) vi = Ops::reduce(up, vi);
     }
-    const T Vi = (le == 0) ? wcarry + vi : vi;  // no row end so far in this unit: the earlier units' sum joins
+    const T Vi = (le == 0) ? Ops::reduce(wcarry, vi) : vi;  // no row end so far in this unit: the earlier units' sum joins
     T cin = __shfl_up_sync(FULL, Vi, 1);
     if (lane == 0) cin = wcarry;
     if (has_b) {
-      const T total = cin + head;
+      const T total = Ops::reduce(cin, head);
       const bool first_end = !seen_end && (m & ((1u << lane) - 1u)) == 0;  // first row end of the tile
       if (first_end) {
         const bool continued = (head_row == prev_row);  // the row came in from the previous tile
         rec->head_row = continued ? head_row : -1;
-        rec->head_val = continued ? total : T(0);
-        if (!continued) coo_store_y(a.y, head_row, total, a.accumulate);
+        rec->head_val = continued ? total : Ops::identity();
+        if (!continued) coo_store_y<T, Ops>(a.y, head_row, total, a.accumulate);
       } else {
-        coo_store_y(a.y, head_row, total, a.accumulate);
+        coo_store_y<T, Ops>(a.y, head_row, total, a.accumulate);
       }
     }
     wcarry = __shfl_sync(FULL, Vi, 31);
@@ -209,18 +209,18 @@ __device__ __forceinline__ void coo_warp_tile(const CooArgs<T> &a, const i64 til
   if (lane == 31) {
     if (!seen_end) {
       rec->head_row = -1;
-      rec->head_val = T(0);
+      rec->head_val = Ops::identity();
     }
     const int last_row = r[U - 1][VPL - 1];
     const bool open = last_row >= 0 && last_row == next_row;
     rec->tail_row = open ? last_row : -1;
-    rec->tail_val = open ? wcarry : T(0);
+    rec->tail_val = open ? wcarry : Ops::identity();
     rec->leader = (open && last_row != prev_row) ? 1 : 0;
     rec->pad = 0;
   }
 }
 
-template <typename T, int BLOCK, int MINB, int VPL, int U, int XPOL, int SPOL, bool TABLE>
+template <typename T, int BLOCK, int MINB, int VPL, int U, int XPOL, int SPOL, bool TABLE, typename Ops = SpmvOps<T, 0, 0>>
 __global__ void __launch_bounds__(BLOCK, MINB) coo_warp_kernel(CooArgs<T> a, i64 num_tiles, const int *hot_cols,
                                                                int hot) {
   extern __shared__ __align__(16) unsigned char coo_warp_smem[];
@@ -233,10 +233,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) coo_warp_kernel(CooArgs<T> a, i64
   const i64 stride = (i64)gridDim.x * (BLOCK / 32);
   const uint64_t pol = SPOL ? l2_policy_evict_first() : 0;
   for (i64 tile = (i64)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); tile < num_tiles; tile += stride)
-    coo_warp_tile<T, VPL, U, XPOL, SPOL, TABLE>(a, tile, lane, tab, pol);
+    coo_warp_tile<T, VPL, U, XPOL, SPOL, TABLE, Ops>(a, tile, lane, tab, pol);
 }
 
-template <typename T, int BLOCK, int MINB, int VPL, int U, int XPOL, int SPOL, bool TABLE>
+template <typename T, int BLOCK, int MINB, int VPL, int U, int XPOL, int SPOL, bool TABLE, typename Ops = SpmvOps<T, 0, 0>>
 static b200sp_status launch_coo_warp(b200sp_handle h, cudaStream_t st, CooArgs<T> a, int ctas_per_sm,
                                      const int *hot_cols, int hot, int capacity) {
   constexpr int WT = 32 * VPL * U;
@@ -244,7 +244,7 @@ static b200sp_status launch_coo_warp(b200sp_handle h, cudaStream_t st, CooArgs<T
   b200sp_status s = ensure_scratch(h, (size_t)tiles * sizeof(CooCarry<T>));
   if (s != B200SP_OK) return s;
   a.carry = reinterpret_cast<CooCarry<T> *>(h->scratch);
-  auto kern = coo_warp_kernel<T, BLOCK, MINB, VPL, U, XPOL, SPOL, TABLE>;
+  auto kern = coo_warp_kernel<T, BLOCK, MINB, VPL, U, XPOL, SPOL, TABLE, Ops>;
   const size_t smem = TABLE ? (size_t)capacity * sizeof(T) : 0;
   if constexpr (TABLE) {
     if (smem > (size_t)h->max_smem_optin)
@@ -265,7 +265,9 @@ static b200sp_status launch_coo_warp(b200sp_handle h, cudaStream_t st, CooArgs<T
   }
   kern<<<(unsigned)grid, BLOCK, smem, st>>>(a, tiles, hot_cols, hot);
   B200SP_LAUNCH_CHECK(h, "coo_warp_kernel");
-  return launch_coo_fixup<T>(h, st, tiles, a.carry, a.y, a.accumulate);
+  coo_fixup_kernel<T, Ops><<<(unsigned)ceil_div(tiles, 256), 256, 0, st>>>(tiles, a.carry, a.y, a.accumulate);
+  B200SP_LAUNCH_CHECK(h, "coo_fixup_kernel");
+  return B200SP_OK;
 }
 
 }  // namespace b200sp

@@ -217,75 +217,10 @@ __global__ void __launch_bounds__(BLOCK) coo_segscan_kernel(CooArgs<T> a) {
   }
 }
 
-// Second pass: one thread per tile.  A tile whose open tail row began inside it ("leader") owns
-// that row's total: its tail, then the tails of the following tiles that lie entirely inside the
-// row, then the head of the tile in which the row ends.  Most chains are one record long and are
-// finished by the leader's own lane; a chain that goes on (a hub row spanning many tiles) is
-// walked by the whole warp, 32 records per step, with a fixed shuffle tree per step — the order
-// of additions depends only on the tile shape, never on timing.
-template <typename T>
-__global__ void coo_fixup_kernel(i64 num_tiles, const CooCarry<T> *carry, T *y, int accumulate) {
-  constexpr unsigned FULL = 0xffffffffu;
-  const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  bool leader = false, walk = false;
-  int row = -1;
-  T total = T(0);
-  if (t < num_tiles) {
-    const CooCarry<T> me = carry[t];
-    if (me.tail_row >= 0 && me.leader) {
-      leader = true;
-      row = me.tail_row;
-      total = me.tail_val;
-      if (t + 1 < num_tiles) {
-        const CooCarry<T> nx = carry[t + 1];
-        if (nx.head_row == row) {
-          total = total + nx.head_val;
-        } else if (nx.tail_row == row && !nx.leader) {
-          total = total + nx.tail_val;
-          walk = true;
-        }
-      }
-    }
-  }
-  unsigned walkers = __ballot_sync(FULL, walk);
-  while (walkers) {
-    const int src = __ffs(walkers) - 1;
-    walkers &= walkers - 1;
-    const i64 t0 = __shfl_sync(FULL, t, src);
-    const int wrow = __shfl_sync(FULL, row, src);
-    T wtot = __shfl_sync(FULL, total, src);
-    for (i64 base = t0 + 2;; base += 32) {
-      const i64 u = base + lane;
-      int cls = 2;  // 0: tile inside the row, 1: the row ends in this tile, 2: not part of the chain
-      T val = T(0);
-      if (u < num_tiles) {
-        const CooCarry<T> nx = carry[u];
-        if (nx.head_row == wrow) {
-          cls = 1;
-          val = nx.head_val;
-        } else if (nx.tail_row == wrow && !nx.leader) {
-          cls = 0;
-          val = nx.tail_val;
-        }
-      }
-      const unsigned stop = __ballot_sync(FULL, cls != 0);
-      const int first = stop ? __ffs(stop) - 1 : 32;
-      T contrib = (lane < first || (lane == first && cls == 1)) ? val : T(0);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) contrib = contrib + __shfl_xor_sync(FULL, contrib, o);
-      wtot = wtot + contrib;
-      if (stop) break;
-    }
-    if (lane == src) total = wtot;
-  }
-  if (leader) y[row] = accumulate ? y[row] + total : total;  // !accumulate: y[row] still holds the memset zero
-}
-
 template <typename T>
 b200sp_status launch_coo_fixup(b200sp_handle h, cudaStream_t st, i64 tiles, const CooCarry<T> *carry, T *y,
                                int accumulate) {
-  coo_fixup_kernel<T><<<(unsigned)ceil_div(tiles, 256), 256, 0, st>>>(tiles, carry, y, accumulate);
+  coo_fixup_kernel<T, SpmvOps<T, 0, 0>><<<(unsigned)ceil_div(tiles, 256), 256, 0, st>>>(tiles, carry, y, accumulate);
   B200SP_LAUNCH_CHECK(h, "coo_fixup_kernel");
   return B200SP_OK;
 }
@@ -560,6 +495,7 @@ b200sp_status spmv_csr_balanced(b200sp_handle h, cudaStream_t st, i64 rows, i64 
   a.carry = nullptr;
   a.Ap = Ap;
   a.tile_first_row = nullptr;
+  a.scalar_loads = 0;
 #define CASE(B, V) \
   if (block == B && vpt == V) return launch_csr_balanced<T, B, V>(h, st, a);
   CASE(128, 7) CASE(256, 5) CASE(256, 7) CASE(256, 9)
@@ -693,6 +629,7 @@ b200sp_status spmv_coo(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64
   a.carry = nullptr;
   a.Ap = nullptr;
   a.tile_first_row = nullptr;
+  a.scalar_loads = 0;
   if (c.kernel == B200SP_K_COO_WARP) {
     // vector loads need 16- / 32-byte aligned bases; otherwise the scalar-load kernel gives the same sums
     const uintptr_t m = (uintptr_t)(c.vector_width == 8 ? 31 : 15);

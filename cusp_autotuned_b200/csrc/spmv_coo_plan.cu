@@ -142,7 +142,7 @@ static b200sp_status spmv_coo_plan(b200sp_handle h, cudaStream_t st, b200sp_coo_
   CooArgs<T> a;
   a.rows = p->rows; a.cols = p->cols; a.nnz = p->nnz; a.Ai = p->Ai; a.Aj = p->Aj_remapped; a.Ax = Ax; a.x = x; a.y = y;
   a.accumulate = accumulate;
-  a.carry = nullptr; a.Ap = nullptr; a.tile_first_row = nullptr;
+  a.carry = nullptr; a.Ap = nullptr; a.tile_first_row = nullptr; a.scalar_loads = 0;
   const b200sp_cfg c = cfg ? *cfg : b200sp_cfg{};
   return spmv_coo_hot<T>(h, st, a, c, p->hot_cols, p->hot, p->capacity);
 }

@@ -511,8 +511,11 @@ static b200sp_status launch_stream(b200sp_handle h, cudaStream_t st, CsrArgs<T> 
   if (R < 32) R = 32;
   if (R > 2048) R = 2048;
   const i64 grid = ceil_div(a.rows, R);
-  if (a.dotv && grid > RED_MAX_PARTIALS)
-    return set_error(h, B200SP_INVALID_INPUT, "csr: too many CTAs for fused dot");
+  const T *late_dotv = nullptr;  // see launch_vec
+  if (a.dotv && grid > RED_MAX_PARTIALS) {
+    late_dotv = a.dotv;
+    a.dotv = nullptr;
+  }
   const size_t smem = (size_t)(CAP + 16 + R) * sizeof(T) + (size_t)(CAP + 16 + R + 1) * sizeof(int);
   auto kern = csr_stream_kernel<T, BLOCK, NPT>;
   if (smem > 48 * 1024)
@@ -520,6 +523,7 @@ static b200sp_status launch_stream(b200sp_handle h, cudaStream_t st, CsrArgs<T> 
   const int tma_aligned = aligned16(a.Aj) && aligned16(a.Ax);
   kern<<<(unsigned)grid, BLOCK, smem, st>>>(a, (int)R, tma_aligned);
   B200SP_LAUNCH_CHECK(h, "csr_stream_kernel");
+  if (late_dotv) return reduce<T, 0>(h, st, a.rows, a.y, late_dotv, a.dot_result, nullptr);
   return B200SP_OK;
 }
 
@@ -537,10 +541,16 @@ static b200sp_status dispatch_stream(b200sp_handle h, cudaStream_t st, const Csr
 template <typename T, int BLOCK, int TPR, int RPT>
 static b200sp_status launch_vec(b200sp_handle h, cudaStream_t st, CsrArgs<T> a) {
   const i64 grid = ceil_div(a.rows, (i64)(BLOCK / TPR) * RPT);
-  if (a.dotv && grid > RED_MAX_PARTIALS)
-    return set_error(h, B200SP_INVALID_INPUT, "csr: too many CTAs for fused dot");
+  // the fused <y, dotv> epilogue keeps one partial per CTA: beyond the workspace the dot runs as its own
+  // deterministic reduction after the product (as the COO / HYB / balanced paths always do)
+  const T *late_dotv = nullptr;
+  if (a.dotv && grid > RED_MAX_PARTIALS) {
+    late_dotv = a.dotv;
+    a.dotv = nullptr;
+  }
   csr_vector_kernel<T, BLOCK, TPR, RPT><<<(unsigned)grid, BLOCK, 0, st>>>(a);
   B200SP_LAUNCH_CHECK(h, "csr_vector_kernel");
+  if (late_dotv) return reduce<T, 0>(h, st, a.rows, a.y, late_dotv, a.dot_result, nullptr);
   return B200SP_OK;
 }
 

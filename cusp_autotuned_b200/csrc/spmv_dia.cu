@@ -28,6 +28,9 @@
 
 namespace b200sp {
 
+template <typename T, int MODE>
+b200sp_status reduce(b200sp_handle, cudaStream_t, i64, const T *, const T *, T *, T *);  // blas1.cu
+
 typedef FusedXchg DiaXchg;  // comm.h
 
 template <typename T>
@@ -368,10 +371,14 @@ template <typename T, int BLOCK, int RPT>
 static b200sp_status launch_ldg(b200sp_handle h, cudaStream_t st, DiaArgs<T> a, i64 nrows) {
   const i64 grid = ceil_div(nrows, (i64)BLOCK * RPT);
   if (grid == 0) return B200SP_OK;
-  if (a.dotv && grid > RED_MAX_PARTIALS)
-    return set_error(h, B200SP_INVALID_INPUT, "dia: too many CTAs for fused dot");
+  const T *late_dotv = nullptr;  // one partial per CTA: beyond the workspace the dot runs after the product
+  if (a.dotv && grid > RED_MAX_PARTIALS) {
+    late_dotv = a.dotv;
+    a.dotv = nullptr;
+  }
   dia_ldg_kernel<T, BLOCK, RPT><<<(unsigned)grid, BLOCK, 0, st>>>(a);
   B200SP_LAUNCH_CHECK(h, "dia_ldg_kernel");
+  if (late_dotv) return reduce<T, 0>(h, st, nrows, a.y + a.row_begin, late_dotv + a.row_begin, a.dot_result, nullptr);
   return B200SP_OK;
 }
 

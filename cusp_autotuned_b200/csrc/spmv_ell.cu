@@ -22,6 +22,9 @@
 
 namespace b200sp {
 
+template <typename T, int MODE>
+b200sp_status reduce(b200sp_handle, cudaStream_t, i64, const T *, const T *, T *, T *);  // blas1.cu
+
 template <typename T>
 struct EllArgs {
   i64 rows, cols, pitch;
@@ -270,10 +273,16 @@ __global__ void ell_row_lengths_kernel(i64 rows, int K, i64 pitch, const int *ci
 template <typename T, int BLOCK, int RPT>
 static b200sp_status launch_ldg(b200sp_handle h, cudaStream_t st, EllArgs<T> a) {
   const i64 grid = ceil_div(a.rows, (i64)BLOCK * RPT);
-  if (a.dotv && grid > RED_MAX_PARTIALS)
-    return set_error(h, B200SP_INVALID_INPUT, "ell: too many CTAs for fused dot");
+  // the fused <y, dotv> epilogue keeps one partial per CTA: beyond the workspace the dot runs as its own
+  // deterministic reduction after the product
+  const T *late_dotv = nullptr;
+  if (a.dotv && grid > RED_MAX_PARTIALS) {
+    late_dotv = a.dotv;
+    a.dotv = nullptr;
+  }
   ell_ldg_kernel<T, BLOCK, RPT><<<(unsigned)grid, BLOCK, 0, st>>>(a);
   B200SP_LAUNCH_CHECK(h, "ell_ldg_kernel");
+  if (late_dotv) return reduce<T, 0>(h, st, a.rows, a.y, late_dotv, a.dot_result, nullptr);
   return B200SP_OK;
 }
 

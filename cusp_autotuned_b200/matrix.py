@@ -49,6 +49,21 @@ def _check_dev(*ts):
             raise capi.InvalidInput(capi.ST_INVALID_INPUT, "container arrays must be contiguous")
 
 
+def _check_index(name, t, expected_len):
+    """index arrays are int32 in the ABI: torch's default index dtype (int64 from arange / nonzero /
+    crow_indices) would be reinterpreted by the kernels — refuse it here, and check the length the shape implies"""
+    if t.dtype != torch.int32:
+        raise capi.InvalidInput(capi.ST_INVALID_INPUT, f"{name} must be torch.int32, got {t.dtype}")
+    if expected_len is not None and t.numel() != expected_len:
+        raise capi.InvalidInput(capi.ST_INVALID_INPUT, f"{name} has {t.numel()} elements, the shape implies {expected_len}")
+
+
+def _check_values(values, min_len=None):
+    _dt(values)
+    if min_len is not None and values.numel() < min_len:
+        raise capi.InvalidInput(capi.ST_INVALID_INPUT, f"values has {values.numel()} elements, the shape needs {min_len}")
+
+
 class _Base:
     format = -1
 
@@ -65,6 +80,9 @@ class csr_matrix(_Base):
     format = capi.FMT_CSR
 
     def __init__(self, num_rows, num_cols, row_offsets, column_indices, values):
+        _check_values(values)
+        _check_index("row_offsets", row_offsets, int(num_rows) + 1)
+        _check_index("column_indices", column_indices, int(values.numel()))
         _check_dev(row_offsets, column_indices, values)
         self.num_rows, self.num_cols, self.num_entries = int(num_rows), int(num_cols), int(values.numel())
         self.row_offsets, self.column_indices, self.values = row_offsets, column_indices, values
@@ -81,6 +99,9 @@ class coo_matrix(_Base):
     format = capi.FMT_COO
 
     def __init__(self, num_rows, num_cols, row_indices, column_indices, values):
+        _check_values(values)
+        _check_index("row_indices", row_indices, int(values.numel()))
+        _check_index("column_indices", column_indices, int(values.numel()))
         _check_dev(row_indices, column_indices, values)
         self.num_rows, self.num_cols, self.num_entries = int(num_rows), int(num_cols), int(values.numel())
         self.row_indices, self.column_indices, self.values = row_indices, column_indices, values
@@ -99,6 +120,12 @@ class ell_matrix(_Base):
     invalid_index = -1
 
     def __init__(self, num_rows, num_cols, num_entries, num_cols_per_row, pitch, column_indices, values):
+        if int(pitch) < int(num_rows):
+            raise capi.InvalidInput(capi.ST_INVALID_INPUT, "ell: pitch < num_rows")
+        _check_values(values, int(num_cols_per_row) * int(pitch))
+        _check_index("column_indices", column_indices, None)
+        if column_indices.numel() < int(num_cols_per_row) * int(pitch):
+            raise capi.InvalidInput(capi.ST_INVALID_INPUT, "ell: column_indices shorter than num_cols_per_row * pitch")
         _check_dev(column_indices, values)
         self.num_rows, self.num_cols, self.num_entries = int(num_rows), int(num_cols), int(num_entries)
         self.num_cols_per_row, self.pitch = int(num_cols_per_row), int(pitch)
@@ -134,6 +161,10 @@ class dia_matrix(_Base):
     format = capi.FMT_DIA
 
     def __init__(self, num_rows, num_cols, num_entries, diagonal_offsets, pitch, values):
+        if int(pitch) < int(num_rows):
+            raise capi.InvalidInput(capi.ST_INVALID_INPUT, "dia: pitch < num_rows")
+        _check_index("diagonal_offsets", diagonal_offsets, None)
+        _check_values(values, int(diagonal_offsets.numel()) * int(pitch))
         _check_dev(diagonal_offsets, values)
         self.num_rows, self.num_cols, self.num_entries = int(num_rows), int(num_cols), int(num_entries)
         self.diagonal_offsets, self.pitch, self.values = diagonal_offsets, int(pitch), values
@@ -151,6 +182,10 @@ class hyb_matrix(_Base):
     format = capi.FMT_HYB
 
     def __init__(self, ell: ell_matrix, coo: coo_matrix):
+        if ell.values.dtype != coo.values.dtype:
+            raise capi.InvalidInput(capi.ST_INVALID_INPUT, "hyb: ell and coo parts must share one value type")
+        if (ell.num_rows, ell.num_cols) != (coo.num_rows, coo.num_cols):
+            raise capi.InvalidInput(capi.ST_INVALID_INPUT, "hyb: ell and coo parts must have the same shape")
         self.ell, self.coo = ell, coo
         self.num_rows, self.num_cols = ell.num_rows, ell.num_cols
         self.num_entries = ell.num_entries + coo.num_entries

@@ -18,7 +18,8 @@
  *   - `accumulate` selects the `initialize` functor of the reference's 7-arg
  *     multiply: 0 -> constant_functor(0)  (y  = A x,  generic/multiply.inl:158-162)
  *               1 -> identity             (y += A x,  testing/multiply.cu:514-645);
- *     `combine` is always multiplies, `reduce` always plus;
+ *     `combine` is multiplies and `reduce` plus in these entry points; other functor
+ *     triples go through b200sp_spmv_generalized;
  *   - every call is asynchronous on `stream` unless it returns a scalar to the
  *     host, in which case it synchronises that stream only;
  *   - scratch memory is owned by the handle (the reference allocates per call,
@@ -262,6 +263,32 @@ typedef struct {
 b200sp_status b200sp_spmv(b200sp_handle h, b200sp_stream stream,
                           const b200sp_matrix *A, const void *x, void *y,
                           int accumulate, const b200sp_cfg *cfg);
+
+/* ---- generalized product: y[i] = reduce(initialize(y[i]), combine(a_ij, x_j) ...) ---------------------
+ * cusp::multiply(A, x, y, initialize, combine, reduce) / cusp::generalized_spmv (cusp/multiply.h:163-280,
+ * cusp/system/detail/generic/multiply/generalized_spmv.h:61-303; the reference's device kernels are templated on
+ * the functor triple, e.g. cuda/detail/multiply/csr_vector_spmv.h:66-161).  A C ABI cannot carry C++ functor
+ * objects, so the triple is named by code; include/cusp/multiply.h maps cusp:: / thrust:: / std:: functor types to
+ * these codes and throws cusp::not_implemented_exception for anything else.  Every format of b200sp_matrix.
+ * (multiplies, plus) with constant(0) | identity is b200sp_spmv.  ELL / DIA / short-row CSR keep the host loop's
+ * order of operations (bit-identical for every pair); long-row CSR and COO regroup (exact for minimum / maximum). */
+typedef enum { B200SP_INIT_CONSTANT = 0 /* cusp::constant_functor(init_value) */, B200SP_INIT_IDENTITY = 1 } b200sp_init_op;
+typedef enum {
+  B200SP_COMBINE_MULTIPLIES = 0, /* a * x                       */
+  B200SP_COMBINE_PLUS = 1,       /* a + x        (min-plus / max-plus semirings) */
+  B200SP_COMBINE_MINIMUM = 2,    /* min(a, x)                   */
+  B200SP_COMBINE_MAXIMUM = 3,    /* max(a, x)                   */
+  B200SP_COMBINE_PROJECT2ND = 4  /* x            (structure-only products: reachability, label propagation) */
+} b200sp_combine_op;
+typedef enum { B200SP_REDUCE_PLUS = 0, B200SP_REDUCE_MINIMUM = 1, B200SP_REDUCE_MAXIMUM = 2 } b200sp_reduce_op;
+typedef struct {
+  int initialize;    /* b200sp_init_op    */
+  double init_value; /* B200SP_INIT_CONSTANT: the constant (converted to A.dtype) */
+  int combine;       /* b200sp_combine_op */
+  int reduce;        /* b200sp_reduce_op  */
+} b200sp_functors;
+b200sp_status b200sp_spmv_generalized(b200sp_handle h, b200sp_stream stream, const b200sp_matrix *A,
+                                      const void *x, void *y, const b200sp_functors *functors);
 
 /* Same product through HOST buffers: x_host -> device, SpMV, y -> y_host.
  * The matrix stays device-resident like a cusp::*_matrix<.., device_memory>;

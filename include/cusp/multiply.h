@@ -136,13 +136,39 @@ void multiply_in(host_memory, const M &A, const V1 &x, V2 &y, F0 initialize, F1 
   host_multiply(A, x, y, initialize, combine, reduce, typename M::format());
 }
 // device memory
+template <typename M, typename V1, typename V2>
+void device_generalized(const M &A, const V1 &x, V2 &y, const b200sp_functors &f, std::true_type) {
+  static_assert(std::is_same<typename M::value_type, typename V1::value_type>::value &&
+                    std::is_same<typename M::value_type, typename V2::value_type>::value,
+                "cusp::multiply on device_memory: A, x and y must share one value type (float or double)");
+  b200sp_matrix d = describe(A);
+  check(b200sp_spmv_generalized(engine(), current_stream(), &d, raw_ptr(x), raw_ptr(y), &f));
+}
+template <typename M, typename V1, typename V2>
+void device_generalized(const M &, const V1 &, V2 &, const b200sp_functors &, std::false_type) {
+  throw cusp::not_implemented_exception(
+      "cusp::multiply on device_memory: the B200 engine takes sparse matrices with 32-bit indices and float/double "
+      "values");
+}
 template <typename M, typename V1, typename V2, typename F0, typename F1, typename F2>
 void multiply_in(device_memory, const M &A, const V1 &x, V2 &y, F0 initialize, F1, F2, bool allow_dynamic_tuning) {
   const int acc = init_kind<F0>::of(initialize);
-  if (acc < 0 || !is_multiplies<F1>::value || !is_plus<F2>::value)
+  if (acc >= 0 && is_multiplies<F1>::value && is_plus<F2>::value) {  // the tuned kernels
+    device_spmv(A, x, y, acc, allow_dynamic_tuning, std::integral_constant<bool, abi_matrix<M>::value>());
+    return;
+  }
+  // any other triple the C ABI can name (b200sp_spmv_generalized): functor types -> codes
+  b200sp_functors f;
+  f.init_value = 0.0;
+  f.initialize = init_code<F0>::of(initialize, f.init_value);
+  f.combine = combine_code<F1>::value;
+  f.reduce = reduce_code<F2>::value;
+  if (f.initialize < 0 || f.combine < 0 || f.reduce < 0)
     throw cusp::not_implemented_exception(
-        "cusp::multiply on device_memory supports (constant_functor(0) | identity, multiplies, plus)");
-  device_spmv(A, x, y, acc, allow_dynamic_tuning, std::integral_constant<bool, abi_matrix<M>::value>());
+        "cusp::multiply on device_memory: initialize in {constant_functor, identity}, combine in {multiplies, plus, "
+        "minimum, maximum, project2nd}, reduce in {plus, minimum, maximum} (a C ABI cannot run user functor code on the "
+        "device)");
+  device_generalized(A, x, y, f, std::integral_constant<bool, abi_matrix<M>::value>());
 }
 
 // ---------------------------------------------------------------------------

@@ -164,6 +164,73 @@ def spmv(A: dict, x, y=None, accumulate=False, impl="oracle", nthreads=1):
 
 
 # ---------------------------------------------------------------------------
+# generalized product (numpy restatement of the reference's host loops with a functor triple)
+# ---------------------------------------------------------------------------
+_COMBINE = {"multiplies": lambda a, x: a * x, "plus": lambda a, x: a + x,
+            "minimum": lambda a, x: np.where(x < a, x, a),      # thrust::minimum: rhs < lhs ? rhs : lhs
+            "maximum": lambda a, x: np.where(a < x, x, a),      # thrust::maximum: lhs < rhs ? rhs : lhs
+            "project2nd": lambda a, x: x + 0 * a}
+_REDUCE = {"plus": lambda a, b: a + b, "minimum": lambda a, b: np.where(b < a, b, a), "maximum": lambda a, b: np.where(a < b, b, a)}
+
+
+def stored_entries(A: dict):
+    """(rows, cols, values) of the entries the reference's host loop of A's format visits, in that loop's order per
+    row: CSR / COO storage order (sequential/multiply/csr_spmv.h:44-62, coo_spmv.h:45-62); ELL slot by slot without
+    the padding (ell_spmv.h:52-72); DIA diagonal by diagonal, every slot whose column lies inside the matrix —
+    explicit zeros included (dia_spmv.h:52-79); HYB = ELL part then COO part (hyb_spmv.h:45-56)."""
+    fmt = A["format"]
+    rows, cols = int(A["num_rows"]), int(A["num_cols"])
+    if fmt == "csr":
+        return csr_to_coo(A)["row_indices"].astype(np.int64), A["column_indices"].astype(np.int64), A["values"]
+    if fmt == "coo":
+        return A["row_indices"].astype(np.int64), A["column_indices"].astype(np.int64), A["values"]
+    if fmt in ("ell", "ellr"):
+        K, pitch = int(A["num_cols_per_row"]), int(A["pitch"])
+        cj = A["column_indices"].reshape(K, pitch)[:, :rows]
+        av = A["values"].reshape(K, pitch)[:, :rows]
+        keep = cj >= 0
+        if fmt == "ellr":
+            keep &= np.arange(K)[:, None] < A["row_lengths"][None, :rows]
+        ri = np.broadcast_to(np.arange(rows)[None, :], cj.shape)
+        return ri[keep].astype(np.int64), cj[keep].astype(np.int64), av[keep]   # slot-major = per-row slot order
+    if fmt == "dia":
+        nd, pitch = len(A["diagonal_offsets"]), int(A["pitch"])
+        av = A["values"].reshape(nd, pitch)[:, :rows]
+        ri = np.broadcast_to(np.arange(rows, dtype=np.int64)[None, :], av.shape)
+        cj = ri + A["diagonal_offsets"].astype(np.int64)[:, None]
+        keep = (cj >= 0) & (cj < cols)
+        return ri[keep], cj[keep], av[keep]
+    if fmt == "hyb":
+        r1, c1, v1 = stored_entries(A["ell"])
+        r2, c2, v2 = stored_entries(A["coo"])
+        return np.concatenate([r1, r2]), np.concatenate([c1, c2]), np.concatenate([v1, v2])
+    raise ValueError(fmt)
+
+
+def spmv_generalized(A: dict, x, y, initialize="constant", init_value=0.0, combine="multiplies", reduce="plus"):
+    """y[i] = reduce(initialize(y[i]), combine(a_ij, x_j) ...) over the stored entries of row i, one entry at a time
+    in the host loop's order (cusp/multiply.h:163-195; generic/multiply/generalized_spmv.h:61-303)."""
+    vals = A["ell"]["values"] if A["format"] == "hyb" else A["values"]
+    dt = vals.dtype
+    x = _c(x, dt)
+    acc = _c(y, dt).copy() if initialize == "identity" else np.full(int(A["num_rows"]), init_value, dtype=dt)
+    ri, cj, av = stored_entries(A)
+    if len(ri) == 0:
+        return acc
+    prod = _COMBINE[combine](av.astype(dt), x[cj]).astype(dt)
+    # one entry per row per round keeps the per-row order of the reductions (and the rounding of `plus`)
+    order = np.argsort(ri, kind="stable")
+    ri, prod = ri[order], prod[order]
+    first = np.r_[0, np.flatnonzero(np.diff(ri)) + 1]
+    rank_in_row = np.arange(len(ri)) - np.repeat(first, np.diff(np.r_[first, len(ri)]))
+    red = _REDUCE[reduce]
+    for k in range(int(rank_in_row.max()) + 1):
+        sel = rank_in_row == k
+        acc[ri[sel]] = red(acc[ri[sel]], prod[sel]).astype(dt)
+    return acc
+
+
+# ---------------------------------------------------------------------------
 # BLAS-1 / CG
 # ---------------------------------------------------------------------------
 def axpy(x, y, alpha):

@@ -1,7 +1,8 @@
 // cusp::generalized_spmv — testing/generalized_spmv.cu:13-180 restated: z = y + A x with
 // (multiplies, plus) for {coo,csr,dia,ell,hyb} x {host_memory,device_memory}: the known-answer
 // 5x4 matrix, then poisson5pt / gallery::random matrices against cusp::multiply + y (exact:
-// integer-valued data).  On device_memory the call is cusp::blas::copy + b200sp_spmv(accumulate).
+// integer-valued data).  On device_memory the call is cusp::blas::copy + b200sp_spmv(accumulate); other functor
+// triples (semirings) go to b200sp_spmv_generalized (TestGeneralizedFunctors).
 #include <cusp/array2d.h>
 #include <cusp/coo_matrix.h>
 #include <cusp/csr_matrix.h>
@@ -66,6 +67,77 @@ void GeneralizedSpMV() {
     ASSERT_EQUAL(z, reference);
   }
 }
+
+// Functor triples other than (multiplies, plus): the reference's kernels are templated on them
+// (generic/multiply/generalized_spmv.h:61-303); on device_memory the shim maps the functor TYPES to the codes of
+// b200sp_spmv_generalized.  Device result == host loop result for every format (integer data: exact for plus,
+// min / max are exact on any data); a functor the ABI cannot name throws not_implemented on the device only.
+template <typename T>
+struct my_combine {
+  T operator()(const T &a, const T &b) const { return a * b + T(1); }
+};
+template <typename Matrix>
+void GeneralizedFunctors() {
+  typedef typename Matrix::value_type T;
+  typedef typename Matrix::memory_space MemorySpace;
+  const bool is_dia = std::is_same<typename Matrix::format, cusp::dia_format>::value;
+  typedef cusp::coo_matrix<int, T, cusp::host_memory> HostMatrix;
+  std::vector<HostMatrix> matrices;
+  {
+    HostMatrix M;
+    cusp::gallery::poisson5pt(M, 37, 29);
+    matrices.push_back(M);
+  }
+  if (!is_dia) {
+    HostMatrix M;
+    cusp::gallery::random(M, 355, 378, 2340);
+    for (size_t k = 0; k < M.num_entries; ++k) M.values[k] = (T)((int)(k % 9) - 4);
+    matrices.push_back(M);
+  }
+  for (size_t i = 0; i < matrices.size(); ++i) {
+    typedef typename Matrix::template rebind<cusp::host_memory>::type HostSame;
+    HostSame Mh(matrices[i]);
+    Matrix M(matrices[i]);
+    cusp::array1d<T, cusp::host_memory> xh(M.num_cols), yh(M.num_rows);
+    for (size_t k = 0; k < xh.size(); ++k) xh[k] = (T)((int)((k * 7 + i) % 11) - 5);
+    for (size_t k = 0; k < yh.size(); ++k) yh[k] = (T)((int)((k * 13 + i) % 17) - 8);
+    cusp::array1d<T, MemorySpace> x(xh);
+#define CHECK_TRIPLE(INIT, COMBINE, REDUCE)                \
+  {                                                        \
+    cusp::array1d<T, cusp::host_memory> want(yh);          \
+    cusp::multiply(Mh, xh, want, INIT, COMBINE, REDUCE);   \
+    cusp::array1d<T, MemorySpace> got(yh);                 \
+    cusp::multiply(M, x, got, INIT, COMBINE, REDUCE);      \
+    ASSERT_EQUAL(got, want);                               \
+  }
+    CHECK_TRIPLE(cusp::constant_functor<T>(T(1e30)), cusp::plus_function<T>(), cusp::minimum_function<T>())  // (min,+)
+    CHECK_TRIPLE(cusp::identity_function<T>(), cusp::plus_function<T>(), cusp::minimum_function<T>())
+    CHECK_TRIPLE(cusp::constant_functor<T>(T(-1e30)), cusp::multiplies_function<T>(), cusp::maximum_function<T>())  // (max,x)
+    CHECK_TRIPLE(cusp::constant_functor<T>(T(-1e30)), cusp::minimum_function<T>(), cusp::maximum_function<T>())  // (max,min)
+    CHECK_TRIPLE(cusp::constant_functor<T>(T(0)), cusp::project2nd_function<T>(), cusp::plus_function<T>())   // sum of x over the pattern
+    CHECK_TRIPLE(cusp::constant_functor<T>(T(3)), cusp::multiplies_function<T>(), cusp::plus_function<T>())   // y = 3 + A x
+    CHECK_TRIPLE(cusp::identity_function<T>(), cusp::maximum_function<T>(), cusp::plus_function<T>())
+#undef CHECK_TRIPLE
+    cusp::array1d<T, MemorySpace> y(yh);
+    if (std::is_same<MemorySpace, cusp::device_memory>::value) {
+      ASSERT_THROWS(cusp::multiply(M, x, y, cusp::identity_function<T>(), my_combine<T>(), cusp::plus_function<T>()),
+                    cusp::not_implemented_exception);
+    } else {
+      cusp::multiply(M, x, y, cusp::identity_function<T>(), my_combine<T>(), cusp::plus_function<T>());  // host: any functor
+    }
+  }
+}
+template <class MemorySpace>
+void TestGeneralizedFunctors() {
+  GeneralizedFunctors<cusp::coo_matrix<int, float, MemorySpace>>();
+  GeneralizedFunctors<cusp::csr_matrix<int, float, MemorySpace>>();
+  GeneralizedFunctors<cusp::dia_matrix<int, float, MemorySpace>>();
+  GeneralizedFunctors<cusp::ell_matrix<int, float, MemorySpace>>();
+  GeneralizedFunctors<cusp::hyb_matrix<int, float, MemorySpace>>();
+  GeneralizedFunctors<cusp::csr_matrix<int, double, MemorySpace>>();
+  GeneralizedFunctors<cusp::coo_matrix<int, double, MemorySpace>>();
+}
+TEST_HOST_DEVICE(TestGeneralizedFunctors)
 
 template <class MemorySpace>
 void TestGeneralizedSpMV() {

@@ -142,3 +142,30 @@ def test_release_order_checker_flags_an_unconsumed_load():
     assert sites == 1 and not flagged
     other = "\n\tFunction : _ZN6b200sp11dot_kernelIfEEvv\n" + lds + arrive  # not a ring kernel: ignored
     assert check_release_order.scan_text(other) == (0, [])
+
+
+def test_containers_refuse_wrong_index_dtype_and_lengths():
+    """torch's default index dtype is int64; the ABI takes int32 and would reinterpret the bytes.  The containers
+    refuse it, and any array whose length contradicts the shape, before a pointer reaches the library."""
+    import torch
+    from cusp_autotuned_b200 import matrix as M
+    i64 = torch.arange(4)
+    i32 = i64.to(torch.int32)
+    v3 = torch.ones(3)
+    for bad in (lambda: M.csr_matrix(3, 3, i64, i32[:3], v3),                      # int64 offsets
+                lambda: M.csr_matrix(3, 3, i32, i64[:3], v3),                      # int64 columns
+                lambda: M.csr_matrix(4, 3, i32, i32[:3], v3),                      # offsets length != rows + 1
+                lambda: M.csr_matrix(3, 3, i32, i32[:2], v3),                      # columns length != nnz
+                lambda: M.coo_matrix(3, 3, i64[:3], i32[:3], v3),
+                lambda: M.coo_matrix(3, 3, i32[:2], i32[:3], v3),
+                lambda: M.ell_matrix(3, 3, 3, 2, 4, i32, torch.ones(8)),            # indices shorter than K * pitch
+                lambda: M.ell_matrix(3, 3, 3, 1, 2, i32, torch.ones(8)),            # pitch < rows
+                lambda: M.dia_matrix(3, 3, 3, i64[:1], 3, v3),
+                lambda: M.dia_matrix(3, 3, 3, i32[:2], 3, v3),                      # values shorter than ndiag * pitch
+                lambda: M.csr_matrix(3, 3, i32, i32[:3], torch.ones(3, dtype=torch.float16))):
+        with pytest.raises(capi.InvalidInput):
+            bad()
+    # well-formed host tensors get as far as the device check ("no CPU fallback" behind device containers)
+    with pytest.raises(capi.InvalidInput) as e:
+        M.csr_matrix(3, 3, i32, i32[:3], v3)
+    assert "host tensor" in str(e.value)

@@ -567,3 +567,63 @@ def test_csr_block_multiply_bit_exact(ndt, tdt, dev):
     assert torch.equal(Y, torch.zeros_like(Y))
     with pytest.raises(capi.InvalidInput):
         cusp.multiply_block(A0, torch.ones(4, 3, dtype=tdt, device=dev), Y)
+
+
+# ---------------------------------------------------------------------------
+# generalized product (b200sp_spmv_generalized): functor triples by code
+# ---------------------------------------------------------------------------
+GEN_TRIPLES = [("constant", 1e30, "plus", "minimum"), ("identity", 0.0, "plus", "minimum"),
+               ("constant", -1e30, "multiplies", "maximum"), ("constant", -1e30, "minimum", "maximum"),
+               ("constant", 0.0, "project2nd", "plus"), ("constant", 3.0, "multiplies", "plus"),
+               ("identity", 0.0, "maximum", "plus"), ("constant", 1e30, "maximum", "minimum"),
+               ("identity", 0.0, "multiplies", "plus"), ("constant", 0.0, "multiplies", "plus"),
+               ("constant", 2.0, "plus", "plus"), ("identity", 0.0, "project2nd", "maximum")]
+
+
+@pytest.mark.parametrize("ndt,tdt", DTYPES)
+@pytest.mark.parametrize("fmt", FORMATS)
+def test_generalized_functor_triples(fmt, ndt, tdt, dev, handle):
+    """every (initialize, combine, reduce) code x every format against the numpy restatement of the reference's host
+    loops (oracle.spmv_generalized, pinned to the C oracle for the default triple): integer-valued data -> exact for
+    every pair; rows with no entries get initialize(y) only; long rows (sub-warp CSR, COO tiles, hub rows)."""
+    rng = np.random.default_rng(31)
+    mats = [O.poisson(5, (37, 29), ndt, "coo")]
+    if fmt != "dia":
+        for m, n, s in ((355, 378, 2340), (64, 3000, 60000)):   # ragged rows; 64 long rows (~900 entries each)
+            coo = O.gallery_random(m, n, s, ndt, "coo")
+            coo["values"] = rng.integers(-4, 5, coo["num_entries"]).astype(ndt)
+            mats.append(coo)
+    for coo in mats:
+        A = to_fmt(coo, fmt)
+        Ad = upload_any(fmt, A, dev)
+        x = rng.integers(-5, 6, coo["num_cols"]).astype(ndt)
+        y0 = rng.integers(-8, 9, coo["num_rows"]).astype(ndt)
+        xd = tdev(x, dev)
+        for init, c0, comb, red in GEN_TRIPLES:
+            want = O.spmv_generalized(A, x, y0, init, c0, comb, red)
+            yd = tdev(y0, dev)
+            handle.spmv_generalized(Ad.descriptor(), xd, yd, init, c0, comb, red)
+            assert np.array_equal(yd.cpu().numpy(), want), (fmt, init, c0, comb, red, coo["num_rows"])
+
+
+def test_generalized_min_plus_on_real_data(dev, handle):
+    """(min, +) on non-integer data: min is exact, so any grouping gives the host loop's bits — one relaxation step of
+    single-source shortest paths on a weighted R-MAT-like graph, all formats"""
+    rng = np.random.default_rng(32)
+    n, nnz = 20000, 400000
+    rows = np.sort(rng.integers(0, n, nnz)).astype(np.int32)
+    rows[3000:150000] = rows[3000]          # a hub row
+    rows = np.sort(rows)
+    cols = rng.integers(0, n, nnz).astype(np.int32)
+    key = np.unique(rows.astype(np.int64) * n + cols)
+    rows, cols = (key // n).astype(np.int32), (key % n).astype(np.int32)
+    w = rng.uniform(0.1, 5.0, len(key)).astype(np.float32)
+    coo = dict(format="coo", num_rows=n, num_cols=n, num_entries=len(key), row_indices=rows, column_indices=cols, values=w)
+    dist = np.full(n, 1e30, np.float32)
+    dist[rng.integers(0, n, 50)] = rng.uniform(0, 3, 50).astype(np.float32)
+    for fmt in ("coo", "csr", "hyb"):
+        A = to_fmt(coo, fmt)
+        want = O.spmv_generalized(A, dist, dist, "identity", 0.0, "plus", "minimum")
+        yd = tdev(dist, dev)
+        handle.spmv_generalized(upload_any(fmt, A, dev).descriptor(), tdev(dist, dev), yd, "identity", 0.0, "plus", "minimum")
+        assert np.array_equal(yd.cpu().numpy(), want), fmt
