@@ -139,7 +139,9 @@ EXPORTED_SYMBOLS = (
      "b200sp_tune_reset", "b200sp_tune_lookup", "b200sp_tune_save", "b200sp_tune_load",
      "b200sp_poisson_num_entries", "b200sp_poisson_csr_offsets",
      "b200sp_offsets_to_indices", "b200sp_indices_to_offsets", "b200sp_csr_convert_query"]
-    + [f"b200sp_{op}_{s}" for op in ("csr_to_ell", "csr_to_coo_tail", "csr_to_dia", "count_zeros") for s in _SFX]
+    + [f"b200sp_{op}_{s}" for op in ("csr_to_ell", "csr_to_coo_tail", "csr_to_dia", "count_zeros", "dia_to_ell",
+                                       "dia_to_csr_offsets", "dia_to_csr_fill", "ell_to_csr_offsets", "ell_to_csr_fill",
+                                       "hyb_to_csr_offsets", "hyb_to_csr_fill") for s in _SFX]
     + [f"b200sp_spmv_{f}_{s}" for f in ("csr", "ell", "dia", "coo", "hyb", "ellr") for s in _SFX]
     + [f"b200sp_{op}_{s}" for op in ("axpy", "axpby", "axpbypcz", "xmy", "copy", "fill", "scal", "dot", "nrm2", "asum", "nrmmax",
                                        "amax") for s in _SFX]
@@ -522,6 +524,50 @@ class Handle:
         f = getattr(self.lib, "b200sp_csr_to_ell_" + _sfx(values.dtype))
         self.check(f(self._h, _stream(), C.c_int64(num_rows), C.c_int64(K), C.c_int64(pitch), _ptr(row_offsets),
                      _ptr(column_indices), _ptr(values), _ptr(ell_cidx), _ptr(ell_vals)))
+
+    # DIA / ELL / HYB -> CSR on the device: `_offsets` (row_offsets + the entry count), then `_fill`
+    def dia_to_csr_offsets(self, num_rows, nd, pitch, values, row_offsets) -> int:
+        n = C.c_int64(0)
+        f = getattr(self.lib, "b200sp_dia_to_csr_offsets_" + _sfx(values.dtype))
+        self.check(f(self._h, _stream(), C.c_int64(num_rows), C.c_int64(nd), C.c_int64(pitch), _ptr(values),
+                     _ptr(row_offsets), C.byref(n)))
+        return n.value
+
+    def dia_to_csr_fill(self, num_rows, nd, pitch, offsets, values, row_offsets, column_indices, csr_values):
+        f = getattr(self.lib, "b200sp_dia_to_csr_fill_" + _sfx(values.dtype))
+        self.check(f(self._h, _stream(), C.c_int64(num_rows), C.c_int64(nd), C.c_int64(pitch), _ptr(offsets), _ptr(values),
+                     _ptr(row_offsets), _ptr(column_indices), _ptr(csr_values)))
+
+    def ell_to_csr_offsets(self, num_rows, K, pitch, cidx, values, row_offsets) -> int:
+        n = C.c_int64(0)
+        f = getattr(self.lib, "b200sp_ell_to_csr_offsets_" + _sfx(values.dtype))
+        self.check(f(self._h, _stream(), C.c_int64(num_rows), C.c_int64(K), C.c_int64(pitch), _ptr(cidx), _ptr(values),
+                     _ptr(row_offsets), C.byref(n)))
+        return n.value
+
+    def ell_to_csr_fill(self, num_rows, K, pitch, cidx, values, row_offsets, column_indices, csr_values):
+        f = getattr(self.lib, "b200sp_ell_to_csr_fill_" + _sfx(values.dtype))
+        self.check(f(self._h, _stream(), C.c_int64(num_rows), C.c_int64(K), C.c_int64(pitch), _ptr(cidx), _ptr(values),
+                     _ptr(row_offsets), _ptr(column_indices), _ptr(csr_values)))
+
+    def hyb_to_csr_offsets(self, num_rows, K, pitch, cidx, values, cnnz, coo_ri, row_offsets) -> int:
+        n = C.c_int64(0)
+        f = getattr(self.lib, "b200sp_hyb_to_csr_offsets_" + _sfx(values.dtype))
+        self.check(f(self._h, _stream(), C.c_int64(num_rows), C.c_int64(K), C.c_int64(pitch), _ptr(cidx), _ptr(values),
+                     C.c_int64(cnnz), _ptr(coo_ri), _ptr(row_offsets), C.byref(n)))
+        return n.value
+
+    def hyb_to_csr_fill(self, num_rows, K, pitch, cidx, values, cnnz, coo_ri, coo_ci, coo_v, row_offsets, column_indices,
+                        csr_values):
+        f = getattr(self.lib, "b200sp_hyb_to_csr_fill_" + _sfx(values.dtype))
+        self.check(f(self._h, _stream(), C.c_int64(num_rows), C.c_int64(K), C.c_int64(pitch), _ptr(cidx), _ptr(values),
+                     C.c_int64(cnnz), _ptr(coo_ri), _ptr(coo_ci), _ptr(coo_v), _ptr(row_offsets), _ptr(column_indices),
+                     _ptr(csr_values)))
+
+    def dia_to_ell(self, num_rows, nd, pitch, offsets, values, ell_cidx, ell_vals):
+        f = getattr(self.lib, "b200sp_dia_to_ell_" + _sfx(values.dtype))
+        self.check(f(self._h, _stream(), C.c_int64(num_rows), C.c_int64(nd), C.c_int64(pitch), _ptr(offsets), _ptr(values),
+                     _ptr(ell_cidx), _ptr(ell_vals)))
 
     def csr_to_coo_tail(self, num_rows, K, row_offsets, column_indices, values, coo_ri, coo_ci, coo_v):
         f = getattr(self.lib, "b200sp_csr_to_coo_tail_" + _sfx(values.dtype))

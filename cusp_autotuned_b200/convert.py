@@ -133,3 +133,67 @@ def csr_to_dia(A: csr_matrix, alignment: int = 32) -> dia_matrix:
     vals = torch.empty(max(nd * pitch, 1), dtype=A.values.dtype, device=dev)[:nd * pitch]
     h.csr_to_dia(A.num_rows, A.num_cols, nd, pitch, A.row_offsets, A.column_indices, A.values, offs, vals)
     return dia_matrix(A.num_rows, A.num_cols, A.num_entries, offs, pitch, vals)
+
+
+def _empty(n, dtype, dev):
+    return torch.empty(max(int(n), 1), dtype=dtype, device=dev)[:int(n)]
+
+
+def dia_to_csr(A: dia_matrix) -> csr_matrix:
+    """dia_to_other.h:110-161: row-major scan, value != 0 kept (b200sp_dia_to_csr_offsets / _fill)"""
+    h, dev = default_handle(), A.values.device
+    offs = torch.empty(A.num_rows + 1, dtype=torch.int32, device=dev)
+    n = h.dia_to_csr_offsets(A.num_rows, A.num_diagonals, A.pitch, A.values, offs)
+    cj, cv = _empty(n, torch.int32, dev), _empty(n, A.values.dtype, dev)
+    h.dia_to_csr_fill(A.num_rows, A.num_diagonals, A.pitch, A.diagonal_offsets, A.values, offs, cj, cv)
+    return csr_matrix(A.num_rows, A.num_cols, offs, cj, cv)
+
+
+def ell_to_csr(A: ell_matrix) -> csr_matrix:
+    """ell_to_other.h:100-143: row-major scan, value != 0 kept (b200sp_ell_to_csr_offsets / _fill)"""
+    h, dev = default_handle(), A.values.device
+    offs = torch.empty(A.num_rows + 1, dtype=torch.int32, device=dev)
+    n = h.ell_to_csr_offsets(A.num_rows, A.num_cols_per_row, A.pitch, A.column_indices, A.values, offs)
+    cj, cv = _empty(n, torch.int32, dev), _empty(n, A.values.dtype, dev)
+    h.ell_to_csr_fill(A.num_rows, A.num_cols_per_row, A.pitch, A.column_indices, A.values, offs, cj, cv)
+    return csr_matrix(A.num_rows, A.num_cols, offs, cj, cv)
+
+
+def hyb_to_csr(A: hyb_matrix) -> csr_matrix:
+    """hyb_to_other.h:45-56 + detail/coo_matrix.inl:269-341: ELL entries with a valid column merged with the COO
+    entries by (row, column) (b200sp_hyb_to_csr_offsets / _fill)"""
+    h, dev = default_handle(), A.ell.values.device
+    e, c = A.ell, A.coo
+    offs = torch.empty(A.num_rows + 1, dtype=torch.int32, device=dev)
+    n = h.hyb_to_csr_offsets(A.num_rows, e.num_cols_per_row, e.pitch, e.column_indices, e.values, c.num_entries,
+                             c.row_indices, offs)
+    cj, cv = _empty(n, torch.int32, dev), _empty(n, e.values.dtype, dev)
+    h.hyb_to_csr_fill(A.num_rows, e.num_cols_per_row, e.pitch, e.column_indices, e.values, c.num_entries, c.row_indices,
+                      c.column_indices, c.values, offs, cj, cv)
+    return csr_matrix(A.num_rows, A.num_cols, offs, cj, cv)
+
+
+def dia_to_ell(A: dia_matrix) -> ell_matrix:
+    """dia_to_other.h:163-251: K = #diagonals, pitch = the DIA pitch, non-zeros left-packed (b200sp_dia_to_ell)"""
+    h, dev = default_handle(), A.values.device
+    K, p = A.num_diagonals, A.pitch
+    cidx, vals = _empty(K * p, torch.int32, dev), _empty(K * p, A.values.dtype, dev)
+    h.dia_to_ell(A.num_rows, K, p, A.diagonal_offsets, A.values, cidx, vals)
+    return ell_matrix(A.num_rows, A.num_cols, A.num_entries, K, p, cidx, vals)
+
+
+def convert(A, fmt: str, **kw):
+    """cusp::convert(src, dst) for device containers, every source x destination pair, on the device: the formats
+    meet in CSR (the reference meets in COO/CSR too; the layouts are the rules of generic/conversions/*.h)."""
+    src = {capi.FMT_CSR: "csr", capi.FMT_COO: "coo", capi.FMT_DIA: "dia", capi.FMT_ELL: "ell", capi.FMT_HYB: "hyb",
+           capi.FMT_ELLR: "ell"}[A.format]
+    if src == fmt:
+        return A
+    if src == "dia" and fmt == "ell":
+        return dia_to_ell(A)
+    if src == "ell" and fmt == "hyb":  # ell_to_other.h:145-163: the ELL part is the matrix, the COO part is empty
+        dev = A.values.device
+        z = lambda dt: torch.empty(1, dtype=dt, device=dev)[:0]
+        return hyb_matrix(A, coo_matrix(A.num_rows, A.num_cols, z(torch.int32), z(torch.int32), z(A.values.dtype)))
+    csr = {"csr": lambda M: M, "coo": coo_to_csr, "dia": dia_to_csr, "ell": ell_to_csr, "hyb": hyb_to_csr}[src](A)
+    return {"csr": lambda M: M, "coo": csr_to_coo, "ell": csr_to_ell, "hyb": csr_to_hyb, "dia": csr_to_dia}[fmt](csr, **kw)

@@ -293,9 +293,225 @@ static b200sp_status csr_to_dia_impl(b200sp_handle h, cudaStream_t st, i64 rows,
   return B200SP_OK;
 }
 
+// ---------------------------------------------------------------------------
+// slab formats (DIA / ELL / the ELL part of HYB) -> CSR
+//   DIA : dia_to_other.h:61-161   row-major scan of the [rows x ndiag] logical array, keep value != 0,
+//         column = row + diagonal_offsets[d]
+//   ELL : ell_to_other.h:55-143   row-major scan of the [rows x K] logical array, keep value != 0
+//   HYB : hyb_to_other.h:45-56 + cusp/detail/coo_matrix.inl:269-341: ELL entries whose COLUMN is valid (not
+//         value != 0) merged with the COO entries by (row, column), ties ELL first — per row a two-pointer merge
+//         of the row's ELL slots and its COO entries (for a HYB made by cusp::convert: the ELL entries, then the
+//         COO entries).
+// Two passes like a CSR build always is: entries kept per row -> exclusive scan = row_offsets -> fill.
+// One thread per row; the slab reads are coalesced (column-major), the CSR writes are contiguous per row.
+// ---------------------------------------------------------------------------
+enum { SLAB_DIA = 0, SLAB_ELL = 1, SLAB_HYB = 2 };
+
+template <typename T, int KIND>
+__device__ __forceinline__ bool slab_keep(T v, int c) {
+  return KIND == SLAB_HYB ? (c >= 0) : (v != T(0));
+}
+
+template <typename T, int KIND>
+__global__ void slab_count_kernel(i64 rows, int K, i64 pitch, const int *cidx, const T *vals, const int *coo_offsets,
+                                  int *lens) {
+  const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > rows) return;
+  int n = 0;
+  if (r < rows) {
+    for (int k = 0; k < K; ++k) {
+      const T v = vals[(i64)k * pitch + r];
+      const int c = KIND == SLAB_DIA ? 0 : cidx[(i64)k * pitch + r];
+      n += slab_keep<T, KIND>(v, c) ? 1 : 0;
+    }
+    if (KIND == SLAB_HYB && coo_offsets) n += coo_offsets[r + 1] - coo_offsets[r];
+  }
+  lens[r] = n;  // lens[rows] = 0: the scan leaves the total there
+}
+
+template <typename T, int KIND>
+__global__ void slab_fill_kernel(i64 rows, int K, i64 pitch, const int *cidx_or_offs, const T *vals,
+                                 const int *coo_offsets, const int *coo_cols, const T *coo_vals, const int *Ap, int *Aj,
+                                 T *Ax) {
+  const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  i64 o = Ap[r];
+  int j = (KIND == SLAB_HYB && coo_offsets) ? coo_offsets[r] : 0;
+  const int jend = (KIND == SLAB_HYB && coo_offsets) ? coo_offsets[r + 1] : 0;
+  for (int k = 0; k < K; ++k) {
+    const T v = vals[(i64)k * pitch + r];
+    const int c = KIND == SLAB_DIA ? (int)(r + cidx_or_offs[k]) : cidx_or_offs[(i64)k * pitch + r];
+    if (KIND == SLAB_HYB)  // merge by column: the row's COO entries with a smaller column come first (ties: ELL first)
+      for (; j < jend && coo_cols[j] < c; ++j) {
+        Aj[o] = coo_cols[j];
+        Ax[o] = coo_vals[j];
+        ++o;
+      }
+    if (slab_keep<T, KIND>(v, KIND == SLAB_DIA ? 0 : c)) {
+      Aj[o] = c;
+      Ax[o] = v;
+      ++o;
+    }
+  }
+  if (KIND == SLAB_HYB)
+    for (; j < jend; ++j) {
+      Aj[o] = coo_cols[j];
+      Ax[o] = coo_vals[j];
+      ++o;
+    }
+}
+
+// DIA -> ELL as the fork does it (dia_to_other.h:163-251): K = #diagonals, pitch = the DIA pitch, the non-zero
+// values of every row left-packed in diagonal order, column -1 / value 0 behind them and in the padding rows.
+// (The reference issues two stable_partition calls per ROW; this is one thread per row.)
+template <typename T>
+__global__ void dia_to_ell_kernel(i64 rows, int K, i64 pitch, const int *offs, const T *vals, int *cidx, T *evals) {
+  const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= pitch) return;
+  int o = 0;
+  if (r < rows)
+    for (int d = 0; d < K; ++d) {
+      const T v = vals[(i64)d * pitch + r];
+      if (v != T(0)) {
+        cidx[(i64)o * pitch + r] = (int)(r + offs[d]);
+        evals[(i64)o * pitch + r] = v;
+        ++o;
+      }
+    }
+  for (; o < K; ++o) {
+    cidx[(i64)o * pitch + r] = -1;
+    evals[(i64)o * pitch + r] = T(0);
+  }
+}
+
+template <typename T, int KIND>
+static b200sp_status slab_offsets_impl(b200sp_handle h, cudaStream_t st, i64 rows, i64 K, i64 pitch, const int *cidx,
+                                       const T *vals, i64 coo_nnz, const int *coo_rows, int *row_offsets,
+                                       int64_t *num_entries_host) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, rows >= 0 && K >= 0 && K < (1 << 30) && pitch >= rows && row_offsets, "to_csr: bad arguments");
+  B200SP_REQUIRE(h, K == 0 || (vals && (KIND == SLAB_DIA || cidx)), "to_csr: null slab");
+  DevTemp tmp, coo_off;
+  b200sp_status s = tmp.alloc(h, (size_t)scan_tmp_ints(rows + 1) * sizeof(int));
+  if (s != B200SP_OK) return s;
+  const int *coff = nullptr;
+  if (KIND == SLAB_HYB && coo_nnz > 0) {
+    B200SP_REQUIRE(h, coo_rows, "hyb_to_csr: null coo row indices");
+    s = coo_off.alloc(h, (size_t)(rows + 1) * sizeof(int));
+    if (s != B200SP_OK) return s;
+    indices_to_offsets_kernel<<<(unsigned)ceil_div(rows + 1, 256), 256, 0, st>>>(rows, coo_nnz, coo_rows,
+                                                                                 reinterpret_cast<int *>(coo_off.p));
+    B200SP_LAUNCH_CHECK(h, "indices_to_offsets_kernel");
+    coff = reinterpret_cast<int *>(coo_off.p);
+  }
+  slab_count_kernel<T, KIND><<<(unsigned)ceil_div(rows + 1, 256), 256, 0, st>>>(rows, (int)K, pitch, cidx, vals, coff,
+                                                                                 row_offsets);
+  B200SP_LAUNCH_CHECK(h, "slab_count_kernel");
+  s = scan_exclusive(h, st, rows + 1, row_offsets, row_offsets, reinterpret_cast<int *>(tmp.p));
+  if (s != B200SP_OK) return s;
+  int total = 0;
+  B200SP_CUDA(h, cudaMemcpyAsync(&total, row_offsets + rows, sizeof(int), cudaMemcpyDeviceToHost, st));
+  B200SP_CUDA(h, cudaStreamSynchronize(st));
+  if (num_entries_host) *num_entries_host = total;
+  return B200SP_OK;
+}
+
+template <typename T, int KIND>
+static b200sp_status slab_fill_impl(b200sp_handle h, cudaStream_t st, i64 rows, i64 K, i64 pitch, const int *cidx_or_offs,
+                                    const T *vals, i64 coo_nnz, const int *coo_rows, const int *coo_cols,
+                                    const T *coo_vals, const int *row_offsets, int *Aj, T *Ax) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, rows >= 0 && K >= 0 && pitch >= rows && row_offsets, "to_csr: bad arguments");
+  if (rows == 0) return B200SP_OK;
+  DevTemp coo_off;
+  const int *coff = nullptr;
+  if (KIND == SLAB_HYB && coo_nnz > 0) {
+    B200SP_REQUIRE(h, coo_rows && coo_cols && coo_vals, "hyb_to_csr: null coo arrays");
+    b200sp_status s = coo_off.alloc(h, (size_t)(rows + 1) * sizeof(int));
+    if (s != B200SP_OK) return s;
+    indices_to_offsets_kernel<<<(unsigned)ceil_div(rows + 1, 256), 256, 0, st>>>(rows, coo_nnz, coo_rows,
+                                                                                 reinterpret_cast<int *>(coo_off.p));
+    B200SP_LAUNCH_CHECK(h, "indices_to_offsets_kernel");
+    coff = reinterpret_cast<int *>(coo_off.p);
+  }
+  slab_fill_kernel<T, KIND><<<(unsigned)ceil_div(rows, 256), 256, 0, st>>>(rows, (int)K, pitch, cidx_or_offs, vals, coff,
+                                                                            coo_cols, coo_vals, row_offsets, Aj, Ax);
+  B200SP_LAUNCH_CHECK(h, "slab_fill_kernel");
+  if (coff) B200SP_CUDA(h, cudaStreamSynchronize(st));  // the temporary dies with this frame
+  return B200SP_OK;
+}
+
 }  // namespace b200sp
 
 extern "C" {
+
+#define DEF_SLAB(T, sfx)                                                                                              \
+  b200sp_status b200sp_dia_to_csr_offsets_##sfx(b200sp_handle h, b200sp_stream s, int64_t num_rows,                   \
+                                                int64_t num_diagonals, int64_t pitch, const T *values,                \
+                                                int32_t *row_offsets, int64_t *num_entries_host) {                    \
+    return b200sp::slab_offsets_impl<T, b200sp::SLAB_DIA>(h, (cudaStream_t)s, num_rows, num_diagonals, pitch, nullptr, \
+                                                          values, 0, nullptr, row_offsets, num_entries_host);         \
+  }                                                                                                                   \
+  b200sp_status b200sp_dia_to_csr_fill_##sfx(b200sp_handle h, b200sp_stream s, int64_t num_rows,                      \
+                                             int64_t num_diagonals, int64_t pitch, const int32_t *diagonal_offsets,   \
+                                             const T *values, const int32_t *row_offsets, int32_t *column_indices,    \
+                                             T *csr_values) {                                                         \
+    if (h && num_diagonals > 0 && !diagonal_offsets)                                                                  \
+      return b200sp::set_error(h, B200SP_INVALID_INPUT, "dia_to_csr: null diagonal offsets");                         \
+    return b200sp::slab_fill_impl<T, b200sp::SLAB_DIA>(h, (cudaStream_t)s, num_rows, num_diagonals, pitch,            \
+                                                       diagonal_offsets, values, 0, nullptr, nullptr, nullptr,        \
+                                                       row_offsets, column_indices, csr_values);                      \
+  }                                                                                                                   \
+  b200sp_status b200sp_ell_to_csr_offsets_##sfx(b200sp_handle h, b200sp_stream s, int64_t num_rows,                   \
+                                                int64_t num_cols_per_row, int64_t pitch,                              \
+                                                const int32_t *ell_column_indices, const T *ell_values,               \
+                                                int32_t *row_offsets, int64_t *num_entries_host) {                    \
+    return b200sp::slab_offsets_impl<T, b200sp::SLAB_ELL>(h, (cudaStream_t)s, num_rows, num_cols_per_row, pitch,      \
+                                                          ell_column_indices, ell_values, 0, nullptr, row_offsets,    \
+                                                          num_entries_host);                                          \
+  }                                                                                                                   \
+  b200sp_status b200sp_ell_to_csr_fill_##sfx(b200sp_handle h, b200sp_stream s, int64_t num_rows,                      \
+                                             int64_t num_cols_per_row, int64_t pitch,                                 \
+                                             const int32_t *ell_column_indices, const T *ell_values,                  \
+                                             const int32_t *row_offsets, int32_t *column_indices, T *csr_values) {    \
+    return b200sp::slab_fill_impl<T, b200sp::SLAB_ELL>(h, (cudaStream_t)s, num_rows, num_cols_per_row, pitch,         \
+                                                       ell_column_indices, ell_values, 0, nullptr, nullptr, nullptr,  \
+                                                       row_offsets, column_indices, csr_values);                      \
+  }                                                                                                                   \
+  b200sp_status b200sp_hyb_to_csr_offsets_##sfx(b200sp_handle h, b200sp_stream s, int64_t num_rows,                   \
+                                                int64_t ell_cols_per_row, int64_t ell_pitch,                          \
+                                                const int32_t *ell_column_indices, const T *ell_values,               \
+                                                int64_t coo_num_entries, const int32_t *coo_row_indices,              \
+                                                int32_t *row_offsets, int64_t *num_entries_host) {                    \
+    return b200sp::slab_offsets_impl<T, b200sp::SLAB_HYB>(h, (cudaStream_t)s, num_rows, ell_cols_per_row, ell_pitch,  \
+                                                          ell_column_indices, ell_values, coo_num_entries,            \
+                                                          coo_row_indices, row_offsets, num_entries_host);            \
+  }                                                                                                                   \
+  b200sp_status b200sp_hyb_to_csr_fill_##sfx(                                                                         \
+      b200sp_handle h, b200sp_stream s, int64_t num_rows, int64_t ell_cols_per_row, int64_t ell_pitch,                \
+      const int32_t *ell_column_indices, const T *ell_values, int64_t coo_num_entries,                                \
+      const int32_t *coo_row_indices, const int32_t *coo_column_indices, const T *coo_values,                         \
+      const int32_t *row_offsets, int32_t *column_indices, T *csr_values) {                                           \
+    return b200sp::slab_fill_impl<T, b200sp::SLAB_HYB>(h, (cudaStream_t)s, num_rows, ell_cols_per_row, ell_pitch,     \
+                                                       ell_column_indices, ell_values, coo_num_entries,               \
+                                                       coo_row_indices, coo_column_indices, coo_values, row_offsets,  \
+                                                       column_indices, csr_values);                                   \
+  }                                                                                                                   \
+  b200sp_status b200sp_dia_to_ell_##sfx(b200sp_handle h, b200sp_stream s, int64_t num_rows, int64_t num_diagonals,    \
+                                        int64_t pitch, const int32_t *diagonal_offsets, const T *values,              \
+                                        int32_t *ell_column_indices, T *ell_values) {                                 \
+    B200SP_CHECK_HANDLE(h);                                                                                           \
+    B200SP_REQUIRE(h, num_rows >= 0 && num_diagonals >= 0 && pitch >= num_rows, "dia_to_ell: bad dimensions");        \
+    if (num_diagonals == 0 || pitch == 0) return B200SP_OK;                                                           \
+    B200SP_REQUIRE(h, diagonal_offsets && values && ell_column_indices && ell_values, "dia_to_ell: null pointer");    \
+    b200sp::dia_to_ell_kernel<T><<<(unsigned)b200sp::ceil_div(pitch, 256), 256, 0, (cudaStream_t)s>>>(                \
+        num_rows, (int)num_diagonals, pitch, diagonal_offsets, values, ell_column_indices, ell_values);               \
+    B200SP_LAUNCH_CHECK(h, "dia_to_ell_kernel");                                                                      \
+    return B200SP_OK;                                                                                                 \
+  }
+DEF_SLAB(float, f32)
+DEF_SLAB(double, f64)
+#undef DEF_SLAB
 
 b200sp_status b200sp_offsets_to_indices(b200sp_handle h, b200sp_stream stream, int64_t num_rows,
                                         const int32_t *row_offsets, int32_t *row_indices) {

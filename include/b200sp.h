@@ -560,6 +560,54 @@ B200SP_DECL_CONVERT(float, f32)
 B200SP_DECL_CONVERT(double, f64)
 #undef B200SP_DECL_CONVERT
 
+/* DIA / ELL / HYB sources: to CSR on the device (and from there to every other format with the calls above), in two
+ * steps because the caller owns the outputs: `_offsets` computes row_offsets[num_rows + 1] and returns the number of
+ * kept entries to the host (synchronises), `_fill` writes column_indices / values of that size.
+ *   DIA  row-major scan of the [rows x diagonals] slab, keeps value != 0, column = row + diagonal_offsets[d]
+ *        cusp/system/detail/generic/conversions/dia_to_other.h:61-161
+ *   ELL  row-major scan of the [rows x K] slabs, keeps value != 0                           ell_to_other.h:55-143
+ *   HYB  per row the ELL entries with a valid column merged by column with the row's COO entries (ties: ELL first)
+ *        hyb_to_other.h:45-56, cusp/detail/coo_matrix.inl:269-341
+ * b200sp_dia_to_ell: the fork's direct DIA -> ELL (dia_to_other.h:163-251): K = num_diagonals, pitch = the DIA pitch,
+ * non-zero values left-packed per row in diagonal order, padding column -1 / value 0 — one thread per row instead of
+ * two thrust::stable_partition calls per row. */
+#define B200SP_DECL_TO_CSR(T, sfx)                                                                    \
+  b200sp_status b200sp_dia_to_csr_offsets_##sfx(b200sp_handle h, b200sp_stream s, int64_t num_rows,   \
+                                                int64_t num_diagonals, int64_t pitch, const T *values, \
+                                                int32_t *row_offsets, int64_t *num_entries_host);     \
+  b200sp_status b200sp_dia_to_csr_fill_##sfx(b200sp_handle h, b200sp_stream s, int64_t num_rows,      \
+                                             int64_t num_diagonals, int64_t pitch,                    \
+                                             const int32_t *diagonal_offsets, const T *values,        \
+                                             const int32_t *row_offsets, int32_t *column_indices,     \
+                                             T *csr_values);                                          \
+  b200sp_status b200sp_ell_to_csr_offsets_##sfx(b200sp_handle h, b200sp_stream s, int64_t num_rows,   \
+                                                int64_t num_cols_per_row, int64_t pitch,              \
+                                                const int32_t *ell_column_indices,                    \
+                                                const T *ell_values, int32_t *row_offsets,            \
+                                                int64_t *num_entries_host);                           \
+  b200sp_status b200sp_ell_to_csr_fill_##sfx(b200sp_handle h, b200sp_stream s, int64_t num_rows,      \
+                                             int64_t num_cols_per_row, int64_t pitch,                 \
+                                             const int32_t *ell_column_indices, const T *ell_values,  \
+                                             const int32_t *row_offsets, int32_t *column_indices,     \
+                                             T *csr_values);                                          \
+  b200sp_status b200sp_hyb_to_csr_offsets_##sfx(                                                      \
+      b200sp_handle h, b200sp_stream s, int64_t num_rows, int64_t ell_cols_per_row,                   \
+      int64_t ell_pitch, const int32_t *ell_column_indices, const T *ell_values,                      \
+      int64_t coo_num_entries, const int32_t *coo_row_indices, int32_t *row_offsets,                  \
+      int64_t *num_entries_host);                                                                     \
+  b200sp_status b200sp_hyb_to_csr_fill_##sfx(                                                         \
+      b200sp_handle h, b200sp_stream s, int64_t num_rows, int64_t ell_cols_per_row,                   \
+      int64_t ell_pitch, const int32_t *ell_column_indices, const T *ell_values,                      \
+      int64_t coo_num_entries, const int32_t *coo_row_indices, const int32_t *coo_column_indices,     \
+      const T *coo_values, const int32_t *row_offsets, int32_t *column_indices, T *csr_values);       \
+  b200sp_status b200sp_dia_to_ell_##sfx(b200sp_handle h, b200sp_stream s, int64_t num_rows,           \
+                                        int64_t num_diagonals, int64_t pitch,                         \
+                                        const int32_t *diagonal_offsets, const T *values,             \
+                                        int32_t *ell_column_indices, T *ell_values);
+B200SP_DECL_TO_CSR(float, f32)
+B200SP_DECL_TO_CSR(double, f64)
+#undef B200SP_DECL_TO_CSR
+
 /* ---- device-side input builders (cusp::gallery::poisson5pt/7pt via
  *      generate_matrix_from_stencil, gallery/detail/stencil.inl:143-206, then
  *      cusp::convert; produce bit-identical arrays to that pipeline without

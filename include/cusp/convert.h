@@ -20,12 +20,13 @@
 //                COO in CSR order   (csr_to_other.h:229-306, format_utils.inl:281-321,
 //                                    detail/functional.inl:114-132)
 //   anything else goes through COO/CSR                     (convert.inl:53-70)
-// Conversions are setup-time operations.  Device CSR / COO sources with 32-bit indices and
-// float / double values convert on the device through the engine's conversion kernels
-// (b200sp_csr_to_{ell,coo_tail,dia}, b200sp_{offsets_to_indices,indices_to_offsets},
-// b200sp_csr_convert_query — csrc/convert.cu), same layouts bit for bit;
-// every other pair runs on the host and the result is uploaded.  The device builders for
-// the benchmark operators are in cusp/gallery/poisson.h.
+// Conversions are setup-time operations.  Device containers with 32-bit indices and float /
+// double values convert on the device through the engine's conversion kernels, every source
+// x destination pair (b200sp_{dia,ell,hyb}_to_csr_offsets/_fill, b200sp_dia_to_ell,
+// b200sp_csr_to_{ell,coo_tail,dia}, b200sp_{offsets_to_indices,indices_to_offsets},
+// b200sp_csr_convert_query — csrc/convert.cu), same layouts bit for bit; host
+// containers, other index / value types and dense (array2d) ends run on the host.  The device
+// builders for the benchmark operators are in cusp/gallery/poisson.h.
 #pragma once
 #include <algorithm>
 #include <vector>
@@ -116,22 +117,35 @@ void gather(const M &A, host_csr<I, V> &H, ell_format) {
     H.offsets[i + 1] = (I)H.columns.size();
   }
 }
+// HYB (hyb_to_other.h:45-56 + cusp/detail/coo_matrix.inl:269-341): the ELL slots whose COLUMN is valid, merged by
+// (row, column) with the COO entries, ties ELL first
 template <typename I, typename V, typename M>
 void gather(const M &A, host_csr<I, V> &H, hyb_format) {
-  host_csr<I, V> E, C;
-  gather(A.ell, E, ell_format());
+  host_csr<I, V> C;
   gather(A.coo, C, coo_format());
+  auto ec = to_host_vector(A.ell.column_indices.values);
+  auto ev = to_host_vector(A.ell.values.values);
+  const size_t pitch = A.ell.column_indices.pitch, K = A.ell.column_indices.num_cols;
   H.rows = A.num_rows;
   H.cols = A.num_cols;
   H.offsets.assign(H.rows + 1, 0);
   for (size_t i = 0; i < H.rows; ++i) {
-    for (I k = E.offsets[i]; k < E.offsets[i + 1]; ++k) {
-      H.columns.push_back(E.columns[k]);
-      H.values.push_back(E.values[k]);
+    I j = C.offsets[i];
+    const I jend = C.offsets[i + 1];
+    for (size_t k = 0; k < K; ++k) {
+      const I c = (I)ec[k * pitch + i];
+      for (; j < jend && C.columns[j] < c; ++j) {
+        H.columns.push_back(C.columns[j]);
+        H.values.push_back(C.values[j]);
+      }
+      if (c != (I)-1) {
+        H.columns.push_back(c);
+        H.values.push_back((V)ev[k * pitch + i]);
+      }
     }
-    for (I k = C.offsets[i]; k < C.offsets[i + 1]; ++k) {
-      H.columns.push_back(C.columns[k]);
-      H.values.push_back(C.values[k]);
+    for (; j < jend; ++j) {
+      H.columns.push_back(C.columns[j]);
+      H.values.push_back(C.values[j]);
     }
     H.offsets[i + 1] = (I)H.columns.size();
   }
@@ -498,6 +512,119 @@ void device_convert(const S &src, D &dst, coo_format, F2) {
   device_convert(csr, dst, csr_format(), F2());
 }
 
+// ---- DIA / ELL / HYB sources: to CSR on the device (b200sp_{dia,ell,hyb}_to_csr_offsets / _fill:
+// generic/conversions/{dia,ell,hyb}_to_other.h), then on to the destination like any CSR ----
+#define CUSP_B200_TO_CSR_WRAPPERS(T, sfx)                                                                              \
+  inline b200sp_status dia_offs_(int64_t r, int64_t nd, int64_t p, const T *v, int *ro, int64_t *n) {                  \
+    return b200sp_dia_to_csr_offsets_##sfx(engine(), current_stream(), r, nd, p, v, ro, n);                            \
+  }                                                                                                                    \
+  inline b200sp_status dia_fill_(int64_t r, int64_t nd, int64_t p, const int *off, const T *v, const int *ro, int *cj, \
+                                 T *cv) {                                                                              \
+    return b200sp_dia_to_csr_fill_##sfx(engine(), current_stream(), r, nd, p, off, v, ro, cj, cv);                     \
+  }                                                                                                                    \
+  inline b200sp_status ell_offs_(int64_t r, int64_t K, int64_t p, const int *ec, const T *ev, int *ro, int64_t *n) {   \
+    return b200sp_ell_to_csr_offsets_##sfx(engine(), current_stream(), r, K, p, ec, ev, ro, n);                        \
+  }                                                                                                                    \
+  inline b200sp_status ell_fill_(int64_t r, int64_t K, int64_t p, const int *ec, const T *ev, const int *ro, int *cj,  \
+                                 T *cv) {                                                                              \
+    return b200sp_ell_to_csr_fill_##sfx(engine(), current_stream(), r, K, p, ec, ev, ro, cj, cv);                      \
+  }                                                                                                                    \
+  inline b200sp_status hyb_offs_(int64_t r, int64_t K, int64_t p, const int *ec, const T *ev, int64_t cn,              \
+                                 const int *ci, int *ro, int64_t *n) {                                                 \
+    return b200sp_hyb_to_csr_offsets_##sfx(engine(), current_stream(), r, K, p, ec, ev, cn, ci, ro, n);                \
+  }                                                                                                                    \
+  inline b200sp_status hyb_fill_(int64_t r, int64_t K, int64_t p, const int *ec, const T *ev, int64_t cn,              \
+                                 const int *ci, const int *cc, const T *cvv, const int *ro, int *cj, T *cv) {          \
+    return b200sp_hyb_to_csr_fill_##sfx(engine(), current_stream(), r, K, p, ec, ev, cn, ci, cc, cvv, ro, cj, cv);     \
+  }                                                                                                                    \
+  inline b200sp_status dia_to_ell_(int64_t r, int64_t nd, int64_t p, const int *off, const T *v, int *ec, T *ev) {     \
+    return b200sp_dia_to_ell_##sfx(engine(), current_stream(), r, nd, p, off, v, ec, ev);                              \
+  }
+CUSP_B200_TO_CSR_WRAPPERS(float, f32)
+CUSP_B200_TO_CSR_WRAPPERS(double, f64)
+#undef CUSP_B200_TO_CSR_WRAPPERS
+
+template <typename S, typename D>
+void device_convert(const S &src, D &dst, dia_format, csr_format) {
+  dst.resize(src.num_rows, src.num_cols, 0);
+  int64_t n = 0;
+  check(dia_offs_((int64_t)src.num_rows, (int64_t)src.values.num_cols, (int64_t)src.values.pitch,
+                  raw_ptr(src.values.values), raw_ptr(dst.row_offsets), &n));
+  dst.column_indices.resize((size_t)n);  // row_offsets stays as computed
+  dst.values.resize((size_t)n);
+  dst.num_entries = (size_t)n;
+  check(dia_fill_((int64_t)src.num_rows, (int64_t)src.values.num_cols, (int64_t)src.values.pitch,
+                  raw_ptr(src.diagonal_offsets), raw_ptr(src.values.values), raw_ptr(dst.row_offsets),
+                  raw_ptr(dst.column_indices), raw_ptr(dst.values)));
+}
+template <typename S, typename D>
+void device_convert(const S &src, D &dst, ell_format, csr_format) {
+  dst.resize(src.num_rows, src.num_cols, 0);
+  const int64_t K = (int64_t)src.column_indices.num_cols, p = (int64_t)src.column_indices.pitch;
+  int64_t n = 0;
+  check(ell_offs_((int64_t)src.num_rows, K, p, raw_ptr(src.column_indices.values), raw_ptr(src.values.values),
+                  raw_ptr(dst.row_offsets), &n));
+  dst.column_indices.resize((size_t)n);  // row_offsets stays as computed
+  dst.values.resize((size_t)n);
+  dst.num_entries = (size_t)n;
+  check(ell_fill_((int64_t)src.num_rows, K, p, raw_ptr(src.column_indices.values), raw_ptr(src.values.values),
+                  raw_ptr(dst.row_offsets), raw_ptr(dst.column_indices), raw_ptr(dst.values)));
+}
+template <typename S, typename D>
+void device_convert(const S &src, D &dst, hyb_format, csr_format) {
+  dst.resize(src.num_rows, src.num_cols, 0);
+  const int64_t K = (int64_t)src.ell.column_indices.num_cols, p = (int64_t)src.ell.column_indices.pitch;
+  const int64_t cn = (int64_t)src.coo.num_entries;
+  int64_t n = 0;
+  check(hyb_offs_((int64_t)src.num_rows, K, p, raw_ptr(src.ell.column_indices.values), raw_ptr(src.ell.values.values), cn,
+                  raw_ptr(src.coo.row_indices), raw_ptr(dst.row_offsets), &n));
+  dst.column_indices.resize((size_t)n);  // row_offsets stays as computed
+  dst.values.resize((size_t)n);
+  dst.num_entries = (size_t)n;
+  check(hyb_fill_((int64_t)src.num_rows, K, p, raw_ptr(src.ell.column_indices.values), raw_ptr(src.ell.values.values), cn,
+                  raw_ptr(src.coo.row_indices), raw_ptr(src.coo.column_indices), raw_ptr(src.coo.values),
+                  raw_ptr(dst.row_offsets), raw_ptr(dst.column_indices), raw_ptr(dst.values)));
+}
+// DIA -> ELL: the fork's direct rule (dia_to_other.h:163-251): K = #diagonals, pitch = the DIA pitch
+template <typename S, typename D>
+void device_convert(const S &src, D &dst, dia_format, ell_format) {
+  dst.resize(src.num_rows, src.num_cols, src.num_entries, src.values.num_cols, 1);
+  if (dst.column_indices.pitch != src.values.pitch) {  // keep the source's pitch like the reference does
+    dst.column_indices.resize(src.num_rows, src.values.num_cols, src.values.pitch);
+    dst.values.resize(src.num_rows, src.values.num_cols, src.values.pitch);
+  }
+  check(dia_to_ell_((int64_t)src.num_rows, (int64_t)src.values.num_cols, (int64_t)src.values.pitch,
+                    raw_ptr(src.diagonal_offsets), raw_ptr(src.values.values), raw_ptr(dst.column_indices.values),
+                    raw_ptr(dst.values.values)));
+}
+// ELL -> HYB: the ELL part is the matrix itself, the COO part is empty (ell_to_other.h:145-163)
+template <typename S, typename D>
+void device_convert(const S &src, D &dst, ell_format, hyb_format) {
+  dst.resize(src.num_rows, src.num_cols, src.num_entries, 0, src.column_indices.num_cols);
+  dst.ell = src;
+}
+// every other pair with a slab source: through CSR
+template <typename S, typename D, typename F1, typename F2>
+void device_convert_via_csr(const S &src, D &dst, F1, F2) {
+  cusp::csr_matrix<typename S::index_type, typename S::value_type, device_memory> csr;
+  device_convert(src, csr, F1(), csr_format());
+  device_convert(csr, dst, csr_format(), F2());
+}
+template <typename S, typename D>
+void device_convert(const S &src, D &dst, dia_format, coo_format) { device_convert_via_csr(src, dst, dia_format(), coo_format()); }
+template <typename S, typename D>
+void device_convert(const S &src, D &dst, dia_format, hyb_format) { device_convert_via_csr(src, dst, dia_format(), hyb_format()); }
+template <typename S, typename D>
+void device_convert(const S &src, D &dst, ell_format, coo_format) { device_convert_via_csr(src, dst, ell_format(), coo_format()); }
+template <typename S, typename D>
+void device_convert(const S &src, D &dst, ell_format, dia_format) { device_convert_via_csr(src, dst, ell_format(), dia_format()); }
+template <typename S, typename D>
+void device_convert(const S &src, D &dst, hyb_format, coo_format) { device_convert_via_csr(src, dst, hyb_format(), coo_format()); }
+template <typename S, typename D>
+void device_convert(const S &src, D &dst, hyb_format, ell_format) { device_convert_via_csr(src, dst, hyb_format(), ell_format()); }
+template <typename S, typename D>
+void device_convert(const S &src, D &dst, hyb_format, dia_format) { device_convert_via_csr(src, dst, hyb_format(), dia_format()); }
+
 template <typename F1, typename F2>
 struct device_path : std::false_type {};
 template <>
@@ -516,6 +643,22 @@ template <>
 struct device_path<coo_format, hyb_format> : std::true_type {};
 template <>
 struct device_path<coo_format, dia_format> : std::true_type {};
+#define CUSP_B200_DEVICE_PATH(F1, F2) \
+  template <>                         \
+  struct device_path<F1, F2> : std::true_type {};
+CUSP_B200_DEVICE_PATH(dia_format, csr_format)
+CUSP_B200_DEVICE_PATH(dia_format, coo_format)
+CUSP_B200_DEVICE_PATH(dia_format, ell_format)
+CUSP_B200_DEVICE_PATH(dia_format, hyb_format)
+CUSP_B200_DEVICE_PATH(ell_format, csr_format)
+CUSP_B200_DEVICE_PATH(ell_format, coo_format)
+CUSP_B200_DEVICE_PATH(ell_format, dia_format)
+CUSP_B200_DEVICE_PATH(ell_format, hyb_format)
+CUSP_B200_DEVICE_PATH(hyb_format, csr_format)
+CUSP_B200_DEVICE_PATH(hyb_format, coo_format)
+CUSP_B200_DEVICE_PATH(hyb_format, ell_format)
+CUSP_B200_DEVICE_PATH(hyb_format, dia_format)
+#undef CUSP_B200_DEVICE_PATH
 
 template <typename S, typename D, typename F1, typename F2>
 void convert_generic(const S &src, D &dst, F1, F2, std::true_type) {

@@ -282,6 +282,59 @@ static i64 dia_to_coo(i64 rows, i64 cols, i64 ndiag, i64 pitch, const int *offs,
   return n;
 }
 
+// ELL -> COO / CSR (cusp/system/detail/generic/conversions/ell_to_other.h:55-143): row-major scan of the
+// [rows x K] logical array (thrust::copy_if over a row_major -> column_major permutation), keep value != 0
+// (the stencil is the VALUE, not the column: explicit zeros are dropped, like DIA).  Returns the count.
+template <typename T>
+static i64 ell_to_coo(i64 rows, i64 K, i64 pitch, const int *cidx, const T *vals, int *Ai, int *Aj, T *Ax) {
+  i64 n = 0;
+  for (i64 i = 0; i < rows; i++)
+    for (i64 k = 0; k < K; k++) {
+      const T v = vals[k * pitch + i];
+      if (v != T(0)) {
+        if (Ai) {
+          Ai[n] = (int)i;
+          Aj[n] = cidx[k * pitch + i];
+          Ax[n] = v;
+        }
+        n++;
+      }
+    }
+  return n;
+}
+
+// HYB -> COO (hyb_to_other.h:45-56 -> coo view of a hyb matrix, cusp/detail/coo_matrix.inl:269-341): the ELL part
+// in row-major order and the COO part are merged by (row, column) — thrust::merge_by_key, ties: ELL first — and the
+// slots whose COLUMN is the invalid index are removed (explicit zeros stay, unlike ELL -> COO).  Restated as a
+// sequential two-pointer merge of the two row-sorted sequences.
+template <typename T>
+static i64 hyb_to_coo(i64 rows, i64 K, i64 pitch, const int *ecidx, const T *evals, i64 cnnz, const int *ci,
+                      const int *cj, const T *cv, int *Ai, int *Aj, T *Ax) {
+  i64 n = 0, b = 0;  // b: next COO entry
+  auto emit = [&](int r, int c, T v) {
+    if (c != -1) {
+      if (Ai) {
+        Ai[n] = r;
+        Aj[n] = c;
+        Ax[n] = v;
+      }
+      n++;
+    }
+  };
+  for (i64 i = 0; i < rows; i++)
+    for (i64 k = 0; k < K; k++) {
+      const int c = ecidx[k * pitch + i];
+      // COO entries strictly smaller than this ELL entry come first
+      while (b < cnnz && (ci[b] < (int)i || (ci[b] == (int)i && cj[b] < c))) {
+        emit(ci[b], cj[b], cv[b]);
+        b++;
+      }
+      emit((int)i, c, evals[k * pitch + i]);
+    }
+  for (; b < cnnz; b++) emit(ci[b], cj[b], cv[b]);
+  return n;
+}
+
 // indices_to_offsets / offsets_to_indices (cusp/format_utils.h, testing/format_utils.cu:13-75)
 static void indices_to_offsets(i64 nnz, const int *idx, i64 rows, int *offs) {
   // offsets[i] = number of indices < i  (lower_bound over sorted indices)
@@ -500,6 +553,14 @@ extern "C" {
   i64 oracle_dia_to_coo_##sfx(i64 rows, i64 cols, i64 nd, i64 pitch, const int *offs, const T *vals,         \
                               int *Ai, int *Aj, T *Ax) {                                                     \
     return dia_to_coo<T>(rows, cols, nd, pitch, offs, vals, Ai, Aj, Ax);                                     \
+  }                                                                                                          \
+  i64 oracle_ell_to_coo_##sfx(i64 rows, i64 K, i64 pitch, const int *cidx, const T *vals, int *Ai, int *Aj,  \
+                              T *Ax) {                                                                       \
+    return ell_to_coo<T>(rows, K, pitch, cidx, vals, Ai, Aj, Ax);                                            \
+  }                                                                                                          \
+  i64 oracle_hyb_to_coo_##sfx(i64 rows, i64 K, i64 pitch, const int *ecidx, const T *evals, i64 cnnz,        \
+                              const int *ci, const int *cj, const T *cv, int *Ai, int *Aj, T *Ax) {          \
+    return hyb_to_coo<T>(rows, K, pitch, ecidx, evals, cnnz, ci, cj, cv, Ai, Aj, Ax);                        \
   }                                                                                                          \
   void oracle_dia_to_ell_##sfx(i64 rows, i64 nd, i64 pitch, const int *offs, const T *vals, int *cidx,       \
                                T *evals) {                                                                   \

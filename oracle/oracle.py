@@ -36,7 +36,7 @@ def lib():
             ct = C.c_float if s == "f32" else C.c_double
             getattr(_lib, "oracle_dot_" + s).restype = ct
             getattr(_lib, "oracle_nrm2_" + s).restype = ct
-            for n in ("cg_csr", "stencil_dia", "dia_to_coo", "csr_to_hyb", "csr_to_dia"):
+            for n in ("cg_csr", "stencil_dia", "dia_to_coo", "csr_to_hyb", "csr_to_dia", "ell_to_coo", "hyb_to_coo"):
                 getattr(_lib, f"oracle_{n}_{s}").restype = I64
         for n in ("max_entries_per_row", "optimal_entries_per_row", "gallery_random", "make_diagonal"):
             getattr(_lib, "oracle_" + n).restype = I64
@@ -474,8 +474,30 @@ def convert(A: dict, fmt: str, alignment=32, num_entries_per_row=0) -> dict:
                                                  _p(vals))
             return dict(format="dia", num_rows=rows, num_cols=cols, num_entries=len(A["values"]),
                         diagonal_offsets=offs, pitch=p, values=vals)
-    if src in ("ell", "hyb"):
-        return convert(dense_to_coo(to_dense(A), dt), fmt, alignment, num_entries_per_row)
+    if src == "ell":   # ell_to_other.h:55-143 (keeps value != 0); to HYB: the ELL part is the matrix itself (:145-163)
+        rows, cols, K, p = A["num_rows"], A["num_cols"], A["num_cols_per_row"], A["pitch"]
+        if fmt == "hyb":
+            coo = dict(format="coo", num_rows=rows, num_cols=cols, num_entries=0, row_indices=np.zeros(0, np.int32),
+                       column_indices=np.zeros(0, np.int32), values=np.zeros(0, dt))
+            return dict(format="hyb", num_rows=rows, num_cols=cols, num_entries=A["num_entries"], ell=dict(A), coo=coo)
+        args = (I64(rows), I64(K), I64(p), _p(A["column_indices"]), _p(A["values"]))
+        n = getattr(L, "oracle_ell_to_coo_" + s)(*args, None, None, None)
+        Ai, Aj, Ax = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, dt)
+        getattr(L, "oracle_ell_to_coo_" + s)(*args, _p(Ai), _p(Aj), _p(Ax))
+        coo = dict(format="coo", num_rows=rows, num_cols=cols, num_entries=int(n), row_indices=Ai, column_indices=Aj,
+                   values=Ax)
+        return coo if fmt == "coo" else convert(coo, fmt, alignment, num_entries_per_row)
+    if src == "hyb":   # hyb_to_other.h:45-56 + cusp/detail/coo_matrix.inl:269-341 (merge by (row, col), keeps valid columns)
+        e, c = A["ell"], A["coo"]
+        rows, cols = A["num_rows"], A["num_cols"]
+        args = (I64(rows), I64(e["num_cols_per_row"]), I64(e["pitch"]), _p(e["column_indices"]), _p(e["values"]),
+                I64(len(c["values"])), _p(c["row_indices"]), _p(c["column_indices"]), _p(c["values"]))
+        n = getattr(L, "oracle_hyb_to_coo_" + s)(*args, None, None, None)
+        Ai, Aj, Ax = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, dt)
+        getattr(L, "oracle_hyb_to_coo_" + s)(*args, _p(Ai), _p(Aj), _p(Ax))
+        coo = dict(format="coo", num_rows=rows, num_cols=cols, num_entries=int(n), row_indices=Ai, column_indices=Aj,
+                   values=Ax)
+        return coo if fmt == "coo" else convert(coo, fmt, alignment, num_entries_per_row)
     raise ValueError(f"{src} -> {fmt}")
 
 

@@ -131,3 +131,77 @@ def test_tail_extraction_over_twenty_million_rows(dev, handle):
     assert torch.equal(hyb.coo.values, Ax[src]) and torch.equal(hyb.coo.column_indices, Aj[src])
     first = torch.where(lens > 0, Ax[torch.clamp(Ap[:-1].to(torch.int64), max=nnz - 1)], torch.zeros((), device=dev))
     assert torch.equal(hyb.ell.values[:rows], first)
+
+
+def _same_layout(D, H):
+    """device container D against the oracle's dict H: every array bit for bit"""
+    f = H["format"]
+    if f == "csr":
+        return _eq(D.row_offsets, H["row_offsets"]) and _eq(D.column_indices, H["column_indices"]) and _eq(D.values, H["values"])
+    if f == "coo":
+        return _eq(D.row_indices, H["row_indices"]) and _eq(D.column_indices, H["column_indices"]) and _eq(D.values, H["values"])
+    if f == "ell":
+        return (D.num_cols_per_row == H["num_cols_per_row"] and D.pitch == H["pitch"] and
+                _eq(D.column_indices, H["column_indices"]) and _eq(D.values, H["values"]))
+    if f == "dia":
+        return D.pitch == H["pitch"] and _eq(D.diagonal_offsets, H["diagonal_offsets"]) and _eq(D.values, H["values"])
+    if f == "hyb":
+        return _same_layout(D.ell, H["ell"]) and _same_layout(D.coo, H["coo"])
+    raise ValueError(f)
+
+
+@pytest.mark.parametrize("ndt", (np.float32, np.float64))
+def test_every_source_times_destination_on_the_device(ndt, dev, handle):
+    """cusp::convert for all 5 x 5 format pairs with device containers never leaves the device (convert.convert ->
+    b200sp_{dia,ell,hyb}_to_csr_*, b200sp_dia_to_ell, b200sp_csr_to_*): every array of the result equals the oracle's
+    restatement of generic/conversions/{dia,ell,hyb,csr,coo}_to_other.h — stencil operators (every format incl. DIA),
+    a ragged random matrix with stored zeros and empty rows (no DIA), and a HYB whose split leaves a COO tail."""
+    rng = np.random.default_rng(41)
+    cases = [("stencil5", O.poisson(5, (31, 17), ndt, "coo"), True), ("stencil7", O.poisson(7, (9, 8, 7), ndt, "coo"), True)]
+    rnd = O.gallery_random(3000, 2600, 40000, ndt, "coo")
+    rnd["values"] = rng.uniform(0.5, 1.5, rnd["num_entries"]).astype(ndt)
+    rnd["values"][::53] = 0
+    cases.append(("random", rnd, False))
+    for name, coo, banded in cases:
+        fmts = ("csr", "coo", "ell", "hyb", "dia") if banded else ("csr", "coo", "ell", "hyb")
+        for src in fmts:
+            kw = dict(num_entries_per_row=2) if src == "hyb" else {}
+            Sh = O.convert(coo, src, **kw)
+            Sd = upload(src, Sh, dev)
+            for dst in fmts:
+                if dst == src:
+                    continue
+                want = O.convert(Sh, dst)
+                l0 = handle.launch_count
+                got = convert.convert(Sd, dst)
+                assert handle.launch_count > l0 or dst == "hyb", (name, src, dst)  # device kernels did the work
+                assert _same_layout(got, want), (name, src, dst)
+    assert not hasattr(convert, "to_host")  # no host detour in the module
+
+
+@pytest.mark.parametrize("tdt", (torch.float32, torch.float64))
+def test_conversions_at_256_cubed_stay_on_the_device(tdt, dev, handle):
+    """poisson7pt 256^3 (BASELINE configs[1]): DIA -> CSR / COO / ELL and ELL -> CSR, HYB -> CSR on the device equal
+    the arrays the device gallery builds directly (themselves bit-identical to the oracle pipeline,
+    tests/test_gallery_gpu.py) — 117M entries per conversion, no PCIe traffic."""
+    n = 256
+    dia = gallery.poisson("dia", 7, (n, n, n), dtype=tdt)
+    csr_ref = gallery.poisson("csr", 7, (n, n, n), dtype=tdt)
+    csr = convert.dia_to_csr(dia)
+    assert csr.num_entries == 117047296
+    assert torch.equal(csr.row_offsets, csr_ref.row_offsets) and torch.equal(csr.column_indices, csr_ref.column_indices)
+    assert torch.equal(csr.values, csr_ref.values)
+    del csr
+    ell = convert.dia_to_ell(dia)
+    ell_ref = gallery.poisson("ell", 7, (n, n, n), dtype=tdt)
+    assert ell.pitch == ell_ref.pitch and ell.num_cols_per_row == 7
+    assert torch.equal(ell.column_indices, ell_ref.column_indices) and torch.equal(ell.values, ell_ref.values)
+    del dia, ell_ref
+    back = convert.ell_to_csr(ell)
+    assert torch.equal(back.row_offsets, csr_ref.row_offsets) and torch.equal(back.column_indices, csr_ref.column_indices)
+    assert torch.equal(back.values, csr_ref.values)
+    del back, ell
+    hyb = convert.csr_to_hyb(csr_ref, num_entries_per_row=6)
+    back = convert.hyb_to_csr(hyb)
+    assert torch.equal(back.row_offsets, csr_ref.row_offsets) and torch.equal(back.column_indices, csr_ref.column_indices)
+    assert torch.equal(back.values, csr_ref.values)
