@@ -539,44 +539,66 @@ __global__ void coo_analyze_kernel(i64 nnz, const int *Aj, int line_shift, int s
   }
 }
 
-// true: the ring kernel's gather order coalesces (few lines per instruction, and no worse than
-// the consecutive order).  Cached per (column_indices, nnz, element size); a hint only — both
-// kernels are correct on every matrix and produce the same bits.
-static bool coo_prefers_ring(b200sp_handle h, cudaStream_t st, i64 nnz, const int *Aj, size_t elem) {
+// Which lane order suits this column stream?  1: the ring kernel's strided order coalesces (few lines per
+// instruction, and no worse than the consecutive order: stencils, banded operators); 2: only the consecutive order
+// coalesces (one entry per row, e.g. the COO tail of a stencil HYB) -> the LDG scan kernel; 0: neither does
+// (scattered columns: graphs) -> the warp-autonomous kernel.  Cached per (column_indices, nnz, element size); a hint
+// only — every kernel is correct on every matrix.
+static int coo_gather_class(b200sp_handle h, cudaStream_t st, i64 nnz, const int *Aj, size_t elem) {
   const b200sp_context::CsrKey key{Aj, (int64_t)elem, nnz};
   auto it = h->coo_gather_order.find(key);
-  if (it != h->coo_gather_order.end()) return it->second != 0;
+  if (it != h->coo_gather_order.end()) return it->second;
   const int samples = 2048;
   int *d = reinterpret_cast<int *>(h->dev_scalars + 54);  // 2 ints
   int *p = reinterpret_cast<int *>(h->pinned_scalars + 54);
-  int ring = 0;
+  int cls = 2;
   if (cudaMemsetAsync(d, 0, 2 * sizeof(int), st) == cudaSuccess) {
     coo_analyze_kernel<<<samples / 8, 256, 0, st>>>(nnz, Aj, elem == 4 ? 5 : 4, samples, d);
     h->launches++;
     if (cudaMemcpyAsync(p, d, 2 * sizeof(int), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
         cudaStreamSynchronize(st) == cudaSuccess) {
       const double per_instr_seq = (double)p[0] / (7.0 * samples), per_instr_str = (double)p[1] / (7.0 * samples);
-      ring = (per_instr_str <= 4.0 && per_instr_str <= per_instr_seq) ? 1 : 0;
+      if (per_instr_str <= 4.0 && per_instr_str <= per_instr_seq)
+        cls = 1;
+      else if (per_instr_seq > 8.0 && per_instr_str > 8.0)
+        cls = 0;
     }
   }
   cudaGetLastError();
   if (h->coo_gather_order.size() > 256) h->coo_gather_order.clear();
-  h->coo_gather_order[key] = ring;
-  return ring != 0;
+  h->coo_gather_order[key] = cls;
+  return cls;
 }
 
 static void coo_defaults(b200sp_cfg &c, b200sp_handle h, cudaStream_t st, i64 nnz, const int *Aj, size_t elem,
-                         bool tma_ok) {
+                         bool tma_ok, bool vec32_ok) {
   const bool no_shape = c.block_size == 0 && c.unroll == 0;
   if (c.block_size == 0) c.block_size = 256;
   if (c.unroll == 0) c.unroll = 7;
   // The persistent ring needs a few tiles per resident CTA to be worth its prologue, and its
   // gather order must coalesce (stencils, banded operators); scattered or consecutive-column
   // streams (graphs, one entry per row) run the LDG kernel with its 2048 threads per SM.
-  if (c.kernel == 0)
-    c.kernel = (tma_ok && nnz >= (i64)h->num_sms * 8 * c.block_size * c.unroll && coo_prefers_ring(h, st, nnz, Aj, elem))
-                   ? B200SP_K_COO_RING
-                   : B200SP_K_COO_SEGSCAN;
+  if (c.kernel == 0) {
+    const bool big = nnz >= (i64)h->num_sms * 8 * c.block_size * c.unroll;
+    const int cls = big ? coo_gather_class(h, st, nnz, Aj, elem) : 2;
+    if (tma_ok && big && cls == 1) {
+      c.kernel = B200SP_K_COO_RING;
+    } else if (big && cls == 0 && no_shape && vec32_ok) {
+      // scattered columns (graphs): the warp-autonomous kernel, 256-bit loads (R-MAT scale 22 / 24: 0.47 of the copy
+      // rate against 0.41 - 0.44 for the shared-memory scan, profiles/r03_coo_probe.md); a persistent grid once every
+      // warp has tens of tiles
+      c = b200sp_cfg{};
+      c.kernel = B200SP_K_COO_WARP;
+      c.block_size = 256;
+      c.vector_width = 8;
+      const bool many = nnz >= ((i64)1 << 27);
+      c.unroll = many ? 2 : 1;
+      c.ctas_per_sm = many ? 8 : 0;
+      return;
+    } else {
+      c.kernel = B200SP_K_COO_SEGSCAN;
+    }
+  }
   if (c.kernel == B200SP_K_COO_RING && no_shape) {  // profiles/r02_results.md: 512x7 for fp64, 256x9 for fp32
     if (elem == 8)
       c.block_size = 512;
@@ -617,7 +639,8 @@ b200sp_status spmv_coo(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64
   }
   b200sp_cfg c = cfg ? *cfg : b200sp_cfg{};
   const bool tma_ok = aligned16(Ai) && aligned16(Aj) && aligned16(Ax);
-  coo_defaults(c, h, st, nnz, Aj, sizeof(T), tma_ok);
+  const bool vec32_ok = ((((uintptr_t)Ai | (uintptr_t)Aj | (uintptr_t)Ax) & 31) == 0);
+  coo_defaults(c, h, st, nnz, Aj, sizeof(T), tma_ok, vec32_ok);
   if (c.kernel == B200SP_K_COO_RING && !tma_ok) c.kernel = B200SP_K_COO_SEGSCAN;  // bulk copies need 16-byte bases
   if (c.kernel != B200SP_K_COO_SEGSCAN && c.kernel != B200SP_K_COO_RING && c.kernel != B200SP_K_COO_WARP)
     return set_error(h, B200SP_INVALID_INPUT, "coo: unknown kernel id %d", c.kernel);

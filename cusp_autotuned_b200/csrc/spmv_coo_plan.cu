@@ -104,24 +104,21 @@ __global__ void plan_slots_kernel(int hot, const int *hot_cols, int *slot_of) {
 template <typename T>
 b200sp_status spmv_coo_hot(b200sp_handle h, cudaStream_t st, CooArgs<T> a, const b200sp_cfg &c, const int *hot_cols,
                            int hot, int capacity) {
-  const int vpl = c.vector_width ? c.vector_width : 4, u = c.unroll ? c.unroll : 2;
-  const int xpol = c.stages & 3, spol = (c.stages >> 2) & 1;
+  // defaults from the R-MAT sweep (profiles/r03_coo_probe.md): 256-bit loads, one unit per tile; entry streams are
+  // kept out of the little L1 that remains beside the table (0.886 ms against 0.99 ms with ld.global.cs at scale 24)
+  const int vpl = c.vector_width ? c.vector_width : (sizeof(T) == 4 ? 8 : 4), u = c.unroll ? c.unroll : 1;
   const uintptr_t need_idx = (uintptr_t)(4 * vpl) - 1, need_val = (uintptr_t)(sizeof(T) * vpl > 32 ? 32 : sizeof(T) * vpl) - 1;
   if (((uintptr_t)a.Ai & need_idx) || ((uintptr_t)a.Aj & need_idx) || ((uintptr_t)a.Ax & need_val))
     return set_error(h, B200SP_INVALID_INPUT, "coo plan: arrays not aligned for %d-entry vector loads", vpl);
-#define CASE(V, UU, X, S)                              \
-  if (vpl == V && u == UU && xpol == X && spol == S) \
-    return launch_coo_warp<T, 1024, 1, V, UU, X, S, true>(h, st, a, 1, hot_cols, hot, capacity);
-#define CASES(V, UU) CASE(V, UU, 0, 0) CASE(V, UU, 1, 0) CASE(V, UU, 0, 1) CASE(V, UU, 1, 1)
+#define CASE(V, UU) \
+  if (vpl == V && u == UU) return launch_coo_warp<T, 1024, 1, V, UU, 0, 1, true>(h, st, a, 1, hot_cols, hot, capacity);
   if constexpr (sizeof(T) == 4) {
-    CASES(4, 1) CASES(4, 2) CASES(8, 1)
+    CASE(4, 1) CASE(4, 2) CASE(8, 1)
   } else {
-    CASES(4, 1)
+    CASE(4, 1) CASE(4, 2)
   }
-#undef CASES
 #undef CASE
-  return set_error(h, B200SP_INVALID_INPUT, "coo plan: unsupported vector_width=%d unroll=%d stages=%d", vpl, u,
-                   c.stages);
+  return set_error(h, B200SP_INVALID_INPUT, "coo plan: unsupported vector_width=%d unroll=%d", vpl, u);
 }
 template b200sp_status spmv_coo_hot<float>(b200sp_handle, cudaStream_t, CooArgs<float>, const b200sp_cfg &, const int *,
                                            int, int);
@@ -184,8 +181,10 @@ b200sp_status b200sp_coo_plan_create(b200sp_handle h, b200sp_stream stream, int6
   B200SP_REQUIRE(h, num_entries == 0 || (row_indices && column_indices && num_cols > 0), "coo plan: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t elem = dtype == B200SP_F64 ? 8 : 4;
-  // default: everything an SM's shared memory can hold next to the kernel's static needs
-  if (table_bytes <= 0) table_bytes = ((int64_t)h->max_smem_optin - 1024) & ~(int64_t)1023;
+  // default: 128 KiB.  The executor's gathers of the remaining (cold) columns still need L1: with a 192 KiB table
+  // (64 KiB of L1 left) the same product takes 1.45 ms instead of 0.89 ms at R-MAT scale 24, with the whole shared
+  // memory as table 2.7 ms (profiles/r03_coo_probe.md)
+  if (table_bytes <= 0) table_bytes = 128 << 10;
   int capacity = (int)std::min<int64_t>(table_bytes / (int64_t)elem, num_cols > 0 ? num_cols : 1);
   if (capacity < 1) capacity = 1;
   if ((size_t)capacity * elem > (size_t)h->max_smem_optin)

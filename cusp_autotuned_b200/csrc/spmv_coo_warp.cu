@@ -4,36 +4,33 @@
 //   cfg.unroll       = units per warp tile (1, 2, 4): a lane keeps vector_width * unroll gathers in flight
 //   cfg.block_size   = 256
 //   cfg.ctas_per_sm  = 0: one tile per warp; n: persistent grid of n CTAs per SM
-//   cfg.stages       = cache-policy variant (x gathers: 0 nc, 1 nc + L1 evict_last, 2 nc + L1 no_allocate;
-//                      +4: entry streams with L1::no_allocate + L2 evict-first instead of ld.global.cs)
+//
+// Cache policies are fixed by measurement (R-MAT scale 22 / 24 sweep, profiles/r03_coo_probe.md): x gathers
+// ld.global.nc with the default L1 policy (L1::evict_last -3 %, L1::no_allocate -40 %: the L1 hits on hot x sectors
+// matter); entry streams ld.global.cs here, and L1::no_allocate + L2 evict-first in the plan executor, where the
+// table leaves little L1 (0.89 ms against 0.99 ms).
 #include "coo_warp.cuh"
 
 namespace b200sp {
 
 template <typename T>
 b200sp_status spmv_coo_warp(b200sp_handle h, cudaStream_t st, CooArgs<T> a, const b200sp_cfg &c) {
-  const int vpl = c.vector_width ? c.vector_width : 4, u = c.unroll ? c.unroll : 2;
-  const int xpol = c.stages & 3, spol = (c.stages >> 2) & 1;
+  const int vpl = c.vector_width ? c.vector_width : 8, u = c.unroll ? c.unroll : 1;
   if (c.block_size != 0 && c.block_size != 256)
     return set_error(h, B200SP_INVALID_INPUT, "coo warp: unsupported block_size=%d", c.block_size);
   // a lane's vector loads need 16- / 32-byte aligned array bases
   const uintptr_t need_idx = (uintptr_t)(4 * vpl) - 1, need_val = (uintptr_t)(sizeof(T) * vpl > 32 ? 32 : sizeof(T) * vpl) - 1;
   if (((uintptr_t)a.Ai & need_idx) || ((uintptr_t)a.Aj & need_idx) || ((uintptr_t)a.Ax & need_val))
     return set_error(h, B200SP_INVALID_INPUT, "coo warp: arrays not aligned for %d-entry vector loads", vpl);
-#define CASE(V, UU, MINB, X, S)                                \
-  if (vpl == V && u == UU && xpol == X && spol == S)           \
-    return launch_coo_warp<T, 256, MINB, V, UU, X, S, false>(h, st, a, c.ctas_per_sm, nullptr, 0, 0);
-#define CASES(V, UU, MINB) \
-  CASE(V, UU, MINB, 0, 0) CASE(V, UU, MINB, 1, 0) CASE(V, UU, MINB, 2, 0) CASE(V, UU, MINB, 0, 1) CASE(V, UU, MINB, 1, 1) CASE(V, UU, MINB, 2, 1)
+#define CASE(V, UU, MINB) \
+  if (vpl == V && u == UU) return launch_coo_warp<T, 256, MINB, V, UU, 0, 0, false>(h, st, a, c.ctas_per_sm, nullptr, 0, 0);
   if constexpr (sizeof(T) == 4) {
-    CASES(4, 1, 6) CASES(4, 2, 4) CASES(4, 4, 3) CASES(8, 1, 4) CASES(8, 2, 3) CASES(8, 4, 2)
+    CASE(4, 1, 6) CASE(4, 2, 4) CASE(4, 4, 3) CASE(8, 1, 4) CASE(8, 2, 3) CASE(8, 4, 2)
   } else {
-    CASES(4, 1, 4) CASES(4, 2, 3) CASES(4, 4, 2) CASES(8, 1, 3) CASES(8, 2, 2)
+    CASE(4, 1, 4) CASE(4, 2, 3) CASE(4, 4, 2) CASE(8, 1, 3) CASE(8, 2, 2)
   }
-#undef CASES
 #undef CASE
-  return set_error(h, B200SP_INVALID_INPUT, "coo warp: unsupported vector_width=%d unroll=%d stages=%d", vpl, u,
-                   c.stages);
+  return set_error(h, B200SP_INVALID_INPUT, "coo warp: unsupported vector_width=%d unroll=%d", vpl, u);
 }
 
 template b200sp_status spmv_coo_warp<float>(b200sp_handle, cudaStream_t, CooArgs<float>, const b200sp_cfg &);

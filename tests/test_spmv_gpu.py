@@ -256,7 +256,7 @@ def test_coo_hub_row_spanning_many_tiles(ndt, tdt, dev):
              column_indices=cols, values=vals)
     x = rng.integers(-3, 4, n).astype(ndt)
     want = O.spmv(A, x)
-    for cfg in capi.Handle.cfg_space(capi.FMT_COO, 0):
+    for cfg in capi.Handle.cfg_space(capi.FMT_COO, capi.F32 if ndt == np.float32 else capi.F64):
         assert np.array_equal(gpu_multiply("coo", A, x, dev, cfg=cfg), want), cfg
     y0 = rng.integers(-5, 5, n).astype(ndt)
     assert np.array_equal(gpu_multiply("coo", A, x, dev, y0=y0, accumulate=True), O.spmv(A, x, y0, accumulate=True))
@@ -357,9 +357,9 @@ def test_coo_warp_tile_boundaries_and_hubs(ndt, tdt, dev):
 
 
 @pytest.mark.parametrize("ndt,tdt", DTYPES)
-def test_coo_warp_tolerance_and_policies(ndt, tdt, dev):
-    """non-integer data: every shape within the north-star bound of the host loop; the cache-policy variants and the
-    persistent grid change no bit (same tiles, same order)"""
+def test_coo_warp_tolerance_and_persistent_grid(ndt, tdt, dev):
+    """non-integer data: every shape within the north-star bound of the host loop; the persistent grid changes no bit
+    (same tiles, same order)"""
     rng = np.random.default_rng(22)
     n, nnz = 30000, 128 * 3000 + 77
     rows = np.sort(rng.integers(0, n, nnz)).astype(np.int32)
@@ -373,10 +373,23 @@ def test_coo_warp_tolerance_and_policies(ndt, tdt, dev):
     for vw, u in WARP_SHAPES:
         base = gpu_multiply("coo", A, x, dev, cfg=capi.Cfg(kernel=capi.K_COO_WARP, vector_width=vw, unroll=u))
         assert rel_err(base, want) <= TOL[np.dtype(ndt)], (vw, u)
-        for pol, cps in ((1, 0), (2, 0), (4, 0), (5, 2), (6, 0)):
-            got = gpu_multiply("coo", A, x, dev, cfg=capi.Cfg(kernel=capi.K_COO_WARP, vector_width=vw, unroll=u,
-                                                              stages=pol, ctas_per_sm=cps))
-            assert np.array_equal(got, base), (vw, u, pol, cps)
+        for cps in (1, 2, 8):
+            got = gpu_multiply("coo", A, x, dev, cfg=capi.Cfg(kernel=capi.K_COO_WARP, vector_width=vw, unroll=u, ctas_per_sm=cps))
+            assert np.array_equal(got, base), (vw, u, cps)
+
+
+def test_coo_default_kernel_follows_the_column_stream(dev, handle):
+    """the default choice (coo_gather_class probe): scattered columns -> K_COO_WARP, one entry per row -> the LDG scan
+    kernel, banded -> the ring kernel; whatever it picks, the result is the host loop's (integer data, exact)"""
+    rng = np.random.default_rng(24)
+    n, nnz = 1 << 18, 1 << 22
+    rows = np.sort(rng.integers(0, n, nnz)).astype(np.int32)
+    for name, cols in (("scattered", rng.integers(0, n, nnz).astype(np.int32)),
+                       ("banded", np.minimum(rows + (np.arange(nnz) % 5).astype(np.int32), n - 1).astype(np.int32))):
+        vals = rng.integers(-2, 3, nnz).astype(np.float32)
+        A = dict(format="coo", num_rows=n, num_cols=n, num_entries=nnz, row_indices=rows, column_indices=cols, values=vals)
+        x = rng.integers(-3, 4, n).astype(np.float32)
+        assert np.array_equal(gpu_multiply("coo", A, x, dev), O.spmv(A, x)), name
 
 
 @pytest.mark.parametrize("ndt,tdt", DTYPES)
@@ -400,7 +413,7 @@ def test_coo_plan_matches_warp_kernel_bitwise(ndt, tdt, dev, handle):
         if table_bytes:
             assert info["capacity"] == table_bytes // es
         assert 0 < info["hot_entries"] <= nnz
-        for vw, u in ((4, 1), (4, 2), (8, 1)) if ndt == np.float32 else ((4, 1),):
+        for vw, u in ((4, 1), (4, 2), (8, 1)) if ndt == np.float32 else ((4, 1), (4, 2)):
             cfg = capi.Cfg(kernel=capi.K_COO_WARP, vector_width=vw, unroll=u)
             yw = torch.full((n,), 9, dtype=tdt, device=dev)
             handle.spmv_coo(n, n, nnz, ri, ci, va, xd, yw, cfg=cfg)
@@ -412,7 +425,8 @@ def test_coo_plan_matches_warp_kernel_bitwise(ndt, tdt, dev, handle):
             assert torch.equal(yw, yp), (table_bytes, vw, u, "accumulate")
         # attached: the plain entry point takes the executor for these arrays only
         y_plain = torch.empty(n, dtype=tdt, device=dev)
-        handle.spmv_coo(n, n, nnz, ri, ci, va, xd, y_plain, cfg=capi.Cfg(kernel=capi.K_COO_WARP))
+        handle.spmv_coo(n, n, nnz, ri, ci, va, xd, y_plain,
+                        cfg=capi.Cfg(kernel=capi.K_COO_WARP, vector_width=8 if ndt == np.float32 else 4, unroll=1))
         handle.coo_plan_attach(plan)
         y_att = torch.empty(n, dtype=tdt, device=dev)
         handle.spmv_coo(n, n, nnz, ri, ci, va, xd, y_att)

@@ -1,4 +1,4 @@
-"""COO on R-MAT: every K_COO_WARP shape / cache-policy variant and the hot-column plan executor beside the
+"""COO on R-MAT: every K_COO_WARP shape and the hot-column plan executor (table sizes) beside the
 default kernels, with an exactness check per variant.  Writes gpurun_out/coo_probe_s<scale>.json.
 
   python tools/coo_probe.py [scale ...]        (default: 22 24)
@@ -86,12 +86,11 @@ def main():
         quick = os.environ.get("PROBE_QUICK") == "1"
         for vpl in (4, 8):
             for u in (1, 2, 4):
-                for pol in ((0,) if quick else (0, 1, 2, 4, 5, 6)):
-                    for cps in ((0,) if quick or pol else (0, 8)):
-                        cfg = capi.Cfg(kernel=capi.K_COO_WARP, vector_width=vpl, unroll=u, stages=pol, ctas_per_sm=cps)
-                        run(f"warp v{vpl} u{u} pol{pol} cps{cps}", coo(cfg), vpl=vpl, u=u, pol=pol, cps=cps)
-        # plan executor
-        for tb in ((0,) if quick else (64 << 10, 128 << 10, 192 << 10, 0)):
+                for cps in ((0,) if quick else (0, 4, 8)):
+                    cfg = capi.Cfg(kernel=capi.K_COO_WARP, vector_width=vpl, unroll=u, ctas_per_sm=cps)
+                    run(f"warp v{vpl} u{u} cps{cps}", coo(cfg), vpl=vpl, u=u, cps=cps)
+        # plan executor: table size x shape
+        for tb in ((0,) if quick else (64 << 10, 96 << 10, 112 << 10, 128 << 10, 144 << 10, 160 << 10, 0)):
             try:
                 plan = h.coo_plan_create(n, n, nnz, C.row_indices, C.column_indices, capi.F32, tb)
             except capi.B200spError as e:
@@ -100,11 +99,10 @@ def main():
             info = h.coo_plan_info(plan)
             info["hot_fraction"] = info["hot_entries"] / nnz
             for vpl, u in ((4, 1), (4, 2), (8, 1)):
-                for pol in ((0,) if quick else (0, 1, 4, 5)):
-                    cfg = capi.Cfg(kernel=capi.K_COO_WARP, vector_width=vpl, unroll=u, stages=pol)
-                    run(f"plan tb{tb >> 10}K v{vpl} u{u} pol{pol}",
-                        lambda v, xx, yy, acc=False, cfg=cfg: h.spmv_coo_plan(plan, v, xx, yy, accumulate=acc, cfg=cfg),
-                        vpl=vpl, u=u, pol=pol, table_kib=tb >> 10, **info)
+                cfg = capi.Cfg(kernel=capi.K_COO_WARP, vector_width=vpl, unroll=u)
+                run(f"plan tb{tb >> 10}K v{vpl} u{u}",
+                    lambda v, xx, yy, acc=False, cfg=cfg: h.spmv_coo_plan(plan, v, xx, yy, accumulate=acc, cfg=cfg),
+                    vpl=vpl, u=u, table_kib=tb >> 10, **info)
             # through the product entry point with the plan attached
             if tb == 0:
                 h.coo_plan_attach(plan)
