@@ -159,19 +159,45 @@ __global__ void __launch_bounds__(CG_BLOCK) cg_init_kernel(i64 n, const T *b, co
 }
 
 // x += alpha p ; r -= alpha y ; rz_new = <r,r> ; then the scalar step
+// Launched with programmatic stream serialization (see pdl_wait in common.cuh): the first batch of p, x, r — none of
+// which the preceding SpMV writes — is requested before the wait, so those loads and the launch latency overlap the
+// SpMV's tail; y and the scalars are read after it.
 template <typename T, bool DIST>
 __global__ void __launch_bounds__(CG_BLOCK) cg_update_kernel(i64 n, const T *p, const T *y, T *x, T *r,
                                                              CgState<T> *S, T *partials,
                                                              unsigned int *ticket, double *residuals) {
   __shared__ T s_red[32];
+  const i64 stride = (i64)gridDim.x * CG_BLOCK;
+  i64 i = (i64)blockIdx.x * CG_BLOCK + threadIdx.x;
+  T pv[CG_UNROLL], yv[CG_UNROLL], xv[CG_UNROLL], rv[CG_UNROLL];
+  const bool first = i + (CG_UNROLL - 1) * stride < n;
+  if (first) {
+#pragma unroll
+    for (int u = 0; u < CG_UNROLL; ++u) {
+      pv[u] = p[i + u * stride];
+      xv[u] = x[i + u * stride];
+      rv[u] = r[i + u * stride];
+    }
+  }
+  pdl_wait();
+  pdl_trigger();
   if (S->done) return;
   const T alpha = S->rz / S->yp;
   const T nalpha = -alpha;
   T acc = T(0);
-  const i64 stride = (i64)gridDim.x * CG_BLOCK;
-  i64 i = (i64)blockIdx.x * CG_BLOCK + threadIdx.x;
+  if (first) {
+#pragma unroll
+    for (int u = 0; u < CG_UNROLL; ++u) yv[u] = y[i + u * stride];
+#pragma unroll
+    for (int u = 0; u < CG_UNROLL; ++u) {
+      x[i + u * stride] = alpha * pv[u] + xv[u];
+      const T rn = nalpha * yv[u] + rv[u];
+      r[i + u * stride] = rn;
+      acc = acc + rn * rn;
+    }
+    i += CG_UNROLL * stride;
+  }
   for (; i + (CG_UNROLL - 1) * stride < n; i += CG_UNROLL * stride) {
-    T pv[CG_UNROLL], yv[CG_UNROLL], xv[CG_UNROLL], rv[CG_UNROLL];
 #pragma unroll
     for (int u = 0; u < CG_UNROLL; ++u) {
       pv[u] = p[i + u * stride];
@@ -219,18 +245,25 @@ __global__ void cg_scalar_step_kernel(CgState<T> *S, double *residuals, int firs
   monitor_step(S, residuals);
 }
 
-// p = z + beta p  (axpby(z,p,p,1,beta), z == r)
+// p = z + beta p  (axpby(z,p,p,1,beta), z == r).  p is not written by the preceding update kernel: its loads are
+// issued before the dependency wait.
 template <typename T>
 __global__ void __launch_bounds__(CG_BLOCK) cg_direction_kernel(i64 n, const T *r, T *p, const CgState<T> *S) {
-  if (S->done) return;
-  const T beta = S->beta;
   const i64 base = (i64)blockIdx.x * (CG_BLOCK * CG_UNROLL) + threadIdx.x;
   T rv[CG_UNROLL], pv[CG_UNROLL];
 #pragma unroll
   for (int u = 0; u < CG_UNROLL; ++u) {
     const i64 i = base + (i64)u * CG_BLOCK;
-    rv[u] = i < n ? r[i] : T(0);
     pv[u] = i < n ? p[i] : T(0);
+  }
+  pdl_wait();
+  pdl_trigger();
+  if (S->done) return;
+  const T beta = S->beta;
+#pragma unroll
+  for (int u = 0; u < CG_UNROLL; ++u) {
+    const i64 i = base + (i64)u * CG_BLOCK;
+    rv[u] = i < n ? r[i] : T(0);
   }
 #pragma unroll
   for (int u = 0; u < CG_UNROLL; ++u) {
@@ -301,29 +334,60 @@ __device__ __forceinline__ T p2p_sum_warp(const P2PView &c, int ch, unsigned tag
   return sum;
 }
 
+// trace slots per iteration (B200SP_CG_TRACE): globaltimer stamps of CTA 0 / the finishing CTA
+enum { TR_K2_ENTER = 0, TR_K2_POLLED = 1, TR_K2_END = 2, TR_K3_ENTER = 3, TR_K3_POLLED = 4, TR_K3_END = 5, TR_SLOTS = 8 };
+
 template <typename T>
 __global__ void __launch_bounds__(CG_BLOCK) cg_update_p2p_kernel(i64 n, const T *p, const T *y, T *x, T *r,
                                                                  CgState<T> *S, T *partials, unsigned int *ticket,
-                                                                 P2PView c, unsigned tag) {
+                                                                 P2PView c, unsigned tag, unsigned long long *trace) {
   __shared__ T s_red[32];
   __shared__ T s_yp;
   __shared__ double s_pub;
   __shared__ int s_fin;
+  // before the dependency wait: the first batch of p, x, r (the preceding SpMV writes none of them)
+  const i64 stride = (i64)gridDim.x * CG_BLOCK;
+  i64 i = (i64)blockIdx.x * CG_BLOCK + threadIdx.x;
+  T pv[CG_UNROLL], yv[CG_UNROLL], xv[CG_UNROLL], rv[CG_UNROLL];
+  const bool first = i + (CG_UNROLL - 1) * stride < n;
+  if (first) {
+#pragma unroll
+    for (int u = 0; u < CG_UNROLL; ++u) {
+      pv[u] = p[i + u * stride];
+      xv[u] = x[i + u * stride];
+      rv[u] = r[i + u * stride];
+    }
+  }
+  pdl_wait();
+  pdl_trigger();
   if (S->done) return;
+  if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[TR_K2_ENTER] = global_timer_ns();
   if (threadIdx.x == 0) s_fin = 0;
   if (blockIdx.x == 0 && threadIdx.x < c.world) p2p_publish(c, 0, (double)S->yp, tag, threadIdx.x);
+  if (first) {  // y of the first batch is on its way while the slots are polled
+#pragma unroll
+    for (int u = 0; u < CG_UNROLL; ++u) yv[u] = y[i + u * stride];
+  }
   if (threadIdx.x < 32) {
     const T t = p2p_sum_warp<T>(c, 0, tag);
     if (threadIdx.x == 0) s_yp = t;
   }
   __syncthreads();
+  if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[TR_K2_POLLED] = global_timer_ns();
   const T alpha = S->rz / s_yp;
   const T nalpha = -alpha;
   T acc = T(0);
-  const i64 stride = (i64)gridDim.x * CG_BLOCK;
-  i64 i = (i64)blockIdx.x * CG_BLOCK + threadIdx.x;
+  if (first) {
+#pragma unroll
+    for (int u = 0; u < CG_UNROLL; ++u) {
+      x[i + u * stride] = alpha * pv[u] + xv[u];
+      const T rn = nalpha * yv[u] + rv[u];
+      r[i + u * stride] = rn;
+      acc = acc + rn * rn;
+    }
+    i += CG_UNROLL * stride;
+  }
   for (; i + (CG_UNROLL - 1) * stride < n; i += CG_UNROLL * stride) {
-    T pv[CG_UNROLL], yv[CG_UNROLL], xv[CG_UNROLL], rv[CG_UNROLL];
 #pragma unroll
     for (int u = 0; u < CG_UNROLL; ++u) {
       pv[u] = p[i + u * stride];
@@ -353,6 +417,7 @@ __global__ void __launch_bounds__(CG_BLOCK) cg_update_p2p_kernel(i64 n, const T 
   });
   __syncthreads();
   if (s_fin && threadIdx.x < c.world) p2p_publish(c, 1, s_pub, tag, threadIdx.x);  // one lane per peer
+  if (trace && s_fin && threadIdx.x == 0) trace[TR_K2_END] = global_timer_ns();
 }
 
 template <typename T>
@@ -361,9 +426,20 @@ __global__ void __launch_bounds__(CG_BLOCK) cg_direction_p2p_kernel(i64 n, const
                                                                     P2PView c, unsigned tag,
                                                                     unsigned long long epoch, i64 halo_lo,
                                                                     i64 halo_hi, T *dst_lo, T *dst_hi,
-                                                                    int defer_wait) {
+                                                                    int defer_wait, unsigned long long *trace) {
   __shared__ T s_rz;
   __shared__ bool is_last;
+  // before the dependency wait: the first batch of p (the preceding update kernel does not write p)
+  const i64 stride = (i64)gridDim.x * CG_BLOCK;
+  i64 i = (i64)blockIdx.x * CG_BLOCK + threadIdx.x;
+  T rv[CG_UNROLL], pv[CG_UNROLL];
+  const bool first = i + (CG_UNROLL - 1) * stride < n;
+  if (first) {
+#pragma unroll
+    for (int u = 0; u < CG_UNROLL; ++u) pv[u] = p[i + u * stride];
+  }
+  pdl_wait();
+  pdl_trigger();
   if (S->done) {
     // the solve is over, but a next K1 that waits for this epoch may already be queued on a neighbour
     if (defer_wait && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -372,23 +448,28 @@ __global__ void __launch_bounds__(CG_BLOCK) cg_direction_p2p_kernel(i64 n, const
     }
     return;
   }
+  if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[TR_K3_ENTER] = global_timer_ns();
+  if (first) {  // r of the first batch is on its way while the slots are polled
+#pragma unroll
+    for (int u = 0; u < CG_UNROLL; ++u) rv[u] = r[i + u * stride];
+  }
   if (threadIdx.x < 32) {
     const T t = p2p_sum_warp<T>(c, 1, tag);
     if (threadIdx.x == 0) s_rz = t;
   }
   __syncthreads();
+  if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[TR_K3_POLLED] = global_timer_ns();
   const T rz_new = s_rz;
   const T beta = rz_new / S->rz;
-  const i64 stride = (i64)gridDim.x * CG_BLOCK;
   const i64 hi_begin = n - halo_hi;
   bool remote = false;
-  i64 i = (i64)blockIdx.x * CG_BLOCK + threadIdx.x;
-  for (; i + (CG_UNROLL - 1) * stride < n; i += CG_UNROLL * stride) {
-    T rv[CG_UNROLL], pv[CG_UNROLL];
+  for (bool pre = first; i + (CG_UNROLL - 1) * stride < n; i += CG_UNROLL * stride, pre = false) {
+    if (!pre) {
 #pragma unroll
-    for (int u = 0; u < CG_UNROLL; ++u) {
-      rv[u] = r[i + u * stride];
-      pv[u] = p[i + u * stride];
+      for (int u = 0; u < CG_UNROLL; ++u) {
+        rv[u] = r[i + u * stride];
+        pv[u] = p[i + u * stride];
+      }
     }
 #pragma unroll
     for (int u = 0; u < CG_UNROLL; ++u) {
@@ -445,6 +526,7 @@ __global__ void __launch_bounds__(CG_BLOCK) cg_direction_p2p_kernel(i64 n, const
       }
     *ticket = 0;
     __threadfence();
+    if (trace) trace[TR_K3_END] = global_timer_ns();
   }
 }
 
@@ -596,6 +678,31 @@ static b200sp_status cg_impl(b200sp_handle h, cudaStream_t st, const b200sp_matr
     s = comm_halo_exchange(h, st, pwin, n, halo_lo, halo_hi, sizeof(T));
     if (s != B200SP_OK) return s;
   }
+  // Programmatic dependent launch between the three kernels of an iteration (B200SP_CG_PDL=0 switches it off):
+  // every kernel requests what its predecessor does not write before griddepcontrol.wait, so launch latency and
+  // first-batch load latency overlap the predecessor's tail.  The DIA bulk kernel joins in through h->pdl_spmv
+  // (its producer lane streams matrix slabs into the ring while the direction kernel is still finishing).
+  const char *pdl_env = getenv("B200SP_CG_PDL");
+  const bool pdl = !(pdl_env && pdl_env[0] == '0');
+  struct PdlScope {  // the flag must not leak into products outside this solve
+    b200sp_handle h;
+    ~PdlScope() { h->pdl_spmv = false; }
+  } pdl_scope{h};
+  h->pdl_spmv = pdl;
+  // B200SP_CG_TRACE=<path>: globaltimer stamps per iteration (poll waits, kernel ends) -> <path>.<rank>
+  const char *trace_path = getenv("B200SP_CG_TRACE");
+  unsigned long long *trace = nullptr;
+  const size_t trace_words = trace_path ? ((size_t)prm.iteration_limit + 2) * TR_SLOTS : 0;
+  if (trace_words) {
+    B200SP_CUDA(h, cudaMalloc(&trace, trace_words * sizeof(unsigned long long)));
+    B200SP_CUDA(h, cudaMemsetAsync(trace, 0, trace_words * sizeof(unsigned long long), st));
+  }
+  struct TraceScope {
+    unsigned long long *&p;
+    ~TraceScope() {
+      if (p) cudaFree(p);
+    }
+  } trace_scope{trace};
   while (!hs->done) {
     for (int k = 0; k < prm.check_interval; ++k) {
       if (p2p) {
@@ -621,11 +728,14 @@ static b200sp_status cg_impl(b200sp_handle h, cudaStream_t st, const b200sp_matr
           s = spmv_any<T>(h, st, A, pwin, y, 0, cfg, p, &S->yp);
         }
         if (s != B200SP_OK) return s;
-        cg_update_p2p_kernel<T><<<(unsigned)g, CG_BLOCK, 0, st>>>(n, p, y, x, r, S, partials, ticket, view, tag);
-        B200SP_LAUNCH_CHECK(h, "cg_update_p2p_kernel");
-        cg_direction_p2p_kernel<T><<<(unsigned)g, CG_BLOCK, 0, st>>>(n, r, p, S, ticket + 1, res, view, tag, epoch,
-                                                                     halo_lo, halo_hi, dst_lo, dst_hi, defer ? 1 : 0);
-        B200SP_LAUNCH_CHECK(h, "cg_direction_p2p_kernel");
+        unsigned long long *tr = (trace && kiter < (unsigned long long)prm.iteration_limit + 2) ? trace + kiter * TR_SLOTS : nullptr;
+        B200SP_CUDA(h, launch_kernel_pdl(cg_update_p2p_kernel<T>, dim3((unsigned)g), dim3(CG_BLOCK), 0, st, pdl, n, p, y, x,
+                                         r, S, partials, ticket, view, tag, tr));
+        h->launches++;
+        B200SP_CUDA(h, launch_kernel_pdl(cg_direction_p2p_kernel<T>, dim3((unsigned)g), dim3(CG_BLOCK), 0, st, pdl, n, r, p,
+                                         S, ticket + 1, res, view, tag, epoch, halo_lo, halo_hi, dst_lo, dst_hi,
+                                         defer ? 1 : 0, tr));
+        h->launches++;
         continue;
       }
       if (dist) {
@@ -644,16 +754,35 @@ static b200sp_status cg_impl(b200sp_handle h, cudaStream_t st, const b200sp_matr
       } else {
         s = spmv_any<T>(h, st, A, p, y, 0, cfg, p, &S->yp);
         if (s != B200SP_OK) return s;
-        cg_update_kernel<T, false><<<(unsigned)g, CG_BLOCK, 0, st>>>(n, p, y, x, r, S, partials, ticket, res);
-        B200SP_LAUNCH_CHECK(h, "cg_update_kernel");
+        B200SP_CUDA(h, launch_kernel_pdl(cg_update_kernel<T, false>, dim3((unsigned)g), dim3(CG_BLOCK), 0, st, pdl, n,
+                                         (const T *)p, (const T *)y, x, r, S, partials, ticket, res));
+        h->launches++;
       }
-      cg_direction_kernel<T><<<(unsigned)gdir, CG_BLOCK, 0, st>>>(n, r, p, S);
-      B200SP_LAUNCH_CHECK(h, "cg_direction_kernel");
+      B200SP_CUDA(h, launch_kernel_pdl(cg_direction_kernel<T>, dim3((unsigned)gdir), dim3(CG_BLOCK), 0, st, pdl && !dist, n,
+                                       (const T *)r, p, (const CgState<T> *)S));
+      h->launches++;
     }
     s = poll();
     if (s != B200SP_OK) return s;
   }
 
+  h->pdl_spmv = false;
+  if (trace && trace_path) {
+    std::vector<unsigned long long> tr(trace_words);
+    B200SP_CUDA(h, cudaMemcpyAsync(tr.data(), trace, trace_words * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    B200SP_CUDA(h, cudaStreamSynchronize(st));
+    char path[1024];
+    snprintf(path, sizeof(path), "%s.%d", trace_path, h->rank);
+    if (FILE *f = fopen(path, "w")) {
+      fprintf(f, "# iter k2_enter k2_polled k2_end k3_enter k3_polled k3_end (globaltimer ns, this GPU)\n");
+      for (unsigned long long it = 1; it <= kiter && it < (unsigned long long)prm.iteration_limit + 2; ++it) {
+        fprintf(f, "%llu", it);
+        for (int q = 0; q < 6; ++q) fprintf(f, " %llu", tr[it * TR_SLOTS + q]);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+  }
   if (p2p) {
     unsigned long long timeouts = 0;
     B200SP_CUDA(h, cudaMemcpyAsync(&timeouts, &view.mine->timeouts, sizeof(timeouts), cudaMemcpyDeviceToHost, st));

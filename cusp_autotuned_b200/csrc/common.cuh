@@ -93,6 +93,9 @@ struct b200sp_context {
   std::map<CsrKey, int> coo_gather_order;
   std::vector<void *> tune_events;  // cudaEvent_t pair
   std::vector<void *> coo_plans;    // attached b200sp_coo_plan (spmv_coo_plan.cu)
+  // set by the CG driver around its iteration: the DIA bulk kernel is launched with programmatic stream
+  // serialization and waits (griddepcontrol.wait) before its first read of x / y (spmv_dia.cu, cg.cu)
+  bool pdl_spmv = false;
 
   // multi-GPU
   void *nccl_comm = nullptr;
@@ -155,6 +158,26 @@ b200sp_status ensure_scratch(b200sp_handle h, size_t bytes);
   } while (0)
 
 static inline i64 ceil_div(i64 a, i64 b) { return (a + b - 1) / b; }
+
+#ifdef __CUDACC__
+// launch with (pdl) or without programmatic stream serialization; same argument conversion rules as <<< >>>
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                            bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#endif
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // ---------------------------------------------------------------------------
@@ -323,6 +346,22 @@ __device__ __forceinline__ int hi_bits(double v) { return __double2hiint(v); }
 template <typename T>
 __device__ __forceinline__ void consume_before_release(T acc) {
   if (hi_bits(acc) == (int)0x7ff4dead) asm volatile("nanosleep.u32 0;");
+}
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its
+// predecessor in the stream is still draining; pdl_wait() blocks until the predecessor has completed
+// and its writes are visible (a no-op for a normal launch).  pdl_trigger() lets the NEXT dependent
+// kernel's CTAs be scheduled once every CTA of this grid has called it (or exited).  Rule used in
+// this library: a kernel triggers only AFTER its own pdl_wait(), so whatever ran before its
+// predecessor is complete before any successor's pre-wait code runs — a pre-wait prologue may read
+// anything its predecessor does not write.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 
 // L2 eviction policy for slabs that are read exactly once

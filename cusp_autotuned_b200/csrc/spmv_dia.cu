@@ -49,6 +49,7 @@ struct DiaArgs {
   T *dot_result;
   i64 row_begin;  // first row handled by this launch (remainder launches)
   DiaXchg xc;
+  int pdl;  // launched with programmatic stream serialization: wait before the first read of x / y / dotv
 };
 
 constexpr int DIA_DU = 8;            // diagonals in flight per thread
@@ -265,10 +266,17 @@ __global__ void __launch_bounds__(BLOCK + 32) dia_bulk_kernel(DiaArgs<T> a, int 
         }
       }
     } else if (a.xc.enabled == 1) {
+      if (a.pdl) pdl_wait();
       dia_xchg_aux(a.xc, tid - BLOCK);
     }
   } else {
     // ===== consumer warps =====
+    // PDL: the producer lane above is already streaming matrix slabs (never written by a predecessor in a solver
+    // loop) into the ring; x, y and dotv may only be read once the predecessor has completed
+    if (a.pdl) {
+      pdl_wait();
+      pdl_trigger();
+    }
     int s = 0;
     uint32_t ph = 0;
     const int lane = tid & 31;
@@ -411,8 +419,9 @@ static b200sp_status launch_bulk(b200sp_handle h, cudaStream_t st, DiaArgs<T> a,
   i64 grid = (i64)h->num_sms * (ctas_per_sm < resident ? ctas_per_sm : resident);
   if (grid > num_tiles) grid = num_tiles;
   if (a.dotv && grid > RED_MAX_PARTIALS) return set_error(h, B200SP_INVALID_INPUT, "dia: grid too large");
-  kern<<<(unsigned)grid, BLOCK + 32, smem, st>>>(a, stages, num_tiles);
-  B200SP_LAUNCH_CHECK(h, "dia_bulk_kernel");
+  a.pdl = h->pdl_spmv ? 1 : 0;
+  B200SP_CUDA(h, launch_kernel_pdl(kern, dim3((unsigned)grid), dim3(BLOCK + 32), smem, st, a.pdl != 0, a, stages, num_tiles));
+  h->launches++;
   return B200SP_OK;
 }
 
@@ -491,6 +500,7 @@ b200sp_status spmv_dia_xchg(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols
   a.dot_partials = reinterpret_cast<T *>(h->red_partials);
   a.dot_ticket = h->red_counters;
   a.row_begin = 0;
+  a.pdl = 0;
   memset(&a.xc, 0, sizeof(a.xc));
 
   if (c.kernel == B200SP_K_DIA_BULK) {

@@ -182,21 +182,32 @@ static T nrm2(i64 n, const T *x) {
 // cusp::monitor (cusp/detail/monitor.inl:107-111,178-208).  CSR operator.
 // Returns the iteration count; residuals gets one entry per finished() call.
 // ---------------------------------------------------------------------------
+// dot / nrm2 accumulated in long double (x87 80-bit: 64-bit mantissa) and rounded once: the rounding-free
+// reference the sequential sums above and the engine's tree sums are both compared with at 10^8 terms
 template <typename T>
+static T dot_ld(i64 n, const T *x, const T *y) {
+  long double s = 0.0L;
+  for (i64 i = 0; i < n; i++) s += (long double)x[i] * (long double)y[i];
+  return (T)s;
+}
+
+template <typename T, bool COMPENSATED = false>
 static i64 cg_csr(i64 n, const int *Ap, const int *Aj, const T *Ax, T *x, const T *b, i64 limit, double rel,
                   double abs_tol, double *residuals, i64 *nres, int *converged) {
+  auto dot_ = [](i64 m, const T *u, const T *v) { return COMPENSATED ? dot_ld<T>(m, u, v) : dot<T>(m, u, v); };
+  auto nrm2_ = [](i64 m, const T *u) { return COMPENSATED ? (T)std::sqrt((T)dot_ld<T>(m, u, u)) : nrm2<T>(m, u); };
   std::vector<T> y(n), z(n), r(n), p(n);
-  const T bnorm = nrm2<T>(n, b);
+  const T bnorm = nrm2_(n, b);
   const T tol = (T)abs_tol + (T)rel * bnorm;
   spmv_csr<T>(n, Ap, Aj, Ax, x, y.data(), 0);
   axpby<T>(n, T(1), b, T(-1), y.data(), r.data());
   z = r;
   p = z;
-  T rz = dot<T>(n, r.data(), z.data());
+  T rz = dot_(n, r.data(), z.data());
   i64 it = 0, k = 0;
   *converged = 0;
   for (;;) {
-    const T rn = nrm2<T>(n, r.data());
+    const T rn = nrm2_(n, r.data());
     residuals[k++] = (double)rn;
     if (rn <= tol) {
       *converged = 1;
@@ -204,12 +215,12 @@ static i64 cg_csr(i64 n, const int *Ap, const int *Aj, const T *Ax, T *x, const 
     }
     if (it >= limit) break;
     spmv_csr<T>(n, Ap, Aj, Ax, p.data(), y.data(), 0);
-    const T alpha = rz / dot<T>(n, y.data(), p.data());
+    const T alpha = rz / dot_(n, y.data(), p.data());
     axpy<T>(n, alpha, p.data(), x);
     axpy<T>(n, -alpha, y.data(), r.data());
     z = r;
     const T rz_old = rz;
-    rz = dot<T>(n, r.data(), z.data());
+    rz = dot_(n, r.data(), z.data());
     const T beta = rz / rz_old;
     axpby<T>(n, T(1), z.data(), beta, p.data(), p.data());
     ++it;
@@ -545,6 +556,11 @@ extern "C" {
   i64 oracle_cg_csr_##sfx(i64 n, const int *Ap, const int *Aj, const T *Ax, T *x, const T *b, i64 limit,     \
                           double rel, double abs_tol, double *residuals, i64 *nres, int *converged) {        \
     return cg_csr<T>(n, Ap, Aj, Ax, x, b, limit, rel, abs_tol, residuals, nres, converged);                  \
+  }                                                                                                          \
+  i64 oracle_cg_csr_compensated_##sfx(i64 n, const int *Ap, const int *Aj, const T *Ax, T *x, const T *b,    \
+                                      i64 limit, double rel, double abs_tol, double *residuals, i64 *nres,  \
+                                      int *converged) {                                                      \
+    return cg_csr<T, true>(n, Ap, Aj, Ax, x, b, limit, rel, abs_tol, residuals, nres, converged);            \
   }                                                                                                          \
   i64 oracle_stencil_dia_##sfx(int ndim, const i64 *grid, int npts, const int *pts, const T *pvals,          \
                                int *offsets, T *values) {                                                    \

@@ -36,7 +36,7 @@ def lib():
             ct = C.c_float if s == "f32" else C.c_double
             getattr(_lib, "oracle_dot_" + s).restype = ct
             getattr(_lib, "oracle_nrm2_" + s).restype = ct
-            for n in ("cg_csr", "stencil_dia", "dia_to_coo", "csr_to_hyb", "csr_to_dia", "ell_to_coo", "hyb_to_coo"):
+            for n in ("cg_csr", "cg_csr_compensated", "stencil_dia", "dia_to_coo", "csr_to_hyb", "csr_to_dia", "ell_to_coo", "hyb_to_coo"):
                 getattr(_lib, f"oracle_{n}_{s}").restype = I64
         for n in ("max_entries_per_row", "optimal_entries_per_row", "gallery_random", "make_diagonal"):
             getattr(_lib, "oracle_" + n).restype = I64
@@ -255,8 +255,10 @@ def nrm2(x):
     return getattr(lib(), "oracle_nrm2_" + _s(x.dtype))(I64(len(x)), _p(_c(x)))
 
 
-def cg(A: dict, x0, b, iteration_limit=500, relative_tolerance=1e-5, absolute_tolerance=0.0):
-    """cusp::krylov::cg on a CSR dict.  Returns (x, iterations, converged, residuals)."""
+def cg(A: dict, x0, b, iteration_limit=500, relative_tolerance=1e-5, absolute_tolerance=0.0, compensated=False):
+    """cusp::krylov::cg on a CSR dict.  Returns (x, iterations, converged, residuals).
+    compensated=True: dot products and norms accumulated in long double and rounded once (the same iteration with
+    the summation error taken out: what both the sequential sums and the engine's tree sums approximate)."""
     assert A["format"] == "csr"
     dt = A["values"].dtype
     x = _c(x0, dt).copy()
@@ -264,7 +266,7 @@ def cg(A: dict, x0, b, iteration_limit=500, relative_tolerance=1e-5, absolute_to
     hist = np.zeros(iteration_limit + 2, dtype=np.float64)
     nres = I64(0)
     conv = C.c_int(0)
-    it = getattr(lib(), "oracle_cg_csr_" + _s(dt))(
+    it = getattr(lib(), ("oracle_cg_csr_compensated_" if compensated else "oracle_cg_csr_") + _s(dt))(
         I64(A["num_rows"]), _p(A["row_offsets"]), _p(A["column_indices"]), _p(A["values"]), _p(x), _p(b),
         I64(iteration_limit), C.c_double(relative_tolerance), C.c_double(absolute_tolerance), _p(hist),
         C.byref(nres), C.byref(conv))

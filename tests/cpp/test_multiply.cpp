@@ -196,12 +196,17 @@ void TestMultiplyErrors() {
 }
 TEST_HOST_DEVICE(TestMultiplyErrors)
 
-// a functor triple the engine does not implement must fail loudly on the device
+// a functor the C ABI cannot name (user code) must fail loudly on the device; the named ones run there
+// (b200sp_spmv_generalized) and give the host loop's result
+template <typename T>
+struct user_combine {
+  T operator()(const T &a, const T &b) const { return a * b + T(1); }
+};
 void TestDeviceUnsupportedFunctors() {
   TestMatrices<float> m;
   cusp::csr_matrix<int, float, cusp::device_memory> A(m.A);
   cusp::array1d<float, cusp::device_memory> x(4, 1.0f), y(5, 0.0f);
-  ASSERT_THROWS(cusp::multiply(A, x, y, cusp::constant_functor<float>(1.0f), cusp::multiplies_function<float>(),
+  ASSERT_THROWS(cusp::multiply(A, x, y, cusp::constant_functor<float>(1.0f), user_combine<float>(),
                                cusp::plus_function<float>()),
                 cusp::not_implemented_exception);
   // the host path is functor-generic (generalized SpMV, testing/generalized_spmv.cu)
@@ -210,5 +215,11 @@ void TestDeviceUnsupportedFunctors() {
   cusp::multiply(Ah, xh, yh, cusp::constant_functor<float>(1.0f), cusp::multiplies_function<float>(),
                  cusp::plus_function<float>());
   ASSERT_EQUAL(yh[0], 94.0f);
+  // constant_functor(1) is expressible by code: same result on the device
+  cusp::multiply(A, x, y, cusp::constant_functor<float>(1.0f), cusp::multiplies_function<float>(),
+                 cusp::plus_function<float>());
+  cusp::array1d<float, cusp::host_memory> yd(y);
+  ASSERT_EQUAL(yd[0], 94.0f);
+  ASSERT_EQUAL(yd == yh, true);
 }
 TEST_DEVICE(TestDeviceUnsupportedFunctors)

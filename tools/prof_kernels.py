@@ -21,7 +21,7 @@ for fmt in which:
         ri = torch.repeat_interleave(torch.arange(C.num_rows, device=dev, dtype=torch.int32), lens)
         A = coo_matrix(C.num_rows, C.num_cols, ri, C.column_indices, C.values)
         x = ((torch.arange(A.num_cols, device=dev) % 21) - 10).double()
-    else:  # "coo": default kernel; "coow[:vw:u:pol]": K_COO_WARP; "plan[:vw:u:pol]": hot-column plan executor
+    else:  # "coo": default kernel; "coow[:vw:u]": K_COO_WARP; "plan[:vw:u]": hot-column plan executor
         A = convert.rmat(int(os.environ.get("PROF_RMAT_SCALE", "22")), 16, seed=42, dtype=torch.float32)
         x = torch.rand(A.num_cols, device=dev) + 0.5
     y = torch.empty(A.num_rows, dtype=x.dtype, device=dev)
@@ -29,8 +29,8 @@ for fmt in which:
     cfg = None
     parts = fmt.split(":")
     if parts[0] in ("coow", "plan"):
-        vw, u, pol = (int(v) for v in (parts[1:] + ["8", "2", "0"][len(parts) - 1:]))
-        cfg = capi.Cfg(kernel=capi.K_COO_WARP, vector_width=vw, unroll=u, stages=pol)
+        vw, u = (int(v) for v in (parts[1:] + ["8", "1"][len(parts) - 1:])[:2])
+        cfg = capi.Cfg(kernel=capi.K_COO_WARP, vector_width=vw, unroll=u)
     if parts[0] == "plan":
         plan = h.coo_plan_create(A.num_rows, A.num_cols, A.num_entries, A.row_indices, A.column_indices, capi.F32, 0)
         for _ in range(reps):
