@@ -133,7 +133,7 @@ _SFX = ("f32", "f64")
 EXPORTED_SYMBOLS = (
     ["b200sp_version", "b200sp_create", "b200sp_destroy", "b200sp_last_error_string",
      "b200sp_status_string", "b200sp_launch_count", "b200sp_set_l2_persist",
-     "b200sp_ell_row_lengths", "b200sp_spmv", "b200sp_spmv_generalized", "b200sp_spmv_host", "b200sp_cg",
+     "b200sp_ell_row_lengths", "b200sp_spmv", "b200sp_spmv_generalized", "b200sp_spmv_host", "b200sp_cg", "b200sp_krylov",
      "b200sp_comm_unique_id", "b200sp_comm_init", "b200sp_comm_destroy", "b200sp_cg_dist",
      "b200sp_spmv_dist", "b200sp_spmv_dist_host", "b200sp_spmv_dist_gather", "b200sp_comm_p2p_enabled", "b200sp_comm_timeouts", "b200sp_cfg_space", "b200sp_tune", "b200sp_tune_step",
      "b200sp_tune_reset", "b200sp_tune_lookup", "b200sp_tune_save", "b200sp_tune_load",
@@ -413,6 +413,22 @@ class Handle:
                                          C.byref(prm), C.byref(cfg) if cfg else None, C.byref(res), hp)
         self.check(st)
         return res, (hist[: res.num_residuals] if hist is not None else None)
+
+    SOLVERS = {"cg": 0, "bicgstab": 1, "cr": 2}
+
+    def krylov(self, solver: str, A: Matrix, x, b, diagonal_inverse=None, iteration_limit=500, relative_tolerance=1e-5,
+               absolute_tolerance=0.0, check_interval=0, cfg: Optional[Cfg] = None, halo: Optional[Halo] = None):
+        """b200sp_krylov: fused cg / bicgstab / cr with the identity or a diagonal preconditioner; one GPU or the
+        row-block partitioned form (halo).  Returns (result, monitor.residuals)."""
+        import numpy as np
+        prm = CgParams(iteration_limit, relative_tolerance, absolute_tolerance, check_interval)
+        res = CgResult()
+        hist = np.zeros(2 * iteration_limit + 4, dtype=np.float64)
+        self.check(self.lib.b200sp_krylov(self._h, _stream(), C.c_int(self.SOLVERS[solver]), C.byref(A),
+                                          C.byref(halo) if halo is not None else None, _ptr(x), _ptr(b),
+                                          _ptr(diagonal_inverse), C.byref(prm), C.byref(cfg) if cfg else None,
+                                          C.byref(res), hist.ctypes.data_as(C.c_void_p)))
+        return res, hist[: res.num_residuals]
 
     # -- multi-GPU ---------------------------------------------------------------------------
     def comm_unique_id(self) -> bytes:

@@ -1,5 +1,5 @@
-"""cusp::krylov::cg + cusp::monitor (cusp/krylov/detail/cg.inl:35-180,
-cusp/monitor.h:101-245) over b200sp_cg."""
+"""cusp::krylov::{cg, bicgstab, cr} + cusp::monitor + cusp::precond::diagonal (cusp/krylov/detail/{cg,bicgstab,cr}.inl,
+cusp/monitor.h:101-245, cusp/precond/diagonal.h) over b200sp_cg / b200sp_krylov."""
 from __future__ import annotations
 
 import sys
@@ -83,3 +83,48 @@ def cg(A, x, b, mon: monitor | None = None, *, cfg=None, handle=None, check_inte
                      halo=halo)
     mon._absorb(res, hist)
     return mon
+
+
+class diagonal:
+    """cusp::precond::diagonal<V, device_memory>(A): M = diag(A)^-1, held as `diagonal_reciprocals`
+    (cusp/precond/detail/diagonal.inl:30-47: extract_diagonal, then reciprocal).  Set-up time: torch index ops."""
+
+    def __init__(self, A):
+        import torch
+        from . import convert
+        src = {capi.FMT_CSR: "csr", capi.FMT_COO: "coo", capi.FMT_DIA: "dia", capi.FMT_ELL: "ell", capi.FMT_HYB: "hyb"}[A.format]
+        C = A if src == "coo" else convert.convert(A, "coo")
+        d = torch.zeros(A.num_rows, dtype=C.values.dtype, device=C.values.device)
+        on = C.row_indices == C.column_indices
+        d[C.row_indices[on].to(torch.int64)] = C.values[on]
+        self.diagonal_reciprocals = 1.0 / d
+
+
+def _solve(solver, A, x, b, mon, M, cfg, handle, check_interval, halo):
+    if A.num_rows != x.numel() or b.numel() != x.numel():
+        raise capi.InvalidInput(capi.ST_INVALID_INPUT, f"{solver}: dimension mismatch")
+    if mon is None:
+        mon = monitor(b)
+    h = handle or default_handle()
+    dinv = None if M is None else M.diagonal_reciprocals
+    res, hist = h.krylov(solver, A.descriptor(), x, b, diagonal_inverse=dinv, iteration_limit=mon.iteration_limit(),
+                         relative_tolerance=mon.relative_tolerance(), absolute_tolerance=mon.absolute_tolerance(),
+                         check_interval=check_interval, cfg=cfg, halo=halo)
+    mon._absorb(res, hist)
+    return mon
+
+
+def pcg(A, x, b, mon: monitor | None = None, M: diagonal | None = None, *, cfg=None, handle=None, check_interval=0, halo=None):
+    """cusp::krylov::cg(A, x, b, monitor, M) with M = None (identity) or a `diagonal` preconditioner"""
+    return _solve("cg", A, x, b, mon, M, cfg, handle, check_interval, halo)
+
+
+def bicgstab(A, x, b, mon: monitor | None = None, M: diagonal | None = None, *, cfg=None, handle=None, check_interval=0,
+             halo=None):
+    """cusp::krylov::bicgstab(A, x, b[, monitor[, M]]); monitor.residuals gets two entries per iteration (||r||, ||s||)"""
+    return _solve("bicgstab", A, x, b, mon, M, cfg, handle, check_interval, halo)
+
+
+def cr(A, x, b, mon: monitor | None = None, M: diagonal | None = None, *, cfg=None, handle=None, check_interval=0, halo=None):
+    """cusp::krylov::cr(A, x, b[, monitor[, M]])"""
+    return _solve("cr", A, x, b, mon, M, cfg, handle, check_interval, halo)

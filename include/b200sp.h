@@ -455,6 +455,25 @@ b200sp_status b200sp_spmv_dist_gather(b200sp_handle h, b200sp_stream stream,
                                       const b200sp_matrix *A_local, const int64_t *slice_offsets,
                                       void *x_full, void *y_local, const b200sp_cfg *cfg);
 
+/* ---- the other Krylov solvers + the diagonal (Jacobi) preconditioner, fused like CG ------------------
+ * cusp::krylov::cg with cusp::precond::diagonal (cusp/krylov/detail/cg.inl:35-107, cusp/precond/diagonal.h),
+ * cusp::krylov::bicgstab (cusp/krylov/detail/bicgstab.inl:35-123), cusp::krylov::cr (cusp/krylov/detail/cr.inl:39-128)
+ * with cusp::monitor semantics.  Scalars and the monitor live on the device; an iteration is the products (dot
+ * products fused into their epilogues) plus 2-3 fused vector kernels; the host polls every check_interval
+ * iterations.  Same element expressions in the same order as the reference: same iterate sequence (the dot
+ * products are summed in a different order).  residuals_host: monitor.residuals — one entry per
+ * monitor.finished() call (BiCGStab calls it twice per iteration: room for 2 * iteration_limit + 2).
+ *   diagonal_inverse  NULL: identity preconditioner; else the device vector cusp::precond::diagonal holds
+ *                     (1 / a_ii, this rank's rows), applied as z_i = diagonal_inverse_i * r_i
+ *   halo              NULL: one GPU; else the row-block partitioned form of b200sp_cg_dist (A_local in window
+ *                     coordinates, halo planes exchanged before every product, sums all-reduced)
+ * B200SP_SOLVER_CG with diagonal_inverse == NULL is b200sp_cg / b200sp_cg_dist. */
+typedef enum { B200SP_SOLVER_CG = 0, B200SP_SOLVER_BICGSTAB = 1, B200SP_SOLVER_CR = 2 } b200sp_solver;
+b200sp_status b200sp_krylov(b200sp_handle h, b200sp_stream stream, b200sp_solver solver,
+                            const b200sp_matrix *A, const b200sp_halo *halo, void *x, const void *b,
+                            const void *diagonal_inverse, const b200sp_cg_params *params,
+                            const b200sp_cfg *spmv_cfg, b200sp_cg_result *result, double *residuals_host);
+
 /* ---- autotuning (cusp::ktt::{multiply,tune,reset_tuning},
  *      cusp/ktt/detail/ktt.inl:83-142, cuda/ktt/multiply.h:56-153) ----------- */
 typedef enum {

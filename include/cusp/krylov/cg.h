@@ -2,10 +2,10 @@
 // (reference: cusp/krylov/cg.h:43-150, cusp/krylov/detail/cg.inl:35-180).
 //
 // Two routes with one iterate sequence:
-//   * fused: device matrix the C ABI takes + cusp::monitor<V> + the identity
-//     preconditioner  ->  b200sp_cg (3 kernels per iteration, scalars stay on the
-//     device, the monitor rule is evaluated there and the residual history comes
-//     back in one piece);
+//   * fused: device matrix the C ABI takes + cusp::monitor<V> + the identity or the
+//     diagonal (cusp::precond::diagonal) preconditioner  ->  b200sp_krylov / b200sp_cg
+//     (3 kernels per iteration, scalars stay on the device, the monitor rule is
+//     evaluated there and the residual history comes back in one piece);
 //   * generic: any linear operator / monitor / preconditioner  ->  the textbook
 //     loop over cusp::multiply and cusp::blas, operation by operation in the
 //     order of cg.inl:63-105 (each of those calls is again a C-ABI call on
@@ -20,19 +20,11 @@
 #include "../linear_operator.h"
 #include "../monitor.h"
 #include "../multiply.h"
+#include "detail/fused.h"
 
 namespace cusp {
 namespace krylov {
 namespace detail {
-
-template <typename T>
-struct is_identity_operator : std::false_type {};
-template <typename V, typename S, typename I>
-struct is_identity_operator<cusp::identity_operator<V, S, I>> : std::true_type {};
-template <typename T>
-struct is_cusp_monitor : std::false_type {};
-template <typename V>
-struct is_cusp_monitor<cusp::monitor<V>> : std::true_type {};
 
 template <typename LinearOperator, typename V1, typename V2, typename Monitor, typename Preconditioner>
 void cg_generic(const LinearOperator &A, V1 &x, const V2 &b, Monitor &monitor, Preconditioner &M) {
@@ -60,24 +52,10 @@ void cg_generic(const LinearOperator &A, V1 &x, const V2 &b, Monitor &monitor, P
   }
 }
 
-template <typename LinearOperator, typename V1, typename V2, typename Monitor>
-void cg_fused(const LinearOperator &A, V1 &x, const V2 &b, Monitor &monitor) {
-  using namespace cusp::detail;
-  b200sp_matrix d = describe(A);
-  b200sp_cg_params prm;
-  prm.iteration_limit = (int64_t)monitor.iteration_limit();
-  prm.relative_tolerance = (double)monitor.relative_tolerance();
-  prm.absolute_tolerance = (double)monitor.absolute_tolerance();
-  prm.check_interval = 0;
-  b200sp_cg_result res;
-  std::vector<double> history(monitor.iteration_limit() + 2, 0.0);
-  check(b200sp_cg(engine(), current_stream(), &d, raw_ptr(x), raw_ptr(b), &prm, nullptr, &res, history.data()));
-  monitor.absorb((size_t)res.iteration_count, history.data(), (size_t)res.num_residuals, res.b_norm);
-}
-
 template <typename LinearOperator, typename V1, typename V2, typename Monitor, typename Preconditioner>
-void cg_dispatch(const LinearOperator &A, V1 &x, const V2 &b, Monitor &monitor, Preconditioner &, std::true_type) {
-  cg_fused(A, x, b, monitor);
+void cg_dispatch(const LinearOperator &A, V1 &x, const V2 &b, Monitor &monitor, Preconditioner &M, std::true_type) {
+  if (monitor.iteration_count() != 0) return cg_generic(A, x, b, monitor, M);  // a monitor in mid-count: step by step
+  solve_fused(B200SP_SOLVER_CG, A, x, b, monitor, M, 1);
 }
 template <typename LinearOperator, typename V1, typename V2, typename Monitor, typename Preconditioner>
 void cg_dispatch(const LinearOperator &A, V1 &x, const V2 &b, Monitor &monitor, Preconditioner &M, std::false_type) {
@@ -91,12 +69,7 @@ template <typename LinearOperator, typename VectorType1, typename VectorType2, t
 void cg(const LinearOperator &A, VectorType1 &x, const VectorType2 &b, Monitor &monitor, Preconditioner &M) {
   if (A.num_rows != A.num_cols || x.size() != A.num_rows || b.size() != A.num_rows)
     throw cusp::invalid_input_exception("cusp::krylov::cg: A must be square and match x, b");
-  typedef std::integral_constant<
-      bool, cusp::detail::abi_matrix<LinearOperator>::value && detail::is_cusp_monitor<Monitor>::value &&
-                detail::is_identity_operator<typename std::remove_const<Preconditioner>::type>::value &&
-                std::is_same<typename VectorType1::value_type, typename LinearOperator::value_type>::value &&
-                std::is_same<typename VectorType2::value_type, typename LinearOperator::value_type>::value>
-      fused;
+  typedef detail::can_fuse<LinearOperator, VectorType1, VectorType2, Monitor, Preconditioner> fused;
   detail::cg_dispatch(A, x, b, monitor, M, fused());
 }
 

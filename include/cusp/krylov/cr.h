@@ -9,13 +9,15 @@
 #include "../linear_operator.h"
 #include "../monitor.h"
 #include "../multiply.h"
+#include "detail/fused.h"
 
 namespace cusp {
 namespace krylov {
 
+namespace detail {
 template <typename LinearOperator, typename VectorType1, typename VectorType2, typename Monitor,
           typename Preconditioner>
-void cr(const LinearOperator &A, VectorType1 &x, const VectorType2 &b, Monitor &monitor, Preconditioner &M) {
+void cr_generic(const LinearOperator &A, VectorType1 &x, const VectorType2 &b, Monitor &monitor, Preconditioner &M) {
   typedef typename LinearOperator::value_type ValueType;
   typedef typename LinearOperator::memory_space Space;
   if (A.num_rows != A.num_cols || x.size() != A.num_rows || b.size() != A.num_rows)
@@ -51,6 +53,26 @@ void cr(const LinearOperator &A, VectorType1 &x, const VectorType2 &b, Monitor &
     cusp::blas::axpby(Az, y, y, ValueType(1), beta);         // y <- A z + beta y  (= A p)
     ++monitor;
   }
+}
+template <typename LinearOperator, typename V1, typename V2, typename Monitor, typename Preconditioner>
+void cr_dispatch(const LinearOperator &A, V1 &x, const V2 &b, Monitor &monitor, Preconditioner &M, std::true_type) {
+  if (monitor.iteration_count() != 0) return cr_generic(A, x, b, monitor, M);
+  solve_fused(B200SP_SOLVER_CR, A, x, b, monitor, M, 1);
+}
+template <typename LinearOperator, typename V1, typename V2, typename Monitor, typename Preconditioner>
+void cr_dispatch(const LinearOperator &A, V1 &x, const V2 &b, Monitor &monitor, Preconditioner &M, std::false_type) {
+  cr_generic(A, x, b, monitor, M);
+}
+}  // namespace detail
+
+// fused device solve (b200sp_krylov: scalars and the monitor on the device, 2-3 fused vector kernels per iteration)
+// where the operands allow it (detail/fused.h), otherwise operation by operation; one iterate sequence either way
+template <typename LinearOperator, typename VectorType1, typename VectorType2, typename Monitor,
+          typename Preconditioner>
+void cr(const LinearOperator &A, VectorType1 &x, const VectorType2 &b, Monitor &monitor, Preconditioner &M) {
+  if (A.num_rows != A.num_cols || x.size() != A.num_rows || b.size() != A.num_rows)
+    throw cusp::invalid_input_exception("cusp::krylov::cr: A must be square and match x, b");
+  detail::cr_dispatch(A, x, b, monitor, M, detail::can_fuse<LinearOperator, VectorType1, VectorType2, Monitor, Preconditioner>());
 }
 
 template <typename LinearOperator, typename VectorType1, typename VectorType2, typename Monitor>

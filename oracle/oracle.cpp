@@ -230,6 +230,136 @@ static i64 cg_csr(i64 n, const int *Ap, const int *Aj, const T *Ax, T *x, const 
 }
 
 // ---------------------------------------------------------------------------
+// The other Krylov solvers with the identity or a diagonal (Jacobi) preconditioner (dinv == nullptr: identity;
+// cusp::precond::diagonal applies z = diagonal_reciprocals .* r through blas::xmy, precond/detail/diagonal.inl:52-56),
+// CSR operator, sequential sums, the monitor called exactly where the reference calls it.
+// ---------------------------------------------------------------------------
+template <typename T>
+struct OracleMonitor {  // cusp/detail/monitor.inl:178-208
+  T tol;
+  i64 limit, iter = 0, k = 0;
+  double *residuals;
+  int converged = 0;
+  bool finished(i64 n, const T *v) {
+    const T rn = nrm2<T>(n, v);
+    residuals[k++] = (double)rn;
+    if (rn <= tol) {
+      converged = 1;
+      return true;
+    }
+    return iter >= limit;
+  }
+};
+template <typename T>
+static void apply_precond(i64 n, const T *dinv, const T *r, T *z) {
+  for (i64 i = 0; i < n; i++) z[i] = dinv ? dinv[i] * r[i] : r[i];
+}
+template <typename T>
+static void axpbypcz(i64 n, T a, const T *x, T b, const T *y, T c, const T *z, T *out) {
+  for (i64 i = 0; i < n; i++) out[i] = a * x[i] + b * y[i] + c * z[i];
+}
+
+// cusp/krylov/detail/cg.inl:35-107 with a preconditioner
+template <typename T>
+static i64 pcg_csr(i64 n, const int *Ap, const int *Aj, const T *Ax, const T *dinv, T *x, const T *b, i64 limit, double rel,
+                   double abs_tol, double *residuals, i64 *nres, int *converged) {
+  std::vector<T> y(n), z(n), r(n), p(n);
+  OracleMonitor<T> mon{(T)abs_tol + (T)rel * nrm2<T>(n, b), limit, 0, 0, residuals};
+  spmv_csr<T>(n, Ap, Aj, Ax, x, y.data(), 0);
+  axpby<T>(n, T(1), b, T(-1), y.data(), r.data());
+  apply_precond<T>(n, dinv, r.data(), z.data());
+  p = z;
+  T rz = dot<T>(n, r.data(), z.data());
+  while (!mon.finished(n, r.data())) {
+    spmv_csr<T>(n, Ap, Aj, Ax, p.data(), y.data(), 0);
+    const T alpha = rz / dot<T>(n, y.data(), p.data());
+    axpy<T>(n, alpha, p.data(), x);
+    axpy<T>(n, -alpha, y.data(), r.data());
+    apply_precond<T>(n, dinv, r.data(), z.data());
+    const T rz_old = rz;
+    rz = dot<T>(n, r.data(), z.data());
+    const T beta = rz / rz_old;
+    axpby<T>(n, T(1), z.data(), beta, p.data(), p.data());
+    ++mon.iter;
+  }
+  *nres = mon.k;
+  *converged = mon.converged;
+  return mon.iter;
+}
+
+// cusp/krylov/detail/bicgstab.inl:35-123
+template <typename T>
+static i64 bicgstab_csr(i64 n, const int *Ap, const int *Aj, const T *Ax, const T *dinv, T *x, const T *b, i64 limit,
+                        double rel, double abs_tol, double *residuals, i64 *nres, int *converged) {
+  std::vector<T> p(n), r(n), r_star(n), s(n), Mp(n), AMp(n), Ms(n), AMs(n);
+  OracleMonitor<T> mon{(T)abs_tol + (T)rel * nrm2<T>(n, b), limit, 0, 0, residuals};
+  spmv_csr<T>(n, Ap, Aj, Ax, x, r.data(), 0);
+  axpby<T>(n, T(1), b, T(-1), r.data(), r.data());
+  p = r;
+  r_star = r;
+  T rho_old = dot<T>(n, r_star.data(), r.data());
+  while (!mon.finished(n, r.data())) {
+    apply_precond<T>(n, dinv, p.data(), Mp.data());
+    spmv_csr<T>(n, Ap, Aj, Ax, Mp.data(), AMp.data(), 0);
+    const T alpha = rho_old / dot<T>(n, r_star.data(), AMp.data());
+    axpby<T>(n, T(1), r.data(), T(-alpha), AMp.data(), s.data());
+    if (mon.finished(n, s.data())) {
+      axpby<T>(n, T(1), x, T(alpha), Mp.data(), x);
+      break;
+    }
+    apply_precond<T>(n, dinv, s.data(), Ms.data());
+    spmv_csr<T>(n, Ap, Aj, Ax, Ms.data(), AMs.data(), 0);
+    const T omega = dot<T>(n, AMs.data(), s.data()) / dot<T>(n, AMs.data(), AMs.data());
+    axpbypcz<T>(n, T(1), x, alpha, Mp.data(), omega, Ms.data(), x);
+    axpby<T>(n, T(1), s.data(), -omega, AMs.data(), r.data());
+    const T rho_new = dot<T>(n, r_star.data(), r.data());
+    const T beta = (rho_new / rho_old) * (alpha / omega);
+    rho_old = rho_new;
+    axpbypcz<T>(n, T(1), r.data(), beta, p.data(), -beta * omega, AMp.data(), p.data());
+    ++mon.iter;
+  }
+  *nres = mon.k;
+  *converged = mon.converged;
+  return mon.iter;
+}
+
+// cusp/krylov/detail/cr.inl:39-128 (r recomputed from b - A x every 8 iterations)
+template <typename T>
+static i64 cr_csr(i64 n, const int *Ap, const int *Aj, const T *Ax, const T *dinv, T *x, const T *b, i64 limit, double rel,
+                  double abs_tol, double *residuals, i64 *nres, int *converged) {
+  std::vector<T> y(n), z(n), r(n), p(n), Az(n), Axv(n);
+  OracleMonitor<T> mon{(T)abs_tol + (T)rel * nrm2<T>(n, b), limit, 0, 0, residuals};
+  spmv_csr<T>(n, Ap, Aj, Ax, x, Axv.data(), 0);
+  axpby<T>(n, T(1), b, T(-1), Axv.data(), r.data());
+  apply_precond<T>(n, dinv, r.data(), z.data());
+  p = z;
+  spmv_csr<T>(n, Ap, Aj, Ax, p.data(), y.data(), 0);
+  spmv_csr<T>(n, Ap, Aj, Ax, z.data(), Az.data(), 0);
+  T rz = dot<T>(n, r.data(), Az.data());
+  while (!mon.finished(n, r.data())) {
+    const T alpha = rz / dot<T>(n, y.data(), y.data());
+    axpy<T>(n, alpha, p.data(), x);
+    if ((mon.iter % 8) && (mon.iter > 0)) {
+      axpy<T>(n, -alpha, y.data(), r.data());
+    } else {
+      spmv_csr<T>(n, Ap, Aj, Ax, x, Axv.data(), 0);
+      axpby<T>(n, T(1), b, T(-1), Axv.data(), r.data());
+    }
+    apply_precond<T>(n, dinv, r.data(), z.data());
+    spmv_csr<T>(n, Ap, Aj, Ax, z.data(), Az.data(), 0);
+    const T rz_old = rz;
+    rz = dot<T>(n, r.data(), Az.data());
+    const T beta = rz / rz_old;
+    axpby<T>(n, T(1), z.data(), beta, p.data(), p.data());
+    axpby<T>(n, T(1), Az.data(), beta, y.data(), y.data());
+    ++mon.iter;
+  }
+  *nres = mon.k;
+  *converged = mon.converged;
+  return mon.iter;
+}
+
+// ---------------------------------------------------------------------------
 // gallery: generate_matrix_from_stencil -> DIA
 // (cusp/gallery/detail/stencil.inl:33-63 inside_grid, :114-134 fill, :143-188)
 // stencil points: npts x ndim integer offsets + value; grid: ndim extents;
@@ -556,6 +686,13 @@ extern "C" {
   i64 oracle_cg_csr_##sfx(i64 n, const int *Ap, const int *Aj, const T *Ax, T *x, const T *b, i64 limit,     \
                           double rel, double abs_tol, double *residuals, i64 *nres, int *converged) {        \
     return cg_csr<T>(n, Ap, Aj, Ax, x, b, limit, rel, abs_tol, residuals, nres, converged);                  \
+  }                                                                                                          \
+  i64 oracle_krylov_csr_##sfx(int solver, i64 n, const int *Ap, const int *Aj, const T *Ax, const T *dinv, T *x,   \
+                              const T *b, i64 limit, double rel, double abs_tol, double *residuals, i64 *nres,  \
+                              int *converged) {                                                              \
+    if (solver == 0) return pcg_csr<T>(n, Ap, Aj, Ax, dinv, x, b, limit, rel, abs_tol, residuals, nres, converged);      \
+    if (solver == 1) return bicgstab_csr<T>(n, Ap, Aj, Ax, dinv, x, b, limit, rel, abs_tol, residuals, nres, converged); \
+    return cr_csr<T>(n, Ap, Aj, Ax, dinv, x, b, limit, rel, abs_tol, residuals, nres, converged);                        \
   }                                                                                                          \
   i64 oracle_cg_csr_compensated_##sfx(i64 n, const int *Ap, const int *Aj, const T *Ax, T *x, const T *b,    \
                                       i64 limit, double rel, double abs_tol, double *residuals, i64 *nres,  \

@@ -36,7 +36,7 @@ def lib():
             ct = C.c_float if s == "f32" else C.c_double
             getattr(_lib, "oracle_dot_" + s).restype = ct
             getattr(_lib, "oracle_nrm2_" + s).restype = ct
-            for n in ("cg_csr", "cg_csr_compensated", "stencil_dia", "dia_to_coo", "csr_to_hyb", "csr_to_dia", "ell_to_coo", "hyb_to_coo"):
+            for n in ("cg_csr", "cg_csr_compensated", "krylov_csr", "stencil_dia", "dia_to_coo", "csr_to_hyb", "csr_to_dia", "ell_to_coo", "hyb_to_coo"):
                 getattr(_lib, f"oracle_{n}_{s}").restype = I64
         for n in ("max_entries_per_row", "optimal_entries_per_row", "gallery_random", "make_diagonal"):
             getattr(_lib, "oracle_" + n).restype = I64
@@ -271,6 +271,39 @@ def cg(A: dict, x0, b, iteration_limit=500, relative_tolerance=1e-5, absolute_to
         I64(iteration_limit), C.c_double(relative_tolerance), C.c_double(absolute_tolerance), _p(hist),
         C.byref(nres), C.byref(conv))
     return x, int(it), bool(conv.value), hist[: nres.value].copy()
+
+
+SOLVERS = {"cg": 0, "bicgstab": 1, "cr": 2}
+
+
+def krylov(solver: str, A: dict, x0, b, iteration_limit=500, relative_tolerance=1e-5, absolute_tolerance=0.0, dinv=None):
+    """cusp::krylov::{cg,bicgstab,cr}(A, x, b, monitor, M) on a CSR dict with M = identity (dinv=None) or
+    cusp::precond::diagonal (dinv = 1 / diag(A)).  Returns (x, iterations, converged, residuals): residuals holds one
+    entry per monitor.finished() call, like monitor.residuals (BiCGStab: two per iteration)."""
+    assert A["format"] == "csr"
+    dt = A["values"].dtype
+    x = _c(x0, dt).copy()
+    b = _c(b, dt)
+    dv = None if dinv is None else _c(dinv, dt)
+    hist = np.zeros(2 * iteration_limit + 4, dtype=np.float64)
+    nres = I64(0)
+    conv = C.c_int(0)
+    it = getattr(lib(), "oracle_krylov_csr_" + _s(dt))(
+        C.c_int(SOLVERS[solver]), I64(A["num_rows"]), _p(A["row_offsets"]), _p(A["column_indices"]), _p(A["values"]),
+        _p(dv) if dv is not None else None, _p(x), _p(b), I64(iteration_limit), C.c_double(relative_tolerance),
+        C.c_double(absolute_tolerance), _p(hist), C.byref(nres), C.byref(conv))
+    return x, int(it), bool(conv.value), hist[: nres.value].copy()
+
+
+def extract_diagonal(A: dict):
+    """cusp::extract_diagonal on a CSR dict (cusp/format_utils.h): the stored a_ii, 0 where the row has none"""
+    assert A["format"] == "csr"
+    n = A["num_rows"]
+    d = np.zeros(n, dtype=A["values"].dtype)
+    ri = csr_to_coo(A)["row_indices"]
+    on = ri == A["column_indices"]
+    d[ri[on]] = A["values"][on]
+    return d
 
 
 # ---------------------------------------------------------------------------

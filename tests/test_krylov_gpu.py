@@ -1,0 +1,128 @@
+"""Fused Krylov solvers (b200sp_krylov: Jacobi-preconditioned CG, BiCGStab, CR; csrc/krylov.cu) against the oracle's
+restatement of cusp/krylov/detail/{cg,bicgstab,cr}.inl (oracle.krylov): same iteration count, the same monitor.residuals
+entry by entry (fp64: 1e-10 — only the summation order of the dot products differs; fp32: the rounding of the
+regrouped sums is amplified by the recurrences, so the first entries are held tight and the whole history loosely),
+the same solution, for every format, with and without the diagonal preconditioner, for operators on which the
+preconditioner matters (rows scaled by 1 .. 100), early exit inside BiCGStab, iteration limit, host poll interval."""
+import numpy as np
+import pytest
+import torch
+
+import cusp_autotuned_b200 as cusp
+from cusp_autotuned_b200 import capi
+from cusp_autotuned_b200 import krylov as K
+from helpers import tdev, upload
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+DTYPES = [(np.float32, torch.float32), (np.float64, torch.float64)]
+
+
+def scaled_poisson(grid, ndt, seed=5):
+    """D A D with A = poisson5pt/7pt and D = diag(1 .. 10): symmetric positive definite, diagonal from 4 to 600 — the
+    Jacobi preconditioner changes the iteration count"""
+    st = 5 if len(grid) == 2 else 7
+    A = O.poisson(st, grid, ndt, "csr")
+    n = A["num_rows"]
+    d = np.random.default_rng(seed).uniform(1.0, 10.0, n)
+    ri = O.csr_to_coo(A)["row_indices"]
+    A = dict(A, values=(A["values"].astype(np.float64) * d[ri] * d[A["column_indices"]]).astype(ndt))
+    return A
+
+
+def nonsymmetric(grid, ndt):
+    """convection-diffusion-like: poisson5pt + a skew part (upwind), diagonally dominant, for BiCGStab"""
+    A = O.poisson(5, grid, ndt, "csr")
+    ri = O.csr_to_coo(A)["row_indices"]
+    v = A["values"].astype(np.float64).copy()
+    v[A["column_indices"] == ri + 1] -= 0.5
+    v[A["column_indices"] == ri - 1] += 0.5
+    v[A["column_indices"] == ri] += 0.25
+    return dict(A, values=v.astype(ndt))
+
+
+def check(solver, A, fmt, ndt, tdt, dev, jacobi, limit, rel, check_interval=0, b=None):
+    n = A["num_rows"]
+    b = np.ones(n, ndt) if b is None else b.astype(ndt)
+    dinv = (1.0 / O.extract_diagonal(A)).astype(ndt) if jacobi else None
+    xo, it, conv, hist = O.krylov(solver, A, np.zeros(n, ndt), b, limit, rel, dinv=dinv)
+    Ad = upload(fmt, O.convert(A, fmt), dev)
+    M = K.diagonal(Ad) if jacobi else None
+    if jacobi:
+        assert np.array_equal(M.diagonal_reciprocals.cpu().numpy(), dinv)
+    x = torch.zeros(n, dtype=tdt, device=dev)
+    mon = cusp.monitor(None, limit, rel)
+    getattr(K, "pcg" if solver == "cg" else solver)(Ad, x, tdev(b, dev), mon, M, check_interval=check_interval)
+    tag = (solver, fmt, ndt.__name__, jacobi)
+    assert mon.iteration_count() == it, (tag, mon.iteration_count(), it)
+    assert mon.converged() == conv, tag
+    assert len(mon.residuals) == len(hist), (tag, len(mon.residuals), len(hist))
+    got = np.asarray(mon.residuals)
+    if ndt == np.float64:
+        assert np.allclose(got, hist, rtol=1e-9, atol=0), (tag, np.max(np.abs(got - hist) / hist))
+        assert np.allclose(x.cpu().numpy(), xo, rtol=1e-8, atol=1e-12 * np.abs(xo).max()), tag
+    else:
+        m = min(6, len(hist))
+        assert np.allclose(got[:m], hist[:m], rtol=1e-3), tag
+        assert np.all(np.abs(got - hist) <= 2e-2 * hist[0] + 1e-3 * hist), tag
+        assert np.allclose(x.cpu().numpy(), xo, rtol=0, atol=5e-3 * np.abs(xo).max()), tag
+    return mon
+
+
+@pytest.mark.parametrize("ndt,tdt", DTYPES)
+@pytest.mark.parametrize("solver", ["cg", "cr", "bicgstab"])
+@pytest.mark.parametrize("jacobi", [False, True])
+def test_fused_solver_matches_the_reference_iteration(solver, jacobi, ndt, tdt, dev):
+    A = scaled_poisson((24, 19), ndt)
+    rel = 1e-5 if ndt == np.float32 else 1e-9
+    plain = check(solver, A, "csr", ndt, tdt, dev, jacobi, 400, rel)
+    assert plain.converged()
+    for fmt in ("dia", "ell", "coo", "hyb"):
+        check(solver, A, fmt, ndt, tdt, dev, jacobi, 400, rel)
+
+
+def test_jacobi_preconditioner_pays(dev):
+    """on the row-scaled operator the preconditioned solves need far fewer iterations — and exactly the oracle's count"""
+    A = scaled_poisson((30, 30), np.float64)
+    for solver in ("cg", "cr", "bicgstab"):
+        a = check(solver, A, "csr", np.float64, torch.float64, dev, False, 2000, 1e-8)
+        b = check(solver, A, "csr", np.float64, torch.float64, dev, True, 2000, 1e-8)
+        assert b.iteration_count() < 0.6 * a.iteration_count(), (solver, a.iteration_count(), b.iteration_count())
+
+
+@pytest.mark.parametrize("jacobi", [False, True])
+def test_bicgstab_nonsymmetric_and_early_exit(jacobi, dev):
+    """a non-symmetric operator; and a tolerance that is met by s in mid-iteration (bicgstab.inl:77-81: x += alpha M p,
+    break, the iteration is not counted)"""
+    A = nonsymmetric((21, 17), np.float64)
+    check("bicgstab", A, "csr", np.float64, torch.float64, dev, jacobi, 300, 1e-10)
+    xo_hist = O.krylov("bicgstab", A, np.zeros(A["num_rows"]), np.ones(A["num_rows"]), 300, 1e-10,
+                       dinv=(1.0 / O.extract_diagonal(A)) if jacobi else None)[3]
+    # choose a tolerance between some ||s|| and the ||r|| before it: the solve must stop on s
+    norms_r, norms_s = xo_hist[0::2], xo_hist[1::2]
+    k = next(i for i in range(2, len(norms_s)) if norms_s[i] < 0.8 * norms_r[i] and norms_s[i] < min(norms_r[:i + 1]))
+    rel = 0.5 * (norms_s[k] + min(norms_r[k], norms_s[k] * 1.2)) / np.sqrt(A["num_rows"])
+    mon = check("bicgstab", A, "csr", np.float64, torch.float64, dev, jacobi, 300, rel)
+    assert len(mon.residuals) % 2 == 0  # ended on a finished(s) call
+
+
+@pytest.mark.parametrize("check_interval", [1, 5, 16])
+@pytest.mark.parametrize("solver", ["cg", "cr", "bicgstab"])
+def test_iteration_limit_and_poll_interval(solver, check_interval, dev):
+    """limit reached before convergence: count == limit and the history has one entry per monitor.finished() call,
+    however often the host polls; CR passes its every-8-iterations recomputation of r twice"""
+    A = scaled_poisson((12, 11, 10), np.float64)
+    b = np.random.default_rng(3).uniform(-1, 1, A["num_rows"])
+    mon = check(solver, A, "dia" if solver != "bicgstab" else "csr", np.float64, torch.float64, dev, True, 19, 1e-14,
+                check_interval=check_interval, b=b)
+    assert mon.iteration_count() == 19 and not mon.converged()
+    assert len(mon.residuals) == (2 * 19 + 1 if solver == "bicgstab" else 20)
+
+
+def test_krylov_argument_errors(dev, handle):
+    A = upload("csr", O.poisson(5, (4, 4), np.float32, "csr"), dev)
+    with pytest.raises(cusp.InvalidInput):
+        K.bicgstab(A, torch.zeros(15, device=dev), torch.zeros(16, device=dev))
+    R = upload("csr", O.gallery_random(8, 6, 20, np.float32, "csr"), dev)  # not square
+    with pytest.raises(cusp.InvalidInput):
+        handle.krylov("cr", R.descriptor(), torch.zeros(8, device=dev), torch.zeros(8, device=dev))

@@ -638,6 +638,7 @@ def test_generalized_min_plus_on_real_data(dev, handle):
     for fmt in ("coo", "csr", "hyb"):
         A = to_fmt(coo, fmt)
         want = O.spmv_generalized(A, dist, dist, "identity", 0.0, "plus", "minimum")
-        yd = tdev(dist, dev)
-        handle.spmv_generalized(upload_any(fmt, A, dev).descriptor(), tdev(dist, dev), yd, "identity", 0.0, "plus", "minimum")
+        yd, xd = tdev(dist, dev), tdev(dist, dev)
+        Ad = upload_any(fmt, A, dev)  # must outlive the call: the descriptor only borrows its arrays
+        handle.spmv_generalized(Ad.descriptor(), xd, yd, "identity", 0.0, "plus", "minimum")
         assert np.array_equal(yd.cpu().numpy(), want), fmt

@@ -87,7 +87,24 @@ def main():
                 hist_ok = hist_ok and len(hist) == len(hist_o)
                 x_ok = bool(np.allclose(xl.cpu().numpy(), xo[blk.row_begin: blk.row_begin + blk.num_rows],
                                         rtol=1e-3 if ndt == np.float32 else 1e-9))
-                flags = torch.tensor([int(exact), int(same_it), int(hist_ok), int(x_ok)], device=dev)
+                # the other fused solvers, partitioned (b200sp_krylov with halo): Jacobi-CG, BiCGStab, CR
+                kr_ok = 1
+                if fmt == "dia" and ndt == np.float64:
+                    csr_ref = O.convert(ref, "csr")
+                    dinv_g = 1.0 / O.extract_diagonal(csr_ref)
+                    dinv_l = torch.from_numpy(dinv_g[blk.row_begin: blk.row_begin + blk.num_rows]).to(dev)
+                    for solver, jac in (("cg", True), ("bicgstab", False), ("bicgstab", True), ("cr", False), ("cr", True)):
+                        xo2, it2, conv2, hist2 = O.krylov(solver, csr_ref, np.zeros(n), b, 40, 1e-6, dinv=dinv_g if jac else None)
+                        xl2 = torch.zeros(blk.num_rows, dtype=tdt, device=dev)
+                        res2, h2 = h.krylov(solver, A.descriptor(), xl2, bl, diagonal_inverse=dinv_l if jac else None,
+                                            iteration_limit=40, relative_tolerance=1e-6, check_interval=4,
+                                            halo=halo if world > 1 else None)
+                        good = (int(res2.iteration_count) == it2 and len(h2) == len(hist2) and
+                                bool(np.allclose(h2, hist2, rtol=1e-9, atol=0)) and
+                                bool(np.allclose(xl2.cpu().numpy(), xo2[blk.row_begin: blk.row_begin + blk.num_rows], rtol=1e-8,
+                                                 atol=1e-12)))
+                        kr_ok &= int(good)
+                flags = torch.tensor([int(exact), int(same_it), int(hist_ok), int(x_ok) & kr_ok], device=dev)
                 if world > 1:
                     td.all_reduce(flags, op=td.ReduceOp.MIN)
                 f = [int(v) for v in flags.cpu().tolist()]
