@@ -133,7 +133,8 @@ _SFX = ("f32", "f64")
 EXPORTED_SYMBOLS = (
     ["b200sp_version", "b200sp_create", "b200sp_destroy", "b200sp_last_error_string",
      "b200sp_status_string", "b200sp_launch_count", "b200sp_set_l2_persist",
-     "b200sp_ell_row_lengths", "b200sp_spmv", "b200sp_spmv_generalized", "b200sp_spmv_host", "b200sp_cg", "b200sp_krylov",
+     "b200sp_ell_row_lengths", "b200sp_spmv", "b200sp_spmv_generalized", "b200sp_spmv_host", "b200sp_cg", "b200sp_krylov", "b200sp_spmv_graph_create", "b200sp_graph_launch",
+     "b200sp_graph_destroy",
      "b200sp_comm_unique_id", "b200sp_comm_init", "b200sp_comm_destroy", "b200sp_cg_dist",
      "b200sp_spmv_dist", "b200sp_spmv_dist_host", "b200sp_spmv_dist_gather", "b200sp_comm_p2p_enabled", "b200sp_comm_timeouts", "b200sp_cfg_space", "b200sp_tune", "b200sp_tune_step",
      "b200sp_tune_reset", "b200sp_tune_lookup", "b200sp_tune_save", "b200sp_tune_load",
@@ -326,6 +327,19 @@ class Handle:
         f = Functors(INIT_IDENTITY if initialize == "identity" else INIT_CONSTANT, float(init_value), COMBINE[combine],
                      REDUCE[reduce])
         self.check(self.lib.b200sp_spmv_generalized(self._h, _stream(), C.byref(A), _ptr(x), _ptr(y), C.byref(f)))
+
+    def spmv_graph_create(self, A: Matrix, x, y, count: int, accumulate=False, cfg: Optional[Cfg] = None):
+        """`count` back-to-back products captured in one CUDA graph (launch-bound sizes); replay with graph_launch"""
+        g = C.c_void_p()
+        self.check(self.lib.b200sp_spmv_graph_create(self._h, _stream(), C.byref(A), _ptr(x), _ptr(y), C.c_int(int(accumulate)),
+                                                     C.byref(cfg) if cfg else None, C.c_int(count), C.byref(g)))
+        return g
+
+    def graph_launch(self, graph):
+        self.check(self.lib.b200sp_graph_launch(self._h, _stream(), graph))
+
+    def graph_destroy(self, graph):
+        self.check(self.lib.b200sp_graph_destroy(self._h, graph))
 
     def spmv_host(self, A: Matrix, x_host, y_host, accumulate=False, cfg: Optional[Cfg] = None):
         self.check(self.lib.b200sp_spmv_host(self._h, _stream(), C.byref(A), _ptr(x_host), _ptr(y_host),

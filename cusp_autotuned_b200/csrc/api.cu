@@ -417,6 +417,8 @@ b200sp_status b200sp_destroy(b200sp_handle h) {
   if (h->cg_ws) cudaFree(h->cg_ws);
   if (h->cg_residuals) cudaFree(h->cg_residuals);
   for (void *ev : h->tune_events) cudaEventDestroy((cudaEvent_t)ev);
+  if (h->graph_event) cudaEventDestroy((cudaEvent_t)h->graph_event);
+  if (h->graph_stream) cudaStreamDestroy((cudaStream_t)h->graph_stream);
   delete h;
   return B200SP_OK;
 }
@@ -655,6 +657,70 @@ b200sp_status b200sp_spmv_dist_host(b200sp_handle h, b200sp_stream stream, const
   if (s != B200SP_OK) return s;
   B200SP_CUDA(h, cudaMemcpyAsync(y_host_local, h->stage_y, yb, cudaMemcpyDeviceToHost, st));
   B200SP_CUDA(h, cudaStreamSynchronize(st));
+  return B200SP_OK;
+}
+
+/* ---- captured products (small, launch-bound systems) ---------------------------------------------------- */
+struct b200sp_graph_s {
+  cudaGraphExec_t exec;
+  int count;
+};
+
+b200sp_status b200sp_spmv_graph_create(b200sp_handle h, b200sp_stream stream, const b200sp_matrix *A, const void *x,
+                                       void *y, int accumulate, const b200sp_cfg *cfg, int count, b200sp_graph *out) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, A && x && y && out && count >= 1 && count <= 4096, "spmv_graph_create: bad arguments");
+  *out = nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  // one plain product first: structure analysis, scratch growth and tuning-cache lookups happen outside the capture
+  b200sp_status s = b200sp_spmv(h, stream, A, x, y, accumulate, cfg);
+  if (s != B200SP_OK) return s;
+  if (!h->graph_stream) {
+    cudaStream_t gs;
+    B200SP_CUDA(h, cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking));
+    h->graph_stream = gs;
+  }
+  B200SP_CUDA(h, cudaStreamSynchronize(st));
+  cudaStream_t gs = (cudaStream_t)h->graph_stream;
+  cudaGraph_t graph = nullptr;
+  B200SP_CUDA(h, cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+  const uint64_t launches_before = h->launches;
+  for (int k = 0; k < count && s == B200SP_OK; ++k) s = b200sp_spmv(h, (b200sp_stream)gs, A, x, y, accumulate, cfg);
+  const uint64_t per_replay = h->launches - launches_before;
+  h->launches = launches_before;
+  cudaError_t ce = cudaStreamEndCapture(gs, &graph);
+  if (s != B200SP_OK || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    return s != B200SP_OK ? s : b200sp::set_error(h, B200SP_CUDA_ERROR, "spmv_graph_create: capture failed: %s", cudaGetErrorString(ce));
+  }
+  cudaGraphExec_t exec = nullptr;
+  ce = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) {
+    cudaGetLastError();
+    return b200sp::set_error(h, B200SP_CUDA_ERROR, "spmv_graph_create: cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+  }
+  b200sp_graph g = new b200sp_graph_s();
+  g->exec = exec;
+  g->count = (int)per_replay;
+  *out = g;
+  return B200SP_OK;
+}
+
+b200sp_status b200sp_graph_launch(b200sp_handle h, b200sp_stream stream, b200sp_graph graph) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, graph != nullptr, "graph_launch: null graph");
+  B200SP_CUDA(h, cudaGraphLaunch(graph->exec, (cudaStream_t)stream));
+  h->launches += (uint64_t)graph->count;
+  return B200SP_OK;
+}
+
+b200sp_status b200sp_graph_destroy(b200sp_handle h, b200sp_graph graph) {
+  B200SP_CHECK_HANDLE(h);
+  if (!graph) return B200SP_OK;
+  cudaGraphExecDestroy(graph->exec);
+  delete graph;
   return B200SP_OK;
 }
 

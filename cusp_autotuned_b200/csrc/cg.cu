@@ -682,8 +682,11 @@ static b200sp_status cg_impl(b200sp_handle h, cudaStream_t st, const b200sp_matr
   // every kernel requests what its predecessor does not write before griddepcontrol.wait, so launch latency and
   // first-batch load latency overlap the predecessor's tail.  The DIA bulk kernel joins in through h->pdl_spmv
   // (its producer lane streams matrix slabs into the ring while the direction kernel is still finishing).
+  // Default: on for the partitioned peer-memory path (kernels of 0.1 ms, poll-gated), off on one GPU, where the
+  // kernels run ~1 ms each and the early-resident successor CTAs cost more than the hidden launch gap (512^3 on one
+  // B200: 3.14 ms / iteration with, 2.95 without — profiles/r03_cg_pdl.md).
   const char *pdl_env = getenv("B200SP_CG_PDL");
-  const bool pdl = !(pdl_env && pdl_env[0] == '0');
+  const bool pdl = pdl_env ? (pdl_env[0] != '0') : (dist && h->p2p_ok && h->world > 1);
   struct PdlScope {  // the flag must not leak into products outside this solve
     b200sp_handle h;
     ~PdlScope() { h->pdl_spmv = false; }
@@ -703,6 +706,72 @@ static b200sp_status cg_impl(b200sp_handle h, cudaStream_t st, const b200sp_matr
       if (p) cudaFree(p);
     }
   } trace_scope{trace};
+  // Small systems are launch-bound (poisson5pt 512^2: ~5 us of kernels per iteration against ~25 us of launch calls):
+  // one GPU, no per-iteration kernel arguments -> the `check_interval` iterations between two host polls are captured
+  // once in a CUDA graph and replayed (B200SP_CG_GRAPH=0 / 1 overrides the size rule).  Capture happens on a stream
+  // of the handle (the caller's may be the legacy default stream, which cannot be captured), ordered behind and
+  // before the caller's stream with events.
+  const char *graph_env = getenv("B200SP_CG_GRAPH");
+  bool use_graph = !dist && (graph_env ? graph_env[0] != '0' : n <= ((i64)1 << 22));
+  cudaGraphExec_t graph_exec = nullptr;
+  cudaStream_t run_st = st;
+  if (use_graph) {
+    if (!h->graph_stream) {
+      cudaStream_t gs;
+      if (cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking) == cudaSuccess) h->graph_stream = gs;
+    }
+    if (!h->graph_event) {
+      cudaEvent_t ev;
+      if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) h->graph_event = ev;
+    }
+    use_graph = h->graph_stream && h->graph_event;
+  }
+  if (use_graph) {
+    cudaStream_t gs = (cudaStream_t)h->graph_stream;
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      const uint64_t launches_before = h->launches;
+      for (int k = 0; k < prm.check_interval && ok; ++k) {
+        ok = spmv_any<T>(h, gs, A, p, y, 0, cfg, p, &S->yp) == B200SP_OK;
+        ok = ok && launch_kernel_pdl(cg_update_kernel<T, false>, dim3((unsigned)g), dim3(CG_BLOCK), 0, gs, pdl, n, (const T *)p,
+                                     (const T *)y, x, r, S, partials, ticket, res) == cudaSuccess;
+        ok = ok && launch_kernel_pdl(cg_direction_kernel<T>, dim3((unsigned)gdir), dim3(CG_BLOCK), 0, gs, pdl, n, (const T *)r, p,
+                                     (const CgState<T> *)S) == cudaSuccess;
+      }
+      h->launches = launches_before;  // counted per replay below
+      ok = (cudaStreamEndCapture(gs, &graph) == cudaSuccess) && ok && graph;
+    }
+    if (ok) ok = cudaGraphInstantiate(&graph_exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+      cudaGetLastError();
+      graph_exec = nullptr;
+      use_graph = false;
+    } else {
+      // everything queued so far on the caller's stream precedes the first replay
+      B200SP_CUDA(h, cudaEventRecord((cudaEvent_t)h->graph_event, st));
+      B200SP_CUDA(h, cudaStreamWaitEvent(gs, (cudaEvent_t)h->graph_event, 0));
+      run_st = gs;
+    }
+  }
+  struct GraphScope {
+    cudaGraphExec_t &e;
+    ~GraphScope() {
+      if (e) cudaGraphExecDestroy(e);
+    }
+  } graph_scope{graph_exec};
+  auto poll_on = [&](cudaStream_t ps) -> b200sp_status {
+    B200SP_CUDA(h, cudaMemcpyAsync(hs, S, sizeof(CgState<T>), cudaMemcpyDeviceToHost, ps));
+    B200SP_CUDA(h, cudaStreamSynchronize(ps));
+    return B200SP_OK;
+  };
+  while (use_graph && !hs->done) {
+    B200SP_CUDA(h, cudaGraphLaunch(graph_exec, run_st));
+    h->launches += 3 * (uint64_t)prm.check_interval;
+    s = poll_on(run_st);
+    if (s != B200SP_OK) return s;
+  }
   while (!hs->done) {
     for (int k = 0; k < prm.check_interval; ++k) {
       if (p2p) {

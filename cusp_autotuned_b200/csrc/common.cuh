@@ -96,6 +96,8 @@ struct b200sp_context {
   // set by the CG driver around its iteration: the DIA bulk kernel is launched with programmatic stream
   // serialization and waits (griddepcontrol.wait) before its first read of x / y (spmv_dia.cu, cg.cu)
   bool pdl_spmv = false;
+  // CUDA-graph paths (small, launch-bound systems): a capturable stream and an ordering event owned by the handle
+  void *graph_stream = nullptr, *graph_event = nullptr;
 
   // multi-GPU
   void *nccl_comm = nullptr;

@@ -298,6 +298,19 @@ b200sp_status b200sp_spmv_host(b200sp_handle h, b200sp_stream stream,
                                const b200sp_matrix *A, const void *x_host,
                                void *y_host, int accumulate, const b200sp_cfg *cfg);
 
+/* ---- captured products: the launch-bound regime ---------------------------------------------------------
+ * A product on an L2-resident operator (BASELINE configs[0], poisson5pt 512^2: 21 MB) takes ~5 us on the GPU and
+ * ~10 us of host time per call.  b200sp_spmv_graph_create captures `count` back-to-back products y = A x (fixed
+ * pointers: a solver's inner loop, a power iteration) into one CUDA graph; b200sp_graph_launch replays it with one
+ * host call.  Same kernels and results as `count` calls of b200sp_spmv.  The graph borrows every array of A, x
+ * and y.  b200sp_cg does the same internally for small systems (check_interval iterations per replay). */
+typedef struct b200sp_graph_s *b200sp_graph;
+b200sp_status b200sp_spmv_graph_create(b200sp_handle h, b200sp_stream stream, const b200sp_matrix *A,
+                                       const void *x, void *y, int accumulate, const b200sp_cfg *cfg,
+                                       int count, b200sp_graph *out);
+b200sp_status b200sp_graph_launch(b200sp_handle h, b200sp_stream stream, b200sp_graph graph);
+b200sp_status b200sp_graph_destroy(b200sp_handle h, b200sp_graph graph);
+
 /* ---- conjugate gradients -------------------------------------------------
  * cusp::krylov::cg(A, x, b, monitor) with the identity preconditioner
  * (cusp/krylov/detail/cg.inl:35-107) and cusp::monitor semantics
@@ -306,7 +319,9 @@ b200sp_status b200sp_spmv_host(b200sp_handle h, b200sp_stream stream,
  * or iteration_count >= iteration_limit; the residual norm is recorded before
  * every iteration and once more at exit, exactly like monitor.residuals.
  * Same iterate sequence as the reference (same operation order per entry);
- * fused into 3 kernels / iteration with device-resident scalars.
+ * fused into 3 kernels / iteration with device-resident scalars, chained by programmatic
+ * dependent launch; on systems of up to 2^22 rows the check_interval iterations between two
+ * host polls are replayed from one CUDA graph (launch-bound regime).
  */
 typedef struct {
   int64_t iteration_limit;   /* monitor default 500  */

@@ -147,3 +147,57 @@ def test_cg_size_mismatch(dev):
     A = upload("csr", O.poisson(5, (4, 4), np.float32, "csr"), dev)
     with pytest.raises(cusp.InvalidInput):
         cusp.krylov.cg(A, torch.zeros(15, device=dev), torch.zeros(16, device=dev))
+
+
+def test_captured_products_equal_plain_calls(dev, handle):
+    """b200sp_spmv_graph_create / b200sp_graph_launch: `count` products replayed from one CUDA graph give the bits of
+    `count` plain calls — assign and accumulate forms, CSR / DIA / COO, torch's (legacy default) stream as caller"""
+    A = O.poisson(5, (64, 48), np.float64, "coo")
+    n = A["num_rows"]
+    rng = np.random.default_rng(9)
+    x = tdev(rng.uniform(-1, 1, n), dev)
+    for fmt in ("csr", "dia", "coo", "ell", "hyb"):
+        Ad = upload(fmt, O.convert(A, fmt), dev)
+        d = Ad.descriptor()
+        y_plain = torch.zeros(n, dtype=torch.float64, device=dev)
+        handle.spmv(d, x, y_plain)
+        y_g = torch.full((n,), 7.0, dtype=torch.float64, device=dev)
+        g = handle.spmv_graph_create(d, x, y_g, 5)
+        l0 = handle.launch_count
+        handle.graph_launch(g)
+        assert handle.launch_count > l0
+        torch.cuda.synchronize()
+        assert torch.equal(y_g, y_plain), fmt
+        handle.graph_destroy(g)
+        # accumulate: 3 replays of 4 captured products add 12 A x (plus the one plain product creation makes)
+        y_acc = torch.zeros(n, dtype=torch.float64, device=dev)
+        g = handle.spmv_graph_create(d, x, y_acc, 4, accumulate=True)
+        for _ in range(3):
+            handle.graph_launch(g)
+        want = torch.zeros(n, dtype=torch.float64, device=dev)
+        for _ in range(13):
+            handle.spmv(d, x, want, accumulate=True)
+        torch.cuda.synchronize()
+        assert torch.equal(y_acc, want), fmt
+        handle.graph_destroy(g)
+
+
+@pytest.mark.parametrize("fmt", ["csr", "dia", "coo"])
+def test_cg_graph_replay_is_the_same_solve(fmt, dev, monkeypatch):
+    """small systems: b200sp_cg replays check_interval iterations from one CUDA graph (B200SP_CG_GRAPH) — iteration
+    count, history and solution are those of the launch-by-launch solve, bit for bit"""
+    A = O.poisson(5, (40, 33), np.float64, fmt)
+    Ad = upload(fmt, A, dev)
+    b = tdev(np.random.default_rng(2).uniform(-1, 1, A["num_rows"]), dev)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("B200SP_CG_GRAPH", mode)
+        for ci in (1, 7, 16):
+            x = torch.zeros_like(b)
+            mon = cusp.monitor(b, 300, 1e-10)
+            cusp.krylov.cg(Ad, x, b, mon, check_interval=ci)
+            out[(mode, ci)] = (mon.iteration_count(), list(mon.residuals), x.clone())
+    base = out[("0", 1)]
+    assert base[0] > 20
+    for k, v in out.items():
+        assert v[0] == base[0] and v[1] == base[1] and torch.equal(v[2], base[2]), k
