@@ -133,7 +133,7 @@ _SFX = ("f32", "f64")
 EXPORTED_SYMBOLS = (
     ["b200sp_version", "b200sp_create", "b200sp_destroy", "b200sp_last_error_string",
      "b200sp_status_string", "b200sp_launch_count", "b200sp_set_l2_persist",
-     "b200sp_ell_row_lengths", "b200sp_spmv", "b200sp_spmv_generalized", "b200sp_spmv_host", "b200sp_cg", "b200sp_krylov", "b200sp_spmv_graph_create", "b200sp_graph_launch",
+     "b200sp_ell_row_lengths", "b200sp_csr_row_starts", "b200sp_spmv", "b200sp_spmv_generalized", "b200sp_spmv_host", "b200sp_cg", "b200sp_krylov", "b200sp_spmv_graph_create", "b200sp_graph_launch",
      "b200sp_graph_destroy",
      "b200sp_comm_unique_id", "b200sp_comm_init", "b200sp_comm_destroy", "b200sp_cg_dist",
      "b200sp_spmv_dist", "b200sp_spmv_dist_host", "b200sp_spmv_dist_gather", "b200sp_comm_p2p_enabled", "b200sp_comm_timeouts", "b200sp_cfg_space", "b200sp_tune", "b200sp_tune_step",
@@ -327,6 +327,11 @@ class Handle:
         f = Functors(INIT_IDENTITY if initialize == "identity" else INIT_CONSTANT, float(init_value), COMBINE[combine],
                      REDUCE[reduce])
         self.check(self.lib.b200sp_spmv_generalized(self._h, _stream(), C.byref(A), _ptr(x), _ptr(y), C.byref(f)))
+
+    def csr_row_starts(self, num_rows, num_entries, row_offsets, workers, out):
+        """row_starts[w] = row containing entry w * ceil(nnz / workers) (balanced-CSR preprocessing)"""
+        self.check(self.lib.b200sp_csr_row_starts(self._h, _stream(), C.c_int64(num_rows), C.c_int64(num_entries),
+                                                  _ptr(row_offsets), C.c_int64(workers), _ptr(out)))
 
     def spmv_graph_create(self, A: Matrix, x, y, count: int, accumulate=False, cfg: Optional[Cfg] = None):
         """`count` back-to-back products captured in one CUDA graph (launch-bound sizes); replay with graph_launch"""

@@ -727,6 +727,27 @@ template b200sp_status spmv_hyb<double>(b200sp_handle, cudaStream_t, i64, i64, i
 }  // namespace b200sp
 
 extern "C" {
+// row_starts[w] = the row that contains entry w * chunk, chunk = ceil(num_entries / workers); workers whose first
+// entry lies beyond the matrix get 0 — cpu_compute_row_starts / gpu_compute_row_starts of the reference's balanced
+// CSR kernel (cusp/system/cuda/ktt/csr_multiply.h:38-85).  K_CSR_BALANCED computes the same array with chunk = its
+// tile size before every product (csr_tile_rows_kernel above).
+b200sp_status b200sp_csr_row_starts(b200sp_handle h, b200sp_stream stream, int64_t num_rows, int64_t num_entries,
+                                    const int32_t *row_offsets, int64_t workers, int32_t *row_starts) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, num_rows >= 0 && num_entries >= 0 && workers >= 0 && workers < (1ll << 31), "csr_row_starts: bad sizes");
+  if (workers == 0) return B200SP_OK;
+  B200SP_REQUIRE(h, row_starts && (num_rows == 0 || row_offsets), "csr_row_starts: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  B200SP_CUDA(h, cudaMemsetAsync(row_starts, 0, (size_t)workers * sizeof(int32_t), st));
+  if (num_rows == 0 || num_entries == 0) return B200SP_OK;
+  const int64_t chunk = (num_entries + workers - 1) / workers;
+  B200SP_REQUIRE(h, chunk < (1ll << 31), "csr_row_starts: chunk exceeds the int32 range");
+  b200sp::csr_tile_rows_kernel<<<(unsigned)b200sp::ceil_div(num_rows, 256), 256, 0, st>>>(num_rows, row_offsets, (int)chunk,
+                                                                                            row_starts);
+  B200SP_LAUNCH_CHECK(h, "csr_tile_rows_kernel");
+  return B200SP_OK;
+}
+
 #define DEF(T, sfx)                                                                              \
   b200sp_status b200sp_spmv_coo_##sfx(b200sp_handle h, b200sp_stream stream, int64_t num_rows,   \
                                       int64_t num_cols, int64_t num_entries,                     \

@@ -169,6 +169,14 @@ B200SP_DECL_SPMV(float, f32)
 B200SP_DECL_SPMV(double, f64)
 #undef B200SP_DECL_SPMV
 
+/* Preprocessing of the balanced CSR kernel (cusp/system/cuda/ktt/csr_multiply.h:38-85, cpu_compute_row_starts /
+ * gpu_compute_row_starts): row_starts[w] = the row containing entry w * chunk, chunk = ceil(num_entries / workers);
+ * 0 for workers that start beyond the last entry.  K_CSR_BALANCED computes this array (chunk = its tile size) before
+ * every product; the entry point exposes it (bit-exact parity with the reference's host version). */
+b200sp_status b200sp_csr_row_starts(b200sp_handle h, b200sp_stream stream, int64_t num_rows,
+                                    int64_t num_entries, const int32_t *row_offsets, int64_t workers,
+                                    int32_t *row_starts);
+
 /* row_lengths for ELL-R: count of leading non-negative column slots per row
  * (cusp/ktt/detail/ellr_matrix.inl:16-52). */
 b200sp_status b200sp_ell_row_lengths(b200sp_handle h, b200sp_stream stream,

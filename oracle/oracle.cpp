@@ -476,6 +476,22 @@ static i64 hyb_to_coo(i64 rows, i64 K, i64 pitch, const int *ecidx, const T *eva
   return n;
 }
 
+// cpu_compute_row_starts (cusp/system/cuda/ktt/csr_multiply.h:38-61): the preprocessing of the balanced CSR kernel.
+// out[w] = the row whose entry range contains w * chunk, chunk = ceil(nnz / workers); workers beyond the matrix get 0.
+static void compute_row_starts(i64 rows, i64 nnz, const int *Ap, i64 workers, int *out) {
+  i64 count = 0, w = 0;
+  const i64 chunk = workers > 0 ? (nnz + workers - 1) / workers : 0;
+  for (i64 i = 0; i < rows; i++) {
+    const i64 next = Ap[i + 1];
+    while (count <= w * chunk && w * chunk < next && w < workers) {
+      out[w] = (int)i;
+      ++w;
+    }
+    count = next;
+  }
+  for (; w < workers; ++w) out[w] = 0;
+}
+
 // indices_to_offsets / offsets_to_indices (cusp/format_utils.h, testing/format_utils.cu:13-75)
 static void indices_to_offsets(i64 nnz, const int *idx, i64 rows, int *offs) {
   // offsets[i] = number of indices < i  (lower_bound over sorted indices)
@@ -735,6 +751,9 @@ DEF(float, f32)
 DEF(double, f64)
 #undef DEF
 
+void oracle_compute_row_starts(i64 rows, i64 nnz, const int *Ap, i64 workers, int *out) {
+  compute_row_starts(rows, nnz, Ap, workers, out);
+}
 void oracle_indices_to_offsets(i64 nnz, const int *idx, i64 rows, int *offs) {
   indices_to_offsets(nnz, idx, rows, offs);
 }

@@ -425,6 +425,14 @@ def csr_to_coo(A: dict) -> dict:
                 row_indices=idx, column_indices=A["column_indices"].copy(), values=A["values"].copy())
 
 
+def compute_row_starts(row_offsets, workers: int):
+    """cpu_compute_row_starts (cusp/system/cuda/ktt/csr_multiply.h:38-61)"""
+    ro = _c(row_offsets, np.int32)
+    out = np.zeros(max(workers, 1), np.int32)[:workers]
+    lib().oracle_compute_row_starts(I64(len(ro) - 1), I64(int(ro[-1])), _p(ro), I64(workers), _p(out))
+    return out
+
+
 def optimal_entries_per_row(row_offsets, relative_speed=3.0, breakeven_threshold=4096) -> int:
     return int(lib().oracle_optimal_entries_per_row(I64(len(row_offsets) - 1), _p(_c(row_offsets, np.int32)),
                                                     C.c_float(relative_speed), I64(breakeven_threshold)))

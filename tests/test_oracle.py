@@ -269,3 +269,21 @@ def test_committed_cg_history_is_the_oracles():
     assert big["rows"] == 512 ** 3 and big["nnz"] == 937951232 and len(big["residuals"]) == big["iterations"] + 1 == 51
     assert len(big["residuals_compensated"]) == 51 and big["sequential_vs_compensated_max_rel_dev"] < 1e-7
     assert abs(big["residuals"][0] - np.sqrt(512 ** 3)) < 1e-6
+
+
+def test_compute_row_starts_restates_the_balanced_csr_preprocessing():
+    """cpu_compute_row_starts (cusp/system/cuda/ktt/csr_multiply.h:38-61): out[w] = the row containing entry
+    w * ceil(nnz / workers), 0 beyond the matrix — against the definition by binary search, ragged rows incl. empty ones"""
+    rng = np.random.default_rng(8)
+    for rows in (1, 7, 300):
+        lens = rng.integers(0, 9, rows)
+        lens[rng.integers(0, rows, max(1, rows // 5))] = 0
+        lens[0] += 1
+        ro = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+        nnz = int(ro[-1])
+        for workers in (1, 2, 5, 64, nnz, nnz + 9):
+            got = O.compute_row_starts(ro, workers)
+            chunk = -(-nnz // workers)
+            e = np.arange(workers, dtype=np.int64) * chunk
+            want = np.where(e < nnz, np.searchsorted(ro, e, side="right") - 1, 0).astype(np.int32)
+            assert np.array_equal(got, want), (rows, workers)

@@ -642,3 +642,23 @@ def test_generalized_min_plus_on_real_data(dev, handle):
         Ad = upload_any(fmt, A, dev)  # must outlive the call: the descriptor only borrows its arrays
         handle.spmv_generalized(Ad.descriptor(), xd, yd, "identity", 0.0, "plus", "minimum")
         assert np.array_equal(yd.cpu().numpy(), want), fmt
+
+
+def test_csr_row_starts_bit_exact(dev, handle):
+    """the balanced CSR kernel's preprocessing (gpu_compute_row_starts, cusp/system/cuda/ktt/csr_multiply.h:64-85)
+    through b200sp_csr_row_starts against the oracle's restatement of the reference's host version: every entry of the
+    int32 array, ragged and power-law rows, worker counts below / at / above the entry count"""
+    rng = np.random.default_rng(33)
+    for rows, maxlen in ((1, 5), (1000, 9), (40000, 40)):
+        lens = rng.integers(0, maxlen, rows)
+        lens[rng.integers(0, rows, max(1, rows // 7))] = 0
+        if rows > 100:
+            lens[rows // 3] = 200000  # a hub row spanning many chunks
+        lens[0] += 1
+        ro = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+        nnz = int(ro[-1])
+        rod = tdev(ro, dev)
+        for workers in (1, 3, 148 * 32, 148 * 32 * 16, nnz, nnz + 5):
+            out = torch.full((workers,), -7, dtype=torch.int32, device=dev)
+            handle.csr_row_starts(rows, nnz, rod, workers, out)
+            assert np.array_equal(out.cpu().numpy(), O.compute_row_starts(ro, workers)), (rows, workers)
