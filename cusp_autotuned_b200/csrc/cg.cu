@@ -678,15 +678,16 @@ static b200sp_status cg_impl(b200sp_handle h, cudaStream_t st, const b200sp_matr
     s = comm_halo_exchange(h, st, pwin, n, halo_lo, halo_hi, sizeof(T));
     if (s != B200SP_OK) return s;
   }
-  // Programmatic dependent launch between the three kernels of an iteration (B200SP_CG_PDL=0 switches it off):
+  // Programmatic dependent launch between the three kernels of an iteration (opt-in: B200SP_CG_PDL=1):
   // every kernel requests what its predecessor does not write before griddepcontrol.wait, so launch latency and
   // first-batch load latency overlap the predecessor's tail.  The DIA bulk kernel joins in through h->pdl_spmv
   // (its producer lane streams matrix slabs into the ring while the direction kernel is still finishing).
-  // Default: on for the partitioned peer-memory path (kernels of 0.1 ms, poll-gated), off on one GPU, where the
-  // kernels run ~1 ms each and the early-resident successor CTAs cost more than the hidden launch gap (512^3 on one
-  // B200: 3.14 ms / iteration with, 2.95 without — profiles/r03_cg_pdl.md).
+  // Off by default — measured, it loses: 512^3 on one B200 3.14 ms / iteration with PDL against 2.95 without; two GPUs
+  // with 64 planes each (the per-GPU size of the 8-GPU job) 0.428 against 0.420 ms.  The globaltimer trace
+  // (B200SP_CG_TRACE, tools/cg_trace.py, profiles/r03_cg_trace.md) shows why: the K2 -> K3 gap does shrink (5.2 -> 2.3 us)
+  // but the successor's early-resident CTAs slow the predecessor's tail by more than that (K3 body 72 -> 76 us, K1 + 3 us).
   const char *pdl_env = getenv("B200SP_CG_PDL");
-  const bool pdl = pdl_env ? (pdl_env[0] != '0') : (dist && h->p2p_ok && h->world > 1);
+  const bool pdl = pdl_env && pdl_env[0] != '0';
   struct PdlScope {  // the flag must not leak into products outside this solve
     b200sp_handle h;
     ~PdlScope() { h->pdl_spmv = false; }

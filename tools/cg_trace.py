@@ -16,6 +16,8 @@ def main():
     out = {}
     for f in sorted(glob.glob(path + ".*")):
         rank = f.rsplit(".", 1)[1]
+        if not rank.isdigit():
+            continue
         rows = [[int(v) for v in ln.split()] for ln in open(f) if ln.strip() and not ln.startswith("#")]
         a = np.array(rows, dtype=np.int64)
         a = a[(a[:, 1:] > 0).all(axis=1)][skip:]
