@@ -136,7 +136,7 @@ EXPORTED_SYMBOLS = (
      "b200sp_ell_row_lengths", "b200sp_csr_row_starts", "b200sp_spmv", "b200sp_spmv_generalized", "b200sp_spmv_host", "b200sp_cg", "b200sp_krylov", "b200sp_spmv_graph_create", "b200sp_graph_launch",
      "b200sp_graph_destroy",
      "b200sp_comm_unique_id", "b200sp_comm_init", "b200sp_comm_destroy", "b200sp_cg_dist",
-     "b200sp_spmv_dist", "b200sp_spmv_dist_host", "b200sp_spmv_dist_gather", "b200sp_comm_p2p_enabled", "b200sp_comm_timeouts", "b200sp_cfg_space", "b200sp_tune", "b200sp_tune_step",
+     "b200sp_spmv_dist", "b200sp_spmv_dist_host", "b200sp_spmv_dist_gather", "b200sp_comm_p2p_enabled", "b200sp_comm_timeouts", "b200sp_cfg_space", "b200sp_tune", "b200sp_tune_ex", "b200sp_tune_step",
      "b200sp_tune_reset", "b200sp_tune_lookup", "b200sp_tune_save", "b200sp_tune_load",
      "b200sp_poisson_num_entries", "b200sp_poisson_csr_offsets",
      "b200sp_offsets_to_indices", "b200sp_indices_to_offsets", "b200sp_csr_convert_query"]
@@ -503,6 +503,23 @@ class Handle:
         self.check(self.lib.b200sp_tune(self._h, _stream(), C.byref(A), _ptr(x), _ptr(y), _ptr(y_reference),
                                         C.c_double(tol), C.c_int(repeats), results, C.c_int64(n),
                                         C.byref(count), C.byref(best)))
+        return best, list(results)[: count.value]
+
+    def tune_ex(self, A: Matrix, x, y, order=None, stop=None, y_reference=None, tol=0.0, repeats=5):
+        """b200sp_tune_ex: `order` = indices into cfg_space() (the searcher), `stop(result) -> bool` is consulted
+        after every configuration (the stop condition).  Returns (best, results visited)."""
+        n = self.lib.b200sp_cfg_space(A.format, A.dtype, None, 0)
+        visits = len(order) if order is not None else n
+        results = (TuneResult * max(visits, 1))()
+        count = C.c_int64(0)
+        best = Cfg()
+        CB = C.CFUNCTYPE(C.c_int, C.POINTER(TuneResult), C.c_void_p)
+        cb = CB(lambda r, _u: int(bool(stop(r.contents)))) if stop else C.cast(None, CB)
+        arr = (C.c_int64 * max(visits, 1))(*(order if order is not None else []))
+        self.check(self.lib.b200sp_tune_ex(self._h, _stream(), C.byref(A), _ptr(x), _ptr(y), _ptr(y_reference),
+                                           C.c_double(tol), C.c_int(repeats), arr if order is not None else None,
+                                           C.c_int64(len(order) if order is not None else 0), cb, None, results,
+                                           C.c_int64(max(visits, 1)), C.byref(count), C.byref(best)))
         return best, list(results)[: count.value]
 
     def tune_step(self, A: Matrix, x, y) -> TuneResult:

@@ -206,7 +206,8 @@ static b200sp_status tune_events(b200sp_handle h) {
 
 template <typename T>
 static b200sp_status tune_impl(b200sp_handle h, cudaStream_t st, const b200sp_matrix *A, const T *x, T *y,
-                               const T *yref_in, double tol, int repeats, b200sp_tune_result *results,
+                               const T *yref_in, double tol, int repeats, const int64_t *order, int64_t order_len,
+                               b200sp_tune_callback callback, void *user, b200sp_tune_result *results,
                                int64_t capacity, int64_t *num_results, b200sp_cfg *best) {
   if (repeats <= 0) repeats = 5;
   if (tol <= 0) tol = sizeof(T) == 4 ? 1e-5 : 1e-12;
@@ -234,7 +235,14 @@ static b200sp_status tune_impl(b200sp_handle h, cudaStream_t st, const b200sp_ma
   b200sp_cfg best_cfg{};
   bool have = false;
   i64 count = 0;
-  for (const b200sp_cfg &c : space) {
+  // the searcher's order (cuda/ktt/multiply.h:129-133 SetSearcher): a permutation / subset of the space, or the
+  // space's own order; the stop condition is consulted after every configuration (Tune(kernel, stop_condition))
+  const i64 visits = order ? order_len : (i64)space.size();
+  bool stopped = false;
+  for (i64 vi = 0; vi < visits && !stopped; ++vi) {
+    const i64 ci = order ? order[vi] : vi;
+    if (ci < 0 || ci >= (i64)space.size()) continue;
+    const b200sp_cfg &c = space[(size_t)ci];
     b200sp_tune_result r{};
     r.cfg = c;
     char saved[1024];
@@ -273,6 +281,7 @@ static b200sp_status tune_impl(b200sp_handle h, cudaStream_t st, const b200sp_ma
     }
     if (results && count < capacity) results[count] = r;
     ++count;
+    if (callback && callback(&r, user)) stopped = true;
   }
   if (num_results) *num_results = count;
   if (yref) cudaFree(yref);
@@ -281,7 +290,7 @@ static b200sp_status tune_impl(b200sp_handle h, cudaStream_t st, const b200sp_ma
   e.best = best_cfg;
   e.has_best = true;
   e.best_ms = best_ms;
-  e.next_index = (i64)space.size();
+  e.next_index = (i64)space.size();  // dynamic tuning (b200sp_tune_step) starts from the winner of this search
   if (best) *best = best_cfg;
   // leave y = A x computed by the winner
   return spmv_any<T>(h, st, A, x, y, 0, &best_cfg, nullptr, nullptr);
@@ -731,21 +740,31 @@ int64_t b200sp_cfg_space(b200sp_format format, b200sp_dtype dtype, b200sp_cfg *o
   return (int64_t)v.size();
 }
 
+b200sp_status b200sp_tune_ex(b200sp_handle h, b200sp_stream stream, const b200sp_matrix *A, const void *x,
+                             void *y, const void *y_reference, double tol, int repeats, const int64_t *order,
+                             int64_t order_len, b200sp_tune_callback callback, void *user,
+                             b200sp_tune_result *results, int64_t capacity, int64_t *num_results,
+                             b200sp_cfg *best) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, A && x && y, "tune: null argument");
+  B200SP_REQUIRE(h, order_len >= 0 && (order || order_len == 0), "tune: bad search order");
+  if (A->dtype == B200SP_F32)
+    return b200sp::tune_impl<float>(h, (cudaStream_t)stream, A, (const float *)x, (float *)y,
+                                    (const float *)y_reference, tol, repeats, order, order_len, callback, user, results,
+                                    capacity, num_results, best);
+  if (A->dtype == B200SP_F64)
+    return b200sp::tune_impl<double>(h, (cudaStream_t)stream, A, (const double *)x, (double *)y,
+                                     (const double *)y_reference, tol, repeats, order, order_len, callback, user, results,
+                                     capacity, num_results, best);
+  return b200sp::set_error(h, B200SP_INVALID_INPUT, "tune: unknown dtype");
+}
+
 b200sp_status b200sp_tune(b200sp_handle h, b200sp_stream stream, const b200sp_matrix *A, const void *x,
                           void *y, const void *y_reference, double tol, int repeats,
                           b200sp_tune_result *results, int64_t capacity, int64_t *num_results,
                           b200sp_cfg *best) {
-  B200SP_CHECK_HANDLE(h);
-  B200SP_REQUIRE(h, A && x && y, "tune: null argument");
-  if (A->dtype == B200SP_F32)
-    return b200sp::tune_impl<float>(h, (cudaStream_t)stream, A, (const float *)x, (float *)y,
-                                    (const float *)y_reference, tol, repeats, results, capacity,
-                                    num_results, best);
-  if (A->dtype == B200SP_F64)
-    return b200sp::tune_impl<double>(h, (cudaStream_t)stream, A, (const double *)x, (double *)y,
-                                     (const double *)y_reference, tol, repeats, results, capacity,
-                                     num_results, best);
-  return b200sp::set_error(h, B200SP_INVALID_INPUT, "tune: unknown dtype");
+  return b200sp_tune_ex(h, stream, A, x, y, y_reference, tol, repeats, nullptr, 0, nullptr, nullptr, results, capacity,
+                        num_results, best);
 }
 
 b200sp_status b200sp_tune_step(b200sp_handle h, b200sp_stream stream, const b200sp_matrix *A, const void *x,

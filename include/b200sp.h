@@ -530,6 +530,19 @@ b200sp_status b200sp_tune(b200sp_handle h, b200sp_stream stream,
                           const void *y_reference, double tol, int repeats,
                           b200sp_tune_result *results, int64_t capacity,
                           int64_t *num_results, b200sp_cfg *best);
+/* The same search with the two hooks cusp::ktt::tune passes down (cusp/system/cuda/ktt/multiply.h:106-153):
+ *   order / order_len  the searcher: indices into b200sp_cfg_space() in the order to visit them (a permutation for
+ *                      ::ktt::RandomSearcher, a prefix or subset for a budgeted search); NULL = the whole space in
+ *                      its own order (::ktt::DeterministicSearcher)
+ *   callback / user    the stop condition: called after every configuration with its result; a non-zero return
+ *                      ends the search (Tune(kernel, stop_condition)).  The winner among the configurations visited
+ *                      so far is cached and returned like b200sp_tune does. */
+typedef int (*b200sp_tune_callback)(const b200sp_tune_result *result, void *user);
+b200sp_status b200sp_tune_ex(b200sp_handle h, b200sp_stream stream, const b200sp_matrix *A, const void *x,
+                             void *y, const void *y_reference, double tol, int repeats, const int64_t *order,
+                             int64_t order_len, b200sp_tune_callback callback, void *user,
+                             b200sp_tune_result *results, int64_t capacity, int64_t *num_results,
+                             b200sp_cfg *best);
 /* One step of dynamic tuning (cusp::ktt::multiply(A,x,y) / what plain
  * cusp::multiply does for ELL & DIA when ktt is enabled, cuda/ktt/multiply.h:56-77):
  * runs the next untried configuration (timed), or the best one when the space

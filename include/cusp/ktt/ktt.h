@@ -130,7 +130,6 @@ std::vector<::ktt::KernelResult> tune(const Matrix &A, const V1 &x, V2 &y,
                                       std::optional<::ktt::ReferenceComputation> reference_computation = std::nullopt,
                                       std::unique_ptr<::ktt::StopCondition> stop_condition = nullptr,
                                       std::unique_ptr<::ktt::Searcher> searcher = nullptr) {
-  (void)searcher;
   typedef typename V2::value_type T;
   detail::require_device(A, x, y);
   b200sp_matrix d = detail::describe(A);
@@ -144,22 +143,35 @@ std::vector<::ktt::KernelResult> tune(const Matrix &A, const V1 &x, V2 &y,
     y_ref = cusp::array1d<T, cusp::device_memory>(host_ref.begin(), host_ref.end());
     ref_ptr = detail::raw_ptr(y_ref);
   }
+  // the searcher fixes the order of the visit, the stop condition is consulted after every configuration while the
+  // search runs (cuda/ktt/multiply.h:129-146: SetSearcher, Tune(kernel, stop_condition))
+  std::vector<int64_t> order = searcher ? searcher->Order(space) : std::vector<int64_t>();
+  struct Live {
+    ::ktt::StopCondition *stop;
+    std::vector<::ktt::KernelResult> *results;
+    const char *name;
+  };
+  std::vector<::ktt::KernelResult> results;
+  const char *name = cusp::system::cuda::ktt::format_name(d.format);
+  Live live{stop_condition.get(), &results, name};
+  if (stop_condition) stop_condition->Initialize((uint64_t)(searcher ? order.size() : (size_t)space));
+  auto on_result = [](const b200sp_tune_result *r, void *user) -> int {
+    Live *L = static_cast<Live *>(user);
+    // points whose resources (smem ring = stages x K x tile) do not fit this matrix are outside its space, the way KTT
+    // constraints drop configurations before tuning: they are neither reported nor counted
+    if (r->status == B200SP_TUNE_UNSUPPORTED) return 0;
+    L->results->emplace_back(L->name, *r);
+    if (!L->stop) return 0;
+    L->stop->Update(L->results->back());
+    return L->stop->IsFulfilled() ? 1 : 0;
+  };
   int64_t n = 0;
   b200sp_cfg best;
   const double tol = std::is_same<T, float>::value ? 1e-5 : 1e-12;  // north-star parity bound
-  detail::check(b200sp_tune(detail::engine(), detail::current_stream(), &d, detail::raw_ptr(x), detail::raw_ptr(y),
-                            ref_ptr, tol, 3, raw.data(), (int64_t)raw.size(), &n, &best));
-  std::vector<::ktt::KernelResult> results;
-  if (stop_condition) stop_condition->Initialize((uint64_t)n);
-  const char *name = cusp::system::cuda::ktt::format_name(d.format);
-  for (int64_t i = 0; i < n; ++i) {
-    if (stop_condition && stop_condition->IsFulfilled()) break;
-    // points whose resources (smem ring = stages x K x tile) do not fit this matrix are
-    // outside its space, the way KTT constraints drop configurations before tuning
-    if (raw[(size_t)i].status == B200SP_TUNE_UNSUPPORTED) continue;
-    results.emplace_back(name, raw[(size_t)i]);
-    if (stop_condition) stop_condition->Update(results.back());
-  }
+  if (!(stop_condition && stop_condition->IsFulfilled()))
+    detail::check(b200sp_tune_ex(detail::engine(), detail::current_stream(), &d, detail::raw_ptr(x), detail::raw_ptr(y),
+                                 ref_ptr, tol, 3, searcher ? order.data() : nullptr, searcher ? (int64_t)order.size() : 0,
+                                 on_result, &live, raw.data(), (int64_t)raw.size(), &n, &best));
   if (stop_condition) get_tuner().log() << stop_condition->GetStatusString() << std::endl;
   return results;
 }

@@ -146,15 +146,39 @@ class ConfigurationCount : public StopCondition {
   uint64_t target_, seen_;
 };
 
-// The engine's space is small and precompiled (one launch per point, no JIT):
-// every searcher degenerates to the exhaustive order; the type exists so that
-// cusp::ktt::tune(..., std::unique_ptr<Searcher>) keeps its signature.
+// Searchers decide the ORDER in which cusp::ktt::tune visits the space (b200sp_tune_ex takes it as an index list):
+// DeterministicSearcher = the space's own order, RandomSearcher = a uniformly random permutation (optionally seeded).
+// A user searcher overrides Order().
 class Searcher {
  public:
   virtual ~Searcher() = default;
+  virtual std::vector<int64_t> Order(int64_t space_size) const {
+    std::vector<int64_t> o((size_t)space_size);
+    for (int64_t i = 0; i < space_size; ++i) o[(size_t)i] = i;
+    return o;
+  }
 };
 class DeterministicSearcher : public Searcher {};
-class RandomSearcher : public Searcher {};
+class RandomSearcher : public Searcher {
+ public:
+  explicit RandomSearcher(uint64_t seed = 0) : seed_(seed) {}
+  std::vector<int64_t> Order(int64_t space_size) const override {
+    std::vector<int64_t> o = Searcher::Order(space_size);
+    uint64_t s = seed_ ? seed_ : 0x9e3779b97f4a7c15ull;
+    for (int64_t i = space_size - 1; i > 0; --i) {  // Fisher-Yates with splitmix64
+      s += 0x9e3779b97f4a7c15ull;
+      uint64_t z = s;
+      z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+      z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+      z ^= z >> 31;
+      std::swap(o[(size_t)i], o[(size_t)(z % (uint64_t)(i + 1))]);
+    }
+    return o;
+  }
+
+ private:
+  uint64_t seed_;
+};
 
 // stand-in for ::ktt::Tuner: logging controls + configuration factory.  The
 // tuning state itself lives in the engine handle (b200sp_tune_*).

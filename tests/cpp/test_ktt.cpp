@@ -213,3 +213,42 @@ void TestKttDynamicTuning() {
   ASSERT_THROWS(::ktt::KernelConfiguration({{"NO_SUCH_PARAMETER", 1}}), std::runtime_error);
 }
 TEST_DEVICE(TestKttDynamicTuning)
+
+// Searcher and stop condition take effect DURING the search (cuda/ktt/multiply.h:106-153: SetSearcher + Tune(kernel,
+// stop_condition)): a ConfigurationCount(5) budget runs five configurations, a RandomSearcher visits the space in another
+// order than the DeterministicSearcher, and whatever was visited is valid and leaves y = A x.
+void TestKttSearcherAndStopCondition() {
+  cusp::csr_matrix<int, float, cusp::host_memory> Ah;
+  cusp::gallery::poisson5pt(Ah, 64, 48);
+  cusp::csr_matrix<int, float, cusp::device_memory> A(Ah);
+  cusp::array1d<float, cusp::host_memory> xh(A.num_cols), yh(A.num_rows, 0.0f);
+  for (size_t i = 0; i < xh.size(); ++i) xh[i] = (float)((i % 10) + 1);
+  cusp::multiply(Ah, xh, yh);
+  cusp::array1d<float, cusp::device_memory> x(xh), y(A.num_rows, 0.0f);
+  std::ostringstream log;
+  cusp::ktt::get_tuner().SetLoggingTarget(log);
+  auto r5 = cusp::ktt::tune(A, x, y, std::nullopt, std::make_unique<::ktt::ConfigurationCount>(5));
+  ASSERT_EQUAL(r5.size(), (size_t)5);
+  ASSERT_EQUAL(y, yh);
+  cusp::ktt::reset_tuning(A, x, y);
+  auto det = cusp::ktt::tune(A, x, y, std::nullopt, std::make_unique<::ktt::ConfigurationCount>(12),
+                             std::make_unique<::ktt::DeterministicSearcher>());
+  cusp::ktt::reset_tuning(A, x, y);
+  auto rnd = cusp::ktt::tune(A, x, y, std::nullopt, std::make_unique<::ktt::ConfigurationCount>(12),
+                             std::make_unique<::ktt::RandomSearcher>(7));
+  cusp::ktt::get_tuner().SetLoggingTarget(std::cerr);
+  ASSERT_EQUAL(det.size(), (size_t)12);
+  ASSERT_EQUAL(rnd.size(), (size_t)12);
+  for (size_t i = 0; i < 5; ++i)  // the deterministic order is the space's: the first five are the budgeted run's
+    ASSERT_TRUE(det[i].GetConfiguration().GetString() == r5[i].GetConfiguration().GetString());
+  size_t different = 0;
+  for (size_t i = 0; i < 12; ++i) {
+    ASSERT_TRUE(rnd[i].IsValid());
+    if (rnd[i].GetConfiguration().GetString() != det[i].GetConfiguration().GetString()) ++different;
+  }
+  ASSERT_TRUE(different >= 6);
+  ASSERT_EQUAL(y, yh);
+  ASSERT_TRUE(log.str().find("Explored configurations: 12 / 12") != std::string::npos);
+  cusp::ktt::reset_tuning(A, x, y);
+}
+TEST_DEVICE(TestKttSearcherAndStopCondition)

@@ -102,3 +102,30 @@ def test_tuning_cache_save_load_reset(dev, handle, tmp_path):
     assert handle.tune_lookup(Ad.descriptor()).as_dict() == best.as_dict()
     ktt.reset_tuning(Ad)
     assert handle.tune_lookup(Ad.descriptor()) is None
+
+
+def test_searcher_order_and_stop_condition_are_honoured_during_the_search(dev, handle):
+    """b200sp_tune_ex: the searcher's order decides which configurations run and in which order, the stop condition is
+    consulted after every configuration — a budget of 4 runs exactly 4 (cuda/ktt/multiply.h:129-146)"""
+    A = O.poisson(5, (96, 80), np.float64, "csr")
+    Ad = upload("csr", A, dev)
+    d = Ad.descriptor()
+    x = tdev(np.random.default_rng(1).uniform(0.5, 1.5, A["num_cols"]), dev)
+    y = torch.zeros(A["num_rows"], dtype=torch.float64, device=dev)
+    space = capi.Handle.cfg_space(capi.FMT_CSR, capi.F64)
+    key = lambda c: tuple(c.as_dict().values())
+    order = [40, 3, 77, 12, 5, 90]
+    handle.tune_reset(None)
+    best, results = handle.tune_ex(d, x, y, order=order, repeats=2)
+    assert [key(r.cfg) for r in results] == [key(space[i]) for i in order]
+    assert key(best) in {key(space[i]) for i in order}
+    assert handle.tune_lookup(d).as_dict() == best.as_dict()
+    want = O.spmv(A, x.cpu().numpy())
+    assert np.max(np.abs(y.cpu().numpy() - want) / np.abs(want)) <= 1e-12  # y = A x by the winner
+    # stop after 4 configurations of the whole space
+    seen = []
+    handle.tune_reset(None)
+    best, results = handle.tune_ex(d, x, y, stop=lambda r: (seen.append(r.milliseconds), len(seen) >= 4)[1], repeats=2)
+    assert len(results) == 4 and len(seen) == 4
+    assert [key(r.cfg) for r in results] == [key(c) for c in space[:4]]
+    handle.tune_reset(None)
