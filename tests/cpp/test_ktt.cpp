@@ -12,6 +12,7 @@
 #include <cusp/dia_matrix.h>
 #include <cusp/ell_matrix.h>
 #include <cusp/hyb_matrix.h>
+#include <cusp/gallery/poisson.h>
 #include <cusp/ktt/ellr_matrix.h>
 #include <cusp/ktt/ktt.h>
 #include <cusp/ktt/matrix_generation.h>
