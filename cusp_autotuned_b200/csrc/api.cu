@@ -67,14 +67,35 @@ static int ilog2(i64 v) {
   return l;
 }
 
-static b200sp_tune_key make_key(const b200sp_matrix *A) {
+int csr_structure_class(b200sp_handle h, cudaStream_t st, i64 rows, i64 nnz, const int *Ap, const int *Aj);  // spmv_csr.cu
+int coo_structure_class(b200sp_handle h, cudaStream_t st, i64 nnz, const int *Aj, size_t elem);                 // spmv_coo.cu
+
+static b200sp_tune_key make_key(b200sp_handle h, cudaStream_t st, const b200sp_matrix *A) {
   b200sp_tune_key k;
   k.format = (int)A->format;
   k.dtype = (int)A->dtype;
   k.rows_log2 = ilog2(A->num_rows > 0 ? A->num_rows : 1);
   const i64 rows = A->num_rows > 0 ? A->num_rows : 1;
   k.nnz_per_row_log2 = ilog2((stored_entries(A) + rows - 1) / rows);
+  const size_t elem = A->dtype == B200SP_F64 ? 8 : 4;
+  k.structure = 0;  // the probes are cached per array address: one analysis kernel per matrix, then a map lookup
+  if (A->format == B200SP_FMT_CSR)
+    k.structure = csr_structure_class(h, st, A->num_rows, A->num_entries, A->row_offsets, A->column_indices);
+  else if (A->format == B200SP_FMT_COO)
+    k.structure = coo_structure_class(h, st, A->num_entries, A->column_indices, elem);
+  else if (A->format == B200SP_FMT_HYB)
+    k.structure = coo_structure_class(h, st, A->coo_num_entries, A->coo_column_indices, elem);
   return k;
+}
+
+int tune_lookup_on(b200sp_handle h, cudaStream_t st, const b200sp_matrix *A, b200sp_cfg *cfg) {
+  if (!h || !A || h->tune_cache.empty()) return 0;
+  auto it = h->tune_cache.find(make_key(h, st, A));
+  if (it == h->tune_cache.end() || !it->second.has_best) return 0;
+  // during dynamic tuning the cached "best so far" is only used once the space is exhausted
+  if (it->second.next_index < b200sp_cfg_space(A->format, A->dtype, nullptr, 0)) return 0;
+  if (cfg) *cfg = it->second.best;
+  return 1;
 }
 
 // ---- configuration spaces -----------------------------------------------------
@@ -286,7 +307,7 @@ static b200sp_status tune_impl(b200sp_handle h, cudaStream_t st, const b200sp_ma
   if (num_results) *num_results = count;
   if (yref) cudaFree(yref);
   if (!have) return set_error(h, B200SP_CUDA_ERROR, "tune: no configuration produced a valid result");
-  b200sp_tune_entry &e = h->tune_cache[make_key(A)];
+  b200sp_tune_entry &e = h->tune_cache[make_key(h, st, A)];
   e.best = best_cfg;
   e.has_best = true;
   e.best_ms = best_ms;
@@ -300,7 +321,7 @@ template <typename T>
 static b200sp_status tune_step_impl(b200sp_handle h, cudaStream_t st, const b200sp_matrix *A, const T *x,
                                     T *y, b200sp_tune_result *result) {
   std::vector<b200sp_cfg> space = cfg_space_vec(A->format, A->dtype);
-  b200sp_tune_entry &e = h->tune_cache[make_key(A)];
+  b200sp_tune_entry &e = h->tune_cache[make_key(h, st, A)];
   b200sp_status s;
   while (e.next_index < (i64)space.size()) {
     const b200sp_cfg c = space[(size_t)e.next_index++];
@@ -783,18 +804,12 @@ b200sp_status b200sp_tune_reset(b200sp_handle h, const b200sp_matrix *A) {
   if (!A)
     h->tune_cache.clear();
   else
-    h->tune_cache.erase(b200sp::make_key(A));
+    h->tune_cache.erase(b200sp::make_key(h, (cudaStream_t)0, A));
   return B200SP_OK;
 }
 
 int b200sp_tune_lookup(b200sp_handle h, const b200sp_matrix *A, b200sp_cfg *cfg) {
-  if (!h || !A || h->tune_cache.empty()) return 0;
-  auto it = h->tune_cache.find(b200sp::make_key(A));
-  if (it == h->tune_cache.end() || !it->second.has_best) return 0;
-  // during dynamic tuning the cached "best so far" is only used once the space is exhausted
-  if (it->second.next_index < b200sp_cfg_space(A->format, A->dtype, nullptr, 0)) return 0;
-  if (cfg) *cfg = it->second.best;
-  return 1;
+  return b200sp::tune_lookup_on(h, (cudaStream_t)0, A, cfg);
 }
 
 b200sp_status b200sp_tune_save(b200sp_handle h, const char *path) {
@@ -802,13 +817,13 @@ b200sp_status b200sp_tune_save(b200sp_handle h, const char *path) {
   B200SP_REQUIRE(h, path, "tune_save: null path");
   FILE *f = fopen(path, "w");
   if (!f) return b200sp::set_error(h, B200SP_INVALID_INPUT, "tune_save: cannot open %s", path);
-  fprintf(f, "# b200sp tuning cache v1: format dtype rows_log2 nnz_per_row_log2 kernel block tpr unroll vec "
+  fprintf(f, "# b200sp tuning cache v2: format dtype rows_log2 nnz_per_row_log2 structure kernel block tpr unroll vec "
              "tile stages ctas_per_sm ms\n");
   for (auto &kv : h->tune_cache) {
     if (!kv.second.has_best) continue;
     const b200sp_cfg &c = kv.second.best;
-    fprintf(f, "%d %d %d %d %d %d %d %d %d %d %d %d %.6f\n", kv.first.format, kv.first.dtype,
-            kv.first.rows_log2, kv.first.nnz_per_row_log2, c.kernel, c.block_size, c.threads_per_row,
+    fprintf(f, "%d %d %d %d %d %d %d %d %d %d %d %d %d %.6f\n", kv.first.format, kv.first.dtype,
+            kv.first.rows_log2, kv.first.nnz_per_row_log2, kv.first.structure, c.kernel, c.block_size, c.threads_per_row,
             c.unroll, c.vector_width, c.tile_rows, c.stages, c.ctas_per_sm, kv.second.best_ms);
   }
   fclose(f);
@@ -826,9 +841,9 @@ b200sp_status b200sp_tune_load(b200sp_handle h, const char *path) {
     b200sp_tune_key k;
     b200sp_cfg c{};
     float ms = 0.f;
-    if (sscanf(line, "%d %d %d %d %d %d %d %d %d %d %d %d %f", &k.format, &k.dtype, &k.rows_log2,
-               &k.nnz_per_row_log2, &c.kernel, &c.block_size, &c.threads_per_row, &c.unroll,
-               &c.vector_width, &c.tile_rows, &c.stages, &c.ctas_per_sm, &ms) != 13)
+    if (sscanf(line, "%d %d %d %d %d %d %d %d %d %d %d %d %d %f", &k.format, &k.dtype, &k.rows_log2,
+               &k.nnz_per_row_log2, &k.structure, &c.kernel, &c.block_size, &c.threads_per_row, &c.unroll,
+               &c.vector_width, &c.tile_rows, &c.stages, &c.ctas_per_sm, &ms) != 14)
       continue;
     b200sp_tune_entry &e = h->tune_cache[k];
     e.best = c;

@@ -42,6 +42,7 @@ b200sp_status spmv_hyb(b200sp_handle, cudaStream_t, i64, i64, i64, i64, const in
                        const b200sp_cfg *);
 template <typename T, int MODE>
 b200sp_status reduce(b200sp_handle, cudaStream_t, i64, const T *, const T *, T *, T *);
+int tune_lookup_on(b200sp_handle h, cudaStream_t st, const b200sp_matrix *A, b200sp_cfg *cfg);  // api.cu
 template <typename T>
 b200sp_status spmv_dia_xchg(b200sp_handle, cudaStream_t, i64, i64, i64, i64, const int *, const T *, const T *,
                             T *, int, const b200sp_cfg *, const T *, T *, const FusedXchg *, int *);
@@ -56,7 +57,7 @@ b200sp_status spmv_any(b200sp_handle h, cudaStream_t st, const b200sp_matrix *A,
   B200SP_REQUIRE(h, A != nullptr, "spmv: null matrix descriptor");
   const T *vals = reinterpret_cast<const T *>(A->values);
   b200sp_cfg cached;
-  if (!cfg && b200sp_tune_lookup(h, A, &cached)) cfg = &cached;
+  if (!cfg && tune_lookup_on(h, st, A, &cached)) cfg = &cached;
   b200sp_status s;
   switch (A->format) {
     case B200SP_FMT_CSR:
@@ -660,7 +661,7 @@ static b200sp_status cg_impl(b200sp_handle h, cudaStream_t st, const b200sp_matr
   // just before the tiles that read them (visited last)
   b200sp_cfg cached_cfg;
   const b200sp_cfg *use_cfg = cfg;
-  if (!use_cfg && b200sp_tune_lookup(h, A, &cached_cfg)) use_cfg = &cached_cfg;
+  if (!use_cfg && tune_lookup_on(h, st, A, &cached_cfg)) use_cfg = &cached_cfg;
   const bool defer = p2p && A->format == B200SP_FMT_DIA &&
                      dia_can_fuse_xchg(A->num_rows, A->num_cols_per_row, A->pitch, A->values, sizeof(T), use_cfg) &&
                      ((size_t)halo_lo * sizeof(T)) % 128 == 0 && ((size_t)(halo_lo + n) * sizeof(T)) % 128 == 0 &&
@@ -931,7 +932,7 @@ b200sp_status b200sp_spmv_dist(b200sp_handle h, b200sp_stream stream, const b200
   if (A_local->format == B200SP_FMT_DIA && h->world > 1 && h->p2p_ok) {
     b200sp_cfg cached;
     const b200sp_cfg *use = cfg;
-    if (!use && b200sp_tune_lookup(h, A_local, &cached)) use = &cached;
+    if (!use && b200sp::tune_lookup_on(h, (cudaStream_t)stream, A_local, &cached)) use = &cached;
     b200sp::FusedXchg xc;
     if (b200sp::dia_can_fuse_xchg(A_local->num_rows, A_local->num_cols_per_row, A_local->pitch, A_local->values, elem,
                                   use) &&

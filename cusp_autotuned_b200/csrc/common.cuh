@@ -30,11 +30,16 @@ typedef long long i64;
 // ---------------------------------------------------------------------------
 struct b200sp_tune_key {
   int format, dtype, rows_log2, nnz_per_row_log2;
+  // what the defaults already look at when they pick a kernel family: CSR 1 banded / 2 scattered / 3 skewed row
+  // lengths, COO and the COO part of HYB 1 banded / 2 one entry per row / 3 scattered columns, 0 where structure
+  // does not enter (ELL, DIA).  A winner tuned on a banded CSR is not replayed on a random CSR of the same size.
+  int structure;
   bool operator<(const b200sp_tune_key &o) const {
     if (format != o.format) return format < o.format;
     if (dtype != o.dtype) return dtype < o.dtype;
     if (rows_log2 != o.rows_log2) return rows_log2 < o.rows_log2;
-    return nnz_per_row_log2 < o.nnz_per_row_log2;
+    if (nnz_per_row_log2 != o.nnz_per_row_log2) return nnz_per_row_log2 < o.nnz_per_row_log2;
+    return structure < o.structure;
   }
 };
 

@@ -570,6 +570,14 @@ static int coo_gather_class(b200sp_handle h, cudaStream_t st, i64 nnz, const int
   return cls;
 }
 
+// structure class of a COO column stream for the tuning-cache key (api.cu): 1 ring order coalesces (banded),
+// 2 consecutive order coalesces, 3 scattered; 0 for streams too short to probe
+int coo_structure_class(b200sp_handle h, cudaStream_t st, i64 nnz, const int *Aj, size_t elem) {
+  if (!Aj || nnz < (i64)h->num_sms * 8 * 256 * 7) return 0;
+  const int cls = coo_gather_class(h, st, nnz, Aj, elem);
+  return cls == 1 ? 1 : (cls == 2 ? 2 : 3);
+}
+
 static void coo_defaults(b200sp_cfg &c, b200sp_handle h, cudaStream_t st, i64 nnz, const int *Aj, size_t elem,
                          bool tma_ok, bool vec32_ok) {
   const bool no_shape = c.block_size == 0 && c.unroll == 0;

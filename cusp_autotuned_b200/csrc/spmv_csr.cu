@@ -628,6 +628,16 @@ static CsrStructure csr_structure(b200sp_handle h, cudaStream_t st, i64 rows, i6
   return r;
 }
 
+// structure class of a CSR matrix for the tuning-cache key (api.cu): 1 banded, 2 scattered, 3 skewed row lengths
+int csr_structure_class(b200sp_handle h, cudaStream_t st, i64 rows, i64 nnz, const int *Ap, const int *Aj) {
+  if (rows <= 0 || nnz <= 0 || !Ap || !Aj) return 0;
+  const CsrStructure cs = csr_structure(h, st, rows, nnz, Ap, Aj);
+  if (cs.longest_row < 0) return 0;
+  const double mean = (double)nnz / (double)rows;
+  if (cs.longest_row > 2048 && (double)cs.longest_row > 64.0 * (mean > 1.0 ? mean : 1.0)) return 3;
+  return cs.banded ? 1 : 2;
+}
+
 static void csr_defaults(b200sp_cfg &c, i64 rows, i64 nnz, size_t elem, const CsrStructure &cs) {
   const int longest_row = cs.longest_row;
   const double mean = rows > 0 ? (double)nnz / (double)rows : 0.0;

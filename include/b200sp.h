@@ -522,7 +522,10 @@ int64_t b200sp_cfg_space(b200sp_format format, b200sp_dtype dtype, b200sp_cfg *o
  * `repeats` times, validates y against `y_reference` (device, may be NULL ->
  * the engine-default configuration's output is the reference) with
  * |y - y_ref| <= tol*|y_ref| + tol, records results, stores the winner in the
- * handle's tuning cache (key: format, dtype, log2 rows bucket, nnz/row bucket)
+ * handle's tuning cache (key: format, dtype, log2 rows bucket, nnz/row bucket and the
+ * structure class the engine's own defaults distinguish — CSR: banded / scattered /
+ * skewed row lengths, COO and HYB tails: banded / one entry per row / scattered columns —
+ * so a winner is only replayed on matrices of the kind it was found on)
  * and returns it in *best.  y is restored semantics-wise: on return it holds
  * A x computed by the best configuration. */
 b200sp_status b200sp_tune(b200sp_handle h, b200sp_stream stream,

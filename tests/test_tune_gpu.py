@@ -129,3 +129,28 @@ def test_searcher_order_and_stop_condition_are_honoured_during_the_search(dev, h
     assert len(results) == 4 and len(seen) == 4
     assert [key(r.cfg) for r in results] == [key(c) for c in space[:4]]
     handle.tune_reset(None)
+
+
+def test_tuning_cache_distinguishes_structure(dev, handle):
+    """a winner found on a banded CSR is not replayed on a random CSR of the same size class (rows and nnz/row fall in
+    the same log2 buckets): the cache key carries the structure class the defaults use (banded / scattered / skewed)"""
+    rows, k = 1 << 16, 5
+    rng = np.random.default_rng(3)
+    banded_cols = np.clip(np.arange(rows)[:, None] + np.arange(-2, 3)[None, :], 0, rows - 1).astype(np.int32)
+    random_cols = np.sort(rng.integers(0, rows, (rows, k)), axis=1).astype(np.int32)
+    Ap = (np.arange(rows + 1) * k).astype(np.int32)
+    mats = {}
+    for name, cols in (("banded", banded_cols), ("random", random_cols)):
+        A = dict(format="csr", num_rows=rows, num_cols=rows, num_entries=rows * k, row_offsets=Ap,
+                 column_indices=cols.reshape(-1), values=np.ones(rows * k, np.float32))
+        mats[name] = (A, upload("csr", A, dev))
+    x = tdev(rng.integers(-3, 4, rows).astype(np.float32), dev)
+    y = torch.zeros(rows, dtype=torch.float32, device=dev)
+    handle.tune_reset(None)
+    best, _ = handle.tune(mats["banded"][1].descriptor(), x, y, repeats=2)
+    assert handle.tune_lookup(mats["banded"][1].descriptor()).as_dict() == best.as_dict()
+    assert handle.tune_lookup(mats["random"][1].descriptor()) is None
+    for name, (A, Ad) in mats.items():  # products stay exact with and without a cached winner
+        cusp.multiply(Ad, x, y)
+        assert np.array_equal(y.cpu().numpy(), O.spmv(A, x.cpu().numpy())), name
+    handle.tune_reset(None)
