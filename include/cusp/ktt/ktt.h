@@ -6,13 +6,16 @@
 //   get_tuner()                   process-wide ::ktt::Tuner stand-in (logging, CreateConfiguration)
 //   multiply(A, x, y)             one step of dynamic tuning            -> b200sp_tune_step
 //   multiply(A, x, y, conf)       run exactly `conf`                    -> b200sp_spmv(cfg)
-//   tune(A, x, y[, ref, stop, searcher])  offline tuning with validation -> b200sp_tune
-//   reset_tuning(A, x, y)         forget results for A's kernel         -> b200sp_tune_reset
+//   tune(A, x, y[, ref, stop, searcher])  offline tuning with validation -> b200sp_tune_ex; for COO matrices it also
+//                                 inspects the column stream and attaches a hot-column plan when that wins
+//                                 (b200sp_coo_plan_*: tuning is tied to the matrix it ran on, like the reference's)
+//   reset_tuning(A, x, y)         forget results for A's kernel         -> b200sp_tune_reset (+ drop A's plan)
 //
 // Every configuration is a precompiled sm_100a instantiation: a tuning step costs
 // a launch, not an NVRTC compile.  Works for csr / coo / ell / dia / hyb / ellr
 // matrices in device_memory (the reference's KTT glue covers csr, coo, ell, dia, ellr).
 #pragma once
+#include <map>
 #include <memory>
 #include <optional>
 #include <string>
@@ -79,6 +82,75 @@ void require_device(const Matrix &A, const V1 &x, const V2 &y) {
   if (A.num_cols != x.size() || A.num_rows != y.size())
     throw cusp::invalid_input_exception("cusp::ktt: matrix and vector dimensions do not match");
 }
+}  // namespace detail
+
+namespace detail {
+// hot-column plans attached by tune() for COO matrices (and the COO part of HYB), by column-array address
+inline std::map<const void *, b200sp_coo_plan> &coo_plans() {
+  static std::map<const void *, b200sp_coo_plan> plans;
+  return plans;
+}
+inline void drop_coo_plan(const void *column_indices) {
+  auto it = coo_plans().find(column_indices);
+  if (it == coo_plans().end()) return;
+  b200sp_coo_plan_destroy(engine(), it->second);  // detaches too
+  coo_plans().erase(it);
+}
+// Tuning a matrix whose product is gather-bound also inspects its column stream: a plan (b200sp_coo_plan_create) is
+// built, timed against the best configuration just found and attached to the engine when it wins — from then on
+// cusp::multiply on exactly this matrix keeps the hot columns of x in shared memory.  The plan refers to the
+// matrix's index arrays by address: reset_tuning (or tuning again) before changing the sparsity pattern in place.
+template <typename T>
+void try_attach_coo_plan(int64_t rows, int64_t cols, int64_t nnz, const int *Ai, const int *Aj, const T *Ax, const T *x, T *y,
+                         const b200sp_matrix &d) {
+  drop_coo_plan(Aj);
+  if (nnz < (int64_t)1 << 22) return;  // small products are not gather-bound
+  b200sp_coo_plan plan = nullptr;
+  const b200sp_dtype dt = std::is_same<T, float>::value ? B200SP_F32 : B200SP_F64;
+  if (b200sp_coo_plan_create(engine(), current_stream(), rows, cols, nnz, Ai, Aj, dt, 0, &plan) != B200SP_OK || !plan) return;
+  cudaStream_t st = (cudaStream_t)current_stream();
+  cudaEvent_t e0, e1, e2;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventCreate(&e2);
+  const int reps = 3;
+  b200sp_spmv(engine(), current_stream(), &d, x, y, 0, nullptr);  // warm (cached winner)
+  cudaEventRecord(e0, st);
+  for (int k = 0; k < reps; ++k) b200sp_spmv(engine(), current_stream(), &d, x, y, 0, nullptr);
+  cudaEventRecord(e1, st);
+  b200sp_status ps = B200SP_OK;
+  for (int k = 0; k < reps && ps == B200SP_OK; ++k)
+    ps = std::is_same<T, float>::value
+             ? b200sp_spmv_coo_plan_f32(engine(), current_stream(), plan, (const float *)Ax, (const float *)x, (float *)y, 0, nullptr)
+             : b200sp_spmv_coo_plan_f64(engine(), current_stream(), plan, (const double *)Ax, (const double *)x, (double *)y, 0, nullptr);
+  cudaEventRecord(e2, st);
+  cudaEventSynchronize(e2);
+  float ms_plain = 0.f, ms_plan = 0.f;
+  cudaEventElapsedTime(&ms_plain, e0, e1);
+  cudaEventElapsedTime(&ms_plan, e1, e2);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaEventDestroy(e2);
+  if (ps == B200SP_OK && ms_plan < 0.97f * ms_plain && b200sp_coo_plan_attach(engine(), plan) == B200SP_OK) {
+    coo_plans()[Aj] = plan;
+    get_tuner().log() << "coo plan attached: " << ms_plan / reps << " ms against " << ms_plain / reps << " ms" << std::endl;
+  } else {
+    b200sp_coo_plan_destroy(engine(), plan);
+  }
+}
+template <typename Matrix, typename V1, typename V2>
+void after_tune(const Matrix &A, const V1 &x, V2 &y, const b200sp_matrix &d, cusp::coo_format) {
+  try_attach_coo_plan((int64_t)A.num_rows, (int64_t)A.num_cols, (int64_t)A.num_entries, raw_ptr(A.row_indices),
+                      raw_ptr(A.column_indices), raw_ptr(A.values), raw_ptr(x), raw_ptr(y), d);
+}
+template <typename Matrix, typename V1, typename V2, typename Format>
+void after_tune(const Matrix &, const V1 &, V2 &, const b200sp_matrix &, Format) {}
+template <typename Matrix>
+void before_reset(const Matrix &A, cusp::coo_format) {
+  drop_coo_plan(raw_ptr(A.column_indices));
+}
+template <typename Matrix, typename Format>
+void before_reset(const Matrix &, Format) {}
 }  // namespace detail
 
 // one step of dynamic autotuning (cuda/ktt/multiply.h:56-77)
@@ -173,11 +245,13 @@ std::vector<::ktt::KernelResult> tune(const Matrix &A, const V1 &x, V2 &y,
                                  ref_ptr, tol, 3, searcher ? order.data() : nullptr, searcher ? (int64_t)order.size() : 0,
                                  on_result, &live, raw.data(), (int64_t)raw.size(), &n, &best));
   if (stop_condition) get_tuner().log() << stop_condition->GetStatusString() << std::endl;
+  detail::after_tune(A, x, y, d, typename Matrix::format());
   return results;
 }
 
 template <typename MatrixType, typename V1, typename V2>
 void reset_tuning(const MatrixType &A, const V1 &, V2 &) {
+  detail::before_reset(A, typename MatrixType::format());
   b200sp_matrix d = detail::describe(A);
   detail::check(b200sp_tune_reset(detail::engine(), &d));
 }

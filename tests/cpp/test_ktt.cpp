@@ -253,3 +253,57 @@ void TestKttSearcherAndStopCondition() {
   cusp::ktt::reset_tuning(A, x, y);
 }
 TEST_DEVICE(TestKttSearcherAndStopCondition)
+
+// tune() on a COO matrix with scattered, skewed columns also inspects the column stream (hot-column plan): whether or
+// not the plan wins the timing, cusp::multiply stays exact before, with and after it, and reset_tuning drops it.
+void TestKttCooPlanLifecycle() {
+  const int rows = 1 << 18;
+  cusp::coo_matrix<int, float, cusp::host_memory> Ah;
+  {
+    // skewed columns: column = (hash % rows) >> (hash % 9): half of the gathers land in the low column range
+    const size_t per_row = 20;
+    Ah.resize(rows, rows, (size_t)rows * per_row);
+    size_t k = 0;
+    for (int i = 0; i < rows; ++i) {
+      int prev = -1;
+      for (size_t q = 0; q < per_row; ++q) {
+        unsigned long long hsh = ((unsigned long long)i * 1315423911ull + q * 2654435761ull) ^ (q << 17);
+        int c = (int)((hsh % (unsigned long long)rows) >> (hsh % 9));
+        if (c <= prev) c = prev + 1;  // ascending within the row, no duplicates
+        if (c >= rows) break;
+        prev = c;
+        Ah.row_indices[k] = i;
+        Ah.column_indices[k] = c;
+        Ah.values[k] = (float)((int)((hsh >> 7) % 5) - 2);
+        ++k;
+      }
+    }
+    Ah.row_indices.resize(k);
+    Ah.column_indices.resize(k);
+    Ah.values.resize(k);
+    Ah.num_entries = k;
+  }
+  cusp::coo_matrix<int, float, cusp::device_memory> A(Ah);
+  cusp::array1d<float, cusp::host_memory> xh(rows), yh(rows, 0.0f);
+  for (int i = 0; i < rows; ++i) xh[i] = (float)((i % 7) - 3);
+  cusp::multiply(Ah, xh, yh);
+  cusp::array1d<float, cusp::device_memory> x(xh), y(rows, 5.0f);
+  cusp::multiply(A, x, y);
+  ASSERT_EQUAL(y, yh);
+  std::ostringstream log;
+  cusp::ktt::get_tuner().SetLoggingTarget(log);
+  auto results = cusp::ktt::tune(A, x, y, std::nullopt, std::make_unique<::ktt::ConfigurationCount>(6));
+  cusp::ktt::get_tuner().SetLoggingTarget(std::cerr);
+  ASSERT_EQUAL(results.size(), (size_t)6);
+  ASSERT_TRUE(cusp::ktt::detail::coo_plans().size() <= 1);
+  const bool attached = cusp::ktt::detail::coo_plans().size() == 1;
+  ASSERT_TRUE(attached == (log.str().find("coo plan attached") != std::string::npos));
+  y = cusp::array1d<float, cusp::device_memory>(rows, -1.0f);
+  cusp::multiply(A, x, y);  // through the attached plan when it won
+  ASSERT_EQUAL(y, yh);
+  cusp::ktt::reset_tuning(A, x, y);
+  ASSERT_EQUAL(cusp::ktt::detail::coo_plans().size(), (size_t)0);
+  cusp::multiply(A, x, y);
+  ASSERT_EQUAL(y, yh);
+}
+TEST_DEVICE(TestKttCooPlanLifecycle)
