@@ -439,6 +439,7 @@ int amax(cusp::execution_policy<P> &, const Array &x) {
   template <typename P, typename... Args>                                     \
   void name(const cusp::execution_policy<P> &exec, Args &&... args) {         \
     using detail::adl_default::name;                                          \
+    cusp::detail::stream_scope<P> on_stream(cusp::detail::derived_cast(exec)); \
     name(cusp::detail::derived_cast(exec), std::forward<Args>(args)...);      \
   }
 CUSP_B200_POLICY_VOID(axpy)
@@ -454,6 +455,7 @@ CUSP_B200_POLICY_VOID(scal)
   template <typename P, typename... Args>                                                     \
   auto name(const cusp::execution_policy<P> &exec, Args &&... args) {                         \
     using detail::adl_default::name;                                                          \
+    cusp::detail::stream_scope<P> on_stream(cusp::detail::derived_cast(exec));                \
     return name(cusp::detail::derived_cast(exec), std::forward<Args>(args)...);               \
   }
 CUSP_B200_POLICY_VALUE(dot)

@@ -713,6 +713,7 @@ void convert(cusp::execution_policy<P> &, const SourceType &src, DestinationType
 template <typename P, typename SourceType, typename DestinationType>
 void convert(const execution_policy<P> &exec, const SourceType &src, DestinationType &dst) {
   using detail::adl_default::convert;
+  detail::stream_scope<P> on_stream(detail::derived_cast(exec));
   convert(detail::derived_cast(exec), src, dst);
 }
 

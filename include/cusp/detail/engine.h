@@ -63,13 +63,36 @@ struct dtype_of<double> {
 }  // namespace detail
 
 namespace cuda {
-// cusp::cuda::par.on(stream): run subsequent device calls of this thread on `stream`
+// cusp::cuda::par.on(stream) returns a policy VALUE that carries the stream (like the reference's
+// thrust::cuda::par.on): only the call it is passed to runs on that stream — the entry points that take a leading
+// policy install it for the duration of the call (detail::stream_scope) and restore the thread's previous stream.
+struct stream_policy : cusp::execution_policy<stream_policy> {
+  cudaStream_t stream = nullptr;
+};
 struct par_t : cusp::execution_policy<par_t> {
-  const par_t &on(cudaStream_t s) const {
-    cusp::detail::current_stream() = (b200sp_stream)s;
-    return *this;
+  stream_policy on(cudaStream_t s) const {
+    stream_policy p;
+    p.stream = s;
+    return p;
   }
 };
 static const par_t par{};
 }  // namespace cuda
+
+namespace detail {
+template <typename Policy>
+struct stream_scope {
+  explicit stream_scope(const Policy &) {}
+};
+template <>
+struct stream_scope<cusp::cuda::stream_policy> {
+  b200sp_stream saved;
+  explicit stream_scope(const cusp::cuda::stream_policy &p) : saved(current_stream()) {
+    current_stream() = (b200sp_stream)p.stream;
+  }
+  ~stream_scope() { current_stream() = saved; }
+  stream_scope(const stream_scope &) = delete;
+  stream_scope &operator=(const stream_scope &) = delete;
+};
+}  // namespace detail
 }  // namespace cusp

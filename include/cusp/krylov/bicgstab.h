@@ -103,6 +103,7 @@ template <typename P, typename LinearOperator, typename VectorType1, typename Ve
 void bicgstab(const cusp::execution_policy<P> &exec, const LinearOperator &A, VectorType1 &x, const VectorType2 &b,
               Monitor &monitor, Preconditioner &M) {
   using detail::adl_default::bicgstab;
+  cusp::detail::stream_scope<P> on_stream(cusp::detail::derived_cast(exec));
   bicgstab(cusp::detail::derived_cast(exec), A, x, b, monitor, M);
 }
 

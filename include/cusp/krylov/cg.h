@@ -105,6 +105,7 @@ template <typename P, typename LinearOperator, typename VectorType1, typename Ve
 void cg(const cusp::execution_policy<P> &exec, const LinearOperator &A, VectorType1 &x, const VectorType2 &b,
         Monitor &monitor, Preconditioner &M) {
   using detail::adl_default::cg;
+  cusp::detail::stream_scope<P> on_stream(cusp::detail::derived_cast(exec));
   cg(cusp::detail::derived_cast(exec), A, x, b, monitor, M);
 }
 

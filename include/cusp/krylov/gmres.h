@@ -164,6 +164,7 @@ template <typename P, typename LinearOperator, typename VectorType1, typename Ve
 void gmres(const cusp::execution_policy<P> &exec, const LinearOperator &A, VectorType1 &x, const VectorType2 &b,
            const size_t restart, Monitor &monitor, Preconditioner &M) {
   using detail::adl_default::gmres;
+  cusp::detail::stream_scope<P> on_stream(cusp::detail::derived_cast(exec));
   gmres(cusp::detail::derived_cast(exec), A, x, b, restart, monitor, M);
 }
 

@@ -260,6 +260,7 @@ template <typename P, typename LinearOperator, typename MatrixOrVector1, typenam
 void multiply(const execution_policy<P> &exec, const LinearOperator &A, const MatrixOrVector1 &B, MatrixOrVector2 &&C,
               UnaryFunction initialize, BinaryFunction1 combine, BinaryFunction2 reduce) {
   using detail::adl_default::multiply;
+  detail::stream_scope<P> on_stream(detail::derived_cast(exec));
   multiply(detail::derived_cast(exec), A, B, C, initialize, combine, reduce);
 }
 template <typename LinearOperator, typename MatrixOrVector1, typename MatrixOrVector2, typename UnaryFunction,
@@ -310,6 +311,7 @@ void multiply(cusp::execution_policy<P> &, const LinearOperator &A, const Matrix
 template <typename P, typename LinearOperator, typename MatrixOrVector1, typename MatrixOrVector2>
 void multiply(const execution_policy<P> &exec, const LinearOperator &A, const MatrixOrVector1 &B, MatrixOrVector2 &&C) {
   using detail::adl_default::multiply;
+  detail::stream_scope<P> on_stream(detail::derived_cast(exec));
   multiply(detail::derived_cast(exec), A, B, C);
 }
 

@@ -80,9 +80,11 @@ void TestMakeViewsAndStream() {
   cudaStream_t s;
   cudaStreamCreate(&s);
   cusp::multiply(cusp::cuda::par.on(s), A, x, y2);
+  // the policy carries the stream for that one call only: afterwards the thread is back on its own stream
+  ASSERT_TRUE(cusp::detail::current_stream() == nullptr);
   cudaStreamSynchronize(s);
-  cusp::cuda::par.on(0);
   cudaStreamDestroy(s);
+  cusp::multiply(A, x, y2);  // on the default stream again: must not touch the destroyed one
   ASSERT_EQUAL(y, y2);
   cusp::array1d<double, cusp::host_memory> h(y);
   ASSERT_EQUAL(h[0], 2.0);   // corner row: 4 - 1 - 1
