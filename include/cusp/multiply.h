@@ -243,7 +243,9 @@ template <typename P, typename LinearOperator, typename MatrixOrVector1, typenam
           typename BinaryFunction1, typename BinaryFunction2>
 void multiply(cusp::execution_policy<P> &, const LinearOperator &A, const MatrixOrVector1 &B, V2 &C,
               UnaryFunction initialize, BinaryFunction1 combine, BinaryFunction2 reduce) {
-  if constexpr (detail::is_array2d<MatrixOrVector1>::value && std::is_base_of<sparse_format, typename LinearOperator::format>::value) {
+  if constexpr (std::is_base_of<sparse_format, typename MatrixOrVector1::format>::value) {
+    throw cusp::not_implemented_exception("cusp::multiply(A, B, C) with a sparse B (SpGEMM) is not part of the B200 engine");
+  } else if constexpr (detail::is_array2d<MatrixOrVector1>::value && std::is_base_of<sparse_format, typename LinearOperator::format>::value) {
     detail::block_multiply(A, B, C, initialize, combine, reduce);
   } else {
     static_assert(std::is_same<typename LinearOperator::memory_space, typename MatrixOrVector1::memory_space>::value &&
@@ -281,7 +283,10 @@ void multiply3(const LinearOperator &A, const V1 &x, V2 &y, unknown_format) {
 template <typename LinearOperator, typename V1, typename V2>
 void multiply3(const LinearOperator &A, const V1 &x, V2 &y, known_format) {
   typedef typename V2::value_type T;
-  if constexpr (is_array2d<V1>::value && std::is_base_of<sparse_format, typename LinearOperator::format>::value) {
+  if constexpr (std::is_base_of<sparse_format, typename V1::format>::value) {
+    // sparse x sparse (cusp/system/detail/generic/multiply/spgemm.h): outside the SpMV hot path (out of scope)
+    throw cusp::not_implemented_exception("cusp::multiply(A, B, C) with a sparse B (SpGEMM) is not part of the B200 engine");
+  } else if constexpr (is_array2d<V1>::value && std::is_base_of<sparse_format, typename LinearOperator::format>::value) {
     block_multiply(A, x, y, constant_functor<T>(T(0)), multiplies_function<T>(), plus_function<T>());
     return;
   } else {

@@ -223,3 +223,12 @@ void TestDeviceUnsupportedFunctors() {
   ASSERT_EQUAL(yd == yh, true);
 }
 TEST_DEVICE(TestDeviceUnsupportedFunctors)
+
+// sparse x sparse is outside the hot path: a clear exception, not a compile error inside the shape check
+template <class MemorySpace>
+void TestSparseTimesSparseIsRefused() {
+  TestMatrices<float> m;
+  cusp::csr_matrix<int, float, MemorySpace> A(m.A), B(m.A), C;
+  ASSERT_THROWS(cusp::multiply(A, B, C), cusp::not_implemented_exception);
+}
+TEST_HOST_DEVICE(TestSparseTimesSparseIsRefused)
