@@ -143,11 +143,26 @@ void after_tune(const Matrix &A, const V1 &x, V2 &y, const b200sp_matrix &d, cus
   try_attach_coo_plan((int64_t)A.num_rows, (int64_t)A.num_cols, (int64_t)A.num_entries, raw_ptr(A.row_indices),
                       raw_ptr(A.column_indices), raw_ptr(A.values), raw_ptr(x), raw_ptr(y), d);
 }
+// hyb_matrix: the plan goes on the COO tail (spmv_hyb reaches it through the tail's column array); timed on the tail alone
+template <typename Matrix, typename V1, typename V2>
+void after_tune(const Matrix &A, const V1 &x, V2 &y, const b200sp_matrix &, cusp::hyb_format) {
+  if ((int64_t)A.coo.num_entries < ((int64_t)1 << 22)) {
+    drop_coo_plan(raw_ptr(A.coo.column_indices));
+    return;
+  }
+  const b200sp_matrix dc = describe(A.coo);
+  try_attach_coo_plan((int64_t)A.num_rows, (int64_t)A.num_cols, (int64_t)A.coo.num_entries, raw_ptr(A.coo.row_indices),
+                      raw_ptr(A.coo.column_indices), raw_ptr(A.coo.values), raw_ptr(x), raw_ptr(y), dc);
+}
 template <typename Matrix, typename V1, typename V2, typename Format>
 void after_tune(const Matrix &, const V1 &, V2 &, const b200sp_matrix &, Format) {}
 template <typename Matrix>
 void before_reset(const Matrix &A, cusp::coo_format) {
   drop_coo_plan(raw_ptr(A.column_indices));
+}
+template <typename Matrix>
+void before_reset(const Matrix &A, cusp::hyb_format) {
+  drop_coo_plan(raw_ptr(A.coo.column_indices));
 }
 template <typename Matrix, typename Format>
 void before_reset(const Matrix &, Format) {}

@@ -305,5 +305,23 @@ void TestKttCooPlanLifecycle() {
   ASSERT_EQUAL(cusp::ktt::detail::coo_plans().size(), (size_t)0);
   cusp::multiply(A, x, y);
   ASSERT_EQUAL(y, yh);
+  // the same operator as HYB with one ELL column (what the reference's split rule gives power-law graphs): the plan
+  // goes on the COO tail
+  cusp::hyb_matrix<int, float, cusp::host_memory> Hh;
+  cusp::convert(Ah, Hh, (size_t)1);
+  cusp::hyb_matrix<int, float, cusp::device_memory> H(Hh);
+  ASSERT_TRUE(H.coo.num_entries >= ((size_t)1 << 22));
+  y = cusp::array1d<float, cusp::device_memory>(rows, 3.0f);
+  cusp::multiply(H, x, y);
+  ASSERT_EQUAL(y, yh);
+  cusp::ktt::tune(H, x, y, std::nullopt, std::make_unique<::ktt::ConfigurationCount>(4));
+  ASSERT_TRUE(cusp::ktt::detail::coo_plans().size() <= 1);
+  y = cusp::array1d<float, cusp::device_memory>(rows, -2.0f);
+  cusp::multiply(H, x, y);
+  ASSERT_EQUAL(y, yh);
+  cusp::ktt::reset_tuning(H, x, y);
+  ASSERT_EQUAL(cusp::ktt::detail::coo_plans().size(), (size_t)0);
+  cusp::multiply(H, x, y);
+  ASSERT_EQUAL(y, yh);
 }
 TEST_DEVICE(TestKttCooPlanLifecycle)

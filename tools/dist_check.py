@@ -98,20 +98,20 @@ def main():
                     b2 = np.random.default_rng(23).uniform(-1.0, 1.0, n)
                     bl2 = torch.from_numpy(b2[blk.row_begin: blk.row_begin + blk.num_rows]).to(dev)
                     for solver, jac in (("cg", True), ("bicgstab", False), ("bicgstab", True), ("cr", False), ("cr", True)):
-                        xo2, it2, conv2, hist2 = O.krylov(solver, csr_ref, np.zeros(n), b2, 40, 1e-6, dinv=dinv_g if jac else None)
+                        xo2, it2, conv2, hist2 = O.krylov(solver, csr_ref, np.zeros(n), b2, 300, 1e-6, dinv=dinv_g if jac else None)
                         xl2 = torch.zeros(blk.num_rows, dtype=tdt, device=dev)
                         res2, h2 = h.krylov(solver, A.descriptor(), xl2, bl2, diagonal_inverse=dinv_l if jac else None,
-                                            iteration_limit=40, relative_tolerance=1e-6, check_interval=4,
+                                            iteration_limit=300, relative_tolerance=1e-6, check_interval=4,
                                             halo=halo if world > 1 else None)
                         # leading 8 iterations entry by entry (BiCGStab amplifies the regrouped sums' rounding quickly),
                         # the same verdict and count, the same solution to the solve's accuracy
                         per = 2 if solver == "bicgstab" else 1
                         m2 = min(len(h2), len(hist2), 8 * per)
                         bi = solver == "bicgstab"
-                        good = (abs(int(res2.iteration_count) - it2) <= (2 if bi else 1) and bool(res2.converged) == bool(conv2) and
+                        good = (abs(int(res2.iteration_count) - it2) <= (2 + it2 // 20 if bi else 1) and bool(res2.converged) == bool(conv2) and
                                 bool(np.allclose(h2[:m2], hist2[:m2], rtol=1e-8, atol=0)) and
                                 bool(np.abs(xl2.cpu().numpy() - xo2[blk.row_begin: blk.row_begin + blk.num_rows]).max()
-                                     <= (1e-4 if bi else 1e-5) * np.abs(xo2).max()))
+                                     <= 1e-4 * np.abs(xo2).max()))
                         if not good:
                             out.setdefault("krylov_failures", []).append(
                                 [list(grid), solver, jac, int(res2.iteration_count), it2,

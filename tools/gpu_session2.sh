@@ -23,6 +23,8 @@ import json
 d=json.loads(open('$O/${TAG}_cg_pdl$mode.json').read().strip().splitlines()[-1]); print('pdl=$mode', d['cg'], d['parity'])"
         python tools/cg_trace.py $O/${TAG}_trace_pdl$mode > $O/${TAG}_trace_pdl$mode.summary.json; cat $O/${TAG}_trace_pdl$mode.summary.json | head -24
       done ;;
+    bench1)
+      timeout 900 python bench.py > $O/${TAG}_bench1.json 2> $O/${TAG}_bench1.err; echo "bench1 rc=$?"; tail -c 2500 $O/${TAG}_bench1.json ;;
     bench)
       timeout 900 $TR --master-port 29543 bench.py --gpus $N > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; echo "bench rc=$?"; tail -c 1500 $O/${TAG}_bench.json ;;
   esac
