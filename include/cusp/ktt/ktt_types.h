@@ -9,6 +9,7 @@
 // Define CUSP_B200_USE_REAL_KTT to compile against a real <Ktt.h> instead.
 #pragma once
 #ifndef CUSP_B200_USE_REAL_KTT
+#include <chrono>
 #include <cstdint>
 #include <functional>
 #include <iostream>
@@ -144,6 +145,60 @@ class ConfigurationCount : public StopCondition {
 
  private:
   uint64_t target_, seen_;
+};
+
+// explored / total >= fraction
+class ConfigurationFraction : public StopCondition {
+ public:
+  explicit ConfigurationFraction(double fraction) : fraction_(fraction < 0.0 ? 0.0 : (fraction > 1.0 ? 1.0 : fraction)), total_(0), seen_(0) {}
+  bool IsFulfilled() const override { return total_ > 0 && (double)seen_ / (double)total_ >= fraction_; }
+  void Initialize(const uint64_t total) override { total_ = total; seen_ = 0; }
+  void Update(const KernelResult &) override { ++seen_; }
+  std::string GetStatusString() const override {
+    return "Explored configurations: " + std::to_string(seen_) + " / " + std::to_string(total_) + ", target fraction " +
+           std::to_string(fraction_);
+  }
+
+ private:
+  double fraction_;
+  uint64_t total_, seen_;
+};
+
+// a valid configuration whose kernel time is at most `duration` (in milliseconds) has been found
+class ConfigurationDuration : public StopCondition {
+ public:
+  explicit ConfigurationDuration(double duration_ms) : target_ms_(duration_ms), best_ms_(-1.0) {}
+  bool IsFulfilled() const override { return best_ms_ >= 0.0 && best_ms_ <= target_ms_; }
+  void Initialize(const uint64_t) override { best_ms_ = -1.0; }
+  void Update(const KernelResult &r) override {
+    if (!r.IsValid()) return;
+    const double ms = (double)r.GetKernelDuration() * 1e-6;
+    if (best_ms_ < 0.0 || ms < best_ms_) best_ms_ = ms;
+  }
+  std::string GetStatusString() const override {
+    return "Best duration: " + (best_ms_ < 0.0 ? std::string("none") : std::to_string(best_ms_)) + " ms, target " +
+           std::to_string(target_ms_) + " ms";
+  }
+
+ private:
+  double target_ms_, best_ms_;
+};
+
+// wall-clock budget for the whole search, in seconds
+class TuningDuration : public StopCondition {
+ public:
+  explicit TuningDuration(double seconds) : target_s_(seconds), start_(std::chrono::steady_clock::now()) {}
+  bool IsFulfilled() const override { return elapsed() >= target_s_; }
+  void Initialize(const uint64_t) override { start_ = std::chrono::steady_clock::now(); }
+  void Update(const KernelResult &) override {}
+  std::string GetStatusString() const override {
+    return "Tuning time: " + std::to_string(elapsed()) + " / " + std::to_string(target_s_) + " s";
+  }
+
+ private:
+  double elapsed() const { return std::chrono::duration<double>(std::chrono::steady_clock::now() - start_).count(); }
+  double target_s_;
+  std::chrono::steady_clock::time_point start_;
 };
 
 // Searchers decide the ORDER in which cusp::ktt::tune visits the space (b200sp_tune_ex takes it as an index list):

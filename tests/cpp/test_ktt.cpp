@@ -251,8 +251,57 @@ void TestKttSearcherAndStopCondition() {
   ASSERT_EQUAL(y, yh);
   ASSERT_TRUE(log.str().find("Explored configurations: 12 / 12") != std::string::npos);
   cusp::ktt::reset_tuning(A, x, y);
+  // the other KTT stop conditions: a fraction of the space, a time budget that is already spent after the first
+  // configuration, a duration target every valid configuration meets
+  auto all = cusp::ktt::tune(A, x, y);
+  cusp::ktt::reset_tuning(A, x, y);
+  auto quarter = cusp::ktt::tune(A, x, y, std::nullopt, std::make_unique<::ktt::ConfigurationFraction>(0.25));
+  ASSERT_TRUE(quarter.size() >= all.size() / 4 && quarter.size() <= all.size() / 4 + 1);
+  cusp::ktt::reset_tuning(A, x, y);
+  auto timed = cusp::ktt::tune(A, x, y, std::nullopt, std::make_unique<::ktt::TuningDuration>(0.0));
+  ASSERT_EQUAL(timed.size(), (size_t)1);
+  cusp::ktt::reset_tuning(A, x, y);
+  auto fast = cusp::ktt::tune(A, x, y, std::nullopt, std::make_unique<::ktt::ConfigurationDuration>(1000.0));
+  ASSERT_EQUAL(fast.size(), (size_t)1);
+  ASSERT_EQUAL(y, yh);
+  cusp::ktt::reset_tuning(A, x, y);
 }
 TEST_DEVICE(TestKttSearcherAndStopCondition)
+
+// the stop conditions by themselves (host logic)
+void TestKttStopConditionsHost() {
+  b200sp_tune_result ok{};
+  ok.status = B200SP_TUNE_OK;
+  ok.milliseconds = 2.0;
+  b200sp_tune_result bad = ok;
+  bad.status = B200SP_TUNE_VALIDATION_FAILED;
+  bad.milliseconds = 0.1;
+  ::ktt::ConfigurationFraction f(0.5);
+  f.Initialize(4);
+  ASSERT_TRUE(!f.IsFulfilled());
+  f.Update(::ktt::KernelResult("k", ok));
+  ASSERT_TRUE(!f.IsFulfilled());
+  f.Update(::ktt::KernelResult("k", ok));
+  ASSERT_TRUE(f.IsFulfilled());
+  ::ktt::ConfigurationDuration d(1.0);
+  d.Initialize(10);
+  d.Update(::ktt::KernelResult("k", bad));  // invalid results do not count
+  ASSERT_TRUE(!d.IsFulfilled());
+  d.Update(::ktt::KernelResult("k", ok));  // 2 ms > 1 ms
+  ASSERT_TRUE(!d.IsFulfilled());
+  ok.milliseconds = 0.5;
+  d.Update(::ktt::KernelResult("k", ok));
+  ASSERT_TRUE(d.IsFulfilled());
+  ::ktt::TuningDuration t(3600.0);
+  t.Initialize(10);
+  ASSERT_TRUE(!t.IsFulfilled());
+  ::ktt::ConfigurationCount c(3);
+  c.Initialize(2);  // clamped to the size of the space
+  c.Update(::ktt::KernelResult("k", ok));
+  c.Update(::ktt::KernelResult("k", ok));
+  ASSERT_TRUE(c.IsFulfilled());
+}
+TEST_HOST(TestKttStopConditionsHost)
 
 // tune() on a COO matrix with scattered, skewed columns also inspects the column stream (hot-column plan): whether or
 // not the plan wins the timing, cusp::multiply stays exact before, with and after it, and reset_tuning drops it.

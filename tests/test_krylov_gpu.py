@@ -123,7 +123,7 @@ def test_jacobi_preconditioner_pays(dev):
 
 @pytest.mark.parametrize("jacobi", [False, True])
 def test_bicgstab_nonsymmetric_and_early_exit(jacobi, dev):
-    """a non-symmetric operator; and a tolerance that is met by s in mid-iteration (bicgstab.inl:77-81: x += alpha M p,
+    """a non-symmetric operator; and a tolerance that is met by s in mid-iteration (bicgstab.inl:93-97: x += alpha M p,
     break, the iteration is not counted)"""
     A = nonsymmetric((21, 17), np.float64)
     check("bicgstab", A, "csr", np.float64, torch.float64, dev, jacobi, 300, 1e-10, strict=False)
