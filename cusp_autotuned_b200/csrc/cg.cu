@@ -16,6 +16,18 @@
 // reference's monitor would have stopped.  Every element update uses the
 // reference's expression (alpha*p + x, (-alpha)*y + r, z + beta*p with z == r).
 //
+// Opt-in (B200SP_CG_FUSE=1), DIA operators through the bulk kernel: a two-kernel iteration
+//   K1' y = A p  where  p = r + beta p_old  is rebuilt at every gather and stored once per row into the other of two
+//       p buffers, <y,p> fused                                          (matrix + r + p_old + p + y = matrix + 4N)
+//   K2  as above, reading the p that K1' stored                          (6N)
+// i.e. matrix + 10N: the direction update costs no pass of its own, and between GPUs r's edge planes travel instead
+// of p's.  Same expressions, same order: the iterates are bit-identical to the three-kernel form (tests).  Measured on
+// B200 it loses, hence off by default: poisson7pt 512^3 fp64 3.03 ms / iteration against 2.95 (256^3, ncu: K1' 277 us
+// for 1.47 GB of DRAM traffic = 5.3 TB/s, where K1 + K3 take 187 + 53 us for 1.53 GB; the doubled gathers add 40 % to
+// the instruction count of a kernel whose issue slots are half used and whose warps wait on the long scoreboard, and
+// neither more warps (256 x 1: 3.31 ms), a third stage (3.10) nor runs of consecutive tiles per CTA for L1 reuse
+// (3.08 - 3.25) buy it back; profiles/r03_cg_fused_direction.md).
+//
 // Multi-GPU (row-block partition): halo planes of p are exchanged
 // with ncclSend/ncclRecv before K1 and the two scalars are all-reduced with
 // NCCL between the kernels; the scalar step then runs as its own 1-thread kernel.
@@ -47,6 +59,11 @@ template <typename T>
 b200sp_status spmv_dia_xchg(b200sp_handle, cudaStream_t, i64, i64, i64, i64, const int *, const T *, const T *,
                             T *, int, const b200sp_cfg *, const T *, T *, const FusedXchg *, int *);
 bool dia_can_fuse_xchg(i64 rows, i64 ndiag, i64 pitch, const void *vals, size_t elem, const b200sp_cfg *cfg);
+bool dia_can_fuse_direction(i64 rows, i64 ndiag, i64 pitch, const void *vals, size_t elem, const b200sp_cfg *cfg);
+template <typename T>
+b200sp_status spmv_dia_fused_direction(b200sp_handle, cudaStream_t, i64, i64, i64, i64, const int *, const T *, T *,
+                                       const b200sp_cfg *, const T *, const T *, T *, const T *, const int *, int, i64, i64,
+                                       i64, T *, const FusedXchg *);
 
 // y = A x (+ optional fused <y, dotv>).  Formats whose kernel has no fused
 // epilogue (COO / HYB) get a separate deterministic dot kernel.
@@ -531,6 +548,118 @@ __global__ void __launch_bounds__(CG_BLOCK) cg_direction_p2p_kernel(i64 n, const
   }
 }
 
+// Two-kernel iteration on the peer-memory path (K1' = dia_bulk_kernel<..., FUSED>): the update kernel also carries
+// what the direction kernel did between GPUs.  The threads that own the first / last plane store the new r straight
+// into the neighbour's r window (K1' rebuilds the halo rows of p from it: p never travels); the CTA that finishes the
+// local <r,r> publishes it to every rank, raises the neighbours' halo flags, waits for the other ranks' parts (they
+// finish within the skew of the ranks), and does the scalar + monitor step, so the next K1' reads beta and the stop
+// flag from S like on one GPU.
+template <typename T>
+__global__ void __launch_bounds__(CG_BLOCK) cg_update_push_p2p_kernel(i64 n, const T *p, const T *y, T *x, T *r,
+                                                                      CgState<T> *S, T *partials, unsigned int *ticket,
+                                                                      double *residuals, P2PView c, unsigned tag,
+                                                                      unsigned long long epoch, i64 halo_lo, i64 halo_hi,
+                                                                      T *dst_lo, T *dst_hi, unsigned long long *trace) {
+  __shared__ T s_red[32];
+  __shared__ T s_yp;
+  __shared__ double s_pub;
+  __shared__ int s_fin;
+  if (S->done) return;
+  if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[TR_K2_ENTER] = global_timer_ns();
+  const i64 stride = (i64)gridDim.x * CG_BLOCK;
+  i64 i = (i64)blockIdx.x * CG_BLOCK + threadIdx.x;
+  T pv[CG_UNROLL], yv[CG_UNROLL], xv[CG_UNROLL], rv[CG_UNROLL];
+  const bool first = i + (CG_UNROLL - 1) * stride < n;
+  if (threadIdx.x == 0) s_fin = 0;
+  if (blockIdx.x == 0 && threadIdx.x < c.world) p2p_publish(c, 0, (double)S->yp, tag, threadIdx.x);
+  if (first) {  // the first batch is on its way while the slots are polled
+#pragma unroll
+    for (int u = 0; u < CG_UNROLL; ++u) {
+      pv[u] = p[i + u * stride];
+      xv[u] = x[i + u * stride];
+      rv[u] = r[i + u * stride];
+      yv[u] = y[i + u * stride];
+    }
+  }
+  if (threadIdx.x < 32) {
+    const T t = p2p_sum_warp<T>(c, 0, tag);
+    if (threadIdx.x == 0) s_yp = t;
+  }
+  __syncthreads();
+  if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[TR_K2_POLLED] = global_timer_ns();
+  const T alpha = S->rz / s_yp;
+  const T nalpha = -alpha;
+  const i64 hi_begin = n - halo_hi;
+  T acc = T(0);
+  bool remote = false;
+  auto store_r = [&](i64 j, T rn) {
+    r[j] = rn;
+    if (dst_lo && j < halo_lo) {  // rank-1's upper halo, straight over NVLink
+      dst_lo[j] = rn;
+      remote = true;
+    }
+    if (dst_hi && j >= hi_begin) {  // rank+1's lower halo
+      dst_hi[j - hi_begin] = rn;
+      remote = true;
+    }
+  };
+  for (bool pre = first; i + (CG_UNROLL - 1) * stride < n; i += CG_UNROLL * stride, pre = false) {
+    if (!pre) {
+#pragma unroll
+      for (int u = 0; u < CG_UNROLL; ++u) {
+        pv[u] = p[i + u * stride];
+        yv[u] = y[i + u * stride];
+        xv[u] = x[i + u * stride];
+        rv[u] = r[i + u * stride];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < CG_UNROLL; ++u) {
+      x[i + u * stride] = alpha * pv[u] + xv[u];
+      const T rn = nalpha * yv[u] + rv[u];
+      store_r(i + u * stride, rn);
+      acc = acc + rn * rn;
+    }
+  }
+  for (; i < n; i += stride) {
+    x[i] = alpha * p[i] + x[i];
+    const T rn = nalpha * y[i] + r[i];
+    store_r(i, rn);
+    acc = acc + rn * rn;
+  }
+  if (remote) __threadfence_system();  // only the threads that stored into peer memory pay for it
+  T bs = block_sum<CG_BLOCK>(acc, s_red);
+  grid_reduce_finish<CG_BLOCK>(bs, partials, ticket, s_red, [&](T total) {
+    S->rz_new = total;  // local part
+    s_pub = (double)total;
+    s_fin = 1;
+  });
+  __syncthreads();
+  if (!s_fin) return;
+  // the CTA that took the last ticket: every CTA's stores (local and peer) are ordered before its ticket
+  if (threadIdx.x < c.world) p2p_publish(c, 1, s_pub, tag, threadIdx.x);  // one lane per peer
+  if (threadIdx.x == 0) {  // the thread that saw the last ticket
+    __threadfence_system();
+    if (dst_lo) st_release_sys(&c.peer[c.rank - 1]->halo_flag[1], epoch);  // I am its rank+1
+    if (dst_hi) st_release_sys(&c.peer[c.rank + 1]->halo_flag[0], epoch);  // I am its rank-1
+  }
+  if (threadIdx.x < 32) {
+    __syncwarp();
+    const T rz_new = p2p_sum_warp<T>(c, 1, tag);
+    if (threadIdx.x == 0) {
+      S->beta = rz_new / S->rz;
+      S->rz = rz_new;
+      S->iter += 1;
+      monitor_step(S, residuals);
+      __threadfence();
+      if (trace) {
+        const unsigned long long t = global_timer_ns();
+        trace[TR_K2_END] = trace[TR_K3_ENTER] = trace[TR_K3_POLLED] = trace[TR_K3_END] = t;
+      }
+    }
+  }
+}
+
 template <typename T>
 __global__ void cg_setup_state_kernel(CgState<T> *S, const T *bnorm, double rel, double abs_tol, int limit) {
   S->bnorm = *bnorm;
@@ -567,8 +696,22 @@ static b200sp_status cg_impl(b200sp_handle h, cudaStream_t st, const b200sp_matr
   if (prm.check_interval <= 0) prm.check_interval = 16;
   B200SP_REQUIRE(h, prm.iteration_limit >= 0 && prm.iteration_limit < (1ll << 30), "cg: bad iteration limit");
 
-  // workspace: y, r (n each) and the p window (halo_lo + n + halo_hi)
-  const size_t need = ((size_t)3 * n + halo_lo + halo_hi) * sizeof(T) + 256;
+  // the two-kernel iteration (direction update folded into the product): DIA through the bulk kernel, on one GPU or on
+  // the peer-memory path with line-aligned halos
+  b200sp_cfg cached_cfg;
+  const b200sp_cfg *use_cfg = cfg;
+  if (!use_cfg && tune_lookup_on(h, st, A, &cached_cfg)) use_cfg = &cached_cfg;
+  const char *fuse_env = getenv("B200SP_CG_FUSE");
+  const bool p2p = dist && h->p2p_ok && h->world > 1;
+  const bool halo_lines = ((size_t)halo_lo * sizeof(T)) % 128 == 0 && ((size_t)(halo_lo + n) * sizeof(T)) % 128 == 0;
+  const bool fuse_dir = fuse_env && fuse_env[0] == '1' && n > 0 && A->format == B200SP_FMT_DIA &&
+                        dia_can_fuse_direction(A->num_rows, A->num_cols_per_row, A->pitch, A->values, sizeof(T), use_cfg) &&
+                        (!dist || (p2p && halo_lines));
+  // workspace: y (n) | r window | p window [| second p window], windows = halo_lo + n + halo_hi, each 128-byte aligned
+  const size_t win = (size_t)(halo_lo + n + halo_hi);
+  auto lines = [](size_t elems) { return (elems * sizeof(T) + 127) / 128 * 128; };
+  const size_t off_r = lines((size_t)n), off_p0 = off_r + lines(win), off_p1 = off_p0 + lines(win);
+  const size_t need = off_p1 + (fuse_dir ? lines(win) : 0) + 256;
   if (h->cg_ws_bytes < need) {
     if (h->cg_ws) cudaFree(h->cg_ws);
     h->cg_ws = nullptr;
@@ -590,10 +733,13 @@ static b200sp_status cg_impl(b200sp_handle h, cudaStream_t st, const b200sp_matr
     }
     h->cg_residuals_cap = nres_cap;
   }
-  T *y = reinterpret_cast<T *>(h->cg_ws);
-  T *r = y + n;
-  T *pwin = r + n;       // [halo_lo | n | halo_hi]
+  char *ws = reinterpret_cast<char *>(h->cg_ws);
+  T *y = reinterpret_cast<T *>(ws);
+  T *rwin = reinterpret_cast<T *>(ws + off_r);  // [halo_lo | n | halo_hi]; the halos are used by the two-kernel iteration only
+  T *r = rwin + halo_lo;
+  T *pwin = reinterpret_cast<T *>(ws + off_p0);  // [halo_lo | n | halo_hi]
   T *p = pwin + halo_lo;
+  T *pwin_b = reinterpret_cast<T *>(ws + off_p1);  // second p window (two-kernel iteration)
   CgState<T> *S = reinterpret_cast<CgState<T> *>(h->dev_scalars);
   T *bn = reinterpret_cast<T *>(h->dev_scalars + 32);
   T *partials = reinterpret_cast<T *>(h->red_partials);
@@ -653,22 +799,19 @@ static b200sp_status cg_impl(b200sp_handle h, cudaStream_t st, const b200sp_matr
 
   // NVLink peer-memory path: map the neighbours' p windows, agree on a solve id, and
   // exchange the halos of p_0 once with NCCL; from then on the iteration is NCCL-free.
-  const bool p2p = dist && h->p2p_ok && h->world > 1;
   P2PView view;
   T *dst_lo = nullptr, *dst_hi = nullptr;
   unsigned long long solve = 0, kiter = 0;
   // DIA through the bulk kernel: K3 does not wait for the neighbours' planes; the next K1 does,
   // just before the tiles that read them (visited last)
-  b200sp_cfg cached_cfg;
-  const b200sp_cfg *use_cfg = cfg;
-  if (!use_cfg && tune_lookup_on(h, st, A, &cached_cfg)) use_cfg = &cached_cfg;
   const bool defer = p2p && A->format == B200SP_FMT_DIA &&
                      dia_can_fuse_xchg(A->num_rows, A->num_cols_per_row, A->pitch, A->values, sizeof(T), use_cfg) &&
-                     ((size_t)halo_lo * sizeof(T)) % 128 == 0 && ((size_t)(halo_lo + n) * sizeof(T)) % 128 == 0 &&
-                     (reinterpret_cast<uintptr_t>(pwin) & 127) == 0;
+                     halo_lines && (reinterpret_cast<uintptr_t>(pwin) & 127) == 0;
   if (p2p) {
     void *dl = nullptr, *dh = nullptr;
-    s = comm_p2p_map_windows(h, st, h->cg_ws, (size_t)((char *)pwin - (char *)h->cg_ws), n, halo_lo, halo_hi,
+    // the window the neighbours store into: p (three-kernel form) or r (two-kernel form)
+    T *xwin = fuse_dir ? rwin : pwin;
+    s = comm_p2p_map_windows(h, st, h->cg_ws, (size_t)((char *)xwin - (char *)h->cg_ws), n, halo_lo, halo_hi,
                              sizeof(T), &dl, &dh);
     if (s != B200SP_OK) return s;
     dst_lo = reinterpret_cast<T *>(dl);
@@ -676,7 +819,7 @@ static b200sp_status cg_impl(b200sp_handle h, cudaStream_t st, const b200sp_matr
     s = comm_next_solve_id(h, st, &solve);
     if (s != B200SP_OK) return s;
     view = comm_p2p_view(h);
-    s = comm_halo_exchange(h, st, pwin, n, halo_lo, halo_hi, sizeof(T));
+    s = comm_halo_exchange(h, st, fuse_dir ? rwin : pwin, n, halo_lo, halo_hi, sizeof(T));  // halos of p_0 = r_0
     if (s != B200SP_OK) return s;
   }
   // Programmatic dependent launch between the three kernels of an iteration (opt-in: B200SP_CG_PDL=1):
@@ -713,8 +856,22 @@ static b200sp_status cg_impl(b200sp_handle h, cudaStream_t st, const b200sp_matr
   // once in a CUDA graph and replayed (B200SP_CG_GRAPH=0 / 1 overrides the size rule).  Capture happens on a stream
   // of the handle (the caller's may be the legacy default stream, which cannot be captured), ordered behind and
   // before the caller's stream with events.
+  // two-kernel iteration: which p window holds the direction of the previous iteration
+  int pcur = 0;       // K1' reads pwins[pcur] as p_old and stores p into pwins[pcur ^ 1]
+  int first_dir = 1;  // first iteration: p = r
+  T *pwins[2] = {pwin, pwin_b};
+  auto fused_product = [&](cudaStream_t fst, const FusedXchg *xw) -> b200sp_status {
+    b200sp_status fs = spmv_dia_fused_direction<T>(h, fst, A->num_rows, A->num_cols, A->num_cols_per_row, A->pitch,
+                                                   A->diagonal_offsets, reinterpret_cast<const T *>(A->values), y, use_cfg, rwin,
+                                                   pwins[pcur], pwins[pcur ^ 1], &S->beta, &S->done, first_dir, halo_lo, halo_lo,
+                                                   halo_hi, &S->yp, xw);
+    pcur ^= 1;  // pwins[pcur] now holds the current direction
+    first_dir = 0;
+    return fs;
+  };
   const char *graph_env = getenv("B200SP_CG_GRAPH");
   bool use_graph = !dist && (graph_env ? graph_env[0] != '0' : n <= ((i64)1 << 22));
+  int graph_iters = prm.check_interval;
   cudaGraphExec_t graph_exec = nullptr;
   cudaStream_t run_st = st;
   if (use_graph) {
@@ -734,7 +891,23 @@ static b200sp_status cg_impl(b200sp_handle h, cudaStream_t st, const b200sp_matr
     bool ok = cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
     if (ok) {
       const uint64_t launches_before = h->launches;
-      for (int k = 0; k < prm.check_interval && ok; ++k) {
+      if (fuse_dir) {
+        // the first iteration (p = r) runs outside the graph; the graph holds an even number of iterations so that
+        // every replay starts with the two p windows in the same roles
+        const int pairs = (prm.check_interval + 1) / 2;
+        graph_iters = 2 * pairs;
+        first_dir = 0;
+        pcur = 1;  // after the uncaptured first iteration the direction lives in pwins[1]
+        for (int k = 0; k < graph_iters && ok; ++k) {
+          ok = fused_product(gs, nullptr) == B200SP_OK;
+          ok = ok && launch_kernel_pdl(cg_update_kernel<T, false>, dim3((unsigned)g), dim3(CG_BLOCK), 0, gs, false, n,
+                                       (const T *)(pwins[pcur] + halo_lo), (const T *)y, x, r, S, partials, ticket,
+                                       res) == cudaSuccess;
+        }
+        first_dir = 1;
+        pcur = 0;
+      }
+      for (int k = 0; !fuse_dir && k < prm.check_interval && ok; ++k) {
         ok = spmv_any<T>(h, gs, A, p, y, 0, cfg, p, &S->yp) == B200SP_OK;
         ok = ok && launch_kernel_pdl(cg_update_kernel<T, false>, dim3((unsigned)g), dim3(CG_BLOCK), 0, gs, pdl, n, (const T *)p,
                                      (const T *)y, x, r, S, partials, ticket, res) == cudaSuccess;
@@ -768,14 +941,45 @@ static b200sp_status cg_impl(b200sp_handle h, cudaStream_t st, const b200sp_matr
     B200SP_CUDA(h, cudaStreamSynchronize(ps));
     return B200SP_OK;
   };
+  if (use_graph && fuse_dir && !hs->done) {  // the uncaptured first iteration of the two-kernel form
+    s = fused_product(run_st, nullptr);
+    if (s != B200SP_OK) return s;
+    B200SP_CUDA(h, launch_kernel_pdl(cg_update_kernel<T, false>, dim3((unsigned)g), dim3(CG_BLOCK), 0, run_st, false, n,
+                                     (const T *)(pwins[pcur] + halo_lo), (const T *)y, x, r, S, partials, ticket, res));
+    h->launches++;
+  }
   while (use_graph && !hs->done) {
     B200SP_CUDA(h, cudaGraphLaunch(graph_exec, run_st));
-    h->launches += 3 * (uint64_t)prm.check_interval;
+    h->launches += (fuse_dir ? 2 : 3) * (uint64_t)graph_iters;
     s = poll_on(run_st);
     if (s != B200SP_OK) return s;
   }
   while (!hs->done) {
     for (int k = 0; k < prm.check_interval; ++k) {
+      if (p2p && fuse_dir) {
+        const unsigned long long prev_epoch = (solve << 32) | kiter;
+        const unsigned long long epoch = (solve << 32) | (++kiter);
+        const unsigned tag = (unsigned)((solve << 20) + kiter);
+        FusedXchg xw;
+        memset(&xw, 0, sizeof(xw));
+        if (kiter > 1) {  // K1' waits for the planes of r that the neighbours' previous update kernel stored here
+          xw.enabled = 2;
+          xw.mine = view.mine;
+          xw.lo_bytes = dst_lo ? (size_t)halo_lo * sizeof(T) : 0;
+          xw.hi_bytes = dst_hi ? (size_t)halo_hi * sizeof(T) : 0;
+          xw.wait_lo = &view.mine->halo_flag[0];
+          xw.wait_hi = &view.mine->halo_flag[1];
+          xw.wait_epoch = prev_epoch;
+        }
+        s = fused_product(st, kiter > 1 ? &xw : nullptr);
+        if (s != B200SP_OK) return s;
+        unsigned long long *tr = (trace && kiter < (unsigned long long)prm.iteration_limit + 2) ? trace + kiter * TR_SLOTS : nullptr;
+        B200SP_CUDA(h, launch_kernel_pdl(cg_update_push_p2p_kernel<T>, dim3((unsigned)g), dim3(CG_BLOCK), 0, st, false, n,
+                                         (const T *)(pwins[pcur] + halo_lo), (const T *)y, x, r, S, partials, ticket, res, view,
+                                         tag, epoch, halo_lo, halo_hi, dst_lo, dst_hi, tr));
+        h->launches++;
+        continue;
+      }
       if (p2p) {
         const unsigned long long prev_epoch = (solve << 32) | kiter;
         const unsigned long long epoch = (solve << 32) | (++kiter);
@@ -822,6 +1026,13 @@ static b200sp_status cg_impl(b200sp_handle h, cudaStream_t st, const b200sp_matr
         if (s != B200SP_OK) return s;
         cg_scalar_step_kernel<T><<<1, 1, 0, st>>>(S, res, 0);
         B200SP_LAUNCH_CHECK(h, "cg_scalar_step_kernel");
+      } else if (fuse_dir) {
+        s = fused_product(st, nullptr);
+        if (s != B200SP_OK) return s;
+        B200SP_CUDA(h, launch_kernel_pdl(cg_update_kernel<T, false>, dim3((unsigned)g), dim3(CG_BLOCK), 0, st, false, n,
+                                         (const T *)(pwins[pcur] + halo_lo), (const T *)y, x, r, S, partials, ticket, res));
+        h->launches++;
+        continue;
       } else {
         s = spmv_any<T>(h, st, A, p, y, 0, cfg, p, &S->yp);
         if (s != B200SP_OK) return s;

@@ -50,6 +50,21 @@ struct DiaArgs {
   i64 row_begin;  // first row handled by this launch (remainder launches)
   DiaXchg xc;
   int pdl;  // launched with programmatic stream serialization: wait before the first read of x / y / dotv
+  // CG with the direction update folded into the product (dia_bulk_kernel<..., FUSED = true>, cg.cu): the operand is
+  // not read from x but rebuilt where it is gathered,  p[j] = fr[j] + beta * fp[j]  (p = z + beta p, z == r,
+  // cusp/krylov/detail/cg.inl:97-99), and the owner of row i also stores p[i + fshift] into fpn.  All three are
+  // windows [fhalo_lo | rows | fhalo_hi] in the operator's column coordinates; the halo rows of fpn are rebuilt
+  // locally from the halo rows of fr / fp, so p itself never travels between GPUs.
+  const T *fr, *fp;
+  T *fpn;
+  const T *fbeta;    // device scalar
+  const int *fdone;  // device flag: the solve is over, do nothing
+  int ffirst;        // first iteration: p = r
+  i64 fshift, fhalo_lo, fhalo_hi;
+  // tiles are handed to the persistent CTAs in runs of `run` consecutive tiles (CTA b: tiles [b*run, (b+1)*run), then
+  // gridDim.x * run further on): the x lines a tile gathers at row +- R, 2R, ... are the ones its neighbours in the run
+  // gather at offset 0, so they are L1 hits instead of another trip to L2
+  int run;
 };
 
 constexpr int DIA_DU = 8;            // diagonals in flight per thread
@@ -213,10 +228,11 @@ __device__ __forceinline__ void dia_xchg_aux(const DiaXchg &xc, int lane) {
   }
 }
 
-template <typename T, int BLOCK, int RPT>
+template <typename T, int BLOCK, int RPT, bool FUSED = false>
 __global__ void __launch_bounds__(BLOCK + 32) dia_bulk_kernel(DiaArgs<T> a, int stages,
                                                               i64 num_tiles) {
   constexpr int R = BLOCK * RPT;
+  if (FUSED && *a.fdone) return;  // uniform: the monitor has stopped the solve
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // layout: [stages][KC][R] T | full[stages] | empty[stages] | offs[ndiag]
   T *s_vals = reinterpret_cast<T *>(smem_raw);
@@ -239,6 +255,14 @@ __global__ void __launch_bounds__(BLOCK + 32) dia_bulk_kernel(DiaArgs<T> a, int 
   const int nchunks = (a.ndiag + DIA_KC - 1) / DIA_KC;
   const unsigned rows = (unsigned)a.rows, cols = (unsigned)a.cols;
   T dsum = 0;
+  // FUSED: the operand element at window index j (first iteration: beta = 0 and fp = fr, so p = r without a branch)
+  const T fbeta = FUSED ? *a.fbeta : T(0);
+  auto operand = [&](unsigned j) -> T {
+    if (!FUSED) return ld_ro(a.x + j);
+    const T rv = ld_ro(a.fr + j);
+    const T pv = ld_ro(a.fp + j);
+    return T(1) * rv + fbeta * pv;
+  };
 
   if (tid >= BLOCK) {
     // ===== producer warp: one elected lane drives the TMA engine =====
@@ -246,7 +270,8 @@ __global__ void __launch_bounds__(BLOCK + 32) dia_bulk_kernel(DiaArgs<T> a, int 
       const uint64_t pol = l2_policy_evict_first();
       int s = 0;
       uint32_t ph = 0;
-      for (i64 seq = blockIdx.x; seq < num_tiles; seq += gridDim.x) {
+      for (i64 base = (i64)blockIdx.x * a.run; base < num_tiles; base += (i64)gridDim.x * a.run)
+      for (i64 seq = base; seq < base + a.run && seq < num_tiles; ++seq) {
         i64 tile = seq + a.xc.rot;
         if (tile >= num_tiles) tile -= num_tiles;
         const i64 r0 = a.row_begin + tile * R;
@@ -281,7 +306,8 @@ __global__ void __launch_bounds__(BLOCK + 32) dia_bulk_kernel(DiaArgs<T> a, int 
     uint32_t ph = 0;
     const int lane = tid & 31;
     bool ready_lo = !a.xc.enabled, ready_hi = !a.xc.enabled;
-    for (i64 seq = blockIdx.x; seq < num_tiles; seq += gridDim.x) {
+    for (i64 base = (i64)blockIdx.x * a.run; base < num_tiles; base += (i64)gridDim.x * a.run)
+    for (i64 seq = base; seq < base + a.run && seq < num_tiles; ++seq) {
       i64 tile = seq + a.xc.rot;
       if (tile >= num_tiles) tile -= num_tiles;
       // first tile of this warp that reads halo columns: the planes must have landed
@@ -303,6 +329,24 @@ __global__ void __launch_bounds__(BLOCK + 32) dia_bulk_kernel(DiaArgs<T> a, int 
         __syncwarp();
         ready_hi = true;
       }
+      if (FUSED) {
+        // the halo rows of the new direction, rebuilt from the neighbours' r planes (which the waits above have seen
+        // arrive) by the tiles that sit next to them
+        if (tile < a.xc.lo_tiles) {
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            const i64 q = tile * R + tid + i * BLOCK;
+            if (q < a.fhalo_lo) a.fpn[q] = operand((unsigned)q);
+          }
+        }
+        if (tile >= a.xc.hi_tile_begin) {
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            const i64 q = (tile - a.xc.hi_tile_begin) * R + tid + i * BLOCK;
+            if (q < a.fhalo_hi) a.fpn[a.fshift + a.rows + q] = operand((unsigned)(a.fshift + a.rows + q));
+          }
+        }
+      }
       const unsigned r0 = (unsigned)(a.row_begin + tile * R);
       T acc[RPT];
       if ((i64)r0 + R > a.rows) {
@@ -315,10 +359,16 @@ __global__ void __launch_bounds__(BLOCK + 32) dia_bulk_kernel(DiaArgs<T> a, int 
           for (int d = 0; d < a.ndiag; ++d) {
             const unsigned cidx = r + (unsigned)s_off[d];
             if (cidx < cols)
-              s_acc = s_acc + ld_stream(a.vals + (i64)d * a.pitch + r) * ld_ro(a.x + cidx);
+              s_acc = s_acc + ld_stream(a.vals + (i64)d * a.pitch + r) * operand(cidx);
           }
           a.y[r] = s_acc;
-          if (a.dotv) dsum = dsum + s_acc * ld_ro(a.dotv + r);
+          if (FUSED) {
+            const T pn = operand(r + (unsigned)a.fshift);
+            a.fpn[r + a.fshift] = pn;
+            dsum = dsum + s_acc * pn;
+          } else if (a.dotv) {
+            dsum = dsum + s_acc * ld_ro(a.dotv + r);
+          }
         }
         continue;
       }
@@ -335,7 +385,7 @@ __global__ void __launch_bounds__(BLOCK + 32) dia_bulk_kernel(DiaArgs<T> a, int 
           off[u] = (unsigned)s_off[min(d0 + u, a.ndiag - 1)];
 #pragma unroll
           for (int i = 0; i < RPT; ++i)
-            xv[u][i] = ld_ro(a.x + min(r0 + tid + i * BLOCK + off[u], cols - 1));
+            xv[u][i] = operand(min(r0 + tid + i * BLOCK + off[u], cols - 1));
         }
         mbar_wait(&full[s], ph);
         const T *sv = s_vals + (size_t)s * DIA_KC * R;
@@ -360,11 +410,17 @@ __global__ void __launch_bounds__(BLOCK + 32) dia_bulk_kernel(DiaArgs<T> a, int 
       for (int i = 0; i < RPT; ++i) {
         const unsigned r = r0 + tid + i * BLOCK;
         a.y[r] = acc[i];
-        if (a.dotv) dsum = dsum + acc[i] * ld_ro(a.dotv + r);
+        if (FUSED) {
+          const T pn = operand(r + (unsigned)a.fshift);
+          a.fpn[r + a.fshift] = pn;
+          dsum = dsum + acc[i] * pn;
+        } else if (a.dotv) {
+          dsum = dsum + acc[i] * ld_ro(a.dotv + r);
+        }
       }
     }
   }
-  if (a.dotv) {
+  if (FUSED || a.dotv) {
     if (tid >= BLOCK) dsum = 0;
     T bs = block_sum<BLOCK + 32>(dsum, s_red);
     grid_reduce_finish<BLOCK + 32>(bs, a.dot_partials, a.dot_ticket, s_red,
@@ -401,11 +457,11 @@ static b200sp_status dispatch_ldg(b200sp_handle h, cudaStream_t st, const DiaArg
   return set_error(h, B200SP_INVALID_INPUT, "dia ldg: unsupported block_size=%d unroll=%d", block, rpt);
 }
 
-template <typename T, int BLOCK, int RPT>
+template <typename T, int BLOCK, int RPT, bool FUSED = false>
 static b200sp_status launch_bulk(b200sp_handle h, cudaStream_t st, DiaArgs<T> a, i64 num_tiles,
                                  int stages, int ctas_per_sm) {
   constexpr int R = BLOCK * RPT;
-  auto kern = dia_bulk_kernel<T, BLOCK, RPT>;
+  auto kern = dia_bulk_kernel<T, BLOCK, RPT, FUSED>;
   size_t smem = (size_t)stages * DIA_KC * R * sizeof(T) + 2 * stages * sizeof(uint64_t) +
                 (size_t)a.ndiag * sizeof(int) + 16;
   if (smem > (size_t)h->max_smem_optin)
@@ -417,9 +473,16 @@ static b200sp_status launch_bulk(b200sp_handle h, cudaStream_t st, DiaArgs<T> a,
   B200SP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, BLOCK + 32, smem));
   if (resident < 1) return set_error(h, B200SP_INVALID_INPUT, "dia bulk: configuration does not fit on an SM");
   i64 grid = (i64)h->num_sms * (ctas_per_sm < resident ? ctas_per_sm : resident);
-  if (grid > num_tiles) grid = num_tiles;
-  if (a.dotv && grid > RED_MAX_PARTIALS) return set_error(h, B200SP_INVALID_INPUT, "dia: grid too large");
-  a.pdl = h->pdl_spmv ? 1 : 0;
+  // runs of consecutive tiles per CTA, as long as every CTA still gets several runs (load balance).  Measured on
+  // poisson7pt (B200SP_DIA_RUN): the plain product is indifferent up to 4 and loses 4 % at 16 (HBM-bound either way);
+  // the fused-direction product is best at 4 (3.08 ms per 512^3 iteration against 3.16 at 1, 3.25 at 16)
+  int run = FUSED ? 4 : 1;
+  if (const char *e = getenv("B200SP_DIA_RUN")) run = atoi(e) > 0 ? atoi(e) : run;
+  while (run > 1 && num_tiles < grid * run * 4) run /= 2;
+  a.run = run;
+  if (grid > ceil_div(num_tiles, (i64)run)) grid = ceil_div(num_tiles, (i64)run);
+  if ((FUSED || a.dotv) && grid > RED_MAX_PARTIALS) return set_error(h, B200SP_INVALID_INPUT, "dia: grid too large");
+  a.pdl = (h->pdl_spmv && !FUSED) ? 1 : 0;
   B200SP_CUDA(h, launch_kernel_pdl(kern, dim3((unsigned)grid), dim3(BLOCK + 32), smem, st, a.pdl != 0, a, stages, num_tiles));
   h->launches++;
   return B200SP_OK;
@@ -433,6 +496,16 @@ static b200sp_status dispatch_bulk(b200sp_handle h, cudaStream_t st, const DiaAr
   CASE(128, 2) CASE(128, 4) CASE(128, 8) CASE(256, 1) CASE(256, 2) CASE(256, 4)
 #undef CASE
   return set_error(h, B200SP_INVALID_INPUT, "dia bulk: unsupported block_size=%d unroll=%d", block, rpt);
+}
+
+template <typename T>
+static b200sp_status dispatch_bulk_fused(b200sp_handle h, cudaStream_t st, const DiaArgs<T> &a, i64 num_tiles,
+                                         int block, int rpt, int stages, int cps) {
+#define CASE(B, R) \
+  if (block == B && rpt == R) return launch_bulk<T, B, R, true>(h, st, a, num_tiles, stages, cps);
+  CASE(128, 2) CASE(128, 4) CASE(256, 1) CASE(256, 2)
+#undef CASE
+  return set_error(h, B200SP_INVALID_INPUT, "dia bulk (fused direction): unsupported block_size=%d unroll=%d", block, rpt);
 }
 
 // Engine defaults (overridden by cfg / tuning cache).  Chosen on B200 from the
@@ -462,6 +535,68 @@ bool dia_can_fuse_xchg(i64 rows, i64 ndiag, i64 pitch, const void *vals, size_t 
   const int R = c.block_size * c.unroll;
   return (pitch * elem) % 16 == 0 && aligned16(vals) && ((size_t)R * elem) % 16 == 0;
 }
+
+// does spmv_dia_fused_direction() have an instantiation for this configuration?
+bool dia_can_fuse_direction(i64 rows, i64 ndiag, i64 pitch, const void *vals, size_t elem, const b200sp_cfg *cfg) {
+  if (!dia_can_fuse_xchg(rows, ndiag, pitch, vals, elem, cfg)) return false;
+  b200sp_cfg c = cfg ? *cfg : b200sp_cfg{};
+  dia_defaults(c, elem);
+  return (c.block_size == 128 && (c.unroll == 2 || c.unroll == 4)) || (c.block_size == 256 && (c.unroll == 1 || c.unroll == 2));
+}
+
+// y = A p with p[j] = r[j] + beta p_old[j] rebuilt on the fly, p stored into p_new (window coordinates, own rows at
+// [shift, shift + rows) plus both halos), <y, p> into *dot_result: the product and the direction update of one CG
+// iteration in one pass (see DiaArgs).  `xchg` (enabled == 2) makes the tiles next to the halos wait for the
+// neighbours' r planes.
+template <typename T>
+b200sp_status spmv_dia_fused_direction(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64 ndiag, i64 pitch,
+                                       const int *offs, const T *vals, T *y, const b200sp_cfg *cfg, const T *r_win,
+                                       const T *p_old_win, T *p_new_win, const T *beta, const int *done, int first,
+                                       i64 shift, i64 halo_lo, i64 halo_hi, T *dot_result, const DiaXchg *xchg) {
+  B200SP_CHECK_HANDLE(h);
+  B200SP_REQUIRE(h, rows > 0 && ndiag > 0 && rows < (1ll << 31) && cols < (1ll << 31) && pitch >= rows,
+                 "dia (fused direction): bad dimensions");
+  B200SP_REQUIRE(h, y && offs && vals && r_win && p_old_win && p_new_win && beta && done && dot_result,
+                 "dia (fused direction): null pointer");
+  B200SP_REQUIRE(h, cols == shift + rows + halo_hi && shift == halo_lo, "dia (fused direction): window does not match the operator");
+  b200sp_cfg c = cfg ? *cfg : b200sp_cfg{};
+  dia_defaults(c, sizeof(T));
+  if (const char *e = getenv("B200SP_DIA_FUSED_SHAPE")) {  // "block,unroll,stages,ctas" (experiments)
+    int b = 0, u = 0, sg = 0, cp = 0;
+    if (sscanf(e, "%d,%d,%d,%d", &b, &u, &sg, &cp) == 4) {
+      c.block_size = b; c.unroll = u; c.stages = sg; c.ctas_per_sm = cp;
+    }
+  }
+  B200SP_REQUIRE(h, dia_can_fuse_direction(rows, ndiag, pitch, vals, sizeof(T), &c), "dia (fused direction): configuration not supported");
+  DiaArgs<T> a;
+  memset(&a, 0, sizeof(a));
+  a.rows = rows; a.cols = cols; a.pitch = pitch; a.ndiag = (int)ndiag;
+  a.offs = offs; a.vals = vals; a.x = nullptr; a.y = y; a.accumulate = 0;
+  a.dotv = nullptr; a.dot_result = dot_result;
+  a.dot_partials = reinterpret_cast<T *>(h->red_partials);
+  a.dot_ticket = h->red_counters;
+  a.fr = r_win; a.fp = first ? r_win : p_old_win; a.fpn = p_new_win; a.fbeta = beta; a.fdone = done; a.ffirst = first;
+  a.fshift = shift; a.fhalo_lo = halo_lo; a.fhalo_hi = halo_hi;
+  const int R = c.block_size * c.unroll;
+  const i64 tiles = ceil_div(rows, (i64)R);
+  if (xchg && xchg->enabled) a.xc = *xchg;
+  a.xc.lo_tiles = ceil_div(halo_lo, (i64)R);
+  a.xc.hi_tile_begin = halo_hi > 0 ? (rows - halo_hi) / R : tiles;
+  if (a.xc.hi_tile_begin < 0) a.xc.hi_tile_begin = 0;
+  a.xc.rot = a.xc.lo_tiles;
+  if (!a.xc.enabled || a.xc.lo_tiles + (tiles - a.xc.hi_tile_begin) >= tiles) a.xc.rot = 0;
+  if (a.xc.rot >= tiles) a.xc.rot = 0;
+  return dispatch_bulk_fused<T>(h, st, a, tiles, c.block_size, c.unroll, c.stages, c.ctas_per_sm);
+}
+
+template b200sp_status spmv_dia_fused_direction<float>(b200sp_handle, cudaStream_t, i64, i64, i64, i64, const int *,
+                                                       const float *, float *, const b200sp_cfg *, const float *,
+                                                       const float *, float *, const float *, const int *, int, i64, i64,
+                                                       i64, float *, const DiaXchg *);
+template b200sp_status spmv_dia_fused_direction<double>(b200sp_handle, cudaStream_t, i64, i64, i64, i64, const int *,
+                                                        const double *, double *, const b200sp_cfg *, const double *,
+                                                        const double *, double *, const double *, const int *, int, i64,
+                                                        i64, i64, double *, const DiaXchg *);
 
 template <typename T>
 b200sp_status spmv_dia(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64 ndiag, i64 pitch,

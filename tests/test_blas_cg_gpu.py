@@ -201,3 +201,39 @@ def test_cg_graph_replay_is_the_same_solve(fmt, dev, monkeypatch):
     assert base[0] > 20
     for k, v in out.items():
         assert v[0] == base[0] and v[1] == base[1] and torch.equal(v[2], base[2]), k
+
+
+@pytest.mark.parametrize("ndt,tdt", [(np.float32, torch.float32), (np.float64, torch.float64)])
+@pytest.mark.parametrize("grid", [(40, 33), (24, 20, 19), (64, 64, 16)])
+def test_cg_two_kernel_iteration_is_the_same_solve(grid, ndt, tdt, dev, monkeypatch):
+    """DIA through the bulk kernel: the direction update p = r + beta p is folded into the product (B200SP_CG_FUSE,
+    csrc/cg.cu) — same expressions in the same order, so iteration count, history and solution equal the three-kernel
+    solve bit for bit, launch by launch and from a replayed graph, whatever the poll interval (odd ones included: the
+    graph holds an even number of iterations)"""
+    A = O.poisson(5 if len(grid) == 2 else 7, grid, ndt, "dia")
+    Ad = upload("dia", A, dev)
+    b = tdev(np.random.default_rng(4).uniform(-1, 1, A["num_rows"]).astype(ndt), dev)
+    out = {}
+    for fuse in ("0", "1"):
+        monkeypatch.setenv("B200SP_CG_FUSE", fuse)
+        for graph in ("0", "1"):
+            monkeypatch.setenv("B200SP_CG_GRAPH", graph)
+            for ci in (1, 5, 16):
+                x = torch.zeros_like(b)
+                mon = cusp.monitor(b, 200, 1e-5 if ndt == np.float32 else 1e-10)
+                cusp.krylov.cg(Ad, x, b, mon, check_interval=ci)
+                out[(fuse, graph, ci)] = (mon.iteration_count(), list(mon.residuals), x.clone(), mon.converged())
+    base = out[("0", "0", 1)]
+    assert base[0] > 15 and base[3]
+    for k, v in out.items():
+        assert v[0] == base[0] and v[1] == base[1] and torch.equal(v[2], base[2]) and v[3] == base[3], k
+    # and an iteration limit that stops the solve in mid-graph
+    monkeypatch.setenv("B200SP_CG_GRAPH", "1")
+    res = {}
+    for fuse in ("0", "1"):
+        monkeypatch.setenv("B200SP_CG_FUSE", fuse)
+        x = torch.zeros_like(b)
+        mon = cusp.monitor(b, 11, 0.0)
+        cusp.krylov.cg(Ad, x, b, mon, check_interval=8)
+        res[fuse] = (mon.iteration_count(), list(mon.residuals), x.clone())
+    assert res["0"][0] == 11 and res["1"][0] == 11 and res["0"][1] == res["1"][1] and torch.equal(res["0"][2], res["1"][2])

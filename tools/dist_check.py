@@ -178,6 +178,18 @@ def main():
                 prod["cg_hist_max_rel_dev"] = devmax
                 prod["cg_hist_ok"], prod["cg_x_ok"] = int(flags[0].item()), int(flags[1].item())
                 ok = ok and bool(flags[0].item()) and bool(flags[1].item())
+                # the opt-in two-kernel form (r planes travel, p rebuilt inside the product) gives the same bits as
+                # the default three-kernel form (direction update as its own kernel, p planes travel)
+                os.environ["B200SP_CG_FUSE"] = "1"
+                xl3 = torch.zeros(blk.num_rows, dtype=tdt, device=dev)
+                res3, hist3 = h.cg(A.descriptor(), xl3, bl, iteration_limit=40, relative_tolerance=0.0, check_interval=8,
+                                   halo=halo)
+                del os.environ["B200SP_CG_FUSE"]
+                same = int(list(hist3) == list(hist) and torch.equal(xl3, xl) and int(res3.iteration_count) == int(res.iteration_count))
+                flags = torch.tensor([same], device=dev)
+                td.all_reduce(flags, op=td.ReduceOp.MIN)
+                prod["cg_two_vs_three_kernel_bits"] = int(flags.item())
+                ok = ok and bool(flags.item())
             del A, xw, y, want
             torch.cuda.empty_cache()
         out["production"] = prod

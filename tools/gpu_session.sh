@@ -11,6 +11,44 @@ for s in $STEPS; do
       python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 $O/${TAG}_pytest.log ;;
     bench)
       python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; echo "bench rc=$?"; tail -c 1800 $O/${TAG}_bench.json; tail -3 $O/${TAG}_bench.err ;;
+    cgtest)
+      timeout 900 python -m pytest tests/test_blas_cg_gpu.py tests/test_krylov_gpu.py -m gpu -x -q > $O/${TAG}_cgtest.log 2>&1; echo "cgtest rc=$?"; tail -6 $O/${TAG}_cgtest.log ;;
+    cgab)
+      for f in 0 1; do
+        B200SP_CG_FUSE=$f timeout 600 python bench.py --only-cg --steps 10 --warmup 3 > $O/${TAG}_cg_fuse$f.json 2> $O/${TAG}_cg_fuse$f.err; echo "cg fuse=$f rc=$?"
+        python -c "
+import json
+d=json.loads(open('$O/${TAG}_cg_fuse$f.json').read().strip().splitlines()[-1]); print('fuse=$f', d['cg'], d['parity'])"
+      done ;;
+    runab)
+      for run in 1 4 16 64; do
+        B200SP_DIA_RUN=$run timeout 600 python bench.py --only-cg --steps 10 --warmup 3 > $O/${TAG}_cg_run$run.json 2> $O/${TAG}_cg_run$run.err; echo "cg run=$run rc=$?"
+        python -c "
+import json
+d=json.loads(open('$O/${TAG}_cg_run$run.json').read().strip().splitlines()[-1]); print('fused cg run=$run', d['cg']['ms_per_iter'], d['parity']['cg_ok'])"
+      done
+      for run in 1 4 16; do
+        B200SP_DIA_RUN=$run timeout 600 python bench.py --quick --steps 100 > $O/${TAG}_dia_run$run.json 2> $O/${TAG}_dia_run$run.err; echo "dia run=$run rc=$?"
+        python -c "
+import json
+d=json.loads(open('$O/${TAG}_dia_run$run.json').read().strip().splitlines()[-1]); print('plain dia run=$run', d['ms_per_step'], d['roofline']['frac'])"
+      done ;;
+    ncucg)
+      python tools/prof_kernels.py cg > $O/${TAG}_cgplain.log 2>&1 && \
+      ncu --set full --clock-control none --import-source on -k regex:"dia_bulk|cg_update|cg_direction" -c 8 \
+          -f -o $O/${TAG}_cg_full python tools/prof_kernels.py cg > $O/${TAG}_ncu_cg.log 2>&1; echo "ncu cg rc=$?"
+      B200SP_CG_FUSE=0 python tools/prof_kernels.py cg > $O/${TAG}_cgplain3.log 2>&1 && \
+      B200SP_CG_FUSE=0 ncu --set full --clock-control none --import-source on -k regex:"dia_bulk|cg_update|cg_direction" -c 10 \
+          -f -o $O/${TAG}_cg3_full python tools/prof_kernels.py cg > $O/${TAG}_ncu_cg3.log 2>&1; echo "ncu cg3 rc=$?" ;;
+    shapeab)
+      for shape in 128,2,2,4 256,1,2,4 256,1,3,4 256,1,2,6 128,2,3,4 256,2,2,2 128,2,2,3; do
+        B200SP_DIA_RUN=1 B200SP_DIA_FUSED_SHAPE=$shape timeout 600 python bench.py --only-cg --steps 10 --warmup 3 > $O/${TAG}_cg_shape.json 2> $O/${TAG}_cg_shape.err; echo "cg shape=$shape rc=$?"
+        python -c "
+import json
+d=json.loads(open('$O/${TAG}_cg_shape.json').read().strip().splitlines()[-1]); print('fused cg shape=$shape', d['cg']['ms_per_iter'], d['parity']['cg_ok'])"
+      done ;;
+    widen)
+      timeout 900 python tools/widen_time.py > $O/${TAG}_widen.json 2> $O/${TAG}_widen.err; echo "widen rc=$?"; tail -c 3000 $O/${TAG}_widen.json; tail -3 $O/${TAG}_widen.err ;;
     benchref)
       python bench.py --impl reference --steps 5 --warmup 3 > $O/${TAG}_bench_ref.json 2> $O/${TAG}_bench_ref.err; echo "benchref rc=$?" ;;
     probe)

@@ -11,6 +11,15 @@ h = cusp.default_handle()
 dev = torch.device("cuda", 0)
 n = 256
 for fmt in which:
+    if fmt == "cg":  # a few CG iterations on the headline DIA operator (fused-direction product + update kernel)
+        from cusp_autotuned_b200 import krylov as K
+        A = gallery.poisson("dia", 7, (n, n, n), dtype=torch.float64)
+        b = torch.ones(A.num_rows, dtype=torch.float64, device=dev)
+        xk = torch.zeros_like(b)
+        K.cg(A, xk, b, cusp.monitor(b, 4, 0.0), check_interval=4)
+        torch.cuda.synchronize()
+        del A, b, xk
+        continue
     if fmt.split(":")[0] in ("dia", "ell", "csr"):
         A = gallery.poisson(fmt, 7, (n, n, n), dtype=torch.float64)
         x = ((torch.arange(A.num_cols, device=dev) % 21) - 10).double()

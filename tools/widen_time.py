@@ -39,7 +39,12 @@ def timed(fn, reps=20, warm=3):
 
 for tdt, es in ((torch.float32, 4), (torch.float64, 8)):
     for fmt in ("dia", "ell", "csr", "coo", "hyb"):
-        A = gallery.poisson(fmt, 7, (n, n, n), dtype=tdt)
+        if fmt in ("coo", "hyb"):
+            C0 = gallery.poisson("csr", 7, (n, n, n), dtype=tdt)
+            A = convert.csr_to_coo(C0) if fmt == "coo" else convert.csr_to_hyb(C0)
+            del C0
+        else:
+            A = gallery.poisson(fmt, 7, (n, n, n), dtype=tdt)
         x = ((torch.arange(A.num_cols, device=dev) % 21) - 10).to(tdt)
         y = torch.zeros(A.num_rows, dtype=tdt, device=dev)
         B = compulsory_bytes(A, es)
