@@ -257,11 +257,27 @@ __global__ void __launch_bounds__(BLOCK + 32) dia_bulk_kernel(DiaArgs<T> a, int 
   T dsum = 0;
   // FUSED: the operand element at window index j (first iteration: beta = 0 and fp = fr, so p = r without a branch)
   const T fbeta = FUSED ? *a.fbeta : T(0);
-  auto operand = [&](unsigned j) -> T {
-    if (!FUSED) return ld_ro(a.x + j);
-    const T rv = ld_ro(a.fr + j);
-    const T pv = ld_ro(a.fp + j);
-    return T(1) * rv + fbeta * pv;
+  const T *const opx = FUSED ? a.fr : a.x;
+  const T *const opp = a.fp;
+  auto operand = [opx, opp, fbeta](unsigned j) -> T {
+    if constexpr (!FUSED) {
+      return ld_ro(opx + j);
+    } else {
+      const T rv = ld_ro(opx + j);
+      const T pv = ld_ro(opp + j);
+      return T(1) * rv + fbeta * pv;
+    }
+  };
+  // runs of consecutive tiles per CTA (DiaArgs::run): the plain product is indifferent to them, so it keeps the
+  // one-tile stride at compile time
+  const i64 run = FUSED ? (i64)a.run : 1;  // a power of two
+  const i64 seq_first = FUSED ? (i64)blockIdx.x * run : (i64)blockIdx.x;
+  auto seq_next = [run](i64 seq) -> i64 {
+    if constexpr (!FUSED) {
+      return seq + gridDim.x;
+    } else {
+      return ((seq + 1) & (run - 1)) ? seq + 1 : seq + 1 + (i64)(gridDim.x - 1) * run;
+    }
   };
 
   if (tid >= BLOCK) {
@@ -270,8 +286,7 @@ __global__ void __launch_bounds__(BLOCK + 32) dia_bulk_kernel(DiaArgs<T> a, int 
       const uint64_t pol = l2_policy_evict_first();
       int s = 0;
       uint32_t ph = 0;
-      for (i64 base = (i64)blockIdx.x * a.run; base < num_tiles; base += (i64)gridDim.x * a.run)
-      for (i64 seq = base; seq < base + a.run && seq < num_tiles; ++seq) {
+      for (i64 seq = seq_first; seq < num_tiles; seq = seq_next(seq)) {
         i64 tile = seq + a.xc.rot;
         if (tile >= num_tiles) tile -= num_tiles;
         const i64 r0 = a.row_begin + tile * R;
@@ -306,8 +321,7 @@ __global__ void __launch_bounds__(BLOCK + 32) dia_bulk_kernel(DiaArgs<T> a, int 
     uint32_t ph = 0;
     const int lane = tid & 31;
     bool ready_lo = !a.xc.enabled, ready_hi = !a.xc.enabled;
-    for (i64 base = (i64)blockIdx.x * a.run; base < num_tiles; base += (i64)gridDim.x * a.run)
-    for (i64 seq = base; seq < base + a.run && seq < num_tiles; ++seq) {
+    for (i64 seq = seq_first; seq < num_tiles; seq = seq_next(seq)) {
       i64 tile = seq + a.xc.rot;
       if (tile >= num_tiles) tile -= num_tiles;
       // first tile of this warp that reads halo columns: the planes must have landed
@@ -385,7 +399,12 @@ __global__ void __launch_bounds__(BLOCK + 32) dia_bulk_kernel(DiaArgs<T> a, int 
           off[u] = (unsigned)s_off[min(d0 + u, a.ndiag - 1)];
 #pragma unroll
           for (int i = 0; i < RPT; ++i)
-            xv[u][i] = operand(min(r0 + tid + i * BLOCK + off[u], cols - 1));
+            {
+              const unsigned j = min(r0 + tid + i * BLOCK + off[u], cols - 1);
+              // (the plain product reads a.x straight from the parameter bank: routing it through the lambda's
+              // captured pointer costs registers in the headline kernel)
+              xv[u][i] = FUSED ? operand(j) : ld_ro(a.x + j);
+            }
         }
         mbar_wait(&full[s], ph);
         const T *sv = s_vals + (size_t)s * DIA_KC * R;
@@ -474,10 +493,11 @@ static b200sp_status launch_bulk(b200sp_handle h, cudaStream_t st, DiaArgs<T> a,
   if (resident < 1) return set_error(h, B200SP_INVALID_INPUT, "dia bulk: configuration does not fit on an SM");
   i64 grid = (i64)h->num_sms * (ctas_per_sm < resident ? ctas_per_sm : resident);
   // runs of consecutive tiles per CTA, as long as every CTA still gets several runs (load balance).  Measured on
-  // poisson7pt (B200SP_DIA_RUN): the plain product is indifferent up to 4 and loses 4 % at 16 (HBM-bound either way);
-  // the fused-direction product is best at 4 (3.08 ms per 512^3 iteration against 3.16 at 1, 3.25 at 16)
+  // poisson7pt (B200SP_DIA_RUN): the plain product is indifferent up to 4 and loses 4 % at 16 (HBM-bound either way:
+  // it keeps run = 1); the fused-direction product is best at 4 (3.08 ms per 512^3 iteration against 3.16 at 1, 3.25 at 16)
   int run = FUSED ? 4 : 1;
-  if (const char *e = getenv("B200SP_DIA_RUN")) run = atoi(e) > 0 ? atoi(e) : run;
+  if (const char *e = getenv("B200SP_DIA_RUN")) run = (FUSED && atoi(e) > 0) ? atoi(e) : run;
+  while (run & (run - 1)) run &= run - 1;  // a power of two
   while (run > 1 && num_tiles < grid * run * 4) run /= 2;
   a.run = run;
   if (grid > ceil_div(num_tiles, (i64)run)) grid = ceil_div(num_tiles, (i64)run);
