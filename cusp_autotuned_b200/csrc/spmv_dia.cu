@@ -495,7 +495,7 @@ static b200sp_status launch_bulk(b200sp_handle h, cudaStream_t st, DiaArgs<T> a,
   // runs of consecutive tiles per CTA, as long as every CTA still gets several runs (load balance).  Measured on
   // poisson7pt (B200SP_DIA_RUN): the plain product is indifferent up to 4 and loses 4 % at 16 (HBM-bound either way:
   // it keeps run = 1); the fused-direction product is best at 4 (3.08 ms per 512^3 iteration against 3.16 at 1, 3.25 at 16)
-  int run = FUSED ? 4 : 1;
+  int run = 1;  // (runs change which CTA sums which tiles of the fused dot product: 1 keeps the bits of the plain form)
   if (const char *e = getenv("B200SP_DIA_RUN")) run = (FUSED && atoi(e) > 0) ? atoi(e) : run;
   while (run & (run - 1)) run &= run - 1;  // a power of two
   while (run > 1 && num_tiles < grid * run * 4) run /= 2;

@@ -47,6 +47,8 @@ d=json.loads(open('$O/${TAG}_dia_run$run.json').read().strip().splitlines()[-1])
 import json
 d=json.loads(open('$O/${TAG}_cg_shape.json').read().strip().splitlines()[-1]); print('fused cg shape=$shape', d['cg']['ms_per_iter'], d['parity']['cg_ok'])"
       done ;;
+    hybprobe)
+      timeout 600 python tools/hyb_probe.py > $O/${TAG}_hyb_probe.json 2> $O/${TAG}_hyb_probe.err; echo "hyb probe rc=$?"; cat $O/${TAG}_hyb_probe.json; tail -3 $O/${TAG}_hyb_probe.err ;;
     widen)
       timeout 900 python tools/widen_time.py > $O/${TAG}_widen.json 2> $O/${TAG}_widen.err; echo "widen rc=$?"; tail -c 3000 $O/${TAG}_widen.json; tail -3 $O/${TAG}_widen.err ;;
     benchref)
