@@ -34,6 +34,8 @@
 #include "common.cuh"
 #include "comm.h"
 
+#include <cooperative_groups.h>
+
 namespace b200sp {
 
 template <typename T>
@@ -660,6 +662,175 @@ __global__ void __launch_bounds__(CG_BLOCK) cg_update_push_p2p_kernel(i64 n, con
   }
 }
 
+// ---------------------------------------------------------------------------
+// Small systems (CSR, one GPU): the whole solve in ONE persistent cooperative kernel.
+//
+// poisson5pt 512^2 is 21 MB of matrix and 2 MB per vector: launch by launch an iteration costs 25 us, replayed from a
+// CUDA graph 19 us, of which the kernels' own work is a fraction.  Here every CTA (one of 1024 threads per SM) owns a
+// contiguous block of rows and keeps its slice of the matrix (values, columns, offsets) and its rows of x, r, p, y in
+// shared memory for the whole solve; per iteration only r and p pass through L2 (the neighbours' gathers) and two grid
+// barriers are paid: one behind each dot product.  The direction update needs no barrier of its own: the product
+// rebuilds  p[j] = r[j] + beta p_old[j]  where it gathers (both already visible behind the <r,r> barrier), the
+// two-kernel idea of B200SP_CG_FUSE, which does pay here because it saves a barrier rather than a pass over HBM.
+// Same expressions and the same per-row order as the three-kernel form; the dot products are grouped by CTA
+// (tolerance-level difference, like between any two grid sizes).  The stopping rule runs on the device
+// (monitor_step's arithmetic, evaluated identically by every CTA); the host is not involved until the end.
+// A slice that does not fit in shared memory raises *fallback and the solve takes the ordinary path.
+// ---------------------------------------------------------------------------
+constexpr int CGS_BLOCK = 1024;
+
+template <typename T>
+struct CgSmallArgs {
+  i64 n, rows_per_cta;
+  const int *Ap, *Aj;
+  const T *Ax;
+  T *x;
+  const T *b;
+  T *r_g, *p_g0, *p_g1;  // global mirrors of r and of the two direction buffers (n each)
+  T *part_a, *part_b;    // gridDim.x partial sums each: the two alternating reductions of an iteration
+  CgState<T> *S;
+  double *residuals;
+  int *fallback;
+  unsigned smem_bytes;
+};
+
+// Grid-wide sum behind a grid barrier: every CTA stores its partial, cooperative_groups' grid barrier, then every CTA
+// adds all partials itself in index order (the same order everywhere).  Two hand-rolled replacements that fold the
+// barrier into the reduction were measured on B200 (148 CTAs, poisson5pt 512^2) and lost: every CTA polling every
+// CTA's tagged partial (mailbox words as on the multi-GPU path) 16.4 us per iteration — 148 x 148 polls on 19 L2
+// lines; a ticket whose last taker sums and publishes one tagged total that everybody polls 16.3 us; this form 10.4 us.
+template <typename T>
+__device__ __forceinline__ T cgs_allreduce(cooperative_groups::grid_group &grid, T *partials, T block_value /* thread 0 */,
+                                           T *s_red) {
+  if (threadIdx.x == 0) __stcg(partials + blockIdx.x, block_value);
+  __threadfence();
+  grid.sync();
+  if (threadIdx.x < 32) {
+    T v = T(0);
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += 32) v = v + __ldcg(partials + i);
+    v = warp_sum(v);
+    if (threadIdx.x == 0) s_red[0] = v;
+  }
+  __syncthreads();
+  const T t = s_red[0];
+  __syncthreads();
+  return t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CGS_BLOCK, 1) cg_small_csr_kernel(CgSmallArgs<T> a) {
+  namespace cgx = cooperative_groups;
+  cgx::grid_group grid = cgx::this_grid();
+  extern __shared__ __align__(16) unsigned char cgs_smem[];
+  __shared__ T s_red[32];
+  const int tid = threadIdx.x;
+  const i64 r0 = min(a.n, (i64)blockIdx.x * a.rows_per_cta), r1 = min(a.n, r0 + a.rows_per_cta);
+  const int rc = (int)(r1 - r0);
+  const int e0 = rc > 0 ? a.Ap[r0] : 0, e1 = rc > 0 ? a.Ap[r1] : 0;
+  const int nz = e1 - e0;
+  // shared memory: Ax[nz] x[rc] r[rc] p[rc] y[rc] (T) | Aj[nz] off[rc + 1] (int)
+  const size_t need = ((size_t)nz + 4 * (size_t)rc) * sizeof(T) + ((size_t)nz + rc + 1) * sizeof(int) + 16;
+  if (need > a.smem_bytes && tid == 0) atomicExch(a.fallback, 1);
+  __threadfence();
+  grid.sync();
+  if (__ldcg(a.fallback)) return;
+  T *s_ax = reinterpret_cast<T *>(cgs_smem);
+  T *s_x = s_ax + nz, *s_r = s_x + rc, *s_p = s_r + rc, *s_y = s_p + rc;
+  int *s_aj = reinterpret_cast<int *>(s_y + rc);
+  int *s_off = s_aj + nz;
+  for (int k = tid; k < nz; k += CGS_BLOCK) {
+    s_ax[k] = a.Ax[e0 + k];
+    s_aj[k] = a.Aj[e0 + k];
+  }
+  for (int i = tid; i <= rc; i += CGS_BLOCK) s_off[i] = (rc > 0 ? a.Ap[r0 + i] : 0) - e0;
+  __syncthreads();
+
+  CgState<T> *S = a.S;
+  const T tol = S->tol;
+  const int limit = S->limit;
+  int iter = 0, nres = 0, converged = 0;
+  // cusp::monitor::finished (monitor.inl:178-208), evaluated by every CTA; CTA 0 keeps the log
+  T rnorm = T(0);
+  auto finished = [&](T rz) -> bool {
+    rnorm = (T)sqrt((double)rz);
+    if (blockIdx.x == 0 && tid == 0) a.residuals[nres] = (double)rnorm;
+    ++nres;
+    if (rnorm <= tol) {
+      converged = 1;
+      return true;
+    }
+    return iter >= limit;
+  };
+
+  // y = A x0 ; r = b - y ; rz = <r,r>   (cg.inl:63-72)
+  T acc = T(0);
+  for (int i = tid; i < rc; i += CGS_BLOCK) {
+    T sum = T(0);
+    for (int k = s_off[i]; k < s_off[i + 1]; ++k) sum = sum + s_ax[k] * a.x[s_aj[k]];
+    const T ri = T(1) * a.b[r0 + i] + T(-1) * sum;
+    s_x[i] = a.x[r0 + i];
+    s_r[i] = ri;
+    s_p[i] = ri;
+    __stcg(a.r_g + r0 + i, ri);
+    acc = acc + ri * ri;
+  }
+  T bs = block_sum<CGS_BLOCK>(acc, s_red);
+  T rz = cgs_allreduce(grid, a.part_b, bs, s_red);
+  bool done = finished(rz);
+
+  T beta = T(0);
+  const T *p_old = a.r_g;  // first iteration: beta = 0 and p_old = r, so p = r
+  T *p_new = a.p_g0;
+  while (!done) {
+    // y = A p with p rebuilt at the gathers; the own rows' p kept in shared memory and mirrored for the neighbours
+    acc = T(0);
+    for (int i = tid; i < rc; i += CGS_BLOCK) {
+      const T pn = T(1) * s_r[i] + beta * s_p[i];
+      T sum = T(0);
+      for (int k = s_off[i]; k < s_off[i + 1]; ++k) {
+        const int j = s_aj[k];
+        const T pj = T(1) * __ldcg(a.r_g + j) + beta * __ldcg(p_old + j);
+        sum = sum + s_ax[k] * pj;
+      }
+      s_p[i] = pn;
+      __stcg(p_new + r0 + i, pn);
+      s_y[i] = sum;
+      acc = acc + sum * pn;
+    }
+    bs = block_sum<CGS_BLOCK>(acc, s_red);
+    const T yp = cgs_allreduce(grid, a.part_a, bs, s_red);
+    // x += alpha p ; r -= alpha y ; <r,r>
+    const T alpha = rz / yp;
+    const T nalpha = -alpha;
+    acc = T(0);
+    for (int i = tid; i < rc; i += CGS_BLOCK) {
+      s_x[i] = alpha * s_p[i] + s_x[i];
+      const T rn = nalpha * s_y[i] + s_r[i];
+      s_r[i] = rn;
+      __stcg(a.r_g + r0 + i, rn);
+      acc = acc + rn * rn;
+    }
+    bs = block_sum<CGS_BLOCK>(acc, s_red);
+    const T rz_new = cgs_allreduce(grid, a.part_b, bs, s_red);
+    beta = rz_new / rz;
+    rz = rz_new;
+    ++iter;
+    done = finished(rz);
+    p_old = p_new;
+    p_new = (p_new == a.p_g0) ? a.p_g1 : a.p_g0;
+  }
+  for (int i = tid; i < rc; i += CGS_BLOCK) a.x[r0 + i] = s_x[i];
+  if (blockIdx.x == 0 && tid == 0) {
+    S->rz = rz;
+    S->beta = beta;
+    S->rnorm = rnorm;
+    S->iter = iter;
+    S->nres = nres;
+    S->converged = converged;
+    S->done = 1;
+  }
+}
+
 template <typename T>
 __global__ void cg_setup_state_kernel(CgState<T> *S, const T *bnorm, double rel, double abs_tol, int limit) {
   S->bnorm = *bnorm;
@@ -711,7 +882,16 @@ static b200sp_status cg_impl(b200sp_handle h, cudaStream_t st, const b200sp_matr
   const size_t win = (size_t)(halo_lo + n + halo_hi);
   auto lines = [](size_t elems) { return (elems * sizeof(T) + 127) / 128 * 128; };
   const size_t off_r = lines((size_t)n), off_p0 = off_r + lines(win), off_p1 = off_p0 + lines(win);
-  const size_t need = off_p1 + (fuse_dir ? lines(win) : 0) + 256;
+  // one persistent cooperative kernel for small CSR systems on one GPU (cg_small_csr_kernel); B200SP_CG_PERSISTENT=0
+  // turns it off.  The size test is the necessary condition (the mean slice fits); the kernel checks every slice.
+  const char *pers_env = getenv("B200SP_CG_PERSISTENT");
+  const i64 pers_grid = h->num_sms < 1024 ? h->num_sms : 1024;
+  const size_t pers_smem = (size_t)h->max_smem_optin > 1024 ? (size_t)h->max_smem_optin - 1024 : 0;
+  const bool persistent = !(pers_env && pers_env[0] == '0') && !dist && A->format == B200SP_FMT_CSR && n > 0 &&
+                          A->num_entries < (1ll << 31) &&
+                          ((size_t)A->num_entries * (sizeof(T) + 4) + (size_t)n * (4 * sizeof(T) + 4)) / (size_t)pers_grid +
+                                  4096 <= pers_smem;
+  const size_t need = off_p1 + ((fuse_dir || persistent) ? lines(win) : 0) + 256;
   if (h->cg_ws_bytes < need) {
     if (h->cg_ws) cudaFree(h->cg_ws);
     h->cg_ws = nullptr;
@@ -763,8 +943,53 @@ static b200sp_status cg_impl(b200sp_handle h, cudaStream_t st, const b200sp_matr
                                             (int)prm.iteration_limit);
   B200SP_LAUNCH_CHECK(h, "cg_setup_state_kernel");
 
+  CgState<T> *hs = reinterpret_cast<CgState<T> *>(h->pinned_scalars);
+  bool solved = false;
+  if (persistent) {
+    int *fallback = reinterpret_cast<int *>(h->red_counters + 12);
+    B200SP_CUDA(h, cudaMemsetAsync(fallback, 0, sizeof(int), st));
+    CgSmallArgs<T> ka;
+    ka.n = n;
+    ka.rows_per_cta = ceil_div(n, pers_grid);
+    ka.Ap = A->row_offsets;
+    ka.Aj = A->column_indices;
+    ka.Ax = reinterpret_cast<const T *>(A->values);
+    ka.x = x;
+    ka.b = b;
+    ka.r_g = r;
+    ka.p_g0 = p;
+    ka.p_g1 = pwin_b + halo_lo;
+    ka.part_a = partials;
+    ka.part_b = partials + 1024;
+    ka.S = S;
+    ka.residuals = res;
+    ka.fallback = fallback;
+    ka.smem_bytes = (unsigned)pers_smem;
+    auto kern = cg_small_csr_kernel<T>;
+    int resident = 0;
+    bool ok = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pers_smem) == cudaSuccess &&
+              cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, CGS_BLOCK, pers_smem) == cudaSuccess && resident >= 1;
+    if (ok) {
+      void *kargs[] = {&ka};
+      ok = cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)pers_grid), dim3(CGS_BLOCK), kargs, pers_smem, st) ==
+           cudaSuccess;
+    }
+    if (!ok) {
+      cudaGetLastError();  // not launchable here (MPS / MIG limits, co-residency): the ordinary path below
+    } else {
+      h->launches++;
+      int fb = 0;
+      B200SP_CUDA(h, cudaMemcpyAsync(hs, S, sizeof(CgState<T>), cudaMemcpyDeviceToHost, st));
+      B200SP_CUDA(h, cudaMemcpyAsync(&fb, fallback, sizeof(int), cudaMemcpyDeviceToHost, st));
+      B200SP_CUDA(h, cudaStreamSynchronize(st));
+      solved = fb == 0 && hs->done;
+    }
+  }
+
   // y = A x0 ; r = b - y ; p = r ; rz = <r,r>
-  if (dist) {
+  if (solved) {
+    // nothing to set up: the persistent kernel has run the whole solve
+  } else if (dist) {
     // x0 needs its own halo: reuse the p window as staging
     B200SP_CUDA(h, cudaMemcpyAsync(p, x, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st));
     s = comm_halo_exchange(h, st, pwin, n, halo_lo, halo_hi, sizeof(T));
@@ -774,7 +999,8 @@ static b200sp_status cg_impl(b200sp_handle h, cudaStream_t st, const b200sp_matr
     s = spmv_any<T>(h, st, A, x, y, 0, cfg, nullptr, nullptr);
   }
   if (s != B200SP_OK) return s;
-  if (dist) {
+  if (solved) {
+  } else if (dist) {
     cg_init_kernel<T, true><<<(unsigned)g, CG_BLOCK, 0, st>>>(n, b, y, r, p, S, partials, ticket, res);
     B200SP_LAUNCH_CHECK(h, "cg_init_kernel");
     s = comm_allreduce_sum(h, st, &S->rz, 1, sizeof(T) == 8);
@@ -786,14 +1012,15 @@ static b200sp_status cg_impl(b200sp_handle h, cudaStream_t st, const b200sp_matr
     B200SP_LAUNCH_CHECK(h, "cg_init_kernel");
   }
 
-  CgState<T> *hs = reinterpret_cast<CgState<T> *>(h->pinned_scalars);
   auto poll = [&]() -> b200sp_status {
     B200SP_CUDA(h, cudaMemcpyAsync(hs, S, sizeof(CgState<T>), cudaMemcpyDeviceToHost, st));
     B200SP_CUDA(h, cudaStreamSynchronize(st));
     return B200SP_OK;
   };
-  s = poll();
-  if (s != B200SP_OK) return s;
+  if (!solved) {
+    s = poll();
+    if (s != B200SP_OK) return s;
+  }
 
   const i64 gdir = ceil_div(n, (i64)CG_BLOCK * CG_UNROLL);
 
@@ -870,7 +1097,7 @@ static b200sp_status cg_impl(b200sp_handle h, cudaStream_t st, const b200sp_matr
     return fs;
   };
   const char *graph_env = getenv("B200SP_CG_GRAPH");
-  bool use_graph = !dist && (graph_env ? graph_env[0] != '0' : n <= ((i64)1 << 22));
+  bool use_graph = !solved && !dist && (graph_env ? graph_env[0] != '0' : n <= ((i64)1 << 22));
   int graph_iters = prm.check_interval;
   cudaGraphExec_t graph_exec = nullptr;
   cudaStream_t run_st = st;

@@ -603,6 +603,16 @@ static void coo_defaults(b200sp_cfg &c, b200sp_handle h, cudaStream_t st, i64 nn
       c.unroll = many ? 2 : 1;
       c.ctas_per_sm = many ? 8 : 0;
       return;
+    } else if (big && cls == 2 && no_shape && vec32_ok) {
+      // consecutive entries gather neighbouring columns (a HYB tail with one entry per row): warp tiles with 128-bit
+      // loads and two units per warp — poisson7pt 256^3 forced to K = 6: whole HYB product 0.253 / 0.361 ms (fp32 /
+      // fp64) against 0.275 / 0.392 with the shared-memory scan (tools/hyb_probe.py)
+      c = b200sp_cfg{};
+      c.kernel = B200SP_K_COO_WARP;
+      c.block_size = 256;
+      c.vector_width = 4;
+      c.unroll = 2;
+      return;
     } else {
       c.kernel = B200SP_K_COO_SEGSCAN;
     }

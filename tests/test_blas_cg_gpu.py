@@ -190,6 +190,7 @@ def test_cg_graph_replay_is_the_same_solve(fmt, dev, monkeypatch):
     Ad = upload(fmt, A, dev)
     b = tdev(np.random.default_rng(2).uniform(-1, 1, A["num_rows"]), dev)
     out = {}
+    monkeypatch.setenv("B200SP_CG_PERSISTENT", "0")  # (CSR would otherwise take the one-kernel solve in both modes)
     for mode in ("0", "1"):
         monkeypatch.setenv("B200SP_CG_GRAPH", mode)
         for ci in (1, 7, 16):
@@ -237,3 +238,66 @@ def test_cg_two_kernel_iteration_is_the_same_solve(grid, ndt, tdt, dev, monkeypa
         cusp.krylov.cg(Ad, x, b, mon, check_interval=8)
         res[fuse] = (mon.iteration_count(), list(mon.residuals), x.clone())
     assert res["0"][0] == 11 and res["1"][0] == 11 and res["0"][1] == res["1"][1] and torch.equal(res["0"][2], res["1"][2])
+
+
+@pytest.mark.parametrize("ndt,tdt", [(np.float32, torch.float32), (np.float64, torch.float64)])
+@pytest.mark.parametrize("grid", [(10, 10), (37, 29), (512, 512), (20, 18, 16)])
+def test_cg_persistent_kernel_is_the_same_iteration(grid, ndt, tdt, dev, monkeypatch):
+    """small CSR systems on one GPU run as ONE persistent cooperative kernel (cg_small_csr_kernel: matrix slice and
+    vectors in shared memory, two grid barriers per iteration).  Same expressions per element, dot products grouped by
+    CTA instead of by 1024-element blocks: same iteration count, history and solution to rounding, the oracle's
+    history to the usual bar; limit, poll interval and x0 != 0 behave like the ordinary path"""
+    A = O.poisson(5 if len(grid) == 2 else 7, grid, ndt, "csr")
+    n = A["num_rows"]
+    Ad = upload("csr", A, dev)
+    rng = np.random.default_rng(8)
+    bn = rng.uniform(-1, 1, n).astype(ndt)
+    x0 = rng.uniform(-1, 1, n).astype(ndt)
+    b = tdev(bn, dev)
+    rel = 1e-4 if ndt == np.float32 else 1e-9
+    limit = 60 if n > 100000 else 400
+    got = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("B200SP_CG_PERSISTENT", mode)
+        x = tdev(x0, dev)
+        mon = cusp.monitor(b, limit, rel)
+        launches = cusp.default_handle().launch_count
+        cusp.krylov.cg(Ad, x, b, mon, check_interval=7)
+        got[mode] = (mon.iteration_count(), np.asarray(mon.residuals), x.cpu().numpy(), mon.converged(),
+                     cusp.default_handle().launch_count - launches)
+    a, p = got["0"], got["1"]
+    assert p[4] <= 4, p[4]  # ||b||, the state set-up and ONE kernel for the whole solve
+    assert a[4] >= 3 * a[0]
+    assert p[0] == a[0] and p[3] == a[3] and len(p[1]) == len(a[1]), (p[0], a[0])
+    tol = 1e-3 if ndt == np.float32 else 1e-9
+    assert np.allclose(p[1], a[1], rtol=tol, atol=0), np.max(np.abs(p[1] - a[1]) / a[1])
+    assert np.allclose(p[2], a[2], rtol=0, atol=(1e-3 if ndt == np.float32 else 1e-8) * np.abs(a[2]).max())
+    xo, it, conv, hist = O.cg(A, x0, bn, limit, rel)
+    if ndt == np.float64 and n < 100000:
+        assert p[0] == it and np.allclose(p[1], hist, rtol=1e-9)
+
+
+def test_cg_persistent_kernel_falls_back_when_a_slice_does_not_fit(dev, monkeypatch):
+    """the host checks the mean slice, the kernel every slice: a block of heavy rows that overflows one CTA's shared
+    memory raises the fallback flag and the solve takes the ordinary path — same bits as with the kernel turned off"""
+    import scipy.sparse as sp
+    n, heavy, width = 20000, 135, 2000
+    rows = np.repeat(np.arange(heavy), width)
+    cols = np.tile(np.arange(width), heavy)
+    B = sp.coo_matrix((np.full(rows.size, 1e-3), (rows, cols)), shape=(n, n)).tocsr()
+    M = (B + B.T + sp.identity(n) * 10.0).tocsr()
+    M.sum_duplicates()
+    M.sort_indices()
+    A = {"format": "csr", "num_rows": n, "num_cols": n, "num_entries": int(M.nnz), "row_offsets": M.indptr.astype(np.int32),
+         "column_indices": M.indices.astype(np.int32), "values": M.data.astype(np.float64)}
+    Ad = upload("csr", A, dev)
+    b = tdev(np.random.default_rng(1).uniform(-1, 1, n), dev)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("B200SP_CG_PERSISTENT", mode)
+        x = torch.zeros_like(b)
+        mon = cusp.monitor(b, 50, 1e-10)
+        cusp.krylov.cg(Ad, x, b, mon)
+        out[mode] = (mon.iteration_count(), list(mon.residuals), x.clone(), mon.converged())
+    assert out["0"][3] and out["0"][0] >= 2
+    assert out["1"][0] == out["0"][0] and out["1"][1] == out["0"][1] and torch.equal(out["1"][2], out["0"][2])

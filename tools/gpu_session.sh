@@ -47,6 +47,28 @@ d=json.loads(open('$O/${TAG}_dia_run$run.json').read().strip().splitlines()[-1])
 import json
 d=json.loads(open('$O/${TAG}_cg_shape.json').read().strip().splitlines()[-1]); print('fused cg shape=$shape', d['cg']['ms_per_iter'], d['parity']['cg_ok'])"
       done ;;
+    smallcg)
+      python - > $O/${TAG}_smallcg.log 2>&1 <<'PY'
+import os, time, torch
+import cusp_autotuned_b200 as cusp
+from cusp_autotuned_b200 import gallery
+h = cusp.default_handle()
+dev = torch.device("cuda", 0)
+for grid in ((512, 512), (256, 256), (128, 128)):
+    M = gallery.poisson("csr", 5, grid, dtype=torch.float64)
+    n = M.num_rows
+    b = torch.ones(n, dtype=torch.float64, device=dev)
+    for env in ({"B200SP_CG_PERSISTENT": "0", "B200SP_CG_GRAPH": "0"}, {"B200SP_CG_PERSISTENT": "0"}, {}):
+        os.environ.pop("B200SP_CG_PERSISTENT", None); os.environ.pop("B200SP_CG_GRAPH", None)
+        os.environ.update(env)
+        for rep in range(2):
+            x = torch.zeros(n, dtype=torch.float64, device=dev)
+            torch.cuda.synchronize(); t = time.perf_counter()
+            r, _ = h.cg(M.descriptor(), x, b, iteration_limit=1024, relative_tolerance=0.0, check_interval=128, want_residuals=False)
+            torch.cuda.synchronize(); dt = time.perf_counter() - t
+        print(grid, env, "us/iter", round(dt / max(1, int(r.iteration_count)) * 1e6, 2), "iters", int(r.iteration_count), "res", r.residual_norm)
+PY
+      echo "smallcg rc=$?"; cat $O/${TAG}_smallcg.log ;;
     hybprobe)
       timeout 600 python tools/hyb_probe.py > $O/${TAG}_hyb_probe.json 2> $O/${TAG}_hyb_probe.err; echo "hyb probe rc=$?"; cat $O/${TAG}_hyb_probe.json; tail -3 $O/${TAG}_hyb_probe.err ;;
     widen)
