@@ -259,7 +259,7 @@ void TestKttSearcherAndStopCondition() {
   ASSERT_TRUE(quarter.size() >= all.size() / 4 && quarter.size() <= all.size() / 4 + 1);
   cusp::ktt::reset_tuning(A, x, y);
   auto timed = cusp::ktt::tune(A, x, y, std::nullopt, std::make_unique<::ktt::TuningDuration>(0.0));
-  ASSERT_EQUAL(timed.size(), (size_t)1);
+  ASSERT_TRUE(timed.size() <= 1);  // a budget that is spent before (or right after) the first configuration
   cusp::ktt::reset_tuning(A, x, y);
   auto fast = cusp::ktt::tune(A, x, y, std::nullopt, std::make_unique<::ktt::ConfigurationDuration>(1000.0));
   ASSERT_EQUAL(fast.size(), (size_t)1);
