@@ -69,6 +69,20 @@ for grid in ((512, 512), (256, 256), (128, 128)):
         print(grid, env, "us/iter", round(dt / max(1, int(r.iteration_count)) * 1e6, 2), "iters", int(r.iteration_count), "res", r.residual_norm)
 PY
       echo "smallcg rc=$?"; cat $O/${TAG}_smallcg.log ;;
+    nculist)
+      python bench.py --quick --steps 20 --warmup 3 > $O/${TAG}_quick.json 2> $O/${TAG}_quick.err && \
+      ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches_bench_quick.csv \
+          python bench.py --quick --steps 20 --warmup 3 > $O/${TAG}_ncu_quick.log 2>&1; echo "ncu bench list rc=$?"
+      python tools/prof_kernels.py cg > $O/${TAG}_cgplain.log 2>&1 && \
+      ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/${TAG}_launches_cg.csv \
+          python tools/prof_kernels.py cg > $O/${TAG}_ncu_cg_list.log 2>&1; echo "ncu cg list rc=$?" ;;
+    refcoo)
+      REF_COO=full timeout 1500 python tools/ref_gpu_kernels.py 256 8 > $O/${TAG}_ref_kernels.json 2> $O/${TAG}_ref_kernels.err; echo "refcoo rc=$?"
+      python -c "
+import json
+d=json.loads(open('$O/${TAG}_ref_kernels.json').read().strip().splitlines()[-1]); c=d['coo']
+print({k: c[k] for k in c if k not in ('reference_top','invalid')}); print([ (r['cfg'], round(r['ms'],4)) for r in c['reference_top'][:6]]); print(c['invalid'][:3])"
+      tail -3 $O/${TAG}_ref_kernels.err ;;
     hybprobe)
       timeout 600 python tools/hyb_probe.py > $O/${TAG}_hyb_probe.json 2> $O/${TAG}_hyb_probe.err; echo "hyb probe rc=$?"; cat $O/${TAG}_hyb_probe.json; tail -3 $O/${TAG}_hyb_probe.err ;;
     widen)

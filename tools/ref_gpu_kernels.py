@@ -93,8 +93,98 @@ def main():
                                "engine_speedup_over_reference_best": (best["ms"] / ours_ms) if best else None,
                                "valid_configs": len(good), "all": recs}
         del A, x, y, y_ours, scale
+    coo_mode = os.environ.get("REF_COO", "top")  # full: every point; top: the fastest points of the committed full sweep; off
+    if coo_mode != "off":
+        out["coo"] = coo_leg(torch, cusp, h, dev, reps, coo_mode)
     print(json.dumps(out))
     return 0
+
+
+def coo_leg(torch, cusp, h, dev, reps, mode):
+    """configs[2]: the reference's KTT COO kernels (cusp/system/cuda/ktt/kernels/coo_kernel.h, unmodified, every
+    compilable point of coo_multiply.h:22-54) on R-MAT scale 24 fp32 beside the engine's default and planned products.
+    A reference product = its launcher's two kernels (zero_output + coo_spmv)."""
+    from cusp_autotuned_b200 import capi, convert
+    path = os.path.join(ROOT, "oracle", "_ref", "libcuspref_gpu_coo.so")
+    if not os.path.exists(path):
+        return {"unavailable": "oracle/_ref/libcuspref_gpu_coo.so not built"}
+    lib = C.CDLL(path)
+    lib.cuspref_coo_spmv_f32.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_void_p]
+    scale_log2 = int(os.environ.get("REF_COO_RMAT_SCALE", "24"))
+    A = convert.rmat(scale_log2, 16, seed=42, dtype=torch.float32)
+    n, nnz = A.num_rows, A.num_entries
+    x = torch.rand(n, dtype=torch.float32, device=dev) + 0.5
+    y_ours = torch.empty(n, dtype=torch.float32, device=dev)
+    y = torch.empty(n, dtype=torch.float32, device=dev)
+    d = A.descriptor()
+    h.spmv(d, x, y_ours)  # positive data: sum |a x| = y
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    B = nnz * 12 + 2 * n * 4
+
+    def timed(fn, k):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / k
+
+    k = max(3, reps // 4)
+    ours_ms = timed(lambda: h.spmv(d, x, y_ours), k)
+    plan = h.coo_plan_create(n, n, nnz, A.row_indices, A.column_indices, capi.F32, 0)
+    h.coo_plan_attach(plan)
+    planned_ms = timed(lambda: h.spmv(d, x, y), k)
+    planned_ok = bool(torch.equal(y, y_ours) or float(((y - y_ours).abs() / y_ours.clamp_min(1e-30)).max().item()) <= 1e-5)
+    h.coo_plan_detach(plan)
+    h.coo_plan_destroy(plan)
+    ncfg = lib.cuspref_coo_num_configs()
+    names = ("BLOCK_SIZE", "VALUES_PER_THREAD", "IMPL", "USE_CARRY", "AVOID_ATOMIC", "SPECIAL_LOADS")
+    # mode "top" (what bench.py runs, bounded time): only the 12 fastest points of the committed full sweep
+    # (profiles/r03_ref_coo_kernels.json, made by REF_COO=full); without that file every 16th point
+    selected = None
+    if mode == "top":
+        try:
+            sweep = json.load(open(os.path.join(ROOT, "profiles", "r03_ref_coo_kernels.json")))
+            selected = [tuple(r["cfg"][k] for k in names) for r in sweep["coo"]["reference_top"]][:12]
+        except Exception:
+            selected = None
+    recs = []
+    for cfg in range(ncfg):
+        p = (C.c_int * 6)()
+        lib.cuspref_coo_config(cfg, p)
+        if mode == "top" and ((selected is not None and tuple(p) not in selected) or (selected is None and cfg % 16)):
+            continue
+
+        def run():
+            return lib.cuspref_coo_spmv_f32(cfg, A.row_indices.data_ptr(), A.column_indices.data_ptr(), A.values.data_ptr(), nnz,
+                                            x.data_ptr(), y.data_ptr(), n, st)
+        y.fill_(float("nan"))
+        rc = run()
+        torch.cuda.synchronize()
+        rec = {"cfg": dict(zip(names, list(p)))}
+        if rc != 0:
+            rec["error"] = f"cudaError {rc}"
+            recs.append(rec)
+            continue
+        err = float(((y - y_ours).abs() / y_ours.clamp_min(1e-30)).max().item())
+        rec["scaled_err_vs_engine"] = err
+        rec["ok"] = bool(err <= 1e-4)  # atomics / regrouped fp32 sums over hub rows of 10^5 entries
+        if rec["ok"]:
+            rec["ms"] = timed(run, 3)
+        recs.append(rec)
+    good = [r for r in recs if r.get("ok")]
+    best = min(good, key=lambda r: r["ms"]) if good else None
+    good.sort(key=lambda r: r["ms"])
+    return {"workload": f"R-MAT scale {scale_log2} ef 16 fp32 COO, y = A x", "bytes": B, "configs": ncfg, "valid_configs": len(good),
+            "engine_default_ms": ours_ms, "engine_planned_ms": planned_ms, "engine_planned_matches": planned_ok,
+            "mode": mode, "timed_configs": len(recs), "reference_best": best, "reference_top": good[:16],
+            "engine_speedup_over_reference_best": (best["ms"] / ours_ms) if best else None,
+            "planned_speedup_over_reference_best": (best["ms"] / planned_ms) if best else None,
+            "invalid": [r for r in recs if not r.get("ok")][:8]}
 
 
 if __name__ == "__main__":
