@@ -513,7 +513,8 @@ static b200sp_status spmv_host_pipelined_dia(b200sp_handle h, cudaStream_t st, c
     lo = o < -lo ? -(i64)o : lo;  // lo = max(0, -min_off)
     up = o > up ? (i64)o : up;    // up = max(0, max_off)
   }
-  const int want_chunks = 16;
+  int want_chunks = 16;
+  if (const char *e = getenv("B200SP_HOST_CHUNKS")) want_chunks = atoi(e) >= 3 ? atoi(e) : want_chunks;
   i64 chunk = ((ceil_div(rows, (i64)want_chunks) + 1023) / 1024) * 1024;
   if (chunk < lo + 1024 || chunk < up + 1024) return B200SP_OK;  // band wider than a chunk: nothing to overlap
   const int nch = (int)ceil_div(rows, chunk);

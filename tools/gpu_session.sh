@@ -83,6 +83,13 @@ import json
 d=json.loads(open('$O/${TAG}_ref_kernels.json').read().strip().splitlines()[-1]); c=d['coo']
 print({k: c[k] for k in c if k not in ('reference_top','invalid')}); print([ (r['cfg'], round(r['ms'],4)) for r in c['reference_top'][:6]]); print(c['invalid'][:3])"
       tail -3 $O/${TAG}_ref_kernels.err ;;
+    e2eab)
+      for ch in 16 32 64; do for aff in 0 1; do
+        B200SP_HOST_CHUNKS=$ch B200SP_BENCH_AFFINITY=$aff timeout 300 python bench.py --quick --steps 50 > $O/${TAG}_e2e.json 2> $O/${TAG}_e2e.err
+        python -c "
+import json
+d=json.loads(open('$O/${TAG}_e2e.json').read().strip().splitlines()[-1]); print('chunks=$ch affinity=$aff', d['e2e']['ms_per_step'], d['e2e'].get('host_affinity'), d['parity'])"
+      done; done ;;
     hybprobe)
       timeout 600 python tools/hyb_probe.py > $O/${TAG}_hyb_probe.json 2> $O/${TAG}_hyb_probe.err; echo "hyb probe rc=$?"; cat $O/${TAG}_hyb_probe.json; tail -3 $O/${TAG}_hyb_probe.err ;;
     widen)
