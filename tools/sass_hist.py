@@ -10,7 +10,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "cusp_autotuned_b200", "libb200sp.so")
 PAT = re.compile(sys.argv[1]) if len(sys.argv) > 1 else re.compile(
-    r"dia_bulk_kernel<double, 128, 2>|ell_bulk_kernel<double, 256, 1>|csr_ring_kernel<double, 256, 8>|coo_ring_kernel<double, 512, 7>|"
+    r"dia_bulk_kernel<double, 128, 2, (false|true)>|cg_small_csr_kernel<double>|cg_update_push_p2p_kernel<double>|"
+    r"ell_bulk_kernel<double, 256, 1>|csr_ring_kernel<double, 256, 8>|coo_ring_kernel<double, 512, 7>|"
     r"coo_warp_kernel<float, 256, 4, 8, 1, 0, 0, false|coo_warp_kernel<float, 1024, 1, 8, 1, 0, 1, true|coo_segscan_kernel<float, 256, 7, false>|"
     r"cg_update_kernel<double, false>|cg_update_p2p_kernel<double>|cg_direction_p2p_kernel<double>|allgather_push_kernel|csr_vector_kernel<float, 256, 8, 1>")
 KEEP = re.compile(r"^(UBLKCP|SYNCS|LDG|STG|LDS|STS|SHFL|BAR|VOTE|MATCH|ATOM|RED|LDGSTS|UTMA|CCTL|MEMBAR|FENCE|ERRBAR|ACQBULK|DEPBAR|NANOSLEEP|LD\.|ST\.)")
