@@ -96,6 +96,8 @@ struct b200sp_context {
   std::map<CsrKey, int> csr_max_row;
   // COO gather-order probe per (column_indices pointer, element size, nnz): 1 = ring kernel
   std::map<CsrKey, int> coo_gather_order;
+  // longest ELL row range a COO-tail tile would own in the fused HYB kernel, per (row_indices, rows*4096+tile, nnz)
+  std::map<CsrKey, long long> hyb_tile_range;
   std::vector<void *> tune_events;  // cudaEvent_t pair
   std::vector<void *> coo_plans;    // attached b200sp_coo_plan (spmv_coo_plan.cu)
   // set by the CG driver around its iteration: the DIA bulk kernel is launched with programmatic stream

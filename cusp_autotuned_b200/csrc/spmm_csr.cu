@@ -11,6 +11,8 @@
 // (ld.global.nc) with 8 gathers in flight per lane.  Blocks wider than 32 columns are processed
 // in column chunks of 32.  No shared memory (the reference stages the entries there).
 // Algorithmic bytes: (rows+1)*4 + nnz*(4+V) + cols*k*V + rows*k*V.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200sp {
@@ -120,6 +122,259 @@ static b200sp_status launch_spmm(b200sp_handle h, cudaStream_t st, const SpmmArg
   return B200SP_OK;
 }
 
+
+// ---------------------------------------------------------------------------
+// csr_spmm_ring_kernel — the block product on the persistent bulk-copy ring of K_CSR_RING.
+//
+// The one-shot kernel above spends its time issuing instructions, not moving bytes: ncu on poisson7pt 256^3, k = 32
+// (profiles/r04_spmm.md) shows 23 warp instructions per stored entry, issue slots 64 % busy, DRAM 18 %, L1TEX 44 %.
+// Two changes here:
+//   * the matrix streams are decoupled from the gathers: persistent CTAs of 256 consumer threads + one producer
+//     warp; tiles of R consecutive rows; per tile the producer warp writes the tile's R+1 row offsets into the stage
+//     (prefetched one tile ahead in registers) and its first lane issues two cp.async.bulk copies of the tile's
+//     contiguous [Ap[r0], Ap[r0+R)) range of Aj / Ax (L2 evict-first), up to `stages` chunks ahead;
+//   * a lane owns V adjacent columns of the block (V = 4 fp32 / 2 fp64: one 128-bit ld.global.nc per entry and lane,
+//     one 128-bit store of Y), so a sub-warp of K = k / V lanes covers a row and a warp works on 32 / K rows at
+//     once: index, address and shared-memory instructions are shared by V columns.  Blocks whose width, leading
+//     dimensions or base addresses do not allow 16-byte accesses run the same kernel with V = 1.
+// Entry order per (row, column) is storage order: bit-identical to the host loop.  A tile with more entries than a
+// stage becomes several chunks; a row that continues in the next chunk parks its partial sums in Y (the same thread
+// picks them up again).
+// ---------------------------------------------------------------------------
+constexpr int SPMM_BLOCK = 256;
+constexpr int SPMM_CAP = 2048;           // entries per stage
+constexpr int SPMM_STR = SPMM_CAP + 16;  // stage stride: alignment shift + read-ahead slack
+constexpr int SPMM_OSTR = 264;           // row offsets per stage (R + 1 <= 257)
+
+template <typename T, int V>
+struct BlockVec {
+  T v[V];
+};
+template <typename T, int V>
+__device__ __forceinline__ BlockVec<T, V> ldv_ro(const T *p) {
+  BlockVec<T, V> r;
+  if constexpr (V == 1) {
+    r.v[0] = ld_ro(p);
+  } else if constexpr (sizeof(T) == 4 && V == 2) {
+    asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(r.v[0]), "=f"(r.v[1]) : "l"(p));
+  } else if constexpr (sizeof(T) == 4) {
+    static_assert(V == 4, "fp32: two or four columns per lane");
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p));
+  } else {
+    static_assert(V == 2, "fp64: two columns per lane");
+    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(r.v[0]), "=d"(r.v[1]) : "l"(p));
+  }
+  return r;
+}
+template <typename T, int V>
+__device__ __forceinline__ BlockVec<T, V> ldv(const T *p) {  // coherent load (Y: partial sums parked by this thread)
+  BlockVec<T, V> r;
+  if constexpr (V == 1) r.v[0] = *p;
+  else if constexpr (sizeof(T) == 4 && V == 2) {
+    const float2 t = *reinterpret_cast<const float2 *>(p);
+    r.v[0] = t.x; r.v[1] = t.y;
+  } else if constexpr (sizeof(T) == 4) {
+    const float4 t = *reinterpret_cast<const float4 *>(p);
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else {
+    const double2 t = *reinterpret_cast<const double2 *>(p);
+    r.v[0] = t.x; r.v[1] = t.y;
+  }
+  return r;
+}
+template <typename T, int V>
+__device__ __forceinline__ void stv(T *p, const BlockVec<T, V> &r) {
+  if constexpr (V == 1) *p = r.v[0];
+  else if constexpr (sizeof(T) == 4 && V == 2) *reinterpret_cast<float2 *>(p) = make_float2(r.v[0], r.v[1]);
+  else if constexpr (sizeof(T) == 4) *reinterpret_cast<float4 *>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  else *reinterpret_cast<double2 *>(p) = make_double2(r.v[0], r.v[1]);
+}
+
+template <typename T, int K, int V>
+__global__ void __launch_bounds__(SPMM_BLOCK + 32, 2) csr_spmm_ring_kernel(SpmmArgs<T> a, int R, int stages,
+                                                                            i64 num_tiles, i64 nnz) {
+  constexpr int BLOCK = SPMM_BLOCK, CAP = SPMM_CAP, STR = SPMM_STR, OSTR = SPMM_OSTR;
+  constexpr int EPV = 16 / (int)sizeof(T);
+  constexpr int G = 8;           // gathers in flight per lane
+  constexpr int SW = BLOCK / K;  // rows in flight per CTA
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T *s_val = reinterpret_cast<T *>(smem_raw);
+  int *s_col = reinterpret_cast<int *>(smem_raw + (size_t)stages * STR * sizeof(T));
+  int *s_off = s_col + (size_t)stages * STR;
+  uint64_t *full = reinterpret_cast<uint64_t *>(s_off + (size_t)stages * OSTR);
+  uint64_t *empty = full + stages;
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], BLOCK / 32);
+    }
+    mbar_fence_init();
+  }
+  // read-ahead slots must hold valid columns from the first tile on
+  for (int i = tid; i < stages * STR; i += BLOCK + 32) s_col[i] = 0;
+  __syncthreads();
+
+  const i64 rows = a.rows;
+  if (tid >= BLOCK) {
+    // ------------------------------ producer warp ---------------------------
+    const int pl = tid - BLOCK;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const uint64_t pol = l2_policy_evict_first();
+    const int nnz_c = (int)nnz & ~3, nnz_v = (int)nnz & ~(EPV - 1);  // last 16-byte-complete entry
+    constexpr int OQ = (SPMM_BLOCK + 1 + 31) / 32;                   // offsets held per lane
+    int off[OQ], noff[OQ];
+    int s = 0, s0 = 0, s1 = 0;
+    uint32_t ph = 0;
+    i64 tile = blockIdx.x;
+    if (tile < num_tiles) {
+      const i64 r0 = tile * R;
+      const int nr = (int)min((i64)R, rows - r0);
+#pragma unroll
+      for (int q = 0; q < OQ; ++q) off[q] = (pl + 32 * q <= nr) ? ld_ro(a.Ap + r0 + pl + 32 * q) : 0;
+      s0 = ld_ro(a.Ap + r0);
+      s1 = ld_ro(a.Ap + r0 + nr);
+    }
+    while (tile < num_tiles) {
+      const int nr = (int)min((i64)R, rows - tile * R);
+      const i64 next = tile + gridDim.x;
+      int n0 = 0, n1 = 0;
+#pragma unroll
+      for (int q = 0; q < OQ; ++q) noff[q] = 0;
+      if (next < num_tiles) {  // the next tile's offsets: in flight while this tile is issued
+        const i64 r0 = next * R;
+        const int nnr = (int)min((i64)R, rows - r0);
+#pragma unroll
+        for (int q = 0; q < OQ; ++q) noff[q] = (pl + 32 * q <= nnr) ? ld_ro(a.Ap + r0 + pl + 32 * q) : 0;
+        n0 = ld_ro(a.Ap + r0);
+        n1 = ld_ro(a.Ap + r0 + nnr);
+      }
+      int lo = s0;
+      do {  // at least one chunk per tile (its offsets travel with it), also when the tile has no entries
+        const int hi = (s1 - lo > CAP) ? lo + CAP : s1;
+        mbar_wait(&empty[s], ph ^ 1);
+        int *so = s_off + (size_t)s * OSTR;
+#pragma unroll
+        for (int q = 0; q < OQ; ++q)
+          if (pl + 32 * q <= nr) so[pl + 32 * q] = off[q];
+        __syncwarp();
+        if (pl == 0) {
+          int *dc = s_col + (size_t)s * STR;
+          T *dv = s_val + (size_t)s * STR;
+          const int ga_c = lo & ~3, ga_v = lo & ~(EPV - 1);
+          const int end_c = min((hi + 3) & ~3, nnz_c), end_v = min((hi + EPV - 1) & ~(EPV - 1), nnz_v);
+          // the (at most 3) entries after the last complete 16 bytes of the arrays
+          for (int j = max(end_c, ga_c); j < hi; ++j) dc[j - ga_c] = a.Aj[j];
+          for (int j = max(end_v, ga_v); j < hi; ++j) dv[j - ga_v] = a.Ax[j];
+          const int bc = (hi > lo) ? max(end_c - ga_c, 0) : 0, bv = (hi > lo) ? max(end_v - ga_v, 0) : 0;
+          mbar_expect_tx(&full[s], (uint32_t)(bc * sizeof(int) + bv * sizeof(T)));
+          if (bc > 0) bulk_g2s(dc, a.Aj + ga_c, (uint32_t)(bc * sizeof(int)), &full[s], pol);
+          if (bv > 0) bulk_g2s(dv, a.Ax + ga_v, (uint32_t)(bv * sizeof(T)), &full[s], pol);
+        }
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1;
+        }
+        lo = hi;
+      } while (lo < s1);
+      tile = next;
+      s0 = n0;
+      s1 = n1;
+#pragma unroll
+      for (int q = 0; q < OQ; ++q) off[q] = noff[q];
+    }
+  } else {
+    // ------------------------------ consumers -------------------------------
+    const int lane = tid & (K - 1), sub = tid / K;
+    const bool col_ok = lane * V < a.k;  // vector mode: k % V == 0, so a lane's columns are all in or all out
+    const T *Xl = a.X + (col_ok ? lane * V : 0);
+    int s = 0;
+    uint32_t ph = 0;
+    for (i64 tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const i64 r0 = tile * R;
+      const int nr = (int)min((i64)R, rows - r0);
+      int lo = -1, s1 = 0;
+      do {
+        mbar_wait(&full[s], ph);
+        const int *offs = s_off + (size_t)s * OSTR;
+        if (lo < 0) lo = offs[0];
+        s1 = offs[nr];
+        const int hi = (s1 - lo > CAP) ? lo + CAP : s1;
+        const bool last = hi == s1;
+        const int *pc = s_col + (size_t)s * STR + (lo & 3) - lo;  // pc[j], absolute entry index j
+        const T *pv = s_val + (size_t)s * STR + (lo & (EPV - 1)) - lo;
+        T keep = T(0);
+        for (int i = sub; i < nr; i += SW) {
+          const int B = offs[i], E = offs[i + 1];
+          const bool first = B >= lo && (B < hi || last);  // the chunk that initialises the row
+          if (!(first || (B < hi && E > lo))) continue;    // the row has nothing in this chunk
+          const int b = max(B, lo), e = min(E, hi);
+          T *yp = a.Y + (r0 + i) * a.ldy + lane * V;
+          BlockVec<T, V> acc;
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc.v[v] = T(0);
+          // partial sums of a row continued from the previous chunk were parked in Y by this thread
+          if (col_ok && (!first || a.accumulate)) acc = ldv<T, V>(yp);
+          for (int jj = b; jj < e; jj += G) {
+            BlockVec<T, V> xv[G];
+#pragma unroll
+            for (int q = 0; q < G; ++q)  // slots past the row's end hold valid columns (next rows / zero fill)
+              xv[q] = ldv_ro<T, V>(Xl + (i64)(unsigned)pc[jj + q] * a.ldx);
+#pragma unroll
+            for (int q = 0; q < G; ++q)
+#pragma unroll
+              for (int v = 0; v < V; ++v) pin(xv[q].v[v]);
+#pragma unroll
+            for (int q = 0; q < G; ++q) {
+              if (jj + q < e) {
+                const T val = pv[jj + q];
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc.v[v] = acc.v[v] + val * xv[q].v[v];
+              }
+            }
+          }
+          if (col_ok) stv<T, V>(yp, acc);
+          keep = keep + acc.v[0];
+        }
+        consume_before_release(keep);
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1;
+        }
+        lo = hi;
+      } while (lo < s1);
+    }
+  }
+}
+
+template <typename T, int K, int V>
+static b200sp_status launch_spmm_ring(b200sp_handle h, cudaStream_t st, const SpmmArgs<T> &a, i64 nnz) {
+  const int stages = 3;
+  const double mean = (double)nnz / (double)a.rows;
+  i64 R = (i64)(0.9 * (double)SPMM_CAP / (mean > 1.0 ? mean : 1.0));
+  constexpr int PASS = SPMM_BLOCK / K;  // rows per pass of the CTA
+  R = (R / PASS) * PASS;
+  if (R < PASS) R = PASS;
+  if (R > SPMM_BLOCK) R = SPMM_BLOCK;
+  const i64 num_tiles = ceil_div(a.rows, R);
+  const size_t smem = (size_t)stages * (SPMM_STR * (sizeof(T) + sizeof(int)) + SPMM_OSTR * sizeof(int)) +
+                      2 * (size_t)stages * sizeof(uint64_t) + 16;
+  auto kern = csr_spmm_ring_kernel<T, K, V>;
+  B200SP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int resident = 0;
+  B200SP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, SPMM_BLOCK + 32, smem));
+  if (resident < 1) return set_error(h, B200SP_INVALID_INPUT, "csr spmm ring: configuration does not fit on an SM");
+  // persistent, one wave; two CTAs per SM leave ~120 KB of the unified array to L1 for the X rows
+  i64 grid = (i64)h->num_sms * (resident < 2 ? resident : 2);
+  if (grid > num_tiles) grid = num_tiles;
+  kern<<<(unsigned)grid, SPMM_BLOCK + 32, smem, st>>>(a, (int)R, stages, num_tiles, nnz);
+  B200SP_LAUNCH_CHECK(h, "csr_spmm_ring_kernel");
+  return B200SP_OK;
+}
+
 template <typename T>
 b200sp_status spmm_csr(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64 nnz, const int *Ap, const int *Aj,
                        const T *Ax, i64 k, const T *X, i64 ldx, T *Y, i64 ldy, int accumulate) {
@@ -136,12 +391,49 @@ b200sp_status spmm_csr(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64
   if (k == 1 && ldx == 1 && ldy == 1)  // a single contiguous column is a vector (csr_block_spmv.h:198-201)
     return spmv_csr<T>(h, st, rows, cols, nnz, Ap, Aj, Ax, X, Y, accumulate, nullptr, nullptr, nullptr);
   const T dummy = T(0);
+  const char *force = getenv("B200SP_SPMM_LDG");  // measurement switch: the one-shot kernel
+  const char *nv = getenv("B200SP_SPMM_NOVEC");  // measurement switch: one column per lane
+  const bool novec = nv && nv[0] == '1';
+  const bool ring = nnz > 0 && aligned16(Aj) && aligned16(Ax) && !(force && force[0] == '1');
   for (i64 c0 = 0; c0 < k; c0 += 32) {  // column chunks of 32
     a.k = (int)((k - c0 < 32) ? k - c0 : 32);
     a.X = X ? X + c0 : &dummy;
     a.Y = Y + c0;
     b200sp_status s;
-    // sub-warp width = block width rounded up to a power of two, 4 rows (2 for 32 lanes) per sub-warp
+    // sub-warp width = block width rounded up to a power of two
+    if (ring) {  // bulk copies need 16-byte-aligned array bases
+      constexpr int VEC = 16 / (int)sizeof(T);  // columns per lane with 128-bit accesses
+      const bool vec = a.k % VEC == 0 && ldx % VEC == 0 && ldy % VEC == 0 && aligned16(a.X) && aligned16(a.Y) && !novec;
+      const bool vec2 = sizeof(T) == 4 && !vec && a.k % 2 == 0 && ldx % 2 == 0 && ldy % 2 == 0 &&
+                        ((uintptr_t)a.X & 7) == 0 && ((uintptr_t)a.Y & 7) == 0 && !novec;  // fp32: 64-bit accesses
+      const int lanes = vec ? a.k / VEC : (vec2 ? a.k / 2 : a.k);
+      if (vec) {
+        if (lanes <= 1) s = launch_spmm_ring<T, 1, VEC>(h, st, a, nnz);
+        else if (lanes <= 2) s = launch_spmm_ring<T, 2, VEC>(h, st, a, nnz);
+        else if (lanes <= 4) s = launch_spmm_ring<T, 4, VEC>(h, st, a, nnz);
+        else if (lanes <= 8) s = launch_spmm_ring<T, 8, VEC>(h, st, a, nnz);
+        else s = launch_spmm_ring<T, 16, VEC>(h, st, a, nnz);
+      } else if (vec2) {
+        if constexpr (sizeof(T) == 4) {
+          if (lanes <= 1) s = launch_spmm_ring<T, 1, 2>(h, st, a, nnz);
+          else if (lanes <= 2) s = launch_spmm_ring<T, 2, 2>(h, st, a, nnz);
+          else if (lanes <= 4) s = launch_spmm_ring<T, 4, 2>(h, st, a, nnz);
+          else if (lanes <= 8) s = launch_spmm_ring<T, 8, 2>(h, st, a, nnz);
+          else s = launch_spmm_ring<T, 16, 2>(h, st, a, nnz);
+        } else {
+          s = B200SP_INVALID_INPUT;
+        }
+      } else {
+        if (lanes <= 2) s = launch_spmm_ring<T, 2, 1>(h, st, a, nnz);
+        else if (lanes <= 4) s = launch_spmm_ring<T, 4, 1>(h, st, a, nnz);
+        else if (lanes <= 8) s = launch_spmm_ring<T, 8, 1>(h, st, a, nnz);
+        else if (lanes <= 16) s = launch_spmm_ring<T, 16, 1>(h, st, a, nnz);
+        else s = launch_spmm_ring<T, 32, 1>(h, st, a, nnz);
+      }
+      if (s != B200SP_OK) return s;
+      continue;
+    }
+    // one-shot LDG kernel: 4 rows (2 for 32 lanes) per sub-warp
     if (a.k <= 2) s = launch_spmm<T, 2, 4>(h, st, a);
     else if (a.k <= 4) s = launch_spmm<T, 4, 4>(h, st, a);
     else if (a.k <= 8) s = launch_spmm<T, 8, 4>(h, st, a);

@@ -712,6 +712,12 @@ b200sp_status spmv_ell(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64
                        const int *cidx, const T *vals, const int *row_lengths, const T *x, T *y,
                        int accumulate, const b200sp_cfg *cfg, const T *dotv, T *dot_result);
 
+// spmv_hyb_fused.cu
+template <typename T>
+b200sp_status spmv_hyb_fused(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64 K, i64 pitch, const int *ecidx,
+                             const T *evals, i64 cnnz, const int *ci, const int *cj, const T *cv, const T *x, T *y,
+                             int accumulate, const b200sp_cfg &c, int *done);
+
 // HYB = ELL pass (init = caller's) then COO pass with identity
 // (cusp/system/detail/sequential/multiply/hyb_spmv.h:35-57)
 template <typename T>
@@ -720,6 +726,25 @@ b200sp_status spmv_hyb(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64
                        const T *cv, const T *x, T *y, int accumulate, const b200sp_cfg *ecfg,
                        const b200sp_cfg *ccfg) {
   B200SP_CHECK_HANDLE(h);
+  if (cnnz > 0 && rows > 0 && rows < (1ll << 31) && cols > 0 && cols < (1ll << 31) && K >= 0 && ci && cj && cv && x && y &&
+      (K == 0 || (ecidx && evals && pitch >= rows)) && (!ecfg || ecfg->kernel == 0) &&
+      (!ccfg || ccfg->kernel == 0 || ccfg->kernel == B200SP_K_COO_WARP)) {
+    // one pass over y (spmv_hyb_fused.cu) when the tail would run the warp-tile kernel anyway, no hot-column plan
+    // is attached to it, and no tile would own a long stretch of tail-free rows
+    const bool planned = !h->coo_plans.empty() && coo_attached_plan(h, rows, cols, cnnz, ci, cj, sizeof(T)) != nullptr;
+    if (!planned) {
+      b200sp_cfg c = ccfg ? *ccfg : b200sp_cfg{};
+      const bool tma_ok = aligned16(ci) && aligned16(cj) && aligned16(cv);
+      const bool vec32_ok = ((((uintptr_t)ci | (uintptr_t)cj | (uintptr_t)cv) & 31) == 0);
+      coo_defaults(c, h, st, cnnz, cj, sizeof(T), tma_ok, vec32_ok);
+      if (c.kernel == B200SP_K_COO_WARP) {
+        int done = 0;
+        b200sp_status s = spmv_hyb_fused<T>(h, st, rows, cols, K, pitch, ecidx, evals, cnnz, ci, cj, cv, x, y, accumulate,
+                                            c, &done);
+        if (s != B200SP_OK || done) return s;
+      }
+    }
+  }
   if (!accumulate && cnnz > 0 && K == 1 && rows > 0) {
     // y = A x with a one-column ELL part (what the reference's split rule gives power-law graphs):
     // tail first (y zeroed, complete rows stored without reading y), then the ELL column

@@ -7,6 +7,8 @@ on the same inputs.  Bars:
     (fp64), on data without cancellation; on cancelling rows the same tol is
     applied against sum_j |a_ij x_j|.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -552,8 +554,10 @@ def test_csr_block_multiply_bit_exact(ndt, tdt, dev):
         A = dict(A)
         A["values"] = (A["values"] * rng.uniform(0.5, 1.5, A["num_entries"])).astype(ndt)
         Ad = upload("csr", A, dev)
-        for k in (1, 2, 3, 4, 7, 8, 16, 31, 32, 33, 70):
-            pad = 0 if k % 2 else 3
+        # pads: 0 / 4 keep 16-byte-aligned rows (a lane owns 4 fp32 / 2 fp64 columns: 128-bit accesses), 3 does not
+        # (one column per lane); k = 12, 24, 64 exercise idle lanes and two column chunks of the vector path
+        for k, pad in [(1, 0), (2, 0), (2, 3), (3, 0), (4, 0), (4, 3), (4, 4), (7, 0), (8, 0), (8, 3), (12, 4), (16, 0),
+                       (16, 3), (24, 0), (31, 0), (32, 0), (32, 3), (32, 4), (33, 0), (64, 0), (70, 3)]:
             Xh = rng.uniform(-1, 1, (A["num_cols"], k + pad)).astype(ndt)
             Y0 = rng.uniform(-1, 1, (A["num_rows"], k + pad)).astype(ndt)
             X = tdev(Xh, dev)[:, :k]
@@ -573,6 +577,19 @@ def test_csr_block_multiply_bit_exact(ndt, tdt, dev):
                         assert scaled_err(got[:, j], want, scale) <= TOL[np.dtype(ndt)], (name, k, j, acc)
                     else:
                         assert np.array_equal(got[:, j], want), (name, k, j, acc)
+    # a block whose base address is not 16-byte aligned (a view one element into a buffer): scalar column path
+    A = mats["rand"]
+    Ad = upload("csr", A, dev)
+    k = 8
+    Xh = rng.uniform(-1, 1, (A["num_cols"], k)).astype(ndt)
+    buf = torch.zeros(A["num_cols"] * k + 1, dtype=tdt, device=dev)
+    buf[1:] = tdev(Xh, dev).reshape(-1)
+    X = buf[1:].view(A["num_cols"], k)
+    Y = torch.empty(A["num_rows"], k, dtype=tdt, device=dev)
+    cusp.multiply_block(Ad, X, Y)
+    got = Y.cpu().numpy()
+    for j in range(k):
+        assert np.array_equal(got[:, j], O.spmv(A, np.ascontiguousarray(Xh[:, j])))
     # degenerate shapes
     e = torch.zeros(0, dtype=tdt, device=dev)
     A0 = cusp.csr_matrix(4, 5, torch.zeros(5, dtype=torch.int32, device=dev), torch.zeros(0, dtype=torch.int32, device=dev), e)
@@ -581,6 +598,86 @@ def test_csr_block_multiply_bit_exact(ndt, tdt, dev):
     assert torch.equal(Y, torch.zeros_like(Y))
     with pytest.raises(capi.InvalidInput):
         cusp.multiply_block(A0, torch.ones(4, 3, dtype=tdt, device=dev), Y)
+
+
+# ---------------------------------------------------------------------------
+# single-pass HYB (spmv_hyb_fused.cu)
+# ---------------------------------------------------------------------------
+def _hyb_direct(h, Ad, xd, yd, acc, coo_cfg, fused):
+    os.environ["B200SP_HYB_FUSED"] = fused
+    try:
+        e, c = Ad.ell, Ad.coo
+        h.spmv_hyb(Ad.num_rows, Ad.num_cols, e.num_cols_per_row, e.pitch, e.column_indices, e.values, c.num_entries,
+                   c.row_indices, c.column_indices, c.values, xd, yd, accumulate=acc, coo_cfg=coo_cfg)
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("B200SP_HYB_FUSED", None)
+
+
+@pytest.mark.parametrize("ndt,tdt", DTYPES)
+def test_hyb_single_pass_equals_two_pass(ndt, tdt, dev, handle):
+    """the fused kernel (ELL rows of a tile's row range, then the tile's tail entries accumulating) adds, per row, the
+    same two values in the same order as ELL launch + COO launch with the same tile shape: bit-identical y on any
+    data, assign and accumulate, every instantiated shape; and within the regrouped-sum bar of the reference's
+    sequential loops (sequential/multiply/hyb_spmv.h:35-57).  Matrices: a stencil split below its row length (one
+    or more tail entries in every row), a random matrix, hub rows spanning many tiles, a tail concentrated in a few
+    rows (tiles that own thousands of tail-free rows), tail-free rows at both ends"""
+    rng = np.random.default_rng(33)
+    cases = []
+    p7 = O.poisson(7, (23, 19, 17), ndt, "coo")
+    cases += [("p7_k6", p7, 6), ("p7_k3", p7, 3)]
+    rnd = O.gallery_random(5000, 4000, 60000, ndt, "coo")
+    cases += [("rand_k4", rnd, 4), ("rand_k1", rnd, 1)]
+    # hubs: rows 10 and 4200 with 20 000 / 3 000 entries on top of a sparse background; rows >= 4500 empty
+    bg = O.gallery_random(4500, 3000, 9000, ndt, "coo")
+    rows_h = np.concatenate([bg["row_indices"], np.full(20000, 10, np.int32), np.full(3000, 4200, np.int32)])
+    cols_h = np.concatenate([bg["column_indices"], rng.integers(0, 3000, 23000).astype(np.int32)])
+    order = np.lexsort((cols_h, rows_h))
+    hub = dict(format="coo", num_rows=6000, num_cols=3000, num_entries=len(rows_h), row_indices=rows_h[order],
+               column_indices=cols_h[order], values=np.ones(len(rows_h), ndt))
+    cases += [("hub_k2", hub, 2), ("hub_k8", hub, 8)]
+    for name, coo, K in cases:
+        coo = dict(coo)
+        coo["values"] = (coo["values"] * rng.uniform(0.5, 1.5, coo["num_entries"])).astype(ndt)
+        A = O.convert(coo, "hyb", num_entries_per_row=K)
+        assert A["coo"]["num_entries"] > 0, name
+        Ad = upload("hyb", A, dev)
+        x = rng.uniform(-1, 1, A["num_cols"]).astype(ndt)
+        y0 = rng.uniform(-1, 1, A["num_rows"]).astype(ndt)
+        xd = tdev(x, dev)
+        scale = O.spmv(abs_matrix(A), np.abs(x))
+        for vw, u in ((4, 1), (4, 2), (8, 1), (8, 2)):
+            cfg = capi.Cfg(kernel=capi.K_COO_WARP, block_size=256, vector_width=vw, unroll=u)
+            for acc in (False, True):
+                y2 = tdev(y0, dev)
+                _hyb_direct(handle, Ad, xd, y2, acc, cfg, "0")
+                y1 = tdev(y0, dev)
+                n0 = handle.launch_count
+                _hyb_direct(handle, Ad, xd, y1, acc, cfg, "2")
+                assert handle.launch_count - n0 == 2, (name, vw, u)  # fused kernel + carry fix-up, nothing else
+                assert torch.equal(y1, y2), (name, vw, u, acc)
+                want = O.spmv(A, x, y0 if acc else None, accumulate=acc)
+                assert scaled_err(y1.cpu().numpy(), want, scale + (np.abs(y0) if acc else 0)) <= TOL[np.dtype(ndt)], (name, vw, u, acc)
+    # the structure hint keeps tails concentrated in a few rows on the two-launch path (a tile there would own
+    # thousands of tail-free rows), and lets a one-entry-per-row tail through
+    big = O.poisson(7, (64, 64, 32), ndt, "coo")
+    Ab = upload("hyb", O.convert(big, "hyb", num_entries_per_row=6), dev)
+    xb = torch.ones(Ab.num_cols, dtype=tdt, device=dev)
+    yb = torch.empty(Ab.num_rows, dtype=tdt, device=dev)
+    cfg = capi.Cfg(kernel=capi.K_COO_WARP, block_size=256, vector_width=4, unroll=2)
+    _hyb_direct(handle, Ab, xb, yb, False, cfg, "1")
+    n0 = handle.launch_count
+    _hyb_direct(handle, Ab, xb, yb, False, cfg, "1")
+    assert handle.launch_count - n0 == 2
+    assert np.array_equal(yb.cpu().numpy(), O.spmv(O.convert(big, "csr"), np.ones(big["num_cols"], ndt)))
+    hubd = upload("hyb", O.convert(dict(hub, values=np.ones(hub["num_entries"], ndt)), "hyb", num_entries_per_row=8), dev)
+    xh = torch.ones(hubd.num_cols, dtype=tdt, device=dev)
+    yh = torch.empty(hubd.num_rows, dtype=tdt, device=dev)
+    _hyb_direct(handle, hubd, xh, yh, False, cfg, "1")
+    n0 = handle.launch_count
+    _hyb_direct(handle, hubd, xh, yh, False, cfg, "1")
+    assert handle.launch_count - n0 > 2  # ELL launch + tail launch + fix-up (+ memset is not a launch)
+    assert np.array_equal(yh.cpu().numpy(), np.bincount(hub["row_indices"], minlength=hub["num_rows"]).astype(ndt))
 
 
 # ---------------------------------------------------------------------------

@@ -12,7 +12,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KERNELS = ("dia_bulk", "ell_bulk", "csr_ring", "coo_ring")
+KERNELS = ("dia_bulk", "ell_bulk", "csr_ring", "coo_ring", "csr_spmm_ring")
 WINDOW = 300  # instructions scanned before each arrive
 
 

@@ -52,4 +52,26 @@ for tdt, es in ((torch.float32, 4), (torch.float64, 8)):
     out["f32" if es == 4 else "f64"] = rec
     del H, x, y, want
     torch.cuda.empty_cache()
+if len(sys.argv) > 1 and sys.argv[1].startswith("rmat"):  # python tools/hyb_probe.py rmat24: the graph operator's HYB
+    sc = int(sys.argv[1][4:] or 24)
+    C = convert.rmat(sc, 16, seed=42, dtype=torch.float32, values="ones")
+    H = convert.csr_to_hyb(convert.coo_to_csr(C))
+    deg = torch.bincount(C.row_indices.long(), minlength=C.num_rows).float()
+    del C
+    x = torch.ones(H.num_cols, dtype=torch.float32, device=dev)
+    y = torch.zeros(H.num_rows, dtype=torch.float32, device=dev)
+    B = compulsory_bytes(H, 4)
+    d = H.descriptor()
+    for _ in range(3):
+        h.spmv(d, x, y)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        h.spmv(d, x, y)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    out[f"rmat_s{sc}"] = {"K": int(H.ell.num_cols_per_row), "tail_nnz": int(H.coo.num_entries), "ms": round(ms, 5),
+                          "frac": round(B / ms / 1e6 / PEAK, 4), "exact": bool(torch.equal(y, deg)),
+                          "fused_env": os.environ.get("B200SP_HYB_FUSED", "1")}
 print(json.dumps(out))

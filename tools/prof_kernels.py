@@ -20,6 +20,18 @@ for fmt in which:
         torch.cuda.synchronize()
         del A, b, xk
         continue
+    if fmt.split(":")[0] == "spmm":  # "spmm:k[:f64]": CSR x dense block on the stencil operator
+        parts = fmt.split(":")
+        k = int(parts[1]) if len(parts) > 1 else 32
+        dt = torch.float64 if (len(parts) > 2 and parts[2] == "f64") else torch.float32
+        A = gallery.poisson("csr", 7, (n, n, n), dtype=dt)
+        X = torch.rand(A.num_cols, k, dtype=dt, device=dev) + 0.5
+        Y = torch.empty(A.num_rows, k, dtype=dt, device=dev)
+        for _ in range(reps):
+            cusp.multiply_block(A, X, Y)
+        torch.cuda.synchronize()
+        del A, X, Y
+        continue
     if fmt.split(":")[0] in ("dia", "ell", "csr"):
         A = gallery.poisson(fmt, 7, (n, n, n), dtype=torch.float64)
         x = ((torch.arange(A.num_cols, device=dev) % 21) - 10).double()
