@@ -90,10 +90,76 @@ __device__ __forceinline__ void coo_store_y(T *y, int row, T val, int accumulate
   y[row] = accumulate ? Ops::reduce(y[row], val) : val;
 }
 
-// One warp, one tile of U * 32 * VPL consecutive entries.
-template <typename T, int VPL, int U, int XPOL, int SPOL, bool TABLE, typename Ops>
+// ---- fused HYB (spmv_hyb_fused.cu): what a COO-tail tile needs to know about the ELL part -----------------------
+template <typename T>
+struct HybEll {
+  const int *cidx;
+  const T *vals;
+  i64 pitch;
+  int K;
+  i64 rows;
+  int accumulate;        // the caller's: y = y + A x
+  int2 *work;            // row ranges without tail entries left to hyb_gap_kernel: [x, y] inclusive
+  unsigned *work_count;  // ranges appended so far
+  unsigned work_cap;
+};
+constexpr int HYB_GAP_INLINE = 8;    // shorter runs of tail-free rows are finished by the lane that meets them
+constexpr int HYB_GAP_CHUNK = 1024;  // longer ones are cut into work items of at most this many rows
+
+// init(y[r]) + the ELL slots of row r in ascending k: the value the ELL kernels leave in y[r]
+template <typename T>
+__device__ __noinline__ T hyb_row_init(const HybEll<T> &e, const T *x, const T *y, unsigned cols, i64 r) {
+  T acc = e.accumulate ? y[r] : T(0);
+  for (int k0 = 0; k0 < e.K; k0 += 4) {
+    int c[4];
+    T v[4], xv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool kin = k0 + k < e.K;
+      const i64 so = (i64)(kin ? k0 + k : k0) * e.pitch + r;
+      c[k] = ld_stream(e.cidx + so);
+      v[k] = ld_stream(e.vals + so);
+      if (!kin) c[k] = -1;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xv[k] = ld_ro(x + min((unsigned)max(c[k], 0), cols - 1));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const T t = acc + v[k] * xv[k];
+      acc = (c[k] != -1) ? t : acc;
+    }
+  }
+  return acc;
+}
+
+// rows [lo, hi] hold no tail entry: finish them here when they are few, otherwise leave them to hyb_gap_kernel
+template <typename T>
+__device__ __noinline__ void hyb_gap(const HybEll<T> &e, const T *x, T *y, unsigned cols, i64 lo, i64 hi) {
+  const i64 len = hi - lo + 1;
+  if (len <= 0) return;
+  if (len >= HYB_GAP_INLINE) {
+    const unsigned n = (unsigned)((len + HYB_GAP_CHUNK - 1) / HYB_GAP_CHUNK);
+    const unsigned base = atomicAdd(e.work_count, n);
+    if (base + n <= e.work_cap) {  // always, by the capacity bound of launch_hyb_warp
+      for (unsigned i = 0; i < n; ++i) {
+        const i64 b = lo + (i64)i * HYB_GAP_CHUNK;
+        e.work[base + i] = make_int2((int)b, (int)min(hi, b + HYB_GAP_CHUNK - 1));
+      }
+      return;
+    }
+    atomicSub(e.work_count, n);
+  }
+  for (i64 r = lo; r <= hi; ++r) y[r] = hyb_row_init(e, x, y, cols, r);
+}
+
+// One warp, one tile of U * 32 * VPL consecutive entries.  HYB (fused HYB kernel only): `owner` tiles finish their
+// rows themselves — a row that ends here is stored as init + ELL slots + tail sum by the lane that sees its end, runs
+// of rows without tail entries between two entries of the tile go to hyb_gap; other tiles accumulate into the y
+// their warp has just initialised (a.accumulate = 1).
+template <typename T, int VPL, int U, int XPOL, int SPOL, bool TABLE, typename Ops, bool HYB = false>
 __device__ __forceinline__ void coo_warp_tile(const CooArgs<T> &a, const i64 tile, const int lane, const T *tab,
-                                              const uint64_t pol) {
+                                              const uint64_t pol, const HybEll<T> *hyb = nullptr,
+                                              const bool owner = false) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int UNIT = 32 * VPL, WT = UNIT * U;
   constexpr int VW = VPL * (int)sizeof(T) / 4;  // 32-bit words of a lane's values
@@ -172,9 +238,13 @@ __device__ __forceinline__ void coo_warp_tile(const CooArgs<T> &a, const i64 til
           head_row = r[u][q];
           has_b = true;
         } else {
-          coo_store_y<T, Ops>(a.y, r[u][q], run, a.accumulate);  // began and ended inside this lane
+          // began and ended inside this lane
+          if (HYB && owner) a.y[r[u][q]] = hyb_row_init(*hyb, a.x, a.y, cols, r[u][q]) + run;
+          else coo_store_y<T, Ops>(a.y, r[u][q], run, a.accumulate);
         }
         run = Ops::identity();
+        if (HYB && owner && nxt > r[u][q] + 1 && !(lane == 31 && u == U - 1 && q == VPL - 1))
+          hyb_gap(*hyb, a.x, a.y, cols, (i64)r[u][q] + 1, (i64)nxt - 1);  // tail-free rows up to the tile's next entry
       }
     }
 
@@ -198,9 +268,13 @@ __device__ __forceinline__ void coo_warp_tile(const CooArgs<T> &a, const i64 til
         const bool continued = (head_row == prev_row);  // the row came in from the previous tile
         rec->head_row = continued ? head_row : -1;
         rec->head_val = continued ? total : Ops::identity();
-        if (!continued) coo_store_y<T, Ops>(a.y, head_row, total, a.accumulate);
+        if (!continued) {
+          if (HYB && owner) a.y[head_row] = hyb_row_init(*hyb, a.x, a.y, cols, head_row) + total;
+          else coo_store_y<T, Ops>(a.y, head_row, total, a.accumulate);
+        }
       } else {
-        coo_store_y<T, Ops>(a.y, head_row, total, a.accumulate);
+        if (HYB && owner) a.y[head_row] = hyb_row_init(*hyb, a.x, a.y, cols, head_row) + total;
+        else coo_store_y<T, Ops>(a.y, head_row, total, a.accumulate);
       }
     }
     wcarry = __shfl_sync(FULL, Vi, 31);

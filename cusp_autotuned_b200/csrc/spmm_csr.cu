@@ -192,7 +192,7 @@ __device__ __forceinline__ void stv(T *p, const BlockVec<T, V> &r) {
 
 template <typename T, int K, int V>
 __global__ void __launch_bounds__(SPMM_BLOCK + 32, 2) csr_spmm_ring_kernel(SpmmArgs<T> a, int R, int stages,
-                                                                            i64 num_tiles, i64 nnz) {
+                                                                            i64 num_tiles, i64 nnz, i64 per_cta) {
   constexpr int BLOCK = SPMM_BLOCK, CAP = SPMM_CAP, STR = SPMM_STR, OSTR = SPMM_OSTR;
   constexpr int EPV = 16 / (int)sizeof(T);
   constexpr int G = 8;           // gathers in flight per lane
@@ -217,6 +217,11 @@ __global__ void __launch_bounds__(SPMM_BLOCK + 32, 2) csr_spmm_ring_kernel(SpmmA
   __syncthreads();
 
   const i64 rows = a.rows;
+  // tile sequence of this CTA: round-robin over the grid, or (per_cta > 0) a contiguous run of tiles, so that the X
+  // rows a tile leaves in L1 serve the neighbouring tiles' gathers (banded operators)
+  const i64 t_first = per_cta > 0 ? (i64)blockIdx.x * per_cta : (i64)blockIdx.x;
+  const i64 t_step = per_cta > 0 ? 1 : (i64)gridDim.x;
+  const i64 t_end = per_cta > 0 ? min(t_first + per_cta, num_tiles) : num_tiles;
   if (tid >= BLOCK) {
     // ------------------------------ producer warp ---------------------------
     const int pl = tid - BLOCK;
@@ -227,8 +232,8 @@ __global__ void __launch_bounds__(SPMM_BLOCK + 32, 2) csr_spmm_ring_kernel(SpmmA
     int off[OQ], noff[OQ];
     int s = 0, s0 = 0, s1 = 0;
     uint32_t ph = 0;
-    i64 tile = blockIdx.x;
-    if (tile < num_tiles) {
+    i64 tile = t_first;
+    if (tile < t_end) {
       const i64 r0 = tile * R;
       const int nr = (int)min((i64)R, rows - r0);
 #pragma unroll
@@ -236,13 +241,13 @@ __global__ void __launch_bounds__(SPMM_BLOCK + 32, 2) csr_spmm_ring_kernel(SpmmA
       s0 = ld_ro(a.Ap + r0);
       s1 = ld_ro(a.Ap + r0 + nr);
     }
-    while (tile < num_tiles) {
+    while (tile < t_end) {
       const int nr = (int)min((i64)R, rows - tile * R);
-      const i64 next = tile + gridDim.x;
+      const i64 next = tile + t_step;
       int n0 = 0, n1 = 0;
 #pragma unroll
       for (int q = 0; q < OQ; ++q) noff[q] = 0;
-      if (next < num_tiles) {  // the next tile's offsets: in flight while this tile is issued
+      if (next < t_end) {  // the next tile's offsets: in flight while this tile is issued
         const i64 r0 = next * R;
         const int nnr = (int)min((i64)R, rows - r0);
 #pragma unroll
@@ -291,7 +296,7 @@ __global__ void __launch_bounds__(SPMM_BLOCK + 32, 2) csr_spmm_ring_kernel(SpmmA
     const T *Xl = a.X + (col_ok ? lane * V : 0);
     int s = 0;
     uint32_t ph = 0;
-    for (i64 tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (i64 tile = t_first; tile < t_end; tile += t_step) {
       const i64 r0 = tile * R;
       const int nr = (int)min((i64)R, rows - r0);
       int lo = -1, s1 = 0;
@@ -370,7 +375,13 @@ static b200sp_status launch_spmm_ring(b200sp_handle h, cudaStream_t st, const Sp
   // persistent, one wave; two CTAs per SM leave ~120 KB of the unified array to L1 for the X rows
   i64 grid = (i64)h->num_sms * (resident < 2 ? resident : 2);
   if (grid > num_tiles) grid = num_tiles;
-  kern<<<(unsigned)grid, SPMM_BLOCK + 32, smem, st>>>(a, (int)R, stages, num_tiles, nnz);
+  // tiles are dealt round-robin; B200SP_SPMM_BLOCKED=1 gives every CTA one contiguous run of tiles instead
+  // (measured slower on poisson7pt 256^3: k = 32 fp32 2.23 against 1.90 ms — the L1 does not hold three tiles of X
+  // rows, and neighbouring CTAs stop sharing their z-neighbours in L2)
+  const char *bl = getenv("B200SP_SPMM_BLOCKED");
+  i64 per_cta = (bl && bl[0] == '1') ? ceil_div(num_tiles, grid) : 0;
+  if (per_cta > 0) grid = ceil_div(num_tiles, per_cta);
+  kern<<<(unsigned)grid, SPMM_BLOCK + 32, smem, st>>>(a, (int)R, stages, num_tiles, nnz, per_cta);
   B200SP_LAUNCH_CHECK(h, "csr_spmm_ring_kernel");
   return B200SP_OK;
 }

@@ -16,25 +16,32 @@
 // Per row: y = (init + ELL slots in order) + tail sum — the same two values added in the same order as the
 // two-launch form with the same tile shape, so the results are bit-identical to it.
 //
-// A tile's ELL range is as long as the gap in front of its rows: a tail concentrated in a few rows would leave one
-// warp with millions of rows.  The kernel is correct for any input; spmv_hyb uses it only when a probe of the tile
-// boundaries (hyb_tile_range_kernel, cached per (row_indices, num_entries, num_rows, tile) like the other structure
-// hints — stale hints cost time, never correctness) found no range longer than max(2048, num_rows / 1024) rows.
+// A tile's ELL range is as long as the gap in front of its rows (a tail concentrated in a few rows, the boundary
+// planes of a stencil whose interior rows alone reach the tail).  Tiles whose range exceeds HYB_COOP_CAP rows do not
+// walk it: they become "owner" tiles (coo_warp.cuh) — a row that ends in the tile is stored as init + ELL + tail by the
+// lane that sees the end (no read-modify-write), the open last row is initialised by one lane, and every run of
+// tail-free rows (in front of the tile, between two of its entries, behind the last entry of the matrix) is either
+// finished on the spot (< 8 rows) or appended to a work list in pieces of at most 1024 rows; tail-free rows have no
+// ordering constraint, so hyb_gap_kernel works the list off after the grid with a warp per piece.  Work per tile is
+// bounded for every input, and the list holds at most rows/8 + rows/1024 pieces.
+//
+// MEASURED (B200, tools/hyb_probe.py, profiles/r04_hyb_single_pass.md): bit-identical to the two-launch form on every
+// test matrix, and SLOWER — poisson7pt 256^3 split at K = 6 (one tail entry per row): 0.535 against 0.253 ms (fp32),
+// 0.674 against 0.359 ms (fp64); R-MAT scale 24 (K = 1, 97 % of the entries in the tail): 1.965 against 1.143 ms.
+// Both products are bound by the latency of dependent round trips per warp, not by bytes: a warp tile of the
+// two-launch tail does two (entries, then x gathers); here the tile's row range has to be known first (one), then the
+// ELL slots are fetched (two), gathered (three) and stored before the tail entries may accumulate into them (a fourth
+// for the read-modify-write) — and an ELL part as long as the stencil's runs at the LDG rate inside a warp instead of
+// the bulk-copy ring's.  What the second launch and the y round trip cost (5 - 12 % of the bytes) is less than what
+// the serialised phases add.  Kept behind B200SP_HYB_FUSED=1 with its parity test; the default stays ELL launch +
+// COO launch.
 #include <stdlib.h>
 
 #include "coo_warp.cuh"
 
 namespace b200sp {
 
-template <typename T>
-struct HybEll {
-  const int *cidx;
-  const T *vals;
-  i64 pitch;
-  int K;
-  i64 rows;
-  int accumulate;  // the caller's: y = y + A x
-};
+constexpr int HYB_COOP_CAP = 1024;  // rows a tile's warp initialises itself before its tail entries accumulate
 
 // ELL rows [lo, hi] by one warp: 32 consecutive rows per step, RU steps in flight, slots in chunks of KC.
 template <typename T>
@@ -92,70 +99,54 @@ template <typename T, int BLOCK, int MINB, int VPL, int U>
 __global__ void __launch_bounds__(BLOCK, MINB) hyb_warp_kernel(CooArgs<T> a, HybEll<T> e, i64 num_tiles) {
   constexpr int WT = 32 * VPL * U;
   const int lane = threadIdx.x & 31;
+  const unsigned cols = (unsigned)a.cols;
   const i64 stride = (i64)gridDim.x * (BLOCK / 32);
-  // tiles from the back: the longest ELL ranges of graph-like operators (sparse high rows) start first
-  for (i64 it = (i64)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); it < num_tiles; it += stride) {
-    const i64 tile = num_tiles - 1 - it;
+  for (i64 tile = (i64)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); tile < num_tiles; tile += stride) {
     const i64 start = tile * (i64)WT;
-    const i64 p = (start > 0) ? (i64)ld_ro(a.Ai + start - 1) : -1;
-    const i64 L = (tile == num_tiles - 1) ? e.rows - 1 : (i64)ld_ro(a.Ai + start + WT - 1);
-    hyb_ell_rows<T>(e, a.x, a.y, (unsigned)a.cols, p + 1, L, lane);
+    const bool last_tile = tile == num_tiles - 1;
+    const i64 p = (start > 0) ? (i64)ld_ro(a.Ai + start - 1) : -1;                     // row in front of the tile
+    const i64 le = (i64)ld_ro(a.Ai + (last_tile ? a.nnz - 1 : start + WT - 1));        // row of the tile's last entry
+    const i64 L = last_tile ? e.rows - 1 : le;
+    const bool owner = L - p > HYB_COOP_CAP;
+    if (!owner) {
+      hyb_ell_rows<T>(e, a.x, a.y, cols, p + 1, L, lane);
+    } else {
+      if (lane == 0) hyb_gap(e, a.x, a.y, cols, p + 1, (i64)ld_ro(a.Ai + start) - 1);  // rows in front of the first entry
+      if (lane == 1 && last_tile) hyb_gap(e, a.x, a.y, cols, le + 1, e.rows - 1);      // rows behind the last entry
+      // the row left open at the end of the tile is completed by the carry fix-up: its ELL part goes in now
+      if (lane == 2 && !last_tile && le > p && (i64)ld_ro(a.Ai + start + WT) == le)
+        a.y[le] = hyb_row_init(e, a.x, a.y, cols, le);
+    }
     __syncwarp();  // the range's y values are visible to every lane of this warp before the tail accumulates
-    coo_warp_tile<T, VPL, U, 0, 0, false, SpmvOps<T, 0, 0>>(a, tile, lane, nullptr, 0);
+    coo_warp_tile<T, VPL, U, 0, 0, false, SpmvOps<T, 0, 0>, true>(a, tile, lane, nullptr, 0, &e, owner);
   }
 }
 
-// longest ELL range any tile of `wt` entries would own
-__global__ void hyb_tile_range_kernel(i64 nnz, i64 rows, const int *Ai, int wt, i64 num_tiles, int *out) {
-  int worst = 0;
-  for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < num_tiles; t += (i64)gridDim.x * blockDim.x) {
-    const i64 start = t * (i64)wt;
-    const i64 p = (start > 0) ? (i64)Ai[start - 1] : -1;
-    const i64 L = (t == num_tiles - 1) ? rows - 1 : (i64)Ai[start + wt - 1];
-    worst = max(worst, (int)min(L - p, (i64)0x7fffffff));
+// the work list: a warp per piece of at most HYB_GAP_CHUNK tail-free rows
+template <typename T>
+__global__ void __launch_bounds__(256) hyb_gap_kernel(HybEll<T> e, const T *x, T *y, unsigned cols) {
+  const unsigned n = min(*e.work_count, e.work_cap);
+  const int lane = threadIdx.x & 31;
+  for (unsigned i = blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += gridDim.x * 8) {
+    const int2 w = e.work[i];
+    hyb_ell_rows<T>(e, x, y, cols, w.x, w.y, lane);
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) worst = max(worst, __shfl_xor_sync(0xffffffffu, worst, o));
-  if ((threadIdx.x & 31) == 0 && worst > 0) atomicMax(out, worst);
-}
-
-// the hint: longest range, or -1 when it cannot be obtained (stream capture in progress)
-static i64 hyb_tile_range(b200sp_handle h, cudaStream_t st, i64 rows, i64 nnz, const int *Ai, int wt) {
-  const b200sp_context::CsrKey key{Ai, rows * 4096 + wt, nnz};
-  auto it = h->hyb_tile_range.find(key);
-  if (it != h->hyb_tile_range.end()) return it->second;
-  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
-    cudaGetLastError();
-    return -1;
-  }
-  int *d = reinterpret_cast<int *>(h->dev_scalars + 56);
-  int *p = reinterpret_cast<int *>(h->pinned_scalars + 56);
-  const i64 tiles = ceil_div(nnz, (i64)wt);
-  i64 worst = -1;
-  if (cudaMemsetAsync(d, 0, sizeof(int), st) == cudaSuccess) {
-    const unsigned grid = (unsigned)min(ceil_div(tiles, (i64)256), (i64)h->num_sms * 8);
-    hyb_tile_range_kernel<<<grid, 256, 0, st>>>(nnz, rows, Ai, wt, tiles, d);
-    h->launches++;
-    if (cudaMemcpyAsync(p, d, sizeof(int), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
-        cudaStreamSynchronize(st) == cudaSuccess)
-      worst = p[0];
-  }
-  cudaGetLastError();
-  if (worst < 0) return -1;
-  if (h->hyb_tile_range.size() > 256) h->hyb_tile_range.clear();
-  h->hyb_tile_range[key] = worst;
-  return worst;
 }
 
 template <typename T, int MINB, int VPL, int U>
-static b200sp_status launch_hyb_warp(b200sp_handle h, cudaStream_t st, CooArgs<T> a, const HybEll<T> &e, int ctas_per_sm) {
+static b200sp_status launch_hyb_warp(b200sp_handle h, cudaStream_t st, CooArgs<T> a, HybEll<T> e, int ctas_per_sm) {
   constexpr int WT = 32 * VPL * U;
   const i64 tiles = ceil_div(a.nnz, (i64)WT);
-  b200sp_status s = ensure_scratch(h, (size_t)tiles * sizeof(CooCarry<T>));
+  const size_t carry_bytes = ((size_t)tiles * sizeof(CooCarry<T>) + 15) & ~(size_t)15;
+  const i64 work_cap = a.rows / HYB_GAP_INLINE + a.rows / HYB_GAP_CHUNK + 64;
+  b200sp_status s = ensure_scratch(h, carry_bytes + (size_t)work_cap * sizeof(int2));
   if (s != B200SP_OK) return s;
   a.carry = reinterpret_cast<CooCarry<T> *>(h->scratch);
-  a.accumulate = 1;  // the tile's rows were initialised by its ELL range
+  a.accumulate = 1;  // tiles that are not owners accumulate into the y their warp has just initialised
+  e.work = reinterpret_cast<int2 *>(reinterpret_cast<char *>(h->scratch) + carry_bytes);
+  e.work_cap = (unsigned)work_cap;
+  e.work_count = reinterpret_cast<unsigned *>(h->dev_scalars + 55);
+  B200SP_CUDA(h, cudaMemsetAsync(e.work_count, 0, sizeof(unsigned), st));
   auto kern = hyb_warp_kernel<T, 256, MINB, VPL, U>;
   B200SP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
   i64 grid = ceil_div(tiles, (i64)8);
@@ -170,32 +161,29 @@ static b200sp_status launch_hyb_warp(b200sp_handle h, cudaStream_t st, CooArgs<T
   B200SP_LAUNCH_CHECK(h, "hyb_warp_kernel");
   coo_fixup_kernel<T, SpmvOps<T, 0, 0>><<<(unsigned)ceil_div(tiles, 256), 256, 0, st>>>(tiles, a.carry, a.y, 1);
   B200SP_LAUNCH_CHECK(h, "coo_fixup_kernel");
+  const i64 gap_grid = min((i64)h->num_sms * 8, ceil_div(work_cap, (i64)8));
+  hyb_gap_kernel<T><<<(unsigned)gap_grid, 256, 0, st>>>(e, a.x, a.y, (unsigned)a.cols);
+  B200SP_LAUNCH_CHECK(h, "hyb_gap_kernel");
   return B200SP_OK;
 }
 
 // Returns B200SP_OK and sets *done = 1 when the fused kernel ran; *done = 0 (and OK) when the caller should take the
-// two-launch form: arrays not aligned for the tile's vector loads, a tail whose tiles would own long ELL ranges, a
-// shape outside the instantiated set, or B200SP_HYB_FUSED=0.  `c` is the COO configuration the tail would run with
-// (kernel == K_COO_WARP).  B200SP_HYB_FUSED=2 skips the range hint (tests: the kernel on any input).
+// two-launch form: B200SP_HYB_FUSED is not 1 (the default, see MEASURED in the header), arrays not aligned for the
+// tile's vector loads, or a shape outside the instantiated set.  `c` is the COO configuration the tail would run with (kernel ==
+// K_COO_WARP).
 template <typename T>
 b200sp_status spmv_hyb_fused(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64 K, i64 pitch, const int *ecidx,
                              const T *evals, i64 cnnz, const int *ci, const int *cj, const T *cv, const T *x, T *y,
                              int accumulate, const b200sp_cfg &c, int *done) {
   *done = 0;
   const char *env = getenv("B200SP_HYB_FUSED");
-  const int mode = env ? atoi(env) : 1;
+  const int mode = env ? atoi(env) : 0;  // opt-in: measured slower than the two-launch form (header)
   if (mode == 0 || c.kernel != B200SP_K_COO_WARP || cnnz <= 0 || rows <= 0 || K < 0 || K > (1 << 20)) return B200SP_OK;
   const int vpl = c.vector_width ? c.vector_width : 8, u = c.unroll ? c.unroll : 1;
   const uintptr_t m = (uintptr_t)(vpl == 8 ? 31 : 15);
   if ((((uintptr_t)ci | (uintptr_t)cj | (uintptr_t)cv) & m) != 0) return B200SP_OK;
   if (!((vpl == 4 || vpl == 8) && (u == 1 || u == 2))) return B200SP_OK;
   if (K > 0 && (!ecidx || !evals)) return set_error(h, B200SP_INVALID_INPUT, "hyb: null ELL arrays");
-  const int wt = 32 * vpl * u;
-  if (mode != 2) {
-    const i64 worst = hyb_tile_range(h, st, rows, cnnz, ci, wt);
-    const i64 cap = rows / 1024 > 2048 ? rows / 1024 : 2048;
-    if (worst < 0 || worst > cap) return B200SP_OK;
-  }
   CooArgs<T> a;
   a.rows = rows; a.cols = cols; a.nnz = cnnz; a.Ai = ci; a.Aj = cj; a.Ax = cv; a.x = x; a.y = y;
   a.accumulate = 1;
@@ -205,16 +193,18 @@ b200sp_status spmv_hyb_fused(b200sp_handle h, cudaStream_t st, i64 rows, i64 col
   a.scalar_loads = 0;
   HybEll<T> e;
   e.cidx = ecidx; e.vals = evals; e.pitch = pitch; e.K = (int)K; e.rows = rows; e.accumulate = accumulate;
+  e.work = nullptr; e.work_count = nullptr; e.work_cap = 0;
   b200sp_status s;
+  // one resident CTA fewer than the plain tile kernels: the ELL range loop keeps 32 loads in flight per lane
   if constexpr (sizeof(T) == 4) {
-    if (vpl == 4 && u == 1) s = launch_hyb_warp<T, 4, 4, 1>(h, st, a, e, c.ctas_per_sm);
-    else if (vpl == 4) s = launch_hyb_warp<T, 4, 4, 2>(h, st, a, e, c.ctas_per_sm);
-    else if (u == 1) s = launch_hyb_warp<T, 4, 8, 1>(h, st, a, e, c.ctas_per_sm);
-    else s = launch_hyb_warp<T, 3, 8, 2>(h, st, a, e, c.ctas_per_sm);
-  } else {
     if (vpl == 4 && u == 1) s = launch_hyb_warp<T, 4, 4, 1>(h, st, a, e, c.ctas_per_sm);
     else if (vpl == 4) s = launch_hyb_warp<T, 3, 4, 2>(h, st, a, e, c.ctas_per_sm);
     else if (u == 1) s = launch_hyb_warp<T, 3, 8, 1>(h, st, a, e, c.ctas_per_sm);
+    else s = launch_hyb_warp<T, 2, 8, 2>(h, st, a, e, c.ctas_per_sm);
+  } else {
+    if (vpl == 4 && u == 1) s = launch_hyb_warp<T, 3, 4, 1>(h, st, a, e, c.ctas_per_sm);
+    else if (vpl == 4) s = launch_hyb_warp<T, 2, 4, 2>(h, st, a, e, c.ctas_per_sm);
+    else if (u == 1) s = launch_hyb_warp<T, 2, 8, 1>(h, st, a, e, c.ctas_per_sm);
     else s = launch_hyb_warp<T, 2, 8, 2>(h, st, a, e, c.ctas_per_sm);
   }
   if (s == B200SP_OK) *done = 1;
