@@ -447,6 +447,7 @@ b200sp_status b200sp_destroy(b200sp_handle h) {
   if (h->cg_ws) cudaFree(h->cg_ws);
   if (h->cg_residuals) cudaFree(h->cg_residuals);
   for (void *ev : h->tune_events) cudaEventDestroy((cudaEvent_t)ev);
+  for (void *ev : h->coo_choice_events) cudaEventDestroy((cudaEvent_t)ev);
   if (h->graph_event) cudaEventDestroy((cudaEvent_t)h->graph_event);
   if (h->graph_stream) cudaStreamDestroy((cudaStream_t)h->graph_stream);
   delete h;

@@ -99,6 +99,10 @@ struct b200sp_context {
   // longest ELL row range a COO-tail tile would own in the fused HYB kernel, per (row_indices, rows*4096+tile, nnz)
   std::map<CsrKey, long long> hyb_tile_range;
   std::vector<void *> tune_events;  // cudaEvent_t pair
+  // K_COO_WARP on >= 2^27 scattered entries: persistent grid (1) or one tile per warp (0), whichever was faster on
+  // the first product with these arrays (spmv_coo.cu: coo_warp_grid_choice); same tiles, same bits either way
+  std::map<CsrKey, int> coo_grid_choice;
+  std::vector<void *> coo_choice_events;  // three cudaEvent_t
   std::vector<void *> coo_plans;    // attached b200sp_coo_plan (spmv_coo_plan.cu)
   // set by the CG driver around its iteration: the DIA bulk kernel is launched with programmatic stream
   // serialization and waits (griddepcontrol.wait) before its first read of x / y (spmv_dia.cu, cg.cu)

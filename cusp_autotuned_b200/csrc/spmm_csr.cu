@@ -143,7 +143,6 @@ static b200sp_status launch_spmm(b200sp_handle h, cudaStream_t st, const SpmmArg
 // ---------------------------------------------------------------------------
 constexpr int SPMM_BLOCK = 256;
 constexpr int SPMM_CAP = 2048;           // entries per stage
-constexpr int SPMM_STR = SPMM_CAP + 16;  // stage stride: alignment shift + read-ahead slack
 constexpr int SPMM_OSTR = 264;           // row offsets per stage (R + 1 <= 257)
 
 template <typename T, int V>
@@ -190,10 +189,11 @@ __device__ __forceinline__ void stv(T *p, const BlockVec<T, V> &r) {
   else *reinterpret_cast<double2 *>(p) = make_double2(r.v[0], r.v[1]);
 }
 
-template <typename T, int K, int V>
-__global__ void __launch_bounds__(SPMM_BLOCK + 32, 2) csr_spmm_ring_kernel(SpmmArgs<T> a, int R, int stages,
-                                                                            i64 num_tiles, i64 nnz, i64 per_cta) {
-  constexpr int BLOCK = SPMM_BLOCK, CAP = SPMM_CAP, STR = SPMM_STR, OSTR = SPMM_OSTR;
+template <typename T, int K, int V, int MINB, int U>
+__global__ void __launch_bounds__(SPMM_BLOCK + 32, MINB) csr_spmm_ring_kernel(SpmmArgs<T> a, int R, int stages,
+                                                                            i64 num_tiles, i64 nnz, i64 per_cta, int cap) {
+  constexpr int BLOCK = SPMM_BLOCK, OSTR = SPMM_OSTR;
+  const int CAP = cap, STR = cap + 16;  // entries per stage; stride with alignment shift + read-ahead slack
   constexpr int EPV = 16 / (int)sizeof(T);
   constexpr int G = 8;           // gathers in flight per lane
   constexpr int SW = BLOCK / K;  // rows in flight per CTA
@@ -310,37 +310,65 @@ __global__ void __launch_bounds__(SPMM_BLOCK + 32, 2) csr_spmm_ring_kernel(SpmmA
         const int *pc = s_col + (size_t)s * STR + (lo & 3) - lo;  // pc[j], absolute entry index j
         const T *pv = s_val + (size_t)s * STR + (lo & (EPV - 1)) - lo;
         T keep = T(0);
-        for (int i = sub; i < nr; i += SW) {
-          const int B = offs[i], E = offs[i + 1];
-          const bool first = B >= lo && (B < hi || last);  // the chunk that initialises the row
-          if (!(first || (B < hi && E > lo))) continue;    // the row has nothing in this chunk
-          const int b = max(B, lo), e = min(E, hi);
-          T *yp = a.Y + (r0 + i) * a.ldy + lane * V;
-          BlockVec<T, V> acc;
+        for (int i0 = sub; i0 < nr; i0 += SW * U) {
+          // U rows of the sub-warp are worked on together: U * G independent X-row gathers in flight per lane
+          int b[U], e[U];
+          bool act[U];
+          BlockVec<T, V> acc[U];
+          int len_max = 0;
 #pragma unroll
-          for (int v = 0; v < V; ++v) acc.v[v] = T(0);
-          // partial sums of a row continued from the previous chunk were parked in Y by this thread
-          if (col_ok && (!first || a.accumulate)) acc = ldv<T, V>(yp);
-          for (int jj = b; jj < e; jj += G) {
-            BlockVec<T, V> xv[G];
+          for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * SW;
+            act[u] = false;
+            b[u] = e[u] = lo;
 #pragma unroll
-            for (int q = 0; q < G; ++q)  // slots past the row's end hold valid columns (next rows / zero fill)
-              xv[q] = ldv_ro<T, V>(Xl + (i64)(unsigned)pc[jj + q] * a.ldx);
-#pragma unroll
-            for (int q = 0; q < G; ++q)
-#pragma unroll
-              for (int v = 0; v < V; ++v) pin(xv[q].v[v]);
-#pragma unroll
-            for (int q = 0; q < G; ++q) {
-              if (jj + q < e) {
-                const T val = pv[jj + q];
-#pragma unroll
-                for (int v = 0; v < V; ++v) acc.v[v] = acc.v[v] + val * xv[q].v[v];
+            for (int v = 0; v < V; ++v) acc[u].v[v] = T(0);
+            if (i < nr) {
+              const int B = offs[i], E = offs[i + 1];
+              const bool first = B >= lo && (B < hi || last);  // the chunk that initialises the row
+              if (first || (B < hi && E > lo)) {               // else the row has nothing in this chunk
+                act[u] = true;
+                b[u] = max(B, lo);
+                e[u] = max(min(E, hi), b[u]);
+                // partial sums of a row continued from the previous chunk were parked in Y by this thread
+                if (col_ok && (!first || a.accumulate)) acc[u] = ldv<T, V>(a.Y + (r0 + i) * a.ldy + lane * V);
               }
             }
+            len_max = max(len_max, e[u] - b[u]);
           }
-          if (col_ok) stv<T, V>(yp, acc);
-          keep = keep + acc.v[0];
+          for (int jj = 0; jj < len_max; jj += G) {
+            BlockVec<T, V> xv[U][G];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+              for (int q = 0; q < G; ++q) {
+                // slots past a row's end hold valid columns (next rows / zero fill); with several rows in step the
+                // shorter ones stay at their own end
+                const int idx = (U == 1) ? b[u] + jj + q : min(b[u] + jj + q, e[u]);
+                xv[u][q] = ldv_ro<T, V>(Xl + (i64)(unsigned)pc[idx] * a.ldx);
+              }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+              for (int q = 0; q < G; ++q)
+#pragma unroll
+                for (int v = 0; v < V; ++v) pin(xv[u][q].v[v]);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+              for (int q = 0; q < G; ++q) {
+                if (b[u] + jj + q < e[u]) {
+                  const T val = pv[b[u] + jj + q];
+#pragma unroll
+                  for (int v = 0; v < V; ++v) acc[u].v[v] = acc[u].v[v] + val * xv[u][q].v[v];
+                }
+              }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (act[u] && col_ok) stv<T, V>(a.Y + (r0 + i0 + u * SW) * a.ldy + lane * V, acc[u]);
+            keep = keep + acc[u].v[0];
+          }
         }
         consume_before_release(keep);
         __syncwarp();
@@ -355,25 +383,25 @@ __global__ void __launch_bounds__(SPMM_BLOCK + 32, 2) csr_spmm_ring_kernel(SpmmA
   }
 }
 
-template <typename T, int K, int V>
-static b200sp_status launch_spmm_ring(b200sp_handle h, cudaStream_t st, const SpmmArgs<T> &a, i64 nnz) {
-  const int stages = 3;
+template <typename T, int K, int V, int MINB, int U>
+static b200sp_status launch_spmm_ring_m(b200sp_handle h, cudaStream_t st, const SpmmArgs<T> &a, i64 nnz, int stages,
+                                        int cap) {
   const double mean = (double)nnz / (double)a.rows;
-  i64 R = (i64)(0.9 * (double)SPMM_CAP / (mean > 1.0 ? mean : 1.0));
-  constexpr int PASS = SPMM_BLOCK / K;  // rows per pass of the CTA
+  i64 R = (i64)(0.9 * (double)cap / (mean > 1.0 ? mean : 1.0));
+  constexpr int PASS = (SPMM_BLOCK / K) * U;  // rows per pass of the CTA
   R = (R / PASS) * PASS;
   if (R < PASS) R = PASS;
   if (R > SPMM_BLOCK) R = SPMM_BLOCK;
   const i64 num_tiles = ceil_div(a.rows, R);
-  const size_t smem = (size_t)stages * (SPMM_STR * (sizeof(T) + sizeof(int)) + SPMM_OSTR * sizeof(int)) +
+  const size_t smem = (size_t)stages * ((size_t)(cap + 16) * (sizeof(T) + sizeof(int)) + SPMM_OSTR * sizeof(int)) +
                       2 * (size_t)stages * sizeof(uint64_t) + 16;
-  auto kern = csr_spmm_ring_kernel<T, K, V>;
+  auto kern = csr_spmm_ring_kernel<T, K, V, MINB, U>;
   B200SP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int resident = 0;
   B200SP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, SPMM_BLOCK + 32, smem));
   if (resident < 1) return set_error(h, B200SP_INVALID_INPUT, "csr spmm ring: configuration does not fit on an SM");
-  // persistent, one wave; two CTAs per SM leave ~120 KB of the unified array to L1 for the X rows
-  i64 grid = (i64)h->num_sms * (resident < 2 ? resident : 2);
+  // persistent, one wave; MINB CTAs per SM, the rest of the unified array stays L1 for the X rows
+  i64 grid = (i64)h->num_sms * (resident < MINB ? resident : MINB);
   if (grid > num_tiles) grid = num_tiles;
   // tiles are dealt round-robin; B200SP_SPMM_BLOCKED=1 gives every CTA one contiguous run of tiles instead
   // (measured slower on poisson7pt 256^3: k = 32 fp32 2.23 against 1.90 ms — the L1 does not hold three tiles of X
@@ -381,9 +409,23 @@ static b200sp_status launch_spmm_ring(b200sp_handle h, cudaStream_t st, const Sp
   const char *bl = getenv("B200SP_SPMM_BLOCKED");
   i64 per_cta = (bl && bl[0] == '1') ? ceil_div(num_tiles, grid) : 0;
   if (per_cta > 0) grid = ceil_div(num_tiles, per_cta);
-  kern<<<(unsigned)grid, SPMM_BLOCK + 32, smem, st>>>(a, (int)R, stages, num_tiles, nnz, per_cta);
+  kern<<<(unsigned)grid, SPMM_BLOCK + 32, smem, st>>>(a, (int)R, stages, num_tiles, nnz, per_cta, cap);
   B200SP_LAUNCH_CHECK(h, "csr_spmm_ring_kernel");
   return B200SP_OK;
+}
+
+template <typename T, int K, int V>
+static b200sp_status launch_spmm_ring(b200sp_handle h, cudaStream_t st, const SpmmArgs<T> &a, i64 nnz) {
+  // Defaults by measurement (poisson7pt 256^3, profiles/r04_spmm.md): three resident CTAs per SM (72 registers) with a
+  // two-stage ring.  Measurement switches: B200SP_SPMM_MINB = resident CTAs per SM (2 | 3), B200SP_SPMM_STAGES = ring
+  // depth (2..4), B200SP_SPMM_CAP = entries per stage (1024 | 2048).
+  const char *mb = getenv("B200SP_SPMM_MINB"), *sg = getenv("B200SP_SPMM_STAGES"), *cp = getenv("B200SP_SPMM_CAP");
+  const int minb = mb ? atoi(mb) : 3, stages = sg ? atoi(sg) : 2, cap = cp ? atoi(cp) : SPMM_CAP;
+  if (stages < 2 || stages > 4) return set_error(h, B200SP_INVALID_INPUT, "csr spmm ring: stages %d", stages);
+  if (cap != 1024 && cap != 2048) return set_error(h, B200SP_INVALID_INPUT, "csr spmm ring: stage capacity %d", cap);
+  // (two rows in flight per sub-warp — U = 2 — measured: no change, 1.913 / 1.915 ms at k = 32 fp32; not instantiated)
+  if (minb >= 3) return launch_spmm_ring_m<T, K, V, 3, 1>(h, st, a, nnz, stages, cap);
+  return launch_spmm_ring_m<T, K, V, 2, 1>(h, st, a, nnz, stages, cap);
 }
 
 template <typename T>

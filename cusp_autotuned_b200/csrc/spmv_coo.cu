@@ -27,6 +27,8 @@
 //   Summation order is fixed by (nnz, BLOCK, VPT) -> bit-reproducible.
 //
 // Algorithmic bytes: nnz*(8+sizeof(T)) + cols*sizeof(T) + rows*sizeof(T).
+#include <stdlib.h>
+
 #include "coo.cuh"
 
 namespace b200sp {
@@ -636,6 +638,55 @@ template <typename T>
 b200sp_status spmv_coo_attached(b200sp_handle h, cudaStream_t st, b200sp_coo_plan p, const T *Ax, const T *x, T *y,
                                 int accumulate, const b200sp_cfg *cfg);
 
+// K_COO_WARP with the default shape for >= 2^27 scattered entries (v8, two units per tile) ran 4 % faster from a
+// persistent grid than with one tile per warp on the boxes of round 2's first session (1.066 against 1.144 ms on R-MAT
+// scale 24) and 10 - 15 % slower on the boxes of the second (1.23 - 1.28 against 1.12 ms; same binary, the one-shot
+// time did not move: profiles/r04_gather_probe.md).  Both grids cut the entries into the same tiles and add them in
+// the same order, so y is bit-identical either way — the first product with a given set of arrays times both
+// (second of two launches each, CUDA events on the caller's stream, y = A x only: every launch rewrites y completely)
+// and later products use the faster one.  A hint cached per (column_indices, nnz, element size) like the gather
+// class; skipped (one tile per warp) while the stream is being captured.
+template <typename T>
+static b200sp_status spmv_coo_warp_auto_grid(b200sp_handle h, cudaStream_t st, const CooArgs<T> &a, b200sp_cfg c) {
+  const b200sp_context::CsrKey key{a.Aj, (int64_t)sizeof(T), a.nnz};
+  auto it = h->coo_grid_choice.find(key);
+  if (it != h->coo_grid_choice.end()) {
+    c.ctas_per_sm = it->second ? 8 : 0;
+    return spmv_coo_warp<T>(h, st, a, c);
+  }
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (a.accumulate || cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();  // y += A x cannot be repeated, a capture cannot be timed: one tile per warp, nothing cached
+    c.ctas_per_sm = 0;
+    return spmv_coo_warp<T>(h, st, a, c);
+  }
+  while (h->coo_choice_events.size() < 3) {
+    cudaEvent_t e;
+    B200SP_CUDA(h, cudaEventCreate(&e));
+    h->coo_choice_events.push_back(e);
+  }
+  cudaEvent_t e0 = (cudaEvent_t)h->coo_choice_events[0], e1 = (cudaEvent_t)h->coo_choice_events[1],
+              e2 = (cudaEvent_t)h->coo_choice_events[2];
+  b200sp_cfg one = c, per = c;
+  one.ctas_per_sm = 0;
+  per.ctas_per_sm = 8;
+  b200sp_status s;
+  if ((s = spmv_coo_warp<T>(h, st, a, one)) != B200SP_OK) return s;
+  if ((s = spmv_coo_warp<T>(h, st, a, per)) != B200SP_OK) return s;
+  B200SP_CUDA(h, cudaEventRecord(e0, st));
+  if ((s = spmv_coo_warp<T>(h, st, a, one)) != B200SP_OK) return s;
+  B200SP_CUDA(h, cudaEventRecord(e1, st));
+  if ((s = spmv_coo_warp<T>(h, st, a, per)) != B200SP_OK) return s;
+  B200SP_CUDA(h, cudaEventRecord(e2, st));
+  B200SP_CUDA(h, cudaEventSynchronize(e2));
+  float ms_one = 0.f, ms_per = 0.f;
+  B200SP_CUDA(h, cudaEventElapsedTime(&ms_one, e0, e1));
+  B200SP_CUDA(h, cudaEventElapsedTime(&ms_per, e1, e2));
+  if (h->coo_grid_choice.size() > 256) h->coo_grid_choice.clear();
+  h->coo_grid_choice[key] = ms_per < 0.98f * ms_one ? 1 : 0;  // the persistent grid has to win by 2 %
+  return B200SP_OK;
+}
+
 template <typename T>
 b200sp_status spmv_coo(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64 nnz, const int *Ai,
                        const int *Aj, const T *Ax, const T *x, T *y, int accumulate,
@@ -658,7 +709,10 @@ b200sp_status spmv_coo(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64
   b200sp_cfg c = cfg ? *cfg : b200sp_cfg{};
   const bool tma_ok = aligned16(Ai) && aligned16(Aj) && aligned16(Ax);
   const bool vec32_ok = ((((uintptr_t)Ai | (uintptr_t)Aj | (uintptr_t)Ax) & 31) == 0);
+  const bool no_cfg = c.kernel == 0 && c.block_size == 0 && c.unroll == 0;
   coo_defaults(c, h, st, nnz, Aj, sizeof(T), tma_ok, vec32_ok);
+  // the default for >= 2^27 scattered entries: persistent or one-shot grid by measurement (below)
+  const bool auto_grid = no_cfg && c.kernel == B200SP_K_COO_WARP && c.ctas_per_sm == 8;
   if (c.kernel == B200SP_K_COO_RING && !tma_ok) c.kernel = B200SP_K_COO_SEGSCAN;  // bulk copies need 16-byte bases
   if (c.kernel != B200SP_K_COO_SEGSCAN && c.kernel != B200SP_K_COO_RING && c.kernel != B200SP_K_COO_WARP)
     return set_error(h, B200SP_INVALID_INPUT, "coo: unknown kernel id %d", c.kernel);
@@ -674,7 +728,10 @@ b200sp_status spmv_coo(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64
   if (c.kernel == B200SP_K_COO_WARP) {
     // vector loads need 16- / 32-byte aligned bases; otherwise the scalar-load kernel gives the same sums
     const uintptr_t m = (uintptr_t)(c.vector_width == 8 ? 31 : 15);
-    if ((((uintptr_t)Ai | (uintptr_t)Aj | (uintptr_t)Ax) & m) == 0) return spmv_coo_warp<T>(h, st, a, c);
+    if ((((uintptr_t)Ai | (uintptr_t)Aj | (uintptr_t)Ax) & m) == 0) {
+      if (auto_grid) return spmv_coo_warp_auto_grid<T>(h, st, a, c);
+      return spmv_coo_warp<T>(h, st, a, c);
+    }
     c = b200sp_cfg{};
     c.kernel = B200SP_K_COO_SEGSCAN;
     c.block_size = 256;
@@ -726,7 +783,8 @@ b200sp_status spmv_hyb(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64
                        const T *cv, const T *x, T *y, int accumulate, const b200sp_cfg *ecfg,
                        const b200sp_cfg *ccfg) {
   B200SP_CHECK_HANDLE(h);
-  if (cnnz > 0 && rows > 0 && rows < (1ll << 31) && cols > 0 && cols < (1ll << 31) && K >= 0 && ci && cj && cv && x && y &&
+  const char *fused_env = getenv("B200SP_HYB_FUSED");  // opt-in (measured slower, spmv_hyb_fused.cu)
+  if (fused_env && fused_env[0] == '1' && cnnz > 0 && rows > 0 && rows < (1ll << 31) && cols > 0 && cols < (1ll << 31) && K >= 0 && ci && cj && cv && x && y &&
       (K == 0 || (ecidx && evals && pitch >= rows)) && (!ecfg || ecfg->kernel == 0) &&
       (!ccfg || ccfg->kernel == 0 || ccfg->kernel == B200SP_K_COO_WARP)) {
     // one pass over y (spmv_hyb_fused.cu) when the tail would run the warp-tile kernel anyway, no hot-column plan
