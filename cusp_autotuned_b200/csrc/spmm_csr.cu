@@ -448,8 +448,15 @@ b200sp_status spmm_csr(b200sp_handle h, cudaStream_t st, i64 rows, i64 cols, i64
   const char *nv = getenv("B200SP_SPMM_NOVEC");  // measurement switch: one column per lane
   const bool novec = nv && nv[0] == '1';
   const bool ring = nnz > 0 && aligned16(Aj) && aligned16(Ax) && !(force && force[0] == '1');
-  for (i64 c0 = 0; c0 < k; c0 += 32) {  // column chunks of 32
-    a.k = (int)((k - c0 < 32) ? k - c0 : 32);
+  // column chunks: 16 lanes x 4 fp32 columns (64 wide) when the whole block allows 128-bit accesses — half as many
+  // passes over the matrix for wide fp32 blocks — otherwise 32 columns per pass
+  const bool wide = ring && sizeof(T) == 4 && !novec && k > 32 && ldx % 4 == 0 && ldy % 4 == 0 && aligned16(X) && aligned16(Y);
+  i64 cw = 32;
+  for (i64 c0 = 0; c0 < k; c0 += cw) {
+    const i64 left = k - c0;
+    // a 33..64-column chunk only when every lane gets four whole columns (16 lanes x 4); otherwise 32 at a time
+    cw = (wide && left > 32 && (left >= 64 || left % 4 == 0)) ? (left < 64 ? left : 64) : (left < 32 ? left : 32);
+    a.k = (int)cw;
     a.X = X ? X + c0 : &dummy;
     a.Y = Y + c0;
     b200sp_status s;

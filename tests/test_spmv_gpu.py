@@ -557,7 +557,7 @@ def test_csr_block_multiply_bit_exact(ndt, tdt, dev):
         # pads: 0 / 4 keep 16-byte-aligned rows (a lane owns 4 fp32 / 2 fp64 columns: 128-bit accesses), 3 does not
         # (one column per lane); k = 12, 24, 64 exercise idle lanes and two column chunks of the vector path
         for k, pad in [(1, 0), (2, 0), (2, 3), (3, 0), (4, 0), (4, 3), (4, 4), (7, 0), (8, 0), (8, 3), (12, 4), (16, 0),
-                       (16, 3), (24, 0), (31, 0), (32, 0), (32, 3), (32, 4), (33, 0), (64, 0), (70, 3)]:
+                       (16, 3), (24, 0), (31, 0), (32, 0), (32, 3), (32, 4), (33, 0), (64, 0), (70, 3), (96, 0), (98, 2), (100, 0), (130, 2)]:
             Xh = rng.uniform(-1, 1, (A["num_cols"], k + pad)).astype(ndt)
             Y0 = rng.uniform(-1, 1, (A["num_rows"], k + pad)).astype(ndt)
             X = tdev(Xh, dev)[:, :k]

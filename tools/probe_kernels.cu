@@ -54,9 +54,116 @@ __global__ void __launch_bounds__(256) gather_sum_kernel(long long nnz, const in
   out[t] = acc;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// release_order_kernel<MODE>: the ring-stage release hazard of common.cuh (consume_before_release), reproduced in
+// isolation, with the candidate cures side by side ("try fence.proxy.async.shared::cta").
+//
+// Persistent CTAs of 256 consumers + one producer lane; tiles of 2048 ints; src[(t % period) * 2048 + i] = t % period.
+// The producer refills a stage as soon as its `empty` barrier completes (cp.async.bulk, mbarrier complete_tx).  A
+// consumer loads its 8 ints of the stage into registers, RELEASES THE STAGE, and only then looks at the registers:
+// every value must equal the tile's tag.  A mismatch means the load was still queued when the arrive let the producer
+// overwrite the stage.
+//   MODE 0  arrive right after the loads (nothing in between)
+//   MODE 1  fence.proxy.async.shared::cta between the loads and the arrive (the architected generic->async ordering)
+//   MODE 2  the library's cure: a compare-and-branch that consumes every loaded register before the arrive
+//   MODE 3  membar.cta (fence.acq_rel.cta) between the loads and the arrive
+template <int MODE>
+__global__ void __launch_bounds__(288) release_order_kernel(const int *__restrict__ src, long long tiles, int period,
+                                                            int stages, unsigned long long *bad) {
+  constexpr int TILE = 2048, NPT = 8, GATHERS = 16;
+  const unsigned span = (unsigned)period * TILE;
+  int sink = 0;
+  extern __shared__ __align__(128) unsigned char smem[];
+  int *stage = reinterpret_cast<int *>(smem);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)stages * TILE * sizeof(int));
+  uint64_t *empty = full + stages;
+  const int tid = threadIdx.x;
+  auto sptr = [](const void *p) { return (uint32_t)__cvta_generic_to_shared(p); };
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sptr(&full[s])), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sptr(&empty[s])), "r"(8));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto wait = [&](uint64_t *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(ok) : "r"(sptr(bar)), "r"(parity) : "memory");
+  };
+  if (tid >= 256) {
+    if (tid == 256) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        wait(&empty[s], ph ^ 1);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sptr(&full[s])), "r"(TILE * 4) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         sptr(stage + (size_t)s * TILE)), "l"(src + (size_t)(t % period) * TILE), "r"(TILE * 4), "r"(sptr(&full[s]))
+                     : "memory");
+        if (++s == stages) { s = 0; ph ^= 1; }
+      }
+    }
+    return;
+  }
+  int s = 0;
+  uint32_t ph = 0;
+  unsigned long long mism = 0;
+  for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+    wait(&full[s], ph);
+    const int *p = stage + (size_t)s * TILE;
+    // what a sparse product has in the memory pipe in front of its shared-memory loads: scattered global gathers
+    int g[GATHERS];
+    unsigned hsh = (unsigned)(t * 2654435761u) + tid * 40503u;
+#pragma unroll
+    for (int q = 0; q < GATHERS; ++q) {
+      hsh = hsh * 1664525u + 1013904223u;
+      asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(g[q]) : "l"(src + (hsh % span)));
+    }
+    int v[NPT];
+#pragma unroll
+    for (int q = 0; q < NPT; ++q) asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v[q]) : "r"(sptr(p + q * 256 + tid)));
+    if (MODE == 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (MODE == 3) asm volatile("fence.acq_rel.cta;" ::: "memory");
+    if (MODE == 2) {
+      int acc = 0;
+#pragma unroll
+      for (int q = 0; q < NPT; ++q) acc += v[q];
+      if (acc == 0x7ff4dead) asm volatile("nanosleep.u32 0;");
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sptr(&empty[s])) : "memory");
+    const int tag = (int)(t % period);
+#pragma unroll
+    for (int q = 0; q < NPT; ++q) mism += (v[q] != tag);
+#pragma unroll
+    for (int q = 0; q < GATHERS; ++q) sink += g[q];
+    if (++s == stages) { s = 0; ph ^= 1; }
+  }
+  if (mism) atomicAdd(bad, mism);
+  if (sink == 0x7ff4dead) atomicAdd(bad + 1, 1ull);  // keeps the gathers alive
+}
+
 }  // namespace
 
 extern "C" {
+// mode 0..3 as above; `bad` (device, zeroed by the caller) receives the number of stale values seen
+int probe_release_order(int mode, long long tiles, int period, int stages, int ctas, const int *src,
+                        unsigned long long *bad, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)stages * 2048 * sizeof(int) + 2 * (size_t)stages * sizeof(uint64_t);
+#define RUN(M)                                                                                          \
+  {                                                                                                     \
+    cudaFuncSetAttribute(release_order_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    release_order_kernel<M><<<ctas, 288, smem, st>>>(src, tiles, period, stages, bad);                  \
+  }
+  if (mode == 0) RUN(0) else if (mode == 1) RUN(1) else if (mode == 2) RUN(2) else RUN(3)
+#undef RUN
+  return (int)cudaGetLastError();
+}
+
 // variant: 0 = columns only, 1 = columns + values (CSR stream), 2 = rows + columns + values (COO stream);
 // vpl 4 | 8.  Returns cudaError_t of the launch.
 int probe_gather_sum(int variant, int vpl, long long nnz, const int *Ai, const int *Aj, const float *Ax, const float *x,
