@@ -217,11 +217,11 @@ __global__ void __launch_bounds__(SPMM_BLOCK + 32, MINB) csr_spmm_ring_kernel(Sp
   __syncthreads();
 
   const i64 rows = a.rows;
-  // tile sequence of this CTA: round-robin over the grid, or (per_cta > 0) a contiguous run of tiles, so that the X
-  // rows a tile leaves in L1 serve the neighbouring tiles' gathers (banded operators)
-  const i64 t_first = per_cta > 0 ? (i64)blockIdx.x * per_cta : (i64)blockIdx.x;
-  const i64 t_step = per_cta > 0 ? 1 : (i64)gridDim.x;
-  const i64 t_end = per_cta > 0 ? min(t_first + per_cta, num_tiles) : num_tiles;
+  // tile sequence of this CTA: runs of `run` consecutive tiles, the runs dealt round-robin over the grid — the X
+  // rows a tile leaves in L1 serve the next tile's gathers (banded operators) while all CTAs still sweep the matrix
+  // together, so far neighbours stay in L2.  n-th tile of this CTA:
+  const i64 run = per_cta > 0 ? per_cta : 1;
+  auto tile_of = [&](i64 n) { return ((n / run) * (i64)gridDim.x + (i64)blockIdx.x) * run + (n % run); };
   if (tid >= BLOCK) {
     // ------------------------------ producer warp ---------------------------
     const int pl = tid - BLOCK;
@@ -232,8 +232,9 @@ __global__ void __launch_bounds__(SPMM_BLOCK + 32, MINB) csr_spmm_ring_kernel(Sp
     int off[OQ], noff[OQ];
     int s = 0, s0 = 0, s1 = 0;
     uint32_t ph = 0;
-    i64 tile = t_first;
-    if (tile < t_end) {
+    i64 tn = 0;
+    i64 tile = tile_of(0);
+    if (tile < num_tiles) {
       const i64 r0 = tile * R;
       const int nr = (int)min((i64)R, rows - r0);
 #pragma unroll
@@ -241,13 +242,13 @@ __global__ void __launch_bounds__(SPMM_BLOCK + 32, MINB) csr_spmm_ring_kernel(Sp
       s0 = ld_ro(a.Ap + r0);
       s1 = ld_ro(a.Ap + r0 + nr);
     }
-    while (tile < t_end) {
+    while (tile < num_tiles) {
       const int nr = (int)min((i64)R, rows - tile * R);
-      const i64 next = tile + t_step;
+      const i64 next = tile_of(++tn);
       int n0 = 0, n1 = 0;
 #pragma unroll
       for (int q = 0; q < OQ; ++q) noff[q] = 0;
-      if (next < t_end) {  // the next tile's offsets: in flight while this tile is issued
+      if (next < num_tiles) {  // the next tile's offsets: in flight while this tile is issued
         const i64 r0 = next * R;
         const int nnr = (int)min((i64)R, rows - r0);
 #pragma unroll
@@ -296,7 +297,9 @@ __global__ void __launch_bounds__(SPMM_BLOCK + 32, MINB) csr_spmm_ring_kernel(Sp
     const T *Xl = a.X + (col_ok ? lane * V : 0);
     int s = 0;
     uint32_t ph = 0;
-    for (i64 tile = t_first; tile < t_end; tile += t_step) {
+    for (i64 tn = 0;; ++tn) {
+      const i64 tile = tile_of(tn);
+      if (tile >= num_tiles) break;  // the tiles of a CTA ascend: nothing behind the first one past the end
       const i64 r0 = tile * R;
       const int nr = (int)min((i64)R, rows - r0);
       int lo = -1, s1 = 0;
@@ -403,12 +406,11 @@ static b200sp_status launch_spmm_ring_m(b200sp_handle h, cudaStream_t st, const 
   // persistent, one wave; MINB CTAs per SM, the rest of the unified array stays L1 for the X rows
   i64 grid = (i64)h->num_sms * (resident < MINB ? resident : MINB);
   if (grid > num_tiles) grid = num_tiles;
-  // tiles are dealt round-robin; B200SP_SPMM_BLOCKED=1 gives every CTA one contiguous run of tiles instead
-  // (measured slower on poisson7pt 256^3: k = 32 fp32 2.23 against 1.90 ms — the L1 does not hold three tiles of X
-  // rows, and neighbouring CTAs stop sharing their z-neighbours in L2)
-  const char *bl = getenv("B200SP_SPMM_BLOCKED");
-  i64 per_cta = (bl && bl[0] == '1') ? ceil_div(num_tiles, grid) : 0;
-  if (per_cta > 0) grid = ceil_div(num_tiles, per_cta);
+  // runs of consecutive tiles per CTA, the runs dealt round-robin (kernel header); B200SP_SPMM_RUN overrides
+  const char *rn = getenv("B200SP_SPMM_RUN");
+  i64 per_cta = rn ? atoi(rn) : 1;
+  if (per_cta < 1) per_cta = 1;
+  if (grid * per_cta > num_tiles) grid = ceil_div(num_tiles, per_cta);
   kern<<<(unsigned)grid, SPMM_BLOCK + 32, smem, st>>>(a, (int)R, stages, num_tiles, nnz, per_cta, cap);
   B200SP_LAUNCH_CHECK(h, "csr_spmm_ring_kernel");
   return B200SP_OK;
