@@ -518,9 +518,22 @@ static b200sp_status spmv_host_pipelined_dia(b200sp_handle h, cudaStream_t st, c
   if (const char *e = getenv("B200SP_HOST_CHUNKS")) want_chunks = atoi(e) >= 3 ? atoi(e) : want_chunks;
   i64 chunk = ((ceil_div(rows, (i64)want_chunks) + 1023) / 1024) * 1024;
   if (chunk < lo + 1024 || chunk < up + 1024) return B200SP_OK;  // band wider than a chunk: nothing to overlap
-  const int nch = (int)ceil_div(rows, chunk);
-  if (nch < 3) return B200SP_OK;
-  const int npieces = nch;  // piece p = local columns [p*chunk, (p+1)*chunk), the last one runs to local_cols
+  if (ceil_div(rows, chunk) < 3) return B200SP_OK;
+  // Chunk boundaries (rows; the x pieces use the same boundaries as local columns, the last piece runs to local_cols).
+  // Uniform: chunks that ramp from the smallest size the band allows at both ends to the uniform size in the middle
+  // (so that the D2H direction starts after 0.04 instead of 0.35 ms) were measured and bought nothing — 3.417 against
+  // 3.417 ms, 3.38 against 3.32 with y stored straight to host: the steady state, not the fill, sets the time
+  // (tools/host_pipe_trace.py, tools/pcie_probe.py: 38 - 40 GB/s each way once kernels run between the copies,
+  // 48 - 49 GB/s for the same copy pattern without them).
+  std::vector<i64> bnd;
+  for (i64 b = 0; b < rows; b += chunk) bnd.push_back(b);
+  bnd.push_back(rows);
+  const int nch = (int)bnd.size() - 1;
+  const int npieces = nch;  // piece p = local columns [bnd[p], bnd[p+1]), the last one runs to local_cols
+  auto piece_of = [&](i64 col) {
+    int p = (int)(std::upper_bound(bnd.begin(), bnd.end(), col) - bnd.begin()) - 1;
+    return p < 0 ? 0 : (p > npieces - 1 ? npieces - 1 : p);
+  };
 
   if (!h->copy_in_stream) {
     cudaStream_t a, b;
@@ -530,9 +543,16 @@ static b200sp_status spmv_host_pipelined_dia(b200sp_handle h, cudaStream_t st, c
     h->copy_out_stream = b;
   }
   const size_t need_events = (size_t)2 * nch + 2;
+  const char *trace_env = getenv("B200SP_HOST_TRACE");  // 1: print the pipeline's timeline (ms since its start) to stderr
+  const bool trace = trace_env && trace_env[0] == '1';
+  if (trace && !h->pipe_events_timed) {  // events so far were created without timing: replace them once
+    for (void *e : h->pipe_events) cudaEventDestroy((cudaEvent_t)e);
+    h->pipe_events.clear();
+    h->pipe_events_timed = true;
+  }
   while (h->pipe_events.size() < need_events) {
     cudaEvent_t e;
-    B200SP_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    B200SP_CUDA(h, cudaEventCreateWithFlags(&e, h->pipe_events_timed ? cudaEventDefault : cudaEventDisableTiming));
     h->pipe_events.push_back(e);
   }
   cudaStream_t cin = (cudaStream_t)h->copy_in_stream, cout = (cudaStream_t)h->copy_out_stream;
@@ -549,6 +569,19 @@ static b200sp_status spmv_host_pipelined_dia(b200sp_handle h, cudaStream_t st, c
   char *dx = reinterpret_cast<char *>(h->stage_x), *dy = reinterpret_cast<char *>(h->stage_y);
   const char *hx = reinterpret_cast<const char *>(x_host);
   char *hy = reinterpret_cast<char *>(y_host);
+  // Pinned (device-mapped) y: the chunk products store y straight into host memory — posted PCIe writes from the
+  // SMs — instead of into a staging buffer that a second DMA stream then copies down.  One stream fewer, no
+  // per-chunk D2H launch, the last chunk's copy-out no longer trails the pipeline.  B200SP_HOST_Y_DIRECT=0 keeps the
+  // staged form; pageable y always takes it.
+  char *y_direct = nullptr;
+  {
+    const char *e = getenv("B200SP_HOST_Y_DIRECT");
+    cudaPointerAttributes pa;
+    if (!(e && e[0] == '0') && cudaPointerGetAttributes(&pa, y_host) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
+        pa.devicePointer != nullptr)
+      y_direct = reinterpret_cast<char *>(pa.devicePointer);
+    cudaGetLastError();
+  }
   B200SP_CUDA(h, cudaEventRecord(ev(0), st));  // staging buffers are free once prior work on `st` is done
   B200SP_CUDA(h, cudaStreamWaitEvent(cin, ev(0), 0));
   B200SP_CUDA(h, cudaStreamWaitEvent(cout, ev(0), 0));
@@ -561,7 +594,7 @@ static b200sp_status spmv_host_pipelined_dia(b200sp_handle h, cudaStream_t st, c
   for (int k = 0; k < npieces; ++k) {
     const int p = order[(size_t)k];
     ord_of[(size_t)p] = k;
-    const i64 c0 = (i64)p * chunk, c1 = (p == npieces - 1) ? local_cols : std::min(local_cols, c0 + chunk);
+    const i64 c0 = bnd[(size_t)p], c1 = (p == npieces - 1) ? local_cols : std::min(local_cols, bnd[(size_t)p + 1]);
     if (c1 > c0)
       B200SP_CUDA(h, cudaMemcpyAsync(dx + (size_t)(hlo + c0) * elem, hx + (size_t)c0 * elem, (size_t)(c1 - c0) * elem,
                                      cudaMemcpyHostToDevice, cin));
@@ -573,13 +606,12 @@ static b200sp_status spmv_host_pipelined_dia(b200sp_handle h, cudaStream_t st, c
     if (s != B200SP_OK) return s;
   }
   for (int c = 0; c < nch; ++c) {
-    const i64 r0 = (i64)c * chunk, r1 = std::min(rows, r0 + chunk);
+    const i64 r0 = bnd[(size_t)c], r1 = bnd[(size_t)c + 1];
     // window columns the chunk reads -> local pieces -> the one uploaded last
     i64 first_col = r0 - lo - hlo, last_col = std::min(cols, r1 + up) - 1 - hlo;  // in local coordinates
     if (first_col < 0) first_col = 0;
     if (last_col > local_cols - 1) last_col = local_cols - 1;
-    int p_lo = (int)(first_col / chunk), p_hi = (int)(last_col / chunk);
-    if (p_hi > npieces - 1) p_hi = npieces - 1;
+    int p_lo = piece_of(first_col), p_hi = piece_of(last_col);
     if (p_lo > p_hi) p_lo = p_hi;
     int wait_ord = 0;
     for (int p = p_lo; p <= p_hi; ++p) wait_ord = std::max(wait_ord, ord_of[(size_t)p]);
@@ -596,8 +628,9 @@ static b200sp_status spmv_host_pipelined_dia(b200sp_handle h, cudaStream_t st, c
       xp = dx + (size_t)(r0 - lo) * elem;
     }
     sub.num_entries = 0;
-    s = b200sp_spmv(h, (b200sp_stream)st, &sub, xp, dy + (size_t)r0 * elem, 0, cfg);
+    s = b200sp_spmv(h, (b200sp_stream)st, &sub, xp, (y_direct ? y_direct : dy) + (size_t)r0 * elem, 0, cfg);
     if (s != B200SP_OK) return s;
+    if (y_direct) continue;
     B200SP_CUDA(h, cudaEventRecord(ev(1 + (size_t)nch + (size_t)c), st));
     B200SP_CUDA(h, cudaStreamWaitEvent(cout, ev(1 + (size_t)nch + (size_t)c), 0));
     B200SP_CUDA(h, cudaMemcpyAsync(hy + (size_t)r0 * elem, dy + (size_t)r0 * elem, (size_t)(r1 - r0) * elem,
@@ -606,6 +639,22 @@ static b200sp_status spmv_host_pipelined_dia(b200sp_handle h, cudaStream_t st, c
   B200SP_CUDA(h, cudaEventRecord(ev(1 + 2 * (size_t)nch), cout));
   B200SP_CUDA(h, cudaStreamWaitEvent(st, ev(1 + 2 * (size_t)nch), 0));
   B200SP_CUDA(h, cudaStreamSynchronize(st));
+  if (trace) {
+    B200SP_CUDA(h, cudaStreamSynchronize(cin));
+    B200SP_CUDA(h, cudaStreamSynchronize(cout));
+    fprintf(stderr, "[b200sp host pipeline] %d chunks%s; x piece up / product done%s (ms since start)\n", nch,
+            y_direct ? ", y stored straight to host" : "", y_direct ? "" : " (the D2H copy follows it)");
+    for (int c = 0; c < nch; ++c) {
+      float up_ms = 0.f, pr_ms = 0.f;
+      cudaEventElapsedTime(&up_ms, ev(0), ev(1 + (size_t)ord_of[(size_t)c]));
+      if (!y_direct) cudaEventElapsedTime(&pr_ms, ev(0), ev(1 + (size_t)nch + (size_t)c));
+      fprintf(stderr, "  chunk %2d rows %9lld  x up %.3f  product %.3f\n", c, (long long)(bnd[(size_t)c + 1] - bnd[(size_t)c]), up_ms, pr_ms);
+    }
+    float end_ms = 0.f;
+    if (!y_direct) cudaEventElapsedTime(&end_ms, ev(0), ev(1 + 2 * (size_t)nch));
+    fprintf(stderr, "  last D2H done %.3f\n", end_ms);
+    cudaGetLastError();
+  }
   *done = 1;
   return B200SP_OK;
 }

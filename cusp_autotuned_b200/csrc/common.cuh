@@ -74,6 +74,7 @@ struct b200sp_context {
   // pipelined host path (b200sp_spmv_host on banded matrices): copy streams + events
   void *copy_in_stream = nullptr, *copy_out_stream = nullptr;
   std::vector<void *> pipe_events;
+  bool pipe_events_timed = false;  // B200SP_HOST_TRACE=1: the pipeline's events carry timestamps
   // CG workspace
   void *cg_ws = nullptr;
   size_t cg_ws_bytes = 0;
