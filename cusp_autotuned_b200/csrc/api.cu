@@ -571,13 +571,15 @@ static b200sp_status spmv_host_pipelined_dia(b200sp_handle h, cudaStream_t st, c
   char *hy = reinterpret_cast<char *>(y_host);
   // Pinned (device-mapped) y: the chunk products store y straight into host memory — posted PCIe writes from the
   // SMs — instead of into a staging buffer that a second DMA stream then copies down.  One stream fewer, no
-  // per-chunk D2H launch, the last chunk's copy-out no longer trails the pipeline.  B200SP_HOST_Y_DIRECT=0 keeps the
-  // staged form; pageable y always takes it.
+  // per-chunk D2H launch, the last chunk's copy-out no longer trails the pipeline: 3.41 -> 3.31 ms per step on one GPU.
+  // With several GPUs behind one host the SM-issued writes lose to the copy engines (2 GPUs: 4.54 against 4.09 ms), so
+  // the partitioned form keeps the staged y.  B200SP_HOST_Y_DIRECT=0 / 1 forces either; pageable y is always staged.
   char *y_direct = nullptr;
   {
     const char *e = getenv("B200SP_HOST_Y_DIRECT");
     cudaPointerAttributes pa;
-    if (!(e && e[0] == '0') && cudaPointerGetAttributes(&pa, y_host) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
+    const bool want = e ? e[0] == '1' : halo == nullptr;  // default: one GPU only (see above)
+    if (want && cudaPointerGetAttributes(&pa, y_host) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
         pa.devicePointer != nullptr)
       y_direct = reinterpret_cast<char *>(pa.devicePointer);
     cudaGetLastError();
