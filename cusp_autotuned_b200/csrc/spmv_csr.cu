@@ -650,7 +650,15 @@ static void csr_defaults(b200sp_cfg &c, i64 rows, i64 nnz, size_t elem, const Cs
     // longer rows -> lane-per-entry sub-warps (VECTOR).  cusp::ktt::tune refines per matrix.
     if (mean <= 12.0 && cs.banded)
       c.kernel = (rows >= (i64)B200SP_NUM_SMS_FALLBACK * 4 * 256 * 2) ? B200SP_K_CSR_RING : B200SP_K_CSR_STREAM;
-    else
+    else if (!cs.banded && mean >= 192.0 && c.block_size == 0 && c.unroll == 0) {
+      // long rows, scattered columns (BASELINE configs[3] at 256 nnz/row): every row piece is longer than CSR_LONG, so
+      // the stream kernel gives each to a warp that reads its entries from the bulk-copied chunk — 1.005 - 1.012 ms
+      // against 1.087 - 1.094 for the sub-warp kernel on 2^20 x 256 fp32 (profiles/r01_sweep_random.json, the tuned
+      // best of every bench line), which is the rate of a bare gather of that column stream (r04_gather_probe.md)
+      c.kernel = B200SP_K_CSR_STREAM;
+      c.block_size = (elem == 4) ? 128 : 256;
+      c.unroll = 8;
+    } else
       c.kernel = B200SP_K_CSR_VECTOR;  // scattered columns: lane-per-entry keeps the matrix stream coalesced
   }
   if (c.kernel == B200SP_K_CSR_RING) {
