@@ -97,8 +97,6 @@ struct b200sp_context {
   std::map<CsrKey, int> csr_max_row;
   // COO gather-order probe per (column_indices pointer, element size, nnz): 1 = ring kernel
   std::map<CsrKey, int> coo_gather_order;
-  // longest ELL row range a COO-tail tile would own in the fused HYB kernel, per (row_indices, rows*4096+tile, nnz)
-  std::map<CsrKey, long long> hyb_tile_range;
   std::vector<void *> tune_events;  // cudaEvent_t pair
   // K_COO_WARP on >= 2^27 scattered entries: persistent grid (1) or one tile per warp (0), whichever was faster on
   // the first product with these arrays (spmv_coo.cu: coo_warp_grid_choice); same tiles, same bits either way
