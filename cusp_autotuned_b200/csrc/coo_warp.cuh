@@ -156,7 +156,11 @@ __device__ __noinline__ void hyb_gap(const HybEll<T> &e, const T *x, T *y, unsig
 // rows themselves — a row that ends here is stored as init + ELL slots + tail sum by the lane that sees its end, runs
 // of rows without tail entries between two entries of the tile go to hyb_gap; other tiles accumulate into the y
 // their warp has just initialised (a.accumulate = 1).
-template <typename T, int VPL, int U, int XPOL, int SPOL, bool TABLE, typename Ops, bool HYB = false>
+// PREY (y += A x on tails whose entries mostly end a row — one entry per row): the y values of the rows that end at an
+// entry are fetched together with the x gathers instead of by a read-modify-write after the scan — two dependent
+// round trips per tile instead of three; every row has one writer in this kernel, so the early read sees the same
+// value, and the same two operands are added: bit-identical.
+template <typename T, int VPL, int U, int XPOL, int SPOL, bool TABLE, typename Ops, bool HYB = false, bool PREY = false>
 __device__ __forceinline__ void coo_warp_tile(const CooArgs<T> &a, const i64 tile, const int lane, const T *tab,
                                               const uint64_t pol, const HybEll<T> *hyb = nullptr,
                                               const bool owner = false) {
@@ -213,6 +217,24 @@ __device__ __forceinline__ void coo_warp_tile(const CooArgs<T> &a, const i64 til
         xv[u][q] = ld_x<XPOL>(a.x + min((unsigned)cc, cols - 1));
     }
 
+  T yv[PREY ? U : 1][PREY ? VPL : 1];
+  if (PREY) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int rn = __shfl_down_sync(FULL, r[u][0], 1);
+      int r_after = next_row;
+      if (u + 1 < U) r_after = __shfl_sync(FULL, r[(u + 1 < U) ? u + 1 : u][0], 0);
+      if (lane == 31) rn = r_after;
+#pragma unroll
+      for (int q = 0; q < VPL; ++q) {
+        const int nxt = (q + 1 < VPL) ? r[u][(q + 1 < VPL) ? q + 1 : q] : rn;
+        T t = Ops::identity();
+        if (a.accumulate && r[u][q] >= 0 && r[u][q] != nxt) t = a.y[r[u][q]];
+        yv[PREY ? u : 0][PREY ? q : 0] = t;
+      }
+    }
+  }
+
   T wcarry = Ops::identity();  // the open row's sum since its last row end in earlier units of this tile
   bool seen_end = false;  // a row ended earlier in this tile (warp-uniform)
   CooCarry<T> *rec = a.carry + tile;
@@ -224,7 +246,7 @@ __device__ __forceinline__ void coo_warp_tile(const CooArgs<T> &a, const i64 til
     if (lane == 31) rn = r_after;
 
     // serial segmented reduction over the lane's VPL consecutive entries
-    T run = Ops::identity(), head = Ops::identity();
+    T run = Ops::identity(), head = Ops::identity(), head_y = Ops::identity();
     int head_row = -1;
     bool has_b = false;
 #pragma unroll
@@ -236,10 +258,12 @@ __device__ __forceinline__ void coo_warp_tile(const CooArgs<T> &a, const i64 til
         if (!has_b) {
           head = run;
           head_row = r[u][q];
+          if (PREY) head_y = yv[PREY ? u : 0][PREY ? q : 0];
           has_b = true;
         } else {
           // began and ended inside this lane
           if (HYB && owner) a.y[r[u][q]] = hyb_row_init(*hyb, a.x, a.y, cols, r[u][q]) + run;
+          else if (PREY) a.y[r[u][q]] = a.accumulate ? Ops::reduce(yv[PREY ? u : 0][PREY ? q : 0], run) : run;
           else coo_store_y<T, Ops>(a.y, r[u][q], run, a.accumulate);
         }
         run = Ops::identity();
@@ -270,10 +294,12 @@ __device__ __forceinline__ void coo_warp_tile(const CooArgs<T> &a, const i64 til
         rec->head_val = continued ? total : Ops::identity();
         if (!continued) {
           if (HYB && owner) a.y[head_row] = hyb_row_init(*hyb, a.x, a.y, cols, head_row) + total;
+          else if (PREY) a.y[head_row] = a.accumulate ? Ops::reduce(head_y, total) : total;
           else coo_store_y<T, Ops>(a.y, head_row, total, a.accumulate);
         }
       } else {
         if (HYB && owner) a.y[head_row] = hyb_row_init(*hyb, a.x, a.y, cols, head_row) + total;
+        else if (PREY) a.y[head_row] = a.accumulate ? Ops::reduce(head_y, total) : total;
         else coo_store_y<T, Ops>(a.y, head_row, total, a.accumulate);
       }
     }
@@ -294,7 +320,8 @@ __device__ __forceinline__ void coo_warp_tile(const CooArgs<T> &a, const i64 til
   }
 }
 
-template <typename T, int BLOCK, int MINB, int VPL, int U, int XPOL, int SPOL, bool TABLE, typename Ops = SpmvOps<T, 0, 0>>
+template <typename T, int BLOCK, int MINB, int VPL, int U, int XPOL, int SPOL, bool TABLE, typename Ops = SpmvOps<T, 0, 0>,
+          bool PREY = false>
 __global__ void __launch_bounds__(BLOCK, MINB) coo_warp_kernel(CooArgs<T> a, i64 num_tiles, const int *hot_cols,
                                                                int hot) {
   extern __shared__ __align__(16) unsigned char coo_warp_smem[];
@@ -307,10 +334,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) coo_warp_kernel(CooArgs<T> a, i64
   const i64 stride = (i64)gridDim.x * (BLOCK / 32);
   const uint64_t pol = SPOL ? l2_policy_evict_first() : 0;
   for (i64 tile = (i64)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); tile < num_tiles; tile += stride)
-    coo_warp_tile<T, VPL, U, XPOL, SPOL, TABLE, Ops>(a, tile, lane, tab, pol);
+    coo_warp_tile<T, VPL, U, XPOL, SPOL, TABLE, Ops, false, PREY>(a, tile, lane, tab, pol);
 }
 
-template <typename T, int BLOCK, int MINB, int VPL, int U, int XPOL, int SPOL, bool TABLE, typename Ops = SpmvOps<T, 0, 0>>
+template <typename T, int BLOCK, int MINB, int VPL, int U, int XPOL, int SPOL, bool TABLE, typename Ops = SpmvOps<T, 0, 0>,
+          bool PREY = false>
 static b200sp_status launch_coo_warp(b200sp_handle h, cudaStream_t st, CooArgs<T> a, int ctas_per_sm,
                                      const int *hot_cols, int hot, int capacity) {
   constexpr int WT = 32 * VPL * U;
@@ -318,7 +346,7 @@ static b200sp_status launch_coo_warp(b200sp_handle h, cudaStream_t st, CooArgs<T
   b200sp_status s = ensure_scratch(h, (size_t)tiles * sizeof(CooCarry<T>));
   if (s != B200SP_OK) return s;
   a.carry = reinterpret_cast<CooCarry<T> *>(h->scratch);
-  auto kern = coo_warp_kernel<T, BLOCK, MINB, VPL, U, XPOL, SPOL, TABLE, Ops>;
+  auto kern = coo_warp_kernel<T, BLOCK, MINB, VPL, U, XPOL, SPOL, TABLE, Ops, PREY>;
   const size_t smem = TABLE ? (size_t)capacity * sizeof(T) : 0;
   if constexpr (TABLE) {
     if (smem > (size_t)h->max_smem_optin)

@@ -9,6 +9,8 @@
 // ld.global.nc with the default L1 policy (L1::evict_last -3 %, L1::no_allocate -40 %: the L1 hits on hot x sectors
 // matter); entry streams ld.global.cs here, and L1::no_allocate + L2 evict-first in the plan executor, where the
 // table leaves little L1 (0.89 ms against 0.99 ms).
+#include <stdlib.h>
+
 #include "coo_warp.cuh"
 
 namespace b200sp {
@@ -22,6 +24,19 @@ b200sp_status spmv_coo_warp(b200sp_handle h, cudaStream_t st, CooArgs<T> a, cons
   const uintptr_t need_idx = (uintptr_t)(4 * vpl) - 1, need_val = (uintptr_t)(sizeof(T) * vpl > 32 ? 32 : sizeof(T) * vpl) - 1;
   if (((uintptr_t)a.Ai & need_idx) || ((uintptr_t)a.Aj & need_idx) || ((uintptr_t)a.Ax & need_val))
     return set_error(h, B200SP_INVALID_INPUT, "coo warp: arrays not aligned for %d-entry vector loads", vpl);
+  // y += A x with 128-bit tiles (the shape of one-entry-per-row HYB tails): y of the row ends is fetched with the x
+  // gathers (PREY, coo_warp.cuh) — B200SP_COO_PREY=0 keeps the read-modify-write after the scan
+  const char *pe = getenv("B200SP_COO_PREY");
+  const bool prey = a.accumulate && vpl == 4 && !(pe && pe[0] == '0');
+#define CASEP(V, UU, MINB)    \
+  if (prey && vpl == V && u == UU) \
+    return launch_coo_warp<T, 256, MINB, V, UU, 0, 0, false, SpmvOps<T, 0, 0>, true>(h, st, a, c.ctas_per_sm, nullptr, 0, 0);
+  if constexpr (sizeof(T) == 4) {
+    CASEP(4, 1, 6) CASEP(4, 2, 4)
+  } else {
+    CASEP(4, 1, 4) CASEP(4, 2, 3)
+  }
+#undef CASEP
 #define CASE(V, UU, MINB) \
   if (vpl == V && u == UU) return launch_coo_warp<T, 256, MINB, V, UU, 0, 0, false>(h, st, a, c.ctas_per_sm, nullptr, 0, 0);
   if constexpr (sizeof(T) == 4) {
