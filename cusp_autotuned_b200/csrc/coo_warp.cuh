@@ -173,22 +173,27 @@ __device__ __forceinline__ void coo_warp_tile(const CooArgs<T> &a, const i64 til
 
   int r[U][VPL], c[U][VPL];
   T v[U][VPL];
-  if (n == WT && !a.scalar_loads) {
+  bool vector_loads = false;
+  if constexpr (VPL >= 4) {  // VPL = 1: a lane takes every 32nd entry of a unit — scalar, fully coalesced loads (below)
+    vector_loads = n == WT && !a.scalar_loads;
+    if (vector_loads) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const i64 e0 = start + u * UNIT + lane * VPL;
-      uint32_t wr[VPL], wc[VPL], wv[VW];
-      ld_words<SPOL, VPL>(a.Ai + e0, wr, pol);
-      ld_words<SPOL, VPL>(a.Aj + e0, wc, pol);
-      ld_words<SPOL, VW>(a.Ax + e0, wv, pol);
+      for (int u = 0; u < U; ++u) {
+        const i64 e0 = start + u * UNIT + lane * VPL;
+        uint32_t wr[VPL], wc[VPL], wv[VW > 0 ? VW : 1];
+        ld_words<SPOL, VPL>(a.Ai + e0, wr, pol);
+        ld_words<SPOL, VPL>(a.Aj + e0, wc, pol);
+        ld_words<SPOL, VW>(a.Ax + e0, wv, pol);
 #pragma unroll
-      for (int q = 0; q < VPL; ++q) {
-        r[u][q] = (int)wr[q];
-        c[u][q] = (int)wc[q];
-        v[u][q] = from_words(wv + q * ((int)sizeof(T) / 4), T());
+        for (int q = 0; q < VPL; ++q) {
+          r[u][q] = (int)wr[q];
+          c[u][q] = (int)wc[q];
+          v[u][q] = from_words(wv + q * ((int)sizeof(T) / 4), T());
+        }
       }
     }
-  } else {  // the last tile of the matrix (or unaligned arrays): guarded scalar loads, absent entries get row -1
+  }
+  if (!vector_loads) {  // the last tile of the matrix (or unaligned arrays): guarded scalar loads, absent entries get row -1
 #pragma unroll
     for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -277,10 +282,12 @@ __device__ __forceinline__ void coo_warp_tile(const CooArgs<T> &a, const i64 til
     const unsigned le = m & (FULL >> (31 - lane));  // row ends at lanes <= this one
     const int j = le ? 31 - __clz(le) : 0;          // the scan of this lane reaches back to lane j
     T vi = run;
+    if (m != FULL) {  // every lane saw a row end (one entry per row): nothing crosses a lane, no scan
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const T up = __shfl_up_sync(FULL, vi, d);
-      if (lane - d >= j) vi = Ops::reduce(up, vi);
+      for (int d = 1; d < 32; d <<= 1) {
+        const T up = __shfl_up_sync(FULL, vi, d);
+        if (lane - d >= j) vi = Ops::reduce(up, vi);
+      }
     }
     const T Vi = (le == 0) ? Ops::reduce(wcarry, vi) : vi;  // no row end so far in this unit: the earlier units' sum joins
     T cin = __shfl_up_sync(FULL, Vi, 1);
