@@ -5,11 +5,15 @@
 //     acc[j] = init(Y(i,j));  for jj ascending: acc[j] += Ax[jj] * X(Aj[jj], j);  Y(i,j) = acc[j]
 // — per (row, column) the same summation order, so results are bit-identical to it (-fmad=false).
 //
-// Kernel: a sub-warp of K lanes (K = 8, 16 or 32 >= min(k,32)) owns a row; lane j < k owns column j
-// of the block.  The K lanes load K consecutive entries of the row coalesced (ld.global.cs) and
-// hand them round with shuffles, so every entry costs one coalesced K*sizeof(T) gather of X
-// (ld.global.nc) with 8 gathers in flight per lane.  Blocks wider than 32 columns are processed
-// in column chunks of 32.  No shared memory (the reference stages the entries there).
+// Two kernels:
+//   * csr_spmm_ring_kernel (default; needs 16-byte-aligned matrix arrays): persistent CTAs, the matrix streams
+//     staged by a producer warp with cp.async.bulk into an mbarrier ring, a lane owning 4 fp32 / 2 fp64 adjacent
+//     columns of the block (128-bit gathers of X, 128-bit stores of Y) — described at the kernel below;
+//   * csr_spmm_kernel (round 1; unaligned arrays, B200SP_SPMM_LDG=1): a sub-warp of K lanes (K = 2..32 >= min(k,32))
+//     owns a row, lane j < k owns column j; the K lanes load K consecutive entries of the row coalesced
+//     (ld.global.cs) and hand them round with shuffles, one coalesced K*sizeof(T) gather of X (ld.global.nc) per
+//     entry, no shared memory.
+// Blocks wider than one pass (64 fp32 columns with 128-bit accesses, otherwise 32) are processed in column chunks.
 // Algorithmic bytes: (rows+1)*4 + nnz*(4+V) + cols*k*V + rows*k*V.
 #include <stdlib.h>
 
