@@ -146,9 +146,38 @@ __global__ void __launch_bounds__(288) release_order_kernel(const int *__restric
   if (sink == 0x7ff4dead) atomicAdd(bad + 1, 1ull);  // keeps the gathers alive
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// dma_fed_kernel: can ONE resident kernel, fed by the copy engine, keep both PCIe directions busy?  (The host
+// pipeline of b200sp_spmv_host chains copy -> kernel -> copy per chunk with stream events and reaches 40 GB/s each
+// way; the same copies without kernels reach 48.)  The host queues, on one copy stream, for every chunk k: the H2D
+// copy of x piece k, then a 4-byte H2D copy that sets flag[k] = epoch.  This kernel is launched once on another
+// stream; its CTAs walk the chunks in order, spin on flag[k + lag] and then stream chunk k from the device staging
+// buffer to y in MAPPED HOST memory (y = 2 x: a stand-in for the chunk product, which adds 58 MB of HBM reads per chunk).
+__global__ void __launch_bounds__(256) dma_fed_kernel(const double *__restrict__ x_dev, double *__restrict__ y_host,
+                                                      long long n, int chunks, int lag, const volatile int *flag,
+                                                      int epoch) {
+  const long long per = (n + chunks - 1) / chunks;
+  for (int k = 0; k < chunks; ++k) {
+    const int need = min(k + lag, chunks - 1);
+    if (threadIdx.x == 0)
+      while (flag[need] != epoch) __nanosleep(200);
+    __syncthreads();
+    __threadfence();
+    const long long b = (long long)k * per, e = min(n, b + per);
+    for (long long i = b + (long long)blockIdx.x * 256 + threadIdx.x; i < e; i += (long long)gridDim.x * 256)
+      y_host[i] = 2.0 * __ldcv(x_dev + i);
+  }
+}
+
 }  // namespace
 
 extern "C" {
+int probe_dma_fed(const double *x_dev, double *y_host_mapped, long long n, int chunks, int lag, const int *flag, int epoch,
+                  int ctas, void *stream) {
+  dma_fed_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>(x_dev, y_host_mapped, n, chunks, lag, flag, epoch);
+  return (int)cudaGetLastError();
+}
+
 // mode 0..3 as above; `bad` (device, zeroed by the caller) receives the number of stale values seen
 int probe_release_order(int mode, long long tiles, int period, int stages, int ctas, const int *src,
                         unsigned long long *bad, void *stream) {
