@@ -16,6 +16,8 @@
 //                                                               (csr_to_other.h:73-153)
 // Callers size the outputs from the query calls (max row length, HYB width + tail size,
 // number of diagonals); those return scalars to the host and synchronise the stream.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200sp {
@@ -112,13 +114,26 @@ __global__ void indices_to_offsets_kernel(i64 rows, i64 nnz, const int *Ai, int 
 // ---------------------------------------------------------------------------
 // queries
 // ---------------------------------------------------------------------------
+// The histogram goes through a per-CTA shared-memory copy of its first 1024 bins: on a stencil every row has the same
+// length, and 10^7 global atomics on one word took ~10 ms (most of what csr -> ell / hyb cost at 256^3).
 __global__ void row_length_stats_kernel(i64 rows, const int *Ap, int *max_len, unsigned int *hist, int hist_len) {
+  constexpr int SBINS = 1024;
+  __shared__ unsigned int s_hist[SBINS];
+  const int sb = hist ? min(hist_len, SBINS) : 0;
+  for (int i = threadIdx.x; i < sb; i += blockDim.x) s_hist[i] = 0u;
+  __syncthreads();
   int m = 0;
   for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (i64)gridDim.x * blockDim.x) {
     const int len = Ap[r + 1] - Ap[r];
     m = max(m, len);
-    if (hist && len < hist_len) atomicAdd(hist + len, 1u);
+    if (hist && len >= 0 && len < hist_len) {
+      if (len < sb) atomicAdd(s_hist + len, 1u);
+      else atomicAdd(hist + len, 1u);
+    }
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < sb; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(hist + i, s_hist[i]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) atomicMax(max_len, m);
@@ -187,7 +202,12 @@ __global__ void mark_diagonals_kernel(i64 rows, const int *Ap, const int *Aj, in
   const int lane = threadIdx.x & 31;
   for (i64 r = warp; r < rows; r += ((i64)gridDim.x * blockDim.x) >> 5) {
     const int lo = Ap[r], hi = Ap[r + 1];
-    for (int j = lo + lane; j < hi; j += 32) flags[(i64)Aj[j] - r + rows] = 1;  // benign race: all writers store 1
+    for (int j = lo + lane; j < hi; j += 32) {
+      int *f = flags + ((i64)Aj[j] - r + rows);
+      // benign race: all writers store 1.  Look first: a banded operator has a handful of diagonals, and 10^8 stores
+      // to the same few words serialise in L2 where the reads are served from L1
+      if (__ldca(f) == 0) *f = 1;  // a stale 0 from L1 only costs a repeated store
+    }
   }
 }
 __global__ void compact_diagonals_kernel(i64 n, i64 rows, const int *flags, const int *pos, int *offsets) {
@@ -204,6 +224,27 @@ __global__ void csr_to_dia_fill_kernel(i64 rows, i64 pitch, const int *Ap, const
     // duplicates inside a row: the last one in CSR order wins, like thrust::scatter in the reference
     for (int j = lo + lane; j < hi; j += 32) vals[(i64)pos[(i64)Aj[j] - r + rows] * pitch + r] = Ax[j];
   }
+}
+
+// Few diagonals (<= DIA_TILE_MAXD): a thread takes a row, drops its entries into its own column of a
+// [diagonal][row] tile in shared memory (the last duplicate in CSR order wins) and the CTA writes the tile out slab by
+// slab — every slot of the DIA array written once, coalesced, zeros and padding rows included (no memset of the
+// values), instead of one 4- / 8-byte store per entry scattered over the slabs.
+constexpr int DIA_TILE_MAXD = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256) csr_to_dia_tile_kernel(i64 rows, i64 pitch, int ndiag, const int *Ap, const int *Aj,
+                                                              const T *Ax, const int *pos, T *vals) {
+  __shared__ T tile[DIA_TILE_MAXD][256];
+  const int t = threadIdx.x;
+  const i64 r = (i64)blockIdx.x * 256 + t;
+  for (int d = 0; d < ndiag; ++d) tile[d][t] = T(0);
+  if (r < rows) {
+    const int lo = Ap[r], hi = Ap[r + 1];
+    for (int j = lo; j < hi; ++j) tile[pos[(i64)Aj[j] - r + rows]][t] = Ax[j];
+  }
+  if (r < pitch)
+    for (int d = 0; d < ndiag; ++d) vals[(i64)d * pitch + r] = tile[d][t];
 }
 
 static inline unsigned warp_grid(b200sp_handle h, i64 rows) {
@@ -228,6 +269,48 @@ struct DevTemp {  // cudaMalloc'd scratch freed on scope exit (set-up time code)
   }
 };
 
+// The same conversion through shared memory: a CTA takes 256 consecutive rows, reads their contiguous
+// [Ap[r0], Ap[r0 + 256)) range of Aj / Ax once, coalesced, and writes the K slabs from there (thread = row, one
+// coalesced 256-element piece of each slab per k).  The kernel above reads Aj / Ax with a stride of one row length
+// per thread and once per k — 12.8 ms for poisson7pt 256^3 fp64 against the ~0.5 ms the bytes need.  Tiles whose
+// entries do not fit (ELL_TILE_CAP) are handled by direct reads like above.
+constexpr int ELL_TILE_CAP = 4096;
+
+template <typename T>
+__global__ void __launch_bounds__(256) csr_to_ell_tile_kernel(i64 rows, int K, i64 pitch, const int *Ap, const int *Aj,
+                                                              const T *Ax, int *cidx, T *vals) {
+  __shared__ int s_col[ELL_TILE_CAP];
+  __shared__ T s_val[ELL_TILE_CAP];
+  const i64 r0 = (i64)blockIdx.x * 256;
+  const i64 r = r0 + threadIdx.x;
+  const i64 r_end = min(r0 + 256, rows);
+  const int lo0 = (r0 < rows) ? Ap[r0] : 0, hi0 = (r0 < rows) ? Ap[r_end] : 0;
+  const bool staged = hi0 - lo0 <= ELL_TILE_CAP;
+  if (staged) {
+    for (int j = lo0 + threadIdx.x; j < hi0; j += 256) {
+      s_col[j - lo0] = Aj[j];
+      s_val[j - lo0] = Ax[j];
+    }
+  }
+  __syncthreads();
+  if (r >= pitch) return;
+  int lo = 0, len = 0;
+  if (r < rows) {
+    lo = Ap[r];
+    len = Ap[r + 1] - lo;
+  }
+  for (int k = 0; k < K; ++k) {
+    int c = -1;
+    T v = T(0);
+    if (k < len) {
+      c = staged ? s_col[lo - lo0 + k] : Aj[lo + k];
+      v = staged ? s_val[lo - lo0 + k] : Ax[lo + k];
+    }
+    cidx[(i64)k * pitch + r] = c;
+    vals[(i64)k * pitch + r] = v;
+  }
+}
+
 template <typename T>
 static b200sp_status csr_to_ell_impl(b200sp_handle h, cudaStream_t st, i64 rows, i64 K, i64 pitch, const int *Ap,
                                      const int *Aj, const T *Ax, int *cidx, T *vals) {
@@ -235,6 +318,11 @@ static b200sp_status csr_to_ell_impl(b200sp_handle h, cudaStream_t st, i64 rows,
   B200SP_REQUIRE(h, rows >= 0 && K >= 0 && pitch >= rows && K < 65536, "csr_to_ell: bad dimensions");
   if (K == 0 || pitch == 0) return B200SP_OK;
   B200SP_REQUIRE(h, Ap && cidx && vals, "csr_to_ell: null pointer");
+  if (!getenv("B200SP_CONVERT_DIRECT")) {  // measurement switch: the one-thread-per-(row, k) kernel
+    csr_to_ell_tile_kernel<T><<<(unsigned)ceil_div(pitch, 256), 256, 0, st>>>(rows, (int)K, pitch, Ap, Aj, Ax, cidx, vals);
+    B200SP_LAUNCH_CHECK(h, "csr_to_ell_tile_kernel");
+    return B200SP_OK;
+  }
   const dim3 grid((unsigned)ceil_div(pitch, 256), (unsigned)K);
   csr_to_ell_kernel<T><<<grid, 256, 0, st>>>(rows, (int)K, pitch, Ap, Aj, Ax, cidx, vals);
   B200SP_LAUNCH_CHECK(h, "csr_to_ell_kernel");
@@ -285,10 +373,16 @@ static b200sp_status csr_to_dia_impl(b200sp_handle h, cudaStream_t st, i64 rows,
   compact_diagonals_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(n, rows, reinterpret_cast<int *>(flags.p),
                                                                         reinterpret_cast<int *>(pos.p), offsets);
   B200SP_LAUNCH_CHECK(h, "compact_diagonals_kernel");
-  B200SP_CUDA(h, cudaMemsetAsync(vals, 0, (size_t)pitch * (size_t)ndiag * sizeof(T), st));
-  csr_to_dia_fill_kernel<T><<<warp_grid(h, rows), 256, 0, st>>>(rows, pitch, Ap, Aj, Ax, reinterpret_cast<int *>(pos.p),
-                                                                vals);
-  B200SP_LAUNCH_CHECK(h, "csr_to_dia_fill_kernel");
+  if (ndiag <= DIA_TILE_MAXD && !getenv("B200SP_CONVERT_DIRECT")) {
+    csr_to_dia_tile_kernel<T><<<(unsigned)ceil_div(pitch, 256), 256, 0, st>>>(rows, pitch, (int)ndiag, Ap, Aj, Ax,
+                                                                             reinterpret_cast<int *>(pos.p), vals);
+    B200SP_LAUNCH_CHECK(h, "csr_to_dia_tile_kernel");
+  } else {
+    B200SP_CUDA(h, cudaMemsetAsync(vals, 0, (size_t)pitch * (size_t)ndiag * sizeof(T), st));
+    csr_to_dia_fill_kernel<T><<<warp_grid(h, rows), 256, 0, st>>>(rows, pitch, Ap, Aj, Ax, reinterpret_cast<int *>(pos.p),
+                                                                  vals);
+    B200SP_LAUNCH_CHECK(h, "csr_to_dia_fill_kernel");
+  }
   B200SP_CUDA(h, cudaStreamSynchronize(st));
   return B200SP_OK;
 }
