@@ -210,6 +210,16 @@ __global__ void mark_diagonals_kernel(i64 rows, const int *Ap, const int *Aj, in
     }
   }
 }
+// short rows (banded operators): a thread per row instead of a warp per row with most lanes idle
+__global__ void mark_diagonals_rows_kernel(i64 rows, const int *Ap, const int *Aj, int *flags) {
+  const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int lo = Ap[r], hi = Ap[r + 1];
+  for (int j = lo; j < hi; ++j) {
+    int *f = flags + ((i64)Aj[j] - r + rows);
+    if (__ldca(f) == 0) *f = 1;
+  }
+}
 __global__ void compact_diagonals_kernel(i64 n, i64 rows, const int *flags, const int *pos, int *offsets) {
   const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n && flags[k]) offsets[pos[k]] = (int)(k - rows);
@@ -365,7 +375,10 @@ static b200sp_status csr_to_dia_impl(b200sp_handle h, cudaStream_t st, i64 rows,
   if (s == B200SP_OK) s = tmp.alloc(h, (size_t)scan_tmp_ints(n) * sizeof(int));
   if (s != B200SP_OK) return s;
   B200SP_CUDA(h, cudaMemsetAsync(flags.p, 0, (size_t)n * sizeof(int), st));
-  mark_diagonals_kernel<<<warp_grid(h, rows), 256, 0, st>>>(rows, Ap, Aj, reinterpret_cast<int *>(flags.p));
+  if (ndiag <= 64)  // rows of a matrix with few diagonals are short
+    mark_diagonals_rows_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, st>>>(rows, Ap, Aj, reinterpret_cast<int *>(flags.p));
+  else
+    mark_diagonals_kernel<<<warp_grid(h, rows), 256, 0, st>>>(rows, Ap, Aj, reinterpret_cast<int *>(flags.p));
   B200SP_LAUNCH_CHECK(h, "mark_diagonals_kernel");
   s = scan_exclusive(h, st, n, reinterpret_cast<int *>(flags.p), reinterpret_cast<int *>(pos.p),
                      reinterpret_cast<int *>(tmp.p));
@@ -689,8 +702,12 @@ b200sp_status b200sp_csr_convert_query(b200sp_handle h, b200sp_stream stream, in
     if (s != B200SP_OK) return s;
     int *f = reinterpret_cast<int *>(flags.p);
     B200SP_CUDA(h, cudaMemsetAsync(f, 0, (size_t)(n + 1) * sizeof(int), st));
-    b200sp::mark_diagonals_kernel<<<b200sp::warp_grid(h, num_rows), 256, 0, st>>>(num_rows, row_offsets,
-                                                                                  column_indices, f);
+    if (max_len <= 64)
+      b200sp::mark_diagonals_rows_kernel<<<(unsigned)b200sp::ceil_div(num_rows, 256), 256, 0, st>>>(num_rows, row_offsets,
+                                                                                                    column_indices, f);
+    else
+      b200sp::mark_diagonals_kernel<<<b200sp::warp_grid(h, num_rows), 256, 0, st>>>(num_rows, row_offsets,
+                                                                                    column_indices, f);
     B200SP_LAUNCH_CHECK(h, "mark_diagonals_kernel");
     s = b200sp::scan_exclusive(h, st, n + 1, f, f, reinterpret_cast<int *>(tmp.p));  // f[n] = total
     if (s != B200SP_OK) return s;
